@@ -1,0 +1,169 @@
+/* pevit_b200 -- C ABI of the B200-native PEViT fine-tuning hot path.
+ *
+ * The reference (eric-ai-lab/PEViT) has no plugin / FFI layer: its hot path is the Python
+ * nn.Module code in vision_benchmark/evaluation/{model,lora_model,adapter_model,
+ * compacter_model}.py.  This header is therefore the boundary a maintainer binds instead
+ * (ctypes stub shown in INTEGRATION.md); each entry point names the reference code it replaces.
+ *
+ * Conventions
+ *  - plain C types only; every pointer is a DEVICE pointer borrowed from the caller
+ *    (torch `tensor.data_ptr()`), alive until the stream reaches the call; `stream` is a
+ *    `cudaStream_t` passed as void* (torch.cuda.current_stream().cuda_stream).
+ *  - stream-ordered, no implicit synchronisation, no allocation per call; scratch and saved
+ *    activations are caller-allocated with the sizes the *_bytes() queries return.
+ *  - return 0 on success, < 0 on error; the message is in pevit_last_error() (thread-local).
+ *    Nothing throws or exits across the ABI.  There is no CPU fallback.
+ *  - token rows are in the reference's (L, N, D) order: row = l * NB + n  (model.py:1042).
+ *  - "bf16" buffers are raw uint16 storage (torch.bfloat16).
+ */
+#ifndef PEVIT_B200_H_
+#define PEVIT_B200_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define PEVIT_ABI_VERSION 1
+
+enum pevit_method {
+  PEVIT_PLAIN = 0,       /* stock block, no PEFT module (text tower / ablation) */
+  PEVIT_KADAPTATION = 1, /* model.py:423-940    Kronecker delta on q, v          */
+  PEVIT_LORA = 2,        /* lora_model.py:423-  rank-4 delta on q, v             */
+  PEVIT_ADAPTER = 3,     /* adapter_model.py:204-336  bottleneck after the MLP   */
+  PEVIT_COMPACTER = 4    /* compacter_model.py:196-503  PHM bottleneck           */
+};
+
+enum pevit_gemm_epilogue {
+  PEVIT_EPI_F32 = 0,    /* out_f32 = acc + bias + resid                          */
+  PEVIT_EPI_BF16 = 1,   /* out_bf16 = acc + bias                                 */
+  PEVIT_EPI_QGELU = 2,  /* z = acc + bias; out = z*sigmoid(1.702 z); out2 = z    */
+  PEVIT_EPI_DQGELU = 3, /* out = acc * d/dz quickgelu(aux)                       */
+  PEVIT_EPI_QKV = 4     /* head-major q/8,k,v scatter + low-rank T columns        */
+};
+
+/* ------------------------------------------------------------------ library */
+int pevit_abi_version(void);
+const char* pevit_last_error(void);
+/* 0 if the current device is sm_100 (B200); < 0 with a message otherwise. */
+int pevit_check_device(void);
+
+/* ------------------------------------------------------------------ primitives
+ * (exported so every kernel can be parity-tested on its own) */
+
+/* C = A[M,K] * B[N,K]^T, bf16 operands, fp32 accumulation in TMEM (tcgen05).
+ * Replaces F.linear at model.py:305, :816, :958-962 and their autograd dgrads. */
+typedef struct pevit_gemm_args {
+  const void* a; int32_t lda;        /* bf16 [M][lda]  */
+  const void* b; int32_t ldb;        /* bf16 [N][ldb]  */
+  int32_t m, n, k;
+  int32_t epilogue;                  /* enum pevit_gemm_epilogue */
+  const float* bias;                 /* [N] or NULL */
+  const float* resid;                /* fp32 [M][ld_out] or NULL (EPI_F32) */
+  float* out_f32;                    /* EPI_F32 */
+  void* out_bf16;                    /* EPI_BF16 / QGELU / DQGELU */
+  void* out2_bf16;                   /* EPI_QGELU: z (nullable) */
+  const void* aux_bf16;              /* EPI_DQGELU: z */
+  int32_t ld_out;
+  void* qkv_hm; float* t_out;        /* EPI_QKV outputs */
+  int32_t L, NB, H, D, r2;           /* EPI_QKV shape */
+  int32_t force_bn;                  /* 0 = heuristic, else 32/64/128/256 */
+} pevit_gemm_args;
+int pevit_gemm_tn(const pevit_gemm_args* args, void* stream);
+
+/* LayerNorm with fp32 statistics, eps 1e-5 (model.py:154-160). */
+int pevit_layernorm_fwd(const float* x, const float* gamma, const float* beta, void* y_bf16, float* y_f32,
+                        float* mean, float* rstd, int32_t rows, int32_t d, void* stream);
+int pevit_layernorm_bwd(const float* dyn, const float* x, const float* gamma, const float* mean, const float* rstd,
+                        const float* dres, float* dx, void* dx_bf16, float* dgamma, float* dbeta, int32_t rows,
+                        int32_t d, void* stream);
+
+/* Attention core + in-kernel low-rank delta (model.py:786-815, lora_model.py:719-733). */
+typedef struct pevit_attn_args {
+  int32_t L, NB, H, D, r; float alpha;
+  const void *q, *k, *v;             /* bf16 head-major [NB*H][L][64], q pre-scaled */
+  const float* t;                    /* fp32 [L*NB][2r] or NULL */
+  const float* qmat;                 /* fp32 [2][D][r] or NULL  */
+  const float* delta_bias;           /* fp32 [D] or NULL (KAdaptation attn.b) */
+  void* o_tok; float* lse;           /* fwd out: bf16 [L*NB][D], fp32 [NB*H][L] */
+  const void* do_tok;                /* bwd in : bf16 [L*NB][D] */
+  void* dqkv; int32_t ld_dqkv;       /* bwd out: bf16 [L*NB][ld], cols dq/8 | dk | dv */
+  void* ddelta;                      /* bwd out: bf16 [2][NB*H][L][64] (nullable) */
+  int32_t impl;                      /* 0 = default, 1 = CUDA-core cross-check kernel */
+} pevit_attn_args;
+int pevit_attn_fwd(const pevit_attn_args* args, void* stream);
+int pevit_attn_bwd(const pevit_attn_args* args, void* stream);
+
+/* Factor expansion (model.py:563-580 without materialising H; lora_model.py:490-514). */
+int pevit_kad_expand(const float* u1, const float* v1, const float* u2, const float* v2, const float* s,
+                     const float* t, int32_t d, float alpha, void* w_ext, void* w_ext_t, float* qmat, void* qmat_t,
+                     void* stream);
+int pevit_lora_expand(const float* aq, const float* av, const float* bq, const float* bv, int32_t d, int32_t r,
+                      float alpha, void* w_ext, void* w_ext_t, float* qmat, void* qmat_t, void* stream);
+/* C[kc][nc] += scale * A[M][kc]^T B[M][nc] (fp32 atomics; caller zeroes C). */
+int pevit_atb_accumulate(const void* a, int32_t a_is_bf16, int32_t lda, const void* b, int32_t b_is_bf16,
+                         int32_t ldb, int32_t m, int32_t kc, int32_t nc, float scale, float* c, void* stream);
+int pevit_colsum_bf16(const void* x, int32_t m, int32_t d, float* out, void* stream);
+int pevit_kad_factor_grads(const float* dP, const float* dQ, const float* u1, const float* v1, const float* u2,
+                           const float* v2, const float* s, const float* t, int32_t d, float* du1, float* dv1,
+                           float* du2, float* dv2, float* ds, float* dt, void* stream);
+/* weight packing: fp32 [rows][cols] -> bf16 (same layout / transposed with leading dim ldd) */
+int pevit_cast_bf16(const float* src, void* dst, size_t n, void* stream);
+int pevit_transpose_bf16(const float* src, int32_t rows, int32_t cols, void* dst, int32_t ldd, void* stream);
+
+/* ------------------------------------------------------------------ block level
+ * One ResidualAttentionBlock forward / backward (model.py:947-975, lora_model.py,
+ * adapter_model.py:298-336, compacter_model.py:465-503), frozen backbone: dgrad only,
+ * gradients only for the PEFT tensors. */
+typedef struct pevit_block_desc {
+  int32_t L, NB, D, H;
+  int32_t method;      /* enum pevit_method */
+  int32_t r;           /* 32 (KAdaptation), 4 (LoRA), 0 otherwise */
+  float alpha;         /* 160 (KAdaptation), 32 (LoRA) */
+  int32_t save;        /* 1: fill `saved` for a later pevit_block_bwd */
+  int32_t attn_impl;   /* 0 default, 1 CUDA-core cross-check */
+  int32_t need_dx;     /* bwd: 0 skips the input gradient (first layer: nothing upstream trains) */
+} pevit_block_desc;
+
+typedef struct pevit_block_weights {
+  const void* w_qkv_ext;   const void* w_qkv_ext_t;  /* bf16 [3D+2r][D], [D][3D+2r] */
+  const float* b_qkv;                                /* [3D] */
+  const void* w_o;         const void* w_o_t;        /* bf16 [D][D] each */
+  const float* b_o;
+  const void* w_fc;        const void* w_fc_t;       /* bf16 [4D][D], [D][4D] */
+  const float* b_fc;
+  const void* w_proj;      const void* w_proj_t;     /* bf16 [D][4D], [4D][D] */
+  const float* b_proj;
+  const float *ln1_g, *ln1_b, *ln2_g, *ln2_b;
+  const float* qmat;       const void* qmat_t;       /* fp32 [2][D][r]; bf16 [2][r][D] * alpha */
+  const float* delta_bias;                           /* KAdaptation attn.b or NULL */
+  /* bottleneck (Adapter / Compacter): dense down/up weights (Compacter: expanded from PHM factors) */
+  const float *lna_g, *lna_b;                        /* adapter_norm_before */
+  const void* w_down;      const void* w_down_t;     /* bf16 [64][D], [D][64] */
+  const float* b_down;
+  const void* w_up;        const void* w_up_t;       /* bf16 [D][64], [64][D] */
+  const float* b_up;
+} pevit_block_weights;
+
+typedef struct pevit_block_grads {      /* fp32 outputs, all nullable when not applicable */
+  float* d_pmat;   /* [D][2r]   dP = X^T dT            (KAdaptation / LoRA) */
+  float* d_qmat;   /* [2][D][r] dQ = alpha dDelta^T T  (KAdaptation / LoRA) */
+  float* d_bias;   /* [D]       KAdaptation attn.b */
+  float *d_lna_g, *d_lna_b;            /* adapter LayerNorm */
+  float *d_w_down, *d_b_down;          /* [D][64] (= dW_down^T), [64] */
+  float *d_w_up, *d_b_up;              /* [D][64], [D]   */
+} pevit_block_grads;
+
+size_t pevit_block_saved_bytes(const pevit_block_desc* desc);
+size_t pevit_block_workspace_bytes(const pevit_block_desc* desc);
+int pevit_block_fwd(const pevit_block_desc* desc, const pevit_block_weights* w, const float* x, float* y,
+                    void* saved, void* workspace, void* stream);
+int pevit_block_bwd(const pevit_block_desc* desc, const pevit_block_weights* w, const float* x, const float* dy,
+                    float* dx, const pevit_block_grads* grads, const void* saved, void* workspace, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* PEVIT_B200_H_ */

@@ -1,0 +1,404 @@
+// C ABI (include/pevit_b200.h) and the per-block forward / backward schedules.
+#include "../../include/pevit_b200.h"
+
+#include "common.cuh"
+#include "kernels.h"
+
+using namespace pevit;
+
+namespace {
+
+inline cudaStream_t as_stream(void* s) { return static_cast<cudaStream_t>(s); }
+
+// Bump allocator over a caller-provided buffer (256-byte aligned pieces).
+struct Carver {
+  uint8_t* base;
+  size_t off = 0;
+  explicit Carver(void* p) : base(static_cast<uint8_t*>(p)) {}
+  template <typename T>
+  T* take(size_t n) {
+    off = (off + 255) & ~size_t(255);
+    T* p = base ? reinterpret_cast<T*>(base + off) : nullptr;
+    off += n * sizeof(T);
+    return p;
+  }
+};
+
+struct Saved {
+  bf16* xn1; float *mean1, *rstd1; bf16* qkv_hm; float* T; bf16* o_tok; float* lse;
+  float* x1; float *mean2, *rstd2; bf16* z;
+  // bottleneck
+  float* m; float *mean_a, *rstd_a; bf16* a_n; bf16* zd; bf16* u;
+  size_t bytes;
+};
+
+struct Work {
+  // forward
+  bf16* xn2; bf16* h;
+  // backward
+  bf16* dy_bf16; bf16* dz; float* dxn; float* dx1; bf16* dx1_bf16; bf16* do_tok; bf16* dqkv; bf16* ddelta;
+  bf16* dzd; float* dm; bf16* dm_bf16;
+  size_t bytes;
+};
+
+inline bool has_lowrank(const pevit_block_desc& d) { return d.method == PEVIT_KADAPTATION || d.method == PEVIT_LORA; }
+inline bool has_bottleneck(const pevit_block_desc& d) { return d.method == PEVIT_ADAPTER || d.method == PEVIT_COMPACTER; }
+
+Saved carve_saved(const pevit_block_desc& d, void* p) {
+  const size_t M = static_cast<size_t>(d.L) * d.NB, D = d.D;
+  Carver c(p);
+  Saved s{};
+  s.xn1 = c.take<bf16>(M * D);
+  s.mean1 = c.take<float>(M); s.rstd1 = c.take<float>(M);
+  s.qkv_hm = c.take<bf16>(3 * M * D);
+  s.T = c.take<float>(M * 2 * (d.r > 0 ? d.r : 1));
+  s.o_tok = c.take<bf16>(M * D);
+  s.lse = c.take<float>(M * d.H);
+  s.x1 = c.take<float>(M * D);
+  s.mean2 = c.take<float>(M); s.rstd2 = c.take<float>(M);
+  s.z = c.take<bf16>(M * 4 * D);
+  if (has_bottleneck(d)) {
+    s.m = c.take<float>(M * D);
+    s.mean_a = c.take<float>(M); s.rstd_a = c.take<float>(M);
+    s.a_n = c.take<bf16>(M * D);
+    s.zd = c.take<bf16>(M * 64);
+    s.u = c.take<bf16>(M * 64);
+  }
+  s.bytes = (c.off + 255) & ~size_t(255);
+  return s;
+}
+
+Work carve_work(const pevit_block_desc& d, void* p) {
+  const size_t M = static_cast<size_t>(d.L) * d.NB, D = d.D;
+  const size_t W3 = 3 * D + 2 * d.r;
+  Work w{};
+  Carver f(p);
+  w.xn2 = f.take<bf16>(M * D);
+  w.h = f.take<bf16>(M * 4 * D);
+  Carver b(p);  // backward reuses the same bytes
+  w.dy_bf16 = b.take<bf16>(M * D);
+  w.dz = b.take<bf16>(M * 4 * D);
+  w.dxn = b.take<float>(M * D);
+  w.dx1 = b.take<float>(M * D);
+  w.dx1_bf16 = b.take<bf16>(M * D);
+  w.do_tok = b.take<bf16>(M * D);
+  w.dqkv = b.take<bf16>(M * W3);
+  w.ddelta = b.take<bf16>(2 * M * D);
+  if (has_bottleneck(d)) {
+    w.dzd = b.take<bf16>(M * 64);
+    w.dm = b.take<float>(M * D);
+    w.dm_bf16 = b.take<bf16>(M * D);
+  }
+  const size_t mx = f.off > b.off ? f.off : b.off;
+  w.bytes = (mx + 255) & ~size_t(255);
+  return w;
+}
+
+int check_desc(const pevit_block_desc* d) {
+  PEVIT_REQUIRE(d != nullptr, "null block descriptor");
+  PEVIT_REQUIRE(d->L > 0 && d->NB > 0 && d->D > 0 && d->H > 0, "bad block shape L=%d NB=%d D=%d H=%d", d->L, d->NB,
+                d->D, d->H);
+  PEVIT_REQUIRE(d->D == 64 * d->H, "head_dim must be 64 (D=%d, H=%d)", d->D, d->H);
+  PEVIT_REQUIRE(d->D % 128 == 0, "D=%d must be a multiple of 128", d->D);
+  PEVIT_REQUIRE(d->method >= PEVIT_PLAIN && d->method <= PEVIT_COMPACTER, "unknown method %d", d->method);
+  if (has_lowrank(*d))
+    PEVIT_REQUIRE(d->r > 0 && d->r <= 32 && (2 * d->r) % 8 == 0, "low-rank width r=%d unsupported", d->r);
+  else
+    PEVIT_REQUIRE(d->r == 0, "r must be 0 for method %d", d->method);
+  return 0;
+}
+
+int attn_fwd_dispatch(cudaStream_t s, const AttnShape& a, int impl, const bf16* q, const bf16* k, const bf16* v,
+                      const float* T, const float* qmat, const float* bias, bf16* o_tok, float* lse) {
+  (void)impl;
+  return attn_delta_fwd_ref(s, a, q, k, v, T, qmat, bias, o_tok, lse);
+}
+
+int attn_bwd_dispatch(cudaStream_t s, const AttnShape& a, int impl, const bf16* q, const bf16* k, const bf16* v,
+                      const float* T, const float* qmat, const float* bias, const bf16* o_tok, const bf16* do_tok,
+                      const float* lse, bf16* dqkv, int ld, bf16* ddelta) {
+  (void)impl;
+  return attn_delta_bwd_ref(s, a, q, k, v, T, qmat, bias, o_tok, do_tok, lse, dqkv, ld, ddelta);
+}
+
+#define TRY(expr)            \
+  do {                       \
+    int rc__ = (expr);       \
+    if (rc__ != 0) return rc__; \
+  } while (0)
+
+}  // namespace
+
+extern "C" {
+
+int pevit_abi_version(void) { return PEVIT_ABI_VERSION; }
+const char* pevit_last_error(void) { return last_error(); }
+
+int pevit_check_device(void) {
+  int dev = 0;
+  PEVIT_CHECK_CUDA(cudaGetDevice(&dev));
+  int major = 0, minor = 0;
+  PEVIT_CHECK_CUDA(cudaDeviceGetAttribute(&major, cudaDevAttrComputeCapabilityMajor, dev));
+  PEVIT_CHECK_CUDA(cudaDeviceGetAttribute(&minor, cudaDevAttrComputeCapabilityMinor, dev));
+  PEVIT_REQUIRE(major == 10, "pevit_b200 kernels are built for sm_100a only; device %d is sm_%d%d", dev, major, minor);
+  return 0;
+}
+
+int pevit_gemm_tn(const pevit_gemm_args* a, void* stream) {
+  PEVIT_REQUIRE(a != nullptr, "null gemm args");
+  GemmEpilogue ep;
+  ep.bias = a->bias; ep.resid = a->resid; ep.out_f32 = a->out_f32;
+  ep.out_bf16 = static_cast<bf16*>(a->out_bf16); ep.out2_bf16 = static_cast<bf16*>(a->out2_bf16);
+  ep.aux_bf16 = static_cast<const bf16*>(a->aux_bf16); ep.ld_out = a->ld_out;
+  ep.qkv_hm = static_cast<bf16*>(a->qkv_hm); ep.t_out = a->t_out;
+  ep.L = a->L; ep.NB = a->NB; ep.H = a->H; ep.D = a->D; ep.r2 = a->r2;
+  int epi = a->epilogue;
+  // the public enum folds the activation kind into the epilogue id
+  if (epi == PEVIT_EPI_QGELU) { epi = EPI_ACT; ep.act = ACT_QUICKGELU; }
+  else if (epi == PEVIT_EPI_DQGELU) { epi = EPI_DACT; ep.act = ACT_QUICKGELU; }
+  return gemm_tn(as_stream(stream), static_cast<const bf16*>(a->a), a->lda, static_cast<const bf16*>(a->b), a->ldb,
+                 a->m, a->n, a->k, epi, ep, a->force_bn);
+}
+
+int pevit_layernorm_fwd(const float* x, const float* gamma, const float* beta, void* y_bf16, float* y_f32, float* mean,
+                        float* rstd, int32_t rows, int32_t d, void* stream) {
+  return layernorm_fwd(as_stream(stream), x, gamma, beta, static_cast<bf16*>(y_bf16), y_f32, mean, rstd, rows, d);
+}
+
+int pevit_layernorm_bwd(const float* dyn, const float* x, const float* gamma, const float* mean, const float* rstd,
+                        const float* dres, float* dx, void* dx_bf16, float* dgamma, float* dbeta, int32_t rows,
+                        int32_t d, void* stream) {
+  return layernorm_bwd(as_stream(stream), dyn, x, gamma, mean, rstd, dres, dx, static_cast<bf16*>(dx_bf16), dgamma,
+                       dbeta, rows, d);
+}
+
+int pevit_attn_fwd(const pevit_attn_args* a, void* stream) {
+  PEVIT_REQUIRE(a != nullptr, "null attention args");
+  AttnShape sh{a->L, a->NB, a->H, a->D, a->r, a->alpha};
+  return attn_fwd_dispatch(as_stream(stream), sh, a->impl, static_cast<const bf16*>(a->q),
+                           static_cast<const bf16*>(a->k), static_cast<const bf16*>(a->v), a->t, a->qmat,
+                           a->delta_bias, static_cast<bf16*>(a->o_tok), a->lse);
+}
+
+int pevit_attn_bwd(const pevit_attn_args* a, void* stream) {
+  PEVIT_REQUIRE(a != nullptr, "null attention args");
+  AttnShape sh{a->L, a->NB, a->H, a->D, a->r, a->alpha};
+  return attn_bwd_dispatch(as_stream(stream), sh, a->impl, static_cast<const bf16*>(a->q),
+                           static_cast<const bf16*>(a->k), static_cast<const bf16*>(a->v), a->t, a->qmat,
+                           a->delta_bias, static_cast<const bf16*>(a->o_tok), static_cast<const bf16*>(a->do_tok),
+                           a->lse, static_cast<bf16*>(a->dqkv), a->ld_dqkv, static_cast<bf16*>(a->ddelta));
+}
+
+int pevit_kad_expand(const float* u1, const float* v1, const float* u2, const float* v2, const float* s, const float* t,
+                     int32_t d, float alpha, void* w_ext, void* w_ext_t, float* qmat, void* qmat_t, void* stream) {
+  return kad_expand(as_stream(stream), u1, v1, u2, v2, s, t, d, alpha, static_cast<bf16*>(w_ext),
+                    static_cast<bf16*>(w_ext_t), qmat, static_cast<bf16*>(qmat_t));
+}
+
+int pevit_lora_expand(const float* aq, const float* av, const float* bq, const float* bv, int32_t d, int32_t r,
+                      float alpha, void* w_ext, void* w_ext_t, float* qmat, void* qmat_t, void* stream) {
+  return lora_expand(as_stream(stream), aq, av, bq, bv, d, r, alpha, static_cast<bf16*>(w_ext),
+                     static_cast<bf16*>(w_ext_t), qmat, static_cast<bf16*>(qmat_t));
+}
+
+int pevit_atb_accumulate(const void* a, int32_t a_is_bf16, int32_t lda, const void* b, int32_t b_is_bf16, int32_t ldb,
+                         int32_t m, int32_t kc, int32_t nc, float scale, float* c, void* stream) {
+  return atb_accumulate(as_stream(stream), a, a_is_bf16, lda, b, b_is_bf16, ldb, m, kc, nc, scale, c);
+}
+
+int pevit_colsum_bf16(const void* x, int32_t m, int32_t d, float* out, void* stream) {
+  return colsum_bf16(as_stream(stream), static_cast<const bf16*>(x), d, m, d, out);
+}
+
+int pevit_kad_factor_grads(const float* dP, const float* dQ, const float* u1, const float* v1, const float* u2,
+                           const float* v2, const float* s, const float* t, int32_t d, float* du1, float* dv1,
+                           float* du2, float* dv2, float* ds, float* dt, void* stream) {
+  return kad_factor_grads(as_stream(stream), dP, dQ, u1, v1, u2, v2, s, t, d, du1, dv1, du2, dv2, ds, dt);
+}
+
+int pevit_cast_bf16(const float* src, void* dst, size_t n, void* stream) {
+  return cast_f32_to_bf16(as_stream(stream), src, static_cast<bf16*>(dst), n);
+}
+
+int pevit_transpose_bf16(const float* src, int32_t rows, int32_t cols, void* dst, int32_t ldd, void* stream) {
+  return transpose_f32_to_bf16(as_stream(stream), src, rows, cols, static_cast<bf16*>(dst), ldd);
+}
+
+size_t pevit_block_saved_bytes(const pevit_block_desc* desc) {
+  if (check_desc(desc) != 0) return 0;
+  return carve_saved(*desc, nullptr).bytes;
+}
+
+size_t pevit_block_workspace_bytes(const pevit_block_desc* desc) {
+  if (check_desc(desc) != 0) return 0;
+  return carve_work(*desc, nullptr).bytes;
+}
+
+// Forward of one ResidualAttentionBlock:
+//   x1 = x + out_proj(attn(ln_1(x)))            model.py:973
+//   y  = x1 + mlp(ln_2(x1)) [+ bottleneck]      model.py:974, adapter_model.py:333, compacter_model.py:500
+int pevit_block_fwd(const pevit_block_desc* desc, const pevit_block_weights* w, const float* x, float* y, void* saved,
+                    void* workspace, void* stream) {
+  TRY(check_desc(desc));
+  PEVIT_REQUIRE(w && x && y && saved && workspace, "pevit_block_fwd: null pointer argument");
+  const pevit_block_desc& d = *desc;
+  cudaStream_t s = as_stream(stream);
+  const int M = d.L * d.NB, D = d.D, r2 = 2 * d.r, W3 = 3 * D + r2;
+  Saved sv = carve_saved(d, saved);
+  Work wk = carve_work(d, workspace);
+  const size_t plane = static_cast<size_t>(M) * D;
+
+  // ln_1 -> bf16 A operand
+  TRY(layernorm_fwd(s, x, w->ln1_g, w->ln1_b, sv.xn1, nullptr, sv.mean1, sv.rstd1, M, D));
+  // in-projection (+ low-rank T columns), head split, q scale
+  {
+    GemmEpilogue ep;
+    ep.bias = w->b_qkv; ep.qkv_hm = sv.qkv_hm; ep.t_out = sv.T;
+    ep.L = d.L; ep.NB = d.NB; ep.H = d.H; ep.D = D; ep.r2 = r2;
+    TRY(gemm_tn(s, sv.xn1, D, static_cast<const bf16*>(w->w_qkv_ext), D, M, W3, D, EPI_QKV, ep));
+  }
+  // attention core with in-kernel delta
+  {
+    AttnShape a{d.L, d.NB, d.H, D, d.r, d.alpha};
+    TRY(attn_fwd_dispatch(s, a, d.attn_impl, sv.qkv_hm, sv.qkv_hm + plane, sv.qkv_hm + 2 * plane,
+                          has_lowrank(d) ? sv.T : nullptr, has_lowrank(d) ? w->qmat : nullptr,
+                          d.method == PEVIT_KADAPTATION ? w->delta_bias : nullptr, sv.o_tok, sv.lse));
+  }
+  // out-projection + residual
+  {
+    GemmEpilogue ep;
+    ep.bias = w->b_o; ep.resid = x; ep.out_f32 = sv.x1; ep.ld_out = D;
+    TRY(gemm_tn(s, sv.o_tok, D, static_cast<const bf16*>(w->w_o), D, M, D, D, EPI_F32, ep));
+  }
+  // ln_2, c_fc + QuickGELU
+  TRY(layernorm_fwd(s, sv.x1, w->ln2_g, w->ln2_b, wk.xn2, nullptr, sv.mean2, sv.rstd2, M, D));
+  {
+    GemmEpilogue ep;
+    ep.bias = w->b_fc; ep.out_bf16 = wk.h; ep.out2_bf16 = d.save ? sv.z : nullptr; ep.ld_out = 4 * D;
+    ep.act = ACT_QUICKGELU;
+    TRY(gemm_tn(s, wk.xn2, D, static_cast<const bf16*>(w->w_fc), D, M, 4 * D, D, EPI_ACT, ep));
+  }
+  if (!has_bottleneck(d)) {
+    GemmEpilogue ep;
+    ep.bias = w->b_proj; ep.resid = sv.x1; ep.out_f32 = y; ep.ld_out = D;
+    TRY(gemm_tn(s, wk.h, 4 * D, static_cast<const bf16*>(w->w_proj), 4 * D, M, D, 4 * D, EPI_F32, ep));
+    return 0;
+  }
+  // bottleneck: y = x1 + m + up(act(down(LN_a(m)))), m = mlp output  (adapter_model.py:264-282, F8)
+  {
+    GemmEpilogue ep;
+    ep.bias = w->b_proj; ep.out_f32 = sv.m; ep.ld_out = D;
+    TRY(gemm_tn(s, wk.h, 4 * D, static_cast<const bf16*>(w->w_proj), 4 * D, M, D, 4 * D, EPI_F32, ep));
+  }
+  TRY(layernorm_fwd(s, sv.m, w->lna_g, w->lna_b, sv.a_n, nullptr, sv.mean_a, sv.rstd_a, M, D));
+  {
+    GemmEpilogue ep;
+    ep.bias = w->b_down; ep.out_bf16 = sv.u; ep.out2_bf16 = sv.zd; ep.ld_out = 64;
+    ep.act = d.method == PEVIT_ADAPTER ? ACT_RELU : ACT_GELU_NEW;
+    TRY(gemm_tn(s, sv.a_n, D, static_cast<const bf16*>(w->w_down), D, M, 64, D, EPI_ACT, ep));
+  }
+  {
+    GemmEpilogue ep;
+    ep.bias = w->b_up; ep.resid = sv.x1; ep.resid2 = sv.m; ep.out_f32 = y; ep.ld_out = D;
+    TRY(gemm_tn(s, sv.u, 64, static_cast<const bf16*>(w->w_up), 64, M, D, 64, EPI_F32, ep));
+  }
+  return 0;
+}
+
+// Backward: activation gradients flow through every frozen GEMM (dgrad only);
+// weight gradients exist only for the PEFT tensors.
+int pevit_block_bwd(const pevit_block_desc* desc, const pevit_block_weights* w, const float* x, const float* dy,
+                    float* dx, const pevit_block_grads* g, const void* saved, void* workspace, void* stream) {
+  TRY(check_desc(desc));
+  PEVIT_REQUIRE(w && x && dy && g && saved && workspace && (dx || !desc->need_dx),
+                "pevit_block_bwd: null pointer argument");
+  const pevit_block_desc& d = *desc;
+  cudaStream_t s = as_stream(stream);
+  const int M = d.L * d.NB, D = d.D, r = d.r, r2 = 2 * r, W3 = 3 * D + r2;
+  Saved sv = carve_saved(d, const_cast<void*>(saved));
+  Work wk = carve_work(d, workspace);
+  const size_t plane = static_cast<size_t>(M) * D;
+
+  TRY(cast_f32_to_bf16(s, dy, wk.dy_bf16, plane));
+  const bf16* dmlp_bf16 = wk.dy_bf16;  // gradient w.r.t. the MLP output m
+  if (has_bottleneck(d)) {
+    const int act = d.method == PEVIT_ADAPTER ? ACT_RELU : ACT_GELU_NEW;
+    // up projection: dW_up = dy^T u, db_up = colsum(dy), du = dy W_up, dzd = du * act'(zd)
+    if (g->d_w_up) TRY(atb_accumulate(s, wk.dy_bf16, 1, D, sv.u, 1, 64, M, D, 64, 1.f, g->d_w_up));
+    if (g->d_b_up) TRY(colsum_bf16(s, wk.dy_bf16, D, M, D, g->d_b_up));
+    {
+      GemmEpilogue ep;
+      ep.out_bf16 = wk.dzd; ep.aux_bf16 = sv.zd; ep.ld_out = 64; ep.act = act;
+      TRY(gemm_tn(s, wk.dy_bf16, D, static_cast<const bf16*>(w->w_up_t), D, M, 64, D, EPI_DACT, ep));
+    }
+    // down projection: dW_down^T = a_n^T dzd, db_down = colsum(dzd), da_n = dzd W_down
+    if (g->d_w_down) TRY(atb_accumulate(s, sv.a_n, 1, D, wk.dzd, 1, 64, M, D, 64, 1.f, g->d_w_down));
+    if (g->d_b_down) TRY(colsum_bf16(s, wk.dzd, 64, M, 64, g->d_b_down));
+    {
+      GemmEpilogue ep;
+      ep.out_f32 = wk.dxn; ep.ld_out = D;
+      TRY(gemm_tn(s, wk.dzd, 64, static_cast<const bf16*>(w->w_down_t), 64, M, D, 64, EPI_F32, ep));
+    }
+    // adapter LayerNorm backward (+ the direct `+ m` path: dres = dy), with its affine grads
+    TRY(layernorm_bwd(s, wk.dxn, sv.m, w->lna_g, sv.mean_a, sv.rstd_a, dy, nullptr, wk.dm_bf16, g->d_lna_g, g->d_lna_b,
+                      M, D));
+    dmlp_bf16 = wk.dm_bf16;
+  }
+  // c_proj dgrad fused with QuickGELU': dz = (dm W_proj) * g'(z)
+  {
+    GemmEpilogue ep;
+    ep.out_bf16 = wk.dz; ep.aux_bf16 = sv.z; ep.ld_out = 4 * D; ep.act = ACT_QUICKGELU;
+    TRY(gemm_tn(s, dmlp_bf16, D, static_cast<const bf16*>(w->w_proj_t), D, M, 4 * D, D, EPI_DACT, ep));
+  }
+  // c_fc dgrad -> d ln_2 output
+  {
+    GemmEpilogue ep;
+    ep.out_f32 = wk.dxn; ep.ld_out = D;
+    TRY(gemm_tn(s, wk.dz, 4 * D, static_cast<const bf16*>(w->w_fc_t), 4 * D, M, D, 4 * D, EPI_F32, ep));
+  }
+  // ln_2 backward + residual path
+  TRY(layernorm_bwd(s, wk.dxn, sv.x1, w->ln2_g, sv.mean2, sv.rstd2, dy, wk.dx1, wk.dx1_bf16, nullptr, nullptr, M, D));
+  // out-proj dgrad -> dO (token rows)
+  {
+    GemmEpilogue ep;
+    ep.out_bf16 = wk.do_tok; ep.ld_out = D;
+    TRY(gemm_tn(s, wk.dx1_bf16, D, static_cast<const bf16*>(w->w_o_t), D, M, D, D, EPI_BF16, ep));
+  }
+  // attention backward
+  {
+    AttnShape a{d.L, d.NB, d.H, D, r, d.alpha};
+    TRY(attn_bwd_dispatch(s, a, d.attn_impl, sv.qkv_hm, sv.qkv_hm + plane, sv.qkv_hm + 2 * plane,
+                          has_lowrank(d) ? sv.T : nullptr, has_lowrank(d) ? w->qmat : nullptr,
+                          d.method == PEVIT_KADAPTATION ? w->delta_bias : nullptr, sv.o_tok, wk.do_tok, sv.lse, wk.dqkv,
+                          W3, has_lowrank(d) ? wk.ddelta : nullptr));
+  }
+  if (has_lowrank(d)) {
+    const bf16* qmat_t = static_cast<const bf16*>(w->qmat_t);
+    for (int which = 0; which < 2; ++which) {
+      const bf16* dd = wk.ddelta + which * plane;  // d(delta) viewed as [M][D] in LND rows (F4)
+      // dT = alpha * dDelta * Q  -> bf16 straight into the extra K columns of the QKV dgrad operand
+      GemmEpilogue ep;
+      ep.out_bf16 = wk.dqkv + 3 * D + which * r; ep.ld_out = W3;
+      TRY(gemm_tn(s, dd, D, qmat_t + static_cast<size_t>(which) * r * D, D, M, r, D, EPI_BF16, ep));
+      // dQ = alpha * dDelta^T T
+      if (g->d_qmat)
+        TRY(atb_accumulate(s, dd, 1, D, sv.T + which * r, 0, r2, M, D, r, d.alpha,
+                           g->d_qmat + static_cast<size_t>(which) * D * r));
+      if (d.method == PEVIT_KADAPTATION && g->d_bias) TRY(colsum_bf16(s, dd, D, M, D, g->d_bias));
+    }
+    // dP = X^T dT  ([D][2r], q | v)
+    if (g->d_pmat) TRY(atb_accumulate(s, sv.xn1, 1, D, wk.dqkv + 3 * D, 1, W3, M, D, r2, 1.f, g->d_pmat));
+  }
+  if (!d.need_dx) return 0;  // first layer: nothing upstream of this block trains
+  // in-projection dgrad (K = 3D + 2r: the low-rank columns ride along)
+  {
+    GemmEpilogue ep;
+    ep.out_f32 = wk.dxn; ep.ld_out = D;
+    TRY(gemm_tn(s, wk.dqkv, W3, static_cast<const bf16*>(w->w_qkv_ext_t), W3, M, D, W3, EPI_F32, ep));
+  }
+  // ln_1 backward + residual path
+  TRY(layernorm_bwd(s, wk.dxn, x, w->ln1_g, sv.mean1, sv.rstd1, wk.dx1, dx, nullptr, nullptr, nullptr, M, D));
+  return 0;
+}
+
+}  // extern "C"

@@ -1,0 +1,385 @@
+// C[M,N] = A[M,K] * B[N,K]^T on the 5th-gen tensor cores (tcgen05.mma, fp32 accumulators in
+// TMEM), bf16 operands staged by TMA into 128B-swizzled shared memory.  Persistent,
+// warp-specialised: warp 0 = TMA producer, warp 1 = MMA issuer, warps 2-5 = epilogue
+// (TMEM -> registers -> fused epilogue -> global).  Two TMEM accumulator stages let the
+// epilogue of tile i overlap the mainloop of tile i+1.
+//
+// Replaces on the hot path (reference evaluation/model.py): the in-projection `linear`
+// (:305) + head split/scale (:729-740,786-787) + the X*P half of adapter_forward (:563-584)
+// [EPI_QKV]; out-proj / c_proj `linear` + residual add (:816, :973-974) [EPI_F32];
+// c_fc + QuickGELU (:958-962, :165) [EPI_ACT]; and every dgrad GEMM autograd would run.
+#include "common.cuh"
+#include "kernels.h"
+
+namespace pevit {
+
+namespace {
+
+constexpr int BM = 128;
+constexpr int BK = 64;  // 64 bf16 = one 128-byte swizzle row
+constexpr int GEMM_THREADS = 192;
+
+template <int BN>
+struct TileCfg {
+  static constexpr int STAGES = BN >= 256 ? 4 : (BN >= 128 ? 6 : 8);
+  static constexpr int A_BYTES = BM * BK * 2;
+  static constexpr int B_BYTES = BN * BK * 2;
+  static constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
+  static constexpr int TMEM_COLS = 2 * BN < 32 ? 32 : 2 * BN;  // two accumulator stages
+  static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + 256 + 1024;  // + barriers + align slack
+};
+
+__device__ __forceinline__ float sigmoidf_fast(float x) { return 1.f / (1.f + __expf(-x)); }
+
+// activations of the path: QuickGELU (model.py:163-165), ReLU (adapter_model.py:305),
+// gelu_new (compacter_model.py:374 -> transformers NewGELUActivation)
+__device__ __forceinline__ float act_fwd(int kind, float z) {
+  if (kind == ACT_QUICKGELU) return z * sigmoidf_fast(1.702f * z);
+  if (kind == ACT_RELU) return fmaxf(z, 0.f);
+  const float u = 0.7978845608028654f * (z + 0.044715f * z * z * z);
+  return 0.5f * z * (1.f + tanhf(u));
+}
+__device__ __forceinline__ float act_bwd(int kind, float z) {
+  if (kind == ACT_QUICKGELU) {
+    const float s = sigmoidf_fast(1.702f * z);
+    return s * (1.f + 1.702f * z * (1.f - s));
+  }
+  if (kind == ACT_RELU) return z > 0.f ? 1.f : 0.f;
+  const float u = 0.7978845608028654f * (z + 0.044715f * z * z * z);
+  const float t = tanhf(u);
+  return 0.5f * (1.f + t) + 0.5f * z * (1.f - t * t) * 0.7978845608028654f * (1.f + 3.f * 0.044715f * z * z);
+}
+
+// Epilogue for one 32-column chunk of one accumulator row.  v[] holds raw fp32 bits.
+template <int EPI>
+__device__ __forceinline__ void epilogue_chunk(const GemmEpilogue& ep, int m, int c0,
+                                               uint32_t (&v)[32], int N) {
+  float a[32];
+#pragma unroll
+  for (int j = 0; j < 32; ++j) a[j] = __uint_as_float(v[j]);
+  const bool full = (c0 + 32 <= N);
+
+  if (ep.bias != nullptr && !(EPI == EPI_QKV && c0 >= 3 * ep.D)) {
+    if (full) {
+#pragma unroll
+      for (int j = 0; j < 32; j += 4) {
+        float4 b = __ldg(reinterpret_cast<const float4*>(ep.bias + c0 + j));
+        a[j] += b.x; a[j + 1] += b.y; a[j + 2] += b.z; a[j + 3] += b.w;
+      }
+    } else {
+      _Pragma("unroll") for (int j = 0; j < 32; ++j) if (c0 + j < N) a[j] += __ldg(ep.bias + c0 + j);
+    }
+  }
+
+  if constexpr (EPI == EPI_F32) {
+    const size_t off = static_cast<size_t>(m) * ep.ld_out + c0;
+    if (full) {
+      if (ep.resid != nullptr) {
+#pragma unroll
+        for (int j = 0; j < 32; j += 4) {
+          float4 r = *reinterpret_cast<const float4*>(ep.resid + off + j);
+          a[j] += r.x; a[j + 1] += r.y; a[j + 2] += r.z; a[j + 3] += r.w;
+        }
+      }
+      if (ep.resid2 != nullptr) {
+#pragma unroll
+        for (int j = 0; j < 32; j += 4) {
+          float4 r = *reinterpret_cast<const float4*>(ep.resid2 + off + j);
+          a[j] += r.x; a[j + 1] += r.y; a[j + 2] += r.z; a[j + 3] += r.w;
+        }
+      }
+#pragma unroll
+      for (int j = 0; j < 32; j += 4)
+        *reinterpret_cast<float4*>(ep.out_f32 + off + j) = make_float4(a[j], a[j + 1], a[j + 2], a[j + 3]);
+    } else {
+      _Pragma("unroll") for (int j = 0; j < 32; ++j) if (c0 + j < N)
+        ep.out_f32[off + j] = a[j] + (ep.resid != nullptr ? ep.resid[off + j] : 0.f) +
+                              (ep.resid2 != nullptr ? ep.resid2[off + j] : 0.f);
+    }
+  } else if constexpr (EPI == EPI_BF16) {
+    const size_t off = static_cast<size_t>(m) * ep.ld_out + c0;
+    if (full) {
+#pragma unroll
+      for (int j = 0; j < 32; j += 8) {
+        uint4 p = make_uint4(pack_bf16(a[j], a[j + 1]), pack_bf16(a[j + 2], a[j + 3]),
+                             pack_bf16(a[j + 4], a[j + 5]), pack_bf16(a[j + 6], a[j + 7]));
+        *reinterpret_cast<uint4*>(ep.out_bf16 + off + j) = p;
+      }
+    } else {
+      _Pragma("unroll") for (int j = 0; j < 32; ++j) if (c0 + j < N) ep.out_bf16[off + j] = __float2bfloat16(a[j]);
+    }
+  } else if constexpr (EPI == EPI_ACT) {
+    // z = acc + bias (kept for backward in out2), out = act(z)
+    const size_t off = static_cast<size_t>(m) * ep.ld_out + c0;
+    float h[32];
+#pragma unroll
+    for (int j = 0; j < 32; ++j) h[j] = act_fwd(ep.act, a[j]);
+    if (full) {
+#pragma unroll
+      for (int j = 0; j < 32; j += 8) {
+        *reinterpret_cast<uint4*>(ep.out_bf16 + off + j) =
+            make_uint4(pack_bf16(h[j], h[j + 1]), pack_bf16(h[j + 2], h[j + 3]),
+                       pack_bf16(h[j + 4], h[j + 5]), pack_bf16(h[j + 6], h[j + 7]));
+        if (ep.out2_bf16 != nullptr)
+          *reinterpret_cast<uint4*>(ep.out2_bf16 + off + j) =
+              make_uint4(pack_bf16(a[j], a[j + 1]), pack_bf16(a[j + 2], a[j + 3]),
+                         pack_bf16(a[j + 4], a[j + 5]), pack_bf16(a[j + 6], a[j + 7]));
+      }
+    } else {
+      _Pragma("unroll") for (int j = 0; j < 32; ++j) if (c0 + j < N) {
+        ep.out_bf16[off + j] = __float2bfloat16(h[j]);
+        if (ep.out2_bf16 != nullptr) ep.out2_bf16[off + j] = __float2bfloat16(a[j]);
+      }
+    }
+  } else if constexpr (EPI == EPI_DACT) {
+    // dz = acc * act'(z)
+    const size_t off = static_cast<size_t>(m) * ep.ld_out + c0;
+    if (full) {
+#pragma unroll
+      for (int j = 0; j < 32; j += 8) {
+        uint4 zz = *reinterpret_cast<const uint4*>(ep.aux_bf16 + off + j);
+        uint32_t zw[4] = {zz.x, zz.y, zz.z, zz.w};
+        uint32_t o[4];
+#pragma unroll
+        for (int t = 0; t < 4; ++t) {
+          float2 z = unpack_bf16(zw[t]);
+          o[t] = pack_bf16(a[j + 2 * t] * act_bwd(ep.act, z.x), a[j + 2 * t + 1] * act_bwd(ep.act, z.y));
+        }
+        *reinterpret_cast<uint4*>(ep.out_bf16 + off + j) = make_uint4(o[0], o[1], o[2], o[3]);
+      }
+    } else {
+      _Pragma("unroll") for (int j = 0; j < 32; ++j) if (c0 + j < N) {
+        float z = __bfloat162float(ep.aux_bf16[off + j]);
+        ep.out_bf16[off + j] = __float2bfloat16(a[j] * act_bwd(ep.act, z));
+      }
+    }
+  } else if constexpr (EPI == EPI_QKV) {
+    // rows are tokens in LND order (m = l*NB + n).  Columns [0,3D): q|k|v -> head-major bf16
+    // tiles [which][n*H+h][l][64] with q pre-scaled by 1/sqrt(64) (exact: power of two);
+    // columns [3D, 3D+r2): low-rank activations T = X*P kept in fp32, row-major [M][r2].
+    const int l = m / ep.NB, n = m - l * ep.NB;
+    const int threeD = 3 * ep.D;
+    if (c0 < threeD) {
+      const int which = c0 / ep.D;
+      const int within = c0 - which * ep.D;
+      const int h = within >> 6, d0 = within & 63;
+      const float sc = which == 0 ? 0.125f : 1.f;
+      bf16* dst = ep.qkv_hm +
+                  ((static_cast<size_t>(which) * ep.NB * ep.H + static_cast<size_t>(n) * ep.H + h) * ep.L + l) * 64 + d0;
+#pragma unroll
+      for (int j = 0; j < 32; j += 8)
+        *reinterpret_cast<uint4*>(dst + j) =
+            make_uint4(pack_bf16(a[j] * sc, a[j + 1] * sc), pack_bf16(a[j + 2] * sc, a[j + 3] * sc),
+                       pack_bf16(a[j + 4] * sc, a[j + 5] * sc), pack_bf16(a[j + 6] * sc, a[j + 7] * sc));
+    } else {
+      const int t0 = c0 - threeD;
+      float* dst = ep.t_out + static_cast<size_t>(m) * ep.r2 + t0;
+      _Pragma("unroll") for (int j = 0; j < 32; ++j) if (t0 + j < ep.r2) dst[j] = a[j];
+    }
+  }
+}
+
+template <int BN, int EPI>
+__global__ void __launch_bounds__(GEMM_THREADS, 1)
+gemm_tn_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_b,
+               int M, int N, int K, GemmEpilogue ep) {
+  using Cfg = TileCfg<BN>;
+  constexpr int STAGES = Cfg::STAGES;
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + STAGES * Cfg::STAGE_BYTES);
+  uint64_t* empty_bar = full_bar + STAGES;
+  uint64_t* tfull_bar = empty_bar + STAGES;
+  uint64_t* tempty_bar = tfull_bar + 2;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tempty_bar + 2);
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+  const int tiles_n = (N + BN - 1) / BN;
+  const int tiles_m = (M + BM - 1) / BM;
+  const int num_tiles = tiles_m * tiles_n;
+  const int num_kb = (K + BK - 1) / BK;
+
+  if (warp == 0 && lane == 0) {
+    tma_prefetch_desc(&tmap_a);
+    tma_prefetch_desc(&tmap_b);
+  }
+  if (warp == 1 && lane == 0) {
+    for (int s = 0; s < STAGES; ++s) {
+      mbar_init(&full_bar[s], 1);
+      mbar_init(&empty_bar[s], 1);
+    }
+    for (int s = 0; s < 2; ++s) {
+      mbar_init(&tfull_bar[s], 1);
+      mbar_init(&tempty_bar[s], 4);  // one arrive per epilogue warp
+    }
+    fence_mbar_init();
+  }
+  if (warp == 2) {
+    tmem_alloc(tmem_slot, Cfg::TMEM_COLS);
+    tmem_relinquish();
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  if (warp == 0) {
+    // ------------------------------------------------------------ TMA producer
+    if (lane == 0) {
+      int stage = 0;
+      uint32_t phase = 0;
+      for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+        const int m0 = (tile / tiles_n) * BM;
+        const int n0 = (tile % tiles_n) * BN;
+        for (int kb = 0; kb < num_kb; ++kb) {
+          mbar_wait(&empty_bar[stage], phase ^ 1);
+          uint8_t* sa = smem + stage * Cfg::STAGE_BYTES;
+          mbar_expect_tx(&full_bar[stage], Cfg::STAGE_BYTES);
+          tma_load_2d(sa, &tmap_a, &full_bar[stage], kb * BK, m0);
+          tma_load_2d(sa + Cfg::A_BYTES, &tmap_b, &full_bar[stage], kb * BK, n0);
+          if (++stage == STAGES) { stage = 0; phase ^= 1; }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ------------------------------------------------------------ MMA issuer
+    constexpr uint32_t idesc = umma_idesc_bf16(BM, BN);
+    int stage = 0;
+    uint32_t phase = 0;
+    int it = 0;
+    for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++it) {
+      const int acc = it & 1;
+      const uint32_t acc_phase = (it >> 1) & 1;
+      mbar_wait(&tempty_bar[acc], acc_phase ^ 1);
+      tc_fence_after();
+      const uint32_t d_tmem = tmem_base + acc * BN;
+      for (int kb = 0; kb < num_kb; ++kb) {
+        mbar_wait(&full_bar[stage], phase);
+        tc_fence_after();
+        if (lane == 0) {
+          const uint32_t sa = smem_u32(smem + stage * Cfg::STAGE_BYTES);
+          const uint64_t da = umma_desc_kmajor_sw128(sa);
+          const uint64_t db = umma_desc_kmajor_sw128(sa + Cfg::A_BYTES);
+#pragma unroll
+          for (int k = 0; k < BK / 16; ++k)  // +32 B per 16-element K step (encoded >> 4)
+            umma_bf16_ss(d_tmem, da + 2 * k, db + 2 * k, idesc, (kb | k) != 0);
+          umma_commit(&empty_bar[stage]);
+          if (kb == num_kb - 1) umma_commit(&tfull_bar[acc]);
+        }
+        __syncwarp();
+        if (++stage == STAGES) { stage = 0; phase ^= 1; }
+      }
+    }
+  } else {
+    // ------------------------------------------------------------ epilogue warps
+    const int quad = warp & 3;  // TMEM lane quadrant this warp may read
+    int it = 0;
+    for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++it) {
+      const int acc = it & 1;
+      const uint32_t acc_phase = (it >> 1) & 1;
+      const int m = (tile / tiles_n) * BM + quad * 32 + lane;
+      const int n0 = (tile % tiles_n) * BN;
+      mbar_wait(&tfull_bar[acc], acc_phase);
+      tc_fence_after();
+      const uint32_t t_row = tmem_base + (static_cast<uint32_t>(quad * 32) << 16) + acc * BN;
+#pragma unroll 1
+      for (int c = 0; c < BN; c += 32) {
+        uint32_t v[32];
+        tmem_ld_32x32(t_row + c, v);
+        tmem_ld_wait();
+        if (m < M && n0 + c < N) epilogue_chunk<EPI>(ep, m, n0 + c, v, N);
+      }
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&tempty_bar[acc]);
+    }
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 2) {
+    tc_fence_after();
+    tmem_dealloc(tmem_base, Cfg::TMEM_COLS);
+  }
+}
+
+template <int BN, int EPI>
+int launch(cudaStream_t stream, const CUtensorMap& ta, const CUtensorMap& tb, int M, int N, int K,
+           const GemmEpilogue& ep) {
+  using Cfg = TileCfg<BN>;
+  static bool configured[64] = {};  // per instantiation and device (the attribute is per context)
+  auto kern = gemm_tn_kernel<BN, EPI>;
+  int dev = 0;
+  PEVIT_CHECK_CUDA(cudaGetDevice(&dev));
+  if (!configured[dev & 63]) {
+    PEVIT_CHECK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM_BYTES));
+    configured[dev & 63] = true;
+  }
+  const int tiles = ((M + BM - 1) / BM) * ((N + BN - 1) / BN);
+  const int grid = tiles < sm_count() ? tiles : sm_count();
+  kern<<<grid, GEMM_THREADS, Cfg::SMEM_BYTES, stream>>>(ta, tb, M, N, K, ep);
+  PEVIT_CHECK_LAUNCH();
+  return 0;
+}
+
+template <int BN>
+int dispatch_epi(int epi, cudaStream_t s, const CUtensorMap& ta, const CUtensorMap& tb, int M, int N, int K,
+                 const GemmEpilogue& ep) {
+  switch (epi) {
+    case EPI_F32: return launch<BN, EPI_F32>(s, ta, tb, M, N, K, ep);
+    case EPI_BF16: return launch<BN, EPI_BF16>(s, ta, tb, M, N, K, ep);
+    case EPI_ACT: return launch<BN, EPI_ACT>(s, ta, tb, M, N, K, ep);
+    case EPI_DACT: return launch<BN, EPI_DACT>(s, ta, tb, M, N, K, ep);
+    case EPI_QKV: return launch<BN, EPI_QKV>(s, ta, tb, M, N, K, ep);
+  }
+  set_error("gemm_tn: unknown epilogue %d", epi);
+  return -1;
+}
+
+int pick_bn(int M, int N, int forced) {
+  if (forced == 32 || forced == 64 || forced == 128 || forced == 256) return forced;
+  if (N <= 32) return 32;
+  if (N <= 64) return 64;
+  // fewest waves wins; ties go to the wider tile (more operand reuse per byte staged)
+  const int sms = sm_count();
+  const int tm = (M + BM - 1) / BM;
+  int best = 256;
+  double best_cost = 1e30;
+  for (int bn : {256, 128, 64}) {
+    const int tiles = tm * ((N + bn - 1) / bn);
+    const int waves = (tiles + sms - 1) / sms;
+    const double cost = static_cast<double>(waves) * (bn + 24);  // + fixed per-tile pipeline fill
+    if (cost < best_cost - 1e-9) { best_cost = cost; best = bn; }
+  }
+  return best;
+}
+
+}  // namespace
+
+int gemm_tn(cudaStream_t stream, const bf16* A, int lda, const bf16* B, int ldb, int M, int N, int K, int epi,
+            const GemmEpilogue& ep, int force_bn) {
+  PEVIT_REQUIRE(M > 0 && N > 0 && K > 0, "gemm_tn: empty problem %d x %d x %d", M, N, K);
+  PEVIT_REQUIRE(K % 8 == 0 && lda % 8 == 0 && ldb % 8 == 0,
+                "gemm_tn: K, lda, ldb must be multiples of 8 (16-byte TMA strides): K=%d lda=%d ldb=%d", K, lda, ldb);
+  PEVIT_REQUIRE((reinterpret_cast<uintptr_t>(A) & 15) == 0 && (reinterpret_cast<uintptr_t>(B) & 15) == 0,
+                "gemm_tn: operands must be 16-byte aligned");
+  if (epi == EPI_QKV)
+    PEVIT_REQUIRE(ep.D % 64 == 0 && N == 3 * ep.D + ep.r2 && M == ep.L * ep.NB && ep.H * 64 == ep.D,
+                  "gemm_tn[qkv]: inconsistent shape M=%d N=%d D=%d r2=%d L=%d NB=%d H=%d", M, N, ep.D, ep.r2, ep.L,
+                  ep.NB, ep.H);
+  else
+    PEVIT_REQUIRE(ep.ld_out % 8 == 0, "gemm_tn: ld_out must be a multiple of 8");
+  const int bn = pick_bn(M, N, force_bn);
+  CUtensorMap ta, tb;
+  if (make_tmap_bf16_2d(&ta, A, M, K, lda, BM, BK) != 0) return -1;
+  if (make_tmap_bf16_2d(&tb, B, N, K, ldb, bn, BK) != 0) return -1;
+  switch (bn) {
+    case 32: return dispatch_epi<32>(epi, stream, ta, tb, M, N, K, ep);
+    case 64: return dispatch_epi<64>(epi, stream, ta, tb, M, N, K, ep);
+    case 128: return dispatch_epi<128>(epi, stream, ta, tb, M, N, K, ep);
+    default: return dispatch_epi<256>(epi, stream, ta, tb, M, N, K, ep);
+  }
+}
+
+}  // namespace pevit

@@ -1,0 +1,85 @@
+// Internal C++ interface between the kernel translation units and the C-ABI layer (api.cu).
+#pragma once
+
+#include "common.cuh"
+
+namespace pevit {
+
+// ------------------------------------------------------------------ gemm_tcgen05.cu
+enum GemmEpi { EPI_F32 = 0, EPI_BF16 = 1, EPI_ACT = 2, EPI_DACT = 3, EPI_QKV = 4 };
+enum ActKind { ACT_QUICKGELU = 0, ACT_RELU = 1, ACT_GELU_NEW = 2 };
+
+struct GemmEpilogue {
+  const float* bias = nullptr;     // [N] fp32, added to the accumulator (all modes)
+  const float* resid = nullptr;    // EPI_F32: fp32 [M][ld_out] added to the result
+  const float* resid2 = nullptr;   // EPI_F32: second residual (bottleneck: x1 + m)
+  float* out_f32 = nullptr;        // EPI_F32
+  bf16* out_bf16 = nullptr;        // EPI_BF16 / EPI_ACT (act(z)) / EPI_DACT (dz)
+  bf16* out2_bf16 = nullptr;       // EPI_ACT: pre-activation z (nullable)
+  const bf16* aux_bf16 = nullptr;  // EPI_DACT: saved pre-activation z
+  int act = ACT_QUICKGELU;         // EPI_ACT / EPI_DACT
+  int ld_out = 0;                  // row stride (elements) of out / resid / aux
+  // EPI_QKV
+  bf16* qkv_hm = nullptr;          // [3][NB*H][L][64] head-major q (pre-scaled 1/8), k, v
+  float* t_out = nullptr;          // [M][r2] low-rank activations
+  int L = 0, NB = 0, H = 0, D = 0, r2 = 0;
+};
+
+int gemm_tn(cudaStream_t stream, const bf16* A, int lda, const bf16* B, int ldb, int M, int N, int K, int epi,
+            const GemmEpilogue& ep, int force_bn = 0);
+
+// ------------------------------------------------------------------ layernorm.cu
+// y = (x - mean) * rstd * gamma + beta, statistics in fp32 (model.py:154-160).
+int layernorm_fwd(cudaStream_t s, const float* x, const float* gamma, const float* beta, bf16* y_bf16, float* y_f32,
+                  float* mean, float* rstd, int M, int D);
+// dx = LN'(dy_n) [+ dres]; dy_n given as fp32.  gamma frozen unless dgamma/dbeta non-null
+// (adapter LayerNorm: atomically accumulated, caller zeroes).
+int layernorm_bwd(cudaStream_t s, const float* dyn, const float* x, const float* gamma, const float* mean,
+                  const float* rstd, const float* dres, float* dx, bf16* dx_bf16, float* dgamma, float* dbeta, int M,
+                  int D);
+
+// ------------------------------------------------------------------ attention_ref.cu
+struct AttnShape {
+  int L, NB, H, D, r;  // r = low-rank width per projection (32 KAdaptation, 4 LoRA, 0 none)
+  float alpha;         // 160 / 32
+};
+// q,k,v: head-major bf16 [NB*H][L][64] (q pre-scaled).  T: fp32 [L*NB][2r] (LND rows).
+// Qmat: fp32 [2][D][r] (q then v factor), bias: fp32 [D] or null.
+// out: o_tok bf16 [L*NB][D] (token rows, LND), lse fp32 [NB*H][L].
+int attn_delta_fwd_ref(cudaStream_t s, const AttnShape& a, const bf16* q, const bf16* k, const bf16* v, const float* T,
+                       const float* Qmat, const float* bias, bf16* o_tok, float* lse);
+// in: do_tok bf16 [L*NB][D].  out: dqkv bf16 [L*NB][ld] token rows, cols [0,D)=dq/8,[D,2D)=dk,[2D,3D)=dv;
+// ddelta bf16 [2][NB*H][L][64] = dQ' and dV' head-major (== d(delta) viewed as [L*NB][D], F4).
+int attn_delta_bwd_ref(cudaStream_t s, const AttnShape& a, const bf16* q, const bf16* k, const bf16* v, const float* T,
+                       const float* Qmat, const float* bias, const bf16* o_tok, const bf16* do_tok, const float* lse,
+                       bf16* dqkv, int ld_dqkv, bf16* ddelta);
+
+// ------------------------------------------------------------------ lowrank.cu
+// KAdaptation factor expansion: from u1,u2 (rule*_left [32][32]), v1,v2 (rule*_right),
+// s (q_proj_adapter1_left [32][D/32]), t (q_proj_adapter1_right [32][D/32]) build
+//   w_ext rows [3D,3D+64)  : P_q^T | P_v^T  (bf16, K-major rows of length D)   -- forward B operand
+//   w_ext_t cols [3D,3D+64): P_q | P_v      (bf16, [D][3D+64])                 -- dgrad B operand
+//   qmat  fp32 [2][D][32], qmat_t bf16 [2][32][D] (B operand of dT = alpha * dDelta * Q)
+int kad_expand(cudaStream_t s, const float* u1, const float* v1, const float* u2, const float* v2, const float* sfac,
+               const float* tfac, int D, float alpha, bf16* w_ext, bf16* w_ext_t, float* qmat, bf16* qmat_t);
+// LoRA: A_q, A_v [r][D]; B_q, B_v [D][r].
+int lora_expand(cudaStream_t s, const float* Aq, const float* Av, const float* Bq, const float* Bv, int D, int r,
+                float alpha, bf16* w_ext, bf16* w_ext_t, float* qmat, bf16* qmat_t);
+// C[Kc][Nc] (fp32, += with atomics; caller zeroes) = scale * A[M][Kc]^T * B[M][Nc]; A bf16 or fp32, B fp32 or bf16.
+int atb_accumulate(cudaStream_t s, const void* A, int a_is_bf16, int lda, const void* B, int b_is_bf16, int ldb, int M,
+                   int Kc, int Nc, float scale, float* C);
+// column sums of a bf16 [M][ld] matrix (first D columns), atomically accumulated into out[D] (caller zeroes).
+int colsum_bf16(cudaStream_t s, const bf16* X, int ld, int M, int D, float* out);
+// KAdaptation factor gradients from dP [D][64] (q|v) and dQ [2][D][32].
+int kad_factor_grads(cudaStream_t s, const float* dP, const float* dQ, const float* u1, const float* v1, const float* u2,
+                     const float* v2, const float* sfac, const float* tfac, int D, float* du1, float* dv1, float* du2,
+                     float* dv2, float* dsfac, float* dtfac);
+// dT (fp32 [M][r2 cols starting at col0]) -> bf16 into dqkv_ext[:, 3D+col0 ...]
+int cast_f32_to_bf16_2d(cudaStream_t s, const float* src, int lds, bf16* dst, int ldd, int rows, int cols);
+
+// ------------------------------------------------------------------ elementwise.cu
+int cast_f32_to_bf16(cudaStream_t s, const float* src, bf16* dst, size_t n);
+// dst[c][r] = src[r][c]  (fp32 -> bf16 transpose; weight prep for dgrad GEMMs)
+int transpose_f32_to_bf16(cudaStream_t s, const float* src, int rows, int cols, bf16* dst, int ldd);
+
+}  // namespace pevit

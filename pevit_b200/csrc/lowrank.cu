@@ -1,0 +1,273 @@
+// Small-factor kernels of the parameter-efficient updates.
+//
+// KAdaptation (reference evaluation/model.py:563-584) builds H = sum_i kron(u_i v_i^T, s_i t_i^T)
+// as a materialised (32, D, D) einsum and multiplies x by it.  Here H is never formed:
+// H = P Q^T with P[:, i] = u_i (x) s_i, Q[:, i] = v_i (x) t_i, so the
+// forward only needs P^T appended as 2*32 extra rows of the in-projection weight (the QKV GEMM
+// then emits T = X P for free) and Q for the in-attention expansion.  The factor gradients are
+// the matching contractions of dP = X^T dT and dQ = alpha * dDelta^T T.
+// LoRA (lora_model.py:490-514) is the same with P = A^T, Q = B, r = 4.
+#include "common.cuh"
+#include "kernels.h"
+
+namespace pevit {
+namespace {
+
+__global__ void kad_expand_kernel(const float* __restrict__ u1, const float* __restrict__ v1,
+                                  const float* __restrict__ u2, const float* __restrict__ v2,
+                                  const float* __restrict__ sf, const float* __restrict__ tf, int D, float alpha,
+                                  bf16* __restrict__ w_ext, bf16* __restrict__ w_ext_t, float* __restrict__ qmat,
+                                  bf16* __restrict__ qmat_t) {
+  const int F = D / 32;
+  const int ld_t = 3 * D + 64;
+  const int total = 32 * D;  // (i, a, k)
+  for (int idx = blockIdx.x * blockDim.x + threadIdx.x; idx < total; idx += gridDim.x * blockDim.x) {
+    const int i = idx / D, col = idx % D;  // col = a*F + k  (or c*F + p)
+    const int a = col / F, k = col % F;
+    const float s = sf[i * F + k], t = tf[i * F + k];
+    const float pq = u1[i * 32 + a] * s, pv = u2[i * 32 + a] * s;
+    const float qq = v1[i * 32 + a] * t, qv = v2[i * 32 + a] * t;
+    w_ext[static_cast<size_t>(3 * D + i) * D + col] = __float2bfloat16(pq);
+    w_ext[static_cast<size_t>(3 * D + 32 + i) * D + col] = __float2bfloat16(pv);
+    w_ext_t[static_cast<size_t>(col) * ld_t + 3 * D + i] = __float2bfloat16(pq);
+    w_ext_t[static_cast<size_t>(col) * ld_t + 3 * D + 32 + i] = __float2bfloat16(pv);
+    qmat[static_cast<size_t>(col) * 32 + i] = qq;
+    qmat[static_cast<size_t>(D + col) * 32 + i] = qv;
+    qmat_t[static_cast<size_t>(i) * D + col] = __float2bfloat16(alpha * qq);
+    qmat_t[static_cast<size_t>(32 + i) * D + col] = __float2bfloat16(alpha * qv);
+  }
+}
+
+__global__ void lora_expand_kernel(const float* __restrict__ Aq, const float* __restrict__ Av,
+                                   const float* __restrict__ Bq, const float* __restrict__ Bv, int D, int r,
+                                   float alpha, bf16* __restrict__ w_ext, bf16* __restrict__ w_ext_t,
+                                   float* __restrict__ qmat, bf16* __restrict__ qmat_t) {
+  const int ld_t = 3 * D + 2 * r;
+  const int total = r * D;
+  for (int idx = blockIdx.x * blockDim.x + threadIdx.x; idx < total; idx += gridDim.x * blockDim.x) {
+    const int i = idx / D, col = idx % D;
+    const float pq = Aq[i * D + col], pv = Av[i * D + col];
+    const float qq = Bq[col * r + i], qv = Bv[col * r + i];
+    w_ext[static_cast<size_t>(3 * D + i) * D + col] = __float2bfloat16(pq);
+    w_ext[static_cast<size_t>(3 * D + r + i) * D + col] = __float2bfloat16(pv);
+    w_ext_t[static_cast<size_t>(col) * ld_t + 3 * D + i] = __float2bfloat16(pq);
+    w_ext_t[static_cast<size_t>(col) * ld_t + 3 * D + r + i] = __float2bfloat16(pv);
+    qmat[static_cast<size_t>(col) * r + i] = qq;
+    qmat[static_cast<size_t>(D + col) * r + i] = qv;
+    qmat_t[static_cast<size_t>(i) * D + col] = __float2bfloat16(alpha * qq);
+    qmat_t[static_cast<size_t>(r + i) * D + col] = __float2bfloat16(alpha * qv);
+  }
+}
+
+// C[kc][nc] += scale * sum_m A[m][kc] * B[m][nc].  CUDA-core split-M version: each CTA owns a
+// 64-wide slab of kc and a slice of rows, stages A (64 cols) and B (<= 64 cols) tiles of 32 rows in
+// shared memory, then adds its partial with one atomic per output.
+constexpr int ATB_TK = 64, ATB_TM = 32, ATB_THREADS = 256;
+
+template <typename TA, typename TB>
+__global__ void __launch_bounds__(ATB_THREADS)
+atb_kernel(const TA* __restrict__ A, int lda, const TB* __restrict__ B, int ldb, int M, int Kc, int Nc, float scale,
+           float* __restrict__ C, int rows_per_cta) {
+  __shared__ float sA[ATB_TM][ATB_TK + 1];
+  __shared__ float sB[ATB_TM][64 + 1];
+  const int kc0 = blockIdx.x * ATB_TK;
+  const int m_begin = blockIdx.y * rows_per_cta;
+  const int m_end = min(M, m_begin + rows_per_cta);
+  // thread owns outputs (kc = tid/4 .. , nc = (tid%4)*16 .. +16): 64 x 64 tile / 256 threads = 16 each
+  const int tk = threadIdx.x >> 2;        // 0..63
+  const int tn0 = (threadIdx.x & 3) * 16;  // 0,16,32,48
+  float acc[16];
+#pragma unroll
+  for (int j = 0; j < 16; ++j) acc[j] = 0.f;
+  for (int m0 = m_begin; m0 < m_end; m0 += ATB_TM) {
+    for (int idx = threadIdx.x; idx < ATB_TM * ATB_TK; idx += ATB_THREADS) {
+      const int mm = idx / ATB_TK, kk = idx % ATB_TK;
+      const int m = m0 + mm, kc = kc0 + kk;
+      sA[mm][kk] = (m < m_end && kc < Kc) ? static_cast<float>(A[static_cast<size_t>(m) * lda + kc]) : 0.f;
+    }
+    for (int idx = threadIdx.x; idx < ATB_TM * 64; idx += ATB_THREADS) {
+      const int mm = idx / 64, nn = idx % 64;
+      const int m = m0 + mm;
+      sB[mm][nn] = (m < m_end && nn < Nc) ? static_cast<float>(B[static_cast<size_t>(m) * ldb + nn]) : 0.f;
+    }
+    __syncthreads();
+#pragma unroll 4
+    for (int mm = 0; mm < ATB_TM; ++mm) {
+      const float av = sA[mm][tk];
+#pragma unroll
+      for (int j = 0; j < 16; ++j) acc[j] = fmaf(av, sB[mm][tn0 + j], acc[j]);
+    }
+    __syncthreads();
+  }
+  const int kc = kc0 + tk;
+  if (kc < Kc) {
+#pragma unroll
+    for (int j = 0; j < 16; ++j)
+      if (tn0 + j < Nc) atomicAdd(C + static_cast<size_t>(kc) * Nc + tn0 + j, scale * acc[j]);
+  }
+}
+
+__global__ void colsum_bf16_kernel(const bf16* __restrict__ X, int ld, int M, int D, float* __restrict__ out,
+                                   int rows_per_cta) {
+  const int m_begin = blockIdx.y * rows_per_cta;
+  const int m_end = min(M, m_begin + rows_per_cta);
+  const int c = blockIdx.x * blockDim.x + threadIdx.x;
+  if (c >= D) return;
+  float acc = 0.f;
+  for (int m = m_begin; m < m_end; ++m) acc += __bfloat162float(X[static_cast<size_t>(m) * ld + c]);
+  atomicAdd(out + c, acc);
+}
+
+// one CTA per Kronecker term i.  dP [D][64] (q | v), dQ [2][D][32].
+__global__ void kad_factor_grads_kernel(const float* __restrict__ dP, const float* __restrict__ dQ,
+                                        const float* __restrict__ u1, const float* __restrict__ v1,
+                                        const float* __restrict__ u2, const float* __restrict__ v2,
+                                        const float* __restrict__ sf, const float* __restrict__ tf, int D,
+                                        float* __restrict__ du1, float* __restrict__ dv1, float* __restrict__ du2,
+                                        float* __restrict__ dv2, float* __restrict__ dsf, float* __restrict__ dtf) {
+  const int i = blockIdx.x;
+  const int F = D / 32;
+  // du*[i][a] and dv*[i][a]: a < 32
+  for (int a = threadIdx.x; a < 32; a += blockDim.x) {
+    float gu1 = 0.f, gu2 = 0.f, gv1 = 0.f, gv2 = 0.f;
+    for (int k = 0; k < F; ++k) {
+      const int col = a * F + k;
+      const float s = sf[i * F + k], t = tf[i * F + k];
+      gu1 = fmaf(dP[static_cast<size_t>(col) * 64 + i], s, gu1);
+      gu2 = fmaf(dP[static_cast<size_t>(col) * 64 + 32 + i], s, gu2);
+      gv1 = fmaf(dQ[static_cast<size_t>(col) * 32 + i], t, gv1);
+      gv2 = fmaf(dQ[static_cast<size_t>(D + col) * 32 + i], t, gv2);
+    }
+    du1[i * 32 + a] = gu1; du2[i * 32 + a] = gu2;
+    dv1[i * 32 + a] = gv1; dv2[i * 32 + a] = gv2;
+  }
+  // ds[i][k], dt[i][k]: k < F  (s and t are shared by the q and v branches -- F2)
+  for (int k = threadIdx.x; k < F; k += blockDim.x) {
+    float gs = 0.f, gt = 0.f;
+    for (int a = 0; a < 32; ++a) {
+      const int col = a * F + k;
+      gs = fmaf(dP[static_cast<size_t>(col) * 64 + i], u1[i * 32 + a], gs);
+      gs = fmaf(dP[static_cast<size_t>(col) * 64 + 32 + i], u2[i * 32 + a], gs);
+      gt = fmaf(dQ[static_cast<size_t>(col) * 32 + i], v1[i * 32 + a], gt);
+      gt = fmaf(dQ[static_cast<size_t>(D + col) * 32 + i], v2[i * 32 + a], gt);
+    }
+    dsf[i * F + k] = gs;
+    dtf[i * F + k] = gt;
+  }
+}
+
+__global__ void cast2d_kernel(const float* __restrict__ src, int lds, bf16* __restrict__ dst, int ldd, int rows,
+                              int cols) {
+  const size_t total = static_cast<size_t>(rows) * cols;
+  for (size_t idx = blockIdx.x * static_cast<size_t>(blockDim.x) + threadIdx.x; idx < total;
+       idx += static_cast<size_t>(gridDim.x) * blockDim.x) {
+    const size_t r = idx / cols, c = idx % cols;
+    dst[r * ldd + c] = __float2bfloat16(src[r * lds + c]);
+  }
+}
+
+__global__ void cast_kernel(const float* __restrict__ src, bf16* __restrict__ dst, size_t n) {
+  for (size_t i = blockIdx.x * static_cast<size_t>(blockDim.x) + threadIdx.x; i < n;
+       i += static_cast<size_t>(gridDim.x) * blockDim.x)
+    dst[i] = __float2bfloat16(src[i]);
+}
+
+__global__ void transpose_cast_kernel(const float* __restrict__ src, int rows, int cols, bf16* __restrict__ dst,
+                                      int ldd) {
+  __shared__ float tile[32][33];
+  const int c0 = blockIdx.x * 32, r0 = blockIdx.y * 32;
+  for (int j = threadIdx.y; j < 32; j += blockDim.y) {
+    const int r = r0 + j, c = c0 + threadIdx.x;
+    tile[j][threadIdx.x] = (r < rows && c < cols) ? src[static_cast<size_t>(r) * cols + c] : 0.f;
+  }
+  __syncthreads();
+  for (int j = threadIdx.y; j < 32; j += blockDim.y) {
+    const int c = c0 + j, r = r0 + threadIdx.x;
+    if (c < cols && r < rows) dst[static_cast<size_t>(c) * ldd + r] = __float2bfloat16(tile[threadIdx.x][j]);
+  }
+}
+
+int grid_for(size_t n, int threads) {
+  size_t g = (n + threads - 1) / threads;
+  const size_t cap = static_cast<size_t>(sm_count()) * 8;
+  return static_cast<int>(g < 1 ? 1 : (g > cap ? cap : g));
+}
+
+}  // namespace
+
+int kad_expand(cudaStream_t s, const float* u1, const float* v1, const float* u2, const float* v2, const float* sfac,
+               const float* tfac, int D, float alpha, bf16* w_ext, bf16* w_ext_t, float* qmat, bf16* qmat_t) {
+  PEVIT_REQUIRE(D % 32 == 0, "kad_expand: D=%d not divisible by phm_dim 32", D);
+  kad_expand_kernel<<<grid_for(32 * static_cast<size_t>(D), 256), 256, 0, s>>>(u1, v1, u2, v2, sfac, tfac, D, alpha,
+                                                                               w_ext, w_ext_t, qmat, qmat_t);
+  PEVIT_CHECK_LAUNCH();
+  return 0;
+}
+
+int lora_expand(cudaStream_t s, const float* Aq, const float* Av, const float* Bq, const float* Bv, int D, int r,
+                float alpha, bf16* w_ext, bf16* w_ext_t, float* qmat, bf16* qmat_t) {
+  lora_expand_kernel<<<grid_for(static_cast<size_t>(r) * D, 256), 256, 0, s>>>(Aq, Av, Bq, Bv, D, r, alpha, w_ext,
+                                                                               w_ext_t, qmat, qmat_t);
+  PEVIT_CHECK_LAUNCH();
+  return 0;
+}
+
+int atb_accumulate(cudaStream_t s, const void* A, int a_is_bf16, int lda, const void* B, int b_is_bf16, int ldb, int M,
+                   int Kc, int Nc, float scale, float* C) {
+  PEVIT_REQUIRE(Nc >= 1 && Nc <= 64, "atb_accumulate: Nc=%d must be in 1..64", Nc);
+  const int gx = (Kc + ATB_TK - 1) / ATB_TK;
+  int splits = (sm_count() * 4 + gx - 1) / gx;
+  int rows_per_cta = (M + splits - 1) / splits;
+  rows_per_cta = ((rows_per_cta + ATB_TM - 1) / ATB_TM) * ATB_TM;
+  splits = (M + rows_per_cta - 1) / rows_per_cta;
+  dim3 grid(gx, splits);
+  if (a_is_bf16 && b_is_bf16)
+    atb_kernel<bf16, bf16><<<grid, ATB_THREADS, 0, s>>>((const bf16*)A, lda, (const bf16*)B, ldb, M, Kc, Nc, scale, C, rows_per_cta);
+  else if (a_is_bf16)
+    atb_kernel<bf16, float><<<grid, ATB_THREADS, 0, s>>>((const bf16*)A, lda, (const float*)B, ldb, M, Kc, Nc, scale, C, rows_per_cta);
+  else if (b_is_bf16)
+    atb_kernel<float, bf16><<<grid, ATB_THREADS, 0, s>>>((const float*)A, lda, (const bf16*)B, ldb, M, Kc, Nc, scale, C, rows_per_cta);
+  else
+    atb_kernel<float, float><<<grid, ATB_THREADS, 0, s>>>((const float*)A, lda, (const float*)B, ldb, M, Kc, Nc, scale, C, rows_per_cta);
+  PEVIT_CHECK_LAUNCH();
+  return 0;
+}
+
+int colsum_bf16(cudaStream_t s, const bf16* X, int ld, int M, int D, float* out) {
+  const int gx = (D + 255) / 256;
+  int splits = (sm_count() * 4 + gx - 1) / gx;
+  const int rows_per_cta = (M + splits - 1) / splits;
+  splits = (M + rows_per_cta - 1) / rows_per_cta;
+  colsum_bf16_kernel<<<dim3(gx, splits), 256, 0, s>>>(X, ld, M, D, out, rows_per_cta);
+  PEVIT_CHECK_LAUNCH();
+  return 0;
+}
+
+int kad_factor_grads(cudaStream_t s, const float* dP, const float* dQ, const float* u1, const float* v1, const float* u2,
+                     const float* v2, const float* sfac, const float* tfac, int D, float* du1, float* dv1, float* du2,
+                     float* dv2, float* dsfac, float* dtfac) {
+  kad_factor_grads_kernel<<<32, 64, 0, s>>>(dP, dQ, u1, v1, u2, v2, sfac, tfac, D, du1, dv1, du2, dv2, dsfac, dtfac);
+  PEVIT_CHECK_LAUNCH();
+  return 0;
+}
+
+int cast_f32_to_bf16_2d(cudaStream_t s, const float* src, int lds, bf16* dst, int ldd, int rows, int cols) {
+  cast2d_kernel<<<grid_for(static_cast<size_t>(rows) * cols, 256), 256, 0, s>>>(src, lds, dst, ldd, rows, cols);
+  PEVIT_CHECK_LAUNCH();
+  return 0;
+}
+
+int cast_f32_to_bf16(cudaStream_t s, const float* src, bf16* dst, size_t n) {
+  cast_kernel<<<grid_for(n, 256), 256, 0, s>>>(src, dst, n);
+  PEVIT_CHECK_LAUNCH();
+  return 0;
+}
+
+int transpose_f32_to_bf16(cudaStream_t s, const float* src, int rows, int cols, bf16* dst, int ldd) {
+  dim3 grid((cols + 31) / 32, (rows + 31) / 32), block(32, 8);
+  transpose_cast_kernel<<<grid, block, 0, s>>>(src, rows, cols, dst, ldd);
+  PEVIT_CHECK_LAUNCH();
+  return 0;
+}
+
+}  // namespace pevit

@@ -1,0 +1,236 @@
+"""Autograd bridge between the nn.Module surface and the C ABI.
+
+``block_forward(block, x)`` runs one ResidualAttentionBlock through
+``pevit_block_fwd`` / ``pevit_block_bwd``.  Frozen weights are packed once per block
+into bf16 operand layouts (``BlockPack``); only the PEFT tensors and the input are
+autograd inputs, so frozen-backbone gradients are never allocated.
+"""
+from __future__ import annotations
+
+import ctypes as C
+from typing import Dict, Optional, Tuple
+
+import torch
+
+from . import _lib as L
+
+METHOD_IDS = {"plain": L.PLAIN, "kadaptation": L.KADAPTATION, "lora": L.LORA,
+              "adapter": L.ADAPTER, "compacter": L.COMPACTER}
+# scale factors hard-coded in the reference constructors (F6):
+KAD_ALPHA = 128 / 4 * 5      # model.py:564
+LORA_ALPHA = 128 / 4         # lora_model.py:491
+BOTTLENECK = 64              # adapter_model.py:305 / compacter_model.py:477 (down_sample=64)
+
+
+def _ptr(t: Optional[torch.Tensor]) -> Optional[int]:
+    return None if t is None else t.data_ptr()
+
+
+def _stream() -> int:
+    return torch.cuda.current_stream().cuda_stream
+
+
+def _f32c(t: torch.Tensor) -> torch.Tensor:
+    """contiguous fp32 view/copy (parameters are fp32 in the reference; F10)."""
+    if t.dtype != torch.float32:
+        t = t.float()
+    return t.contiguous()
+
+
+_workspace: Dict[Tuple[int, int], torch.Tensor] = {}
+
+
+def workspace(device: torch.device, nbytes: int) -> torch.Tensor:
+    """One scratch buffer per (device, stream); all blocks share it (stream-ordered reuse)."""
+    key = (device.index or 0, _stream())
+    buf = _workspace.get(key)
+    if buf is None or buf.numel() < nbytes:
+        buf = torch.empty(nbytes, dtype=torch.uint8, device=device)
+        _workspace[key] = buf
+    return buf
+
+
+class BlockPack:
+    """bf16 operand copies of one block's frozen weights (+ slots for the expanded factors)."""
+
+    def __init__(self, block, method: str):
+        self.method = method
+        attn = block.attn
+        w_in = attn.in_proj_weight.detach()
+        dev = w_in.device
+        D = w_in.shape[1]
+        self.D, self.H = D, attn.num_heads
+        self.r = {"kadaptation": 32, "lora": 4}.get(method, 0)
+        self.alpha = {"kadaptation": KAD_ALPHA, "lora": LORA_ALPHA}.get(method, 0.0)
+        W3 = 3 * D + 2 * self.r
+        bf = dict(dtype=torch.bfloat16, device=dev)
+        cast, transpose = self.cast, self.transpose
+
+        self.w_qkv_ext = torch.zeros(W3, D, **bf)
+        self.w_qkv_ext_t = torch.zeros(D, W3, **bf)
+        cast(w_in, self.w_qkv_ext)                      # rows [0, 3D)
+        transpose(w_in, self.w_qkv_ext_t, W3)           # cols [0, 3D)
+        wo = attn.out_proj.weight
+        self.w_o, self.w_o_t = torch.empty(D, D, **bf), torch.empty(D, D, **bf)
+        cast(wo, self.w_o); transpose(wo, self.w_o_t, D)
+        wfc, wpr = block.mlp.c_fc.weight, block.mlp.c_proj.weight
+        self.w_fc, self.w_fc_t = torch.empty(4 * D, D, **bf), torch.empty(D, 4 * D, **bf)
+        cast(wfc, self.w_fc); transpose(wfc, self.w_fc_t, 4 * D)
+        self.w_proj, self.w_proj_t = torch.empty(D, 4 * D, **bf), torch.empty(4 * D, D, **bf)
+        cast(wpr, self.w_proj); transpose(wpr, self.w_proj_t, D)
+        self.small = [_f32c(t.detach()) for t in (
+            attn.in_proj_bias, attn.out_proj.bias, block.mlp.c_fc.bias, block.mlp.c_proj.bias,
+            block.ln_1.weight, block.ln_1.bias, block.ln_2.weight, block.ln_2.bias)]
+        if self.r:
+            self.qmat = torch.zeros(2, D, self.r, dtype=torch.float32, device=dev)
+            self.qmat_t = torch.zeros(2, self.r, D, **bf)
+        else:
+            self.qmat = self.qmat_t = None
+        if method in ("adapter", "compacter"):
+            self.w_down, self.w_down_t = torch.empty(BOTTLENECK, D, **bf), torch.empty(D, BOTTLENECK, **bf)
+            self.w_up, self.w_up_t = torch.empty(D, BOTTLENECK, **bf), torch.empty(BOTTLENECK, D, **bf)
+        self.key = self.signature(block)
+
+    @staticmethod
+    def cast(src: torch.Tensor, dst: torch.Tensor) -> None:
+        """fp32 -> bf16, same layout (written into the leading elements of dst)."""
+        src = _f32c(src.detach())
+        L.check(L.lib().pevit_cast_bf16(src.data_ptr(), dst.data_ptr(), src.numel(), _stream()), "pevit_cast_bf16")
+
+    @staticmethod
+    def transpose(src: torch.Tensor, dst: torch.Tensor, ldd: int) -> None:
+        """dst[c][r] = bf16(src[r][c]) with leading dimension ldd."""
+        src = _f32c(src.detach())
+        L.check(L.lib().pevit_transpose_bf16(src.data_ptr(), src.shape[0], src.shape[1], dst.data_ptr(), ldd,
+                                             _stream()), "pevit_transpose_bf16")
+
+    @staticmethod
+    def signature(block) -> tuple:
+        ts = (block.attn.in_proj_weight, block.attn.in_proj_bias, block.attn.out_proj.weight,
+              block.attn.out_proj.bias, block.mlp.c_fc.weight, block.mlp.c_fc.bias, block.mlp.c_proj.weight,
+              block.mlp.c_proj.bias, block.ln_1.weight, block.ln_1.bias, block.ln_2.weight, block.ln_2.bias)
+        return tuple((t.data_ptr(), t._version, str(t.device)) for t in ts)
+
+    def weights_struct(self, delta_bias=None, lna=None, b_down=None, b_up=None) -> L.BlockWeights:
+        s = self.small
+        w = L.BlockWeights()
+        w.w_qkv_ext, w.w_qkv_ext_t, w.b_qkv = _ptr(self.w_qkv_ext), _ptr(self.w_qkv_ext_t), _ptr(s[0])
+        w.w_o, w.w_o_t, w.b_o = _ptr(self.w_o), _ptr(self.w_o_t), _ptr(s[1])
+        w.w_fc, w.w_fc_t, w.b_fc = _ptr(self.w_fc), _ptr(self.w_fc_t), _ptr(s[2])
+        w.w_proj, w.w_proj_t, w.b_proj = _ptr(self.w_proj), _ptr(self.w_proj_t), _ptr(s[3])
+        w.ln1_g, w.ln1_b, w.ln2_g, w.ln2_b = (_ptr(t) for t in s[4:8])
+        w.qmat, w.qmat_t, w.delta_bias = _ptr(self.qmat), _ptr(self.qmat_t), _ptr(delta_bias)
+        if lna is not None:
+            w.lna_g, w.lna_b = _ptr(lna[0]), _ptr(lna[1])
+            w.w_down, w.w_down_t, w.b_down = _ptr(self.w_down), _ptr(self.w_down_t), _ptr(b_down)
+            w.w_up, w.w_up_t, w.b_up = _ptr(self.w_up), _ptr(self.w_up_t), _ptr(b_up)
+        return w
+
+
+def get_pack(block, method: str) -> BlockPack:
+    pack = getattr(block, "_pevit_pack", None)
+    if pack is None or pack.method != method or pack.key != BlockPack.signature(block):
+        pack = BlockPack(block, method)
+        object.__setattr__(block, "_pevit_pack", pack)
+    return pack
+
+
+class _BlockFn(torch.autograd.Function):
+    """y = ResidualAttentionBlock(x); differentiable w.r.t. x and the PEFT tensors only."""
+
+    @staticmethod
+    def forward(ctx, x, pack: BlockPack, attn_impl: int, *peft):
+        lib = L.lib()
+        method = pack.method
+        Lt, NB, D = x.shape
+        st = _stream()
+        x = _f32c(x)
+        peft_c = tuple(_f32c(t.detach()) for t in peft)
+        delta_bias = lna = b_down = b_up = None
+        if method == "kadaptation":
+            u1, v1, u2, v2, s, t, b = peft_c
+            L.check(lib.pevit_kad_expand(_ptr(u1), _ptr(v1), _ptr(u2), _ptr(v2), _ptr(s), _ptr(t), D, pack.alpha,
+                                         _ptr(pack.w_qkv_ext), _ptr(pack.w_qkv_ext_t), _ptr(pack.qmat),
+                                         _ptr(pack.qmat_t), st), "pevit_kad_expand")
+            delta_bias = b
+        elif method == "lora":
+            aq, bq, av, bv = peft_c
+            L.check(lib.pevit_lora_expand(_ptr(aq), _ptr(av), _ptr(bq), _ptr(bv), D, pack.r, pack.alpha,
+                                          _ptr(pack.w_qkv_ext), _ptr(pack.w_qkv_ext_t), _ptr(pack.qmat),
+                                          _ptr(pack.qmat_t), st), "pevit_lora_expand")
+        elif method in ("adapter", "compacter"):
+            g, bta, w_down, b_down, w_up, b_up = peft_c   # w_down [64][D], w_up [D][64] dense
+            lna = (g, bta)
+            pack.cast(w_down, pack.w_down); pack.transpose(w_down, pack.w_down_t, BOTTLENECK)
+            pack.cast(w_up, pack.w_up); pack.transpose(w_up, pack.w_up_t, D)
+        need_grad = any(ctx.needs_input_grad)
+        desc = L.BlockDesc(Lt, NB, D, pack.H, METHOD_IDS[method], pack.r, pack.alpha, int(need_grad), attn_impl,
+                           int(ctx.needs_input_grad[0]))
+        saved = torch.empty(lib.pevit_block_saved_bytes(C.byref(desc)), dtype=torch.uint8, device=x.device)
+        ws = workspace(x.device, lib.pevit_block_workspace_bytes(C.byref(desc)))
+        y = torch.empty_like(x)
+        w = pack.weights_struct(delta_bias, lna, b_down, b_up)
+        L.check(lib.pevit_block_fwd(C.byref(desc), C.byref(w), _ptr(x), _ptr(y), _ptr(saved), _ptr(ws), st),
+                "pevit_block_fwd")
+        ctx.pack, ctx.desc = pack, desc
+        ctx.save_for_backward(x, saved, *peft_c)
+        return y
+
+    @staticmethod
+    def backward(ctx, dy):
+        lib = L.lib()
+        pack, desc = ctx.pack, ctx.desc
+        method = pack.method
+        x, saved, *peft_c = ctx.saved_tensors
+        D, r = pack.D, pack.r
+        dev = x.device
+        st = _stream()
+        dy = _f32c(dy)
+        f32 = dict(dtype=torch.float32, device=dev)
+        dx = torch.empty_like(x) if desc.need_dx else None
+        g = L.BlockGrads()
+        delta_bias = lna = b_down = b_up = None
+        if method in ("kadaptation", "lora"):
+            d_pmat = torch.zeros(D, 2 * r, **f32)
+            d_qmat = torch.zeros(2, D, r, **f32)
+            g.d_pmat, g.d_qmat = _ptr(d_pmat), _ptr(d_qmat)
+            if method == "kadaptation":
+                d_bias = torch.zeros(D, **f32)
+                g.d_bias = _ptr(d_bias)
+                delta_bias = peft_c[6]
+        else:
+            lna = (peft_c[0], peft_c[1]); b_down, b_up = peft_c[3], peft_c[5]
+            d_lna_g, d_lna_b = torch.zeros(D, **f32), torch.zeros(D, **f32)
+            d_w_down_t, d_b_down = torch.zeros(D, BOTTLENECK, **f32), torch.zeros(BOTTLENECK, **f32)
+            d_w_up, d_b_up = torch.zeros(D, BOTTLENECK, **f32), torch.zeros(D, **f32)
+            g.d_lna_g, g.d_lna_b = _ptr(d_lna_g), _ptr(d_lna_b)
+            g.d_w_down, g.d_b_down, g.d_w_up, g.d_b_up = _ptr(d_w_down_t), _ptr(d_b_down), _ptr(d_w_up), _ptr(d_b_up)
+        w = pack.weights_struct(delta_bias, lna, b_down, b_up)
+        ws = workspace(dev, lib.pevit_block_workspace_bytes(C.byref(desc)))
+        L.check(lib.pevit_block_bwd(C.byref(desc), C.byref(w), _ptr(x), _ptr(dy), _ptr(dx), C.byref(g), _ptr(saved),
+                                    _ptr(ws), st), "pevit_block_bwd")
+        if method == "kadaptation":
+            u1, v1, u2, v2, s, t, _ = peft_c
+            outs = [torch.empty_like(p) for p in (u1, v1, u2, v2, s, t)]
+            L.check(lib.pevit_kad_factor_grads(_ptr(d_pmat), _ptr(d_qmat), _ptr(u1), _ptr(v1), _ptr(u2), _ptr(v2),
+                                               _ptr(s), _ptr(t), D, *(_ptr(o) for o in outs), st),
+                    "pevit_kad_factor_grads")
+            grads = (*outs, d_bias)
+        elif method == "lora":
+            # P = A^T, Q = B  ->  dA = dP^T, dB = dQ   (lora_model.py:490-514)
+            grads = (d_pmat[:, :r].t().contiguous(), d_qmat[0], d_pmat[:, r:].t().contiguous(), d_qmat[1])
+        else:
+            grads = (d_lna_g, d_lna_b, d_w_down_t.t().contiguous(), d_b_down, d_w_up, d_b_up)
+        return (dx, None, None, *grads)
+
+
+def block_forward(block, x: torch.Tensor, method: str, peft: tuple, attn_impl: int = 0) -> torch.Tensor:
+    if not x.is_cuda:
+        raise RuntimeError("pevit_b200 blocks run on CUDA (sm_100a) only; there is no CPU fallback")
+    if block.training and method == "kadaptation":
+        # F7: the reference never puts the backbone in train mode; kdropout(0.5) on H is unsupported.
+        raise RuntimeError("pevit_b200 KAdaptation blocks support eval mode only (reference never calls .train())")
+    if x.dim() != 3:
+        raise ValueError(f"expected (L, N, D) input, got {tuple(x.shape)}")
+    pack = get_pack(block, method)
+    return _BlockFn.apply(x, pack, attn_impl, *peft)

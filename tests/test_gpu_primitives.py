@@ -1,0 +1,292 @@
+"""Parity of every exported CUDA primitive against a plain PyTorch fp32 statement of the same op
+(run on the B200 box: ``pytest -m gpu``).  All calls go through the C ABI (ctypes).
+
+Tolerances (bf16 operands, fp32 accumulation): rel-inf 1e-2 for bf16 outputs, 3e-3 for fp32
+outputs of bf16 GEMMs, 1e-5 for pure fp32 kernels (LayerNorm).
+"""
+import ctypes as C
+import math
+
+import pytest
+import torch
+
+from pevit_b200 import _lib as L
+from tests._util import rel_inf
+
+pytestmark = pytest.mark.gpu
+
+
+def st():
+    return torch.cuda.current_stream().cuda_stream
+
+
+def bf(t):
+    return t.to(torch.bfloat16).contiguous()
+
+
+@pytest.fixture(scope="module")
+def lib():
+    handle = L.lib()
+    torch.cuda.init()
+    L.check(handle.pevit_check_device(), "pevit_check_device")
+    return handle
+
+
+def run_gemm(lib, a, b, epi, **kw):
+    args = L.GemmArgs()
+    args.a, args.lda, args.b, args.ldb = a.data_ptr(), a.stride(0), b.data_ptr(), b.stride(0)
+    args.m, args.n, args.k, args.epilogue = a.shape[0], b.shape[0], a.shape[1], epi
+    for k, v in kw.items():
+        setattr(args, k, v.data_ptr() if isinstance(v, torch.Tensor) else v)
+    L.check(lib.pevit_gemm_tn(C.byref(args), st()), "pevit_gemm_tn")
+    torch.cuda.synchronize()
+
+
+@pytest.mark.parametrize("M,N,K,bn", [
+    (128, 256, 64, 0), (256, 128, 128, 128), (400, 768, 768, 0), (400, 768, 768, 64), (400, 768, 768, 256),
+    (12800, 768, 3072, 0), (1000, 3072, 768, 0), (130, 72, 776, 0), (400, 32, 768, 0), (400, 4, 768, 0),
+    (400, 768, 64, 0),
+])
+def test_gemm_f32_bias_resid(lib, M, N, K, bn):
+    g = torch.Generator(device="cuda").manual_seed(M + N + K)
+    a = bf(torch.randn(M, K, device="cuda", generator=g))
+    b = bf(torch.randn(N, K, device="cuda", generator=g) / math.sqrt(K))
+    ldo = (N + 7) // 8 * 8
+    bias = torch.randn(N, device="cuda", generator=g)
+    resid = torch.randn(M, ldo, device="cuda", generator=g)
+    out = torch.full((M, ldo), float("nan"), device="cuda")
+    run_gemm(lib, a, b, L.EPI_F32, bias=bias, resid=resid, out_f32=out, ld_out=ldo, force_bn=bn)
+    ref = a.float() @ b.float().t() + bias + resid[:, :N]
+    assert torch.isfinite(out[:, :N]).all()
+    assert rel_inf(out[:, :N], ref) < 3e-3
+    if ldo > N:
+        assert torch.isnan(out[:, N:]).all(), "wrote past N"
+
+
+def test_gemm_bf16_and_strided_out(lib):
+    M, N, K = 400, 32, 768
+    a = bf(torch.randn(M, K, device="cuda"))
+    b = bf(torch.randn(N, K, device="cuda") / math.sqrt(K))
+    big = torch.zeros(M, 2368, dtype=torch.bfloat16, device="cuda")
+    args_out = big[:, 2304 + 32:]
+    run_gemm(lib, a, b, L.EPI_BF16, out_bf16=args_out, ld_out=2368)
+    ref = a.float() @ b.float().t()
+    assert rel_inf(big[:, 2336:2368].float(), ref) < 1e-2
+    assert big[:, :2336].abs().max() == 0
+
+
+def test_gemm_quickgelu_fwd_bwd(lib):
+    M, N, K = 400, 3072, 768
+    a = bf(torch.randn(M, K, device="cuda"))
+    b = bf(torch.randn(N, K, device="cuda") / math.sqrt(K))
+    bias = torch.randn(N, device="cuda") * 0.1
+    h = torch.empty(M, N, dtype=torch.bfloat16, device="cuda")
+    z = torch.empty_like(h)
+    run_gemm(lib, a, b, L.EPI_QGELU, bias=bias, out_bf16=h, out2_bf16=z, ld_out=N)
+    zr = a.float() @ b.float().t() + bias
+    assert rel_inf(z.float(), zr) < 1e-2
+    assert rel_inf(h.float(), zr * torch.sigmoid(1.702 * zr)) < 1e-2
+    # backward epilogue: dz = (dy W) * g'(z)
+    dy = bf(torch.randn(M, 768, device="cuda"))
+    wt = bf(torch.randn(N, 768, device="cuda") / math.sqrt(768))
+    dz = torch.empty(M, N, dtype=torch.bfloat16, device="cuda")
+    run_gemm(lib, dy, wt, L.EPI_DQGELU, out_bf16=dz, aux_bf16=z, ld_out=N)
+    zf = z.float()
+    s = torch.sigmoid(1.702 * zf)
+    ref = (dy.float() @ wt.float().t()) * (s * (1 + 1.702 * zf * (1 - s)))
+    assert rel_inf(dz.float(), ref) < 1e-2
+
+
+@pytest.mark.parametrize("Lt,NB,D,r2", [(50, 8, 768, 64), (5, 3, 128, 64), (197, 2, 768, 8), (50, 8, 768, 0)])
+def test_gemm_qkv_epilogue(lib, Lt, NB, D, r2):
+    H, M, W3 = D // 64, Lt * NB, 3 * D + r2
+    x = bf(torch.randn(M, D, device="cuda"))
+    w = bf(torch.randn(W3, D, device="cuda") / math.sqrt(D))
+    bias = torch.randn(3 * D, device="cuda") * 0.1
+    qkv = torch.full((3, NB * H, Lt, 64), float("nan"), dtype=torch.bfloat16, device="cuda")
+    t = torch.full((M, max(r2, 1)), float("nan"), device="cuda")
+    run_gemm(lib, x, w, L.EPI_QKV, bias=bias, qkv_hm=qkv, t_out=t, L=Lt, NB=NB, H=H, D=D, r2=r2)
+    full = x.float() @ w.float().t()
+    proj = (full[:, :3 * D] + bias).view(Lt, NB, 3, H, 64).permute(2, 1, 3, 0, 4).reshape(3, NB * H, Lt, 64).clone()
+    proj[0] *= 0.125
+    assert rel_inf(qkv.float(), proj) < 1e-2
+    if r2:
+        assert rel_inf(t, full[:, 3 * D:]) < 3e-3
+
+
+@pytest.mark.parametrize("M,D", [(400, 768), (257, 1024), (15, 128)])
+def test_layernorm_fwd_bwd(lib, M, D):
+    x = (torch.randn(M, D, device="cuda") * 2 + 0.5).requires_grad_(True)
+    g = (1 + 0.1 * torch.randn(D, device="cuda")).requires_grad_(True)
+    b = (0.1 * torch.randn(D, device="cuda")).requires_grad_(True)
+    y16 = torch.empty(M, D, dtype=torch.bfloat16, device="cuda")
+    y32 = torch.empty(M, D, device="cuda")
+    mean, rstd = torch.empty(M, device="cuda"), torch.empty(M, device="cuda")
+    L.check(lib.pevit_layernorm_fwd(x.data_ptr(), g.data_ptr(), b.data_ptr(), y16.data_ptr(), y32.data_ptr(),
+                                    mean.data_ptr(), rstd.data_ptr(), M, D, st()), "ln_fwd")
+    ref = torch.nn.functional.layer_norm(x, (D,), g, b, 1e-5)
+    assert rel_inf(y32, ref.detach()) < 1e-5
+    assert rel_inf(y16.float(), ref.detach()) < 5e-3
+    dyn = torch.randn(M, D, device="cuda")
+    dres = torch.randn(M, D, device="cuda")
+    ref.backward(dyn)
+    dx = torch.empty(M, D, device="cuda")
+    dx16 = torch.empty(M, D, dtype=torch.bfloat16, device="cuda")
+    dg, db = torch.zeros(D, device="cuda"), torch.zeros(D, device="cuda")
+    L.check(lib.pevit_layernorm_bwd(dyn.data_ptr(), x.data_ptr(), g.data_ptr(), mean.data_ptr(), rstd.data_ptr(),
+                                    dres.data_ptr(), dx.data_ptr(), dx16.data_ptr(), dg.data_ptr(), db.data_ptr(),
+                                    M, D, st()), "ln_bwd")
+    torch.cuda.synchronize()
+    assert rel_inf(dx, x.grad + dres) < 2e-5
+    assert rel_inf(dx16.float(), x.grad + dres) < 5e-3
+    assert rel_inf(dg, g.grad) < 1e-4
+    assert rel_inf(db, b.grad) < 1e-4
+    # frozen-gamma variant
+    dx2 = torch.empty(M, D, device="cuda")
+    L.check(lib.pevit_layernorm_bwd(dyn.data_ptr(), x.data_ptr(), g.data_ptr(), mean.data_ptr(), rstd.data_ptr(),
+                                    None, dx2.data_ptr(), None, None, None, M, D, st()), "ln_bwd")
+    torch.cuda.synchronize()
+    assert rel_inf(dx2, x.grad) < 2e-5
+
+
+def torch_attention(q, k, v, T, qmat, bias, alpha, Lt, NB, H, D, r):
+    """fp32 statement of model.py:786-815 on head-major inputs (q pre-scaled)."""
+    q, k, v = q.float(), k.float(), v.float()
+    if r:
+        dq = alpha * T[:, :r] @ qmat[0].t()
+        dv = alpha * T[:, r:] @ qmat[1].t()
+        if bias is not None:
+            dq, dv = dq + bias, dv + bias
+        q = q + dq.reshape(NB * H, Lt, 64)   # F4: raw reinterpretation of the (L*N, D) delta
+        v = v + dv.reshape(NB * H, Lt, 64)
+    p = torch.softmax(q @ k.transpose(1, 2), dim=-1)
+    o = p @ v                                  # (NB*H, L, 64)
+    o_tok = o.view(NB, H, Lt, 64).permute(2, 0, 1, 3).reshape(Lt * NB, D)
+    lse = torch.logsumexp(q @ k.transpose(1, 2), dim=-1)
+    return o_tok, lse
+
+
+@pytest.mark.parametrize("Lt,NB,D,r,use_bias", [(50, 8, 768, 32, True), (5, 3, 128, 32, True), (197, 2, 768, 4, False),
+                                                (50, 5, 768, 0, False), (257, 2, 1024, 32, True)])
+@pytest.mark.parametrize("impl", [0, 1])
+def test_attention_fwd_bwd(lib, Lt, NB, D, r, use_bias, impl):
+    H, M = D // 64, Lt * NB
+    alpha = 160.0 if r == 32 else 32.0
+    dev = "cuda"
+    q = (torch.randn(NB * H, Lt, 64, device=dev) * 0.5)
+    k = torch.randn(NB * H, Lt, 64, device=dev)
+    v = torch.randn(NB * H, Lt, 64, device=dev)
+    q16, k16, v16 = bf(q), bf(k), bf(v)
+    T = (torch.randn(M, max(2 * r, 1), device=dev) * 0.05) if r else None
+    qmat = (torch.randn(2, D, r, device=dev) * 0.02) if r else None
+    bias = (torch.randn(D, device=dev) * 0.1) if use_bias else None
+    leaves = [t.float().clone().requires_grad_(True) for t in (q16, k16, v16)]
+    Tl = T.clone().requires_grad_(True) if r else None
+    ql = qmat.clone().requires_grad_(True) if r else None
+    bl = bias.clone().requires_grad_(True) if use_bias else None
+    o_ref, lse_ref = torch_attention(leaves[0], leaves[1], leaves[2], Tl, ql, bl, alpha, Lt, NB, H, D, r)
+
+    a = L.AttnArgs()
+    a.L, a.NB, a.H, a.D, a.r, a.alpha, a.impl = Lt, NB, H, D, r, alpha, impl
+    a.q, a.k, a.v = q16.data_ptr(), k16.data_ptr(), v16.data_ptr()
+    a.t = T.data_ptr() if r else None
+    a.qmat = qmat.data_ptr() if r else None
+    a.delta_bias = bias.data_ptr() if use_bias else None
+    o = torch.empty(M, D, dtype=torch.bfloat16, device=dev)
+    lse = torch.empty(NB * H, Lt, device=dev)
+    a.o_tok, a.lse = o.data_ptr(), lse.data_ptr()
+    L.check(lib.pevit_attn_fwd(C.byref(a), st()), "attn_fwd")
+    torch.cuda.synchronize()
+    assert rel_inf(o.float(), o_ref.detach()) < 1e-2
+    assert rel_inf(lse, lse_ref.detach()) < 2e-3
+
+    do = bf(torch.randn(M, D, device=dev))
+    o_ref.backward(do.float())
+    ld = 3 * D + 2 * r
+    dqkv = torch.zeros(M, ld, dtype=torch.bfloat16, device=dev)
+    dd = torch.zeros(2, NB * H, Lt, 64, dtype=torch.bfloat16, device=dev)
+    a.do_tok, a.dqkv, a.ld_dqkv, a.ddelta = do.data_ptr(), dqkv.data_ptr(), ld, dd.data_ptr()
+    L.check(lib.pevit_attn_bwd(C.byref(a), st()), "attn_bwd")
+    torch.cuda.synchronize()
+
+    def tok(g):  # head-major grad -> token-major (L*NB, D)
+        return g.view(NB, H, Lt, 64).permute(2, 0, 1, 3).reshape(M, D)
+    # leaves[0] is q/8-scaled input: dqkv holds d(x Wq) = dq' / 8
+    assert rel_inf(dqkv[:, :D].float(), tok(leaves[0].grad) * 0.125) < 1.5e-2
+    assert rel_inf(dqkv[:, D:2 * D].float(), tok(leaves[1].grad)) < 1.5e-2
+    assert rel_inf(dqkv[:, 2 * D:3 * D].float(), tok(leaves[2].grad)) < 1.5e-2
+    assert rel_inf(dd[0].float(), leaves[0].grad) < 1.5e-2
+    assert rel_inf(dd[1].float(), leaves[2].grad) < 1.5e-2
+    if r:
+        # the downstream contractions the block performs on d(delta) (F4: same memory, viewed (M, D))
+        ddq, ddv = dd[0].float().reshape(M, D), dd[1].float().reshape(M, D)
+        dT = torch.cat([alpha * ddq @ qmat[0], alpha * ddv @ qmat[1]], dim=1)
+        assert rel_inf(dT, Tl.grad) < 1.5e-2
+        dQ = torch.stack([alpha * ddq.t() @ T[:, :r], alpha * ddv.t() @ T[:, r:]])
+        assert rel_inf(dQ, ql.grad) < 1.5e-2
+        if use_bias:
+            assert rel_inf(ddq.sum(0) + ddv.sum(0), bl.grad) < 1.5e-2
+
+
+def test_atb_colsum_and_kad_factors(lib):
+    M, D = 1000, 768
+    dev = "cuda"
+    a16 = bf(torch.randn(M, D, device=dev))
+    b32 = torch.randn(M, 64, device=dev)
+    c = torch.zeros(D, 64, device=dev)
+    L.check(lib.pevit_atb_accumulate(a16.data_ptr(), 1, D, b32.data_ptr(), 0, 64, M, D, 64, 2.0, c.data_ptr(), st()),
+            "atb")
+    cs = torch.zeros(D, device=dev)
+    L.check(lib.pevit_colsum_bf16(a16.data_ptr(), M, D, cs.data_ptr(), st()), "colsum")
+    # narrow B inside a wider matrix (LoRA: Nc = 4 of ldb = 8), bf16 B
+    b16 = bf(torch.randn(M, 8, device=dev))
+    c4 = torch.zeros(D, 4, device=dev)
+    L.check(lib.pevit_atb_accumulate(a16.data_ptr(), 1, D, b16[:, 4:].data_ptr(), 1, 8, M, D, 4, 1.0, c4.data_ptr(),
+                                     st()), "atb")
+    torch.cuda.synchronize()
+    assert rel_inf(c, 2.0 * a16.float().t() @ b32) < 1e-4
+    assert rel_inf(cs, a16.float().sum(0)) < 1e-4
+    assert rel_inf(c4, a16.float().t() @ b16[:, 4:].float()) < 1e-4
+
+    # KAdaptation expansion and factor gradients against autograd over the materialised Kronecker sum
+    F_ = D // 32
+    prm = [torch.randn(*s, device=dev) * 0.3 for s in ((32, 32), (32, 32), (32, 32), (32, 32), (32, F_), (32, F_))]
+    u1, v1, u2, v2, s_, t_ = [p.clone().requires_grad_(True) for p in prm]
+    alpha = 160.0
+    W3 = 3 * D + 64
+    w_ext = torch.zeros(W3, D, dtype=torch.bfloat16, device=dev)
+    w_ext_t = torch.zeros(D, W3, dtype=torch.bfloat16, device=dev)
+    qmat = torch.zeros(2, D, 32, device=dev)
+    qmat_t = torch.zeros(2, 32, D, dtype=torch.bfloat16, device=dev)
+    L.check(lib.pevit_kad_expand(*(p.data_ptr() for p in prm), D, alpha, w_ext.data_ptr(), w_ext_t.data_ptr(),
+                                 qmat.data_ptr(), qmat_t.data_ptr(), st()), "kad_expand")
+    torch.cuda.synchronize()
+
+    def H_of(u, v):  # model.py:406-417, 567-575: sum_i kron(u_i v_i^T, s_i t_i^T)
+        rule = torch.einsum("ia,ic->iac", u, v)
+        w = torch.einsum("ik,ip->ikp", s_, t_)
+        return torch.einsum("iac,ikp->akcp", rule, w).reshape(D, D)
+    Pq = w_ext[3 * D:3 * D + 32].float().t()
+    Pv = w_ext[3 * D + 32:].float().t()
+    assert rel_inf(Pq @ qmat[0].t(), H_of(u1, v1).detach()) < 1e-2
+    assert rel_inf(Pv @ qmat[1].t(), H_of(u2, v2).detach()) < 1e-2
+    assert torch.equal(w_ext_t[:, 3 * D:], w_ext[3 * D:].t())
+    assert rel_inf(qmat_t.float(), alpha * qmat.transpose(1, 2)) < 1e-2
+    # gradients: loss = <G1, H_q> + <G2, H_v>  =>  dP = G Q, dQ = G^T P
+    G1, G2 = torch.randn(D, D, device=dev), torch.randn(D, D, device=dev)
+    ((G1 * H_of(u1, v1)).sum() + (G2 * H_of(u2, v2)).sum()).backward()
+    with torch.no_grad():
+        def PQ(u, v):
+            P = torch.einsum("ia,ik->aki", u, s_).reshape(D, 32)
+            Q = torch.einsum("ic,ip->cpi", v, t_).reshape(D, 32)
+            return P, Q
+        P1, Q1 = PQ(u1, v1)
+        P2, Q2 = PQ(u2, v2)
+        dP = torch.cat([G1 @ Q1, G2 @ Q2], dim=1).contiguous()
+        dQ = torch.stack([G1.t() @ P1, G2.t() @ P2]).contiguous()
+    outs = [torch.empty_like(p) for p in prm]
+    L.check(lib.pevit_kad_factor_grads(dP.data_ptr(), dQ.data_ptr(), *(p.data_ptr() for p in prm), D,
+                                       *(o.data_ptr() for o in outs), st()), "kad_factor_grads")
+    torch.cuda.synchronize()
+    for o, p in zip(outs, (u1, v1, u2, v2, s_, t_)):
+        assert rel_inf(o, p.grad) < 1e-4
