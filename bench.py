@@ -1,0 +1,373 @@
+#!/usr/bin/env python
+"""Headline benchmark: images/sec of one ViT-B/32 KAdaptation fine-tune step (BASELINE.json).
+
+    python bench.py [--gpus N] [--steps K] [--warmup W]            # this repo's sm_100a path
+    python bench.py --impl reference [...]                         # reference algorithm on the host CPU
+
+A step = zero_grad + forward + CrossEntropy + backward + (N>1: one NCCL all-reduce of the flat
+adapter-gradient buffer) + SGD, on one batch of synthetic 224x224 images per GPU (weak scaling,
+256 images per GPU = BASELINE configs[1]).  One JSON line is printed by rank 0.
+
+  value    : whole-job images/s, inputs already resident in HBM, CUDA-event timed, max over ranks
+  e2e      : same step driven from pinned HOST buffers: per-step H2D copy of the image batch and
+             labels (prefetched on a copy stream, inside the timed region) and a D2H read of the loss
+  roofline : dominant kernel class of the step (by device time, CUDA events around every launch of
+             this library inside the timed region) against the measured peaks in MEASURED_PEAKS.json
+  cpu_baseline : the oracle (CPU restatement of the reference algorithm) timed on the host cores
+"""
+from __future__ import annotations
+
+import argparse
+import ctypes as C
+import json
+import os
+import statistics
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+import torch  # noqa: E402
+
+METRIC = "images/sec ViT-B/32 KAdaptation step at 1/2/4/8 B200; logits max-abs-err"
+FALLBACK_PEAKS = {"hbm_gbs": 6650.0, "bf16_tflops": 1590.0, "bf16_tflops_sustained": 1400.0}
+
+
+def parse():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=5)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--method", default="kadaptation", choices=["kadaptation", "lora", "adapter", "compacter"])
+    ap.add_argument("--model", default="vit_b32", choices=["vit_b32", "vit_b16", "vit_l14"])
+    ap.add_argument("--batch", type=int, default=256, help="images per GPU per step")
+    ap.add_argument("--cpu-batch", type=int, default=32, help="images per CPU-baseline step (bounded sample)")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    return ap.parse_args()
+
+
+def shape_of(name):
+    from pevit_b200 import synth
+    return {"vit_b32": synth.VIT_B32, "vit_b16": synth.VIT_B16, "vit_l14": synth.VIT_L14}[name]
+
+
+def workload(args, shape):
+    return {"workload": f"{args.model} CLIP + {args.method} fine-tune step, synthetic 224x224, "
+                        f"batch {args.batch}/GPU", "model": args.model, "method": args.method,
+            "per_gpu_batch": args.batch, "global_batch": args.batch * args.gpus, "tokens": shape.tokens,
+            "width": shape.vision_width, "layers": shape.vision_layers, "parallelism": f"dp{args.gpus}",
+            "l2_policy": "inputs larger than L2 (154 MB fp32 image batch, >3 GB of saved activations per step)"}
+
+
+# ----------------------------------------------------------------------------- clocks
+class ClockSampler:
+    Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+         "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index: int):
+        self.rows, self.proc = [], None
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--id={index}", f"--query-gpu={self.Q}",
+                                          "--format=csv,noheader,nounits", "-lms", "100"],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.thread = threading.Thread(target=self._pump, daemon=True)
+            self.thread.start()
+        except OSError:
+            self.proc = None
+
+    def _pump(self):
+        for line in self.proc.stdout:
+            self.rows.append((time.time(), line.strip()))
+
+    def mark(self):
+        return time.time()
+
+    def stop(self):
+        if self.proc is not None:
+            self.proc.terminate()
+            try:
+                self.proc.wait(timeout=2)
+            except Exception:
+                self.proc.kill()
+
+    def summary(self, t0: float, t1: float) -> dict:
+        sm, smax, reasons = [], 0.0, set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for ts, line in self.rows:
+            if not (t0 <= ts <= t1 + 0.2):
+                continue
+            f = [x.strip() for x in line.split(",")]
+            try:
+                sm.append(float(f[0])); smax = max(smax, float(f[1]))
+            except (ValueError, IndexError):
+                continue
+            for nm, val in zip(names, f[3:7]):
+                if val.lower().startswith("active"):
+                    reasons.add(nm)
+        return {"sm_mhz": statistics.median(sm) if sm else None, "sm_max_mhz": smax or None,
+                "reasons": sorted(reasons), "samples": len(sm)}
+
+
+# ----------------------------------------------------------------------------- CPU arm (oracle)
+def oracle_step_fn(args, shape):
+    from oracle import pevit_oracle as O
+    from pevit_b200 import synth
+    p = dict(synth.clip_state_dict(shape, seed=0))
+    O.init_adapters(p, args.method, seed=0)
+    synth.randomize_adapters(p.items(), seed=1)
+    g = torch.Generator().manual_seed(4)
+    hw = torch.randn(10, shape.embed_dim, generator=g) * shape.embed_dim ** -0.5
+    hb = torch.zeros(10)
+
+    def step(n, seed):
+        img, lab = synth.images(n, shape.image_resolution, seed=seed), synth.labels(n, 10, seed=seed + 1)
+        t0 = time.perf_counter()
+        O.train_step_grads(img, lab, p, hw, hb, args.method)
+        return time.perf_counter() - t0
+    return step
+
+
+def cpu_baseline(args, shape, steps=2, warmup=1) -> dict:
+    step = oracle_step_fn(args, shape)
+    for i in range(warmup):
+        step(min(4, args.cpu_batch), 100 + i)
+    ts = [step(args.cpu_batch, 200 + i) for i in range(steps)]
+    return {"value": args.cpu_batch / statistics.median(ts), "unit": "images/s", "cores": torch.get_num_threads(),
+            "kind": "port", "host_cpus": os.cpu_count(),
+            "sample": f"{steps} fwd+bwd step(s) of {args.cpu_batch} images, {args.model} {args.method}, fp32, "
+                      "oracle/pevit_oracle.py (reference algorithm: materialised Kronecker sums)"}
+
+
+def run_reference(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    shape = shape_of(args.model)
+    step = oracle_step_fn(args, shape)
+    for i in range(args.warmup):
+        step(args.cpu_batch, 100 + i)
+    ts = [step(args.cpu_batch, 200 + i) for i in range(args.steps)]
+    total = sum(ts)
+    ips = args.cpu_batch * args.steps / total
+    cfg = workload(args, shape)
+    cfg["sample"] = f"each step = {args.cpu_batch} images (bounded sample of the {args.batch}-image batch)"
+    line = {"impl": "reference", "metric": METRIC, "value": ips, "unit": "images/s", "n_gpus": args.gpus,
+            "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * total / args.steps,
+            "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "config": cfg,
+            "cpu_baseline": {"value": ips, "unit": "images/s", "cores": torch.get_num_threads(), "kind": "port",
+                             "host_cpus": os.cpu_count(),
+                             "sample": f"{args.steps} fwd+bwd steps of {args.cpu_batch} images on the host CPU, "
+                                       "oracle/pevit_oracle.py (the Python reference cannot travel to the GPU box)"},
+            "e2e": {"value": ips, "unit": "images/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+            "gpu_launches": 0}
+    print(json.dumps(line), flush=True)
+
+
+# ----------------------------------------------------------------------------- B200 arm
+def peaks():
+    path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(path):
+        with open(path) as fh:
+            d = json.load(fh)
+        return d, "measured (MEASURED_PEAKS.json)"
+    return dict(FALLBACK_PEAKS), "fallback (B200_PROFILING.md)"
+
+
+def gemm_flops(cls: str, M: int, D: int, r2: int) -> float:
+    W3 = 3 * D + r2
+    dims = {"gemm_qkv": (W3, D), "gemm_out": (D, D), "gemm_fc": (4 * D, D), "gemm_proj": (D, 4 * D),
+            "gemm_dproj": (4 * D, D), "gemm_dfc": (D, 4 * D), "gemm_dout": (D, D), "gemm_dqkv": (D, W3),
+            "gemm_dT": (r2 // 2, D)}
+    n, k = dims[cls]
+    return 2.0 * M * n * k
+
+
+def attn_bytes(cls: str, L: int, NB: int, D: int, H: int, r: int) -> float:
+    # per image per layer, bf16 q,k,v,o in HBM
+    per_img = (8 * L * D + 4 * L * r + 4 * L * H) if cls == "attn_fwd" else (16 * L * D + 8 * L * r + 4 * L * H)
+    return float(per_img) * NB
+
+
+def run_b200(args):
+    import torch.distributed as dist
+    from pevit_b200 import _lib, engine
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    if world != args.gpus:
+        raise SystemExit(f"--gpus {args.gpus} but WORLD_SIZE={world}: launch with torch.distributed.run")
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        dist.init_process_group("nccl", device_id=dev)
+    lib = _lib.lib()
+    _lib.check(lib.pevit_check_device(), "pevit_check_device")
+    shape = shape_of(args.model)
+    tuner = engine.FineTuner(args.method, shape, device=dev, distributed=world > 1, seed=0)
+    N, R = args.batch, shape.image_resolution
+    g = torch.Generator(device=dev).manual_seed(1000 + rank)
+    images = torch.randn(N, 3, R, R, device=dev, generator=g)
+    labels = torch.randint(0, 10, (N,), device=dev, generator=g)
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def reduce_max(ms: float) -> float:
+        if world == 1:
+            return ms
+        t = torch.tensor([ms], device=dev, dtype=torch.float64)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t.item())
+
+    for _ in range(max(args.warmup, 3)):
+        tuner.step(images, labels)
+    clocks = ClockSampler(local) if rank == 0 else None
+
+    # ---- device-resident timing (value) with per-launch events for the roofline
+    ncls = lib.pevit_prof_num_classes()
+    lib.pevit_prof_reset()
+    barrier()
+    lib.pevit_prof_enable(1)
+    launches0 = lib.pevit_launch_count()
+    t_wall0 = time.time()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(args.steps):
+        tuner.step(images, labels)
+    e1.record()
+    torch.cuda.synchronize()
+    lib.pevit_prof_enable(0)
+    launches = lib.pevit_launch_count() - launches0
+    ms_total = reduce_max(e0.elapsed_time(e1))
+    barrier()
+    t_wall1 = time.time()
+    ms_arr, cnt_arr = (C.c_double * ncls)(), (C.c_int64 * ncls)()
+    _lib.check(lib.pevit_prof_read(ms_arr, cnt_arr, ncls), "pevit_prof_read")
+
+    # ---- end-to-end timing: host-resident inputs, H2D every step (prefetched), loss read back every step
+    host_img = [torch.randn(N, 3, R, R).pin_memory() for _ in range(2)]
+    host_lab = [torch.randint(0, 10, (N,)).pin_memory() for _ in range(2)]
+    dev_img = [torch.empty_like(images) for _ in range(2)]
+    dev_lab = [torch.empty_like(labels) for _ in range(2)]
+    copy_stream = torch.cuda.Stream(device=dev)
+    ready = [torch.cuda.Event() for _ in range(2)]
+    consumed = [torch.cuda.Event() for _ in range(2)]
+
+    def prefetch(i):
+        b = i & 1
+        with torch.cuda.stream(copy_stream):
+            copy_stream.wait_event(consumed[b])
+            dev_img[b].copy_(host_img[b], non_blocking=True)
+            dev_lab[b].copy_(host_lab[b], non_blocking=True)
+            ready[b].record(copy_stream)
+
+    def e2e_loop(steps):
+        for b in range(2):
+            consumed[b].record()
+        prefetch(0)
+        loss_host = 0.0
+        for i in range(steps):
+            b = i & 1
+            if i + 1 < steps:
+                prefetch(i + 1)
+            torch.cuda.current_stream().wait_event(ready[b])
+            loss = tuner.step(dev_img[b], dev_lab[b])
+            consumed[b].record()
+            loss_host = loss.item()  # D2H of the step's result (kadaptation_clip.py:354)
+        return loss_host
+
+    e2e_loop(2)
+    barrier()
+    e2, e3 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e2.record()
+    last_loss = e2e_loop(args.steps)
+    e3.record()
+    torch.cuda.synchronize()
+    ms_e2e = reduce_max(e2.elapsed_time(e3))
+    barrier()
+    t_wall2 = time.time()
+    if clocks is not None:
+        clocks.stop()
+    if rank != 0:
+        if world > 1:
+            dist.destroy_process_group()
+        return
+
+    ms_step = ms_total / args.steps
+    value = N * world * args.steps / (ms_total / 1e3)
+    e2e_value = N * world * args.steps / (ms_e2e / 1e3)
+    pk, pk_src = peaks()
+    L_, D, H = shape.tokens, shape.vision_width, shape.heads
+    r = {"kadaptation": 32, "lora": 4}.get(args.method, 0)
+    M = L_ * N
+    kernels = {}
+    for i in range(ncls):
+        if cnt_arr[i]:
+            name = lib.pevit_prof_class_name(i).decode()
+            kernels[name] = {"ms_per_step": ms_arr[i] / args.steps, "launches_per_step": cnt_arr[i] / args.steps,
+                             "avg_us": 1e3 * ms_arr[i] / cnt_arr[i]}
+    own_ms = sum(k["ms_per_step"] for k in kernels.values())
+    for k in kernels.values():
+        k["share_of_step"] = k["ms_per_step"] / ms_step
+
+    def roofline_of(name):
+        k = kernels[name]
+        sec = k["avg_us"] * 1e-6
+        if name.startswith("attn"):
+            alg = attn_bytes(name, L_, N, D, H, r)
+            ach, peak, unit, bound = alg / sec / 1e9, pk["hbm_gbs"], "GB/s", "hbm"
+        else:
+            alg = gemm_flops(name, M, D, 2 * r)
+            ach, peak, unit, bound = alg / sec / 1e12, pk.get("bf16_tflops_sustained", pk["bf16_tflops"]), "TFLOP/s", "tensor"
+        return {"kernel": name, "bound": bound, "achieved": ach, "peak": peak, "unit": unit, "frac": ach / peak,
+                "traffic": None, "algorithmic_per_launch": alg, "avg_launch_us": k["avg_us"],
+                "share_of_step": k["share_of_step"], "peak_source": pk_src}
+
+    rated = [n for n in kernels if n.startswith("attn") or (n.startswith("gemm") and n not in
+                                                              ("gemm_other", "gemm_bottleneck"))]
+    dominant = max(rated, key=lambda n: kernels[n]["ms_per_step"])
+    roof = roofline_of(dominant)
+    traffic_file = os.path.join(ROOT, "profiles", "ncu_traffic.json")
+    if os.path.exists(traffic_file):
+        with open(traffic_file) as fh:
+            roof["traffic"] = json.load(fh).get(dominant)
+    line = {
+        "metric": METRIC, "value": value, "unit": "images/s", "n_gpus": world, "steps": args.steps,
+        "warmup": max(args.warmup, 3), "ms_per_step": ms_step, "higher_is_better": True, "scaling": "weak",
+        "vs_baseline": None, "dtype": "bf16", "data": "synthetic", "config": workload(args, shape),
+        "clocks": clocks.summary(t_wall0, t_wall2) if clocks else None,
+        "e2e": {"value": e2e_value, "unit": "images/s", "ms_per_step": ms_e2e / args.steps,
+                "h2d_bytes_per_step": (images.numel() * 4 + labels.numel() * 8) * world,
+                "d2h_bytes_per_step": 4 * world, "last_loss": last_loss},
+        "gpu_launches": int(launches),
+        "roofline": roof,
+        "roofline_attn": {n: roofline_of(n) for n in ("attn_fwd", "attn_bwd") if n in kernels},
+        "kernels": kernels, "own_kernel_ms_per_step": own_ms,
+        "trainable_params": tuner.trainable_numel(),
+    }
+    if world == 1 and not args.no_cpu_baseline:
+        line["cpu_baseline"] = cpu_baseline(args, shape)
+    print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def main():
+    args = parse()
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        run_b200(args)
+
+
+if __name__ == "__main__":
+    main()

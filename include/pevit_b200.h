@@ -50,6 +50,15 @@ const char* pevit_last_error(void);
 /* 0 if the current device is sm_100 (B200); < 0 with a message otherwise. */
 int pevit_check_device(void);
 
+/* Launch accounting: every kernel launch of this library is counted; with profiling enabled each
+ * launch is bracketed by CUDA events on its stream and attributed to a kernel class. */
+int pevit_prof_enable(int32_t on);
+int pevit_prof_reset(void);
+int pevit_prof_num_classes(void);
+const char* pevit_prof_class_name(int32_t cls);
+int pevit_prof_read(double* ms, int64_t* launches, int32_t n); /* waits for the events, then clears */
+int64_t pevit_launch_count(void);                              /* launches since the library was loaded */
+
 /* ------------------------------------------------------------------ primitives
  * (exported so every kernel can be parity-tested on its own) */
 

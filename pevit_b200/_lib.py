@@ -68,6 +68,12 @@ _SIGNATURES = {
     "pevit_abi_version": (c_int32, []),
     "pevit_last_error": (C.c_char_p, []),
     "pevit_check_device": (c_int32, []),
+    "pevit_prof_enable": (c_int32, [c_int32]),
+    "pevit_prof_reset": (c_int32, []),
+    "pevit_prof_num_classes": (c_int32, []),
+    "pevit_prof_class_name": (C.c_char_p, [c_int32]),
+    "pevit_prof_read": (c_int32, [c_void_p, c_void_p, c_int32]),
+    "pevit_launch_count": (C.c_int64, []),
     "pevit_gemm_tn": (c_int32, [_P(GemmArgs), c_void_p]),
     "pevit_layernorm_fwd": (c_int32, [c_void_p] * 7 + [c_int32, c_int32, c_void_p]),
     "pevit_layernorm_bwd": (c_int32, [c_void_p] * 10 + [c_int32, c_int32, c_void_p]),

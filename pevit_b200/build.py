@@ -40,7 +40,8 @@ def _sources():
 
 def _stamp() -> str:
     h = hashlib.sha256()
-    for f in sorted(os.listdir(CSRC)) + ["../../include/pevit_b200.h"]:
+    srcs = [f for f in sorted(os.listdir(CSRC)) if f.endswith((".cu", ".cuh", ".h"))]
+    for f in srcs + ["../../include/pevit_b200.h"]:
         with open(os.path.join(CSRC, f), "rb") as fh:
             h.update(f.encode() + b"\0" + fh.read())
     h.update(" ".join(NVCC_FLAGS).encode())

@@ -224,6 +224,16 @@ int pevit_transpose_bf16(const float* src, int32_t rows, int32_t cols, void* dst
   return transpose_f32_to_bf16(as_stream(stream), src, rows, cols, static_cast<bf16*>(dst), ldd);
 }
 
+int pevit_prof_enable(int32_t on) { return prof_enable(on); }
+int pevit_prof_reset(void) { return prof_reset(); }
+int pevit_prof_num_classes(void) { return PC_COUNT; }
+const char* pevit_prof_class_name(int32_t cls) { return prof_class_name(cls); }
+int pevit_prof_read(double* ms, int64_t* launches, int32_t n) {
+  static_assert(sizeof(long long) == sizeof(int64_t), "int64 layout");
+  return prof_read(ms, reinterpret_cast<long long*>(launches), n);
+}
+int64_t pevit_launch_count(void) { return launch_count(); }
+
 size_t pevit_block_saved_bytes(const pevit_block_desc* desc) {
   if (check_desc(desc) != 0) return 0;
   return carve_saved(*desc, nullptr).bytes;
@@ -255,6 +265,7 @@ int pevit_block_fwd(const pevit_block_desc* desc, const pevit_block_weights* w, 
     GemmEpilogue ep;
     ep.bias = w->b_qkv; ep.qkv_hm = sv.qkv_hm; ep.t_out = sv.T;
     ep.L = d.L; ep.NB = d.NB; ep.H = d.H; ep.D = D; ep.r2 = r2;
+    prof_set_tag(PC_GEMM_QKV);
     TRY(gemm_tn(s, sv.xn1, D, static_cast<const bf16*>(w->w_qkv_ext), D, M, W3, D, EPI_QKV, ep));
   }
   // attention core with in-kernel delta
@@ -268,6 +279,7 @@ int pevit_block_fwd(const pevit_block_desc* desc, const pevit_block_weights* w, 
   {
     GemmEpilogue ep;
     ep.bias = w->b_o; ep.resid = x; ep.out_f32 = sv.x1; ep.ld_out = D;
+    prof_set_tag(PC_GEMM_OUT);
     TRY(gemm_tn(s, sv.o_tok, D, static_cast<const bf16*>(w->w_o), D, M, D, D, EPI_F32, ep));
   }
   // ln_2, c_fc + QuickGELU
@@ -276,11 +288,13 @@ int pevit_block_fwd(const pevit_block_desc* desc, const pevit_block_weights* w, 
     GemmEpilogue ep;
     ep.bias = w->b_fc; ep.out_bf16 = wk.h; ep.out2_bf16 = d.save ? sv.z : nullptr; ep.ld_out = 4 * D;
     ep.act = ACT_QUICKGELU;
+    prof_set_tag(PC_GEMM_FC);
     TRY(gemm_tn(s, wk.xn2, D, static_cast<const bf16*>(w->w_fc), D, M, 4 * D, D, EPI_ACT, ep));
   }
   if (!has_bottleneck(d)) {
     GemmEpilogue ep;
     ep.bias = w->b_proj; ep.resid = sv.x1; ep.out_f32 = y; ep.ld_out = D;
+    prof_set_tag(PC_GEMM_PROJ);
     TRY(gemm_tn(s, wk.h, 4 * D, static_cast<const bf16*>(w->w_proj), 4 * D, M, D, 4 * D, EPI_F32, ep));
     return 0;
   }
@@ -288,6 +302,7 @@ int pevit_block_fwd(const pevit_block_desc* desc, const pevit_block_weights* w, 
   {
     GemmEpilogue ep;
     ep.bias = w->b_proj; ep.out_f32 = sv.m; ep.ld_out = D;
+    prof_set_tag(PC_GEMM_PROJ);
     TRY(gemm_tn(s, wk.h, 4 * D, static_cast<const bf16*>(w->w_proj), 4 * D, M, D, 4 * D, EPI_F32, ep));
   }
   TRY(layernorm_fwd(s, sv.m, w->lna_g, w->lna_b, sv.a_n, nullptr, sv.mean_a, sv.rstd_a, M, D));
@@ -295,11 +310,13 @@ int pevit_block_fwd(const pevit_block_desc* desc, const pevit_block_weights* w, 
     GemmEpilogue ep;
     ep.bias = w->b_down; ep.out_bf16 = sv.u; ep.out2_bf16 = sv.zd; ep.ld_out = 64;
     ep.act = d.method == PEVIT_ADAPTER ? ACT_RELU : ACT_GELU_NEW;
+    prof_set_tag(PC_GEMM_BOTTLENECK);
     TRY(gemm_tn(s, sv.a_n, D, static_cast<const bf16*>(w->w_down), D, M, 64, D, EPI_ACT, ep));
   }
   {
     GemmEpilogue ep;
     ep.bias = w->b_up; ep.resid = sv.x1; ep.resid2 = sv.m; ep.out_f32 = y; ep.ld_out = D;
+    prof_set_tag(PC_GEMM_BOTTLENECK);
     TRY(gemm_tn(s, sv.u, 64, static_cast<const bf16*>(w->w_up), 64, M, D, 64, EPI_F32, ep));
   }
   return 0;
@@ -329,6 +346,7 @@ int pevit_block_bwd(const pevit_block_desc* desc, const pevit_block_weights* w, 
     {
       GemmEpilogue ep;
       ep.out_bf16 = wk.dzd; ep.aux_bf16 = sv.zd; ep.ld_out = 64; ep.act = act;
+      prof_set_tag(PC_GEMM_BOTTLENECK);
       TRY(gemm_tn(s, wk.dy_bf16, D, static_cast<const bf16*>(w->w_up_t), D, M, 64, D, EPI_DACT, ep));
     }
     // down projection: dW_down^T = a_n^T dzd, db_down = colsum(dzd), da_n = dzd W_down
@@ -337,6 +355,7 @@ int pevit_block_bwd(const pevit_block_desc* desc, const pevit_block_weights* w, 
     {
       GemmEpilogue ep;
       ep.out_f32 = wk.dxn; ep.ld_out = D;
+      prof_set_tag(PC_GEMM_BOTTLENECK);
       TRY(gemm_tn(s, wk.dzd, 64, static_cast<const bf16*>(w->w_down_t), 64, M, D, 64, EPI_F32, ep));
     }
     // adapter LayerNorm backward (+ the direct `+ m` path: dres = dy), with its affine grads
@@ -348,12 +367,14 @@ int pevit_block_bwd(const pevit_block_desc* desc, const pevit_block_weights* w, 
   {
     GemmEpilogue ep;
     ep.out_bf16 = wk.dz; ep.aux_bf16 = sv.z; ep.ld_out = 4 * D; ep.act = ACT_QUICKGELU;
+    prof_set_tag(PC_GEMM_DPROJ);
     TRY(gemm_tn(s, dmlp_bf16, D, static_cast<const bf16*>(w->w_proj_t), D, M, 4 * D, D, EPI_DACT, ep));
   }
   // c_fc dgrad -> d ln_2 output
   {
     GemmEpilogue ep;
     ep.out_f32 = wk.dxn; ep.ld_out = D;
+    prof_set_tag(PC_GEMM_DFC);
     TRY(gemm_tn(s, wk.dz, 4 * D, static_cast<const bf16*>(w->w_fc_t), 4 * D, M, D, 4 * D, EPI_F32, ep));
   }
   // ln_2 backward + residual path
@@ -362,6 +383,7 @@ int pevit_block_bwd(const pevit_block_desc* desc, const pevit_block_weights* w, 
   {
     GemmEpilogue ep;
     ep.out_bf16 = wk.do_tok; ep.ld_out = D;
+    prof_set_tag(PC_GEMM_DOUT);
     TRY(gemm_tn(s, wk.dx1_bf16, D, static_cast<const bf16*>(w->w_o_t), D, M, D, D, EPI_BF16, ep));
   }
   // attention backward
@@ -379,6 +401,7 @@ int pevit_block_bwd(const pevit_block_desc* desc, const pevit_block_weights* w, 
       // dT = alpha * dDelta * Q  -> bf16 straight into the extra K columns of the QKV dgrad operand
       GemmEpilogue ep;
       ep.out_bf16 = wk.dqkv + 3 * D + which * r; ep.ld_out = W3;
+      prof_set_tag(PC_GEMM_DT);
       TRY(gemm_tn(s, dd, D, qmat_t + static_cast<size_t>(which) * r * D, D, M, r, D, EPI_BF16, ep));
       // dQ = alpha * dDelta^T T
       if (g->d_qmat)
@@ -394,6 +417,7 @@ int pevit_block_bwd(const pevit_block_desc* desc, const pevit_block_weights* w, 
   {
     GemmEpilogue ep;
     ep.out_f32 = wk.dxn; ep.ld_out = D;
+    prof_set_tag(PC_GEMM_DQKV);
     TRY(gemm_tn(s, wk.dqkv, W3, static_cast<const bf16*>(w->w_qkv_ext_t), W3, M, D, W3, EPI_F32, ep));
   }
   // ln_1 backward + residual path

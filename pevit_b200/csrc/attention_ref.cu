@@ -154,23 +154,19 @@ attn_bwd_ref_kernel(AttnShape a, const bf16* __restrict__ q, const bf16* __restr
   }
   for (int i = threadIdx.x; i < L; i += AT_THREADS) sLse[i] = lse[(static_cast<size_t>(n) * H + h) * L + i];
   __syncthreads();
-  for (int i = warp; i < L; i += AT_WARPS) {
-    const bf16* orow = o_tok + (static_cast<size_t>(i) * NB + n) * D + h * 64;
-    float acc = __bfloat162float(orow[lane]) * __bfloat162float(sdO[i * KS + lane]) +
-                __bfloat162float(orow[lane + 32]) * __bfloat162float(sdO[i * KS + lane + 32]);
-    acc = warp_sum(acc);
-    if (lane == 0) sDel[i] = acc;
-  }
-  __syncthreads();
-
   float* myA = sA + warp * L;
   float* myB = sB + warp * L;
-  // ---- pass A: one warp per query row i -> dQ'[i]
+  // ---- pass A: one warp per query row i -> dQ'[i].  delta_i = sum_j P_ij dP_ij is taken from the
+  // very P and dP that form dS (identical to rowsum(dO * O) in exact arithmetic, but free of the
+  // bf16 rounding of O, so sum_j dS_ij stays ~0) and is kept in shared memory for pass B.
   for (int i = warp; i < L; i += AT_WARPS) {
-    const float lse_i = sLse[i], del_i = sDel[i];
+    const float lse_i = sLse[i];
+    float pv[MAXT], dpv[MAXT];
+    float del = 0.f;
 #pragma unroll
     for (int t = 0; t < MAXT; ++t) {
       const int j = lane + 32 * t;
+      pv[t] = 0.f; dpv[t] = 0.f;
       if (j < L) {
         float sc = 0.f, dp = 0.f;
         const __nv_bfloat162* kr = reinterpret_cast<const __nv_bfloat162*>(sK + j * KS);
@@ -184,9 +180,17 @@ attn_bwd_ref_kernel(AttnShape a, const bf16* __restrict__ q, const bf16* __restr
           dp = fmaf(dd.x, sV[j * QS + 2 * d], dp);
           dp = fmaf(dd.y, sV[j * QS + 2 * d + 1], dp);
         }
-        const float p = __expf(sc - lse_i);
-        myB[j] = p * (dp - del_i);
+        pv[t] = __expf(sc - lse_i);
+        dpv[t] = dp;
+        del = fmaf(pv[t], dp, del);
       }
+    }
+    del = warp_sum(del);
+    if (lane == 0) sDel[i] = del;
+#pragma unroll
+    for (int t = 0; t < MAXT; ++t) {
+      const int j = lane + 32 * t;
+      if (j < L) myB[j] = pv[t] * (dpv[t] - del);
     }
     __syncwarp();
     float g0 = 0.f, g1 = 0.f;
@@ -204,6 +208,7 @@ attn_bwd_ref_kernel(AttnShape a, const bf16* __restrict__ q, const bf16* __restr
     }
     __syncwarp();
   }
+  __syncthreads();  // sDel complete
   // ---- pass B: one warp per key row j -> dK[j], dV'[j]
   const size_t dv_plane = static_cast<size_t>(NB) * H * L * 64;
   for (int j = warp; j < L; j += AT_WARPS) {
@@ -264,6 +269,7 @@ int attn_delta_fwd_ref(cudaStream_t s, const AttnShape& a, const bf16* q, const 
   if (check_shape(a) != 0) return -1;
   const size_t smem = (2 * a.L * QS + AT_WARPS * a.L) * sizeof(float) + static_cast<size_t>(a.L) * KS * sizeof(bf16);
   PEVIT_CHECK_CUDA(cudaFuncSetAttribute(attn_fwd_ref_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  ProfScope prof(s, PC_ATTN_FWD);
   attn_fwd_ref_kernel<<<a.NB * a.H, AT_THREADS, smem, s>>>(a, q, k, v, T, Qmat, bias, o_tok, lse);
   PEVIT_CHECK_LAUNCH();
   return 0;
@@ -276,6 +282,7 @@ int attn_delta_bwd_ref(cudaStream_t s, const AttnShape& a, const bf16* q, const 
   const size_t smem = (2 * a.L * QS + 2 * AT_WARPS * a.L + 2 * a.L) * sizeof(float) +
                       2 * static_cast<size_t>(a.L) * KS * sizeof(bf16);
   PEVIT_CHECK_CUDA(cudaFuncSetAttribute(attn_bwd_ref_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  ProfScope prof(s, PC_ATTN_BWD);
   attn_bwd_ref_kernel<<<a.NB * a.H, AT_THREADS, smem, s>>>(a, q, k, v, T, Qmat, bias, o_tok, do_tok, lse, dqkv,
                                                             ld_dqkv, ddelta);
   PEVIT_CHECK_LAUNCH();

@@ -37,6 +37,28 @@ const char* last_error();
 
 int sm_count();
 
+// ---------------------------------------------------------------- host: launch accounting
+// Every kernel launcher opens a ProfScope: it counts the launch and, when profiling is enabled
+// (pevit_prof_enable), brackets it with CUDA events on the launching stream so bench.py can
+// attribute device time to kernel classes inside the timed region.
+enum ProfClass {
+  PC_GEMM_QKV = 0, PC_GEMM_OUT, PC_GEMM_FC, PC_GEMM_PROJ, PC_GEMM_DPROJ, PC_GEMM_DFC, PC_GEMM_DOUT, PC_GEMM_DQKV,
+  PC_GEMM_DT, PC_GEMM_BOTTLENECK, PC_GEMM_OTHER, PC_ATTN_FWD, PC_ATTN_BWD, PC_LN_FWD, PC_LN_BWD, PC_ATB, PC_COLSUM,
+  PC_EXPAND, PC_FACTOR_GRADS, PC_CAST, PC_COUNT
+};
+void prof_set_tag(int cls);  // class of the next launch on this thread (overrides the launcher's default)
+struct ProfScope {
+  cudaStream_t stream;
+  int slot;
+  ProfScope(cudaStream_t s, int default_cls);
+  ~ProfScope();
+};
+int prof_enable(int on);
+int prof_reset();
+int prof_read(double* ms, long long* launches, int n);
+long long launch_count();
+const char* prof_class_name(int cls);
+
 // 2-D bf16 row-major tensor map: dims (rows, cols), box (box_rows, box_cols), 128B swizzle.
 int make_tmap_bf16_2d(CUtensorMap* out, const void* base, uint64_t rows, uint64_t cols,
                       uint64_t row_stride_elems, uint32_t box_rows, uint32_t box_cols);

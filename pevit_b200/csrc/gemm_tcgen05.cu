@@ -318,6 +318,7 @@ int launch(cudaStream_t stream, const CUtensorMap& ta, const CUtensorMap& tb, in
   }
   const int tiles = ((M + BM - 1) / BM) * ((N + BN - 1) / BN);
   const int grid = tiles < sm_count() ? tiles : sm_count();
+  ProfScope prof(stream, PC_GEMM_OTHER);
   kern<<<grid, GEMM_THREADS, Cfg::SMEM_BYTES, stream>>>(ta, tb, M, N, K, ep);
   PEVIT_CHECK_LAUNCH();
   return 0;

@@ -2,8 +2,11 @@
 // queries, and TMA tensor-map creation.  cuTensorMapEncodeTiled is looked up through the
 // runtime (cudaGetDriverEntryPoint) so the library has no link-time dependency on libcuda
 // and can be loaded (symbols checked) on a machine without a GPU driver.
+#include <atomic>
 #include <cstdarg>
 #include <cstdio>
+#include <mutex>
+#include <vector>
 
 #include "common.cuh"
 
@@ -37,6 +40,79 @@ int sm_count() {
   }
   return cached[dev & 63];
 }
+
+// ------------------------------------------------------------------ launch accounting
+namespace {
+struct ProfEvent { cudaEvent_t start, stop; int cls; };
+std::vector<ProfEvent> g_events;   // recorded pairs since the last read
+std::vector<ProfEvent> g_pool;     // reusable pairs
+std::mutex g_prof_mu;
+bool g_prof_on = false;
+std::atomic<long long> g_launches{0};
+long long g_class_launches[PC_COUNT] = {};
+thread_local int g_tag = -1;
+const char* const kClassNames[PC_COUNT] = {
+    "gemm_qkv", "gemm_out", "gemm_fc", "gemm_proj", "gemm_dproj", "gemm_dfc", "gemm_dout", "gemm_dqkv", "gemm_dT",
+    "gemm_bottleneck", "gemm_other", "attn_fwd", "attn_bwd", "ln_fwd", "ln_bwd", "atb", "colsum", "expand",
+    "factor_grads", "cast"};
+}  // namespace
+
+void prof_set_tag(int cls) { g_tag = cls; }
+
+ProfScope::ProfScope(cudaStream_t s, int default_cls) : stream(s), slot(-1) {
+  const int cls = (g_tag >= 0 && g_tag < PC_COUNT) ? g_tag : default_cls;
+  g_tag = -1;
+  g_launches.fetch_add(1, std::memory_order_relaxed);
+  if (!g_prof_on) return;
+  std::lock_guard<std::mutex> lk(g_prof_mu);
+  ProfEvent ev;
+  if (!g_pool.empty()) {
+    ev = g_pool.back();
+    g_pool.pop_back();
+  } else if (cudaEventCreate(&ev.start) != cudaSuccess || cudaEventCreate(&ev.stop) != cudaSuccess) {
+    return;
+  }
+  ev.cls = cls;
+  cudaEventRecord(ev.start, s);
+  g_events.push_back(ev);
+  slot = static_cast<int>(g_events.size()) - 1;
+}
+
+ProfScope::~ProfScope() {
+  if (slot < 0) return;
+  std::lock_guard<std::mutex> lk(g_prof_mu);
+  if (slot < static_cast<int>(g_events.size())) cudaEventRecord(g_events[slot].stop, stream);
+}
+
+int prof_enable(int on) {
+  g_prof_on = on != 0;
+  return 0;
+}
+
+int prof_reset() {
+  std::lock_guard<std::mutex> lk(g_prof_mu);
+  for (auto& e : g_events) g_pool.push_back(e);
+  g_events.clear();
+  return 0;
+}
+
+// Accumulates elapsed ms and launch counts per class (waits for the recorded events), then recycles them.
+int prof_read(double* ms, long long* launches, int n) {
+  std::lock_guard<std::mutex> lk(g_prof_mu);
+  for (int i = 0; i < n; ++i) { ms[i] = 0.0; launches[i] = 0; }
+  for (auto& e : g_events) {
+    if (cudaEventSynchronize(e.stop) != cudaSuccess) { set_error("prof_read: event sync failed"); return -2; }
+    float t = 0.f;
+    if (cudaEventElapsedTime(&t, e.start, e.stop) != cudaSuccess) { set_error("prof_read: elapsed failed"); return -2; }
+    if (e.cls < n) { ms[e.cls] += t; launches[e.cls] += 1; }
+    g_pool.push_back(e);
+  }
+  g_events.clear();
+  return 0;
+}
+
+long long launch_count() { return g_launches.load(std::memory_order_relaxed); }
+const char* prof_class_name(int cls) { return (cls >= 0 && cls < PC_COUNT) ? kClassNames[cls] : "?"; }
 
 int make_tmap_bf16_2d(CUtensorMap* out, const void* base, uint64_t rows, uint64_t cols, uint64_t row_stride_elems,
                       uint32_t box_rows, uint32_t box_cols) {

@@ -138,6 +138,7 @@ int layernorm_fwd(cudaStream_t s, const float* x, const float* gamma, const floa
   PEVIT_REQUIRE(D % 128 == 0 && D <= 128 * MAXV, "layernorm: D=%d must be a multiple of 128 and <= %d", D, 128 * MAXV);
   PEVIT_REQUIRE(y_bf16 != nullptr || y_f32 != nullptr, "layernorm_fwd: no output");
   const int grid = (M + LN_THREADS / 32 - 1) / (LN_THREADS / 32);
+  ProfScope prof(s, PC_LN_FWD);
   if (y_bf16 && y_f32)
     ln_fwd_kernel<true, true><<<grid, LN_THREADS, 0, s>>>(x, gamma, beta, y_bf16, y_f32, mean, rstd, M, D);
   else if (y_bf16)
@@ -153,6 +154,7 @@ int layernorm_bwd(cudaStream_t s, const float* dyn, const float* x, const float*
                   int D) {
   PEVIT_REQUIRE(D % 128 == 0 && D <= 128 * MAXV, "layernorm: D=%d must be a multiple of 128 and <= %d", D, 128 * MAXV);
   const int rows_per_block = LN_THREADS / 32;
+  ProfScope prof(s, PC_LN_BWD);
   if (dgamma != nullptr) {
     PEVIT_REQUIRE(dbeta != nullptr, "layernorm_bwd: dgamma without dbeta");
     int grid = (M + rows_per_block - 1) / rows_per_block;

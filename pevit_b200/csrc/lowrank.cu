@@ -198,6 +198,7 @@ int grid_for(size_t n, int threads) {
 int kad_expand(cudaStream_t s, const float* u1, const float* v1, const float* u2, const float* v2, const float* sfac,
                const float* tfac, int D, float alpha, bf16* w_ext, bf16* w_ext_t, float* qmat, bf16* qmat_t) {
   PEVIT_REQUIRE(D % 32 == 0, "kad_expand: D=%d not divisible by phm_dim 32", D);
+  ProfScope prof(s, PC_EXPAND);
   kad_expand_kernel<<<grid_for(32 * static_cast<size_t>(D), 256), 256, 0, s>>>(u1, v1, u2, v2, sfac, tfac, D, alpha,
                                                                                w_ext, w_ext_t, qmat, qmat_t);
   PEVIT_CHECK_LAUNCH();
@@ -206,6 +207,7 @@ int kad_expand(cudaStream_t s, const float* u1, const float* v1, const float* u2
 
 int lora_expand(cudaStream_t s, const float* Aq, const float* Av, const float* Bq, const float* Bv, int D, int r,
                 float alpha, bf16* w_ext, bf16* w_ext_t, float* qmat, bf16* qmat_t) {
+  ProfScope prof(s, PC_EXPAND);
   lora_expand_kernel<<<grid_for(static_cast<size_t>(r) * D, 256), 256, 0, s>>>(Aq, Av, Bq, Bv, D, r, alpha, w_ext,
                                                                                w_ext_t, qmat, qmat_t);
   PEVIT_CHECK_LAUNCH();
@@ -221,6 +223,7 @@ int atb_accumulate(cudaStream_t s, const void* A, int a_is_bf16, int lda, const 
   rows_per_cta = ((rows_per_cta + ATB_TM - 1) / ATB_TM) * ATB_TM;
   splits = (M + rows_per_cta - 1) / rows_per_cta;
   dim3 grid(gx, splits);
+  ProfScope prof(s, PC_ATB);
   if (a_is_bf16 && b_is_bf16)
     atb_kernel<bf16, bf16><<<grid, ATB_THREADS, 0, s>>>((const bf16*)A, lda, (const bf16*)B, ldb, M, Kc, Nc, scale, C, rows_per_cta);
   else if (a_is_bf16)
@@ -238,6 +241,7 @@ int colsum_bf16(cudaStream_t s, const bf16* X, int ld, int M, int D, float* out)
   int splits = (sm_count() * 4 + gx - 1) / gx;
   const int rows_per_cta = (M + splits - 1) / splits;
   splits = (M + rows_per_cta - 1) / rows_per_cta;
+  ProfScope prof(s, PC_COLSUM);
   colsum_bf16_kernel<<<dim3(gx, splits), 256, 0, s>>>(X, ld, M, D, out, rows_per_cta);
   PEVIT_CHECK_LAUNCH();
   return 0;
@@ -246,18 +250,21 @@ int colsum_bf16(cudaStream_t s, const bf16* X, int ld, int M, int D, float* out)
 int kad_factor_grads(cudaStream_t s, const float* dP, const float* dQ, const float* u1, const float* v1, const float* u2,
                      const float* v2, const float* sfac, const float* tfac, int D, float* du1, float* dv1, float* du2,
                      float* dv2, float* dsfac, float* dtfac) {
+  ProfScope prof(s, PC_FACTOR_GRADS);
   kad_factor_grads_kernel<<<32, 64, 0, s>>>(dP, dQ, u1, v1, u2, v2, sfac, tfac, D, du1, dv1, du2, dv2, dsfac, dtfac);
   PEVIT_CHECK_LAUNCH();
   return 0;
 }
 
 int cast_f32_to_bf16_2d(cudaStream_t s, const float* src, int lds, bf16* dst, int ldd, int rows, int cols) {
+  ProfScope prof(s, PC_CAST);
   cast2d_kernel<<<grid_for(static_cast<size_t>(rows) * cols, 256), 256, 0, s>>>(src, lds, dst, ldd, rows, cols);
   PEVIT_CHECK_LAUNCH();
   return 0;
 }
 
 int cast_f32_to_bf16(cudaStream_t s, const float* src, bf16* dst, size_t n) {
+  ProfScope prof(s, PC_CAST);
   cast_kernel<<<grid_for(n, 256), 256, 0, s>>>(src, dst, n);
   PEVIT_CHECK_LAUNCH();
   return 0;
@@ -265,6 +272,7 @@ int cast_f32_to_bf16(cudaStream_t s, const float* src, bf16* dst, size_t n) {
 
 int transpose_f32_to_bf16(cudaStream_t s, const float* src, int rows, int cols, bf16* dst, int ldd) {
   dim3 grid((cols + 31) / 32, (rows + 31) / 32), block(32, 8);
+  ProfScope prof(s, PC_CAST);
   transpose_cast_kernel<<<grid, block, 0, s>>>(src, rows, cols, dst, ldd);
   PEVIT_CHECK_LAUNCH();
   return 0;

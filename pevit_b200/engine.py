@@ -1,0 +1,82 @@
+"""Fine-tune step driver: the reference's ``train_one`` inner loop (kadaptation_clip.py:347-353 --
+zero_grad, forward, CrossEntropyLoss, backward, SGD) on the fused blocks, plus the data-parallel
+exchange the reference lacks: one NCCL all-reduce per step over a single flat fp32
+buffer that holds every trainable gradient (adapters + linear head; frozen-backbone gradients are
+never allocated).
+"""
+from __future__ import annotations
+
+from typing import Optional
+
+import torch
+import torch.distributed as dist
+import torch.nn.functional as F
+from torch import nn
+
+from . import _clip, synth
+
+BUILD = {"kadaptation": _clip.KAD, "lora": _clip.LORA, "adapter": _clip.ADAPTER, "compacter": _clip.COMPACTER}
+
+
+def trainable_by_name(name: str, method: str) -> bool:
+    """Name-based un-freezing of the reference drivers (kadaptation_clip.py:104-122, compacter_clip.py:122-123)."""
+    if not name.startswith("visual."):
+        return False
+    if method == "compacter":
+        return "compacter" in name
+    return "adapter" in name or "phm_rule" in name or "attn.b" in name
+
+
+class FineTuner(nn.Module):
+    """Backbone (frozen CLIP visual tower + PEFT tensors) and a linear head, stepped with SGD(momentum)."""
+
+    def __init__(self, method: str, shape: synth.ClipShape, num_classes: int = 10, device="cuda", lr: float = 1e-3,
+                 momentum: float = 0.9, weight_decay: float = 0.0, seed: int = 0, randomize: bool = True,
+                 process_group: Optional[dist.ProcessGroup] = None, distributed: bool = False):
+        super().__init__()
+        self.method = method
+        sd = synth.clip_state_dict(shape, seed=seed)
+        self.backbone = _clip.build(dict(sd), BUILD[method])
+        if randomize:  # non-zero adapters: the shipped KAdaptation init is a zero-gradient saddle (F3)
+            synth.randomize_adapters(self.backbone.named_parameters(), seed=seed + 1)
+        for name, prm in self.backbone.named_parameters():
+            prm.requires_grad_(trainable_by_name(name, method))
+        g = torch.Generator().manual_seed(seed + 4)
+        self.head = nn.Linear(shape.embed_dim, num_classes)
+        with torch.no_grad():
+            self.head.weight.copy_(torch.randn(num_classes, shape.embed_dim, generator=g) * shape.embed_dim ** -0.5)
+            self.head.bias.zero_()
+        self.to(device)
+        self.backbone.eval()  # the reference never leaves eval mode on the PEFT path (F7)
+        self.distributed = distributed
+        self.group = process_group
+        self.world = dist.get_world_size(process_group) if distributed else 1
+        # flat gradient buffer; every trainable .grad is a view into it
+        self.params = [p for p in self.parameters() if p.requires_grad]
+        # F2: KAdaptation's v_proj_adapter1_* are trainable by name but never receive a gradient
+        self.used = [p for n, p in self.named_parameters()
+                     if p.requires_grad and not (method == "kadaptation" and "v_proj_adapter1_" in n)]
+        total = sum(p.numel() for p in self.used)
+        self.flat_grad = torch.zeros(total, dtype=torch.float32, device=device)
+        off = 0
+        for p in self.used:
+            p.grad = self.flat_grad[off:off + p.numel()].view_as(p)
+            off += p.numel()
+        self.opt = torch.optim.SGD(self.used, lr=lr, momentum=momentum, weight_decay=weight_decay)
+
+    def forward(self, images: torch.Tensor) -> torch.Tensor:
+        return self.head(self.backbone.encode_image(images).float())
+
+    def step(self, images: torch.Tensor, labels: torch.Tensor) -> torch.Tensor:
+        """One fine-tune step on this rank's local batch; returns the (device) loss."""
+        self.flat_grad.zero_()
+        loss = F.cross_entropy(self.forward(images), labels)
+        loss.backward()
+        if self.distributed and self.world > 1:
+            dist.all_reduce(self.flat_grad, group=self.group)
+            self.flat_grad.div_(self.world)
+        self.opt.step()
+        return loss.detach()
+
+    def trainable_numel(self) -> int:
+        return sum(p.numel() for p in self.params)

@@ -41,3 +41,35 @@ def rel_l2(a: torch.Tensor, b: torch.Tensor) -> float:
     den = b.norm().item()
     num = (a - b).norm().item()
     return num / den if den > 0 else num
+
+
+def bf16_floor_step(fix: dict, p: dict, method: str) -> dict:
+    """Error of the REFERENCE ALGORITHM ITSELF when run under bf16 autocast (oracle on CPU, fp32
+    parameters, torch.autocast(bfloat16)) against the fp32 reference fixture: the bf16 noise floor
+    of every tensor (SURVEY 7.6 / 8c "bf16 oracle").  Keys: 'logits', 'features', 'grad:<name>'."""
+    from oracle import pevit_oracle as O
+    with torch.autocast("cpu", dtype=torch.bfloat16):
+        logits, _, grads = O.train_step_grads(fix["images"], fix["labels"], p, fix["head.weight"], fix["head.bias"],
+                                              method)
+    out = {"logits": rel_inf(logits.float(), fix["logits"])}
+    for k, g_ref in fix.items():
+        if k.startswith("grad:") and grads.get(k[5:]) is not None and g_ref.abs().max() > 0:
+            out[k] = rel_inf(grads[k[5:]].float(), g_ref)
+    return out
+
+
+def bf16_floor_block(fix: dict, p: dict, x: torch.Tensor, wy: torch.Tensor, heads: int, method: str) -> dict:
+    """Same for one ResidualAttentionBlock (b32blk fixtures): keys 'grad:<name>' and 'dx'."""
+    from oracle import pevit_oracle as O
+    q = {k: v.detach().clone() for k, v in p.items()}
+    names = [k[5:] for k in fix if k.startswith("grad:")]
+    for n in names:
+        q[n].requires_grad_(True)
+    xx = x.detach().clone().requires_grad_(True)
+    with torch.autocast("cpu", dtype=torch.bfloat16):
+        y = O.residual_block(xx, q, "visual.transformer.resblocks.0.", heads, method)
+        (y.float() * wy).sum().backward()
+    out = {"dx": rel_inf(xx.grad[:, :, ::8], fix["dx_sub"]), "y": rel_inf(y.detach().float()[:, :, ::8], fix["y_sub"])}
+    for n in names:
+        out["grad:" + n] = rel_inf(q[n].grad.float(), fix["grad:" + n])
+    return out
