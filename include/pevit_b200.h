@@ -75,8 +75,9 @@ typedef struct pevit_gemm_args {
   void* out_bf16;                    /* EPI_BF16 / QGELU / DQGELU */
   void* out2_bf16;                   /* EPI_QGELU: z (nullable) */
   const void* aux_bf16;              /* EPI_DQGELU: z */
+  const void* resid_bf16;            /* EPI_BF16: bf16 [M][ld_out] added before rounding (may alias out) */
   int32_t ld_out;
-  void* qkv_hm; float* t_out;        /* EPI_QKV outputs */
+  void* qkv_hm; void* t_out;         /* EPI_QKV outputs: head-major q/8|k|v, bf16 T [M][r2] */
   int32_t L, NB, H, D, r2;           /* EPI_QKV shape */
   int32_t force_bn;                  /* 0 = heuristic, else 32/64/128/256 */
 } pevit_gemm_args;
@@ -93,7 +94,7 @@ int pevit_layernorm_bwd(const float* dyn, const float* x, const float* gamma, co
 typedef struct pevit_attn_args {
   int32_t L, NB, H, D, r; float alpha;
   const void *q, *k, *v;             /* bf16 head-major [NB*H][L][64], q pre-scaled */
-  const float* t;                    /* fp32 [L*NB][2r] or NULL */
+  const void* t;                     /* bf16 [L*NB][2r] or NULL (impl 1 only: in-kernel delta) */
   const float* qmat;                 /* fp32 [2][D][r] or NULL  */
   const float* delta_bias;           /* fp32 [D] or NULL (KAdaptation attn.b) */
   void* o_tok; float* lse;           /* fwd out: bf16 [L*NB][D], fp32 [NB*H][L] */
@@ -108,9 +109,9 @@ int pevit_attn_bwd(const pevit_attn_args* args, void* stream);
 /* Factor expansion (model.py:563-580 without materialising H; lora_model.py:490-514). */
 int pevit_kad_expand(const float* u1, const float* v1, const float* u2, const float* v2, const float* s,
                      const float* t, int32_t d, float alpha, void* w_ext, void* w_ext_t, float* qmat, void* qmat_t,
-                     void* stream);
+                     void* delta_w, void* stream);
 int pevit_lora_expand(const float* aq, const float* av, const float* bq, const float* bv, int32_t d, int32_t r,
-                      float alpha, void* w_ext, void* w_ext_t, float* qmat, void* qmat_t, void* stream);
+                      float alpha, void* w_ext, void* w_ext_t, float* qmat, void* qmat_t, void* delta_w, void* stream);
 /* C[kc][nc] += scale * A[M][kc]^T B[M][nc] (fp32 atomics; caller zeroes C). */
 int pevit_atb_accumulate(const void* a, int32_t a_is_bf16, int32_t lda, const void* b, int32_t b_is_bf16,
                          int32_t ldb, int32_t m, int32_t kc, int32_t nc, float scale, float* c, void* stream);
@@ -132,7 +133,7 @@ typedef struct pevit_block_desc {
   int32_t r;           /* 32 (KAdaptation), 4 (LoRA), 0 otherwise */
   float alpha;         /* 160 (KAdaptation), 32 (LoRA) */
   int32_t save;        /* 1: fill `saved` for a later pevit_block_bwd */
-  int32_t attn_impl;   /* 0 default, 1 CUDA-core cross-check */
+  int32_t attn_impl;   /* 0 default (delta GEMM + tcgen05 attention), 1 CUDA-core kernel with in-kernel delta */
   int32_t need_dx;     /* bwd: 0 skips the input gradient (first layer: nothing upstream trains) */
 } pevit_block_desc;
 
@@ -148,6 +149,7 @@ typedef struct pevit_block_weights {
   const float *ln1_g, *ln1_b, *ln2_g, *ln2_b;
   const float* qmat;       const void* qmat_t;       /* fp32 [2][D][r]; bf16 [2][r][D] * alpha */
   const float* delta_bias;                           /* KAdaptation attn.b or NULL */
+  const void* delta_w;                               /* bf16 [2][D][2r]: alpha*[Q_q|0], alpha*[0|Q_v] */
   /* bottleneck (Adapter / Compacter): dense down/up weights (Compacter: expanded from PHM factors) */
   const float *lna_g, *lna_b;                        /* adapter_norm_before */
   const void* w_down;      const void* w_down_t;     /* bf16 [64][D], [D][64] */

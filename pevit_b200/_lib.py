@@ -24,7 +24,7 @@ class GemmArgs(C.Structure):
         ("a", c_void_p), ("lda", c_int32), ("b", c_void_p), ("ldb", c_int32),
         ("m", c_int32), ("n", c_int32), ("k", c_int32), ("epilogue", c_int32),
         ("bias", c_void_p), ("resid", c_void_p), ("out_f32", c_void_p), ("out_bf16", c_void_p),
-        ("out2_bf16", c_void_p), ("aux_bf16", c_void_p), ("ld_out", c_int32),
+        ("out2_bf16", c_void_p), ("aux_bf16", c_void_p), ("resid_bf16", c_void_p), ("ld_out", c_int32),
         ("qkv_hm", c_void_p), ("t_out", c_void_p),
         ("L", c_int32), ("NB", c_int32), ("H", c_int32), ("D", c_int32), ("r2", c_int32),
         ("force_bn", c_int32),
@@ -49,7 +49,7 @@ class BlockDesc(C.Structure):
 
 _W_FIELDS = [
     "w_qkv_ext", "w_qkv_ext_t", "b_qkv", "w_o", "w_o_t", "b_o", "w_fc", "w_fc_t", "b_fc",
-    "w_proj", "w_proj_t", "b_proj", "ln1_g", "ln1_b", "ln2_g", "ln2_b", "qmat", "qmat_t", "delta_bias",
+    "w_proj", "w_proj_t", "b_proj", "ln1_g", "ln1_b", "ln2_g", "ln2_b", "qmat", "qmat_t", "delta_bias", "delta_w",
     "lna_g", "lna_b", "w_down", "w_down_t", "b_down", "w_up", "w_up_t", "b_up",
 ]
 _G_FIELDS = ["d_pmat", "d_qmat", "d_bias", "d_lna_g", "d_lna_b", "d_w_down", "d_b_down", "d_w_up", "d_b_up"]
@@ -79,8 +79,8 @@ _SIGNATURES = {
     "pevit_layernorm_bwd": (c_int32, [c_void_p] * 10 + [c_int32, c_int32, c_void_p]),
     "pevit_attn_fwd": (c_int32, [_P(AttnArgs), c_void_p]),
     "pevit_attn_bwd": (c_int32, [_P(AttnArgs), c_void_p]),
-    "pevit_kad_expand": (c_int32, [c_void_p] * 6 + [c_int32, c_float] + [c_void_p] * 5),
-    "pevit_lora_expand": (c_int32, [c_void_p] * 4 + [c_int32, c_int32, c_float] + [c_void_p] * 5),
+    "pevit_kad_expand": (c_int32, [c_void_p] * 6 + [c_int32, c_float] + [c_void_p] * 6),
+    "pevit_lora_expand": (c_int32, [c_void_p] * 4 + [c_int32, c_int32, c_float] + [c_void_p] * 6),
     "pevit_atb_accumulate": (c_int32, [c_void_p, c_int32, c_int32, c_void_p, c_int32, c_int32, c_int32, c_int32,
                                        c_int32, c_float, c_void_p, c_void_p]),
     "pevit_colsum_bf16": (c_int32, [c_void_p, c_int32, c_int32, c_void_p, c_void_p]),

@@ -25,7 +25,7 @@ struct Carver {
 };
 
 struct Saved {
-  bf16* xn1; float *mean1, *rstd1; bf16* qkv_hm; float* T; bf16* o_tok; float* lse;
+  bf16* xn1; float *mean1, *rstd1; bf16* qkv_hm; bf16* T; bf16* o_tok; float* lse;
   float* x1; float *mean2, *rstd2; bf16* z;
   // bottleneck
   float* m; float *mean_a, *rstd_a; bf16* a_n; bf16* zd; bf16* u;
@@ -51,7 +51,7 @@ Saved carve_saved(const pevit_block_desc& d, void* p) {
   s.xn1 = c.take<bf16>(M * D);
   s.mean1 = c.take<float>(M); s.rstd1 = c.take<float>(M);
   s.qkv_hm = c.take<bf16>(3 * M * D);
-  s.T = c.take<float>(M * 2 * (d.r > 0 ? d.r : 1));
+  s.T = c.take<bf16>(M * 2 * (d.r > 0 ? d.r : 4));
   s.o_tok = c.take<bf16>(M * D);
   s.lse = c.take<float>(M * d.H);
   s.x1 = c.take<float>(M * D);
@@ -109,13 +109,13 @@ int check_desc(const pevit_block_desc* d) {
 }
 
 int attn_fwd_dispatch(cudaStream_t s, const AttnShape& a, int impl, const bf16* q, const bf16* k, const bf16* v,
-                      const float* T, const float* qmat, const float* bias, bf16* o_tok, float* lse) {
-  (void)impl;
+                      const bf16* T, const float* qmat, const float* bias, bf16* o_tok, float* lse) {
+  if (impl == 0 && attn_tc_supported(a)) return attn_fwd_tc(s, a, q, k, v, o_tok, lse);
   return attn_delta_fwd_ref(s, a, q, k, v, T, qmat, bias, o_tok, lse);
 }
 
 int attn_bwd_dispatch(cudaStream_t s, const AttnShape& a, int impl, const bf16* q, const bf16* k, const bf16* v,
-                      const float* T, const float* qmat, const float* bias, const bf16* o_tok, const bf16* do_tok,
+                      const bf16* T, const float* qmat, const float* bias, const bf16* o_tok, const bf16* do_tok,
                       const float* lse, bf16* dqkv, int ld, bf16* ddelta) {
   (void)impl;
   return attn_delta_bwd_ref(s, a, q, k, v, T, qmat, bias, o_tok, do_tok, lse, dqkv, ld, ddelta);
@@ -150,7 +150,8 @@ int pevit_gemm_tn(const pevit_gemm_args* a, void* stream) {
   ep.bias = a->bias; ep.resid = a->resid; ep.out_f32 = a->out_f32;
   ep.out_bf16 = static_cast<bf16*>(a->out_bf16); ep.out2_bf16 = static_cast<bf16*>(a->out2_bf16);
   ep.aux_bf16 = static_cast<const bf16*>(a->aux_bf16); ep.ld_out = a->ld_out;
-  ep.qkv_hm = static_cast<bf16*>(a->qkv_hm); ep.t_out = a->t_out;
+  ep.qkv_hm = static_cast<bf16*>(a->qkv_hm); ep.t_out = static_cast<bf16*>(a->t_out);
+  ep.resid_bf16 = static_cast<const bf16*>(a->resid_bf16);
   ep.L = a->L; ep.NB = a->NB; ep.H = a->H; ep.D = a->D; ep.r2 = a->r2;
   int epi = a->epilogue;
   // the public enum folds the activation kind into the epilogue id
@@ -176,29 +177,32 @@ int pevit_attn_fwd(const pevit_attn_args* a, void* stream) {
   PEVIT_REQUIRE(a != nullptr, "null attention args");
   AttnShape sh{a->L, a->NB, a->H, a->D, a->r, a->alpha};
   return attn_fwd_dispatch(as_stream(stream), sh, a->impl, static_cast<const bf16*>(a->q),
-                           static_cast<const bf16*>(a->k), static_cast<const bf16*>(a->v), a->t, a->qmat,
-                           a->delta_bias, static_cast<bf16*>(a->o_tok), a->lse);
+                           static_cast<const bf16*>(a->k), static_cast<const bf16*>(a->v),
+                           static_cast<const bf16*>(a->t), a->qmat, a->delta_bias, static_cast<bf16*>(a->o_tok), a->lse);
 }
 
 int pevit_attn_bwd(const pevit_attn_args* a, void* stream) {
   PEVIT_REQUIRE(a != nullptr, "null attention args");
   AttnShape sh{a->L, a->NB, a->H, a->D, a->r, a->alpha};
   return attn_bwd_dispatch(as_stream(stream), sh, a->impl, static_cast<const bf16*>(a->q),
-                           static_cast<const bf16*>(a->k), static_cast<const bf16*>(a->v), a->t, a->qmat,
-                           a->delta_bias, static_cast<const bf16*>(a->o_tok), static_cast<const bf16*>(a->do_tok),
+                           static_cast<const bf16*>(a->k), static_cast<const bf16*>(a->v),
+                           static_cast<const bf16*>(a->t), a->qmat, a->delta_bias,
+                           static_cast<const bf16*>(a->o_tok), static_cast<const bf16*>(a->do_tok),
                            a->lse, static_cast<bf16*>(a->dqkv), a->ld_dqkv, static_cast<bf16*>(a->ddelta));
 }
 
 int pevit_kad_expand(const float* u1, const float* v1, const float* u2, const float* v2, const float* s, const float* t,
-                     int32_t d, float alpha, void* w_ext, void* w_ext_t, float* qmat, void* qmat_t, void* stream) {
+                     int32_t d, float alpha, void* w_ext, void* w_ext_t, float* qmat, void* qmat_t, void* delta_w,
+                     void* stream) {
   return kad_expand(as_stream(stream), u1, v1, u2, v2, s, t, d, alpha, static_cast<bf16*>(w_ext),
-                    static_cast<bf16*>(w_ext_t), qmat, static_cast<bf16*>(qmat_t));
+                    static_cast<bf16*>(w_ext_t), qmat, static_cast<bf16*>(qmat_t), static_cast<bf16*>(delta_w));
 }
 
 int pevit_lora_expand(const float* aq, const float* av, const float* bq, const float* bv, int32_t d, int32_t r,
-                      float alpha, void* w_ext, void* w_ext_t, float* qmat, void* qmat_t, void* stream) {
+                      float alpha, void* w_ext, void* w_ext_t, float* qmat, void* qmat_t, void* delta_w,
+                      void* stream) {
   return lora_expand(as_stream(stream), aq, av, bq, bv, d, r, alpha, static_cast<bf16*>(w_ext),
-                     static_cast<bf16*>(w_ext_t), qmat, static_cast<bf16*>(qmat_t));
+                     static_cast<bf16*>(w_ext_t), qmat, static_cast<bf16*>(qmat_t), static_cast<bf16*>(delta_w));
 }
 
 int pevit_atb_accumulate(const void* a, int32_t a_is_bf16, int32_t lda, const void* b, int32_t b_is_bf16, int32_t ldb,
@@ -268,12 +272,26 @@ int pevit_block_fwd(const pevit_block_desc* desc, const pevit_block_weights* w, 
     prof_set_tag(PC_GEMM_QKV);
     TRY(gemm_tn(s, sv.xn1, D, static_cast<const bf16*>(w->w_qkv_ext), D, M, W3, D, EPI_QKV, ep));
   }
-  // attention core with in-kernel delta
+  const bool fused_delta = has_lowrank(d) && d.attn_impl == 1;  // cross-check kernel expands the delta itself
+  if (has_lowrank(d) && !fused_delta) {
+    // q' = q + scr(alpha T_q Q_q^T + b), v' = v + scr(alpha T_v Q_v^T + b): F4 makes scr() the identity on the
+    // flat head-major buffer viewed as [M][D], so the delta is a rank-2r GEMM accumulated in place (model.py:796-799)
+    const bf16* dw = static_cast<const bf16*>(w->delta_w);
+    for (int which = 0; which < 2; ++which) {
+      bf16* dst = sv.qkv_hm + (which == 0 ? 0 : 2) * plane;
+      GemmEpilogue ep;
+      ep.bias = d.method == PEVIT_KADAPTATION ? w->delta_bias : nullptr;
+      ep.out_bf16 = dst; ep.resid_bf16 = dst; ep.ld_out = D;
+      prof_set_tag(PC_GEMM_DELTA);
+      TRY(gemm_tn(s, sv.T, r2, dw + static_cast<size_t>(which) * D * r2, r2, M, D, r2, EPI_BF16, ep));
+    }
+  }
+  // attention core
   {
-    AttnShape a{d.L, d.NB, d.H, D, d.r, d.alpha};
+    AttnShape a{d.L, d.NB, d.H, D, fused_delta ? d.r : 0, d.alpha};
     TRY(attn_fwd_dispatch(s, a, d.attn_impl, sv.qkv_hm, sv.qkv_hm + plane, sv.qkv_hm + 2 * plane,
-                          has_lowrank(d) ? sv.T : nullptr, has_lowrank(d) ? w->qmat : nullptr,
-                          d.method == PEVIT_KADAPTATION ? w->delta_bias : nullptr, sv.o_tok, sv.lse));
+                          fused_delta ? sv.T : nullptr, fused_delta ? w->qmat : nullptr,
+                          fused_delta && d.method == PEVIT_KADAPTATION ? w->delta_bias : nullptr, sv.o_tok, sv.lse));
   }
   // out-projection + residual
   {
@@ -388,11 +406,12 @@ int pevit_block_bwd(const pevit_block_desc* desc, const pevit_block_weights* w, 
   }
   // attention backward
   {
-    AttnShape a{d.L, d.NB, d.H, D, r, d.alpha};
+    const bool fused_delta = has_lowrank(d) && d.attn_impl == 1;
+    AttnShape a{d.L, d.NB, d.H, D, fused_delta ? r : 0, d.alpha};
     TRY(attn_bwd_dispatch(s, a, d.attn_impl, sv.qkv_hm, sv.qkv_hm + plane, sv.qkv_hm + 2 * plane,
-                          has_lowrank(d) ? sv.T : nullptr, has_lowrank(d) ? w->qmat : nullptr,
-                          d.method == PEVIT_KADAPTATION ? w->delta_bias : nullptr, sv.o_tok, wk.do_tok, sv.lse, wk.dqkv,
-                          W3, has_lowrank(d) ? wk.ddelta : nullptr));
+                          fused_delta ? sv.T : nullptr, fused_delta ? w->qmat : nullptr,
+                          fused_delta && d.method == PEVIT_KADAPTATION ? w->delta_bias : nullptr, sv.o_tok, wk.do_tok,
+                          sv.lse, wk.dqkv, W3, has_lowrank(d) ? wk.ddelta : nullptr));
   }
   if (has_lowrank(d)) {
     const bf16* qmat_t = static_cast<const bf16*>(w->qmat_t);
@@ -405,7 +424,7 @@ int pevit_block_bwd(const pevit_block_desc* desc, const pevit_block_weights* w, 
       TRY(gemm_tn(s, dd, D, qmat_t + static_cast<size_t>(which) * r * D, D, M, r, D, EPI_BF16, ep));
       // dQ = alpha * dDelta^T T
       if (g->d_qmat)
-        TRY(atb_accumulate(s, dd, 1, D, sv.T + which * r, 0, r2, M, D, r, d.alpha,
+        TRY(atb_accumulate(s, dd, 1, D, sv.T + which * r, 1, r2, M, D, r, d.alpha,
                            g->d_qmat + static_cast<size_t>(which) * D * r));
       if (d.method == PEVIT_KADAPTATION && g->d_bias) TRY(colsum_bf16(s, dd, D, M, D, g->d_bias));
     }

@@ -27,16 +27,16 @@ __device__ __forceinline__ void delta_rowcol(int n, int h, int l, int L, int H, 
   colblk = j % H;
 }
 
-__device__ __forceinline__ float delta_elem(const float* __restrict__ Trow, const float* __restrict__ Qrow, int r,
+__device__ __forceinline__ float delta_elem(const bf16* __restrict__ Trow, const float* __restrict__ Qrow, int r,
                                             float alpha) {
   float acc = 0.f;
-  for (int i = 0; i < r; ++i) acc = fmaf(__ldg(Trow + i), __ldg(Qrow + i), acc);
+  for (int i = 0; i < r; ++i) acc = fmaf(__bfloat162float(Trow[i]), __ldg(Qrow + i), acc);
   return alpha * acc;
 }
 
 // Loads q', k, v' of one (n, h) into shared memory.  sQ/sV fp32 [L][QS]; sK bf16 [L][KS].
 __device__ void load_head(const AttnShape& a, int n, int h, const bf16* __restrict__ q, const bf16* __restrict__ k,
-                          const bf16* __restrict__ v, const float* __restrict__ T, const float* __restrict__ Qmat,
+                          const bf16* __restrict__ v, const bf16* __restrict__ T, const float* __restrict__ Qmat,
                           const float* __restrict__ bias, float* sQ, bf16* sK, float* sV) {
   const int L = a.L, H = a.H, D = a.D, r = a.r;
   const size_t head_off = (static_cast<size_t>(n) * H + h) * L * 64;
@@ -51,7 +51,7 @@ __device__ void load_head(const AttnShape& a, int n, int h, const bf16* __restri
       const int col = cb * 64 + d;
       float dq = 0.f, dv = 0.f;
       if (r > 0) {
-        const float* Trow = T + static_cast<size_t>(row) * 2 * r;
+        const bf16* Trow = T + static_cast<size_t>(row) * 2 * r;
         dq = delta_elem(Trow, Qmat + static_cast<size_t>(col) * r, r, a.alpha);
         dv = delta_elem(Trow + r, Qmat + (static_cast<size_t>(D) + col) * r, r, a.alpha);
       }
@@ -66,7 +66,7 @@ __device__ void load_head(const AttnShape& a, int n, int h, const bf16* __restri
 
 __global__ void __launch_bounds__(AT_THREADS)
 attn_fwd_ref_kernel(AttnShape a, const bf16* __restrict__ q, const bf16* __restrict__ k, const bf16* __restrict__ v,
-                    const float* __restrict__ T, const float* __restrict__ Qmat, const float* __restrict__ bias,
+                    const bf16* __restrict__ T, const float* __restrict__ Qmat, const float* __restrict__ bias,
                     bf16* __restrict__ o_tok, float* __restrict__ lse) {
   extern __shared__ __align__(16) uint8_t smem[];
   const int L = a.L, H = a.H;
@@ -130,7 +130,7 @@ attn_fwd_ref_kernel(AttnShape a, const bf16* __restrict__ q, const bf16* __restr
 
 __global__ void __launch_bounds__(AT_THREADS)
 attn_bwd_ref_kernel(AttnShape a, const bf16* __restrict__ q, const bf16* __restrict__ k, const bf16* __restrict__ v,
-                    const float* __restrict__ T, const float* __restrict__ Qmat, const float* __restrict__ bias,
+                    const bf16* __restrict__ T, const float* __restrict__ Qmat, const float* __restrict__ bias,
                     const bf16* __restrict__ o_tok, const bf16* __restrict__ do_tok, const float* __restrict__ lse,
                     bf16* __restrict__ dqkv, int ld, bf16* __restrict__ ddelta) {
   extern __shared__ __align__(16) uint8_t smem[];
@@ -264,7 +264,7 @@ int check_shape(const AttnShape& a) {
 
 }  // namespace
 
-int attn_delta_fwd_ref(cudaStream_t s, const AttnShape& a, const bf16* q, const bf16* k, const bf16* v, const float* T,
+int attn_delta_fwd_ref(cudaStream_t s, const AttnShape& a, const bf16* q, const bf16* k, const bf16* v, const bf16* T,
                        const float* Qmat, const float* bias, bf16* o_tok, float* lse) {
   if (check_shape(a) != 0) return -1;
   const size_t smem = (2 * a.L * QS + AT_WARPS * a.L) * sizeof(float) + static_cast<size_t>(a.L) * KS * sizeof(bf16);
@@ -275,7 +275,7 @@ int attn_delta_fwd_ref(cudaStream_t s, const AttnShape& a, const bf16* q, const 
   return 0;
 }
 
-int attn_delta_bwd_ref(cudaStream_t s, const AttnShape& a, const bf16* q, const bf16* k, const bf16* v, const float* T,
+int attn_delta_bwd_ref(cudaStream_t s, const AttnShape& a, const bf16* q, const bf16* k, const bf16* v, const bf16* T,
                        const float* Qmat, const float* bias, const bf16* o_tok, const bf16* do_tok, const float* lse,
                        bf16* dqkv, int ld_dqkv, bf16* ddelta) {
   if (check_shape(a) != 0) return -1;

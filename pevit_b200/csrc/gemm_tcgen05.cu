@@ -98,6 +98,23 @@ __device__ __forceinline__ void epilogue_chunk(const GemmEpilogue& ep, int m, in
     }
   } else if constexpr (EPI == EPI_BF16) {
     const size_t off = static_cast<size_t>(m) * ep.ld_out + c0;
+    if (ep.resid_bf16 != nullptr) {  // in-place low-rank delta: q' = q + (alpha T Q^T + b)
+      if (full) {
+#pragma unroll
+        for (int j = 0; j < 32; j += 8) {
+          const uint4 rr = *reinterpret_cast<const uint4*>(ep.resid_bf16 + off + j);
+          const uint32_t rw[4] = {rr.x, rr.y, rr.z, rr.w};
+#pragma unroll
+          for (int t = 0; t < 4; ++t) {
+            const float2 f = unpack_bf16(rw[t]);
+            a[j + 2 * t] += f.x;
+            a[j + 2 * t + 1] += f.y;
+          }
+        }
+      } else {
+        _Pragma("unroll") for (int j = 0; j < 32; ++j) if (c0 + j < N) a[j] += __bfloat162float(ep.resid_bf16[off + j]);
+      }
+    }
     if (full) {
 #pragma unroll
       for (int j = 0; j < 32; j += 8) {
@@ -173,8 +190,8 @@ __device__ __forceinline__ void epilogue_chunk(const GemmEpilogue& ep, int m, in
                        pack_bf16(a[j + 4] * sc, a[j + 5] * sc), pack_bf16(a[j + 6] * sc, a[j + 7] * sc));
     } else {
       const int t0 = c0 - threeD;
-      float* dst = ep.t_out + static_cast<size_t>(m) * ep.r2 + t0;
-      _Pragma("unroll") for (int j = 0; j < 32; ++j) if (t0 + j < ep.r2) dst[j] = a[j];
+      bf16* dst = ep.t_out + static_cast<size_t>(m) * ep.r2 + t0;
+      _Pragma("unroll") for (int j = 0; j < 32; ++j) if (t0 + j < ep.r2) dst[j] = __float2bfloat16(a[j]);
     }
   }
 }

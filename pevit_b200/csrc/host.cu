@@ -53,7 +53,7 @@ long long g_class_launches[PC_COUNT] = {};
 thread_local int g_tag = -1;
 const char* const kClassNames[PC_COUNT] = {
     "gemm_qkv", "gemm_out", "gemm_fc", "gemm_proj", "gemm_dproj", "gemm_dfc", "gemm_dout", "gemm_dqkv", "gemm_dT",
-    "gemm_bottleneck", "gemm_other", "attn_fwd", "attn_bwd", "ln_fwd", "ln_bwd", "atb", "colsum", "expand",
+    "gemm_delta", "gemm_bottleneck", "gemm_other", "attn_fwd", "attn_bwd", "ln_fwd", "ln_bwd", "atb", "colsum", "expand",
     "factor_grads", "cast"};
 }  // namespace
 

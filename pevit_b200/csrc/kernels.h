@@ -17,11 +17,12 @@ struct GemmEpilogue {
   bf16* out_bf16 = nullptr;        // EPI_BF16 / EPI_ACT (act(z)) / EPI_DACT (dz)
   bf16* out2_bf16 = nullptr;       // EPI_ACT: pre-activation z (nullable)
   const bf16* aux_bf16 = nullptr;  // EPI_DACT: saved pre-activation z
+  const bf16* resid_bf16 = nullptr;  // EPI_BF16: bf16 [M][ld_out] added before rounding (may alias out_bf16)
   int act = ACT_QUICKGELU;         // EPI_ACT / EPI_DACT
   int ld_out = 0;                  // row stride (elements) of out / resid / aux
   // EPI_QKV
   bf16* qkv_hm = nullptr;          // [3][NB*H][L][64] head-major q (pre-scaled 1/8), k, v
-  float* t_out = nullptr;          // [M][r2] low-rank activations
+  bf16* t_out = nullptr;           // [M][r2] low-rank activations T = X P (bf16: A operand of the delta GEMM)
   int L = 0, NB = 0, H = 0, D = 0, r2 = 0;
 };
 
@@ -43,16 +44,22 @@ struct AttnShape {
   int L, NB, H, D, r;  // r = low-rank width per projection (32 KAdaptation, 4 LoRA, 0 none)
   float alpha;         // 160 / 32
 };
-// q,k,v: head-major bf16 [NB*H][L][64] (q pre-scaled).  T: fp32 [L*NB][2r] (LND rows).
+// q,k,v: head-major bf16 [NB*H][L][64] (q pre-scaled).  T: bf16 [L*NB][2r] (LND rows).
 // Qmat: fp32 [2][D][r] (q then v factor), bias: fp32 [D] or null.
 // out: o_tok bf16 [L*NB][D] (token rows, LND), lse fp32 [NB*H][L].
-int attn_delta_fwd_ref(cudaStream_t s, const AttnShape& a, const bf16* q, const bf16* k, const bf16* v, const float* T,
+int attn_delta_fwd_ref(cudaStream_t s, const AttnShape& a, const bf16* q, const bf16* k, const bf16* v, const bf16* T,
                        const float* Qmat, const float* bias, bf16* o_tok, float* lse);
 // in: do_tok bf16 [L*NB][D].  out: dqkv bf16 [L*NB][ld] token rows, cols [0,D)=dq/8,[D,2D)=dk,[2D,3D)=dv;
 // ddelta bf16 [2][NB*H][L][64] = dQ' and dV' head-major (== d(delta) viewed as [L*NB][D], F4).
-int attn_delta_bwd_ref(cudaStream_t s, const AttnShape& a, const bf16* q, const bf16* k, const bf16* v, const float* T,
+int attn_delta_bwd_ref(cudaStream_t s, const AttnShape& a, const bf16* q, const bf16* k, const bf16* v, const bf16* T,
                        const float* Qmat, const float* bias, const bf16* o_tok, const bf16* do_tok, const float* lse,
                        bf16* dqkv, int ld_dqkv, bf16* ddelta);
+
+// ------------------------------------------------------------------ attention_tc.cu (tcgen05 / TMEM)
+// q', k, v' head-major bf16 with the low-rank delta already applied (a.r must be 0); L <= 128.
+bool attn_tc_supported(const AttnShape& a);
+int attn_fwd_tc(cudaStream_t s, const AttnShape& a, const bf16* q, const bf16* k, const bf16* v, bf16* o_tok,
+                float* lse);
 
 // ------------------------------------------------------------------ lowrank.cu
 // KAdaptation factor expansion: from u1,u2 (rule*_left [32][32]), v1,v2 (rule*_right),
@@ -60,11 +67,13 @@ int attn_delta_bwd_ref(cudaStream_t s, const AttnShape& a, const bf16* q, const 
 //   w_ext rows [3D,3D+64)  : P_q^T | P_v^T  (bf16, K-major rows of length D)   -- forward B operand
 //   w_ext_t cols [3D,3D+64): P_q | P_v      (bf16, [D][3D+64])                 -- dgrad B operand
 //   qmat  fp32 [2][D][32], qmat_t bf16 [2][32][D] (B operand of dT = alpha * dDelta * Q)
+//   delta_w bf16 [2][D][64]: alpha*[Q_q | 0] and alpha*[0 | Q_v], B operands of delta = T * delta_w^T (K = 2r)
 int kad_expand(cudaStream_t s, const float* u1, const float* v1, const float* u2, const float* v2, const float* sfac,
-               const float* tfac, int D, float alpha, bf16* w_ext, bf16* w_ext_t, float* qmat, bf16* qmat_t);
+               const float* tfac, int D, float alpha, bf16* w_ext, bf16* w_ext_t, float* qmat, bf16* qmat_t,
+               bf16* delta_w);
 // LoRA: A_q, A_v [r][D]; B_q, B_v [D][r].
 int lora_expand(cudaStream_t s, const float* Aq, const float* Av, const float* Bq, const float* Bv, int D, int r,
-                float alpha, bf16* w_ext, bf16* w_ext_t, float* qmat, bf16* qmat_t);
+                float alpha, bf16* w_ext, bf16* w_ext_t, float* qmat, bf16* qmat_t, bf16* delta_w);
 // C[Kc][Nc] (fp32, += with atomics; caller zeroes) = scale * A[M][Kc]^T * B[M][Nc]; A bf16 or fp32, B fp32 or bf16.
 int atb_accumulate(cudaStream_t s, const void* A, int a_is_bf16, int lda, const void* B, int b_is_bf16, int ldb, int M,
                    int Kc, int Nc, float scale, float* C);

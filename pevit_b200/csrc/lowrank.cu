@@ -17,7 +17,7 @@ __global__ void kad_expand_kernel(const float* __restrict__ u1, const float* __r
                                   const float* __restrict__ u2, const float* __restrict__ v2,
                                   const float* __restrict__ sf, const float* __restrict__ tf, int D, float alpha,
                                   bf16* __restrict__ w_ext, bf16* __restrict__ w_ext_t, float* __restrict__ qmat,
-                                  bf16* __restrict__ qmat_t) {
+                                  bf16* __restrict__ qmat_t, bf16* __restrict__ delta_w) {
   const int F = D / 32;
   const int ld_t = 3 * D + 64;
   const int total = 32 * D;  // (i, a, k)
@@ -35,13 +35,18 @@ __global__ void kad_expand_kernel(const float* __restrict__ u1, const float* __r
     qmat[static_cast<size_t>(D + col) * 32 + i] = qv;
     qmat_t[static_cast<size_t>(i) * D + col] = __float2bfloat16(alpha * qq);
     qmat_t[static_cast<size_t>(32 + i) * D + col] = __float2bfloat16(alpha * qv);
+    // delta_w[which][col][64]: q uses the T_q half of K, v the T_v half (the other half multiplies zeros)
+    delta_w[static_cast<size_t>(col) * 64 + i] = __float2bfloat16(alpha * qq);
+    delta_w[static_cast<size_t>(col) * 64 + 32 + i] = __float2bfloat16(0.f);
+    delta_w[static_cast<size_t>(D + col) * 64 + i] = __float2bfloat16(0.f);
+    delta_w[static_cast<size_t>(D + col) * 64 + 32 + i] = __float2bfloat16(alpha * qv);
   }
 }
 
 __global__ void lora_expand_kernel(const float* __restrict__ Aq, const float* __restrict__ Av,
                                    const float* __restrict__ Bq, const float* __restrict__ Bv, int D, int r,
                                    float alpha, bf16* __restrict__ w_ext, bf16* __restrict__ w_ext_t,
-                                   float* __restrict__ qmat, bf16* __restrict__ qmat_t) {
+                                   float* __restrict__ qmat, bf16* __restrict__ qmat_t, bf16* __restrict__ delta_w) {
   const int ld_t = 3 * D + 2 * r;
   const int total = r * D;
   for (int idx = blockIdx.x * blockDim.x + threadIdx.x; idx < total; idx += gridDim.x * blockDim.x) {
@@ -56,6 +61,10 @@ __global__ void lora_expand_kernel(const float* __restrict__ Aq, const float* __
     qmat[static_cast<size_t>(D + col) * r + i] = qv;
     qmat_t[static_cast<size_t>(i) * D + col] = __float2bfloat16(alpha * qq);
     qmat_t[static_cast<size_t>(r + i) * D + col] = __float2bfloat16(alpha * qv);
+    delta_w[static_cast<size_t>(col) * 2 * r + i] = __float2bfloat16(alpha * qq);
+    delta_w[static_cast<size_t>(col) * 2 * r + r + i] = __float2bfloat16(0.f);
+    delta_w[static_cast<size_t>(D + col) * 2 * r + i] = __float2bfloat16(0.f);
+    delta_w[static_cast<size_t>(D + col) * 2 * r + r + i] = __float2bfloat16(alpha * qv);
   }
 }
 
@@ -196,20 +205,21 @@ int grid_for(size_t n, int threads) {
 }  // namespace
 
 int kad_expand(cudaStream_t s, const float* u1, const float* v1, const float* u2, const float* v2, const float* sfac,
-               const float* tfac, int D, float alpha, bf16* w_ext, bf16* w_ext_t, float* qmat, bf16* qmat_t) {
+               const float* tfac, int D, float alpha, bf16* w_ext, bf16* w_ext_t, float* qmat, bf16* qmat_t,
+               bf16* delta_w) {
   PEVIT_REQUIRE(D % 32 == 0, "kad_expand: D=%d not divisible by phm_dim 32", D);
   ProfScope prof(s, PC_EXPAND);
   kad_expand_kernel<<<grid_for(32 * static_cast<size_t>(D), 256), 256, 0, s>>>(u1, v1, u2, v2, sfac, tfac, D, alpha,
-                                                                               w_ext, w_ext_t, qmat, qmat_t);
+                                                                               w_ext, w_ext_t, qmat, qmat_t, delta_w);
   PEVIT_CHECK_LAUNCH();
   return 0;
 }
 
 int lora_expand(cudaStream_t s, const float* Aq, const float* Av, const float* Bq, const float* Bv, int D, int r,
-                float alpha, bf16* w_ext, bf16* w_ext_t, float* qmat, bf16* qmat_t) {
+                float alpha, bf16* w_ext, bf16* w_ext_t, float* qmat, bf16* qmat_t, bf16* delta_w) {
   ProfScope prof(s, PC_EXPAND);
   lora_expand_kernel<<<grid_for(static_cast<size_t>(r) * D, 256), 256, 0, s>>>(Aq, Av, Bq, Bv, D, r, alpha, w_ext,
-                                                                               w_ext_t, qmat, qmat_t);
+                                                                               w_ext_t, qmat, qmat_t, delta_w);
   PEVIT_CHECK_LAUNCH();
   return 0;
 }

@@ -84,8 +84,9 @@ class BlockPack:
         if self.r:
             self.qmat = torch.zeros(2, D, self.r, dtype=torch.float32, device=dev)
             self.qmat_t = torch.zeros(2, self.r, D, **bf)
+            self.delta_w = torch.zeros(2, D, 2 * self.r, **bf)
         else:
-            self.qmat = self.qmat_t = None
+            self.qmat = self.qmat_t = self.delta_w = None
         if method in ("adapter", "compacter"):
             self.w_down, self.w_down_t = torch.empty(BOTTLENECK, D, **bf), torch.empty(D, BOTTLENECK, **bf)
             self.w_up, self.w_up_t = torch.empty(D, BOTTLENECK, **bf), torch.empty(BOTTLENECK, D, **bf)
@@ -120,6 +121,7 @@ class BlockPack:
         w.w_proj, w.w_proj_t, w.b_proj = _ptr(self.w_proj), _ptr(self.w_proj_t), _ptr(s[3])
         w.ln1_g, w.ln1_b, w.ln2_g, w.ln2_b = (_ptr(t) for t in s[4:8])
         w.qmat, w.qmat_t, w.delta_bias = _ptr(self.qmat), _ptr(self.qmat_t), _ptr(delta_bias)
+        w.delta_w = _ptr(self.delta_w)
         if lna is not None:
             w.lna_g, w.lna_b = _ptr(lna[0]), _ptr(lna[1])
             w.w_down, w.w_down_t, w.b_down = _ptr(self.w_down), _ptr(self.w_down_t), _ptr(b_down)
@@ -151,13 +153,13 @@ class _BlockFn(torch.autograd.Function):
             u1, v1, u2, v2, s, t, b = peft_c
             L.check(lib.pevit_kad_expand(_ptr(u1), _ptr(v1), _ptr(u2), _ptr(v2), _ptr(s), _ptr(t), D, pack.alpha,
                                          _ptr(pack.w_qkv_ext), _ptr(pack.w_qkv_ext_t), _ptr(pack.qmat),
-                                         _ptr(pack.qmat_t), st), "pevit_kad_expand")
+                                         _ptr(pack.qmat_t), _ptr(pack.delta_w), st), "pevit_kad_expand")
             delta_bias = b
         elif method == "lora":
             aq, bq, av, bv = peft_c
             L.check(lib.pevit_lora_expand(_ptr(aq), _ptr(av), _ptr(bq), _ptr(bv), D, pack.r, pack.alpha,
                                           _ptr(pack.w_qkv_ext), _ptr(pack.w_qkv_ext_t), _ptr(pack.qmat),
-                                          _ptr(pack.qmat_t), st), "pevit_lora_expand")
+                                          _ptr(pack.qmat_t), _ptr(pack.delta_w), st), "pevit_lora_expand")
         elif method in ("adapter", "compacter"):
             g, bta, w_down, b_down, w_up, b_up = peft_c   # w_down [64][D], w_up [D][64] dense
             lna = (g, bta)
