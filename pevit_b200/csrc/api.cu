@@ -117,7 +117,7 @@ int attn_fwd_dispatch(cudaStream_t s, const AttnShape& a, int impl, const bf16* 
 int attn_bwd_dispatch(cudaStream_t s, const AttnShape& a, int impl, const bf16* q, const bf16* k, const bf16* v,
                       const bf16* T, const float* qmat, const float* bias, const bf16* o_tok, const bf16* do_tok,
                       const float* lse, bf16* dqkv, int ld, bf16* ddelta) {
-  (void)impl;
+  if (impl == 0 && attn_tc_supported(a)) return attn_bwd_tc(s, a, q, k, v, do_tok, lse, dqkv, ld, ddelta);
   return attn_delta_bwd_ref(s, a, q, k, v, T, qmat, bias, o_tok, do_tok, lse, dqkv, ld, ddelta);
 }
 

@@ -62,6 +62,10 @@ const char* prof_class_name(int cls);
 // 2-D bf16 row-major tensor map: dims (rows, cols), box (box_rows, box_cols), 128B swizzle.
 int make_tmap_bf16_2d(CUtensorMap* out, const void* base, uint64_t rows, uint64_t cols,
                       uint64_t row_stride_elems, uint32_t box_rows, uint32_t box_cols);
+// Token-major [L][NB][H][64] bf16 activations viewed per head: dims (64, H, NB, L), box (64, 1, 1, box_l):
+// one TMA brings the L rows of one (image, head) into a [box_l][64] 128B-swizzled tile.
+int make_tmap_bf16_tok_heads(CUtensorMap* out, const void* base, int L, int NB, int H, uint64_t row_stride_elems,
+                             uint32_t box_l);
 
 #ifdef __CUDACC__
 // ---------------------------------------------------------------- device: misc
@@ -150,6 +154,16 @@ __device__ __forceinline__ void tma_load_2d(void* smem_dst, const CUtensorMap* m
       " [%0], [%1, {%3, %4}], [%2];"
       ::"r"(smem_u32(smem_dst)), "l"(reinterpret_cast<uint64_t>(m)), "r"(smem_u32(bar)),
       "r"(c0), "r"(c1)
+      : "memory");
+}
+
+__device__ __forceinline__ void tma_load_4d(void* smem_dst, const CUtensorMap* m, uint64_t* bar, int32_t c0,
+                                            int32_t c1, int32_t c2, int32_t c3) {
+  asm volatile(
+      "cp.async.bulk.tensor.4d.shared::cluster.global.mbarrier::complete_tx::bytes"
+      " [%0], [%1, {%3, %4, %5, %6}], [%2];"
+      ::"r"(smem_u32(smem_dst)), "l"(reinterpret_cast<uint64_t>(m)), "r"(smem_u32(bar)),
+      "r"(c0), "r"(c1), "r"(c2), "r"(c3)
       : "memory");
 }
 

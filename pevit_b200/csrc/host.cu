@@ -142,4 +142,23 @@ int make_tmap_bf16_2d(CUtensorMap* out, const void* base, uint64_t rows, uint64_
   return 0;
 }
 
+int make_tmap_bf16_tok_heads(CUtensorMap* out, const void* base, int L, int NB, int H, uint64_t row_stride_elems,
+                             uint32_t box_l) {
+  CUtensorMap dummy;
+  if (g_encode == nullptr && make_tmap_bf16_2d(&dummy, base, 8, 64, 64, 8, 64) != 0) return -2;  // resolves g_encode
+  const cuuint64_t gdim[4] = {64, static_cast<cuuint64_t>(H), static_cast<cuuint64_t>(NB), static_cast<cuuint64_t>(L)};
+  const cuuint64_t gstride[3] = {128, row_stride_elems * 2, static_cast<cuuint64_t>(NB) * row_stride_elems * 2};
+  const cuuint32_t box[4] = {64, 1, 1, box_l};
+  const cuuint32_t estride[4] = {1, 1, 1, 1};
+  CUresult r = g_encode(out, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, const_cast<void*>(base), gdim, gstride, box, estride,
+                        CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                        CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) {
+    set_error("cuTensorMapEncodeTiled(4d) failed (%d): base=%p L=%d NB=%d H=%d stride=%llu", (int)r, base, L, NB, H,
+              (unsigned long long)row_stride_elems);
+    return -2;
+  }
+  return 0;
+}
+
 }  // namespace pevit

@@ -60,6 +60,8 @@ int attn_delta_bwd_ref(cudaStream_t s, const AttnShape& a, const bf16* q, const 
 bool attn_tc_supported(const AttnShape& a);
 int attn_fwd_tc(cudaStream_t s, const AttnShape& a, const bf16* q, const bf16* k, const bf16* v, bf16* o_tok,
                 float* lse);
+int attn_bwd_tc(cudaStream_t s, const AttnShape& a, const bf16* q, const bf16* k, const bf16* v, const bf16* do_tok,
+                const float* lse, bf16* dqkv, int ld_dqkv, bf16* ddelta);
 
 // ------------------------------------------------------------------ lowrank.cu
 // KAdaptation factor expansion: from u1,u2 (rule*_left [32][32]), v1,v2 (rule*_right),
