@@ -115,6 +115,10 @@ int pevit_lora_expand(const float* aq, const float* av, const float* bq, const f
 /* C[kc][nc] += scale * A[M][kc]^T B[M][nc] (fp32 atomics; caller zeroes C). */
 int pevit_atb_accumulate(const void* a, int32_t a_is_bf16, int32_t lda, const void* b, int32_t b_is_bf16,
                          int32_t ldb, int32_t m, int32_t kc, int32_t nc, float scale, float* c, void* stream);
+/* Same product on tcgen05 (bf16 operands, rows split across CTAs, fp32 red.add): b exposes nb_cols (<= 64)
+ * columns, columns [n_lo, n_lo+n_cnt) of A^T B are accumulated into c[kc][0..n_cnt) (row stride ldc). */
+int pevit_atb_tc(const void* a, int32_t lda, const void* b, int32_t ldb, int32_t nb_cols, int32_t m, int32_t kc,
+                 int32_t n_lo, int32_t n_cnt, float scale, float* c, int32_t ldc, void* stream);
 int pevit_colsum_bf16(const void* x, int32_t m, int32_t d, float* out, void* stream);
 int pevit_kad_factor_grads(const float* dP, const float* dQ, const float* u1, const float* v1, const float* u2,
                            const float* v2, const float* s, const float* t, int32_t d, float* du1, float* dv1,

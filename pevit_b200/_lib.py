@@ -83,6 +83,8 @@ _SIGNATURES = {
     "pevit_lora_expand": (c_int32, [c_void_p] * 4 + [c_int32, c_int32, c_float] + [c_void_p] * 6),
     "pevit_atb_accumulate": (c_int32, [c_void_p, c_int32, c_int32, c_void_p, c_int32, c_int32, c_int32, c_int32,
                                        c_int32, c_float, c_void_p, c_void_p]),
+    "pevit_atb_tc": (c_int32, [c_void_p, c_int32, c_void_p, c_int32, c_int32, c_int32, c_int32, c_int32, c_int32,
+                               c_float, c_void_p, c_int32, c_void_p]),
     "pevit_colsum_bf16": (c_int32, [c_void_p, c_int32, c_int32, c_void_p, c_void_p]),
     "pevit_kad_factor_grads": (c_int32, [c_void_p] * 8 + [c_int32] + [c_void_p] * 7),
     "pevit_cast_bf16": (c_int32, [c_void_p, c_void_p, c_size_t, c_void_p]),

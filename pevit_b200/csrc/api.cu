@@ -210,6 +210,12 @@ int pevit_atb_accumulate(const void* a, int32_t a_is_bf16, int32_t lda, const vo
   return atb_accumulate(as_stream(stream), a, a_is_bf16, lda, b, b_is_bf16, ldb, m, kc, nc, scale, c);
 }
 
+int pevit_atb_tc(const void* a, int32_t lda, const void* b, int32_t ldb, int32_t nb_cols, int32_t m, int32_t kc,
+                 int32_t n_lo, int32_t n_cnt, float scale, float* c, int32_t ldc, void* stream) {
+  return atb_tc(as_stream(stream), static_cast<const bf16*>(a), lda, static_cast<const bf16*>(b), ldb, nb_cols, m, kc,
+                n_lo, n_cnt, scale, c, ldc);
+}
+
 int pevit_colsum_bf16(const void* x, int32_t m, int32_t d, float* out, void* stream) {
   return colsum_bf16(as_stream(stream), static_cast<const bf16*>(x), d, m, d, out);
 }
@@ -359,7 +365,7 @@ int pevit_block_bwd(const pevit_block_desc* desc, const pevit_block_weights* w, 
   if (has_bottleneck(d)) {
     const int act = d.method == PEVIT_ADAPTER ? ACT_RELU : ACT_GELU_NEW;
     // up projection: dW_up = dy^T u, db_up = colsum(dy), du = dy W_up, dzd = du * act'(zd)
-    if (g->d_w_up) TRY(atb_accumulate(s, wk.dy_bf16, 1, D, sv.u, 1, 64, M, D, 64, 1.f, g->d_w_up));
+    if (g->d_w_up) TRY(atb_tc(s, wk.dy_bf16, D, sv.u, 64, 64, M, D, 0, 64, 1.f, g->d_w_up, 64));
     if (g->d_b_up) TRY(colsum_bf16(s, wk.dy_bf16, D, M, D, g->d_b_up));
     {
       GemmEpilogue ep;
@@ -368,7 +374,7 @@ int pevit_block_bwd(const pevit_block_desc* desc, const pevit_block_weights* w, 
       TRY(gemm_tn(s, wk.dy_bf16, D, static_cast<const bf16*>(w->w_up_t), D, M, 64, D, EPI_DACT, ep));
     }
     // down projection: dW_down^T = a_n^T dzd, db_down = colsum(dzd), da_n = dzd W_down
-    if (g->d_w_down) TRY(atb_accumulate(s, sv.a_n, 1, D, wk.dzd, 1, 64, M, D, 64, 1.f, g->d_w_down));
+    if (g->d_w_down) TRY(atb_tc(s, sv.a_n, D, wk.dzd, 64, 64, M, D, 0, 64, 1.f, g->d_w_down, 64));
     if (g->d_b_down) TRY(colsum_bf16(s, wk.dzd, 64, M, 64, g->d_b_down));
     {
       GemmEpilogue ep;
@@ -424,12 +430,11 @@ int pevit_block_bwd(const pevit_block_desc* desc, const pevit_block_weights* w, 
       TRY(gemm_tn(s, dd, D, qmat_t + static_cast<size_t>(which) * r * D, D, M, r, D, EPI_BF16, ep));
       // dQ = alpha * dDelta^T T
       if (g->d_qmat)
-        TRY(atb_accumulate(s, dd, 1, D, sv.T + which * r, 1, r2, M, D, r, d.alpha,
-                           g->d_qmat + static_cast<size_t>(which) * D * r));
+        TRY(atb_tc(s, dd, D, sv.T, r2, r2, M, D, which * r, r, d.alpha, g->d_qmat + static_cast<size_t>(which) * D * r, r));
       if (d.method == PEVIT_KADAPTATION && g->d_bias) TRY(colsum_bf16(s, dd, D, M, D, g->d_bias));
     }
     // dP = X^T dT  ([D][2r], q | v)
-    if (g->d_pmat) TRY(atb_accumulate(s, sv.xn1, 1, D, wk.dqkv + 3 * D, 1, W3, M, D, r2, 1.f, g->d_pmat));
+    if (g->d_pmat) TRY(atb_tc(s, sv.xn1, D, wk.dqkv + 3 * D, W3, r2, M, D, 0, r2, 1.f, g->d_pmat, r2));
   }
   if (!d.need_dx) return 0;  // first layer: nothing upstream of this block trains
   // in-projection dgrad (K = 3D + 2r: the low-rank columns ride along)

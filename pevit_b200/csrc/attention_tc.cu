@@ -23,20 +23,6 @@ constexpr int FWD_SMEM = TC_STAGES * STAGE_BYTES + 2 * P_BYTES + 256 + 1024;
 constexpr int FWD_THREADS = 320;  // 8 softmax warps, 1 TMA warp, 1 MMA warp
 constexpr float LOG2E = 1.4426950408889634f;
 
-// MN-major operand tile: rows are K (keys / query rows), each row holds 64 contiguous MN elements
-// (128 B), 128B-swizzled -- byte-identical to a K-major [rows][64] tile, only the roles differ.
-// SBO = 1024 B between 8-row K groups; LBO = distance between 64-wide MN blocks.
-__device__ __forceinline__ uint64_t umma_desc_mnmajor_sw128(uint32_t smem_addr, uint32_t lbo_bytes) {
-  uint64_t d = 0;
-  d |= static_cast<uint64_t>((smem_addr & 0x3FFFF) >> 4);
-  d |= static_cast<uint64_t>((lbo_bytes >> 4) & 0x3FFF) << 16;
-  d |= static_cast<uint64_t>(1024 >> 4) << 32;
-  d |= static_cast<uint64_t>(1) << 46;
-  d |= static_cast<uint64_t>(2) << 61;
-  return d;
-}
-constexpr uint32_t IDESC_A_MN = 1u << 15, IDESC_B_MN = 1u << 16;
-
 __device__ __forceinline__ float fast_exp2(float x) {
   float y;
   asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));

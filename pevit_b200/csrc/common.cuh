@@ -62,6 +62,9 @@ const char* prof_class_name(int cls);
 // 2-D bf16 row-major tensor map: dims (rows, cols), box (box_rows, box_cols), 128B swizzle.
 int make_tmap_bf16_2d(CUtensorMap* out, const void* base, uint64_t rows, uint64_t cols,
                       uint64_t row_stride_elems, uint32_t box_rows, uint32_t box_cols);
+// 2-D output tensor map for TMA stores (bf16: elem_bytes 2, fp32: 4); box rows x (128 / elem_bytes) columns.
+int make_tmap_out_2d(CUtensorMap* out, const void* base, uint64_t rows, uint64_t cols, uint64_t row_stride_elems,
+                     uint32_t box_rows, int elem_bytes);
 // Token-major [L][NB][H][64] bf16 activations viewed per head: dims (64, H, NB, L), box (64, 1, 1, box_l):
 // one TMA brings the L rows of one (image, head) into a [box_l][64] 128B-swizzled tile.
 int make_tmap_bf16_tok_heads(CUtensorMap* out, const void* base, int L, int NB, int H, uint64_t row_stride_elems,
@@ -157,6 +160,25 @@ __device__ __forceinline__ void tma_load_2d(void* smem_dst, const CUtensorMap* m
       : "memory");
 }
 
+// smem tile -> global (clipped to the tensor bounds); completion tracked per bulk group of the issuing thread
+__device__ __forceinline__ void tma_store_2d(const CUtensorMap* m, const void* smem_src, int32_t c0, int32_t c1) {
+  asm volatile("cp.async.bulk.tensor.2d.global.shared::cta.bulk_group [%0, {%2, %3}], [%1];"
+               ::"l"(reinterpret_cast<uint64_t>(m)), "r"(smem_u32(smem_src)), "r"(c0), "r"(c1)
+               : "memory");
+}
+__device__ __forceinline__ void tma_store_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
+template <int N>
+__device__ __forceinline__ void tma_store_wait_read() {
+  asm volatile("cp.async.bulk.wait_group.read %0;" ::"n"(N) : "memory");
+}
+template <int N>
+__device__ __forceinline__ void tma_store_wait_all() {
+  asm volatile("cp.async.bulk.wait_group %0;" ::"n"(N) : "memory");
+}
+__device__ __forceinline__ void named_bar_sync(int id, int nthreads) {
+  asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(nthreads) : "memory");
+}
+
 __device__ __forceinline__ void tma_load_4d(void* smem_dst, const CUtensorMap* m, uint64_t* bar, int32_t c0,
                                             int32_t c1, int32_t c2, int32_t c3) {
   asm volatile(
@@ -233,6 +255,20 @@ __device__ __forceinline__ uint64_t umma_desc_kmajor_sw128(uint32_t smem_addr) {
   d |= static_cast<uint64_t>(2) << 61;                     // SWIZZLE_128B
   return d;
 }
+// MN-major operand tile: rows are K (keys / query rows), each row holds 64 contiguous MN elements
+// (128 B), 128B-swizzled -- byte-identical to a K-major [rows][64] tile, only the roles differ.
+// SBO = 1024 B between 8-row K groups; LBO = distance between 64-wide MN blocks.
+__device__ __forceinline__ uint64_t umma_desc_mnmajor_sw128(uint32_t smem_addr, uint32_t lbo_bytes) {
+  uint64_t d = 0;
+  d |= static_cast<uint64_t>((smem_addr & 0x3FFFF) >> 4);
+  d |= static_cast<uint64_t>((lbo_bytes >> 4) & 0x3FFF) << 16;
+  d |= static_cast<uint64_t>(1024 >> 4) << 32;
+  d |= static_cast<uint64_t>(1) << 46;
+  d |= static_cast<uint64_t>(2) << 61;
+  return d;
+}
+constexpr uint32_t IDESC_A_MN = 1u << 15, IDESC_B_MN = 1u << 16;
+
 // Instruction descriptor for kind::f16, A/B = bf16 K-major, D = fp32, shape M x N.
 __host__ __device__ constexpr uint32_t umma_idesc_bf16(int M, int N) {
   return (1u << 4) | (1u << 7) | (1u << 10) | (static_cast<uint32_t>(N >> 3) << 17) |

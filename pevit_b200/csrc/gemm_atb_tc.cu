@@ -1,0 +1,148 @@
+// C[kc][n] += scale * sum_m A[m][kc] * B[m][n]  -- the "weight-gradient shaped" products of the PEFT
+// tensors (dP = X^T dT, dQ = alpha dDelta^T T, dW_up = dY^T u, dW_down^T = a_n^T dzd): the contraction
+// runs over the L*N token rows, the outputs are tiny (D x <=64).  tcgen05 with BOTH operands MN-major
+// (row-major [m][..] tiles as TMA delivers them, no transposes), split over the token rows across
+// CTAs, fp32 partials reduced with red.global.add.  Replaces the autograd MulBackward/SumBackward over
+// the reference's materialised Kronecker einsum (evaluation/model.py:406-417).
+#include "common.cuh"
+#include "kernels.h"
+
+namespace pevit {
+namespace {
+
+constexpr int ATB_BK = 64;                       // token rows per pipeline stage
+constexpr int ATB_STAGES = 4;
+constexpr int ATB_BLK = 64 * 128;                // one [64 rows][64 cols] bf16 block
+constexpr int ATB_STAGE_BYTES = 3 * ATB_BLK;     // A: two 64-wide kc blocks, B: one 64-wide n block
+constexpr int ATB_SMEM = ATB_STAGES * ATB_STAGE_BYTES + 128 + 1024;
+constexpr int ATB_THREADS = 192;
+
+struct AtbParams {
+  int M, Kc, n_lo, n_cnt, ldc, rows_per_split;
+  float scale;
+  float* C;
+};
+
+__global__ void __launch_bounds__(ATB_THREADS)
+atb_tc_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant__ CUtensorMap tm_b, AtbParams p) {
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  uint64_t* full = reinterpret_cast<uint64_t*>(smem + ATB_STAGES * ATB_STAGE_BYTES);
+  uint64_t* empty = full + ATB_STAGES;
+  uint64_t* done = empty + ATB_STAGES;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(done + 1);
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int kc0 = blockIdx.x * 128;
+  const int m_begin = blockIdx.y * p.rows_per_split;
+  const int m_end = min(p.M, m_begin + p.rows_per_split);
+  const int num_kb = (m_end - m_begin + ATB_BK - 1) / ATB_BK;
+
+  if (warp == 0 && lane == 0) {
+    tma_prefetch_desc(&tm_a); tma_prefetch_desc(&tm_b);
+    for (int s = 0; s < ATB_STAGES; ++s) { mbar_init(&full[s], 1); mbar_init(&empty[s], 1); }
+    mbar_init(done, 1);
+    fence_mbar_init();
+  }
+  if (warp == 1) {
+    tmem_alloc(tmem_slot, 64);
+    tmem_relinquish();
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  if (warp == 0) {
+    if (lane == 0) {
+      for (int kb = 0; kb < num_kb; ++kb) {
+        const int s = kb % ATB_STAGES;
+        mbar_wait(&empty[s], ((kb / ATB_STAGES) & 1) ^ 1);
+        uint8_t* st = smem + s * ATB_STAGE_BYTES;
+        const int m0 = m_begin + kb * ATB_BK;
+        mbar_expect_tx(&full[s], ATB_STAGE_BYTES);
+        tma_load_2d(st, &tm_a, &full[s], kc0, m0);
+        tma_load_2d(st + ATB_BLK, &tm_a, &full[s], kc0 + 64, m0);
+        tma_load_2d(st + 2 * ATB_BLK, &tm_b, &full[s], 0, m0);
+      }
+    }
+  } else if (warp == 1) {
+    constexpr uint32_t idesc = umma_idesc_bf16(128, 64) | IDESC_A_MN | IDESC_B_MN;
+    for (int kb = 0; kb < num_kb; ++kb) {
+      const int s = kb % ATB_STAGES;
+      mbar_wait(&full[s], (kb / ATB_STAGES) & 1);
+      tc_fence_after();
+      if (lane == 0) {
+        const uint32_t st = smem_u32(smem + s * ATB_STAGE_BYTES);
+#pragma unroll
+        for (int k = 0; k < ATB_BK / 16; ++k)
+          umma_bf16_ss(tmem_base, umma_desc_mnmajor_sw128(st + k * 2048, ATB_BLK),
+                       umma_desc_mnmajor_sw128(st + 2 * ATB_BLK + k * 2048, ATB_BLK), idesc, (kb | k) != 0);
+        umma_commit(&empty[s]);
+        if (kb == num_kb - 1) umma_commit(done);
+      }
+      __syncwarp();
+    }
+  } else {
+    const int quad = warp & 3;
+    const int kc = kc0 + quad * 32 + lane;
+    if (num_kb > 0) {
+      mbar_wait(done, 0);
+      tc_fence_after();
+#pragma unroll
+      for (int c = 0; c < 64; c += 32) {
+        uint32_t v[32];
+        tmem_ld_32x32(tmem_base + (static_cast<uint32_t>(quad * 32) << 16) + c, v);
+        tmem_ld_wait();
+        if (kc < p.Kc) {
+          float* crow = p.C + static_cast<size_t>(kc) * p.ldc;
+#pragma unroll
+          for (int j = 0; j < 32; ++j) {
+            const int n = c + j - p.n_lo;
+            if (n >= 0 && n < p.n_cnt) atomicAdd(crow + n, p.scale * __uint_as_float(v[j]));
+          }
+        }
+      }
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    tc_fence_after();
+    tmem_dealloc(tmem_base, 64);
+  }
+}
+
+}  // namespace
+
+// A: bf16 [M][lda] (uses Kc columns).  B: bf16 [M][ldb] with nb_cols (<= 64) columns visible; columns
+// [n_lo, n_lo + n_cnt) of the product are accumulated into C[kc][0 .. n_cnt) (row stride ldc).
+int atb_tc(cudaStream_t s, const bf16* A, int lda, const bf16* B, int ldb, int nb_cols, int M, int Kc, int n_lo,
+           int n_cnt, float scale, float* C, int ldc) {
+  PEVIT_REQUIRE(nb_cols >= 1 && nb_cols <= 64 && n_lo >= 0 && n_lo + n_cnt <= nb_cols,
+                "atb_tc: column window [%d,%d) outside the %d visible columns", n_lo, n_lo + n_cnt, nb_cols);
+  PEVIT_REQUIRE(lda % 8 == 0 && ldb % 8 == 0 && (reinterpret_cast<uintptr_t>(A) & 15) == 0 &&
+                    (reinterpret_cast<uintptr_t>(B) & 15) == 0,
+                "atb_tc: operands need 16-byte aligned rows (lda=%d ldb=%d)", lda, ldb);
+  CUtensorMap ta, tb;
+  if (make_tmap_bf16_2d(&ta, A, M, Kc, lda, ATB_BK, 64) != 0) return -1;
+  if (make_tmap_bf16_2d(&tb, B, M, nb_cols, ldb, ATB_BK, 64) != 0) return -1;
+  const int gx = (Kc + 127) / 128;
+  int splits = (2 * sm_count() + gx - 1) / gx;
+  int rps = (M + splits - 1) / splits;
+  rps = ((rps + ATB_BK - 1) / ATB_BK) * ATB_BK;
+  splits = (M + rps - 1) / rps;
+  AtbParams p{M, Kc, n_lo, n_cnt, ldc, rps, scale, C};
+  static bool configured[64] = {};
+  int dev = 0;
+  PEVIT_CHECK_CUDA(cudaGetDevice(&dev));
+  if (!configured[dev & 63]) {
+    PEVIT_CHECK_CUDA(cudaFuncSetAttribute(atb_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, ATB_SMEM));
+    configured[dev & 63] = true;
+  }
+  ProfScope prof(s, PC_ATB);
+  atb_tc_kernel<<<dim3(gx, splits), ATB_THREADS, ATB_SMEM, s>>>(ta, tb, p);
+  PEVIT_CHECK_LAUNCH();
+  return 0;
+}
+
+}  // namespace pevit

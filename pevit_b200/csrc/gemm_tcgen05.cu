@@ -26,7 +26,8 @@ struct TileCfg {
   static constexpr int B_BYTES = BN * BK * 2;
   static constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
   static constexpr int TMEM_COLS = 2 * BN < 32 ? 32 : 2 * BN;  // two accumulator stages
-  static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + 256 + 1024;  // + barriers + align slack
+  static constexpr int STAGING_BYTES = 2 * 16384;  // two [128 rows][128 B] TMA-store boxes
+  static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + STAGING_BYTES + 256 + 1024;  // + barriers + align slack
 };
 
 __device__ __forceinline__ float sigmoidf_fast(float x) { return 1.f / (1.f + __expf(-x)); }
@@ -196,15 +197,95 @@ __device__ __forceinline__ void epilogue_chunk(const GemmEpilogue& ep, int m, in
   }
 }
 
-template <int BN, int EPI>
+// Staged epilogue: final values of one 32-column chunk (second output z for EPI_ACT).  Requires N % 32 == 0.
+template <int EPI>
+__device__ __forceinline__ void epilogue_values(const GemmEpilogue& ep, int m, int c0, bool row_ok, uint32_t (&v)[32],
+                                                float (&a)[32], float (&z)[32]) {
+#pragma unroll
+  for (int j = 0; j < 32; ++j) a[j] = __uint_as_float(v[j]);
+  if (ep.bias != nullptr) {
+#pragma unroll
+    for (int j = 0; j < 32; j += 4) {
+      const float4 b = __ldg(reinterpret_cast<const float4*>(ep.bias + c0 + j));
+      a[j] += b.x; a[j + 1] += b.y; a[j + 2] += b.z; a[j + 3] += b.w;
+    }
+  }
+  const size_t off = static_cast<size_t>(m) * ep.ld_out + c0;
+  if constexpr (EPI == EPI_F32) {
+    if (row_ok && ep.resid != nullptr) {
+#pragma unroll
+      for (int j = 0; j < 32; j += 4) {
+        const float4 r = *reinterpret_cast<const float4*>(ep.resid + off + j);
+        a[j] += r.x; a[j + 1] += r.y; a[j + 2] += r.z; a[j + 3] += r.w;
+      }
+    }
+    if (row_ok && ep.resid2 != nullptr) {
+#pragma unroll
+      for (int j = 0; j < 32; j += 4) {
+        const float4 r = *reinterpret_cast<const float4*>(ep.resid2 + off + j);
+        a[j] += r.x; a[j + 1] += r.y; a[j + 2] += r.z; a[j + 3] += r.w;
+      }
+    }
+  } else if constexpr (EPI == EPI_BF16) {
+    if (row_ok && ep.resid_bf16 != nullptr) {
+#pragma unroll
+      for (int j = 0; j < 32; j += 8) {
+        const uint4 rr = *reinterpret_cast<const uint4*>(ep.resid_bf16 + off + j);
+        const uint32_t rw[4] = {rr.x, rr.y, rr.z, rr.w};
+#pragma unroll
+        for (int t = 0; t < 4; ++t) {
+          const float2 f = unpack_bf16(rw[t]);
+          a[j + 2 * t] += f.x;
+          a[j + 2 * t + 1] += f.y;
+        }
+      }
+    }
+  } else if constexpr (EPI == EPI_ACT) {
+#pragma unroll
+    for (int j = 0; j < 32; ++j) { z[j] = a[j]; a[j] = act_fwd(ep.act, a[j]); }
+  } else if constexpr (EPI == EPI_DACT) {
+    if (row_ok) {
+#pragma unroll
+      for (int j = 0; j < 32; j += 8) {
+        const uint4 zz = *reinterpret_cast<const uint4*>(ep.aux_bf16 + off + j);
+        const uint32_t zw[4] = {zz.x, zz.y, zz.z, zz.w};
+#pragma unroll
+        for (int t = 0; t < 4; ++t) {
+          const float2 f = unpack_bf16(zw[t]);
+          a[j + 2 * t] *= act_bwd(ep.act, f.x);
+          a[j + 2 * t + 1] *= act_bwd(ep.act, f.y);
+        }
+      }
+    }
+  }
+}
+
+// 32 fp32 values -> one row of a 128B-swizzled staging box (fp32: the whole 128-B row; bf16: half `sub` of it)
+__device__ __forceinline__ void stage_row_f32(uint8_t* box, int row, const float (&a)[32]) {
+#pragma unroll
+  for (int q = 0; q < 8; ++q)
+    *reinterpret_cast<float4*>(box + row * 128 + ((q ^ (row & 7)) << 4)) =
+        make_float4(a[4 * q], a[4 * q + 1], a[4 * q + 2], a[4 * q + 3]);
+}
+__device__ __forceinline__ void stage_row_bf16(uint8_t* box, int row, int sub, const float (&a)[32]) {
+#pragma unroll
+  for (int q = 0; q < 4; ++q)
+    *reinterpret_cast<uint4*>(box + row * 128 + (((sub * 4 + q) ^ (row & 7)) << 4)) =
+        make_uint4(pack_bf16(a[8 * q], a[8 * q + 1]), pack_bf16(a[8 * q + 2], a[8 * q + 3]),
+                   pack_bf16(a[8 * q + 4], a[8 * q + 5]), pack_bf16(a[8 * q + 6], a[8 * q + 7]));
+}
+
+template <int BN, int EPI, bool TS>
 __global__ void __launch_bounds__(GEMM_THREADS, 1)
 gemm_tn_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_b,
+               const __grid_constant__ CUtensorMap tmap_c, const __grid_constant__ CUtensorMap tmap_c2,
                int M, int N, int K, GemmEpilogue ep) {
   using Cfg = TileCfg<BN>;
   constexpr int STAGES = Cfg::STAGES;
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
-  uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + STAGES * Cfg::STAGE_BYTES);
+  uint8_t* staging = smem + STAGES * Cfg::STAGE_BYTES;  // 1024-aligned: STAGE_BYTES is a multiple of 1024
+  uint64_t* full_bar = reinterpret_cast<uint64_t*>(staging + Cfg::STAGING_BYTES);
   uint64_t* empty_bar = full_bar + STAGES;
   uint64_t* tfull_bar = empty_bar + STAGES;
   uint64_t* tempty_bar = tfull_bar + 2;
@@ -292,6 +373,7 @@ gemm_tn_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
     // ------------------------------------------------------------ epilogue warps
     const int quad = warp & 3;  // TMEM lane quadrant this warp may read
     int it = 0;
+    int box_count = 0;
     for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++it) {
       const int acc = it & 1;
       const uint32_t acc_phase = (it >> 1) & 1;
@@ -300,16 +382,63 @@ gemm_tn_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
       mbar_wait(&tfull_bar[acc], acc_phase);
       tc_fence_after();
       const uint32_t t_row = tmem_base + (static_cast<uint32_t>(quad * 32) << 16) + acc * BN;
+      if constexpr (!TS) {
 #pragma unroll 1
-      for (int c = 0; c < BN; c += 32) {
-        uint32_t v[32];
-        tmem_ld_32x32(t_row + c, v);
-        tmem_ld_wait();
-        if (m < M && n0 + c < N) epilogue_chunk<EPI>(ep, m, n0 + c, v, N);
+        for (int c = 0; c < BN; c += 32) {
+          uint32_t v[32];
+          tmem_ld_32x32(t_row + c, v);
+          tmem_ld_wait();
+          if (m < M && n0 + c < N) epilogue_chunk<EPI>(ep, m, n0 + c, v, N);
+        }
+      } else {
+        // Staged epilogue: rows are written into 128B-swizzled [128][128 B] boxes in shared memory and
+        // leave through TMA stores (coalesced, clipped at M / N), two boxes in flight.
+        constexpr bool kF32 = (EPI == EPI_F32);
+        constexpr bool kTwo = (EPI == EPI_ACT);            // h and z leave together
+        constexpr int CH_PER_BOX = kF32 ? 1 : 2;           // 32-column chunks per box
+        const int row = quad * 32 + lane;
+        const int m0 = (tile / tiles_n) * BM;
+        const bool elected = (threadIdx.x == 64);
+        const bool two = kTwo && ep.out2_bf16 != nullptr;
+#pragma unroll 1
+        for (int c = 0; c < BN; c += 32) {
+          uint32_t v[32];
+          tmem_ld_32x32(t_row + c, v);
+          tmem_ld_wait();
+          if (n0 + c >= N) continue;                       // warp-uniform (N % 32 == 0)
+          float a[32], z[32];
+          epilogue_values<EPI>(ep, m, n0 + c, m < M, v, a, z);
+          const int sub = kF32 ? 0 : ((c >> 5) & 1);
+          const int buf = kTwo ? 0 : (box_count & 1);
+          if (sub == 0) {  // opening a box: its previous TMA store must have finished reading shared memory
+            if (elected) { if (kTwo) tma_store_wait_read<0>(); else tma_store_wait_read<1>(); }
+            named_bar_sync(1, 128);
+          }
+          if constexpr (kF32) {
+            stage_row_f32(staging + buf * 16384, row, a);
+          } else {
+            stage_row_bf16(staging + buf * 16384, row, sub, a);
+            if constexpr (kTwo) { if (two) stage_row_bf16(staging + 16384, row, sub, z); }
+          }
+          if (sub == CH_PER_BOX - 1) {
+            fence_proxy_async_smem();
+            named_bar_sync(1, 128);
+            if (elected) {
+              const int col = n0 + c - 32 * (CH_PER_BOX - 1);
+              tma_store_2d(&tmap_c, staging + buf * 16384, col, m0);
+              if (two) tma_store_2d(&tmap_c2, staging + 16384, col, m0);
+              tma_store_commit();
+            }
+            ++box_count;
+          }
+        }
       }
       tc_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive(&tempty_bar[acc]);
+    }
+    if constexpr (TS) {
+      if (threadIdx.x == 64) tma_store_wait_all<0>();  // shared memory must outlive the last store
     }
   }
 
@@ -321,12 +450,12 @@ gemm_tn_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
   }
 }
 
-template <int BN, int EPI>
-int launch(cudaStream_t stream, const CUtensorMap& ta, const CUtensorMap& tb, int M, int N, int K,
-           const GemmEpilogue& ep) {
+template <int BN, int EPI, bool TS>
+int launch(cudaStream_t stream, const CUtensorMap& ta, const CUtensorMap& tb, const CUtensorMap& tc,
+           const CUtensorMap& tc2, int M, int N, int K, const GemmEpilogue& ep) {
   using Cfg = TileCfg<BN>;
   static bool configured[64] = {};  // per instantiation and device (the attribute is per context)
-  auto kern = gemm_tn_kernel<BN, EPI>;
+  auto kern = gemm_tn_kernel<BN, EPI, TS>;
   int dev = 0;
   PEVIT_CHECK_CUDA(cudaGetDevice(&dev));
   if (!configured[dev & 63]) {
@@ -336,26 +465,31 @@ int launch(cudaStream_t stream, const CUtensorMap& ta, const CUtensorMap& tb, in
   const int tiles = ((M + BM - 1) / BM) * ((N + BN - 1) / BN);
   const int grid = tiles < sm_count() ? tiles : sm_count();
   ProfScope prof(stream, PC_GEMM_OTHER);
-  kern<<<grid, GEMM_THREADS, Cfg::SMEM_BYTES, stream>>>(ta, tb, M, N, K, ep);
+  kern<<<grid, GEMM_THREADS, Cfg::SMEM_BYTES, stream>>>(ta, tb, tc, tc2, M, N, K, ep);
   PEVIT_CHECK_LAUNCH();
   return 0;
 }
 
 template <int BN>
-int dispatch_epi(int epi, cudaStream_t s, const CUtensorMap& ta, const CUtensorMap& tb, int M, int N, int K,
-                 const GemmEpilogue& ep) {
+int dispatch_epi(int epi, bool ts, cudaStream_t s, const CUtensorMap& ta, const CUtensorMap& tb, const CUtensorMap& tc,
+                 const CUtensorMap& tc2, int M, int N, int K, const GemmEpilogue& ep) {
   switch (epi) {
-    case EPI_F32: return launch<BN, EPI_F32>(s, ta, tb, M, N, K, ep);
-    case EPI_BF16: return launch<BN, EPI_BF16>(s, ta, tb, M, N, K, ep);
-    case EPI_ACT: return launch<BN, EPI_ACT>(s, ta, tb, M, N, K, ep);
-    case EPI_DACT: return launch<BN, EPI_DACT>(s, ta, tb, M, N, K, ep);
-    case EPI_QKV: return launch<BN, EPI_QKV>(s, ta, tb, M, N, K, ep);
+    case EPI_F32: return ts ? launch<BN, EPI_F32, true>(s, ta, tb, tc, tc2, M, N, K, ep)
+                            : launch<BN, EPI_F32, false>(s, ta, tb, tc, tc2, M, N, K, ep);
+    case EPI_BF16: return ts ? launch<BN, EPI_BF16, true>(s, ta, tb, tc, tc2, M, N, K, ep)
+                             : launch<BN, EPI_BF16, false>(s, ta, tb, tc, tc2, M, N, K, ep);
+    case EPI_ACT: return ts ? launch<BN, EPI_ACT, true>(s, ta, tb, tc, tc2, M, N, K, ep)
+                            : launch<BN, EPI_ACT, false>(s, ta, tb, tc, tc2, M, N, K, ep);
+    case EPI_DACT: return ts ? launch<BN, EPI_DACT, true>(s, ta, tb, tc, tc2, M, N, K, ep)
+                             : launch<BN, EPI_DACT, false>(s, ta, tb, tc, tc2, M, N, K, ep);
+    case EPI_QKV: return launch<BN, EPI_QKV, false>(s, ta, tb, tc, tc2, M, N, K, ep);
   }
   set_error("gemm_tn: unknown epilogue %d", epi);
   return -1;
 }
 
 int pick_bn(int M, int N, int forced) {
+  if (forced < 0) forced = -forced;  // negative: same tile width, direct-store epilogue (cross-check)
   if (forced == 32 || forced == 64 || forced == 128 || forced == 256) return forced;
   if (N <= 32) return 32;
   if (N <= 64) return 64;
@@ -389,14 +523,28 @@ int gemm_tn(cudaStream_t stream, const bf16* A, int lda, const bf16* B, int ldb,
   else
     PEVIT_REQUIRE(ep.ld_out % 8 == 0, "gemm_tn: ld_out must be a multiple of 8");
   const int bn = pick_bn(M, N, force_bn);
-  CUtensorMap ta, tb;
+  CUtensorMap ta, tb, tc, tc2;
   if (make_tmap_bf16_2d(&ta, A, M, K, lda, BM, BK) != 0) return -1;
   if (make_tmap_bf16_2d(&tb, B, N, K, ldb, bn, BK) != 0) return -1;
+  // Staged TMA-store epilogue for row-major outputs with 16-byte aligned rows; direct stores otherwise.
+  const void* out = epi == EPI_F32 ? static_cast<const void*>(ep.out_f32) : static_cast<const void*>(ep.out_bf16);
+  const int elt = epi == EPI_F32 ? 4 : 2;
+  const bool ts = epi != EPI_QKV && N % 64 == 0 && out != nullptr &&
+                  (reinterpret_cast<uintptr_t>(out) & 15) == 0 && (static_cast<size_t>(ep.ld_out) * elt) % 16 == 0 &&
+                  (ep.out2_bf16 == nullptr || (reinterpret_cast<uintptr_t>(ep.out2_bf16) & 15) == 0) &&
+                  force_bn >= 0;
+  tc = ta;
+  tc2 = ta;
+  if (ts) {
+    if (make_tmap_out_2d(&tc, out, M, N, ep.ld_out, BM, elt) != 0) return -1;
+    if (epi == EPI_ACT && ep.out2_bf16 != nullptr && make_tmap_out_2d(&tc2, ep.out2_bf16, M, N, ep.ld_out, BM, 2) != 0)
+      return -1;
+  }
   switch (bn) {
-    case 32: return dispatch_epi<32>(epi, stream, ta, tb, M, N, K, ep);
-    case 64: return dispatch_epi<64>(epi, stream, ta, tb, M, N, K, ep);
-    case 128: return dispatch_epi<128>(epi, stream, ta, tb, M, N, K, ep);
-    default: return dispatch_epi<256>(epi, stream, ta, tb, M, N, K, ep);
+    case 32: return dispatch_epi<32>(epi, ts, stream, ta, tb, tc, tc2, M, N, K, ep);
+    case 64: return dispatch_epi<64>(epi, ts, stream, ta, tb, tc, tc2, M, N, K, ep);
+    case 128: return dispatch_epi<128>(epi, ts, stream, ta, tb, tc, tc2, M, N, K, ep);
+    default: return dispatch_epi<256>(epi, ts, stream, ta, tb, tc, tc2, M, N, K, ep);
   }
 }
 

@@ -142,6 +142,25 @@ int make_tmap_bf16_2d(CUtensorMap* out, const void* base, uint64_t rows, uint64_
   return 0;
 }
 
+int make_tmap_out_2d(CUtensorMap* out, const void* base, uint64_t rows, uint64_t cols, uint64_t row_stride_elems,
+                     uint32_t box_rows, int elem_bytes) {
+  CUtensorMap dummy;
+  if (g_encode == nullptr && make_tmap_bf16_2d(&dummy, base, 8, 64, 64, 8, 64) != 0) return -2;  // resolves g_encode
+  const cuuint64_t gdim[2] = {cols, rows};
+  const cuuint64_t gstride[1] = {row_stride_elems * static_cast<cuuint64_t>(elem_bytes)};
+  const cuuint32_t box[2] = {static_cast<cuuint32_t>(128 / elem_bytes), box_rows};
+  const cuuint32_t estride[2] = {1, 1};
+  CUresult r = g_encode(out, elem_bytes == 4 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT32 : CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2,
+                        const_cast<void*>(base), gdim, gstride, box, estride, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                        CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) {
+    set_error("cuTensorMapEncodeTiled(out) failed (%d): base=%p rows=%llu cols=%llu stride=%llu", (int)r, base,
+              (unsigned long long)rows, (unsigned long long)cols, (unsigned long long)row_stride_elems);
+    return -2;
+  }
+  return 0;
+}
+
 int make_tmap_bf16_tok_heads(CUtensorMap* out, const void* base, int L, int NB, int H, uint64_t row_stride_elems,
                              uint32_t box_l) {
   CUtensorMap dummy;

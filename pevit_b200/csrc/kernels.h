@@ -79,6 +79,10 @@ int lora_expand(cudaStream_t s, const float* Aq, const float* Av, const float* B
 // C[Kc][Nc] (fp32, += with atomics; caller zeroes) = scale * A[M][Kc]^T * B[M][Nc]; A bf16 or fp32, B fp32 or bf16.
 int atb_accumulate(cudaStream_t s, const void* A, int a_is_bf16, int lda, const void* B, int b_is_bf16, int ldb, int M,
                    int Kc, int Nc, float scale, float* C);
+// gemm_atb_tc.cu: the same product on tcgen05 (both operands MN-major, split over rows, red.add epilogue).
+// B exposes nb_cols (<= 64) columns; columns [n_lo, n_lo+n_cnt) of A^T B go to C[kc][0..n_cnt) (row stride ldc).
+int atb_tc(cudaStream_t s, const bf16* A, int lda, const bf16* B, int ldb, int nb_cols, int M, int Kc, int n_lo,
+           int n_cnt, float scale, float* C, int ldc);
 // column sums of a bf16 [M][ld] matrix (first D columns), atomically accumulated into out[D] (caller zeroes).
 int colsum_bf16(cudaStream_t s, const bf16* X, int ld, int M, int D, float* out);
 // KAdaptation factor gradients from dP [D][64] (q|v) and dQ [2][D][32].

@@ -45,8 +45,8 @@ def run_gemm(lib, a, b, epi, **kw):
 @pytest.mark.parametrize("M,N,K,bn", [
     (128, 256, 64, 0), (256, 128, 128, 128), (400, 768, 768, 0), (400, 768, 768, 64), (400, 768, 768, 256),
     (12800, 768, 3072, 0), (1000, 3072, 768, 0), (130, 72, 776, 0), (400, 32, 768, 0), (400, 4, 768, 0),
-    (400, 768, 64, 0),
-])
+    (400, 768, 64, 0), (400, 768, 768, -128), (130, 192, 776, 0), (1000, 3072, 768, -256), (129, 64, 64, 0),
+])  # bn < 0: direct-store epilogue instead of the staged TMA-store one
 def test_gemm_f32_bias_resid(lib, M, N, K, bn):
     g = torch.Generator(device="cuda").manual_seed(M + N + K)
     a = bf(torch.randn(M, K, device="cuda", generator=g))
@@ -83,6 +83,9 @@ def test_gemm_quickgelu_fwd_bwd(lib):
     h = torch.empty(M, N, dtype=torch.bfloat16, device="cuda")
     z = torch.empty_like(h)
     run_gemm(lib, a, b, L.EPI_QGELU, bias=bias, out_bf16=h, out2_bf16=z, ld_out=N)
+    h2, z2 = torch.empty_like(h), torch.empty_like(z)
+    run_gemm(lib, a, b, L.EPI_QGELU, bias=bias, out_bf16=h2, out2_bf16=z2, ld_out=N, force_bn=-256)
+    assert torch.equal(h, h2) and torch.equal(z, z2), "staged and direct epilogues must agree bit for bit"
     zr = a.float() @ b.float().t() + bias
     assert rel_inf(z.float(), zr) < 1e-2
     assert rel_inf(h.float(), zr * torch.sigmoid(1.702 * zr)) < 1e-2
@@ -310,3 +313,19 @@ def test_gemm_delta_apply_in_place(lib):
     ref = q.float() + T.float() @ W.float().t() + bias
     run_gemm(lib, T, W, L.EPI_BF16, bias=bias, out_bf16=q, resid_bf16=q, ld_out=D)
     assert rel_inf(q.float(), ref) < 1e-2
+
+
+@pytest.mark.parametrize("M,Kc,nb,n_lo,n_cnt", [(1000, 768, 64, 0, 64), (12800, 768, 64, 32, 32), (400, 768, 8, 4, 4),
+                                                (15, 128, 64, 0, 32), (130, 1024, 64, 0, 64)])
+def test_atb_tc(lib, M, Kc, nb, n_lo, n_cnt):
+    """C += scale * A^T B on tcgen05 with both operands MN-major (row-major token-by-feature tiles)."""
+    dev = "cuda"
+    a = bf(torch.randn(M, Kc, device=dev))
+    wide = bf(torch.randn(M, 80, device=dev))          # B lives inside a wider row (like dT inside dqkv)
+    b = wide[:, 8:8 + nb]
+    c = torch.zeros(Kc, n_cnt, device=dev)
+    L.check(lib.pevit_atb_tc(a.data_ptr(), Kc, b.data_ptr(), 80, nb, M, Kc, n_lo, n_cnt, 0.5, c.data_ptr(), n_cnt,
+                             st()), "atb_tc")
+    torch.cuda.synchronize()
+    ref = 0.5 * a.float().t() @ b.float()[:, n_lo:n_lo + n_cnt]
+    assert rel_inf(c, ref) < 2e-3
