@@ -30,25 +30,45 @@ struct TileCfg {
   static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + STAGING_BYTES + 256 + 1024;  // + barriers + align slack
 };
 
-__device__ __forceinline__ float sigmoidf_fast(float x) { return 1.f / (1.f + __expf(-x)); }
+// The activation kind rides in the upper bits of the EPI template argument so that each kernel
+// instantiation contains exactly one activation (a runtime switch made ptxas predicate all three).
+constexpr int epi_base(int epi) { return epi & 0xff; }
+constexpr int epi_act(int epi) { return epi >> 8; }
+constexpr int epi_with_act(int epi, int act) { return epi | (act << 8); }
+
+__device__ __forceinline__ float tanh_fast(float x) {
+  float y;
+  asm("tanh.approx.f32 %0, %1;" : "=f"(y) : "f"(x));
+  return y;
+}
+// sigmoid(x) = 0.5 tanh(x/2) + 0.5: one MUFU op instead of ex2 + rcp
+__device__ __forceinline__ float sigmoid_fast(float x) { return fmaf(0.5f, tanh_fast(0.5f * x), 0.5f); }
 
 // activations of the path: QuickGELU (model.py:163-165), ReLU (adapter_model.py:305),
 // gelu_new (compacter_model.py:374 -> transformers NewGELUActivation)
-__device__ __forceinline__ float act_fwd(int kind, float z) {
-  if (kind == ACT_QUICKGELU) return z * sigmoidf_fast(1.702f * z);
-  if (kind == ACT_RELU) return fmaxf(z, 0.f);
-  const float u = 0.7978845608028654f * (z + 0.044715f * z * z * z);
-  return 0.5f * z * (1.f + tanhf(u));
-}
-__device__ __forceinline__ float act_bwd(int kind, float z) {
-  if (kind == ACT_QUICKGELU) {
-    const float s = sigmoidf_fast(1.702f * z);
-    return s * (1.f + 1.702f * z * (1.f - s));
+template <int KIND>
+__device__ __forceinline__ float act_fwd(float z) {
+  if constexpr (KIND == ACT_QUICKGELU) {
+    return z * sigmoid_fast(1.702f * z);
+  } else if constexpr (KIND == ACT_RELU) {
+    return fmaxf(z, 0.f);
+  } else {
+    const float u = 0.7978845608028654f * (z + 0.044715f * z * z * z);
+    return 0.5f * z * (1.f + tanh_fast(u));
   }
-  if (kind == ACT_RELU) return z > 0.f ? 1.f : 0.f;
-  const float u = 0.7978845608028654f * (z + 0.044715f * z * z * z);
-  const float t = tanhf(u);
-  return 0.5f * (1.f + t) + 0.5f * z * (1.f - t * t) * 0.7978845608028654f * (1.f + 3.f * 0.044715f * z * z);
+}
+template <int KIND>
+__device__ __forceinline__ float act_bwd(float z) {
+  if constexpr (KIND == ACT_QUICKGELU) {
+    const float s = sigmoid_fast(1.702f * z);
+    return s * (1.f + 1.702f * z * (1.f - s));
+  } else if constexpr (KIND == ACT_RELU) {
+    return z > 0.f ? 1.f : 0.f;
+  } else {
+    const float u = 0.7978845608028654f * (z + 0.044715f * z * z * z);
+    const float t = tanh_fast(u);
+    return 0.5f * (1.f + t) + 0.5f * z * (1.f - t * t) * 0.7978845608028654f * (1.f + 3.f * 0.044715f * z * z);
+  }
 }
 
 // Epilogue for one 32-column chunk of one accumulator row.  v[] holds raw fp32 bits.
@@ -60,7 +80,7 @@ __device__ __forceinline__ void epilogue_chunk(const GemmEpilogue& ep, int m, in
   for (int j = 0; j < 32; ++j) a[j] = __uint_as_float(v[j]);
   const bool full = (c0 + 32 <= N);
 
-  if (ep.bias != nullptr && !(EPI == EPI_QKV && c0 >= 3 * ep.D)) {
+  if (ep.bias != nullptr && !(epi_base(EPI) == EPI_QKV && c0 >= 3 * ep.D)) {
     if (full) {
 #pragma unroll
       for (int j = 0; j < 32; j += 4) {
@@ -72,7 +92,7 @@ __device__ __forceinline__ void epilogue_chunk(const GemmEpilogue& ep, int m, in
     }
   }
 
-  if constexpr (EPI == EPI_F32) {
+  if constexpr (epi_base(EPI) == EPI_F32) {
     const size_t off = static_cast<size_t>(m) * ep.ld_out + c0;
     if (full) {
       if (ep.resid != nullptr) {
@@ -97,7 +117,7 @@ __device__ __forceinline__ void epilogue_chunk(const GemmEpilogue& ep, int m, in
         ep.out_f32[off + j] = a[j] + (ep.resid != nullptr ? ep.resid[off + j] : 0.f) +
                               (ep.resid2 != nullptr ? ep.resid2[off + j] : 0.f);
     }
-  } else if constexpr (EPI == EPI_BF16) {
+  } else if constexpr (epi_base(EPI) == EPI_BF16) {
     const size_t off = static_cast<size_t>(m) * ep.ld_out + c0;
     if (ep.resid_bf16 != nullptr) {  // in-place low-rank delta: q' = q + (alpha T Q^T + b)
       if (full) {
@@ -126,12 +146,12 @@ __device__ __forceinline__ void epilogue_chunk(const GemmEpilogue& ep, int m, in
     } else {
       _Pragma("unroll") for (int j = 0; j < 32; ++j) if (c0 + j < N) ep.out_bf16[off + j] = __float2bfloat16(a[j]);
     }
-  } else if constexpr (EPI == EPI_ACT) {
+  } else if constexpr (epi_base(EPI) == EPI_ACT) {
     // z = acc + bias (kept for backward in out2), out = act(z)
     const size_t off = static_cast<size_t>(m) * ep.ld_out + c0;
     float h[32];
 #pragma unroll
-    for (int j = 0; j < 32; ++j) h[j] = act_fwd(ep.act, a[j]);
+    for (int j = 0; j < 32; ++j) h[j] = act_fwd<epi_act(EPI)>(a[j]);
     if (full) {
 #pragma unroll
       for (int j = 0; j < 32; j += 8) {
@@ -149,7 +169,7 @@ __device__ __forceinline__ void epilogue_chunk(const GemmEpilogue& ep, int m, in
         if (ep.out2_bf16 != nullptr) ep.out2_bf16[off + j] = __float2bfloat16(a[j]);
       }
     }
-  } else if constexpr (EPI == EPI_DACT) {
+  } else if constexpr (epi_base(EPI) == EPI_DACT) {
     // dz = acc * act'(z)
     const size_t off = static_cast<size_t>(m) * ep.ld_out + c0;
     if (full) {
@@ -161,17 +181,17 @@ __device__ __forceinline__ void epilogue_chunk(const GemmEpilogue& ep, int m, in
 #pragma unroll
         for (int t = 0; t < 4; ++t) {
           float2 z = unpack_bf16(zw[t]);
-          o[t] = pack_bf16(a[j + 2 * t] * act_bwd(ep.act, z.x), a[j + 2 * t + 1] * act_bwd(ep.act, z.y));
+          o[t] = pack_bf16(a[j + 2 * t] * act_bwd<epi_act(EPI)>(z.x), a[j + 2 * t + 1] * act_bwd<epi_act(EPI)>(z.y));
         }
         *reinterpret_cast<uint4*>(ep.out_bf16 + off + j) = make_uint4(o[0], o[1], o[2], o[3]);
       }
     } else {
       _Pragma("unroll") for (int j = 0; j < 32; ++j) if (c0 + j < N) {
         float z = __bfloat162float(ep.aux_bf16[off + j]);
-        ep.out_bf16[off + j] = __float2bfloat16(a[j] * act_bwd(ep.act, z));
+        ep.out_bf16[off + j] = __float2bfloat16(a[j] * act_bwd<epi_act(EPI)>(z));
       }
     }
-  } else if constexpr (EPI == EPI_QKV) {
+  } else if constexpr (epi_base(EPI) == EPI_QKV) {
     // rows are tokens in LND order (m = l*NB + n).  Columns [0,3D): q|k|v -> head-major bf16
     // tiles [which][n*H+h][l][64] with q pre-scaled by 1/sqrt(64) (exact: power of two);
     // columns [3D, 3D+r2): low-rank activations T = X*P kept in fp32, row-major [M][r2].
@@ -211,7 +231,7 @@ __device__ __forceinline__ void epilogue_values(const GemmEpilogue& ep, int m, i
     }
   }
   const size_t off = static_cast<size_t>(m) * ep.ld_out + c0;
-  if constexpr (EPI == EPI_F32) {
+  if constexpr (epi_base(EPI) == EPI_F32) {
     if (row_ok && ep.resid != nullptr) {
 #pragma unroll
       for (int j = 0; j < 32; j += 4) {
@@ -226,7 +246,7 @@ __device__ __forceinline__ void epilogue_values(const GemmEpilogue& ep, int m, i
         a[j] += r.x; a[j + 1] += r.y; a[j + 2] += r.z; a[j + 3] += r.w;
       }
     }
-  } else if constexpr (EPI == EPI_BF16) {
+  } else if constexpr (epi_base(EPI) == EPI_BF16) {
     if (row_ok && ep.resid_bf16 != nullptr) {
 #pragma unroll
       for (int j = 0; j < 32; j += 8) {
@@ -240,10 +260,10 @@ __device__ __forceinline__ void epilogue_values(const GemmEpilogue& ep, int m, i
         }
       }
     }
-  } else if constexpr (EPI == EPI_ACT) {
+  } else if constexpr (epi_base(EPI) == EPI_ACT) {
 #pragma unroll
-    for (int j = 0; j < 32; ++j) { z[j] = a[j]; a[j] = act_fwd(ep.act, a[j]); }
-  } else if constexpr (EPI == EPI_DACT) {
+    for (int j = 0; j < 32; ++j) { z[j] = a[j]; a[j] = act_fwd<epi_act(EPI)>(a[j]); }
+  } else if constexpr (epi_base(EPI) == EPI_DACT) {
     if (row_ok) {
 #pragma unroll
       for (int j = 0; j < 32; j += 8) {
@@ -252,8 +272,8 @@ __device__ __forceinline__ void epilogue_values(const GemmEpilogue& ep, int m, i
 #pragma unroll
         for (int t = 0; t < 4; ++t) {
           const float2 f = unpack_bf16(zw[t]);
-          a[j + 2 * t] *= act_bwd(ep.act, f.x);
-          a[j + 2 * t + 1] *= act_bwd(ep.act, f.y);
+          a[j + 2 * t] *= act_bwd<epi_act(EPI)>(f.x);
+          a[j + 2 * t + 1] *= act_bwd<epi_act(EPI)>(f.y);
         }
       }
     }
@@ -393,8 +413,8 @@ gemm_tn_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
       } else {
         // Staged epilogue: rows are written into 128B-swizzled [128][128 B] boxes in shared memory and
         // leave through TMA stores (coalesced, clipped at M / N), two boxes in flight.
-        constexpr bool kF32 = (EPI == EPI_F32);
-        constexpr bool kTwo = (EPI == EPI_ACT);            // h and z leave together
+        constexpr bool kF32 = (epi_base(EPI) == EPI_F32);
+        constexpr bool kTwo = (epi_base(EPI) == EPI_ACT);            // h and z leave together
         constexpr int CH_PER_BOX = kF32 ? 1 : 2;           // 32-column chunks per box
         const int row = quad * 32 + lane;
         const int m0 = (tile / tiles_n) * BM;
@@ -478,10 +498,18 @@ int dispatch_epi(int epi, bool ts, cudaStream_t s, const CUtensorMap& ta, const 
                             : launch<BN, EPI_F32, false>(s, ta, tb, tc, tc2, M, N, K, ep);
     case EPI_BF16: return ts ? launch<BN, EPI_BF16, true>(s, ta, tb, tc, tc2, M, N, K, ep)
                              : launch<BN, EPI_BF16, false>(s, ta, tb, tc, tc2, M, N, K, ep);
-    case EPI_ACT: return ts ? launch<BN, EPI_ACT, true>(s, ta, tb, tc, tc2, M, N, K, ep)
-                            : launch<BN, EPI_ACT, false>(s, ta, tb, tc, tc2, M, N, K, ep);
-    case EPI_DACT: return ts ? launch<BN, EPI_DACT, true>(s, ta, tb, tc, tc2, M, N, K, ep)
-                             : launch<BN, EPI_DACT, false>(s, ta, tb, tc, tc2, M, N, K, ep);
+    case EPI_ACT:
+      if (ep.act == ACT_QUICKGELU)
+        return ts ? launch<BN, epi_with_act(EPI_ACT, ACT_QUICKGELU), true>(s, ta, tb, tc, tc2, M, N, K, ep)
+                  : launch<BN, epi_with_act(EPI_ACT, ACT_QUICKGELU), false>(s, ta, tb, tc, tc2, M, N, K, ep);
+      if (ep.act == ACT_RELU) return launch<BN, epi_with_act(EPI_ACT, ACT_RELU), false>(s, ta, tb, tc, tc2, M, N, K, ep);
+      return launch<BN, epi_with_act(EPI_ACT, ACT_GELU_NEW), false>(s, ta, tb, tc, tc2, M, N, K, ep);
+    case EPI_DACT:
+      if (ep.act == ACT_QUICKGELU)
+        return ts ? launch<BN, epi_with_act(EPI_DACT, ACT_QUICKGELU), true>(s, ta, tb, tc, tc2, M, N, K, ep)
+                  : launch<BN, epi_with_act(EPI_DACT, ACT_QUICKGELU), false>(s, ta, tb, tc, tc2, M, N, K, ep);
+      if (ep.act == ACT_RELU) return launch<BN, epi_with_act(EPI_DACT, ACT_RELU), false>(s, ta, tb, tc, tc2, M, N, K, ep);
+      return launch<BN, epi_with_act(EPI_DACT, ACT_GELU_NEW), false>(s, ta, tb, tc, tc2, M, N, K, ep);
     case EPI_QKV: return launch<BN, EPI_QKV, false>(s, ta, tb, tc, tc2, M, N, K, ep);
   }
   set_error("gemm_tn: unknown epilogue %d", epi);
@@ -529,7 +557,8 @@ int gemm_tn(cudaStream_t stream, const bf16* A, int lda, const bf16* B, int ldb,
   // Staged TMA-store epilogue for row-major outputs with 16-byte aligned rows; direct stores otherwise.
   const void* out = epi == EPI_F32 ? static_cast<const void*>(ep.out_f32) : static_cast<const void*>(ep.out_bf16);
   const int elt = epi == EPI_F32 ? 4 : 2;
-  const bool ts = epi != EPI_QKV && N % 64 == 0 && out != nullptr &&
+  const bool act_plain = !((epi == EPI_ACT || epi == EPI_DACT) && ep.act != ACT_QUICKGELU);  // bottleneck acts: direct
+  const bool ts = epi != EPI_QKV && act_plain && N % 64 == 0 && out != nullptr &&
                   (reinterpret_cast<uintptr_t>(out) & 15) == 0 && (static_cast<size_t>(ep.ld_out) * elt) % 16 == 0 &&
                   (ep.out2_bf16 == nullptr || (reinterpret_cast<uintptr_t>(ep.out2_bf16) & 15) == 0) &&
                   force_bn >= 0;
