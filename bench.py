@@ -183,7 +183,7 @@ def gemm_flops(cls: str, M: int, D: int, r2: int) -> float:
     W3 = 3 * D + r2
     dims = {"gemm_qkv": (W3, D), "gemm_out": (D, D), "gemm_fc": (4 * D, D), "gemm_proj": (D, 4 * D),
             "gemm_dproj": (4 * D, D), "gemm_dfc": (D, 4 * D), "gemm_dout": (D, D), "gemm_dqkv": (D, W3),
-            "gemm_dT": (r2 // 2, D)}
+            "gemm_dT": (r2 // 2, D), "gemm_delta": (D, r2), "gemm_stem": (D, 3072)}
     n, k = dims[cls]
     return 2.0 * M * n * k
 

@@ -127,6 +127,15 @@ int pevit_kad_factor_grads(const float* dP, const float* dQ, const float* u1, co
 int pevit_cast_bf16(const float* src, void* dst, size_t n, void* stream);
 int pevit_transpose_bf16(const float* src, int32_t rows, int32_t cols, void* dst, int32_t ldd, void* stream);
 
+/* ------------------------------------------------------------------ stem
+ * VisionTransformer.forward up to the first block (model.py:1034-1042): stride-p conv1 as im2col + tcgen05
+ * GEMM, class token, positional embedding, ln_pre, NLD -> LND.  images fp32 (N,3,R,R) -> x fp32 (L,N,D).
+ * w_patch: bf16 [D][ceil8(3 p^2)] flattened conv1.weight, zero padded along K.  Frozen parameters: no backward. */
+size_t pevit_patch_embed_workspace_bytes(int32_t nb, int32_t resolution, int32_t patch, int32_t d);
+int pevit_patch_embed(const float* images, const void* w_patch, const float* cls, const float* pos, const float* ln_g,
+                      const float* ln_b, float* x, void* workspace, int32_t nb, int32_t resolution, int32_t patch,
+                      int32_t d, void* stream);
+
 /* ------------------------------------------------------------------ block level
  * One ResidualAttentionBlock forward / backward (model.py:947-975, lora_model.py,
  * adapter_model.py:298-336, compacter_model.py:465-503), frozen backbone: dgrad only,

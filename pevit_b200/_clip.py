@@ -283,13 +283,20 @@ class VisionTransformer(nn.Module):
         self.ln_post = LayerNorm(width)
         self.proj = nn.Parameter(scale * torch.randn(width, output_dim))
 
+    def _stem_is_frozen(self) -> bool:
+        ps = (self.conv1.weight, self.class_embedding, self.positional_embedding, self.ln_pre.weight, self.ln_pre.bias)
+        return not (torch.is_grad_enabled() and any(p.requires_grad for p in ps))
+
     def forward(self, x: torch.Tensor) -> torch.Tensor:
-        x = self.conv1(x)                                        # (N, D, g, g)
-        x = x.flatten(2).transpose(1, 2)                         # (N, g*g, D)
-        cls = self.class_embedding.to(x.dtype).expand(x.shape[0], 1, -1)
-        x = torch.cat([cls, x], dim=1) + self.positional_embedding.to(x.dtype)
-        x = self.ln_pre(x)
-        x = self.transformer(x.transpose(0, 1).contiguous())     # (L, N, D) rows, as the reference (model.py:1042)
+        if x.is_cuda and not x.requires_grad and self._stem_is_frozen() and x.shape[-1] % self.conv1.kernel_size[0] == 0:
+            x = ops.stem_forward(self, x)                        # fused stem -> (L, N, D)
+        else:  # stem parameters being trained (not a PEViT setting): stock ops keep autograd semantics
+            x = self.conv1(x)                                    # (N, D, g, g)
+            x = x.flatten(2).transpose(1, 2)                     # (N, g*g, D)
+            cls = self.class_embedding.to(x.dtype).expand(x.shape[0], 1, -1)
+            x = torch.cat([cls, x], dim=1) + self.positional_embedding.to(x.dtype)
+            x = self.ln_pre(x).transpose(0, 1).contiguous()      # (L, N, D) rows, as the reference (model.py:1042)
+        x = self.transformer(x)
         x = self.ln_post(x[0])                                   # class token of every image
         if self.proj is not None:
             x = x @ self.proj

@@ -244,6 +244,18 @@ int pevit_prof_read(double* ms, int64_t* launches, int32_t n) {
 }
 int64_t pevit_launch_count(void) { return launch_count(); }
 
+size_t pevit_patch_embed_workspace_bytes(int32_t nb, int32_t resolution, int32_t patch, int32_t d) {
+  return patch_embed_workspace_bytes(nb, resolution, patch, d);
+}
+
+int pevit_patch_embed(const float* images, const void* w_patch, const float* cls, const float* pos, const float* ln_g,
+                      const float* ln_b, float* x, void* workspace, int32_t nb, int32_t resolution, int32_t patch,
+                      int32_t d, void* stream) {
+  PEVIT_REQUIRE(images && w_patch && cls && pos && ln_g && ln_b && x && workspace, "pevit_patch_embed: null pointer");
+  return patch_embed(as_stream(stream), images, static_cast<const bf16*>(w_patch), cls, pos, ln_g, ln_b, x, workspace, nb,
+                     resolution, patch, d);
+}
+
 size_t pevit_block_saved_bytes(const pevit_block_desc* desc) {
   if (check_desc(desc) != 0) return 0;
   return carve_saved(*desc, nullptr).bytes;

@@ -92,6 +92,13 @@ int kad_factor_grads(cudaStream_t s, const float* dP, const float* dQ, const flo
 // dT (fp32 [M][r2 cols starting at col0]) -> bf16 into dqkv_ext[:, 3D+col0 ...]
 int cast_f32_to_bf16_2d(cudaStream_t s, const float* src, int lds, bf16* dst, int ldd, int rows, int cols);
 
+// ------------------------------------------------------------------ stem.cu
+// Patch embedding + class token + positional embedding + ln_pre -> x (L, N, D) fp32 (model.py:1034-1042).
+// w_patch: bf16 [D][Kpad], Kpad = ceil8(3 p^2), the flattened conv1 weight zero-padded along K.
+size_t patch_embed_workspace_bytes(int NB, int R, int p, int D);
+int patch_embed(cudaStream_t s, const float* img, const bf16* w_patch, const float* cls, const float* pos,
+                const float* ln_g, const float* ln_b, float* x, void* workspace, int NB, int R, int p, int D);
+
 // ------------------------------------------------------------------ elementwise.cu
 int cast_f32_to_bf16(cudaStream_t s, const float* src, bf16* dst, size_t n);
 // dst[c][r] = src[r][c]  (fp32 -> bf16 transpose; weight prep for dgrad GEMMs)

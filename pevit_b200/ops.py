@@ -236,3 +236,44 @@ def block_forward(block, x: torch.Tensor, method: str, peft: tuple, attn_impl: i
         raise ValueError(f"expected (L, N, D) input, got {tuple(x.shape)}")
     pack = get_pack(block, method)
     return _BlockFn.apply(x, pack, attn_impl, *peft)
+
+
+class StemPack:
+    """bf16 [D][Kpad] copy of the (frozen) patch-embedding conv weight."""
+
+    def __init__(self, visual):
+        w = visual.conv1.weight.detach()
+        D, K = w.shape[0], w[0].numel()
+        self.Kpad = (K + 7) // 8 * 8
+        flat = torch.zeros(D, self.Kpad, dtype=torch.float32, device=w.device)
+        flat[:, :K] = w.reshape(D, K).float()
+        self.w = torch.empty(D, self.Kpad, dtype=torch.bfloat16, device=w.device)
+        BlockPack.cast(flat, self.w)
+        self.key = self.signature(visual)
+
+    @staticmethod
+    def signature(visual) -> tuple:
+        w = visual.conv1.weight
+        return (w.data_ptr(), w._version, str(w.device))
+
+
+def stem_forward(visual, images: torch.Tensor) -> torch.Tensor:
+    """conv1 + class token + positional embedding + ln_pre -> (L, N, D) fp32 (model.py:1034-1042)."""
+    lib = L.lib()
+    pack = getattr(visual, "_pevit_stem", None)
+    if pack is None or pack.key != StemPack.signature(visual):
+        pack = StemPack(visual)
+        object.__setattr__(visual, "_pevit_stem", pack)
+    images = _f32c(images)
+    NB, _, R, _ = images.shape
+    p = visual.conv1.kernel_size[0]
+    D = visual.conv1.out_channels
+    Lt = (R // p) ** 2 + 1
+    x = torch.empty(Lt, NB, D, dtype=torch.float32, device=images.device)
+    nbytes = lib.pevit_patch_embed_workspace_bytes(NB, R, p, D)
+    ws = torch.empty(nbytes, dtype=torch.uint8, device=images.device)
+    small = [_f32c(t.detach()) for t in (visual.class_embedding, visual.positional_embedding, visual.ln_pre.weight,
+                                         visual.ln_pre.bias)]
+    L.check(lib.pevit_patch_embed(_ptr(images), _ptr(pack.w), *(_ptr(t) for t in small), _ptr(x), _ptr(ws), NB, R, p, D,
+                                  _stream()), "pevit_patch_embed")
+    return x

@@ -329,3 +329,22 @@ def test_atb_tc(lib, M, Kc, nb, n_lo, n_cnt):
     torch.cuda.synchronize()
     ref = 0.5 * a.float().t() @ b.float()[:, n_lo:n_lo + n_cnt]
     assert rel_inf(c, ref) < 2e-3
+
+
+@pytest.mark.parametrize("NB,R,p,D", [(4, 224, 32, 768), (3, 32, 16, 128), (2, 224, 14, 1024)])
+def test_patch_embed_stem(lib, NB, R, p, D):
+    """conv1 (stride = kernel) + class token + positional embedding + ln_pre + NLD->LND (model.py:1034-1042)."""
+    from pevit_b200 import _clip, ops
+    torch.manual_seed(0)
+    vis = _clip.VisionTransformer(R, p, D, 1, D // 64, 64, method="plain").cuda().eval()
+    with torch.no_grad():
+        vis.ln_pre.weight.add_(0.1 * torch.randn_like(vis.ln_pre.weight))
+        vis.ln_pre.bias.add_(0.1 * torch.randn_like(vis.ln_pre.bias))
+        img = torch.randn(NB, 3, R, R, device="cuda")
+        x = vis.conv1(img).flatten(2).transpose(1, 2)
+        x = torch.cat([vis.class_embedding.expand(NB, 1, -1), x], dim=1) + vis.positional_embedding
+        ref = vis.ln_pre(x).transpose(0, 1).contiguous()
+        got = ops.stem_forward(vis, img)
+    torch.cuda.synchronize()
+    assert got.shape == ref.shape
+    assert rel_inf(got, ref) < 1e-2
