@@ -126,6 +126,14 @@ def b32_block(method: str) -> dict:
     return out
 
 
+def surface(method: str, sd) -> dict:
+    """state_dict keys / named_parameters names with shapes: the drop-in boundary."""
+    torch.manual_seed(0)
+    model = ref_import.build(method, sd)
+    return {"state_dict": [[k, list(v.shape)] for k, v in model.state_dict().items()],      # ordered
+            "named_parameters": [[k, list(v.shape)] for k, v in model.named_parameters()]}
+
+
 def save(name: str, d: dict) -> None:
     arrs = {k: (v.detach().cpu().numpy() if isinstance(v, torch.Tensor) else v) for k, v in d.items()}
     path = os.path.join(HERE, name)
@@ -141,6 +149,10 @@ def main() -> None:
         for case in ("R", "Z"):
             save(f"tiny_{m}_{case}.npz", tiny_case(m, case, sd))
         save(f"b32blk_{m}.npz", b32_block(m))
+    import json
+    with open(os.path.join(HERE, "surface.json"), "w") as fh:
+        json.dump({m: surface(m, sd) for m in METHODS}, fh, indent=0)
+    print("wrote surface.json")
 
 
 if __name__ == "__main__":

@@ -1,0 +1,90 @@
+#!/usr/bin/env python
+"""Turn the ncu captures in gpurun_out/ into the committed summaries under profiles/.
+
+    python tools/summarize_profiles.py r01
+
+Writes profiles/<round>_launches.csv (per-kernel totals of the launch list), profiles/<round>_ncu_kernels.csv
+(one row per --set full capture: duration, DRAM bytes, tensor-pipe %, L2->SM bytes, registers) and
+profiles/ncu_traffic.json (dram bytes per launch by kernel class, read by bench.py for roofline.traffic).
+"""
+import collections
+import csv
+import json
+import os
+import subprocess
+import sys
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+OUT = os.path.join(ROOT, "gpurun_out")
+PROF = os.path.join(ROOT, "profiles")
+METRICS = ["gpu__time_duration.sum", "dram__bytes_read.sum", "dram__bytes_write.sum",
+           "sm__pipe_tensor_cycles_active.avg.pct_of_peak_sustained_active",
+           "gpu__dram_throughput.avg.pct_of_peak_sustained_elapsed",
+           "lts__throughput.avg.pct_of_peak_sustained_elapsed", "l1tex__m_xbar2l1tex_read_bytes.sum",
+           "sm__warps_active.avg.pct_of_peak_sustained_active", "launch__registers_per_thread", "launch__grid_size",
+           "launch__block_size", "sm__throughput.avg.pct_of_peak_sustained_elapsed"]
+
+
+def launches(tag):
+    path = os.path.join(OUT, "launches.csv")
+    if not os.path.exists(path):
+        return
+    rows = [r for r in csv.reader(open(path)) if len(r) > 10 and r[0].isdigit()]
+    agg = collections.OrderedDict()
+    for r in rows:
+        name, val, unit = r[4], float(r[-1]), r[-2]
+        us = val / 1000.0 if unit.startswith("n") else val
+        a = agg.setdefault(name, [0, 0.0])
+        a[0] += 1
+        a[1] += us
+    tot = sum(v[1] for v in agg.values())
+    with open(os.path.join(PROF, f"{tag}_launches.csv"), "w", newline="") as fh:
+        w = csv.writer(fh)
+        w.writerow(["kernel", "launches", "total_us", "avg_us", "share_of_captured_time"])
+        for k, v in sorted(agg.items(), key=lambda kv: -kv[1][1]):
+            w.writerow([k, v[0], f"{v[1]:.1f}", f"{v[1] / v[0]:.2f}", f"{v[1] / tot:.4f}"])
+    print(f"launch list: {len(rows)} launches, {tot / 1e3:.2f} ms captured")
+
+
+def full_captures(tag):
+    out_rows, traffic = [], {}
+    for rep in sorted(f for f in os.listdir(OUT) if f.endswith(".ncu-rep")):
+        res = subprocess.run(["ncu", "-i", os.path.join(OUT, rep), "--page", "raw", "--csv"], capture_output=True, text=True)
+        rows = list(csv.reader(res.stdout.splitlines()))
+        if len(rows) < 3:
+            continue
+        hdr = rows[0]
+        for r in rows[2:]:
+            rec = {"report": rep, "kernel": r[hdr.index("Kernel Name")]}
+            for m in METRICS:
+                rec[m] = r[hdr.index(m)] if m in hdr else ""
+            out_rows.append(rec)
+    if not out_rows:
+        return
+    with open(os.path.join(PROF, f"{tag}_ncu_kernels.csv"), "w", newline="") as fh:
+        w = csv.DictWriter(fh, fieldnames=["report", "kernel"] + METRICS)
+        w.writeheader()
+        w.writerows(out_rows)
+    for rec in out_rows:  # dram traffic per launch, keyed like bench.py's kernel classes where unambiguous
+        try:
+            b = (float(rec["dram__bytes_read.sum"]) + float(rec["dram__bytes_write.sum"])) * 1e6
+        except ValueError:
+            continue
+        k = rec["kernel"]
+        if "attn_fwd_tc" in k:
+            traffic["attn_fwd"] = b
+        elif "attn_bwd_tc" in k:
+            traffic["attn_bwd"] = b
+    extra = os.path.join(OUT, "gemm_class_traffic.json")
+    if os.path.exists(extra):
+        traffic.update(json.load(open(extra)))
+    with open(os.path.join(PROF, "ncu_traffic.json"), "w") as fh:
+        json.dump(traffic, fh, indent=1, sort_keys=True)
+    print(f"full captures: {len(out_rows)} kernels")
+
+
+if __name__ == "__main__":
+    tag = sys.argv[1] if len(sys.argv) > 1 else "r01"
+    os.makedirs(PROF, exist_ok=True)
+    launches(tag)
+    full_captures(tag)
