@@ -27,6 +27,29 @@ def trainable_by_name(name: str, method: str) -> bool:
     return "adapter" in name or "phm_rule" in name or "attn.b" in name
 
 
+class FlatGrads:
+    """One flat fp32 buffer holding every trainable gradient; each ``p.grad`` is a view into it, so the
+    data-parallel exchange is ONE collective per step regardless of how many PEFT tensors there are."""
+
+    def __init__(self, params, device=None):
+        self.params = list(params)
+        device = device if device is not None else self.params[0].device
+        self.flat = torch.zeros(sum(p.numel() for p in self.params), dtype=torch.float32, device=device)
+        off = 0
+        for p in self.params:
+            p.grad = self.flat[off:off + p.numel()].view_as(p)
+            off += p.numel()
+
+    def zero_(self) -> None:
+        self.flat.zero_()
+
+    def all_reduce_mean(self, group=None) -> None:
+        world = dist.get_world_size(group)
+        if world > 1:
+            dist.all_reduce(self.flat, group=group)
+            self.flat.div_(world)
+
+
 class FineTuner(nn.Module):
     """Backbone (frozen CLIP visual tower + PEFT tensors) and a linear head, stepped with SGD(momentum)."""
 
@@ -56,12 +79,8 @@ class FineTuner(nn.Module):
         # F2: KAdaptation's v_proj_adapter1_* are trainable by name but never receive a gradient
         self.used = [p for n, p in self.named_parameters()
                      if p.requires_grad and not (method == "kadaptation" and "v_proj_adapter1_" in n)]
-        total = sum(p.numel() for p in self.used)
-        self.flat_grad = torch.zeros(total, dtype=torch.float32, device=device)
-        off = 0
-        for p in self.used:
-            p.grad = self.flat_grad[off:off + p.numel()].view_as(p)
-            off += p.numel()
+        self.grads = FlatGrads(self.used, device)
+        self.flat_grad = self.grads.flat
         self.opt = torch.optim.SGD(self.used, lr=lr, momentum=momentum, weight_decay=weight_decay)
 
     def forward(self, images: torch.Tensor) -> torch.Tensor:
@@ -69,12 +88,11 @@ class FineTuner(nn.Module):
 
     def step(self, images: torch.Tensor, labels: torch.Tensor) -> torch.Tensor:
         """One fine-tune step on this rank's local batch; returns the (device) loss."""
-        self.flat_grad.zero_()
+        self.grads.zero_()
         loss = F.cross_entropy(self.forward(images), labels)
         loss.backward()
-        if self.distributed and self.world > 1:
-            dist.all_reduce(self.flat_grad, group=self.group)
-            self.flat_grad.div_(self.world)
+        if self.distributed:
+            self.grads.all_reduce_mean(self.group)
         self.opt.step()
         return loss.detach()
 

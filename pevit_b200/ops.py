@@ -234,6 +234,17 @@ def block_forward(block, x: torch.Tensor, method: str, peft: tuple, attn_impl: i
         raise RuntimeError("pevit_b200 KAdaptation blocks support eval mode only (reference never calls .train())")
     if x.dim() != 3:
         raise ValueError(f"expected (L, N, D) input, got {tuple(x.shape)}")
+    if torch.is_grad_enabled():
+        a, m = block.attn, block.mlp
+        frozen = (a.in_proj_weight, a.in_proj_bias, a.out_proj.weight, a.out_proj.bias, m.c_fc.weight, m.c_fc.bias,
+                  m.c_proj.weight, m.c_proj.bias, block.ln_1.weight, block.ln_1.bias, block.ln_2.weight,
+                  block.ln_2.bias)
+        if any(p.requires_grad for p in frozen):
+            # the fused block computes activation gradients (dgrad) only; silently dropping weight gradients
+            # would be wrong, so full fine-tuning is refused (PEViT freezes the backbone by name).
+            raise RuntimeError("pevit_b200 blocks need a frozen backbone: set requires_grad=False on the base "
+                               "weights (the reference Classifier does, kadaptation_clip.py:104-122) or run under "
+                               "torch.no_grad()")
     pack = get_pack(block, method)
     return _BlockFn.apply(x, pack, attn_impl, *peft)
 
