@@ -184,8 +184,11 @@ size_t pevit_block_saved_bytes(const pevit_block_desc* desc);
 size_t pevit_block_workspace_bytes(const pevit_block_desc* desc);
 int pevit_block_fwd(const pevit_block_desc* desc, const pevit_block_weights* w, const float* x, float* y,
                     void* saved, void* workspace, void* stream);
+/* dy_bf16 (nullable in): bf16 copy of dy if the caller has one; dx_bf16 (nullable out): bf16 copy of dx, to be
+ * handed to the block below as its dy_bf16 (saves one cast pass per block). */
 int pevit_block_bwd(const pevit_block_desc* desc, const pevit_block_weights* w, const float* x, const float* dy,
-                    float* dx, const pevit_block_grads* grads, const void* saved, void* workspace, void* stream);
+                    const void* dy_bf16, float* dx, void* dx_bf16, const pevit_block_grads* grads, const void* saved,
+                    void* workspace, void* stream);
 
 #ifdef __cplusplus
 }

@@ -94,8 +94,8 @@ _SIGNATURES = {
     "pevit_block_saved_bytes": (c_size_t, [_P(BlockDesc)]),
     "pevit_block_workspace_bytes": (c_size_t, [_P(BlockDesc)]),
     "pevit_block_fwd": (c_int32, [_P(BlockDesc), _P(BlockWeights), c_void_p, c_void_p, c_void_p, c_void_p, c_void_p]),
-    "pevit_block_bwd": (c_int32, [_P(BlockDesc), _P(BlockWeights), c_void_p, c_void_p, c_void_p, _P(BlockGrads),
-                                  c_void_p, c_void_p, c_void_p]),
+    "pevit_block_bwd": (c_int32, [_P(BlockDesc), _P(BlockWeights), c_void_p, c_void_p, c_void_p, c_void_p, c_void_p,
+                                  _P(BlockGrads), c_void_p, c_void_p, c_void_p]),
 }
 EXPORTED = tuple(_SIGNATURES)
 

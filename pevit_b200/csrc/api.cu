@@ -217,7 +217,7 @@ int pevit_atb_tc(const void* a, int32_t lda, const void* b, int32_t ldb, int32_t
 }
 
 int pevit_colsum_bf16(const void* x, int32_t m, int32_t d, float* out, void* stream) {
-  return colsum_bf16(as_stream(stream), static_cast<const bf16*>(x), d, m, d, out);
+  return colsum_bf16(as_stream(stream), static_cast<const bf16*>(x), nullptr, d, m, d, out);
 }
 
 int pevit_kad_factor_grads(const float* dP, const float* dQ, const float* u1, const float* v1, const float* u2,
@@ -361,7 +361,8 @@ int pevit_block_fwd(const pevit_block_desc* desc, const pevit_block_weights* w, 
 // Backward: activation gradients flow through every frozen GEMM (dgrad only);
 // weight gradients exist only for the PEFT tensors.
 int pevit_block_bwd(const pevit_block_desc* desc, const pevit_block_weights* w, const float* x, const float* dy,
-                    float* dx, const pevit_block_grads* g, const void* saved, void* workspace, void* stream) {
+                    const void* dy_bf16, float* dx, void* dx_bf16, const pevit_block_grads* g, const void* saved,
+                    void* workspace, void* stream) {
   TRY(check_desc(desc));
   PEVIT_REQUIRE(w && x && dy && g && saved && workspace && (dx || !desc->need_dx),
                 "pevit_block_bwd: null pointer argument");
@@ -372,22 +373,27 @@ int pevit_block_bwd(const pevit_block_desc* desc, const pevit_block_weights* w, 
   Work wk = carve_work(d, workspace);
   const size_t plane = static_cast<size_t>(M) * D;
 
-  TRY(cast_f32_to_bf16(s, dy, wk.dy_bf16, plane));
-  const bf16* dmlp_bf16 = wk.dy_bf16;  // gradient w.r.t. the MLP output m
+  // bf16 copy of dy (A operand of the first dgrad GEMM): handed over by the block above when it produced one
+  const bf16* dyb = static_cast<const bf16*>(dy_bf16);
+  if (dyb == nullptr) {
+    TRY(cast_f32_to_bf16(s, dy, wk.dy_bf16, plane));
+    dyb = wk.dy_bf16;
+  }
+  const bf16* dmlp_bf16 = dyb;  // gradient w.r.t. the MLP output m
   if (has_bottleneck(d)) {
     const int act = d.method == PEVIT_ADAPTER ? ACT_RELU : ACT_GELU_NEW;
     // up projection: dW_up = dy^T u, db_up = colsum(dy), du = dy W_up, dzd = du * act'(zd)
-    if (g->d_w_up) TRY(atb_tc(s, wk.dy_bf16, D, sv.u, 64, 64, M, D, 0, 64, 1.f, g->d_w_up, 64));
-    if (g->d_b_up) TRY(colsum_bf16(s, wk.dy_bf16, D, M, D, g->d_b_up));
+    if (g->d_w_up) TRY(atb_tc(s, dyb, D, sv.u, 64, 64, M, D, 0, 64, 1.f, g->d_w_up, 64));
+    if (g->d_b_up) TRY(colsum_bf16(s, dyb, nullptr, D, M, D, g->d_b_up));
     {
       GemmEpilogue ep;
       ep.out_bf16 = wk.dzd; ep.aux_bf16 = sv.zd; ep.ld_out = 64; ep.act = act;
       prof_set_tag(PC_GEMM_BOTTLENECK);
-      TRY(gemm_tn(s, wk.dy_bf16, D, static_cast<const bf16*>(w->w_up_t), D, M, 64, D, EPI_DACT, ep));
+      TRY(gemm_tn(s, dyb, D, static_cast<const bf16*>(w->w_up_t), D, M, 64, D, EPI_DACT, ep));
     }
     // down projection: dW_down^T = a_n^T dzd, db_down = colsum(dzd), da_n = dzd W_down
     if (g->d_w_down) TRY(atb_tc(s, sv.a_n, D, wk.dzd, 64, 64, M, D, 0, 64, 1.f, g->d_w_down, 64));
-    if (g->d_b_down) TRY(colsum_bf16(s, wk.dzd, 64, M, 64, g->d_b_down));
+    if (g->d_b_down) TRY(colsum_bf16(s, wk.dzd, nullptr, 64, M, 64, g->d_b_down));
     {
       GemmEpilogue ep;
       ep.out_f32 = wk.dxn; ep.ld_out = D;
@@ -443,8 +449,8 @@ int pevit_block_bwd(const pevit_block_desc* desc, const pevit_block_weights* w, 
       // dQ = alpha * dDelta^T T
       if (g->d_qmat)
         TRY(atb_tc(s, dd, D, sv.T, r2, r2, M, D, which * r, r, d.alpha, g->d_qmat + static_cast<size_t>(which) * D * r, r));
-      if (d.method == PEVIT_KADAPTATION && g->d_bias) TRY(colsum_bf16(s, dd, D, M, D, g->d_bias));
     }
+    if (d.method == PEVIT_KADAPTATION && g->d_bias) TRY(colsum_bf16(s, wk.ddelta, wk.ddelta + plane, D, M, D, g->d_bias));
     // dP = X^T dT  ([D][2r], q | v)
     if (g->d_pmat) TRY(atb_tc(s, sv.xn1, D, wk.dqkv + 3 * D, W3, r2, M, D, 0, r2, 1.f, g->d_pmat, r2));
   }
@@ -457,7 +463,8 @@ int pevit_block_bwd(const pevit_block_desc* desc, const pevit_block_weights* w, 
     TRY(gemm_tn(s, wk.dqkv, W3, static_cast<const bf16*>(w->w_qkv_ext_t), W3, M, D, W3, EPI_F32, ep));
   }
   // ln_1 backward + residual path
-  TRY(layernorm_bwd(s, wk.dxn, x, w->ln1_g, sv.mean1, sv.rstd1, wk.dx1, dx, nullptr, nullptr, nullptr, M, D));
+  TRY(layernorm_bwd(s, wk.dxn, x, w->ln1_g, sv.mean1, sv.rstd1, wk.dx1, dx, static_cast<bf16*>(dx_bf16), nullptr, nullptr,
+                    M, D));
   return 0;
 }
 

@@ -18,7 +18,7 @@ constexpr int ATB_SMEM = ATB_STAGES * ATB_STAGE_BYTES + 128 + 1024;
 constexpr int ATB_THREADS = 192;
 
 struct AtbParams {
-  int M, Kc, n_lo, n_cnt, ldc, rows_per_split;
+  int M, Kc, n_lo, n_cnt, ldc, rows_per_split, vec4;
   float scale;
   float* C;
 };
@@ -95,10 +95,22 @@ atb_tc_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant__ 
         tmem_ld_wait();
         if (kc < p.Kc) {
           float* crow = p.C + static_cast<size_t>(kc) * p.ldc;
+          if (p.vec4) {  // 16-byte vector reductions: window and row stride are multiples of 4 floats
 #pragma unroll
-          for (int j = 0; j < 32; ++j) {
-            const int n = c + j - p.n_lo;
-            if (n >= 0 && n < p.n_cnt) atomicAdd(crow + n, p.scale * __uint_as_float(v[j]));
+            for (int j = 0; j < 32; j += 4) {
+              const int n = c + j - p.n_lo;
+              if (n >= 0 && n < p.n_cnt)
+                asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(crow + n),
+                             "f"(p.scale * __uint_as_float(v[j])), "f"(p.scale * __uint_as_float(v[j + 1])),
+                             "f"(p.scale * __uint_as_float(v[j + 2])), "f"(p.scale * __uint_as_float(v[j + 3]))
+                             : "memory");
+            }
+          } else {
+#pragma unroll
+            for (int j = 0; j < 32; ++j) {
+              const int n = c + j - p.n_lo;
+              if (n >= 0 && n < p.n_cnt) atomicAdd(crow + n, p.scale * __uint_as_float(v[j]));
+            }
           }
         }
       }
@@ -127,11 +139,12 @@ int atb_tc(cudaStream_t s, const bf16* A, int lda, const bf16* B, int ldb, int n
   if (make_tmap_bf16_2d(&ta, A, M, Kc, lda, ATB_BK, 64) != 0) return -1;
   if (make_tmap_bf16_2d(&tb, B, M, nb_cols, ldb, ATB_BK, 64) != 0) return -1;
   const int gx = (Kc + 127) / 128;
-  int splits = (2 * sm_count() + gx - 1) / gx;
+  int splits = (sm_count() + gx - 1) / gx;  // ~one CTA per SM: fewer partial tiles to reduce with atomics
   int rps = (M + splits - 1) / splits;
   rps = ((rps + ATB_BK - 1) / ATB_BK) * ATB_BK;
   splits = (M + rps - 1) / rps;
-  AtbParams p{M, Kc, n_lo, n_cnt, ldc, rps, scale, C};
+  const int vec4 = (n_lo % 4 == 0 && n_cnt % 4 == 0 && ldc % 4 == 0 && (reinterpret_cast<uintptr_t>(C) & 15) == 0) ? 1 : 0;
+  AtbParams p{M, Kc, n_lo, n_cnt, ldc, rps, vec4, scale, C};
   static bool configured[64] = {};
   int dev = 0;
   PEVIT_CHECK_CUDA(cudaGetDevice(&dev));

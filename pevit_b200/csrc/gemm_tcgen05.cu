@@ -217,9 +217,42 @@ __device__ __forceinline__ void epilogue_chunk(const GemmEpilogue& ep, int m, in
   }
 }
 
-// Staged epilogue: final values of one 32-column chunk (second output z for EPI_ACT).  Requires N % 32 == 0.
+// Staged epilogue.  The per-row residual / auxiliary operands of a 32-column chunk are fetched one chunk
+// ahead (EpiAux) so their L2 latency overlaps the previous chunk's math instead of serialising with it.
+struct EpiAux {
+  uint4 r[16];  // EPI_F32: resid (8) + resid2 (8) as float4 bits; EPI_BF16 / EPI_DACT: 4 x uint4 of bf16
+};
+
 template <int EPI>
-__device__ __forceinline__ void epilogue_values(const GemmEpilogue& ep, int m, int c0, bool row_ok, uint32_t (&v)[32],
+__device__ __forceinline__ void epilogue_prefetch(const GemmEpilogue& ep, int m, int c0, bool ok, EpiAux& x) {
+  const size_t off = static_cast<size_t>(m) * ep.ld_out + c0;
+  if constexpr (epi_base(EPI) == EPI_F32) {
+    if (ep.resid != nullptr) {
+#pragma unroll
+      for (int q = 0; q < 8; ++q)
+        x.r[q] = ok ? *reinterpret_cast<const uint4*>(ep.resid + off + 4 * q) : make_uint4(0, 0, 0, 0);
+    }
+    if (ep.resid2 != nullptr) {
+#pragma unroll
+      for (int q = 0; q < 8; ++q)
+        x.r[8 + q] = ok ? *reinterpret_cast<const uint4*>(ep.resid2 + off + 4 * q) : make_uint4(0, 0, 0, 0);
+    }
+  } else if constexpr (epi_base(EPI) == EPI_BF16) {
+    if (ep.resid_bf16 != nullptr) {
+#pragma unroll
+      for (int q = 0; q < 4; ++q)
+        x.r[q] = ok ? *reinterpret_cast<const uint4*>(ep.resid_bf16 + off + 8 * q) : make_uint4(0, 0, 0, 0);
+    }
+  } else if constexpr (epi_base(EPI) == EPI_DACT) {
+#pragma unroll
+    for (int q = 0; q < 4; ++q)
+      x.r[q] = ok ? *reinterpret_cast<const uint4*>(ep.aux_bf16 + off + 8 * q) : make_uint4(0, 0, 0, 0);
+  }
+}
+
+// final values of one 32-column chunk (second output z for EPI_ACT).  Requires N % 32 == 0.
+template <int EPI>
+__device__ __forceinline__ void epilogue_values(const GemmEpilogue& ep, int c0, const EpiAux& x, uint32_t (&v)[32],
                                                 float (&a)[32], float (&z)[32]) {
 #pragma unroll
   for (int j = 0; j < 32; ++j) a[j] = __uint_as_float(v[j]);
@@ -230,33 +263,31 @@ __device__ __forceinline__ void epilogue_values(const GemmEpilogue& ep, int m, i
       a[j] += b.x; a[j + 1] += b.y; a[j + 2] += b.z; a[j + 3] += b.w;
     }
   }
-  const size_t off = static_cast<size_t>(m) * ep.ld_out + c0;
   if constexpr (epi_base(EPI) == EPI_F32) {
-    if (row_ok && ep.resid != nullptr) {
+    if (ep.resid != nullptr) {
 #pragma unroll
-      for (int j = 0; j < 32; j += 4) {
-        const float4 r = *reinterpret_cast<const float4*>(ep.resid + off + j);
-        a[j] += r.x; a[j + 1] += r.y; a[j + 2] += r.z; a[j + 3] += r.w;
+      for (int q = 0; q < 8; ++q) {
+        a[4 * q] += __uint_as_float(x.r[q].x); a[4 * q + 1] += __uint_as_float(x.r[q].y);
+        a[4 * q + 2] += __uint_as_float(x.r[q].z); a[4 * q + 3] += __uint_as_float(x.r[q].w);
       }
     }
-    if (row_ok && ep.resid2 != nullptr) {
+    if (ep.resid2 != nullptr) {
 #pragma unroll
-      for (int j = 0; j < 32; j += 4) {
-        const float4 r = *reinterpret_cast<const float4*>(ep.resid2 + off + j);
-        a[j] += r.x; a[j + 1] += r.y; a[j + 2] += r.z; a[j + 3] += r.w;
+      for (int q = 0; q < 8; ++q) {
+        a[4 * q] += __uint_as_float(x.r[8 + q].x); a[4 * q + 1] += __uint_as_float(x.r[8 + q].y);
+        a[4 * q + 2] += __uint_as_float(x.r[8 + q].z); a[4 * q + 3] += __uint_as_float(x.r[8 + q].w);
       }
     }
   } else if constexpr (epi_base(EPI) == EPI_BF16) {
-    if (row_ok && ep.resid_bf16 != nullptr) {
+    if (ep.resid_bf16 != nullptr) {
 #pragma unroll
-      for (int j = 0; j < 32; j += 8) {
-        const uint4 rr = *reinterpret_cast<const uint4*>(ep.resid_bf16 + off + j);
-        const uint32_t rw[4] = {rr.x, rr.y, rr.z, rr.w};
+      for (int q = 0; q < 4; ++q) {
+        const uint32_t rw[4] = {x.r[q].x, x.r[q].y, x.r[q].z, x.r[q].w};
 #pragma unroll
         for (int t = 0; t < 4; ++t) {
           const float2 f = unpack_bf16(rw[t]);
-          a[j + 2 * t] += f.x;
-          a[j + 2 * t + 1] += f.y;
+          a[8 * q + 2 * t] += f.x;
+          a[8 * q + 2 * t + 1] += f.y;
         }
       }
     }
@@ -264,17 +295,14 @@ __device__ __forceinline__ void epilogue_values(const GemmEpilogue& ep, int m, i
 #pragma unroll
     for (int j = 0; j < 32; ++j) { z[j] = a[j]; a[j] = act_fwd<epi_act(EPI)>(a[j]); }
   } else if constexpr (epi_base(EPI) == EPI_DACT) {
-    if (row_ok) {
 #pragma unroll
-      for (int j = 0; j < 32; j += 8) {
-        const uint4 zz = *reinterpret_cast<const uint4*>(ep.aux_bf16 + off + j);
-        const uint32_t zw[4] = {zz.x, zz.y, zz.z, zz.w};
+    for (int q = 0; q < 4; ++q) {
+      const uint32_t zw[4] = {x.r[q].x, x.r[q].y, x.r[q].z, x.r[q].w};
 #pragma unroll
-        for (int t = 0; t < 4; ++t) {
-          const float2 f = unpack_bf16(zw[t]);
-          a[j + 2 * t] *= act_bwd<epi_act(EPI)>(f.x);
-          a[j + 2 * t + 1] *= act_bwd<epi_act(EPI)>(f.y);
-        }
+      for (int t = 0; t < 4; ++t) {
+        const float2 f = unpack_bf16(zw[t]);
+        a[8 * q + 2 * t] *= act_bwd<epi_act(EPI)>(f.x);
+        a[8 * q + 2 * t + 1] *= act_bwd<epi_act(EPI)>(f.y);
       }
     }
   }
@@ -420,14 +448,18 @@ gemm_tn_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
         const int m0 = (tile / tiles_n) * BM;
         const bool elected = (threadIdx.x == 64);
         const bool two = kTwo && ep.out2_bf16 != nullptr;
+        EpiAux aux_cur, aux_next;
+        epilogue_prefetch<EPI>(ep, m, n0, m < M && n0 < N, aux_cur);
 #pragma unroll 1
         for (int c = 0; c < BN; c += 32) {
           uint32_t v[32];
           tmem_ld_32x32(t_row + c, v);
+          epilogue_prefetch<EPI>(ep, m, n0 + c + 32, m < M && c + 32 < BN && n0 + c + 32 < N, aux_next);
           tmem_ld_wait();
           if (n0 + c >= N) continue;                       // warp-uniform (N % 32 == 0)
           float a[32], z[32];
-          epilogue_values<EPI>(ep, m, n0 + c, m < M, v, a, z);
+          epilogue_values<EPI>(ep, n0 + c, aux_cur, v, a, z);
+          aux_cur = aux_next;
           const int sub = kF32 ? 0 : ((c >> 5) & 1);
           const int buf = kTwo ? 0 : (box_count & 1);
           if (sub == 0) {  // opening a box: its previous TMA store must have finished reading shared memory

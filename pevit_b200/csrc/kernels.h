@@ -83,8 +83,9 @@ int atb_accumulate(cudaStream_t s, const void* A, int a_is_bf16, int lda, const 
 // B exposes nb_cols (<= 64) columns; columns [n_lo, n_lo+n_cnt) of A^T B go to C[kc][0..n_cnt) (row stride ldc).
 int atb_tc(cudaStream_t s, const bf16* A, int lda, const bf16* B, int ldb, int nb_cols, int M, int Kc, int n_lo,
            int n_cnt, float scale, float* C, int ldc);
-// column sums of a bf16 [M][ld] matrix (first D columns), atomically accumulated into out[D] (caller zeroes).
-int colsum_bf16(cudaStream_t s, const bf16* X, int ld, int M, int D, float* out);
+// column sums of one or two (X1 nullable) bf16 [M][ld] matrices (first D columns), atomically accumulated into
+// out[D] (caller zeroes).
+int colsum_bf16(cudaStream_t s, const bf16* X0, const bf16* X1, int ld, int M, int D, float* out);
 // KAdaptation factor gradients from dP [D][64] (q|v) and dQ [2][D][32].
 int kad_factor_grads(cudaStream_t s, const float* dP, const float* dQ, const float* u1, const float* v1, const float* u2,
                      const float* v2, const float* sfac, const float* tfac, int D, float* du1, float* dv1, float* du2,

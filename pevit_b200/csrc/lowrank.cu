@@ -116,52 +116,97 @@ atb_kernel(const TA* __restrict__ A, int lda, const TB* __restrict__ B, int ldb,
   }
 }
 
-__global__ void colsum_bf16_kernel(const bf16* __restrict__ X, int ld, int M, int D, float* __restrict__ out,
-                                   int rows_per_cta) {
+// out[c] += sum_m X0[m][c] (+ X1[m][c]).  Thread = 8 columns (one 16-byte load) x a strided slice of rows;
+// the 8 row-lanes of a block are reduced through shared memory, then one atomic per column per block.
+constexpr int CS_COLG = 32, CS_ROWL = 8;  // 32 column groups x 8 row lanes = 256 threads
+__global__ void __launch_bounds__(CS_COLG* CS_ROWL)
+colsum_bf16_kernel(const bf16* __restrict__ X0, const bf16* __restrict__ X1, int ld, int M, int D,
+                   float* __restrict__ out, int rows_per_cta) {
+  __shared__ float red[CS_ROWL][CS_COLG * 8 + 1];
+  const int cg = threadIdx.x % CS_COLG, rl = threadIdx.x / CS_COLG;
+  const int c0 = (blockIdx.x * CS_COLG + cg) * 8;
   const int m_begin = blockIdx.y * rows_per_cta;
   const int m_end = min(M, m_begin + rows_per_cta);
-  const int c = blockIdx.x * blockDim.x + threadIdx.x;
-  if (c >= D) return;
-  float acc = 0.f;
-  for (int m = m_begin; m < m_end; ++m) acc += __bfloat162float(X[static_cast<size_t>(m) * ld + c]);
-  atomicAdd(out + c, acc);
+  float acc[8];
+#pragma unroll
+  for (int j = 0; j < 8; ++j) acc[j] = 0.f;
+  if (c0 + 8 <= D) {
+    for (int m = m_begin + rl; m < m_end; m += CS_ROWL) {
+      const uint4 a = *reinterpret_cast<const uint4*>(X0 + static_cast<size_t>(m) * ld + c0);
+      const uint32_t w[4] = {a.x, a.y, a.z, a.w};
+#pragma unroll
+      for (int t = 0; t < 4; ++t) { const float2 f = unpack_bf16(w[t]); acc[2 * t] += f.x; acc[2 * t + 1] += f.y; }
+      if (X1 != nullptr) {
+        const uint4 b = *reinterpret_cast<const uint4*>(X1 + static_cast<size_t>(m) * ld + c0);
+        const uint32_t u[4] = {b.x, b.y, b.z, b.w};
+#pragma unroll
+        for (int t = 0; t < 4; ++t) { const float2 f = unpack_bf16(u[t]); acc[2 * t] += f.x; acc[2 * t + 1] += f.y; }
+      }
+    }
+  } else {
+    for (int j = 0; j < 8; ++j)
+      if (c0 + j < D)
+        for (int m = m_begin + rl; m < m_end; m += CS_ROWL) {
+          acc[j] += __bfloat162float(X0[static_cast<size_t>(m) * ld + c0 + j]);
+          if (X1 != nullptr) acc[j] += __bfloat162float(X1[static_cast<size_t>(m) * ld + c0 + j]);
+        }
+  }
+#pragma unroll
+  for (int j = 0; j < 8; ++j) red[rl][cg * 8 + j] = acc[j];
+  __syncthreads();
+  for (int c = threadIdx.x; c < CS_COLG * 8; c += blockDim.x) {
+    float t = 0.f;
+#pragma unroll
+    for (int r = 0; r < CS_ROWL; ++r) t += red[r][c];
+    const int col = blockIdx.x * CS_COLG * 8 + c;
+    if (col < D) atomicAdd(out + col, t);
+  }
 }
 
-// one CTA per Kronecker term i.  dP [D][64] (q | v), dQ [2][D][32].
-__global__ void kad_factor_grads_kernel(const float* __restrict__ dP, const float* __restrict__ dQ,
-                                        const float* __restrict__ u1, const float* __restrict__ v1,
-                                        const float* __restrict__ u2, const float* __restrict__ v2,
-                                        const float* __restrict__ sf, const float* __restrict__ tf, int D,
-                                        float* __restrict__ du1, float* __restrict__ dv1, float* __restrict__ du2,
-                                        float* __restrict__ dv2, float* __restrict__ dsf, float* __restrict__ dtf) {
+// one CTA per Kronecker term i.  dP [D][64] (q | v), dQ [2][D][32].  Column i of dP / dQ is staged in shared
+// memory first (all loads independent), then the 4*32 + 2*F small dot products run out of shared memory.
+__global__ void __launch_bounds__(256)
+kad_factor_grads_kernel(const float* __restrict__ dP, const float* __restrict__ dQ, const float* __restrict__ u1,
+                        const float* __restrict__ v1, const float* __restrict__ u2, const float* __restrict__ v2,
+                        const float* __restrict__ sf, const float* __restrict__ tf, int D, float* __restrict__ du1,
+                        float* __restrict__ dv1, float* __restrict__ du2, float* __restrict__ dv2,
+                        float* __restrict__ dsf, float* __restrict__ dtf) {
+  extern __shared__ float sm[];  // [4][D]: dPq, dPv, dQq, dQv columns i; then s, t, u1, u2, v1, v2 rows i
   const int i = blockIdx.x;
   const int F = D / 32;
-  // du*[i][a] and dv*[i][a]: a < 32
-  for (int a = threadIdx.x; a < 32; a += blockDim.x) {
-    float gu1 = 0.f, gu2 = 0.f, gv1 = 0.f, gv2 = 0.f;
-    for (int k = 0; k < F; ++k) {
-      const int col = a * F + k;
-      const float s = sf[i * F + k], t = tf[i * F + k];
-      gu1 = fmaf(dP[static_cast<size_t>(col) * 64 + i], s, gu1);
-      gu2 = fmaf(dP[static_cast<size_t>(col) * 64 + 32 + i], s, gu2);
-      gv1 = fmaf(dQ[static_cast<size_t>(col) * 32 + i], t, gv1);
-      gv2 = fmaf(dQ[static_cast<size_t>(D + col) * 32 + i], t, gv2);
-    }
-    du1[i * 32 + a] = gu1; du2[i * 32 + a] = gu2;
-    dv1[i * 32 + a] = gv1; dv2[i * 32 + a] = gv2;
+  float* cPq = sm; float* cPv = sm + D; float* cQq = sm + 2 * D; float* cQv = sm + 3 * D;
+  float* ss = sm + 4 * D; float* tt = ss + F; float* a1 = tt + F; float* a2 = a1 + 32; float* b1 = a2 + 32; float* b2 = b1 + 32;
+  for (int c = threadIdx.x; c < D; c += blockDim.x) {
+    cPq[c] = dP[static_cast<size_t>(c) * 64 + i];
+    cPv[c] = dP[static_cast<size_t>(c) * 64 + 32 + i];
+    cQq[c] = dQ[static_cast<size_t>(c) * 32 + i];
+    cQv[c] = dQ[static_cast<size_t>(D + c) * 32 + i];
   }
-  // ds[i][k], dt[i][k]: k < F  (s and t are shared by the q and v branches -- F2)
-  for (int k = threadIdx.x; k < F; k += blockDim.x) {
-    float gs = 0.f, gt = 0.f;
-    for (int a = 0; a < 32; ++a) {
-      const int col = a * F + k;
-      gs = fmaf(dP[static_cast<size_t>(col) * 64 + i], u1[i * 32 + a], gs);
-      gs = fmaf(dP[static_cast<size_t>(col) * 64 + 32 + i], u2[i * 32 + a], gs);
-      gt = fmaf(dQ[static_cast<size_t>(col) * 32 + i], v1[i * 32 + a], gt);
-      gt = fmaf(dQ[static_cast<size_t>(D + col) * 32 + i], v2[i * 32 + a], gt);
+  for (int k = threadIdx.x; k < F; k += blockDim.x) { ss[k] = sf[i * F + k]; tt[k] = tf[i * F + k]; }
+  if (threadIdx.x < 32) {
+    a1[threadIdx.x] = u1[i * 32 + threadIdx.x]; a2[threadIdx.x] = u2[i * 32 + threadIdx.x];
+    b1[threadIdx.x] = v1[i * 32 + threadIdx.x]; b2[threadIdx.x] = v2[i * 32 + threadIdx.x];
+  }
+  __syncthreads();
+  // outputs 0..127: du1, du2, dv1, dv2 [a]; 128..128+2F: ds[k], dt[k]   (s and t are shared by q and v -- F2)
+  for (int o = threadIdx.x; o < 128 + 2 * F; o += blockDim.x) {
+    float g = 0.f;
+    if (o < 128) {
+      const int which = o >> 5, a = o & 31;
+      const float* col = which == 0 ? cPq : (which == 1 ? cPv : (which == 2 ? cQq : cQv));
+      const float* fac = which < 2 ? ss : tt;
+      for (int k = 0; k < F; ++k) g = fmaf(col[a * F + k], fac[k], g);
+      float* dst = which == 0 ? du1 : (which == 1 ? du2 : (which == 2 ? dv1 : dv2));
+      dst[i * 32 + a] = g;
+    } else if (o < 128 + F) {
+      const int k = o - 128;
+      for (int a = 0; a < 32; ++a) g = fmaf(cPq[a * F + k], a1[a], fmaf(cPv[a * F + k], a2[a], g));
+      dsf[i * F + k] = g;
+    } else {
+      const int k = o - 128 - F;
+      for (int a = 0; a < 32; ++a) g = fmaf(cQq[a * F + k], b1[a], fmaf(cQv[a * F + k], b2[a], g));
+      dtf[i * F + k] = g;
     }
-    dsf[i * F + k] = gs;
-    dtf[i * F + k] = gt;
   }
 }
 
@@ -246,13 +291,16 @@ int atb_accumulate(cudaStream_t s, const void* A, int a_is_bf16, int lda, const 
   return 0;
 }
 
-int colsum_bf16(cudaStream_t s, const bf16* X, int ld, int M, int D, float* out) {
-  const int gx = (D + 255) / 256;
-  int splits = (sm_count() * 4 + gx - 1) / gx;
-  const int rows_per_cta = (M + splits - 1) / splits;
+int colsum_bf16(cudaStream_t s, const bf16* X0, const bf16* X1, int ld, int M, int D, float* out) {
+  PEVIT_REQUIRE(ld % 8 == 0 && (reinterpret_cast<uintptr_t>(X0) & 15) == 0 && (reinterpret_cast<uintptr_t>(X1) & 15) == 0,
+                "colsum_bf16: rows must be 16-byte aligned (ld=%d)", ld);
+  const int gx = (D + CS_COLG * 8 - 1) / (CS_COLG * 8);
+  int splits = (sm_count() * 2 + gx - 1) / gx;
+  int rows_per_cta = (M + splits - 1) / splits;
+  if (rows_per_cta < CS_ROWL) rows_per_cta = CS_ROWL;
   splits = (M + rows_per_cta - 1) / rows_per_cta;
   ProfScope prof(s, PC_COLSUM);
-  colsum_bf16_kernel<<<dim3(gx, splits), 256, 0, s>>>(X, ld, M, D, out, rows_per_cta);
+  colsum_bf16_kernel<<<dim3(gx, splits), CS_COLG * CS_ROWL, 0, s>>>(X0, X1, ld, M, D, out, rows_per_cta);
   PEVIT_CHECK_LAUNCH();
   return 0;
 }
@@ -261,7 +309,8 @@ int kad_factor_grads(cudaStream_t s, const float* dP, const float* dQ, const flo
                      const float* v2, const float* sfac, const float* tfac, int D, float* du1, float* dv1, float* du2,
                      float* dv2, float* dsfac, float* dtfac) {
   ProfScope prof(s, PC_FACTOR_GRADS);
-  kad_factor_grads_kernel<<<32, 64, 0, s>>>(dP, dQ, u1, v1, u2, v2, sfac, tfac, D, du1, dv1, du2, dv2, dsfac, dtfac);
+  const size_t smem = (4 * static_cast<size_t>(D) + 2 * (D / 32) + 128) * sizeof(float);
+  kad_factor_grads_kernel<<<32, 256, smem, s>>>(dP, dQ, u1, v1, u2, v2, sfac, tfac, D, du1, dv1, du2, dv2, dsfac, dtfac);
   PEVIT_CHECK_LAUNCH();
   return 0;
 }

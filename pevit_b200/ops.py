@@ -38,6 +38,9 @@ def _f32c(t: torch.Tensor) -> torch.Tensor:
 
 
 _workspace: Dict[Tuple[int, int], torch.Tensor] = {}
+# bf16 shadow of the most recent block input-gradient: (data_ptr, version, shape) of the fp32 dx -> bf16 copy.
+# The block below receives that very tensor as its dy, so it can skip re-casting it (one slot is enough).
+_dx_shadow: list = [None]
 
 
 def workspace(device: torch.device, nbytes: int) -> torch.Tensor:
@@ -190,6 +193,11 @@ class _BlockFn(torch.autograd.Function):
         dy = _f32c(dy)
         f32 = dict(dtype=torch.float32, device=dev)
         dx = torch.empty_like(x) if desc.need_dx else None
+        dx16 = torch.empty(x.shape, dtype=torch.bfloat16, device=dev) if desc.need_dx else None
+        shadow, _dx_shadow[0] = _dx_shadow[0], None
+        dy16 = None
+        if shadow is not None and shadow[0] == (dy.data_ptr(), dy._version, tuple(dy.shape)):
+            dy16 = shadow[1]
         g = L.BlockGrads()
         delta_bias = lna = b_down = b_up = None
         if method in ("kadaptation", "lora"):
@@ -209,8 +217,10 @@ class _BlockFn(torch.autograd.Function):
             g.d_w_down, g.d_b_down, g.d_w_up, g.d_b_up = _ptr(d_w_down_t), _ptr(d_b_down), _ptr(d_w_up), _ptr(d_b_up)
         w = pack.weights_struct(delta_bias, lna, b_down, b_up)
         ws = workspace(dev, lib.pevit_block_workspace_bytes(C.byref(desc)))
-        L.check(lib.pevit_block_bwd(C.byref(desc), C.byref(w), _ptr(x), _ptr(dy), _ptr(dx), C.byref(g), _ptr(saved),
-                                    _ptr(ws), st), "pevit_block_bwd")
+        L.check(lib.pevit_block_bwd(C.byref(desc), C.byref(w), _ptr(x), _ptr(dy), _ptr(dy16), _ptr(dx), _ptr(dx16),
+                                    C.byref(g), _ptr(saved), _ptr(ws), st), "pevit_block_bwd")
+        if dx is not None:
+            _dx_shadow[0] = ((dx.data_ptr(), dx._version, tuple(dx.shape)), dx16)
         if method == "kadaptation":
             u1, v1, u2, v2, s, t, _ = peft_c
             outs = [torch.empty_like(p) for p in (u1, v1, u2, v2, s, t)]
