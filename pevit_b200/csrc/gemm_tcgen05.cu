@@ -21,11 +21,11 @@ constexpr int GEMM_THREADS = 192;
 
 template <int BN>
 struct TileCfg {
-  static constexpr int STAGES = BN >= 256 ? 4 : (BN >= 128 ? 6 : 8);
+  static constexpr int STAGES = BN >= 256 ? 4 : (BN >= 192 ? 4 : (BN >= 128 ? 6 : 8));
   static constexpr int A_BYTES = BM * BK * 2;
   static constexpr int B_BYTES = BN * BK * 2;
   static constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
-  static constexpr int TMEM_COLS = 2 * BN < 32 ? 32 : 2 * BN;  // two accumulator stages
+  static constexpr int TMEM_COLS = 2 * BN <= 32 ? 32 : (2 * BN <= 64 ? 64 : (2 * BN <= 128 ? 128 : (2 * BN <= 256 ? 256 : 512)));  // two accumulator stages, power of two
   static constexpr int STAGING_BYTES = 2 * 16384;  // two [128 rows][128 B] TMA-store boxes
   static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + STAGING_BYTES + 256 + 1024;  // + barriers + align slack
 };
@@ -550,18 +550,18 @@ int dispatch_epi(int epi, bool ts, cudaStream_t s, const CUtensorMap& ta, const 
 
 int pick_bn(int M, int N, int forced) {
   if (forced < 0) forced = -forced;  // negative: same tile width, direct-store epilogue (cross-check)
-  if (forced == 32 || forced == 64 || forced == 128 || forced == 256) return forced;
+  if (forced == 32 || forced == 64 || forced == 128 || forced == 192 || forced == 256) return forced;
   if (N <= 32) return 32;
   if (N <= 64) return 64;
-  // fewest waves wins; ties go to the wider tile (more operand reuse per byte staged)
+  // wave count x bytes staged per tile; ties go to the wider tile (more operand reuse per byte staged)
   const int sms = sm_count();
   const int tm = (M + BM - 1) / BM;
   int best = 256;
   double best_cost = 1e30;
-  for (int bn : {256, 128, 64}) {
+  for (int bn : {256, 192, 128, 64}) {
     const int tiles = tm * ((N + bn - 1) / bn);
     const int waves = (tiles + sms - 1) / sms;
-    const double cost = static_cast<double>(waves) * (bn + 24);  // + fixed per-tile pipeline fill
+    const double cost = static_cast<double>(waves) * (BM + bn);  // tiles are operand-fetch (L2 -> SM) bound
     if (cost < best_cost - 1e-9) { best_cost = cost; best = bn; }
   }
   return best;
@@ -605,6 +605,7 @@ int gemm_tn(cudaStream_t stream, const bf16* A, int lda, const bf16* B, int ldb,
     case 32: return dispatch_epi<32>(epi, ts, stream, ta, tb, tc, tc2, M, N, K, ep);
     case 64: return dispatch_epi<64>(epi, ts, stream, ta, tb, tc, tc2, M, N, K, ep);
     case 128: return dispatch_epi<128>(epi, ts, stream, ta, tb, tc, tc2, M, N, K, ep);
+    case 192: return dispatch_epi<192>(epi, ts, stream, ta, tb, tc, tc2, M, N, K, ep);
     default: return dispatch_epi<256>(epi, ts, stream, ta, tb, tc, tc2, M, N, K, ep);
   }
 }
