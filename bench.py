@@ -114,8 +114,19 @@ class ClockSampler:
 
 
 # ----------------------------------------------------------------------------- CPU arm (oracle)
+def use_all_host_threads() -> int:
+    """torchrun exports OMP_NUM_THREADS=1; the CPU arm is meant to use every core it may run on."""
+    try:
+        n = len(os.sched_getaffinity(0))
+    except AttributeError:
+        n = os.cpu_count() or 1
+    torch.set_num_threads(max(1, n))
+    return torch.get_num_threads()
+
+
 def oracle_step_fn(args, shape):
     from oracle import pevit_oracle as O
+    use_all_host_threads()
     from pevit_b200 import synth
     p = dict(synth.clip_state_dict(shape, seed=0))
     O.init_adapters(p, args.method, seed=0)

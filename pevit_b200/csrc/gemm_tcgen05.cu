@@ -1,6 +1,6 @@
 // C[M,N] = A[M,K] * B[N,K]^T on the 5th-gen tensor cores (tcgen05.mma, fp32 accumulators in
 // TMEM), bf16 operands staged by TMA into 128B-swizzled shared memory.  Persistent,
-// warp-specialised: warp 0 = TMA producer, warp 1 = MMA issuer, warps 2-5 = epilogue
+// warp-specialised: warp 0 = TMA producer, warp 1 = MMA issuer, warps 2-9 = epilogue
 // (TMEM -> registers -> fused epilogue -> global).  Two TMEM accumulator stages let the
 // epilogue of tile i overlap the mainloop of tile i+1.
 //
@@ -17,7 +17,7 @@ namespace {
 
 constexpr int BM = 128;
 constexpr int BK = 64;  // 64 bf16 = one 128-byte swizzle row
-constexpr int GEMM_THREADS = 192;
+constexpr int GEMM_THREADS = 320;  // TMA warp, MMA warp, 2 x 4 epilogue warps
 
 template <int BN>
 struct TileCfg {
@@ -357,7 +357,7 @@ gemm_tn_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
     }
     for (int s = 0; s < 2; ++s) {
       mbar_init(&tfull_bar[s], 1);
-      mbar_init(&tempty_bar[s], 4);  // one arrive per epilogue warp
+      mbar_init(&tempty_bar[s], 8);  // one arrive per epilogue warp
     }
     fence_mbar_init();
   }
@@ -418,8 +418,11 @@ gemm_tn_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
       }
     }
   } else {
-    // ------------------------------------------------------------ epilogue warps
-    const int quad = warp & 3;  // TMEM lane quadrant this warp may read
+    // ------------------------------------------------------------ epilogue: two warpgroups (warps 2-5, 6-9)
+    // Both warpgroups cover all 128 accumulator rows (TMEM lane quadrant = warp % 4) and take alternate
+    // 32-column chunks, which doubles the loads in flight for the residual / auxiliary operands.
+    const int quad = warp & 3;          // TMEM lane quadrant this warp may read
+    const int wg = (warp - 2) >> 2;     // 0 or 1
     int it = 0;
     int box_count = 0;
     for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++it) {
@@ -432,7 +435,7 @@ gemm_tn_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
       const uint32_t t_row = tmem_base + (static_cast<uint32_t>(quad * 32) << 16) + acc * BN;
       if constexpr (!TS) {
 #pragma unroll 1
-        for (int c = 0; c < BN; c += 32) {
+        for (int c = wg * 32; c < BN; c += 64) {
           uint32_t v[32];
           tmem_ld_32x32(t_row + c, v);
           tmem_ld_wait();
@@ -440,45 +443,49 @@ gemm_tn_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
         }
       } else {
         // Staged epilogue: rows are written into 128B-swizzled [128][128 B] boxes in shared memory and
-        // leave through TMA stores (coalesced, clipped at M / N), two boxes in flight.
+        // leave through TMA stores (coalesced, clipped at M / N).
+        //   bf16 outputs: a box is 64 columns = one chunk from each warpgroup; two boxes alternate.
+        //   fp32 outputs: a box is 32 columns = one chunk; each warpgroup owns one box and its own stores.
         constexpr bool kF32 = (epi_base(EPI) == EPI_F32);
         constexpr bool kTwo = (epi_base(EPI) == EPI_ACT);            // h and z leave together
-        constexpr int CH_PER_BOX = kF32 ? 1 : 2;           // 32-column chunks per box
         const int row = quad * 32 + lane;
         const int m0 = (tile / tiles_n) * BM;
-        const bool elected = (threadIdx.x == 64);
         const bool two = kTwo && ep.out2_bf16 != nullptr;
+        const bool elected = kF32 ? (threadIdx.x == 64 + wg * 128) : (threadIdx.x == 64);
         EpiAux aux_cur, aux_next;
-        epilogue_prefetch<EPI>(ep, m, n0, m < M && n0 < N, aux_cur);
+        epilogue_prefetch<EPI>(ep, m, n0 + wg * 32, m < M && n0 + wg * 32 < N, aux_cur);
 #pragma unroll 1
-        for (int c = 0; c < BN; c += 32) {
+        for (int c = wg * 32; c < BN; c += 64) {
           uint32_t v[32];
           tmem_ld_32x32(t_row + c, v);
-          epilogue_prefetch<EPI>(ep, m, n0 + c + 32, m < M && c + 32 < BN && n0 + c + 32 < N, aux_next);
+          epilogue_prefetch<EPI>(ep, m, n0 + c + 64, m < M && c + 64 < BN && n0 + c + 64 < N, aux_next);
           tmem_ld_wait();
-          if (n0 + c >= N) continue;                       // warp-uniform (N % 32 == 0)
+          if (n0 + c >= N) continue;                       // uniform over both warpgroups (N % 64 == 0)
           float a[32], z[32];
           epilogue_values<EPI>(ep, n0 + c, aux_cur, v, a, z);
           aux_cur = aux_next;
-          const int sub = kF32 ? 0 : ((c >> 5) & 1);
-          const int buf = kTwo ? 0 : (box_count & 1);
-          if (sub == 0) {  // opening a box: its previous TMA store must have finished reading shared memory
-            if (elected) { if (kTwo) tma_store_wait_read<0>(); else tma_store_wait_read<1>(); }
-            named_bar_sync(1, 128);
-          }
           if constexpr (kF32) {
-            stage_row_f32(staging + buf * 16384, row, a);
-          } else {
-            stage_row_bf16(staging + buf * 16384, row, sub, a);
-            if constexpr (kTwo) { if (two) stage_row_bf16(staging + 16384, row, sub, z); }
-          }
-          if (sub == CH_PER_BOX - 1) {
+            uint8_t* box = staging + wg * 16384;
+            if (elected) tma_store_wait_read<0>();         // this warpgroup's previous store has drained the box
+            if (wg == 0) named_bar_sync(1, 128); else named_bar_sync(2, 128);
+            stage_row_f32(box, row, a);
             fence_proxy_async_smem();
-            named_bar_sync(1, 128);
+            if (wg == 0) named_bar_sync(1, 128); else named_bar_sync(2, 128);
             if (elected) {
-              const int col = n0 + c - 32 * (CH_PER_BOX - 1);
-              tma_store_2d(&tmap_c, staging + buf * 16384, col, m0);
-              if (two) tma_store_2d(&tmap_c2, staging + 16384, col, m0);
+              tma_store_2d(&tmap_c, box, n0 + c, m0);
+              tma_store_commit();
+            }
+          } else {
+            const int buf = kTwo ? 0 : (box_count & 1);
+            if (elected) { if (kTwo) tma_store_wait_read<0>(); else tma_store_wait_read<1>(); }
+            named_bar_sync(1, 256);
+            stage_row_bf16(staging + buf * 16384, row, wg, a);
+            if constexpr (kTwo) { if (two) stage_row_bf16(staging + 16384, row, wg, z); }
+            fence_proxy_async_smem();
+            named_bar_sync(1, 256);
+            if (elected) {
+              tma_store_2d(&tmap_c, staging + buf * 16384, n0 + c, m0);   // wg 0 elects: c is the box's first column
+              if (two) tma_store_2d(&tmap_c2, staging + 16384, n0 + c, m0);
               tma_store_commit();
             }
             ++box_count;
@@ -490,7 +497,7 @@ gemm_tn_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
       if (lane == 0) mbar_arrive(&tempty_bar[acc]);
     }
     if constexpr (TS) {
-      if (threadIdx.x == 64) tma_store_wait_all<0>();  // shared memory must outlive the last store
+      if (threadIdx.x == 64 || threadIdx.x == 192) tma_store_wait_all<0>();  // smem must outlive the last stores
     }
   }
 
