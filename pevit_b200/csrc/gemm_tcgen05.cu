@@ -8,6 +8,8 @@
 // (:305) + head split/scale (:729-740,786-787) + the X*P half of adapter_forward (:563-584)
 // [EPI_QKV]; out-proj / c_proj `linear` + residual add (:816, :973-974) [EPI_F32];
 // c_fc + QuickGELU (:958-962, :165) [EPI_ACT]; and every dgrad GEMM autograd would run.
+#include <cstdlib>
+
 #include "common.cuh"
 #include "kernels.h"
 
@@ -19,14 +21,17 @@ constexpr int BM = 128;
 constexpr int BK = 64;  // 64 bf16 = one 128-byte swizzle row
 constexpr int GEMM_THREADS = 320;  // TMA warp, MMA warp, 2 x 4 epilogue warps
 
-template <int BN>
+template <int BN, bool CTA2>
 struct TileCfg {
-  static constexpr int STAGES = BN >= 256 ? 4 : (BN >= 192 ? 4 : (BN >= 128 ? 6 : 8));
+  // CTA2: two CTAs (one TPC) share a 256 x BN tile; each stages its own 128 A rows and HALF of B's rows
+  static constexpr int B_ROWS = CTA2 ? BN / 2 : BN;
   static constexpr int A_BYTES = BM * BK * 2;
-  static constexpr int B_BYTES = BN * BK * 2;
+  static constexpr int B_BYTES = B_ROWS * BK * 2;
   static constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
-  static constexpr int TMEM_COLS = 2 * BN <= 32 ? 32 : (2 * BN <= 64 ? 64 : (2 * BN <= 128 ? 128 : (2 * BN <= 256 ? 256 : 512)));  // two accumulator stages, power of two
   static constexpr int STAGING_BYTES = 2 * 16384;  // two [128 rows][128 B] TMA-store boxes
+  static constexpr int STAGES_FIT = (227 * 1024 - STAGING_BYTES - 2048) / STAGE_BYTES;
+  static constexpr int STAGES = STAGES_FIT > 8 ? 8 : STAGES_FIT;
+  static constexpr int TMEM_COLS = 2 * BN <= 32 ? 32 : (2 * BN <= 64 ? 64 : (2 * BN <= 128 ? 128 : (2 * BN <= 256 ? 256 : 512)));  // two accumulator stages, power of two
   static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + STAGING_BYTES + 256 + 1024;  // + barriers + align slack
 };
 
@@ -323,13 +328,14 @@ __device__ __forceinline__ void stage_row_bf16(uint8_t* box, int row, int sub, c
                    pack_bf16(a[8 * q + 4], a[8 * q + 5]), pack_bf16(a[8 * q + 6], a[8 * q + 7]));
 }
 
-template <int BN, int EPI, bool TS>
+template <int BN, int EPI, bool TS, bool CTA2>
 __global__ void __launch_bounds__(GEMM_THREADS, 1)
 gemm_tn_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_b,
                const __grid_constant__ CUtensorMap tmap_c, const __grid_constant__ CUtensorMap tmap_c2,
                int M, int N, int K, GemmEpilogue ep) {
-  using Cfg = TileCfg<BN>;
+  using Cfg = TileCfg<BN, CTA2>;
   constexpr int STAGES = Cfg::STAGES;
+  constexpr int TILE_M = CTA2 ? 2 * BM : BM;  // rows of C covered by one (pair of) CTA(s) per tile
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   uint8_t* staging = smem + STAGES * Cfg::STAGE_BYTES;  // 1024-aligned: STAGE_BYTES is a multiple of 1024
@@ -342,9 +348,12 @@ gemm_tn_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
   const int tiles_n = (N + BN - 1) / BN;
-  const int tiles_m = (M + BM - 1) / BM;
+  const int tiles_m = (M + TILE_M - 1) / TILE_M;
   const int num_tiles = tiles_m * tiles_n;
   const int num_kb = (K + BK - 1) / BK;
+  const uint32_t cta_rank = CTA2 ? cluster_ctarank() : 0u;       // 0 = leader (issues the MMAs)
+  const int first_tile = CTA2 ? static_cast<int>(blockIdx.x >> 1) : static_cast<int>(blockIdx.x);
+  const int tile_step = CTA2 ? static_cast<int>(gridDim.x >> 1) : static_cast<int>(gridDim.x);
 
   if (warp == 0 && lane == 0) {
     tma_prefetch_desc(&tmap_a);
@@ -357,16 +366,17 @@ gemm_tn_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
     }
     for (int s = 0; s < 2; ++s) {
       mbar_init(&tfull_bar[s], 1);
-      mbar_init(&tempty_bar[s], 8);  // one arrive per epilogue warp
+      mbar_init(&tempty_bar[s], CTA2 ? 16 : 8);  // one arrive per epilogue warp (of both CTAs)
     }
     fence_mbar_init();
   }
   if (warp == 2) {
-    tmem_alloc(tmem_slot, Cfg::TMEM_COLS);
-    tmem_relinquish();
+    if constexpr (CTA2) { tmem_alloc_pair(tmem_slot, Cfg::TMEM_COLS); tmem_relinquish_pair(); }
+    else { tmem_alloc(tmem_slot, Cfg::TMEM_COLS); tmem_relinquish(); }
   }
   tc_fence_before();
   __syncthreads();
+  if constexpr (CTA2) cluster_sync_all();  // the peer's barriers exist before anything arrives on them remotely
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
 
@@ -375,26 +385,33 @@ gemm_tn_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
     if (lane == 0) {
       int stage = 0;
       uint32_t phase = 0;
-      for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
-        const int m0 = (tile / tiles_n) * BM;
-        const int n0 = (tile % tiles_n) * BN;
+      for (int tile = first_tile; tile < num_tiles; tile += tile_step) {
+        const int m0 = (tile / tiles_n) * TILE_M + static_cast<int>(cta_rank) * BM;
+        const int n0 = (tile % tiles_n) * BN + static_cast<int>(cta_rank) * Cfg::B_ROWS * (CTA2 ? 1 : 0);
         for (int kb = 0; kb < num_kb; ++kb) {
           mbar_wait(&empty_bar[stage], phase ^ 1);
           uint8_t* sa = smem + stage * Cfg::STAGE_BYTES;
-          mbar_expect_tx(&full_bar[stage], Cfg::STAGE_BYTES);
-          tma_load_2d(sa, &tmap_a, &full_bar[stage], kb * BK, m0);
-          tma_load_2d(sa + Cfg::A_BYTES, &tmap_b, &full_bar[stage], kb * BK, n0);
+          if constexpr (CTA2) {
+            // both CTAs' loads credit the leader's barrier, which is armed for the bytes of the whole pair
+            if (cta_rank == 0) mbar_expect_tx(&full_bar[stage], 2 * Cfg::STAGE_BYTES);
+            tma_load_2d_pair(sa, &tmap_a, &full_bar[stage], kb * BK, m0);
+            tma_load_2d_pair(sa + Cfg::A_BYTES, &tmap_b, &full_bar[stage], kb * BK, n0);
+          } else {
+            mbar_expect_tx(&full_bar[stage], Cfg::STAGE_BYTES);
+            tma_load_2d(sa, &tmap_a, &full_bar[stage], kb * BK, m0);
+            tma_load_2d(sa + Cfg::A_BYTES, &tmap_b, &full_bar[stage], kb * BK, n0);
+          }
           if (++stage == STAGES) { stage = 0; phase ^= 1; }
         }
       }
     }
   } else if (warp == 1) {
-    // ------------------------------------------------------------ MMA issuer
-    constexpr uint32_t idesc = umma_idesc_bf16(BM, BN);
+    // ------------------------------------------------------------ MMA issuer (leader CTA only when paired)
+    constexpr uint32_t idesc = umma_idesc_bf16(TILE_M, BN);
     int stage = 0;
     uint32_t phase = 0;
     int it = 0;
-    for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++it) {
+    for (int tile = first_tile; tile < num_tiles && cta_rank == 0; tile += tile_step, ++it) {
       const int acc = it & 1;
       const uint32_t acc_phase = (it >> 1) & 1;
       mbar_wait(&tempty_bar[acc], acc_phase ^ 1);
@@ -408,10 +425,17 @@ gemm_tn_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
           const uint64_t da = umma_desc_kmajor_sw128(sa);
           const uint64_t db = umma_desc_kmajor_sw128(sa + Cfg::A_BYTES);
 #pragma unroll
-          for (int k = 0; k < BK / 16; ++k)  // +32 B per 16-element K step (encoded >> 4)
-            umma_bf16_ss(d_tmem, da + 2 * k, db + 2 * k, idesc, (kb | k) != 0);
-          umma_commit(&empty_bar[stage]);
-          if (kb == num_kb - 1) umma_commit(&tfull_bar[acc]);
+          for (int k = 0; k < BK / 16; ++k) {  // +32 B per 16-element K step (encoded >> 4)
+            if constexpr (CTA2) umma_bf16_ss_pair(d_tmem, da + 2 * k, db + 2 * k, idesc, (kb | k) != 0);
+            else umma_bf16_ss(d_tmem, da + 2 * k, db + 2 * k, idesc, (kb | k) != 0);
+          }
+          if constexpr (CTA2) {
+            umma_commit_pair(&empty_bar[stage]);
+            if (kb == num_kb - 1) umma_commit_pair(&tfull_bar[acc]);
+          } else {
+            umma_commit(&empty_bar[stage]);
+            if (kb == num_kb - 1) umma_commit(&tfull_bar[acc]);
+          }
         }
         __syncwarp();
         if (++stage == STAGES) { stage = 0; phase ^= 1; }
@@ -425,10 +449,11 @@ gemm_tn_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
     const int wg = (warp - 2) >> 2;     // 0 or 1
     int it = 0;
     int box_count = 0;
-    for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++it) {
+    for (int tile = first_tile; tile < num_tiles; tile += tile_step, ++it) {
       const int acc = it & 1;
       const uint32_t acc_phase = (it >> 1) & 1;
-      const int m = (tile / tiles_n) * BM + quad * 32 + lane;
+      const int m_base = (tile / tiles_n) * TILE_M + static_cast<int>(cta_rank) * BM;
+      const int m = m_base + quad * 32 + lane;
       const int n0 = (tile % tiles_n) * BN;
       mbar_wait(&tfull_bar[acc], acc_phase);
       tc_fence_after();
@@ -449,7 +474,7 @@ gemm_tn_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
         constexpr bool kF32 = (epi_base(EPI) == EPI_F32);
         constexpr bool kTwo = (epi_base(EPI) == EPI_ACT);            // h and z leave together
         const int row = quad * 32 + lane;
-        const int m0 = (tile / tiles_n) * BM;
+        const int m0 = m_base;
         const bool two = kTwo && ep.out2_bf16 != nullptr;
         const bool elected = kF32 ? (threadIdx.x == 64 + wg * 128) : (threadIdx.x == 64);
         EpiAux aux_cur, aux_next;
@@ -494,7 +519,10 @@ gemm_tn_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
       }
       tc_fence_before();
       __syncwarp();
-      if (lane == 0) mbar_arrive(&tempty_bar[acc]);
+      if (lane == 0) {
+        if constexpr (CTA2) mbar_arrive_cluster(&tempty_bar[acc], 0);  // the leader's MMA warp owns the accumulators
+        else mbar_arrive(&tempty_bar[acc]);
+      }
     }
     if constexpr (TS) {
       if (threadIdx.x == 64 || threadIdx.x == 192) tma_store_wait_all<0>();  // smem must outlive the last stores
@@ -503,30 +531,63 @@ gemm_tn_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
 
   tc_fence_before();
   __syncthreads();
+  if constexpr (CTA2) cluster_sync_all();  // no CTA may exit (or free TMEM) while its peer still signals it
   if (warp == 2) {
     tc_fence_after();
-    tmem_dealloc(tmem_base, Cfg::TMEM_COLS);
+    if constexpr (CTA2) tmem_dealloc_pair(tmem_base, Cfg::TMEM_COLS);
+    else tmem_dealloc(tmem_base, Cfg::TMEM_COLS);
   }
 }
 
-template <int BN, int EPI, bool TS>
-int launch(cudaStream_t stream, const CUtensorMap& ta, const CUtensorMap& tb, const CUtensorMap& tc,
-           const CUtensorMap& tc2, int M, int N, int K, const GemmEpilogue& ep) {
-  using Cfg = TileCfg<BN>;
+template <int BN, int EPI, bool TS, bool CTA2>
+int launch_impl(cudaStream_t stream, const CUtensorMap& ta, const CUtensorMap& tb, const CUtensorMap& tc,
+                const CUtensorMap& tc2, int M, int N, int K, const GemmEpilogue& ep) {
+  using Cfg = TileCfg<BN, CTA2>;
+  static_assert(Cfg::STAGES >= 3, "pipeline too shallow");
   static bool configured[64] = {};  // per instantiation and device (the attribute is per context)
-  auto kern = gemm_tn_kernel<BN, EPI, TS>;
+  auto kern = gemm_tn_kernel<BN, EPI, TS, CTA2>;
   int dev = 0;
   PEVIT_CHECK_CUDA(cudaGetDevice(&dev));
   if (!configured[dev & 63]) {
     PEVIT_CHECK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM_BYTES));
     configured[dev & 63] = true;
   }
-  const int tiles = ((M + BM - 1) / BM) * ((N + BN - 1) / BN);
-  const int grid = tiles < sm_count() ? tiles : sm_count();
+  const int tile_m = CTA2 ? 2 * BM : BM;
+  const int tiles = ((M + tile_m - 1) / tile_m) * ((N + BN - 1) / BN);
   ProfScope prof(stream, PC_GEMM_OTHER);
-  kern<<<grid, GEMM_THREADS, Cfg::SMEM_BYTES, stream>>>(ta, tb, tc, tc2, M, N, K, ep);
+  if constexpr (CTA2) {
+    const int pairs = sm_count() / 2;
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3(2 * (tiles < pairs ? tiles : pairs));
+    cfg.blockDim = dim3(GEMM_THREADS);
+    cfg.dynamicSmemBytes = Cfg::SMEM_BYTES;
+    cfg.stream = stream;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeClusterDimension;
+    attr[0].val.clusterDim.x = 2;
+    attr[0].val.clusterDim.y = 1;
+    attr[0].val.clusterDim.z = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = 1;
+    PEVIT_CHECK_CUDA(cudaLaunchKernelEx(&cfg, kern, ta, tb, tc, tc2, M, N, K, ep));
+  } else {
+    const int grid = tiles < sm_count() ? tiles : sm_count();
+    kern<<<grid, GEMM_THREADS, Cfg::SMEM_BYTES, stream>>>(ta, tb, tc, tc2, M, N, K, ep);
+  }
   PEVIT_CHECK_LAUNCH();
   return 0;
+}
+
+// CTA pairs are used for the wide tiles of the big GEMMs; narrow tiles (skinny N) stay single-CTA.
+thread_local bool g_use_pair = false;
+
+template <int BN, int EPI, bool TS>
+int launch(cudaStream_t stream, const CUtensorMap& ta, const CUtensorMap& tb, const CUtensorMap& tc,
+           const CUtensorMap& tc2, int M, int N, int K, const GemmEpilogue& ep) {
+  if constexpr (BN >= 128) {
+    if (g_use_pair) return launch_impl<BN, EPI, TS, true>(stream, ta, tb, tc, tc2, M, N, K, ep);
+  }
+  return launch_impl<BN, EPI, TS, false>(stream, ta, tb, tc, tc2, M, N, K, ep);
 }
 
 template <int BN>
@@ -555,21 +616,32 @@ int dispatch_epi(int epi, bool ts, cudaStream_t s, const CUtensorMap& ta, const 
   return -1;
 }
 
-int pick_bn(int M, int N, int forced) {
+// Tile choice.  Tiles are operand-fetch (L2 -> SM) bound, so the cost of a schedule is (number of waves) x (bytes
+// one CTA stages per k-block): BM + BN rows single-CTA, BM + BN/2 rows when a CTA pair shares the B tile.
+int pick_tile(int M, int N, int forced, bool allow_pair, bool* pair) {
+  *pair = false;
   if (forced < 0) forced = -forced;  // negative: same tile width, direct-store epilogue (cross-check)
-  if (forced == 32 || forced == 64 || forced == 128 || forced == 192 || forced == 256) return forced;
+  const bool forced_pair = forced >= 1000;
+  if (forced_pair) forced -= 1000;
+  if (forced == 32 || forced == 64 || forced == 128 || forced == 192 || forced == 256) {
+    *pair = forced_pair && forced >= 128;
+    return forced;
+  }
   if (N <= 32) return 32;
   if (N <= 64) return 64;
-  // wave count x bytes staged per tile; ties go to the wider tile (more operand reuse per byte staged)
   const int sms = sm_count();
-  const int tm = (M + BM - 1) / BM;
   int best = 256;
   double best_cost = 1e30;
-  for (int bn : {256, 192, 128, 64}) {
-    const int tiles = tm * ((N + bn - 1) / bn);
-    const int waves = (tiles + sms - 1) / sms;
-    const double cost = static_cast<double>(waves) * (BM + bn);  // tiles are operand-fetch (L2 -> SM) bound
-    if (cost < best_cost - 1e-9) { best_cost = cost; best = bn; }
+  for (int use_pair = (allow_pair && M > BM) ? 1 : 0; use_pair >= 0; --use_pair) {
+    for (int bn : {256, 192, 128, 64}) {
+      if (use_pair && bn < 128) continue;
+      const int tile_m = use_pair ? 2 * BM : BM;
+      const int units = use_pair ? sms / 2 : sms;
+      const int tiles = ((M + tile_m - 1) / tile_m) * ((N + bn - 1) / bn);
+      const int waves = (tiles + units - 1) / units;
+      const double cost = static_cast<double>(waves) * (BM + (use_pair ? bn / 2 : bn));
+      if (cost < best_cost - 1e-9) { best_cost = cost; best = bn; *pair = use_pair != 0; }
+    }
   }
   return best;
 }
@@ -589,10 +661,13 @@ int gemm_tn(cudaStream_t stream, const bf16* A, int lda, const bf16* B, int ldb,
                   ep.NB, ep.H);
   else
     PEVIT_REQUIRE(ep.ld_out % 8 == 0, "gemm_tn: ld_out must be a multiple of 8");
-  const int bn = pick_bn(M, N, force_bn);
+  bool pair = false;
+  static const bool pair_disabled = getenv("PEVIT_GEMM_NO_PAIR") != nullptr;
+  const int bn = pick_tile(M, N, force_bn, !pair_disabled, &pair);
+  g_use_pair = pair;
   CUtensorMap ta, tb, tc, tc2;
   if (make_tmap_bf16_2d(&ta, A, M, K, lda, BM, BK) != 0) return -1;
-  if (make_tmap_bf16_2d(&tb, B, N, K, ldb, bn, BK) != 0) return -1;
+  if (make_tmap_bf16_2d(&tb, B, N, K, ldb, pair ? bn / 2 : bn, BK) != 0) return -1;
   // Staged TMA-store epilogue for row-major outputs with 16-byte aligned rows; direct stores otherwise.
   const void* out = epi == EPI_F32 ? static_cast<const void*>(ep.out_f32) : static_cast<const void*>(ep.out_bf16);
   const int elt = epi == EPI_F32 ? 4 : 2;

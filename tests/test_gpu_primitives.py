@@ -46,7 +46,9 @@ def run_gemm(lib, a, b, epi, **kw):
     (128, 256, 64, 0), (256, 128, 128, 128), (400, 768, 768, 0), (400, 768, 768, 64), (400, 768, 768, 256),
     (12800, 768, 3072, 0), (1000, 3072, 768, 0), (130, 72, 776, 0), (400, 32, 768, 0), (400, 4, 768, 0),
     (400, 768, 64, 0), (400, 768, 768, -128), (130, 192, 776, 0), (1000, 3072, 768, -256), (129, 64, 64, 0),
-])  # bn < 0: direct-store epilogue instead of the staged TMA-store one
+    (400, 768, 768, 1256), (400, 768, 768, 1192), (1000, 3072, 768, 1128), (12800, 768, 3072, 1192), (130, 192, 776, 1128),
+    (300, 256, 64, 1256), (12800, 768, 768, 128),
+])  # bn < 0: direct-store epilogue instead of the staged TMA-store one; bn >= 1000: CTA pair (cta_group::2)
 def test_gemm_f32_bias_resid(lib, M, N, K, bn):
     g = torch.Generator(device="cuda").manual_seed(M + N + K)
     a = bf(torch.randn(M, K, device="cuda", generator=g))
