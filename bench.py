@@ -252,8 +252,10 @@ def run_b200(args):
     t_wall0 = time.time()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e0.record()
+    t_cpu0 = time.perf_counter()
     for _ in range(args.steps):
         tuner.step(images, labels)
+    cpu_ms_per_step = 1e3 * (time.perf_counter() - t_cpu0) / args.steps  # host time to ENQUEUE a step
     e1.record()
     torch.cuda.synchronize()
     lib.pevit_prof_enable(0)
@@ -363,7 +365,7 @@ def run_b200(args):
         "roofline": roof,
         "roofline_attn": {n: roofline_of(n) for n in ("attn_fwd", "attn_bwd") if n in kernels},
         "kernels": kernels, "own_kernel_ms_per_step": own_ms,
-        "trainable_params": tuner.trainable_numel(),
+        "trainable_params": tuner.trainable_numel(), "host_enqueue_ms_per_step": cpu_ms_per_step,
     }
     if world == 1 and not args.no_cpu_baseline:
         line["cpu_baseline"] = cpu_baseline(args, shape)

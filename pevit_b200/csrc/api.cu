@@ -152,13 +152,15 @@ int pevit_gemm_tn(const pevit_gemm_args* a, void* stream) {
   ep.aux_bf16 = static_cast<const bf16*>(a->aux_bf16); ep.ld_out = a->ld_out;
   ep.qkv_hm = static_cast<bf16*>(a->qkv_hm); ep.t_out = static_cast<bf16*>(a->t_out);
   ep.resid_bf16 = static_cast<const bf16*>(a->resid_bf16);
+  ep.debug = a->force_bn >= 100000 ? a->force_bn / 100000 : 0;  // diagnostics (tools/gemm_bench.py)
+  const int force_bn = a->force_bn >= 100000 ? a->force_bn % 100000 : a->force_bn;
   ep.L = a->L; ep.NB = a->NB; ep.H = a->H; ep.D = a->D; ep.r2 = a->r2;
   int epi = a->epilogue;
   // the public enum folds the activation kind into the epilogue id
   if (epi == PEVIT_EPI_QGELU) { epi = EPI_ACT; ep.act = ACT_QUICKGELU; }
   else if (epi == PEVIT_EPI_DQGELU) { epi = EPI_DACT; ep.act = ACT_QUICKGELU; }
   return gemm_tn(as_stream(stream), static_cast<const bf16*>(a->a), a->lda, static_cast<const bf16*>(a->b), a->ldb,
-                 a->m, a->n, a->k, epi, ep, a->force_bn);
+                 a->m, a->n, a->k, epi, ep, force_bn);
 }
 
 int pevit_layernorm_fwd(const float* x, const float* gamma, const float* beta, void* y_bf16, float* y_f32, float* mean,

@@ -396,6 +396,8 @@ gemm_tn_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
             if (cta_rank == 0) mbar_expect_tx(&full_bar[stage], 2 * Cfg::STAGE_BYTES);
             tma_load_2d_pair(sa, &tmap_a, &full_bar[stage], kb * BK, m0);
             tma_load_2d_pair(sa + Cfg::A_BYTES, &tmap_b, &full_bar[stage], kb * BK, n0);
+          } else if (ep.debug & 1) {
+            mbar_arrive(&full_bar[stage]);  // diagnostics: pipeline without operand traffic
           } else {
             mbar_expect_tx(&full_bar[stage], Cfg::STAGE_BYTES);
             tma_load_2d(sa, &tmap_a, &full_bar[stage], kb * BK, m0);
@@ -425,13 +427,16 @@ gemm_tn_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
           const uint64_t da = umma_desc_kmajor_sw128(sa);
           const uint64_t db = umma_desc_kmajor_sw128(sa + Cfg::A_BYTES);
 #pragma unroll
-          for (int k = 0; k < BK / 16; ++k) {  // +32 B per 16-element K step (encoded >> 4)
+          for (int k = 0; k < BK / 16 && !(ep.debug & 2); ++k) {  // +32 B per 16-element K step (encoded >> 4)
             if constexpr (CTA2) umma_bf16_ss_pair(d_tmem, da + 2 * k, db + 2 * k, idesc, (kb | k) != 0);
             else umma_bf16_ss(d_tmem, da + 2 * k, db + 2 * k, idesc, (kb | k) != 0);
           }
           if constexpr (CTA2) {
             umma_commit_pair(&empty_bar[stage]);
             if (kb == num_kb - 1) umma_commit_pair(&tfull_bar[acc]);
+          } else if (ep.debug & 2) {
+            mbar_arrive(&empty_bar[stage]);  // diagnostics: operand traffic without tensor-core work
+            if (kb == num_kb - 1) mbar_arrive(&tfull_bar[acc]);
           } else {
             umma_commit(&empty_bar[stage]);
             if (kb == num_kb - 1) umma_commit(&tfull_bar[acc]);
@@ -485,7 +490,7 @@ gemm_tn_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
           tmem_ld_32x32(t_row + c, v);
           epilogue_prefetch<EPI>(ep, m, n0 + c + 64, m < M && c + 64 < BN && n0 + c + 64 < N, aux_next);
           tmem_ld_wait();
-          if (n0 + c >= N) continue;                       // uniform over both warpgroups (N % 64 == 0)
+          if (n0 + c >= N || (ep.debug & 4)) continue;     // uniform over both warpgroups (N % 64 == 0)
           float a[32], z[32];
           epilogue_values<EPI>(ep, n0 + c, aux_cur, v, a, z);
           aux_cur = aux_next;

@@ -114,8 +114,39 @@ int prof_read(double* ms, long long* launches, int n) {
 long long launch_count() { return g_launches.load(std::memory_order_relaxed); }
 const char* prof_class_name(int cls) { return (cls >= 0 && cls < PC_COUNT) ? kClassNames[cls] : "?"; }
 
+// cuTensorMapEncodeTiled costs microseconds of host time and the step issues ~200 GEMM launches, most of them on
+// the same (pointer, shape) tuples every step (frozen weights always; activations whenever the caching allocator
+// hands back the same block).  A descriptor depends only on the tuple hashed here, so cached copies stay valid.
+namespace {
+struct TmapKey {
+  const void* base; uint64_t a, b, c; uint32_t d, e, kind;
+  bool operator==(const TmapKey& o) const {
+    return base == o.base && a == o.a && b == o.b && c == o.c && d == o.d && e == o.e && kind == o.kind;
+  }
+};
+struct TmapSlot { TmapKey key; CUtensorMap map; bool used; };
+constexpr int kTmapSlots = 8192;  // direct-mapped
+thread_local TmapSlot* g_tmap_cache = nullptr;
+inline size_t tmap_hash(const TmapKey& k) {
+  uint64_t h = reinterpret_cast<uint64_t>(k.base) * 0x9E3779B97F4A7C15ull;
+  h ^= (k.a + 0x7F4A7C15u) * 0xC2B2AE3D27D4EB4Full; h ^= (k.b << 17) ^ (k.c << 31) ^ (uint64_t(k.d) << 43) ^ (uint64_t(k.e) << 7) ^ k.kind;
+  h ^= h >> 29;
+  return static_cast<size_t>(h % kTmapSlots);
+}
+inline bool tmap_lookup(const TmapKey& k, CUtensorMap* out, TmapSlot** slot) {
+  if (g_tmap_cache == nullptr) g_tmap_cache = new TmapSlot[kTmapSlots]();
+  *slot = &g_tmap_cache[tmap_hash(k)];
+  if ((*slot)->used && (*slot)->key == k) { *out = (*slot)->map; return true; }
+  return false;
+}
+inline void tmap_store(TmapSlot* slot, const TmapKey& k, const CUtensorMap& m) { slot->key = k; slot->map = m; slot->used = true; }
+}  // namespace
+
 int make_tmap_bf16_2d(CUtensorMap* out, const void* base, uint64_t rows, uint64_t cols, uint64_t row_stride_elems,
                       uint32_t box_rows, uint32_t box_cols) {
+  const TmapKey key{base, rows, cols, row_stride_elems, box_rows, box_cols, 1};
+  TmapSlot* slot = nullptr;
+  if (tmap_lookup(key, out, &slot)) return 0;
   if (g_encode == nullptr) {
     void* fn = nullptr;
     cudaDriverEntryPointQueryResult qres;
@@ -139,11 +170,15 @@ int make_tmap_bf16_2d(CUtensorMap* out, const void* base, uint64_t rows, uint64_
               box_cols);
     return -2;
   }
+  tmap_store(slot, key, *out);
   return 0;
 }
 
 int make_tmap_out_2d(CUtensorMap* out, const void* base, uint64_t rows, uint64_t cols, uint64_t row_stride_elems,
                      uint32_t box_rows, int elem_bytes) {
+  const TmapKey key{base, rows, cols, row_stride_elems, box_rows, static_cast<uint32_t>(elem_bytes), 2};
+  TmapSlot* slot = nullptr;
+  if (tmap_lookup(key, out, &slot)) return 0;
   CUtensorMap dummy;
   if (g_encode == nullptr && make_tmap_bf16_2d(&dummy, base, 8, 64, 64, 8, 64) != 0) return -2;  // resolves g_encode
   const cuuint64_t gdim[2] = {cols, rows};
@@ -158,11 +193,16 @@ int make_tmap_out_2d(CUtensorMap* out, const void* base, uint64_t rows, uint64_t
               (unsigned long long)rows, (unsigned long long)cols, (unsigned long long)row_stride_elems);
     return -2;
   }
+  tmap_store(slot, key, *out);
   return 0;
 }
 
 int make_tmap_bf16_tok_heads(CUtensorMap* out, const void* base, int L, int NB, int H, uint64_t row_stride_elems,
                              uint32_t box_l) {
+  const TmapKey key{base, static_cast<uint64_t>(L), static_cast<uint64_t>(NB), row_stride_elems, static_cast<uint32_t>(H),
+                    box_l, 3};
+  TmapSlot* slot = nullptr;
+  if (tmap_lookup(key, out, &slot)) return 0;
   CUtensorMap dummy;
   if (g_encode == nullptr && make_tmap_bf16_2d(&dummy, base, 8, 64, 64, 8, 64) != 0) return -2;  // resolves g_encode
   const cuuint64_t gdim[4] = {64, static_cast<cuuint64_t>(H), static_cast<cuuint64_t>(NB), static_cast<cuuint64_t>(L)};
@@ -177,6 +217,7 @@ int make_tmap_bf16_tok_heads(CUtensorMap* out, const void* base, int L, int NB, 
               (unsigned long long)row_stride_elems);
     return -2;
   }
+  tmap_store(slot, key, *out);
   return 0;
 }
 

@@ -24,6 +24,7 @@ struct GemmEpilogue {
   bf16* qkv_hm = nullptr;          // [3][NB*H][L][64] head-major q (pre-scaled 1/8), k, v
   bf16* t_out = nullptr;           // [M][r2] low-rank activations T = X P (bf16: A operand of the delta GEMM)
   int L = 0, NB = 0, H = 0, D = 0, r2 = 0;
+  int debug = 0;  // diagnostics only (tools/gemm_bench.py): 1 = no TMA loads, 2 = no MMAs, 4 = no epilogue stores
 };
 
 int gemm_tn(cudaStream_t stream, const bf16* A, int lda, const bf16* B, int ldb, int M, int N, int K, int epi,

@@ -54,15 +54,19 @@ def run(M, N, K, epi, bn, resid=False, bias=False, cold=False, iters=20):
 
 if __name__ == "__main__":
     print(f"{'shape':28s} {'epi':6s} {'bn':>4s} {'extra':10s} {'warm us':>9s} {'TF/s':>7s} {'cold us':>9s} {'TF/s':>7s}")
+    D = 100000  # debug flag multiplier: 1 = no TMA, 2 = no MMA, 4 = no epilogue stores
+    W = 128 * 148
     cases = [
-        (12800, 768, 768, L.EPI_F32, 192, True, True), (12800, 768, 768, L.EPI_F32, 1192, True, True),
-        (12800, 768, 768, L.EPI_F32, 1256, True, True), (12800, 768, 768, L.EPI_F32, 1128, True, True),
-        (12800, 768, 3072, L.EPI_F32, 192, True, True), (12800, 768, 3072, L.EPI_F32, 1192, True, True),
-        (12800, 768, 3072, L.EPI_F32, 1256, True, True),
-        (12800, 3072, 768, L.EPI_QGELU, 256, False, True), (12800, 3072, 768, L.EPI_QGELU, 1256, False, True),
-        (12800, 3072, 768, L.EPI_DQGELU, 256, False, False), (12800, 3072, 768, L.EPI_DQGELU, 1256, False, False),
-        (12800, 768, 2368, L.EPI_F32, 192, False, False), (12800, 768, 2368, L.EPI_F32, 1192, False, False),
-        (8192, 8192, 8192, L.EPI_BF16, 256, False, False), (8192, 8192, 8192, L.EPI_BF16, 1256, False, False),
+        (W, 192, 64, L.EPI_BF16, 192, False, False), (2 * W, 192, 64, L.EPI_BF16, 192, False, False),
+        (4 * W, 192, 64, L.EPI_BF16, 192, False, False), (8 * W, 192, 64, L.EPI_BF16, 192, False, False),
+        (8 * W, 192, 64, L.EPI_BF16, 4 * D + 192, False, False), (8 * W, 192, 64, L.EPI_BF16, 7 * D + 192, False, False),
+        (8 * W, 192, 64, L.EPI_BF16, -192, False, False),
+        (W, 192, 64, L.EPI_F32, 192, False, False), (8 * W, 192, 64, L.EPI_F32, 192, False, False),
+        (W, 192, 3072, L.EPI_BF16, 192, False, False), (2 * W, 192, 3072, L.EPI_BF16, 192, False, False),
+        (4 * W, 192, 3072, L.EPI_BF16, 192, False, False),
+        (W, 256, 3072, L.EPI_BF16, 256, False, False), (4 * W, 256, 3072, L.EPI_BF16, 256, False, False),
+        (4 * W, 256, 3072, L.EPI_BF16, 1256, False, False),
+        (4 * W, 256, 3072, L.EPI_BF16, 5 * D + 256, False, False),
     ]
     for (M, N, K, epi, bn, resid, bias) in cases:
         w = run(M, N, K, epi, bn, resid, bias, cold=False)
