@@ -47,6 +47,7 @@ def parse():
     ap.add_argument("--batch", type=int, default=256, help="images per GPU per step")
     ap.add_argument("--cpu-batch", type=int, default=32, help="images per CPU-baseline step (bounded sample)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-graph", action="store_true", help="time the eager step instead of the CUDA-graph replay")
     return ap.parse_args()
 
 
@@ -241,26 +242,51 @@ def run_b200(args):
 
     for _ in range(max(args.warmup, 3)):
         tuner.step(images, labels)
+    torch.cuda.synchronize()
+    # whole-step CUDA graph (eager fallback if capture is not possible in this configuration)
+    graphed = False
+    if not args.no_graph:
+        try:
+            tuner.capture(images, labels)
+            for _ in range(2):
+                tuner.step_graphed()
+            torch.cuda.synchronize()
+            graphed = True
+        except Exception as exc:  # pragma: no cover - depends on the runtime (e.g. NCCL capture support)
+            print(f"[bench] CUDA-graph capture unavailable, timing the eager step: {exc!r}", file=sys.stderr)
+            torch.cuda.synchronize()
+    run_step = (lambda: tuner.step_graphed()) if graphed else (lambda: tuner.step(images, labels))
     clocks = ClockSampler(local) if rank == 0 else None
 
-    # ---- device-resident timing (value) with per-launch events for the roofline
-    ncls = lib.pevit_prof_num_classes()
-    lib.pevit_prof_reset()
+    # ---- device-resident timing (value)
     barrier()
-    lib.pevit_prof_enable(1)
-    launches0 = lib.pevit_launch_count()
     t_wall0 = time.time()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e0.record()
     t_cpu0 = time.perf_counter()
     for _ in range(args.steps):
-        tuner.step(images, labels)
+        run_step()
     cpu_ms_per_step = 1e3 * (time.perf_counter() - t_cpu0) / args.steps  # host time to ENQUEUE a step
     e1.record()
     torch.cuda.synchronize()
+    ms_total = reduce_max(e0.elapsed_time(e1))
+    barrier()
+
+    # ---- per-kernel-class device time: the same K steps again, eagerly, every launch of this library bracketed by
+    # CUDA events on its stream (a graph replay has no per-kernel events; this pass is not the reported value)
+    ncls = lib.pevit_prof_num_classes()
+    lib.pevit_prof_reset()
+    lib.pevit_prof_enable(1)
+    launches0 = lib.pevit_launch_count()
+    ep0, ep1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    ep0.record()
+    for _ in range(args.steps):
+        tuner.step(images, labels)
+    ep1.record()
+    torch.cuda.synchronize()
     lib.pevit_prof_enable(0)
     launches = lib.pevit_launch_count() - launches0
-    ms_total = reduce_max(e0.elapsed_time(e1))
+    ms_eager = reduce_max(ep0.elapsed_time(ep1))
     barrier()
     t_wall1 = time.time()
     ms_arr, cnt_arr = (C.c_double * ncls)(), (C.c_int64 * ncls)()
@@ -293,7 +319,7 @@ def run_b200(args):
             if i + 1 < steps:
                 prefetch(i + 1)
             torch.cuda.current_stream().wait_event(ready[b])
-            loss = tuner.step(dev_img[b], dev_lab[b])
+            loss = tuner.step_graphed(dev_img[b], dev_lab[b]) if graphed else tuner.step(dev_img[b], dev_lab[b])
             consumed[b].record()
             loss_host = loss.item()  # D2H of the step's result (kadaptation_clip.py:354)
         return loss_host
@@ -329,8 +355,9 @@ def run_b200(args):
             kernels[name] = {"ms_per_step": ms_arr[i] / args.steps, "launches_per_step": cnt_arr[i] / args.steps,
                              "avg_us": 1e3 * ms_arr[i] / cnt_arr[i]}
     own_ms = sum(k["ms_per_step"] for k in kernels.values())
+    ms_step_eager = ms_eager / args.steps
     for k in kernels.values():
-        k["share_of_step"] = k["ms_per_step"] / ms_step
+        k["share_of_step"] = k["ms_per_step"] / ms_step_eager
 
     def roofline_of(name):
         k = kernels[name]
@@ -361,11 +388,13 @@ def run_b200(args):
         "e2e": {"value": e2e_value, "unit": "images/s", "ms_per_step": ms_e2e / args.steps,
                 "h2d_bytes_per_step": (images.numel() * 4 + labels.numel() * 8) * world,
                 "d2h_bytes_per_step": 4 * world, "last_loss": last_loss},
-        "gpu_launches": int(launches),
+        "gpu_launches": int(launches),  # this library's kernels per K steps (counted in the eager pass; the graph replays the same launches)
         "roofline": roof,
         "roofline_attn": {n: roofline_of(n) for n in ("attn_fwd", "attn_bwd") if n in kernels},
         "kernels": kernels, "own_kernel_ms_per_step": own_ms,
         "trainable_params": tuner.trainable_numel(), "host_enqueue_ms_per_step": cpu_ms_per_step,
+        "cuda_graph": graphed, "eager_profiled_ms_per_step": ms_step_eager,
+        "kernel_timing": "per-launch CUDA events in a separate eager pass of the same K steps right after the timed region",
     }
     if world == 1 and not args.no_cpu_baseline:
         line["cpu_baseline"] = cpu_baseline(args, shape)
