@@ -77,6 +77,8 @@ attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_consta
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
+  pdl_launch_dependents();
+  pdl_wait();
   // TMEM columns: S0 [0,128) S1 [128,256) O0 [256,320) O1 [320,384)
 
   if (warp == 8) {
@@ -290,6 +292,8 @@ attn_bwd_tc_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_consta
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
+  pdl_launch_dependents();
+  pdl_wait();
 
   if (warp == 8) {
     // ------------------------------------------------------------ TMA producer
@@ -498,10 +502,10 @@ int attn_fwd_tc(cudaStream_t s, const AttnShape& a, const bf16* q, const bf16* k
   ProfScope prof(s, PC_ATTN_FWD);
   if (pack == 2) {
     PEVIT_CHECK_CUDA(cudaFuncSetAttribute(attn_fwd_tc_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, FWD_SMEM));
-    attn_fwd_tc_kernel<2><<<grid, FWD_THREADS, FWD_SMEM, s>>>(tq, tk, tv, p);
+    PEVIT_CHECK_CUDA(launch_kernel(attn_fwd_tc_kernel<2>, dim3(grid), dim3(FWD_THREADS), FWD_SMEM, s, 1, tq, tk, tv, p));
   } else {
     PEVIT_CHECK_CUDA(cudaFuncSetAttribute(attn_fwd_tc_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, FWD_SMEM));
-    attn_fwd_tc_kernel<1><<<grid, FWD_THREADS, FWD_SMEM, s>>>(tq, tk, tv, p);
+    PEVIT_CHECK_CUDA(launch_kernel(attn_fwd_tc_kernel<1>, dim3(grid), dim3(FWD_THREADS), FWD_SMEM, s, 1, tq, tk, tv, p));
   }
   PEVIT_CHECK_LAUNCH();
   return 0;
@@ -525,10 +529,10 @@ int attn_bwd_tc(cudaStream_t s, const AttnShape& a, const bf16* q, const bf16* k
   ProfScope prof(s, PC_ATTN_BWD);
   if (pack == 2) {
     PEVIT_CHECK_CUDA(cudaFuncSetAttribute(attn_bwd_tc_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, BWD_SMEM));
-    attn_bwd_tc_kernel<2><<<grid, BWD_THREADS, BWD_SMEM, s>>>(tq, tk, tv, tdo, p);
+    PEVIT_CHECK_CUDA(launch_kernel(attn_bwd_tc_kernel<2>, dim3(grid), dim3(BWD_THREADS), BWD_SMEM, s, 1, tq, tk, tv, tdo, p));
   } else {
     PEVIT_CHECK_CUDA(cudaFuncSetAttribute(attn_bwd_tc_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, BWD_SMEM));
-    attn_bwd_tc_kernel<1><<<grid, BWD_THREADS, BWD_SMEM, s>>>(tq, tk, tv, tdo, p);
+    PEVIT_CHECK_CUDA(launch_kernel(attn_bwd_tc_kernel<1>, dim3(grid), dim3(BWD_THREADS), BWD_SMEM, s, 1, tq, tk, tv, tdo, p));
   }
   PEVIT_CHECK_LAUNCH();
   return 0;

@@ -37,6 +37,40 @@ const char* last_error();
 
 int sm_count();
 
+// ---------------------------------------------------------------- host: launches
+// Hot kernels can be launched with programmatic stream serialization (PDL, PEVIT_PDL=1): the grid may become resident
+// while its predecessor in the stream drains, runs its prologue (barrier init, TMEM allocation, descriptor prefetch)
+// and then blocks in pdl_wait() until the predecessor has completed and flushed.  A kernel launched through here MUST
+// call pdl_wait() before its first global-memory access.  Off by default: measured on B200 inside the whole-step CUDA
+// graph, PDL edges gave no gain (9.09 vs 9.09 ms/step) and an early launch_dependents trigger cost 3 % (9.37 ms).
+bool pdl_enabled();
+template <typename... KArgs, typename... Args>
+inline cudaError_t launch_kernel(void (*kern)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t stream,
+                                 int cluster_x, Args&&... args) {
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = grid;
+  cfg.blockDim = block;
+  cfg.dynamicSmemBytes = smem;
+  cfg.stream = stream;
+  cudaLaunchAttribute attr[2];
+  unsigned n = 0;
+  if (pdl_enabled()) {
+    attr[n].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[n].val.programmaticStreamSerializationAllowed = 1;
+    ++n;
+  }
+  if (cluster_x > 1) {
+    attr[n].id = cudaLaunchAttributeClusterDimension;
+    attr[n].val.clusterDim.x = static_cast<unsigned>(cluster_x);
+    attr[n].val.clusterDim.y = 1;
+    attr[n].val.clusterDim.z = 1;
+    ++n;
+  }
+  cfg.attrs = attr;
+  cfg.numAttrs = n;
+  return cudaLaunchKernelEx(&cfg, kern, static_cast<KArgs>(args)...);
+}
+
 // ---------------------------------------------------------------- host: launch accounting
 // Every kernel launcher opens a ProfScope: it counts the launch and, when profiling is enabled
 // (pevit_prof_enable), brackets it with CUDA events on the launching stream so bench.py can
@@ -76,6 +110,18 @@ __device__ __forceinline__ uint32_t smem_u32(const void* p) {
   return static_cast<uint32_t>(__cvta_generic_to_shared(p));
 }
 __device__ __forceinline__ uint32_t lane_id() { return threadIdx.x & 31; }
+
+// Programmatic dependent launch: wait for the predecessor grid (complete + memory visible) / allow the successor
+// grid to start becoming resident.  Both are no-ops when the launch carries no programmatic dependency.
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+#ifndef PEVIT_PDL_EARLY_TRIGGER
+#define PEVIT_PDL_EARLY_TRIGGER 0
+#endif
+__device__ __forceinline__ void pdl_launch_dependents() {
+#if PEVIT_PDL_EARLY_TRIGGER
+  asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
+#endif
+}
 
 __device__ __forceinline__ bool elect_one() {
   uint32_t pred = 0;

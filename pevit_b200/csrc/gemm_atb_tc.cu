@@ -51,6 +51,8 @@ atb_tc_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant__ 
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
+  pdl_launch_dependents();
+  pdl_wait();
 
   if (warp == 0) {
     if (lane == 0) {
@@ -153,7 +155,7 @@ int atb_tc(cudaStream_t s, const bf16* A, int lda, const bf16* B, int ldb, int n
     configured[dev & 63] = true;
   }
   ProfScope prof(s, PC_ATB);
-  atb_tc_kernel<<<dim3(gx, splits), ATB_THREADS, ATB_SMEM, s>>>(ta, tb, p);
+  PEVIT_CHECK_CUDA(launch_kernel(atb_tc_kernel, dim3(gx, splits), dim3(ATB_THREADS), ATB_SMEM, s, 1, ta, tb, p));
   PEVIT_CHECK_LAUNCH();
   return 0;
 }

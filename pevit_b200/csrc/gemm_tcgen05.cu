@@ -379,6 +379,8 @@ gemm_tn_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
   if constexpr (CTA2) cluster_sync_all();  // the peer's barriers exist before anything arrives on them remotely
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
+  pdl_launch_dependents();  // only after the TMEM allocation: a co-resident successor must not take the columns first
+  pdl_wait();               // predecessor grid complete and visible; nothing above touches global memory
 
   if (warp == 0) {
     // ------------------------------------------------------------ TMA producer
@@ -560,25 +562,15 @@ int launch_impl(cudaStream_t stream, const CUtensorMap& ta, const CUtensorMap& t
   const int tile_m = CTA2 ? 2 * BM : BM;
   const int tiles = ((M + tile_m - 1) / tile_m) * ((N + BN - 1) / BN);
   ProfScope prof(stream, PC_GEMM_OTHER);
+  int grid;
   if constexpr (CTA2) {
     const int pairs = sm_count() / 2;
-    cudaLaunchConfig_t cfg = {};
-    cfg.gridDim = dim3(2 * (tiles < pairs ? tiles : pairs));
-    cfg.blockDim = dim3(GEMM_THREADS);
-    cfg.dynamicSmemBytes = Cfg::SMEM_BYTES;
-    cfg.stream = stream;
-    cudaLaunchAttribute attr[1];
-    attr[0].id = cudaLaunchAttributeClusterDimension;
-    attr[0].val.clusterDim.x = 2;
-    attr[0].val.clusterDim.y = 1;
-    attr[0].val.clusterDim.z = 1;
-    cfg.attrs = attr;
-    cfg.numAttrs = 1;
-    PEVIT_CHECK_CUDA(cudaLaunchKernelEx(&cfg, kern, ta, tb, tc, tc2, M, N, K, ep));
+    grid = 2 * (tiles < pairs ? tiles : pairs);
   } else {
-    const int grid = tiles < sm_count() ? tiles : sm_count();
-    kern<<<grid, GEMM_THREADS, Cfg::SMEM_BYTES, stream>>>(ta, tb, tc, tc2, M, N, K, ep);
+    grid = tiles < sm_count() ? tiles : sm_count();
   }
+  PEVIT_CHECK_CUDA(launch_kernel(kern, dim3(grid), dim3(GEMM_THREADS), Cfg::SMEM_BYTES, stream, CTA2 ? 2 : 1, ta, tb, tc,
+                                 tc2, M, N, K, ep));
   PEVIT_CHECK_LAUNCH();
   return 0;
 }

@@ -5,6 +5,7 @@
 #include <atomic>
 #include <cstdarg>
 #include <cstdio>
+#include <cstdlib>
 #include <mutex>
 #include <vector>
 
@@ -39,6 +40,11 @@ int sm_count() {
     cached[dev & 63] = n;
   }
   return cached[dev & 63];
+}
+
+bool pdl_enabled() {
+  static const bool on = getenv("PEVIT_PDL") != nullptr;
+  return on;
 }
 
 // ------------------------------------------------------------------ launch accounting

@@ -21,6 +21,8 @@ __global__ void __launch_bounds__(LN_THREADS)
 ln_fwd_kernel(const float* __restrict__ x, const float* __restrict__ gamma, const float* __restrict__ beta,
               bf16* __restrict__ y_bf16, float* __restrict__ y_f32, float* __restrict__ mean_out,
               float* __restrict__ rstd_out, int M, int D) {
+  pdl_launch_dependents();
+  pdl_wait();
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const float inv_d = 1.f / D;
   const float4* g4 = reinterpret_cast<const float4*>(gamma);
@@ -69,6 +71,8 @@ ln_bwd_kernel(const float* __restrict__ dyn, const float* __restrict__ x, const 
               const float* __restrict__ mean_in, const float* __restrict__ rstd_in, const float* __restrict__ dres,
               float* __restrict__ dx, bf16* __restrict__ dx_bf16, float* __restrict__ dgamma,
               float* __restrict__ dbeta, int M, int D) {
+  pdl_launch_dependents();
+  pdl_wait();
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const float inv_d = 1.f / D;
   const float4* g4 = reinterpret_cast<const float4*>(gamma);
@@ -145,11 +149,11 @@ int launch_fwd(cudaStream_t s, const float* x, const float* gamma, const float* 
                float* mean, float* rstd, int M, int D) {
   const int grid = ln_grid(M, 6);
   if (y_bf16 && y_f32)
-    ln_fwd_kernel<NV, true, true><<<grid, LN_THREADS, 0, s>>>(x, gamma, beta, y_bf16, y_f32, mean, rstd, M, D);
+    launch_kernel(ln_fwd_kernel<NV, true, true>, dim3(grid), dim3(LN_THREADS), 0, s, 1, x, gamma, beta, y_bf16, y_f32, mean, rstd, M, D);
   else if (y_bf16)
-    ln_fwd_kernel<NV, false, true><<<grid, LN_THREADS, 0, s>>>(x, gamma, beta, y_bf16, y_f32, mean, rstd, M, D);
+    launch_kernel(ln_fwd_kernel<NV, false, true>, dim3(grid), dim3(LN_THREADS), 0, s, 1, x, gamma, beta, y_bf16, y_f32, mean, rstd, M, D);
   else
-    ln_fwd_kernel<NV, true, false><<<grid, LN_THREADS, 0, s>>>(x, gamma, beta, y_bf16, y_f32, mean, rstd, M, D);
+    launch_kernel(ln_fwd_kernel<NV, true, false>, dim3(grid), dim3(LN_THREADS), 0, s, 1, x, gamma, beta, y_bf16, y_f32, mean, rstd, M, D);
   return 0;
 }
 
@@ -158,11 +162,11 @@ int launch_bwd(cudaStream_t s, const float* dyn, const float* x, const float* ga
                const float* rstd, const float* dres, float* dx, bf16* dx_bf16, float* dgamma, float* dbeta, int M,
                int D) {
   if (dgamma != nullptr)
-    ln_bwd_kernel<NV, true><<<ln_grid(M, 2), LN_THREADS, 0, s>>>(dyn, x, gamma, mean, rstd, dres, dx, dx_bf16, dgamma,
-                                                                 dbeta, M, D);
+    launch_kernel(ln_bwd_kernel<NV, true>, dim3(ln_grid(M, 2)), dim3(LN_THREADS), 0, s, 1, dyn, x, gamma, mean, rstd, dres, dx,
+                  dx_bf16, dgamma, dbeta, M, D);
   else
-    ln_bwd_kernel<NV, false><<<ln_grid(M, 4), LN_THREADS, 0, s>>>(dyn, x, gamma, mean, rstd, dres, dx, dx_bf16,
-                                                                  nullptr, nullptr, M, D);
+    launch_kernel(ln_bwd_kernel<NV, false>, dim3(ln_grid(M, 4)), dim3(LN_THREADS), 0, s, 1, dyn, x, gamma, mean, rstd, dres, dx,
+                  dx_bf16, static_cast<float*>(nullptr), static_cast<float*>(nullptr), M, D);
   return 0;
 }
 

@@ -18,6 +18,8 @@ __global__ void kad_expand_kernel(const float* __restrict__ u1, const float* __r
                                   const float* __restrict__ sf, const float* __restrict__ tf, int D, float alpha,
                                   bf16* __restrict__ w_ext, bf16* __restrict__ w_ext_t, float* __restrict__ qmat,
                                   bf16* __restrict__ qmat_t, bf16* __restrict__ delta_w) {
+  pdl_launch_dependents();
+  pdl_wait();
   const int F = D / 32;
   const int ld_t = 3 * D + 64;
   const int total = 32 * D;  // (i, a, k)
@@ -47,6 +49,8 @@ __global__ void lora_expand_kernel(const float* __restrict__ Aq, const float* __
                                    const float* __restrict__ Bq, const float* __restrict__ Bv, int D, int r,
                                    float alpha, bf16* __restrict__ w_ext, bf16* __restrict__ w_ext_t,
                                    float* __restrict__ qmat, bf16* __restrict__ qmat_t, bf16* __restrict__ delta_w) {
+  pdl_launch_dependents();
+  pdl_wait();
   const int ld_t = 3 * D + 2 * r;
   const int total = r * D;
   for (int idx = blockIdx.x * blockDim.x + threadIdx.x; idx < total; idx += gridDim.x * blockDim.x) {
@@ -122,6 +126,8 @@ constexpr int CS_COLG = 32, CS_ROWL = 8;  // 32 column groups x 8 row lanes = 25
 __global__ void __launch_bounds__(CS_COLG* CS_ROWL)
 colsum_bf16_kernel(const bf16* __restrict__ X0, const bf16* __restrict__ X1, int ld, int M, int D,
                    float* __restrict__ out, int rows_per_cta) {
+  pdl_launch_dependents();
+  pdl_wait();
   __shared__ float red[CS_ROWL][CS_COLG * 8 + 1];
   const int cg = threadIdx.x % CS_COLG, rl = threadIdx.x / CS_COLG;
   const int c0 = (blockIdx.x * CS_COLG + cg) * 8;
@@ -171,6 +177,8 @@ kad_factor_grads_kernel(const float* __restrict__ dP, const float* __restrict__ 
                         const float* __restrict__ sf, const float* __restrict__ tf, int D, float* __restrict__ du1,
                         float* __restrict__ dv1, float* __restrict__ du2, float* __restrict__ dv2,
                         float* __restrict__ dsf, float* __restrict__ dtf) {
+  pdl_launch_dependents();
+  pdl_wait();
   extern __shared__ float sm[];  // [4][D]: dPq, dPv, dQq, dQv columns i; then s, t, u1, u2, v1, v2 rows i
   const int i = blockIdx.x;
   const int F = D / 32;
@@ -212,6 +220,8 @@ kad_factor_grads_kernel(const float* __restrict__ dP, const float* __restrict__ 
 
 __global__ void cast2d_kernel(const float* __restrict__ src, int lds, bf16* __restrict__ dst, int ldd, int rows,
                               int cols) {
+  pdl_launch_dependents();
+  pdl_wait();
   const size_t total = static_cast<size_t>(rows) * cols;
   for (size_t idx = blockIdx.x * static_cast<size_t>(blockDim.x) + threadIdx.x; idx < total;
        idx += static_cast<size_t>(gridDim.x) * blockDim.x) {
@@ -221,6 +231,8 @@ __global__ void cast2d_kernel(const float* __restrict__ src, int lds, bf16* __re
 }
 
 __global__ void cast_kernel(const float* __restrict__ src, bf16* __restrict__ dst, size_t n) {
+  pdl_launch_dependents();
+  pdl_wait();
   for (size_t i = blockIdx.x * static_cast<size_t>(blockDim.x) + threadIdx.x; i < n;
        i += static_cast<size_t>(gridDim.x) * blockDim.x)
     dst[i] = __float2bfloat16(src[i]);
@@ -254,8 +266,8 @@ int kad_expand(cudaStream_t s, const float* u1, const float* v1, const float* u2
                bf16* delta_w) {
   PEVIT_REQUIRE(D % 32 == 0, "kad_expand: D=%d not divisible by phm_dim 32", D);
   ProfScope prof(s, PC_EXPAND);
-  kad_expand_kernel<<<grid_for(32 * static_cast<size_t>(D), 256), 256, 0, s>>>(u1, v1, u2, v2, sfac, tfac, D, alpha,
-                                                                               w_ext, w_ext_t, qmat, qmat_t, delta_w);
+  PEVIT_CHECK_CUDA(launch_kernel(kad_expand_kernel, dim3(grid_for(32 * static_cast<size_t>(D), 256)), dim3(256), 0, s, 1, u1, v1,
+                                 u2, v2, sfac, tfac, D, alpha, w_ext, w_ext_t, qmat, qmat_t, delta_w));
   PEVIT_CHECK_LAUNCH();
   return 0;
 }
@@ -263,8 +275,8 @@ int kad_expand(cudaStream_t s, const float* u1, const float* v1, const float* u2
 int lora_expand(cudaStream_t s, const float* Aq, const float* Av, const float* Bq, const float* Bv, int D, int r,
                 float alpha, bf16* w_ext, bf16* w_ext_t, float* qmat, bf16* qmat_t, bf16* delta_w) {
   ProfScope prof(s, PC_EXPAND);
-  lora_expand_kernel<<<grid_for(static_cast<size_t>(r) * D, 256), 256, 0, s>>>(Aq, Av, Bq, Bv, D, r, alpha, w_ext,
-                                                                               w_ext_t, qmat, qmat_t, delta_w);
+  PEVIT_CHECK_CUDA(launch_kernel(lora_expand_kernel, dim3(grid_for(static_cast<size_t>(r) * D, 256)), dim3(256), 0, s, 1, Aq, Av,
+                                 Bq, Bv, D, r, alpha, w_ext, w_ext_t, qmat, qmat_t, delta_w));
   PEVIT_CHECK_LAUNCH();
   return 0;
 }
@@ -300,7 +312,8 @@ int colsum_bf16(cudaStream_t s, const bf16* X0, const bf16* X1, int ld, int M, i
   if (rows_per_cta < CS_ROWL) rows_per_cta = CS_ROWL;
   splits = (M + rows_per_cta - 1) / rows_per_cta;
   ProfScope prof(s, PC_COLSUM);
-  colsum_bf16_kernel<<<dim3(gx, splits), CS_COLG * CS_ROWL, 0, s>>>(X0, X1, ld, M, D, out, rows_per_cta);
+  PEVIT_CHECK_CUDA(launch_kernel(colsum_bf16_kernel, dim3(gx, splits), dim3(CS_COLG * CS_ROWL), 0, s, 1, X0, X1, ld, M, D, out,
+                                 rows_per_cta));
   PEVIT_CHECK_LAUNCH();
   return 0;
 }
@@ -310,21 +323,23 @@ int kad_factor_grads(cudaStream_t s, const float* dP, const float* dQ, const flo
                      float* dv2, float* dsfac, float* dtfac) {
   ProfScope prof(s, PC_FACTOR_GRADS);
   const size_t smem = (4 * static_cast<size_t>(D) + 2 * (D / 32) + 128) * sizeof(float);
-  kad_factor_grads_kernel<<<32, 256, smem, s>>>(dP, dQ, u1, v1, u2, v2, sfac, tfac, D, du1, dv1, du2, dv2, dsfac, dtfac);
+  PEVIT_CHECK_CUDA(launch_kernel(kad_factor_grads_kernel, dim3(32), dim3(256), smem, s, 1, dP, dQ, u1, v1, u2, v2, sfac, tfac, D,
+                                 du1, dv1, du2, dv2, dsfac, dtfac));
   PEVIT_CHECK_LAUNCH();
   return 0;
 }
 
 int cast_f32_to_bf16_2d(cudaStream_t s, const float* src, int lds, bf16* dst, int ldd, int rows, int cols) {
   ProfScope prof(s, PC_CAST);
-  cast2d_kernel<<<grid_for(static_cast<size_t>(rows) * cols, 256), 256, 0, s>>>(src, lds, dst, ldd, rows, cols);
+  PEVIT_CHECK_CUDA(launch_kernel(cast2d_kernel, dim3(grid_for(static_cast<size_t>(rows) * cols, 256)), dim3(256), 0, s, 1, src,
+                                 lds, dst, ldd, rows, cols));
   PEVIT_CHECK_LAUNCH();
   return 0;
 }
 
 int cast_f32_to_bf16(cudaStream_t s, const float* src, bf16* dst, size_t n) {
   ProfScope prof(s, PC_CAST);
-  cast_kernel<<<grid_for(n, 256), 256, 0, s>>>(src, dst, n);
+  PEVIT_CHECK_CUDA(launch_kernel(cast_kernel, dim3(grid_for(n, 256)), dim3(256), 0, s, 1, src, dst, n));
   PEVIT_CHECK_LAUNCH();
   return 0;
 }

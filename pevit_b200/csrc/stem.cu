@@ -13,6 +13,8 @@ namespace {
 // patches[(n*G + gy)*G + gx][c*p*p + i*p + j] = img[n][c][gy*p + i][gx*p + j]   (bf16, K padded with zeros)
 __global__ void im2col_kernel(const float* __restrict__ img, bf16* __restrict__ patches, int NB, int R, int p, int G,
                               int K, int Kpad) {
+  pdl_launch_dependents();
+  pdl_wait();
   const int row = blockIdx.x;  // (n, gy, gx)
   const int n = row / (G * G), g = row - n * G * G;
   const int gy = g / G, gx = g - gy * G;
@@ -38,6 +40,8 @@ __global__ void __launch_bounds__(FIN_THREADS)
 embed_finalize_kernel(const float* __restrict__ emb, const float* __restrict__ cls, const float* __restrict__ pos,
                       const float* __restrict__ gamma, const float* __restrict__ beta, float* __restrict__ x, int NB,
                       int L, int D) {
+  pdl_launch_dependents();
+  pdl_wait();
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int row = blockIdx.x * (FIN_THREADS / 32) + warp;  // output row in LND order
   if (row >= L * NB) return;
@@ -94,7 +98,7 @@ int patch_embed(cudaStream_t s, const float* img, const bf16* w_patch, const flo
                                         ((static_cast<size_t>(rows) * Kpad * sizeof(bf16) + 255) & ~size_t(255)));
   {
     ProfScope prof(s, PC_STEM);
-    im2col_kernel<<<rows, 256, 0, s>>>(img, patches, NB, R, p, G, K, Kpad);
+    PEVIT_CHECK_CUDA(launch_kernel(im2col_kernel, dim3(rows), dim3(256), 0, s, 1, img, patches, NB, R, p, G, K, Kpad));
     PEVIT_CHECK_LAUNCH();
   }
   GemmEpilogue ep;
@@ -106,7 +110,7 @@ int patch_embed(cudaStream_t s, const float* img, const bf16* w_patch, const flo
   {
     ProfScope prof(s, PC_STEM);
     const int grid = (L * NB + FIN_THREADS / 32 - 1) / (FIN_THREADS / 32);
-    embed_finalize_kernel<<<grid, FIN_THREADS, 0, s>>>(emb, cls, pos, ln_g, ln_b, x, NB, L, D);
+    PEVIT_CHECK_CUDA(launch_kernel(embed_finalize_kernel, dim3(grid), dim3(FIN_THREADS), 0, s, 1, emb, cls, pos, ln_g, ln_b, x, NB, L, D));
     PEVIT_CHECK_LAUNCH();
   }
   return 0;
