@@ -99,6 +99,9 @@ int make_tmap_bf16_2d(CUtensorMap* out, const void* base, uint64_t rows, uint64_
 // 2-D output tensor map for TMA stores (bf16: elem_bytes 2, fp32: 4); box rows x (128 / elem_bytes) columns.
 int make_tmap_out_2d(CUtensorMap* out, const void* base, uint64_t rows, uint64_t cols, uint64_t row_stride_elems,
                      uint32_t box_rows, int elem_bytes);
+// Head-major q/k/v [3][NB][H][L][64] bf16 as a 5-D tensor (64, L, H, NB, 3) with box (64, 1, 1, box_n, 1): one TMA
+// store scatters the 64-column head slice of box_n consecutive images (same token l) to their head-major rows.
+int make_tmap_qkv_hm_5d(CUtensorMap* out, const void* base, int L, int NB, int H, uint32_t box_n);
 // Token-major [L][NB][H][64] bf16 activations viewed per head: dims (64, H, NB, L), box (64, 1, 1, box_l):
 // one TMA brings the L rows of one (image, head) into a [box_l][64] 128B-swizzled tile.
 int make_tmap_bf16_tok_heads(CUtensorMap* out, const void* base, int L, int NB, int H, uint64_t row_stride_elems,
@@ -210,6 +213,19 @@ __device__ __forceinline__ void tma_load_2d(void* smem_dst, const CUtensorMap* m
 __device__ __forceinline__ void tma_store_2d(const CUtensorMap* m, const void* smem_src, int32_t c0, int32_t c1) {
   asm volatile("cp.async.bulk.tensor.2d.global.shared::cta.bulk_group [%0, {%2, %3}], [%1];"
                ::"l"(reinterpret_cast<uint64_t>(m)), "r"(smem_u32(smem_src)), "r"(c0), "r"(c1)
+               : "memory");
+}
+// 5-D store (head-major q/k/v scatter of the in-projection epilogue)
+__device__ __forceinline__ void tma_store_5d(const CUtensorMap* m, const void* smem_src, int32_t c0, int32_t c1,
+                                             int32_t c2, int32_t c3, int32_t c4) {
+  asm volatile("cp.async.bulk.tensor.5d.global.shared::cta.bulk_group [%0, {%2, %3, %4, %5, %6}], [%1];"
+               ::"l"(reinterpret_cast<uint64_t>(m)), "r"(smem_u32(smem_src)), "r"(c0), "r"(c1), "r"(c2), "r"(c3), "r"(c4)
+               : "memory");
+}
+// pull one box of a tensor into L2 (no shared-memory destination, no completion tracking)
+__device__ __forceinline__ void tma_prefetch_l2_2d(const CUtensorMap* m, int32_t c0, int32_t c1) {
+  asm volatile("cp.async.bulk.prefetch.tensor.2d.L2.global [%0, {%1, %2}];"
+               ::"l"(reinterpret_cast<uint64_t>(m)), "r"(c0), "r"(c1)
                : "memory");
 }
 __device__ __forceinline__ void tma_store_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }

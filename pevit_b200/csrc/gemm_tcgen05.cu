@@ -21,14 +21,14 @@ constexpr int BM = 128;
 constexpr int BK = 64;  // 64 bf16 = one 128-byte swizzle row
 constexpr int GEMM_THREADS = 320;  // TMA warp, MMA warp, 2 x 4 epilogue warps
 
-template <int BN, bool CTA2>
+template <int BN, bool CTA2, bool TS>
 struct TileCfg {
   // CTA2: two CTAs (one TPC) share a 256 x BN tile; each stages its own 128 A rows and HALF of B's rows
   static constexpr int B_ROWS = CTA2 ? BN / 2 : BN;
   static constexpr int A_BYTES = BM * BK * 2;
   static constexpr int B_BYTES = B_ROWS * BK * 2;
   static constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
-  static constexpr int STAGING_BYTES = 2 * 16384;  // two [128 rows][128 B] TMA-store boxes
+  static constexpr int STAGING_BYTES = TS ? 4 * 16384 : 0;  // staged epilogue: 2 warpgroups x 2 [128 rows][128 B] boxes
   static constexpr int STAGES_FIT = (227 * 1024 - STAGING_BYTES - 2048) / STAGE_BYTES;
   static constexpr int STAGES = STAGES_FIT > 8 ? 8 : STAGES_FIT;
   static constexpr int TMEM_COLS = 2 * BN <= 32 ? 32 : (2 * BN <= 64 ? 64 : (2 * BN <= 128 ? 128 : (2 * BN <= 256 ? 256 : 512)));  // two accumulator stages, power of two
@@ -222,46 +222,22 @@ __device__ __forceinline__ void epilogue_chunk(const GemmEpilogue& ep, int m, in
   }
 }
 
-// Staged epilogue.  The per-row residual / auxiliary operands of a 32-column chunk are fetched one chunk
-// ahead (EpiAux) so their L2 latency overlaps the previous chunk's math instead of serialising with it.
-struct EpiAux {
-  uint4 r[16];  // EPI_F32: resid (8) + resid2 (8) as float4 bits; EPI_BF16 / EPI_DACT: 4 x uint4 of bf16
-};
+// Staged ("box") epilogue.  A box is [128 rows][128 B] of shared memory in the 128B-swizzled layout TMA reads and
+// writes: 32 fp32 or 64 bf16 output columns of the tile.  An auxiliary operand of the epilogue (fp32 residual, bf16
+// residual of the in-place delta, saved pre-activation z) is TMA-loaded INTO the box, combined in place with the
+// accumulator by the thread that owns the row, and the box leaves through a TMA store -- every global access of the
+// epilogue is a bulk, coalesced, asynchronous copy.
+constexpr int BOX_BYTES = 16384;
 
+// 32 accumulator columns of one row -> the row's slice of the box.  `rowp` = box + row * 128, `r7` = row & 7,
+// `sub` = which 64-byte half of the row (bf16 boxes hold two 32-column halves; fp32 boxes one: the whole row).
 template <int EPI>
-__device__ __forceinline__ void epilogue_prefetch(const GemmEpilogue& ep, int m, int c0, bool ok, EpiAux& x) {
-  const size_t off = static_cast<size_t>(m) * ep.ld_out + c0;
-  if constexpr (epi_base(EPI) == EPI_F32) {
-    if (ep.resid != nullptr) {
-#pragma unroll
-      for (int q = 0; q < 8; ++q)
-        x.r[q] = ok ? *reinterpret_cast<const uint4*>(ep.resid + off + 4 * q) : make_uint4(0, 0, 0, 0);
-    }
-    if (ep.resid2 != nullptr) {
-#pragma unroll
-      for (int q = 0; q < 8; ++q)
-        x.r[8 + q] = ok ? *reinterpret_cast<const uint4*>(ep.resid2 + off + 4 * q) : make_uint4(0, 0, 0, 0);
-    }
-  } else if constexpr (epi_base(EPI) == EPI_BF16) {
-    if (ep.resid_bf16 != nullptr) {
-#pragma unroll
-      for (int q = 0; q < 4; ++q)
-        x.r[q] = ok ? *reinterpret_cast<const uint4*>(ep.resid_bf16 + off + 8 * q) : make_uint4(0, 0, 0, 0);
-    }
-  } else if constexpr (epi_base(EPI) == EPI_DACT) {
-#pragma unroll
-    for (int q = 0; q < 4; ++q)
-      x.r[q] = ok ? *reinterpret_cast<const uint4*>(ep.aux_bf16 + off + 8 * q) : make_uint4(0, 0, 0, 0);
-  }
-}
-
-// final values of one 32-column chunk (second output z for EPI_ACT).  Requires N % 32 == 0.
-template <int EPI>
-__device__ __forceinline__ void epilogue_values(const GemmEpilogue& ep, int c0, const EpiAux& x, uint32_t (&v)[32],
-                                                float (&a)[32], float (&z)[32]) {
+__device__ __forceinline__ void box_half(const GemmEpilogue& ep, int c0, bool has_aux, uint8_t* rowp, uint8_t* rowp2,
+                                         int r7, int sub, float scale, uint32_t (&v)[32]) {
+  float a[32];
 #pragma unroll
   for (int j = 0; j < 32; ++j) a[j] = __uint_as_float(v[j]);
-  if (ep.bias != nullptr) {
+  if (ep.bias != nullptr && !(epi_base(EPI) == EPI_QKV && c0 >= 3 * ep.D)) {
 #pragma unroll
     for (int j = 0; j < 32; j += 4) {
       const float4 b = __ldg(reinterpret_cast<const float4*>(ep.bias + c0 + j));
@@ -269,73 +245,71 @@ __device__ __forceinline__ void epilogue_values(const GemmEpilogue& ep, int c0, 
     }
   }
   if constexpr (epi_base(EPI) == EPI_F32) {
-    if (ep.resid != nullptr) {
 #pragma unroll
-      for (int q = 0; q < 8; ++q) {
-        a[4 * q] += __uint_as_float(x.r[q].x); a[4 * q + 1] += __uint_as_float(x.r[q].y);
-        a[4 * q + 2] += __uint_as_float(x.r[q].z); a[4 * q + 3] += __uint_as_float(x.r[q].w);
-      }
-    }
-    if (ep.resid2 != nullptr) {
-#pragma unroll
-      for (int q = 0; q < 8; ++q) {
-        a[4 * q] += __uint_as_float(x.r[8 + q].x); a[4 * q + 1] += __uint_as_float(x.r[8 + q].y);
-        a[4 * q + 2] += __uint_as_float(x.r[8 + q].z); a[4 * q + 3] += __uint_as_float(x.r[8 + q].w);
-      }
-    }
-  } else if constexpr (epi_base(EPI) == EPI_BF16) {
-    if (ep.resid_bf16 != nullptr) {
-#pragma unroll
-      for (int q = 0; q < 4; ++q) {
-        const uint32_t rw[4] = {x.r[q].x, x.r[q].y, x.r[q].z, x.r[q].w};
-#pragma unroll
-        for (int t = 0; t < 4; ++t) {
-          const float2 f = unpack_bf16(rw[t]);
-          a[8 * q + 2 * t] += f.x;
-          a[8 * q + 2 * t + 1] += f.y;
-        }
-      }
+    for (int q = 0; q < 8; ++q) {
+      float4* p = reinterpret_cast<float4*>(rowp + ((q ^ r7) << 4));
+      float4 o = make_float4(a[4 * q], a[4 * q + 1], a[4 * q + 2], a[4 * q + 3]);
+      if (has_aux) { const float4 r = *p; o.x += r.x; o.y += r.y; o.z += r.z; o.w += r.w; }
+      *p = o;
     }
   } else if constexpr (epi_base(EPI) == EPI_ACT) {
 #pragma unroll
-    for (int j = 0; j < 32; ++j) { z[j] = a[j]; a[j] = act_fwd<epi_act(EPI)>(a[j]); }
-  } else if constexpr (epi_base(EPI) == EPI_DACT) {
+    for (int q = 0; q < 4; ++q) {
+      const int off = ((sub * 4 + q) ^ r7) << 4;
+      float h[8];
+#pragma unroll
+      for (int t = 0; t < 8; ++t) h[t] = act_fwd<epi_act(EPI)>(a[8 * q + t]);
+      *reinterpret_cast<uint4*>(rowp + off) = make_uint4(pack_bf16(h[0], h[1]), pack_bf16(h[2], h[3]),
+                                                         pack_bf16(h[4], h[5]), pack_bf16(h[6], h[7]));
+      if (rowp2 != nullptr)
+        *reinterpret_cast<uint4*>(rowp2 + off) =
+            make_uint4(pack_bf16(a[8 * q], a[8 * q + 1]), pack_bf16(a[8 * q + 2], a[8 * q + 3]),
+                       pack_bf16(a[8 * q + 4], a[8 * q + 5]), pack_bf16(a[8 * q + 6], a[8 * q + 7]));
+    }
+  } else {  // EPI_BF16 (+ in-place bf16 residual), EPI_DACT (x act'(z)), EPI_QKV (x scale)
 #pragma unroll
     for (int q = 0; q < 4; ++q) {
-      const uint32_t zw[4] = {x.r[q].x, x.r[q].y, x.r[q].z, x.r[q].w};
+      uint4* p = reinterpret_cast<uint4*>(rowp + (((sub * 4 + q) ^ r7) << 4));
+      if (epi_base(EPI) == EPI_DACT || (epi_base(EPI) == EPI_BF16 && has_aux)) {
+        const uint4 x = *p;
+        const uint32_t w[4] = {x.x, x.y, x.z, x.w};
 #pragma unroll
-      for (int t = 0; t < 4; ++t) {
-        const float2 f = unpack_bf16(zw[t]);
-        a[8 * q + 2 * t] *= act_bwd<epi_act(EPI)>(f.x);
-        a[8 * q + 2 * t + 1] *= act_bwd<epi_act(EPI)>(f.y);
+        for (int t = 0; t < 4; ++t) {
+          const float2 f = unpack_bf16(w[t]);
+          if constexpr (epi_base(EPI) == EPI_DACT) {
+            a[8 * q + 2 * t] *= act_bwd<epi_act(EPI)>(f.x);
+            a[8 * q + 2 * t + 1] *= act_bwd<epi_act(EPI)>(f.y);
+          } else {
+            a[8 * q + 2 * t] += f.x;
+            a[8 * q + 2 * t + 1] += f.y;
+          }
+        }
       }
+      if constexpr (epi_base(EPI) == EPI_QKV) {
+#pragma unroll
+        for (int t = 0; t < 8; ++t) a[8 * q + t] *= scale;
+      }
+      *p = make_uint4(pack_bf16(a[8 * q], a[8 * q + 1]), pack_bf16(a[8 * q + 2], a[8 * q + 3]),
+                      pack_bf16(a[8 * q + 4], a[8 * q + 5]), pack_bf16(a[8 * q + 6], a[8 * q + 7]));
     }
   }
-}
-
-// 32 fp32 values -> one row of a 128B-swizzled staging box (fp32: the whole 128-B row; bf16: half `sub` of it)
-__device__ __forceinline__ void stage_row_f32(uint8_t* box, int row, const float (&a)[32]) {
-#pragma unroll
-  for (int q = 0; q < 8; ++q)
-    *reinterpret_cast<float4*>(box + row * 128 + ((q ^ (row & 7)) << 4)) =
-        make_float4(a[4 * q], a[4 * q + 1], a[4 * q + 2], a[4 * q + 3]);
-}
-__device__ __forceinline__ void stage_row_bf16(uint8_t* box, int row, int sub, const float (&a)[32]) {
-#pragma unroll
-  for (int q = 0; q < 4; ++q)
-    *reinterpret_cast<uint4*>(box + row * 128 + (((sub * 4 + q) ^ (row & 7)) << 4)) =
-        make_uint4(pack_bf16(a[8 * q], a[8 * q + 1]), pack_bf16(a[8 * q + 2], a[8 * q + 3]),
-                   pack_bf16(a[8 * q + 4], a[8 * q + 5]), pack_bf16(a[8 * q + 6], a[8 * q + 7]));
 }
 
 template <int BN, int EPI, bool TS, bool CTA2>
 __global__ void __launch_bounds__(GEMM_THREADS, 1)
 gemm_tn_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_b,
                const __grid_constant__ CUtensorMap tmap_c, const __grid_constant__ CUtensorMap tmap_c2,
-               int M, int N, int K, GemmEpilogue ep) {
-  using Cfg = TileCfg<BN, CTA2>;
+               const __grid_constant__ CUtensorMap tmap_aux, int M, int N, int K, GemmEpilogue ep) {
+  using Cfg = TileCfg<BN, CTA2, TS>;
   constexpr int STAGES = Cfg::STAGES;
   constexpr int TILE_M = CTA2 ? 2 * BM : BM;  // rows of C covered by one (pair of) CTA(s) per tile
+  // staged epilogue geometry (see box_half): columns per box, boxes per tile
+  constexpr bool kF32 = (epi_base(EPI) == EPI_F32);
+  constexpr bool kTwo = (epi_base(EPI) == EPI_ACT);  // h and z leave together, one box each
+  constexpr bool kQKV = (epi_base(EPI) == EPI_QKV);
+  constexpr int BOXCOLS = kF32 ? 32 : 64;
+  constexpr int NBOXES = BN / BOXCOLS;
+  static_assert(!TS || NBOXES >= 1, "staged epilogue needs at least one box per tile");
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   uint8_t* staging = smem + STAGES * Cfg::STAGE_BYTES;  // 1024-aligned: STAGE_BYTES is a multiple of 1024
@@ -343,7 +317,8 @@ gemm_tn_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
   uint64_t* empty_bar = full_bar + STAGES;
   uint64_t* tfull_bar = empty_bar + STAGES;
   uint64_t* tempty_bar = tfull_bar + 2;
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tempty_bar + 2);
+  uint64_t* aux_bar = tempty_bar + 2;  // [2 warpgroups][2 boxes]
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(aux_bar + 4);
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
@@ -354,10 +329,18 @@ gemm_tn_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
   const uint32_t cta_rank = CTA2 ? cluster_ctarank() : 0u;       // 0 = leader (issues the MMAs)
   const int first_tile = CTA2 ? static_cast<int>(blockIdx.x >> 1) : static_cast<int>(blockIdx.x);
   const int tile_step = CTA2 ? static_cast<int>(gridDim.x >> 1) : static_cast<int>(gridDim.x);
+  // auxiliary epilogue operand that is TMA-loaded into the boxes (staged epilogue only)
+  const bool has_aux = TS && (kF32 ? ep.resid != nullptr
+                                   : (epi_base(EPI) == EPI_BF16 ? ep.resid_bf16 != nullptr : epi_base(EPI) == EPI_DACT));
 
   if (warp == 0 && lane == 0) {
     tma_prefetch_desc(&tmap_a);
     tma_prefetch_desc(&tmap_b);
+    if constexpr (TS) {
+      tma_prefetch_desc(&tmap_c);
+      if (kTwo || kQKV) tma_prefetch_desc(&tmap_c2);
+      if (has_aux) tma_prefetch_desc(&tmap_aux);
+    }
   }
   if (warp == 1 && lane == 0) {
     for (int s = 0; s < STAGES; ++s) {
@@ -368,6 +351,7 @@ gemm_tn_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
       mbar_init(&tfull_bar[s], 1);
       mbar_init(&tempty_bar[s], CTA2 ? 16 : 8);  // one arrive per epilogue warp (of both CTAs)
     }
+    for (int s = 0; s < 4; ++s) mbar_init(&aux_bar[s], 1);
     fence_mbar_init();
   }
   if (warp == 2) {
@@ -390,6 +374,13 @@ gemm_tn_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
       for (int tile = first_tile; tile < num_tiles; tile += tile_step) {
         const int m0 = (tile / tiles_n) * TILE_M + static_cast<int>(cta_rank) * BM;
         const int n0 = (tile % tiles_n) * BN + static_cast<int>(cta_rank) * Cfg::B_ROWS * (CTA2 ? 1 : 0);
+        if (has_aux) {
+          // pull this tile's auxiliary boxes into L2 a whole mainloop ahead of the epilogue that consumes them
+          const int nt = (tile % tiles_n) * BN;
+#pragma unroll 1
+          for (int j = 0; j < NBOXES; ++j)
+            if (nt + j * BOXCOLS < N) tma_prefetch_l2_2d(&tmap_aux, nt + j * BOXCOLS, m0);
+        }
         for (int kb = 0; kb < num_kb; ++kb) {
           mbar_wait(&empty_bar[stage], phase ^ 1);
           uint8_t* sa = smem + stage * Cfg::STAGE_BYTES;
@@ -450,22 +441,21 @@ gemm_tn_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
     }
   } else {
     // ------------------------------------------------------------ epilogue: two warpgroups (warps 2-5, 6-9)
-    // Both warpgroups cover all 128 accumulator rows (TMEM lane quadrant = warp % 4) and take alternate
-    // 32-column chunks, which doubles the loads in flight for the residual / auxiliary operands.
+    // Both warpgroups cover all 128 accumulator rows (TMEM lane quadrant = warp % 4).
     const int quad = warp & 3;          // TMEM lane quadrant this warp may read
     const int wg = (warp - 2) >> 2;     // 0 or 1
-    int it = 0;
-    int box_count = 0;
-    for (int tile = first_tile; tile < num_tiles; tile += tile_step, ++it) {
-      const int acc = it & 1;
-      const uint32_t acc_phase = (it >> 1) & 1;
-      const int m_base = (tile / tiles_n) * TILE_M + static_cast<int>(cta_rank) * BM;
-      const int m = m_base + quad * 32 + lane;
-      const int n0 = (tile % tiles_n) * BN;
-      mbar_wait(&tfull_bar[acc], acc_phase);
-      tc_fence_after();
-      const uint32_t t_row = tmem_base + (static_cast<uint32_t>(quad * 32) << 16) + acc * BN;
-      if constexpr (!TS) {
+    if constexpr (!TS) {
+      // direct stores: the warpgroups take alternate 32-column chunks of every tile
+      int it = 0;
+      for (int tile = first_tile; tile < num_tiles; tile += tile_step, ++it) {
+        const int acc = it & 1;
+        const uint32_t acc_phase = (it >> 1) & 1;
+        const int m_base = (tile / tiles_n) * TILE_M + static_cast<int>(cta_rank) * BM;
+        const int m = m_base + quad * 32 + lane;
+        const int n0 = (tile % tiles_n) * BN;
+        mbar_wait(&tfull_bar[acc], acc_phase);
+        tc_fence_after();
+        const uint32_t t_row = tmem_base + (static_cast<uint32_t>(quad * 32) << 16) + acc * BN;
 #pragma unroll 1
         for (int c = wg * 32; c < BN; c += 64) {
           uint32_t v[32];
@@ -473,66 +463,117 @@ gemm_tn_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
           tmem_ld_wait();
           if (m < M && n0 + c < N) epilogue_chunk<EPI>(ep, m, n0 + c, v, N);
         }
-      } else {
-        // Staged epilogue: rows are written into 128B-swizzled [128][128 B] boxes in shared memory and
-        // leave through TMA stores (coalesced, clipped at M / N).
-        //   bf16 outputs: a box is 64 columns = one chunk from each warpgroup; two boxes alternate.
-        //   fp32 outputs: a box is 32 columns = one chunk; each warpgroup owns one box and its own stores.
-        constexpr bool kF32 = (epi_base(EPI) == EPI_F32);
-        constexpr bool kTwo = (epi_base(EPI) == EPI_ACT);            // h and z leave together
-        const int row = quad * 32 + lane;
-        const int m0 = m_base;
-        const bool two = kTwo && ep.out2_bf16 != nullptr;
-        const bool elected = kF32 ? (threadIdx.x == 64 + wg * 128) : (threadIdx.x == 64);
-        EpiAux aux_cur, aux_next;
-        epilogue_prefetch<EPI>(ep, m, n0 + wg * 32, m < M && n0 + wg * 32 < N, aux_cur);
-#pragma unroll 1
-        for (int c = wg * 32; c < BN; c += 64) {
-          uint32_t v[32];
-          tmem_ld_32x32(t_row + c, v);
-          epilogue_prefetch<EPI>(ep, m, n0 + c + 64, m < M && c + 64 < BN && n0 + c + 64 < N, aux_next);
-          tmem_ld_wait();
-          if (n0 + c >= N || (ep.debug & 4)) continue;     // uniform over both warpgroups (N % 64 == 0)
-          float a[32], z[32];
-          epilogue_values<EPI>(ep, n0 + c, aux_cur, v, a, z);
-          aux_cur = aux_next;
-          if constexpr (kF32) {
-            uint8_t* box = staging + wg * 16384;
-            if (elected) tma_store_wait_read<0>();         // this warpgroup's previous store has drained the box
-            if (wg == 0) named_bar_sync(1, 128); else named_bar_sync(2, 128);
-            stage_row_f32(box, row, a);
-            fence_proxy_async_smem();
-            if (wg == 0) named_bar_sync(1, 128); else named_bar_sync(2, 128);
-            if (elected) {
-              tma_store_2d(&tmap_c, box, n0 + c, m0);
-              tma_store_commit();
-            }
-          } else {
-            const int buf = kTwo ? 0 : (box_count & 1);
-            if (elected) { if (kTwo) tma_store_wait_read<0>(); else tma_store_wait_read<1>(); }
-            named_bar_sync(1, 256);
-            stage_row_bf16(staging + buf * 16384, row, wg, a);
-            if constexpr (kTwo) { if (two) stage_row_bf16(staging + 16384, row, wg, z); }
-            fence_proxy_async_smem();
-            named_bar_sync(1, 256);
-            if (elected) {
-              tma_store_2d(&tmap_c, staging + buf * 16384, n0 + c, m0);   // wg 0 elects: c is the box's first column
-              if (two) tma_store_2d(&tmap_c2, staging + 16384, n0 + c, m0);
-              tma_store_commit();
-            }
-            ++box_count;
-          }
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) {
+          if constexpr (CTA2) mbar_arrive_cluster(&tempty_bar[acc], 0);  // the leader's MMA warp owns the accumulators
+          else mbar_arrive(&tempty_bar[acc]);
         }
       }
-      tc_fence_before();
-      __syncwarp();
-      if (lane == 0) {
-        if constexpr (CTA2) mbar_arrive_cluster(&tempty_bar[acc], 0);  // the leader's MMA warp owns the accumulators
-        else mbar_arrive(&tempty_bar[acc]);
+    } else {
+      // Staged epilogue.  Boxes of the CTA's tile sequence are numbered b = it * NBOXES + j; warpgroup wg owns the
+      // boxes with b % 2 == wg and a private ring of two box buffers:
+      //   [aux TMA load -> box] -> accumulator (+bias) combined in place -> fence -> barrier -> TMA store
+      // The elected thread drains the previous store (other buffer) before the barrier, so right after it the
+      // other buffer is free for the next box's aux load / data.
+      uint8_t* my_boxes = staging + wg * 2 * BOX_BYTES;
+      uint64_t* my_aux = aux_bar + wg * 2;
+      const int row = quad * 32 + lane, r7 = row & 7;
+      const bool elected = (threadIdx.x == 64 + wg * 128);
+      const int bar_id = 1 + wg;
+      auto first_j = [&](int it_) { return (wg ^ ((it_ * NBOXES) & 1)) & 1; };
+      // cursor over this warpgroup's boxes, one ahead of the consumer (aux prefetch)
+      int la_it = 0, la_j = first_j(0);
+      auto la_seek = [&]() -> bool {
+        for (;;) {
+          const int tile_ = first_tile + la_it * tile_step;
+          if (tile_ >= num_tiles) return false;
+          if (la_j < NBOXES && (tile_ % tiles_n) * BN + la_j * BOXCOLS < N) return true;
+          ++la_it;
+          la_j = first_j(la_it);
+        }
+      };
+      auto la_issue = [&](int slot) {  // elected only
+        if (!la_seek()) return;
+        const int tile_ = first_tile + la_it * tile_step;
+        const int m0_ = (tile_ / tiles_n) * TILE_M + static_cast<int>(cta_rank) * BM;
+        const int c0_ = (tile_ % tiles_n) * BN + la_j * BOXCOLS;
+        mbar_expect_tx(&my_aux[slot], BOX_BYTES);
+        tma_load_2d(my_boxes + slot * BOX_BYTES, &tmap_aux, &my_aux[slot], c0_, m0_);
+        la_j += 2;
+      };
+      if (has_aux && elected) la_issue(0);
+      int g = 0;  // boxes processed by this warpgroup
+      int it = 0;
+      for (int tile = first_tile; tile < num_tiles; tile += tile_step, ++it) {
+        const int acc = it & 1;
+        const uint32_t acc_phase = (it >> 1) & 1;
+        const int m0 = (tile / tiles_n) * TILE_M + static_cast<int>(cta_rank) * BM;
+        const int n0 = (tile % tiles_n) * BN;
+        mbar_wait(&tfull_bar[acc], acc_phase);
+        tc_fence_after();
+        const uint32_t t_row = tmem_base + (static_cast<uint32_t>(quad * 32) << 16) + acc * BN;
+#pragma unroll 1
+        for (int j = first_j(it); j < NBOXES; j += 2) {
+          const int c0 = n0 + j * BOXCOLS;
+          if (c0 >= N) break;
+          const int slot = kTwo ? 0 : (g & 1);
+          uint8_t* box = my_boxes + slot * BOX_BYTES;
+          uint8_t* rowp = box + row * 128;
+          uint8_t* rowp2 = (kTwo && ep.out2_bf16 != nullptr) ? rowp + BOX_BYTES : nullptr;
+          float scale = 1.f;
+          if constexpr (kQKV) scale = c0 < ep.D ? 0.125f : 1.f;
+          if (has_aux) mbar_wait(&my_aux[slot], (g >> 1) & 1);
+          if constexpr (kF32) {
+            uint32_t v[32];
+            tmem_ld_32x32(t_row + j * 32, v);
+            tmem_ld_wait();
+            if (!(ep.debug & 4)) box_half<EPI>(ep, c0, has_aux, rowp, nullptr, r7, 0, 1.f, v);
+          } else {
+#pragma unroll
+            for (int sub = 0; sub < 2; ++sub) {
+              uint32_t v[32];
+              tmem_ld_32x32(t_row + j * 64 + sub * 32, v);
+              tmem_ld_wait();
+              if constexpr (kTwo) {
+                if (sub == 0) {  // both buffers are about to be rewritten: the previous h / z stores must have drained
+                  if (elected) tma_store_wait_read<0>();
+                  named_bar_sync(bar_id, 128);
+                }
+              }
+              if (!(ep.debug & 4)) box_half<EPI>(ep, c0 + sub * 32, has_aux, rowp, rowp2, r7, sub, scale, v);
+            }
+          }
+          fence_proxy_async_smem();
+          if constexpr (!kTwo) {
+            if (elected) tma_store_wait_read<0>();  // store of box g-1 (other buffer) drained
+          }
+          named_bar_sync(bar_id, 128);
+          if (elected) {
+            if constexpr (kQKV) {
+              if (c0 < 3 * ep.D) {
+                const int which = c0 / ep.D, h = (c0 - which * ep.D) >> 6;
+                tma_store_5d(&tmap_c, box, 0, m0 / ep.NB, h, m0 % ep.NB, which);  // [64 d][l][h][n][which]
+              } else {
+                tma_store_2d(&tmap_c2, box, c0 - 3 * ep.D, m0);                    // T columns
+              }
+            } else {
+              tma_store_2d(&tmap_c, box, c0, m0);
+              if constexpr (kTwo) { if (rowp2 != nullptr) tma_store_2d(&tmap_c2, box + BOX_BYTES, c0, m0); }
+            }
+            tma_store_commit();
+            if (has_aux) la_issue((g + 1) & 1);
+          }
+          ++g;
+        }
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) {
+          if constexpr (CTA2) mbar_arrive_cluster(&tempty_bar[acc], 0);  // the leader's MMA warp owns the accumulators
+          else mbar_arrive(&tempty_bar[acc]);
+        }
       }
-    }
-    if constexpr (TS) {
-      if (threadIdx.x == 64 || threadIdx.x == 192) tma_store_wait_all<0>();  // smem must outlive the last stores
+      if (elected) tma_store_wait_all<0>();  // smem must outlive the last stores
     }
   }
 
@@ -548,8 +589,8 @@ gemm_tn_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
 
 template <int BN, int EPI, bool TS, bool CTA2>
 int launch_impl(cudaStream_t stream, const CUtensorMap& ta, const CUtensorMap& tb, const CUtensorMap& tc,
-                const CUtensorMap& tc2, int M, int N, int K, const GemmEpilogue& ep) {
-  using Cfg = TileCfg<BN, CTA2>;
+                const CUtensorMap& tc2, const CUtensorMap& taux, int M, int N, int K, const GemmEpilogue& ep) {
+  using Cfg = TileCfg<BN, CTA2, TS>;
   static_assert(Cfg::STAGES >= 3, "pipeline too shallow");
   static bool configured[64] = {};  // per instantiation and device (the attribute is per context)
   auto kern = gemm_tn_kernel<BN, EPI, TS, CTA2>;
@@ -570,7 +611,7 @@ int launch_impl(cudaStream_t stream, const CUtensorMap& ta, const CUtensorMap& t
     grid = tiles < sm_count() ? tiles : sm_count();
   }
   PEVIT_CHECK_CUDA(launch_kernel(kern, dim3(grid), dim3(GEMM_THREADS), Cfg::SMEM_BYTES, stream, CTA2 ? 2 : 1, ta, tb, tc,
-                                 tc2, M, N, K, ep));
+                                 tc2, taux, M, N, K, ep));
   PEVIT_CHECK_LAUNCH();
   return 0;
 }
@@ -578,36 +619,36 @@ int launch_impl(cudaStream_t stream, const CUtensorMap& ta, const CUtensorMap& t
 // CTA pairs are used for the wide tiles of the big GEMMs; narrow tiles (skinny N) stay single-CTA.
 thread_local bool g_use_pair = false;
 
-template <int BN, int EPI, bool TS>
-int launch(cudaStream_t stream, const CUtensorMap& ta, const CUtensorMap& tb, const CUtensorMap& tc,
-           const CUtensorMap& tc2, int M, int N, int K, const GemmEpilogue& ep) {
+struct Tmaps { CUtensorMap a, b, c, c2, aux; };
+
+template <int BN, int EPI, bool TS_REQ>
+int launch(cudaStream_t stream, const Tmaps& t, int M, int N, int K, const GemmEpilogue& ep) {
+  // a tile narrower than one box (32 fp32 / 64 bf16 columns) cannot use the staged epilogue
+  constexpr bool TS = TS_REQ && BN >= (epi_base(EPI) == EPI_F32 ? 32 : 64);
   if constexpr (BN >= 128) {
-    if (g_use_pair) return launch_impl<BN, EPI, TS, true>(stream, ta, tb, tc, tc2, M, N, K, ep);
+    if (g_use_pair) return launch_impl<BN, EPI, TS, true>(stream, t.a, t.b, t.c, t.c2, t.aux, M, N, K, ep);
   }
-  return launch_impl<BN, EPI, TS, false>(stream, ta, tb, tc, tc2, M, N, K, ep);
+  return launch_impl<BN, EPI, TS, false>(stream, t.a, t.b, t.c, t.c2, t.aux, M, N, K, ep);
 }
 
 template <int BN>
-int dispatch_epi(int epi, bool ts, cudaStream_t s, const CUtensorMap& ta, const CUtensorMap& tb, const CUtensorMap& tc,
-                 const CUtensorMap& tc2, int M, int N, int K, const GemmEpilogue& ep) {
+int dispatch_epi(int epi, bool ts, cudaStream_t s, const Tmaps& t, int M, int N, int K, const GemmEpilogue& ep) {
   switch (epi) {
-    case EPI_F32: return ts ? launch<BN, EPI_F32, true>(s, ta, tb, tc, tc2, M, N, K, ep)
-                            : launch<BN, EPI_F32, false>(s, ta, tb, tc, tc2, M, N, K, ep);
-    case EPI_BF16: return ts ? launch<BN, EPI_BF16, true>(s, ta, tb, tc, tc2, M, N, K, ep)
-                             : launch<BN, EPI_BF16, false>(s, ta, tb, tc, tc2, M, N, K, ep);
+    case EPI_F32: return ts ? launch<BN, EPI_F32, true>(s, t, M, N, K, ep) : launch<BN, EPI_F32, false>(s, t, M, N, K, ep);
+    case EPI_BF16: return ts ? launch<BN, EPI_BF16, true>(s, t, M, N, K, ep) : launch<BN, EPI_BF16, false>(s, t, M, N, K, ep);
     case EPI_ACT:
       if (ep.act == ACT_QUICKGELU)
-        return ts ? launch<BN, epi_with_act(EPI_ACT, ACT_QUICKGELU), true>(s, ta, tb, tc, tc2, M, N, K, ep)
-                  : launch<BN, epi_with_act(EPI_ACT, ACT_QUICKGELU), false>(s, ta, tb, tc, tc2, M, N, K, ep);
-      if (ep.act == ACT_RELU) return launch<BN, epi_with_act(EPI_ACT, ACT_RELU), false>(s, ta, tb, tc, tc2, M, N, K, ep);
-      return launch<BN, epi_with_act(EPI_ACT, ACT_GELU_NEW), false>(s, ta, tb, tc, tc2, M, N, K, ep);
+        return ts ? launch<BN, epi_with_act(EPI_ACT, ACT_QUICKGELU), true>(s, t, M, N, K, ep)
+                  : launch<BN, epi_with_act(EPI_ACT, ACT_QUICKGELU), false>(s, t, M, N, K, ep);
+      if (ep.act == ACT_RELU) return launch<BN, epi_with_act(EPI_ACT, ACT_RELU), false>(s, t, M, N, K, ep);
+      return launch<BN, epi_with_act(EPI_ACT, ACT_GELU_NEW), false>(s, t, M, N, K, ep);
     case EPI_DACT:
       if (ep.act == ACT_QUICKGELU)
-        return ts ? launch<BN, epi_with_act(EPI_DACT, ACT_QUICKGELU), true>(s, ta, tb, tc, tc2, M, N, K, ep)
-                  : launch<BN, epi_with_act(EPI_DACT, ACT_QUICKGELU), false>(s, ta, tb, tc, tc2, M, N, K, ep);
-      if (ep.act == ACT_RELU) return launch<BN, epi_with_act(EPI_DACT, ACT_RELU), false>(s, ta, tb, tc, tc2, M, N, K, ep);
-      return launch<BN, epi_with_act(EPI_DACT, ACT_GELU_NEW), false>(s, ta, tb, tc, tc2, M, N, K, ep);
-    case EPI_QKV: return launch<BN, EPI_QKV, false>(s, ta, tb, tc, tc2, M, N, K, ep);
+        return ts ? launch<BN, epi_with_act(EPI_DACT, ACT_QUICKGELU), true>(s, t, M, N, K, ep)
+                  : launch<BN, epi_with_act(EPI_DACT, ACT_QUICKGELU), false>(s, t, M, N, K, ep);
+      if (ep.act == ACT_RELU) return launch<BN, epi_with_act(EPI_DACT, ACT_RELU), false>(s, t, M, N, K, ep);
+      return launch<BN, epi_with_act(EPI_DACT, ACT_GELU_NEW), false>(s, t, M, N, K, ep);
+    case EPI_QKV: return ts ? launch<BN, EPI_QKV, true>(s, t, M, N, K, ep) : launch<BN, EPI_QKV, false>(s, t, M, N, K, ep);
   }
   set_error("gemm_tn: unknown epilogue %d", epi);
   return -1;
@@ -662,30 +703,46 @@ int gemm_tn(cudaStream_t stream, const bf16* A, int lda, const bf16* B, int ldb,
   static const bool pair_disabled = getenv("PEVIT_GEMM_NO_PAIR") != nullptr;
   const int bn = pick_tile(M, N, force_bn, !pair_disabled, &pair);
   g_use_pair = pair;
-  CUtensorMap ta, tb, tc, tc2;
-  if (make_tmap_bf16_2d(&ta, A, M, K, lda, BM, BK) != 0) return -1;
-  if (make_tmap_bf16_2d(&tb, B, N, K, ldb, pair ? bn / 2 : bn, BK) != 0) return -1;
-  // Staged TMA-store epilogue for row-major outputs with 16-byte aligned rows; direct stores otherwise.
-  const void* out = epi == EPI_F32 ? static_cast<const void*>(ep.out_f32) : static_cast<const void*>(ep.out_bf16);
-  const int elt = epi == EPI_F32 ? 4 : 2;
-  const bool act_plain = !((epi == EPI_ACT || epi == EPI_DACT) && ep.act != ACT_QUICKGELU);  // bottleneck acts: direct
-  const bool ts = epi != EPI_QKV && act_plain && N % 64 == 0 && out != nullptr &&
-                  (reinterpret_cast<uintptr_t>(out) & 15) == 0 && (static_cast<size_t>(ep.ld_out) * elt) % 16 == 0 &&
-                  (ep.out2_bf16 == nullptr || (reinterpret_cast<uintptr_t>(ep.out2_bf16) & 15) == 0) &&
-                  force_bn >= 0;
-  tc = ta;
-  tc2 = ta;
-  if (ts) {
-    if (make_tmap_out_2d(&tc, out, M, N, ep.ld_out, BM, elt) != 0) return -1;
-    if (epi == EPI_ACT && ep.out2_bf16 != nullptr && make_tmap_out_2d(&tc2, ep.out2_bf16, M, N, ep.ld_out, BM, 2) != 0)
-      return -1;
+  Tmaps t;
+  if (make_tmap_bf16_2d(&t.a, A, M, K, lda, BM, BK) != 0) return -1;
+  if (make_tmap_bf16_2d(&t.b, B, N, K, ldb, pair ? bn / 2 : bn, BK) != 0) return -1;
+  t.c = t.a;
+  t.c2 = t.a;
+  t.aux = t.a;
+  auto aligned16 = [](const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15) == 0; };
+  bool ts = false;
+  if (epi == EPI_QKV) {
+    // staged head-major scatter: a 128-row tile must be 128 images of ONE token index, and the low-rank columns
+    // (if any) exactly one 64-column box
+    ts = force_bn >= 0 && ep.NB % 128 == 0 && (ep.r2 == 0 || ep.r2 == 64) && aligned16(ep.qkv_hm) &&
+         (ep.r2 == 0 || aligned16(ep.t_out));
+    if (ts) {
+      if (make_tmap_qkv_hm_5d(&t.c, ep.qkv_hm, ep.L, ep.NB, ep.H, BM) != 0) return -1;
+      if (ep.r2 != 0 && make_tmap_out_2d(&t.c2, ep.t_out, M, ep.r2, ep.r2, BM, 2) != 0) return -1;
+    }
+  } else {
+    // Staged TMA epilogue for row-major outputs with 16-byte aligned rows; direct stores otherwise.
+    const void* out = epi == EPI_F32 ? static_cast<const void*>(ep.out_f32) : static_cast<const void*>(ep.out_bf16);
+    const void* aux = epi == EPI_F32 ? static_cast<const void*>(ep.resid)
+                                     : (epi == EPI_BF16 ? static_cast<const void*>(ep.resid_bf16)
+                                                        : (epi == EPI_DACT ? static_cast<const void*>(ep.aux_bf16) : nullptr));
+    const int elt = epi == EPI_F32 ? 4 : 2;
+    const bool act_plain = !((epi == EPI_ACT || epi == EPI_DACT) && ep.act != ACT_QUICKGELU);  // bottleneck acts: direct
+    ts = act_plain && N % 64 == 0 && out != nullptr && aligned16(out) && aligned16(aux) && ep.resid2 == nullptr &&
+         (static_cast<size_t>(ep.ld_out) * elt) % 16 == 0 && aligned16(ep.out2_bf16) && force_bn >= 0;
+    if (ts) {
+      if (make_tmap_out_2d(&t.c, out, M, N, ep.ld_out, BM, elt) != 0) return -1;
+      if (epi == EPI_ACT && ep.out2_bf16 != nullptr && make_tmap_out_2d(&t.c2, ep.out2_bf16, M, N, ep.ld_out, BM, 2) != 0)
+        return -1;
+      if (aux != nullptr && make_tmap_out_2d(&t.aux, aux, M, N, ep.ld_out, BM, elt) != 0) return -1;
+    }
   }
   switch (bn) {
-    case 32: return dispatch_epi<32>(epi, ts, stream, ta, tb, tc, tc2, M, N, K, ep);
-    case 64: return dispatch_epi<64>(epi, ts, stream, ta, tb, tc, tc2, M, N, K, ep);
-    case 128: return dispatch_epi<128>(epi, ts, stream, ta, tb, tc, tc2, M, N, K, ep);
-    case 192: return dispatch_epi<192>(epi, ts, stream, ta, tb, tc, tc2, M, N, K, ep);
-    default: return dispatch_epi<256>(epi, ts, stream, ta, tb, tc, tc2, M, N, K, ep);
+    case 32: return dispatch_epi<32>(epi, ts, stream, t, M, N, K, ep);
+    case 64: return dispatch_epi<64>(epi, ts, stream, t, M, N, K, ep);
+    case 128: return dispatch_epi<128>(epi, ts, stream, t, M, N, K, ep);
+    case 192: return dispatch_epi<192>(epi, ts, stream, t, M, N, K, ep);
+    default: return dispatch_epi<256>(epi, ts, stream, t, M, N, K, ep);
   }
 }
 

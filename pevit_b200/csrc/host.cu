@@ -203,6 +203,28 @@ int make_tmap_out_2d(CUtensorMap* out, const void* base, uint64_t rows, uint64_t
   return 0;
 }
 
+int make_tmap_qkv_hm_5d(CUtensorMap* out, const void* base, int L, int NB, int H, uint32_t box_n) {
+  const TmapKey key{base, static_cast<uint64_t>(L), static_cast<uint64_t>(NB), static_cast<uint64_t>(H), box_n, 0, 4};
+  TmapSlot* slot = nullptr;
+  if (tmap_lookup(key, out, &slot)) return 0;
+  CUtensorMap dummy;
+  if (g_encode == nullptr && make_tmap_bf16_2d(&dummy, base, 8, 64, 64, 8, 64) != 0) return -2;  // resolves g_encode
+  const cuuint64_t l = static_cast<cuuint64_t>(L), h = static_cast<cuuint64_t>(H), nb = static_cast<cuuint64_t>(NB);
+  const cuuint64_t gdim[5] = {64, l, h, nb, 3};
+  const cuuint64_t gstride[4] = {128, l * 128, h * l * 128, nb * h * l * 128};
+  const cuuint32_t box[5] = {64, 1, 1, box_n, 1};
+  const cuuint32_t estride[5] = {1, 1, 1, 1, 1};
+  CUresult r = g_encode(out, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 5, const_cast<void*>(base), gdim, gstride, box, estride,
+                        CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                        CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) {
+    set_error("cuTensorMapEncodeTiled(5d) failed (%d): base=%p L=%d NB=%d H=%d", (int)r, base, L, NB, H);
+    return -2;
+  }
+  tmap_store(slot, key, *out);
+  return 0;
+}
+
 int make_tmap_bf16_tok_heads(CUtensorMap* out, const void* base, int L, int NB, int H, uint64_t row_stride_elems,
                              uint32_t box_l) {
   const TmapKey key{base, static_cast<uint64_t>(L), static_cast<uint64_t>(NB), row_stride_elems, static_cast<uint32_t>(H),

@@ -65,6 +65,27 @@ def test_gemm_f32_bias_resid(lib, M, N, K, bn):
         assert torch.isnan(out[:, N:]).all(), "wrote past N"
 
 
+@pytest.mark.parametrize("M,N,K,bn,epi", [
+    (1000, 768, 768, 0, "f32"), (1000, 768, 768, 0, "bf16"), (12800, 768, 768, 0, "bf16"), (5000, 192, 64, 0, "bf16"),
+    (1000, 768, 768, 64, "bf16"), (1000, 3072, 128, 1256, "bf16"), (777, 3072, 64, 192, "f32"), (300, 64, 768, 0, "bf16"),
+])
+def test_gemm_staged_no_aux(lib, M, N, K, bn, epi):
+    """Row-major outputs without a residual: the box epilogue with no auxiliary load (store ring only)."""
+    g = torch.Generator(device="cuda").manual_seed(M * 3 + N + K)
+    a = bf(torch.randn(M, K, device="cuda", generator=g))
+    b = bf(torch.randn(N, K, device="cuda", generator=g) / math.sqrt(K))
+    bias = torch.randn(N, device="cuda", generator=g)
+    ref = a.float() @ b.float().t() + bias
+    if epi == "f32":
+        out = torch.full((M, N), float("nan"), device="cuda")
+        run_gemm(lib, a, b, L.EPI_F32, bias=bias, out_f32=out, ld_out=N, force_bn=bn)
+        assert rel_inf(out, ref) < 3e-3
+    else:
+        out = torch.full((M, N), float("nan"), device="cuda", dtype=torch.bfloat16)
+        run_gemm(lib, a, b, L.EPI_BF16, bias=bias, out_bf16=out, ld_out=N, force_bn=bn)
+        assert rel_inf(out.float(), ref) < 1e-2
+
+
 def test_gemm_bf16_and_strided_out(lib):
     M, N, K = 400, 32, 768
     a = bf(torch.randn(M, K, device="cuda"))
@@ -102,7 +123,10 @@ def test_gemm_quickgelu_fwd_bwd(lib):
     assert rel_inf(dz.float(), ref) < 1e-2
 
 
-@pytest.mark.parametrize("Lt,NB,D,r2", [(50, 8, 768, 64), (5, 3, 128, 64), (197, 2, 768, 8), (50, 8, 768, 0)])
+@pytest.mark.parametrize("Lt,NB,D,r2", [(50, 8, 768, 64), (5, 3, 128, 64), (197, 2, 768, 8), (50, 8, 768, 0),
+                                        # NB % 128 == 0: staged TMA scatter (5-D tensor map) instead of direct stores
+                                        (5, 128, 768, 64), (3, 256, 128, 64), (7, 128, 256, 0), (2, 384, 768, 64),
+                                        (3, 128, 768, 8)])
 def test_gemm_qkv_epilogue(lib, Lt, NB, D, r2):
     H, M, W3 = D // 64, Lt * NB, 3 * D + r2
     x = bf(torch.randn(M, D, device="cuda"))
@@ -305,9 +329,9 @@ def test_atb_colsum_and_kad_factors(lib):
         assert rel_inf(o, p.grad) < 1e-4
 
 
-def test_gemm_delta_apply_in_place(lib):
+@pytest.mark.parametrize("M,D,K", [(400, 768, 64), (12800, 768, 64), (5000, 1024, 64), (1300, 768, 8)])
+def test_gemm_delta_apply_in_place(lib, M, D, K):
     """q' = q + (T W^T + b) accumulated in place in bf16 (EPI_BF16 with resid_bf16 aliasing the output)."""
-    M, D, K = 400, 768, 64
     T = bf(torch.randn(M, K, device="cuda") * 0.05)
     W = bf(torch.randn(D, K, device="cuda"))
     bias = torch.randn(D, device="cuda") * 0.1
