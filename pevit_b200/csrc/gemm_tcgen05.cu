@@ -21,14 +21,18 @@ constexpr int BM = 128;
 constexpr int BK = 64;  // 64 bf16 = one 128-byte swizzle row
 constexpr int GEMM_THREADS = 320;  // TMA warp, MMA warp, 2 x 4 epilogue warps
 
-template <int BN, bool CTA2, bool TS>
+// boxes per epilogue warpgroup: epilogues that may TMA-load an auxiliary operand run a 3-deep ring (load two boxes
+// ahead), the others a 2-deep one
+constexpr int epi_ring(int epi) { return (epi == EPI_F32 || epi == EPI_BF16 || epi == EPI_DACT) ? 3 : 2; }
+
+template <int BN, bool CTA2, bool TS, int RING>
 struct TileCfg {
   // CTA2: two CTAs (one TPC) share a 256 x BN tile; each stages its own 128 A rows and HALF of B's rows
   static constexpr int B_ROWS = CTA2 ? BN / 2 : BN;
   static constexpr int A_BYTES = BM * BK * 2;
   static constexpr int B_BYTES = B_ROWS * BK * 2;
   static constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
-  static constexpr int STAGING_BYTES = TS ? 4 * 16384 : 0;  // staged epilogue: 2 warpgroups x 2 [128 rows][128 B] boxes
+  static constexpr int STAGING_BYTES = TS ? 2 * RING * 16384 : 0;  // staged epilogue: 2 warpgroups x RING [128 rows][128 B] boxes
   static constexpr int STAGES_FIT = (227 * 1024 - STAGING_BYTES - 2048) / STAGE_BYTES;
   static constexpr int STAGES = STAGES_FIT > 8 ? 8 : STAGES_FIT;
   static constexpr int TMEM_COLS = 2 * BN <= 32 ? 32 : (2 * BN <= 64 ? 64 : (2 * BN <= 128 ? 128 : (2 * BN <= 256 ? 256 : 512)));  // two accumulator stages, power of two
@@ -229,20 +233,54 @@ __device__ __forceinline__ void epilogue_chunk(const GemmEpilogue& ep, int m, in
 // epilogue is a bulk, coalesced, asynchronous copy.
 constexpr int BOX_BYTES = 16384;
 
-// 32 accumulator columns of one row -> the row's slice of the box.  `rowp` = box + row * 128, `r7` = row & 7,
-// `sub` = which 64-byte half of the row (bf16 boxes hold two 32-column halves; fp32 boxes one: the whole row).
+// bias of 32 consecutive columns, fetched before the TMEM load is waited for so that its latency overlaps it
+struct BiasRegs { float4 b[8]; };
 template <int EPI>
-__device__ __forceinline__ void box_half(const GemmEpilogue& ep, int c0, bool has_aux, uint8_t* rowp, uint8_t* rowp2,
-                                         int r7, int sub, float scale, uint32_t (&v)[32]) {
+__device__ __forceinline__ void load_bias(const GemmEpilogue& ep, int c0, BiasRegs& br) {
+  const bool on = ep.bias != nullptr && !(epi_base(EPI) == EPI_QKV && c0 >= 3 * ep.D);
+#pragma unroll
+  for (int q = 0; q < 8; ++q)
+    br.b[q] = on ? __ldg(reinterpret_cast<const float4*>(ep.bias + c0) + q) : make_float4(0.f, 0.f, 0.f, 0.f);
+}
+
+// QuickGELU forward of 32 columns: packed bf16 h = act(z) and z = acc + bias
+template <int EPI>
+__device__ __forceinline__ void act_half_compute(const BiasRegs& br, const uint32_t (&v)[32], uint32_t (&hp)[16],
+                                                 uint32_t (&zp)[16]) {
+#pragma unroll
+  for (int q = 0; q < 8; ++q) {
+    const float z0 = __uint_as_float(v[4 * q]) + br.b[q].x, z1 = __uint_as_float(v[4 * q + 1]) + br.b[q].y;
+    const float z2 = __uint_as_float(v[4 * q + 2]) + br.b[q].z, z3 = __uint_as_float(v[4 * q + 3]) + br.b[q].w;
+    zp[2 * q] = pack_bf16(z0, z1);
+    zp[2 * q + 1] = pack_bf16(z2, z3);
+    hp[2 * q] = pack_bf16(act_fwd<epi_act(EPI)>(z0), act_fwd<epi_act(EPI)>(z1));
+    hp[2 * q + 1] = pack_bf16(act_fwd<epi_act(EPI)>(z2), act_fwd<epi_act(EPI)>(z3));
+  }
+}
+__device__ __forceinline__ void act_half_store(uint8_t* rowp, uint8_t* rowp2, int r7, int sub, const uint32_t (&hp)[16],
+                                               const uint32_t (&zp)[16]) {
+#pragma unroll
+  for (int q = 0; q < 4; ++q) {
+    const int off = ((sub * 4 + q) ^ r7) << 4;
+    *reinterpret_cast<uint4*>(rowp + off) = make_uint4(hp[4 * q], hp[4 * q + 1], hp[4 * q + 2], hp[4 * q + 3]);
+    if (rowp2 != nullptr)
+      *reinterpret_cast<uint4*>(rowp2 + off) = make_uint4(zp[4 * q], zp[4 * q + 1], zp[4 * q + 2], zp[4 * q + 3]);
+  }
+}
+
+// 32 accumulator columns of one row -> the row's slice of the box (all epilogues but EPI_ACT).  `rowp` = box +
+// row * 128, `r7` = row & 7, `sub` = which 64-byte half of the row (bf16 boxes hold two 32-column halves; fp32
+// boxes one: the whole row).
+template <int EPI>
+__device__ __forceinline__ void box_half(const BiasRegs& br, bool has_aux, uint8_t* rowp, int r7, int sub, float scale,
+                                         const uint32_t (&v)[32]) {
   float a[32];
 #pragma unroll
-  for (int j = 0; j < 32; ++j) a[j] = __uint_as_float(v[j]);
-  if (ep.bias != nullptr && !(epi_base(EPI) == EPI_QKV && c0 >= 3 * ep.D)) {
-#pragma unroll
-    for (int j = 0; j < 32; j += 4) {
-      const float4 b = __ldg(reinterpret_cast<const float4*>(ep.bias + c0 + j));
-      a[j] += b.x; a[j + 1] += b.y; a[j + 2] += b.z; a[j + 3] += b.w;
-    }
+  for (int q = 0; q < 8; ++q) {
+    a[4 * q] = __uint_as_float(v[4 * q]) + br.b[q].x;
+    a[4 * q + 1] = __uint_as_float(v[4 * q + 1]) + br.b[q].y;
+    a[4 * q + 2] = __uint_as_float(v[4 * q + 2]) + br.b[q].z;
+    a[4 * q + 3] = __uint_as_float(v[4 * q + 3]) + br.b[q].w;
   }
   if constexpr (epi_base(EPI) == EPI_F32) {
 #pragma unroll
@@ -251,20 +289,6 @@ __device__ __forceinline__ void box_half(const GemmEpilogue& ep, int c0, bool ha
       float4 o = make_float4(a[4 * q], a[4 * q + 1], a[4 * q + 2], a[4 * q + 3]);
       if (has_aux) { const float4 r = *p; o.x += r.x; o.y += r.y; o.z += r.z; o.w += r.w; }
       *p = o;
-    }
-  } else if constexpr (epi_base(EPI) == EPI_ACT) {
-#pragma unroll
-    for (int q = 0; q < 4; ++q) {
-      const int off = ((sub * 4 + q) ^ r7) << 4;
-      float h[8];
-#pragma unroll
-      for (int t = 0; t < 8; ++t) h[t] = act_fwd<epi_act(EPI)>(a[8 * q + t]);
-      *reinterpret_cast<uint4*>(rowp + off) = make_uint4(pack_bf16(h[0], h[1]), pack_bf16(h[2], h[3]),
-                                                         pack_bf16(h[4], h[5]), pack_bf16(h[6], h[7]));
-      if (rowp2 != nullptr)
-        *reinterpret_cast<uint4*>(rowp2 + off) =
-            make_uint4(pack_bf16(a[8 * q], a[8 * q + 1]), pack_bf16(a[8 * q + 2], a[8 * q + 3]),
-                       pack_bf16(a[8 * q + 4], a[8 * q + 5]), pack_bf16(a[8 * q + 6], a[8 * q + 7]));
     }
   } else {  // EPI_BF16 (+ in-place bf16 residual), EPI_DACT (x act'(z)), EPI_QKV (x scale)
 #pragma unroll
@@ -300,7 +324,7 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1)
 gemm_tn_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_b,
                const __grid_constant__ CUtensorMap tmap_c, const __grid_constant__ CUtensorMap tmap_c2,
                const __grid_constant__ CUtensorMap tmap_aux, int M, int N, int K, GemmEpilogue ep) {
-  using Cfg = TileCfg<BN, CTA2, TS>;
+  using Cfg = TileCfg<BN, CTA2, TS, epi_ring(epi_base(EPI))>;
   constexpr int STAGES = Cfg::STAGES;
   constexpr int TILE_M = CTA2 ? 2 * BM : BM;  // rows of C covered by one (pair of) CTA(s) per tile
   // staged epilogue geometry (see box_half): columns per box, boxes per tile
@@ -317,8 +341,8 @@ gemm_tn_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
   uint64_t* empty_bar = full_bar + STAGES;
   uint64_t* tfull_bar = empty_bar + STAGES;
   uint64_t* tempty_bar = tfull_bar + 2;
-  uint64_t* aux_bar = tempty_bar + 2;  // [2 warpgroups][2 boxes]
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(aux_bar + 4);
+  uint64_t* aux_bar = tempty_bar + 2;  // [2 warpgroups][3 boxes]
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(aux_bar + 6);
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
@@ -351,7 +375,7 @@ gemm_tn_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
       mbar_init(&tfull_bar[s], 1);
       mbar_init(&tempty_bar[s], CTA2 ? 16 : 8);  // one arrive per epilogue warp (of both CTAs)
     }
-    for (int s = 0; s < 4; ++s) mbar_init(&aux_bar[s], 1);
+    for (int s = 0; s < 6; ++s) mbar_init(&aux_bar[s], 1);
     fence_mbar_init();
   }
   if (warp == 2) {
@@ -466,23 +490,25 @@ gemm_tn_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
         tc_fence_before();
         __syncwarp();
         if (lane == 0) {
-          if constexpr (CTA2) mbar_arrive_cluster(&tempty_bar[acc], 0);  // the leader's MMA warp owns the accumulators
+          if constexpr (CTA2) mbar_arrive_cluster_relaxed(&tempty_bar[acc], 0);  // the leader's MMA warp owns the accumulators
           else mbar_arrive(&tempty_bar[acc]);
         }
       }
     } else {
       // Staged epilogue.  Boxes of the CTA's tile sequence are numbered b = it * NBOXES + j; warpgroup wg owns the
-      // boxes with b % 2 == wg and a private ring of two box buffers:
+      // boxes with b % 2 == wg and a private ring of RING box buffers:
       //   [aux TMA load -> box] -> accumulator (+bias) combined in place -> fence -> barrier -> TMA store
-      // The elected thread drains the previous store (other buffer) before the barrier, so right after it the
-      // other buffer is free for the next box's aux load / data.
-      uint8_t* my_boxes = staging + wg * 2 * BOX_BYTES;
-      uint64_t* my_aux = aux_bar + wg * 2;
+      // RING = 3 (aux-capable epilogues): the aux load of box g+2 is issued right after the store of box g, once
+      // the store of box g-1 (same buffer) has drained.  RING = 2: the elected thread drains the previous store
+      // before the barrier, so the other buffer is free for the next box.
+      constexpr int RING = epi_ring(epi_base(EPI));
+      uint8_t* my_boxes = staging + wg * RING * BOX_BYTES;
+      uint64_t* my_aux = aux_bar + wg * 3;
       const int row = quad * 32 + lane, r7 = row & 7;
       const bool elected = (threadIdx.x == 64 + wg * 128);
       const int bar_id = 1 + wg;
       auto first_j = [&](int it_) { return (wg ^ ((it_ * NBOXES) & 1)) & 1; };
-      // cursor over this warpgroup's boxes, one ahead of the consumer (aux prefetch)
+      // cursor over this warpgroup's boxes, ahead of the consumer (aux prefetch)
       int la_it = 0, la_j = first_j(0);
       auto la_seek = [&]() -> bool {
         for (;;) {
@@ -502,8 +528,9 @@ gemm_tn_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
         tma_load_2d(my_boxes + slot * BOX_BYTES, &tmap_aux, &my_aux[slot], c0_, m0_);
         la_j += 2;
       };
-      if (has_aux && elected) la_issue(0);
-      int g = 0;  // boxes processed by this warpgroup
+      if (has_aux && elected) { la_issue(0); la_issue(1); }
+      int slot = 0;            // (boxes processed by this warpgroup) % RING
+      uint32_t aux_phase = 0;  // (boxes processed / RING) & 1
       int it = 0;
       for (int tile = first_tile; tile < num_tiles; tile += tile_step, ++it) {
         const int acc = it & 1;
@@ -517,36 +544,42 @@ gemm_tn_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
         for (int j = first_j(it); j < NBOXES; j += 2) {
           const int c0 = n0 + j * BOXCOLS;
           if (c0 >= N) break;
-          const int slot = kTwo ? 0 : (g & 1);
-          uint8_t* box = my_boxes + slot * BOX_BYTES;
+          uint8_t* box = my_boxes + (kTwo ? 0 : slot) * BOX_BYTES;
           uint8_t* rowp = box + row * 128;
-          uint8_t* rowp2 = (kTwo && ep.out2_bf16 != nullptr) ? rowp + BOX_BYTES : nullptr;
-          float scale = 1.f;
-          if constexpr (kQKV) scale = c0 < ep.D ? 0.125f : 1.f;
-          if (has_aux) mbar_wait(&my_aux[slot], (g >> 1) & 1);
-          if constexpr (kF32) {
-            uint32_t v[32];
-            tmem_ld_32x32(t_row + j * 32, v);
-            tmem_ld_wait();
-            if (!(ep.debug & 4)) box_half<EPI>(ep, c0, has_aux, rowp, nullptr, r7, 0, 1.f, v);
-          } else {
+          if constexpr (kTwo) {
+            uint8_t* rowp2 = ep.out2_bf16 != nullptr ? rowp + BOX_BYTES : nullptr;
 #pragma unroll
             for (int sub = 0; sub < 2; ++sub) {
-              uint32_t v[32];
+              uint32_t v[32], hp[16], zp[16];
+              BiasRegs br;
               tmem_ld_32x32(t_row + j * 64 + sub * 32, v);
+              load_bias<EPI>(ep, c0 + sub * 32, br);
               tmem_ld_wait();
-              if constexpr (kTwo) {
-                if (sub == 0) {  // both buffers are about to be rewritten: the previous h / z stores must have drained
-                  if (elected) tma_store_wait_read<0>();
-                  named_bar_sync(bar_id, 128);
-                }
+              act_half_compute<EPI>(br, v, hp, zp);
+              if (sub == 0) {  // both buffers are about to be rewritten: the previous h / z stores must have drained
+                if (elected) tma_store_wait_read<0>();
+                named_bar_sync(bar_id, 128);
               }
-              if (!(ep.debug & 4)) box_half<EPI>(ep, c0 + sub * 32, has_aux, rowp, rowp2, r7, sub, scale, v);
+              act_half_store(rowp, rowp2, r7, sub, hp, zp);
+            }
+          } else {
+            float scale = 1.f;
+            if constexpr (kQKV) scale = c0 < ep.D ? 0.125f : 1.f;
+#pragma unroll
+            for (int sub = 0; sub < (kF32 ? 1 : 2); ++sub) {
+              uint32_t v[32];
+              BiasRegs br;
+              tmem_ld_32x32(t_row + j * BOXCOLS + sub * 32, v);
+              load_bias<EPI>(ep, c0 + sub * 32, br);
+              if (sub == 0 && has_aux) mbar_wait(&my_aux[slot], aux_phase);
+              tmem_ld_wait();
+              if (!(ep.debug & 4)) box_half<EPI>(br, has_aux, rowp, r7, sub, scale, v);
             }
           }
           fence_proxy_async_smem();
           if constexpr (!kTwo) {
-            if (elected) tma_store_wait_read<0>();  // store of box g-1 (other buffer) drained
+            // the buffer of the NEXT box must be free once the barrier below is passed
+            if (elected) tma_store_wait_read<RING - 2>();
           }
           named_bar_sync(bar_id, 128);
           if (elected) {
@@ -559,17 +592,22 @@ gemm_tn_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
               }
             } else {
               tma_store_2d(&tmap_c, box, c0, m0);
-              if constexpr (kTwo) { if (rowp2 != nullptr) tma_store_2d(&tmap_c2, box + BOX_BYTES, c0, m0); }
+              if constexpr (kTwo) { if (ep.out2_bf16 != nullptr) tma_store_2d(&tmap_c2, box + BOX_BYTES, c0, m0); }
             }
             tma_store_commit();
-            if (has_aux) la_issue((g + 1) & 1);
+            if constexpr (RING == 3) {
+              if (has_aux) {
+                tma_store_wait_read<1>();  // store of box g-1 drained: its buffer takes the aux operand of box g+2
+                la_issue(slot == 0 ? 2 : slot - 1);
+              }
+            }
           }
-          ++g;
+          if (++slot == RING) { slot = 0; aux_phase ^= 1; }
         }
         tc_fence_before();
         __syncwarp();
         if (lane == 0) {
-          if constexpr (CTA2) mbar_arrive_cluster(&tempty_bar[acc], 0);  // the leader's MMA warp owns the accumulators
+          if constexpr (CTA2) mbar_arrive_cluster_relaxed(&tempty_bar[acc], 0);  // the leader's MMA warp owns the accumulators
           else mbar_arrive(&tempty_bar[acc]);
         }
       }
@@ -590,8 +628,8 @@ gemm_tn_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
 template <int BN, int EPI, bool TS, bool CTA2>
 int launch_impl(cudaStream_t stream, const CUtensorMap& ta, const CUtensorMap& tb, const CUtensorMap& tc,
                 const CUtensorMap& tc2, const CUtensorMap& taux, int M, int N, int K, const GemmEpilogue& ep) {
-  using Cfg = TileCfg<BN, CTA2, TS>;
-  static_assert(Cfg::STAGES >= 3, "pipeline too shallow");
+  using Cfg = TileCfg<BN, CTA2, TS, epi_ring(epi_base(EPI))>;
+  static_assert(Cfg::STAGES >= 2, "pipeline too shallow");
   static bool configured[64] = {};  // per instantiation and device (the attribute is per context)
   auto kern = gemm_tn_kernel<BN, EPI, TS, CTA2>;
   int dev = 0;
