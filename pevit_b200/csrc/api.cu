@@ -111,6 +111,7 @@ int check_desc(const pevit_block_desc* d) {
 int attn_fwd_dispatch(cudaStream_t s, const AttnShape& a, int impl, const bf16* q, const bf16* k, const bf16* v,
                       const bf16* T, const float* qmat, const float* bias, bf16* o_tok, float* lse) {
   if (impl == 0 && attn_tc_supported(a)) return attn_fwd_tc(s, a, q, k, v, o_tok, lse);
+  if (impl == 0 && attn_tc_long_supported(a)) return attn_fwd_tc_long(s, a, q, k, v, o_tok, lse);
   return attn_delta_fwd_ref(s, a, q, k, v, T, qmat, bias, o_tok, lse);
 }
 
@@ -118,6 +119,7 @@ int attn_bwd_dispatch(cudaStream_t s, const AttnShape& a, int impl, const bf16* 
                       const bf16* T, const float* qmat, const float* bias, const bf16* o_tok, const bf16* do_tok,
                       const float* lse, bf16* dqkv, int ld, bf16* ddelta) {
   if (impl == 0 && attn_tc_supported(a)) return attn_bwd_tc(s, a, q, k, v, do_tok, lse, dqkv, ld, ddelta);
+  if (impl == 0 && attn_tc_long_supported(a)) return attn_bwd_tc_long(s, a, q, k, v, o_tok, do_tok, lse, dqkv, ld, ddelta);
   return attn_delta_bwd_ref(s, a, q, k, v, T, qmat, bias, o_tok, do_tok, lse, dqkv, ld, ddelta);
 }
 

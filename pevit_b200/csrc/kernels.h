@@ -64,6 +64,14 @@ int attn_fwd_tc(cudaStream_t s, const AttnShape& a, const bf16* q, const bf16* k
 int attn_bwd_tc(cudaStream_t s, const AttnShape& a, const bf16* q, const bf16* k, const bf16* v, const bf16* do_tok,
                 const float* lse, bf16* dqkv, int ld_dqkv, bf16* ddelta);
 
+// attention_tc_long.cu: 128 < L <= 384 (ViT-B/16, ViT-L/14), composed over 128 x 128 (query tile, key block) pairs.
+// The backward needs the forward's o_tok (delta = rowsum(dO o O)).
+bool attn_tc_long_supported(const AttnShape& a);
+int attn_fwd_tc_long(cudaStream_t s, const AttnShape& a, const bf16* q, const bf16* k, const bf16* v, bf16* o_tok,
+                     float* lse);
+int attn_bwd_tc_long(cudaStream_t s, const AttnShape& a, const bf16* q, const bf16* k, const bf16* v, const bf16* o_tok,
+                     const bf16* do_tok, const float* lse, bf16* dqkv, int ld_dqkv, bf16* ddelta);
+
 // ------------------------------------------------------------------ lowrank.cu
 // KAdaptation factor expansion: from u1,u2 (rule*_left [32][32]), v1,v2 (rule*_right),
 // s (q_proj_adapter1_left [32][D/32]), t (q_proj_adapter1_right [32][D/32]) build
