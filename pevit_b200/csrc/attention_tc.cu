@@ -9,6 +9,8 @@
 // 64 < L <= 128).  With PACK = 2 the two heads sit at rows 0.. and 64.. of every operand tile;
 // S = Q K^T is then block-diagonal and each softmax thread only reads its own 64-column block,
 // P's off-diagonal blocks stay zero so O = P V is exact.
+#include <cstdlib>
+
 #include "common.cuh"
 #include "kernels.h"
 
@@ -16,11 +18,13 @@ namespace pevit {
 namespace {
 
 constexpr int TC_STAGES = 3;
+constexpr int ATTN_PREFETCH = 5;  // tiles pulled into L2 beyond the shared-memory ring
 constexpr int TILE_BYTES = 128 * 128;  // 128 rows x 64 bf16
 constexpr int STAGE_BYTES = 3 * TILE_BYTES;
 constexpr int P_BYTES = 2 * TILE_BYTES;  // 128 rows x 128 keys
-constexpr int FWD_SMEM = TC_STAGES * STAGE_BYTES + 2 * P_BYTES + 256 + 1024;
-constexpr int FWD_THREADS = 320;  // 8 softmax warps, 1 TMA warp, 1 MMA warp
+constexpr int FWD_STATS_BYTES = 4 * 128 * 8;  // (row max, row sum) of the last four tiles
+constexpr int FWD_SMEM = TC_STAGES * STAGE_BYTES + 2 * P_BYTES + FWD_STATS_BYTES + 256 + 1024;
+constexpr int FWD_THREADS = 320;  // softmax warpgroup, epilogue warpgroup, TMA warp, MMA warp
 constexpr float LOG2E = 1.4426950408889634f;
 
 __device__ __forceinline__ float fast_exp2(float x) {
@@ -31,24 +35,33 @@ __device__ __forceinline__ float fast_exp2(float x) {
 
 struct FwdParams {
   int L, NB, H, D, heads_total, num_tiles;
+  int debug;  // diagnostics (PEVIT_ATTN_DEBUG): 1 = no operand loads, 2 = no softmax math, 4 = no O staging / store
   bf16* o_tok;
   float* lse;
 };
 
+// Roles: warps 0-3 softmax (every tile: S_b -> P_b + row statistics), warps 4-7 epilogue (every tile: O_b ->
+// normalise -> global), warp 8 TMA, warp 9 MMA.  The two warpgroups are pipeline STAGES, not alternating owners of
+// whole tiles: the softmax of tile i+1 never waits for the P V product of tile i, so the per-tile latency chain
+// (TMA -> S -> softmax -> P V -> store) is overlapped three deep and the kernel runs at the rate of its slowest
+// stage instead of the sum of all of them.
 template <int PACK>
 __global__ void __launch_bounds__(FWD_THREADS, 1)
 attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant__ CUtensorMap tm_k,
-                   const __grid_constant__ CUtensorMap tm_v, FwdParams p) {
+                   const __grid_constant__ CUtensorMap tm_v, const __grid_constant__ CUtensorMap tm_o, FwdParams p) {
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   uint8_t* sP = smem + TC_STAGES * STAGE_BYTES;
-  uint64_t* bars = reinterpret_cast<uint64_t*>(sP + 2 * P_BYTES);
+  float2* stats = reinterpret_cast<float2*>(sP + 2 * P_BYTES);  // [tile & 3][row] = (max, sum)
+  uint64_t* bars = reinterpret_cast<uint64_t*>(reinterpret_cast<uint8_t*>(stats) + FWD_STATS_BYTES);
   uint64_t* full = bars;                   // [TC_STAGES]
   uint64_t* empty = full + TC_STAGES;      // [TC_STAGES]
   uint64_t* s_full = empty + TC_STAGES;    // [2]
-  uint64_t* p_full = s_full + 2;           // [2]
+  uint64_t* p_full = s_full + 2;           // [2]  128 arrivals
   uint64_t* o_full = p_full + 2;           // [2]
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(o_full + 2);
+  uint64_t* o_empty = o_full + 2;          // [2]  4 warp arrivals
+  uint64_t* p_free = o_empty + 2;          // [2]  the O tile staged in P_b has left through TMA
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(p_free + 2);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int L = p.L;
@@ -63,9 +76,12 @@ attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_consta
     for (int i = threadIdx.x; i < n16; i += FWD_THREADS) z[i] = make_uint4(0, 0, 0, 0);
   }
   if (warp == 8 && lane == 0) {
-    tma_prefetch_desc(&tm_q); tma_prefetch_desc(&tm_k); tma_prefetch_desc(&tm_v);
+    tma_prefetch_desc(&tm_q); tma_prefetch_desc(&tm_k); tma_prefetch_desc(&tm_v); tma_prefetch_desc(&tm_o);
     for (int s = 0; s < TC_STAGES; ++s) { mbar_init(&full[s], 1); mbar_init(&empty[s], 1); }
-    for (int b = 0; b < 2; ++b) { mbar_init(&s_full[b], 1); mbar_init(&p_full[b], 128); mbar_init(&o_full[b], 1); }
+    for (int b = 0; b < 2; ++b) {
+      mbar_init(&s_full[b], 1); mbar_init(&p_full[b], 128); mbar_init(&o_full[b], 1); mbar_init(&o_empty[b], 4);
+      mbar_init(&p_free[b], 1);
+    }
     fence_mbar_init();
   }
   if (warp == 9) {
@@ -84,14 +100,28 @@ attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_consta
   if (warp == 8) {
     // ------------------------------------------------------------ TMA producer
     if (lane == 0) {
+      // The ring holds three tiles, but a tile's HBM latency is several tile-times: pull the operands of the tiles
+      // further ahead into L2 now, so that the ring's own loads are L2 hits.
+      auto prefetch_tile = [&](int it_) {
+        if (it_ >= n_local) return;
+        const int g0_ = (blockIdx.x + it_ * gridDim.x) * PACK;
+        for (int j = 0; j < PACK && g0_ + j < p.heads_total; ++j) {
+          tma_prefetch_l2_2d(&tm_q, 0, (g0_ + j) * L);
+          tma_prefetch_l2_2d(&tm_k, 0, (g0_ + j) * L);
+          tma_prefetch_l2_2d(&tm_v, 0, (g0_ + j) * L);
+        }
+      };
+      for (int it_ = TC_STAGES; it_ < TC_STAGES + ATTN_PREFETCH; ++it_) prefetch_tile(it_);
       for (int it = 0; it < n_local; ++it) {
         const int tile = blockIdx.x + it * gridDim.x;
         const int s = it % TC_STAGES;
         const uint32_t ph = (it / TC_STAGES) & 1;
+        prefetch_tile(it + TC_STAGES + ATTN_PREFETCH);
         mbar_wait(&empty[s], ph ^ 1);
         const int g0 = tile * PACK;
         const int nheads = min(PACK, p.heads_total - g0);
         uint8_t* st = smem + s * STAGE_BYTES;
+        if (p.debug & 1) { mbar_arrive(&full[s]); continue; }
         mbar_expect_tx(&full[s], static_cast<uint32_t>(nheads) * 3u * static_cast<uint32_t>(L) * 128u);
         for (int j = 0; j < nheads; ++j) {
           const int row = (g0 + j) * L;
@@ -121,7 +151,9 @@ attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_consta
     };
     auto issue_pv = [&](int it) {
       const int s = it % TC_STAGES, b = it & 1;
-      mbar_wait(&p_full[b], (it >> 1) & 1);
+      const uint32_t ph = (it >> 1) & 1;
+      mbar_wait(&p_full[b], ph);
+      mbar_wait(&o_empty[b], ph ^ 1);  // the epilogue warpgroup has read O_b of tile it-2
       tc_fence_after();
       if (lane == 0) {
         const uint32_t sp = smem_u32(sP + b * P_BYTES);
@@ -145,80 +177,120 @@ attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_consta
       issue_pv(it);
     }
   } else {
-    // ------------------------------------------------------------ softmax / epilogue warpgroups
-    const int grp = warp >> 2;              // 0 or 1: handles local items it = grp, grp+2, ...
+    const int wgrole = warp >> 2;           // 0: softmax, 1: epilogue
     const int quad = warp & 3;
     const int row = quad * 32 + lane;       // accumulator row == TMEM lane
     const int slot = PACK == 2 ? (row >> 6) : 0;   // which head of the pack this row belongs to
     const int l = PACK == 2 ? (row & 63) : row;    // token index within the head
     const int col0 = PACK == 2 ? slot * 64 : 0;    // first key column of this row's block
     constexpr int NCOL = PACK == 2 ? 64 : 128;
-    uint8_t* myP = sP + grp * P_BYTES;
     const uint32_t t_lane = tmem_base + (static_cast<uint32_t>(quad * 32) << 16);
-    for (int it = grp; it < n_local; it += 2) {
-      const int tile = blockIdx.x + it * gridDim.x;
-      const uint32_t ph = (it >> 1) & 1;
-      mbar_wait(&s_full[grp], ph);
-      tc_fence_after();
-      // ---- scores of this row: NCOL fp32 values
-      float sc[NCOL];
+    if (wgrole == 0) {
+      // ---------------------------------------------------------- softmax warpgroup
+      for (int it = 0; it < n_local; ++it) {
+        const int b = it & 1;
+        uint8_t* myP = sP + b * P_BYTES;
+        mbar_wait(&s_full[b], (it >> 1) & 1);
+        tc_fence_after();
+        // ---- scores of this row: NCOL fp32 values
+        // One warp per scheduler runs this code, so instruction-level parallelism is all the latency hiding there
+        // is: both TMEM loads are in flight before the wait, and the row max / row sum run as four independent
+        // chains instead of one NCOL-long dependent one.
+        float sc[NCOL];
+        {
+          uint32_t v[NCOL];
 #pragma unroll
-      for (int c = 0; c < NCOL; c += 32) {
-        uint32_t v[32];
-        tmem_ld_32x32(t_lane + grp * 128 + col0 + c, v);
+          for (int c = 0; c < NCOL; c += 32) tmem_ld_32x32(t_lane + b * 128 + col0 + c, *reinterpret_cast<uint32_t(*)[32]>(&v[c]));
+          tmem_ld_wait();
+#pragma unroll
+          for (int j = 0; j < NCOL; ++j) sc[j] = __uint_as_float(v[j]);
+        }
+        float m4[4] = {-INFINITY, -INFINITY, -INFINITY, -INFINITY};
+#pragma unroll
+        for (int j = 0; j < NCOL; ++j) if (j < L) m4[j & 3] = fmaxf(m4[j & 3], sc[j]);
+        const float mx = fmaxf(fmaxf(m4[0], m4[1]), fmaxf(m4[2], m4[3]));
+        float s4[4] = {0.f, 0.f, 0.f, 0.f};
+        const float mxs = mx * LOG2E;
+#pragma unroll
+        for (int j = 0; j < NCOL; ++j) {
+          const float e = (j < L) ? fast_exp2(fmaf(sc[j], LOG2E, -mxs)) : 0.f;
+          sc[j] = e;
+          s4[j & 3] += e;
+        }
+        const float sum = (s4[0] + s4[1]) + (s4[2] + s4[3]);
+        // ---- P (unnormalised, bf16) -> smem as the K-major A operand of O = P V
+        mbar_wait(&p_free[b], ((it >> 1) & 1) ^ 1);  // the O tile of tile it-2, staged in this buffer, has left
+#pragma unroll
+        for (int c = 0; c < NCOL / 8; ++c) {
+          const uint4 pk = make_uint4(pack_bf16(sc[8 * c], sc[8 * c + 1]), pack_bf16(sc[8 * c + 2], sc[8 * c + 3]),
+                                      pack_bf16(sc[8 * c + 4], sc[8 * c + 5]), pack_bf16(sc[8 * c + 6], sc[8 * c + 7]));
+          const int kc = (col0 >> 3) + c;            // 16-byte chunk index along the 128 keys
+          const int half = kc >> 3, ch = kc & 7;     // which [128][64] half-tile, chunk within its 128-B row
+          *reinterpret_cast<uint4*>(myP + half * TILE_BYTES + row * 128 + ((ch ^ (row & 7)) << 4)) = pk;
+        }
+        stats[(it & 3) * 128 + row] = make_float2(mx, sum);  // read by the epilogue warpgroup after o_full
+        fence_proxy_async_smem();
+        tc_fence_before();
+        mbar_arrive(&p_full[b]);
+      }
+    } else {
+      // ---------------------------------------------------------- epilogue warpgroup
+      // The normalised O rows are staged in the part of P_b this row's softmax thread rewrites every tile anyway
+      // (P_b is dead once O_b is complete) and leave as one TMA store per head: [L tokens][64] -> o_tok rows
+      // (l * NB + n), columns h * 64.., coalesced instead of 128 scattered 16-byte stores per warp.
+      const bool elected = (threadIdx.x == 128);
+      for (int it = 0; it < n_local; ++it) {
+        const int tile = blockIdx.x + it * gridDim.x;
+        const int b = it & 1;
+        if (elected && it > 0) {  // previous tile's store has read its staging buffer: hand P_(b^1) back to the softmax
+          tma_store_wait_read<0>();
+          mbar_arrive(&p_free[b ^ 1]);
+        }
+        mbar_wait(&o_full[b], (it >> 1) & 1);
+        tc_fence_after();
+        uint32_t v0[32], v1[32];
+        tmem_ld_32x32(t_lane + 256 + b * 64, v0);
+        tmem_ld_32x32(t_lane + 256 + b * 64 + 32, v1);
         tmem_ld_wait();
-#pragma unroll
-        for (int j = 0; j < 32; ++j) sc[c + j] = __uint_as_float(v[j]);
-      }
-      float mx = -INFINITY;
-#pragma unroll
-      for (int j = 0; j < NCOL; ++j) if (j < L) mx = fmaxf(mx, sc[j]);
-      float sum = 0.f;
-      const float mxs = mx * LOG2E;
-#pragma unroll
-      for (int j = 0; j < NCOL; ++j) {
-        const float e = (j < L) ? fast_exp2(fmaf(sc[j], LOG2E, -mxs)) : 0.f;
-        sc[j] = e;
-        sum += e;
-      }
-      // ---- P (unnormalised, bf16) -> smem as the K-major A operand of O = P V
-#pragma unroll
-      for (int c = 0; c < NCOL / 8; ++c) {
-        const uint4 pk = make_uint4(pack_bf16(sc[8 * c], sc[8 * c + 1]), pack_bf16(sc[8 * c + 2], sc[8 * c + 3]),
-                                    pack_bf16(sc[8 * c + 4], sc[8 * c + 5]), pack_bf16(sc[8 * c + 6], sc[8 * c + 7]));
-        const int kc = (col0 >> 3) + c;            // 16-byte chunk index along the 128 keys
-        const int half = kc >> 3, ch = kc & 7;     // which [128][64] half-tile, chunk within its 128-B row
-        *reinterpret_cast<uint4*>(myP + half * TILE_BYTES + row * 128 + ((ch ^ (row & 7)) << 4)) = pk;
-      }
-      fence_proxy_async_smem();
-      tc_fence_before();
-      mbar_arrive(&p_full[grp]);
-      // ---- O = P V, normalise, merge heads: bf16 rows of o_tok[(l*NB + n)][h*64 ..]
-      mbar_wait(&o_full[grp], ph);
-      tc_fence_after();
-      const int g = tile * PACK + slot;
-      const bool valid = (l < L) && (g < p.heads_total);
-      const float inv = 1.f / sum;
-      const int n = g / p.H, h = g - n * p.H;
-      bf16* orow = p.o_tok + (static_cast<size_t>(l) * p.NB + n) * p.D + h * 64;
-#pragma unroll
-      for (int c = 0; c < 64; c += 32) {
-        uint32_t v[32];
-        tmem_ld_32x32(t_lane + 256 + grp * 64 + c, v);
-        tmem_ld_wait();
-        if (valid) {
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&o_empty[b]);  // O_b is in registers: the P V product of tile it+2 may overwrite it
+        const float2 ms = stats[(it & 3) * 128 + row];
+        const int g = tile * PACK + slot;
+        const bool valid = (l < L) && (g < p.heads_total);
+        uint8_t* stg = sP + b * P_BYTES + (PACK == 2 ? slot * TILE_BYTES : 0) + row * 128;
+        if (valid && !(p.debug & 4)) {
+          const float inv = 1.f / ms.y;
 #pragma unroll
           for (int j = 0; j < 32; j += 8) {
-            float f[8];
-#pragma unroll
-            for (int t = 0; t < 8; ++t) f[t] = __uint_as_float(v[j + t]) * inv;
-            *reinterpret_cast<uint4*>(orow + c + j) = make_uint4(pack_bf16(f[0], f[1]), pack_bf16(f[2], f[3]),
-                                                                  pack_bf16(f[4], f[5]), pack_bf16(f[6], f[7]));
+            *reinterpret_cast<uint4*>(stg + (((j >> 3) ^ (row & 7)) << 4)) =
+                make_uint4(pack_bf16(__uint_as_float(v0[j]) * inv, __uint_as_float(v0[j + 1]) * inv),
+                           pack_bf16(__uint_as_float(v0[j + 2]) * inv, __uint_as_float(v0[j + 3]) * inv),
+                           pack_bf16(__uint_as_float(v0[j + 4]) * inv, __uint_as_float(v0[j + 5]) * inv),
+                           pack_bf16(__uint_as_float(v0[j + 6]) * inv, __uint_as_float(v0[j + 7]) * inv));
+            *reinterpret_cast<uint4*>(stg + ((((j >> 3) + 4) ^ (row & 7)) << 4)) =
+                make_uint4(pack_bf16(__uint_as_float(v1[j]) * inv, __uint_as_float(v1[j + 1]) * inv),
+                           pack_bf16(__uint_as_float(v1[j + 2]) * inv, __uint_as_float(v1[j + 3]) * inv),
+                           pack_bf16(__uint_as_float(v1[j + 4]) * inv, __uint_as_float(v1[j + 5]) * inv),
+                           pack_bf16(__uint_as_float(v1[j + 6]) * inv, __uint_as_float(v1[j + 7]) * inv));
           }
+          p.lse[static_cast<size_t>(g) * L + l] = ms.x + __logf(ms.y);
+        }
+        fence_proxy_async_smem();
+        named_bar_sync(1, 128);
+        if (elected && !(p.debug & 4)) {
+#pragma unroll
+          for (int j = 0; j < PACK; ++j) {
+            const int gj = tile * PACK + j;
+            if (gj < p.heads_total) {
+              const int n = gj / p.H, h = gj - n * p.H;
+              tma_store_4d(&tm_o, sP + b * P_BYTES + (PACK == 2 ? j * (TILE_BYTES + 8192) : 0), 0, h, n, 0);
+            }
+          }
+          tma_store_commit();
         }
       }
-      if (valid) p.lse[static_cast<size_t>(g) * L + l] = mx + __logf(sum);
-      tc_fence_before();
+      if (elected) tma_store_wait_all<0>();
     }
   }
 
@@ -298,9 +370,22 @@ attn_bwd_tc_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_consta
   if (warp == 8) {
     // ------------------------------------------------------------ TMA producer
     if (lane == 0) {
+      auto prefetch_tile = [&](int it_) {  // see the forward kernel: L2 prefetch beyond the two-stage ring
+        if (it_ >= n_local) return;
+        const int g0_ = (blockIdx.x + it_ * gridDim.x) * PACK;
+        for (int j = 0; j < PACK && g0_ + j < p.heads_total; ++j) {
+          const int g_ = g0_ + j, n_ = g_ / p.H, h_ = g_ - n_ * p.H;
+          tma_prefetch_l2_2d(&tm_q, 0, g_ * L);
+          tma_prefetch_l2_2d(&tm_k, 0, g_ * L);
+          tma_prefetch_l2_2d(&tm_v, 0, g_ * L);
+          tma_prefetch_l2_4d(&tm_do, 0, h_, n_, 0);
+        }
+      };
+      for (int it_ = BWD_STAGES; it_ < BWD_STAGES + ATTN_PREFETCH; ++it_) prefetch_tile(it_);
       for (int it = 0; it < n_local; ++it) {
         const int tile = blockIdx.x + it * gridDim.x;
         const int s = it % BWD_STAGES;
+        prefetch_tile(it + BWD_STAGES + ATTN_PREFETCH);
         mbar_wait(&empty[s], ((it / BWD_STAGES) & 1) ^ 1);
         const int g0 = tile * PACK;
         const int nheads = min(PACK, p.heads_total - g0);
@@ -377,53 +462,97 @@ attn_bwd_tc_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_consta
     const uint32_t t_lane = tmem_base + (static_cast<uint32_t>(quad * 32) << 16);
     if (wg == 0) {
       // ---------------------------------------------------------- WG0: P, delta, dS
+      auto load_lse = [&](int it_) -> float {
+        const int g_ = (blockIdx.x + it_ * gridDim.x) * PACK + slot;
+        return (it_ < n_local && l < L && g_ < p.heads_total) ? p.lse[static_cast<size_t>(g_) * L + l] : 0.f;
+      };
+      float lse_next = load_lse(0);  // fetched one tile ahead: its latency hides behind the previous tile's work
       for (int it = 0; it < n_local; ++it) {
         const int tile = blockIdx.x + it * gridDim.x;
         const int g = tile * PACK + slot;
         const bool valid = (l < L) && (g < p.heads_total);
-        const float lse_s = valid ? p.lse[static_cast<size_t>(g) * L + l] * LOG2E : 0.f;
+        const float lse_s = lse_next * LOG2E;
+        lse_next = load_lse(it + 1);
         mbar_wait(s_full, it & 1);
         tc_fence_after();
-        float delta = 0.f;
-#pragma unroll 1
-        for (int c = 0; c < NCOL; c += 32) {
-          uint32_t sv[32], dv[32];
-          tmem_ld_32x32(t_lane + col0 + c, sv);
-          tmem_ld_32x32(t_lane + 128 + col0 + c, dv);
-          tmem_ld_wait();
+        if constexpr (PACK == 2) {
+          // one pass: the row's 64 scores and 64 dP values stay in registers between delta and dS
+          float pr[64], dp[64];
+          {
+            uint32_t sv[64], dv[64];
 #pragma unroll
-          for (int j = 0; j < 32; ++j) {
-            const float pj = (valid && c + j < L) ? fast_exp2(fmaf(__uint_as_float(sv[j]), LOG2E, -lse_s)) : 0.f;
-            delta = fmaf(pj, __uint_as_float(dv[j]), delta);
+            for (int c = 0; c < 64; c += 32) {
+              tmem_ld_32x32(t_lane + col0 + c, *reinterpret_cast<uint32_t(*)[32]>(&sv[c]));
+              tmem_ld_32x32(t_lane + 128 + col0 + c, *reinterpret_cast<uint32_t(*)[32]>(&dv[c]));
+            }
+            tmem_ld_wait();
+#pragma unroll
+            for (int j = 0; j < 64; ++j) {
+              pr[j] = (valid && j < L) ? fast_exp2(fmaf(__uint_as_float(sv[j]), LOG2E, -lse_s)) : 0.f;
+              dp[j] = __uint_as_float(dv[j]);
+            }
           }
-        }
-        if (it > 0) {  // MMA2 of the previous tile must be done reading the P / dS tiles
-          mbar_wait(o2_full, (it - 1) & 1);
-        }
-#pragma unroll 1
-        for (int c = 0; c < NCOL; c += 32) {
-          uint32_t sv[32], dv[32];
-          tmem_ld_32x32(t_lane + col0 + c, sv);
-          tmem_ld_32x32(t_lane + 128 + col0 + c, dv);
-          tmem_ld_wait();
-          float pj[32], ds[32];
+          float d4[4] = {0.f, 0.f, 0.f, 0.f};  // four independent chains (see the forward softmax)
 #pragma unroll
-          for (int j = 0; j < 32; ++j) {
-            const float e = (valid && c + j < L) ? fast_exp2(fmaf(__uint_as_float(sv[j]), LOG2E, -lse_s)) : 0.f;
-            pj[j] = e;
-            ds[j] = e * (__uint_as_float(dv[j]) - delta);
-          }
+          for (int j = 0; j < 64; ++j) d4[j & 3] = fmaf(pr[j], dp[j], d4[j & 3]);
+          const float delta = (d4[0] + d4[1]) + (d4[2] + d4[3]);
+          if (it > 0) mbar_wait(o2_full, (it - 1) & 1);  // MMA2 of the previous tile is done reading P / dS
 #pragma unroll
-          for (int q = 0; q < 4; ++q) {
-            const int kc = ((col0 + c) >> 3) + q;
+          for (int q = 0; q < 8; ++q) {
+            const int kc = (col0 >> 3) + q;
             const int half = kc >> 3, ch = kc & 7;
             const int off = half * TILE_BYTES + row * 128 + ((ch ^ (row & 7)) << 4);
+            float ds[8];
+#pragma unroll
+            for (int t = 0; t < 8; ++t) ds[t] = pr[8 * q + t] * (dp[8 * q + t] - delta);
             *reinterpret_cast<uint4*>(sP + off) =
-                make_uint4(pack_bf16(pj[8 * q], pj[8 * q + 1]), pack_bf16(pj[8 * q + 2], pj[8 * q + 3]),
-                           pack_bf16(pj[8 * q + 4], pj[8 * q + 5]), pack_bf16(pj[8 * q + 6], pj[8 * q + 7]));
-            *reinterpret_cast<uint4*>(sdS + off) =
-                make_uint4(pack_bf16(ds[8 * q], ds[8 * q + 1]), pack_bf16(ds[8 * q + 2], ds[8 * q + 3]),
-                           pack_bf16(ds[8 * q + 4], ds[8 * q + 5]), pack_bf16(ds[8 * q + 6], ds[8 * q + 7]));
+                make_uint4(pack_bf16(pr[8 * q], pr[8 * q + 1]), pack_bf16(pr[8 * q + 2], pr[8 * q + 3]),
+                           pack_bf16(pr[8 * q + 4], pr[8 * q + 5]), pack_bf16(pr[8 * q + 6], pr[8 * q + 7]));
+            *reinterpret_cast<uint4*>(sdS + off) = make_uint4(pack_bf16(ds[0], ds[1]), pack_bf16(ds[2], ds[3]),
+                                                              pack_bf16(ds[4], ds[5]), pack_bf16(ds[6], ds[7]));
+          }
+        } else {
+          float delta = 0.f;
+#pragma unroll 1
+          for (int c = 0; c < NCOL; c += 32) {
+            uint32_t sv[32], dv[32];
+            tmem_ld_32x32(t_lane + col0 + c, sv);
+            tmem_ld_32x32(t_lane + 128 + col0 + c, dv);
+            tmem_ld_wait();
+#pragma unroll
+            for (int j = 0; j < 32; ++j) {
+              const float pj = (valid && c + j < L) ? fast_exp2(fmaf(__uint_as_float(sv[j]), LOG2E, -lse_s)) : 0.f;
+              delta = fmaf(pj, __uint_as_float(dv[j]), delta);
+            }
+          }
+          if (it > 0) {  // MMA2 of the previous tile must be done reading the P / dS tiles
+            mbar_wait(o2_full, (it - 1) & 1);
+          }
+#pragma unroll 1
+          for (int c = 0; c < NCOL; c += 32) {
+            uint32_t sv[32], dv[32];
+            tmem_ld_32x32(t_lane + col0 + c, sv);
+            tmem_ld_32x32(t_lane + 128 + col0 + c, dv);
+            tmem_ld_wait();
+            float pj[32], ds[32];
+#pragma unroll
+            for (int j = 0; j < 32; ++j) {
+              const float e = (valid && c + j < L) ? fast_exp2(fmaf(__uint_as_float(sv[j]), LOG2E, -lse_s)) : 0.f;
+              pj[j] = e;
+              ds[j] = e * (__uint_as_float(dv[j]) - delta);
+            }
+#pragma unroll
+            for (int q = 0; q < 4; ++q) {
+              const int kc = ((col0 + c) >> 3) + q;
+              const int half = kc >> 3, ch = kc & 7;
+              const int off = half * TILE_BYTES + row * 128 + ((ch ^ (row & 7)) << 4);
+              *reinterpret_cast<uint4*>(sP + off) =
+                  make_uint4(pack_bf16(pj[8 * q], pj[8 * q + 1]), pack_bf16(pj[8 * q + 2], pj[8 * q + 3]),
+                             pack_bf16(pj[8 * q + 4], pj[8 * q + 5]), pack_bf16(pj[8 * q + 6], pj[8 * q + 7]));
+              *reinterpret_cast<uint4*>(sdS + off) =
+                  make_uint4(pack_bf16(ds[8 * q], ds[8 * q + 1]), pack_bf16(ds[8 * q + 2], ds[8 * q + 3]),
+                             pack_bf16(ds[8 * q + 4], ds[8 * q + 5]), pack_bf16(ds[8 * q + 6], ds[8 * q + 7]));
+            }
           }
         }
         fence_proxy_async_smem();
@@ -497,15 +626,18 @@ int attn_fwd_tc(cudaStream_t s, const AttnShape& a, const bf16* q, const bf16* k
   if (make_tmap_bf16_2d(&tq, q, rows, 64, 64, a.L, 64) != 0) return -1;
   if (make_tmap_bf16_2d(&tk, k, rows, 64, 64, a.L, 64) != 0) return -1;
   if (make_tmap_bf16_2d(&tv, v, rows, 64, 64, a.L, 64) != 0) return -1;
-  FwdParams p{a.L, a.NB, a.H, a.D, heads, tiles, o_tok, lse};
+  CUtensorMap to;
+  if (make_tmap_bf16_tok_heads(&to, o_tok, a.L, a.NB, a.H, a.D, a.L) != 0) return -1;
+  static const int dbg = getenv("PEVIT_ATTN_DEBUG") ? atoi(getenv("PEVIT_ATTN_DEBUG")) : 0;
+  FwdParams p{a.L, a.NB, a.H, a.D, heads, tiles, dbg, o_tok, lse};
   const int grid = tiles < sm_count() ? tiles : sm_count();
   ProfScope prof(s, PC_ATTN_FWD);
   if (pack == 2) {
     PEVIT_CHECK_CUDA(cudaFuncSetAttribute(attn_fwd_tc_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, FWD_SMEM));
-    PEVIT_CHECK_CUDA(launch_kernel(attn_fwd_tc_kernel<2>, dim3(grid), dim3(FWD_THREADS), FWD_SMEM, s, 1, tq, tk, tv, p));
+    PEVIT_CHECK_CUDA(launch_kernel(attn_fwd_tc_kernel<2>, dim3(grid), dim3(FWD_THREADS), FWD_SMEM, s, 1, tq, tk, tv, to, p));
   } else {
     PEVIT_CHECK_CUDA(cudaFuncSetAttribute(attn_fwd_tc_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, FWD_SMEM));
-    PEVIT_CHECK_CUDA(launch_kernel(attn_fwd_tc_kernel<1>, dim3(grid), dim3(FWD_THREADS), FWD_SMEM, s, 1, tq, tk, tv, p));
+    PEVIT_CHECK_CUDA(launch_kernel(attn_fwd_tc_kernel<1>, dim3(grid), dim3(FWD_THREADS), FWD_SMEM, s, 1, tq, tk, tv, to, p));
   }
   PEVIT_CHECK_LAUNCH();
   return 0;

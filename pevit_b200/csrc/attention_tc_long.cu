@@ -164,25 +164,28 @@ attn_fwd_long_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_cons
         mbar_wait(&s_full[grp], cnt & 1);
         tc_fence_after();
         float sc[128];
+        {
+          uint32_t v[128];
 #pragma unroll
-        for (int c = 0; c < 128; c += 32) {
-          uint32_t v[32];
-          tmem_ld_32x32(t_lane + grp * 128 + c, v);
+          for (int c = 0; c < 128; c += 32) tmem_ld_32x32(t_lane + grp * 128 + c, *reinterpret_cast<uint32_t(*)[32]>(&v[c]));
           tmem_ld_wait();
 #pragma unroll
-          for (int jj = 0; jj < 32; ++jj) sc[c + jj] = __uint_as_float(v[jj]);
+          for (int jj = 0; jj < 128; ++jj) sc[jj] = __uint_as_float(v[jj]);
         }
-        float mx = -INFINITY;
+        // four independent max / sum chains: with few warps per scheduler, ILP is the latency hiding
+        float m4[4] = {-INFINITY, -INFINITY, -INFINITY, -INFINITY};
 #pragma unroll
-        for (int jj = 0; jj < 128; ++jj) if (jj < nvalid) mx = fmaxf(mx, sc[jj]);
-        float sum = 0.f;
+        for (int jj = 0; jj < 128; ++jj) if (jj < nvalid) m4[jj & 3] = fmaxf(m4[jj & 3], sc[jj]);
+        const float mx = fmaxf(fmaxf(m4[0], m4[1]), fmaxf(m4[2], m4[3]));
+        float s4[4] = {0.f, 0.f, 0.f, 0.f};
         const float mxs = mx * LOG2E;
 #pragma unroll
         for (int jj = 0; jj < 128; ++jj) {
           const float e = (jj < nvalid) ? fast_exp2(fmaf(sc[jj], LOG2E, -mxs)) : 0.f;
           sc[jj] = e;
-          sum += e;
+          s4[jj & 3] += e;
         }
+        const float sum = (s4[0] + s4[1]) + (s4[2] + s4[3]);
 #pragma unroll
         for (int c = 0; c < 16; ++c) {
           const uint4 pk = make_uint4(pack_bf16(sc[8 * c], sc[8 * c + 1]), pack_bf16(sc[8 * c + 2], sc[8 * c + 3]),
