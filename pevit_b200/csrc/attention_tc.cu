@@ -303,17 +303,21 @@ attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_consta
 }
 
 // =====================================================================================================
-// Backward.  Per 128-row tile (PACK heads):
-//   MMA1:  S = Q' K^T,  dP = dO V'^T                                  (TMEM cols [0,128) and [128,256))
+// Backward.  Per 128-row tile (PACK heads), TMEM column set b = tile & 1 (256 columns each):
+//   MMA1:  S = Q' K^T  -> set+[0,128),  dP = dO V'^T -> set+[128,256)
 //   WG0 :  P = exp(S - lse), delta = sum_j P dP, dS = P (dP - delta)  -> bf16 P, dS tiles in smem
-//   MMA2:  dV' = P^T dO, dK = dS^T Q', dQ' = dS K                     (TMEM cols [256,320) [320,384) [384,448))
-//   WG1 :  dQ'/8, dK, dV' -> token-major dqkv rows; dQ', dV' -> head-major d(delta) (F4: same memory)
+//   MMA2:  dV' = P^T dO -> set+[0,64), dK = dS^T Q' -> set+[64,128), dQ' = dS K -> set+[128,192)
+//          (the gradients overwrite the S / dP columns WG0 has just consumed, which is what lets the two sets
+//          double-buffer inside the 512 TMEM columns: MMA1 of tile i+1 runs while tile i is still in flight)
+//   WG1 :  dQ'/8, dK, dV' -> token-major dqkv rows, staged in smem and TMA-stored per head (coalesced);
+//          dQ', dV' -> head-major d(delta) (F4: same memory), contiguous per head so stored directly
 // P^T and dS^T are not materialised: the [row][key] tiles are read as MN-major A operands, and dO, Q', K
 // (64 contiguous d per row) as MN-major B operands.  delta uses the same P and dP that build dS, so the
 // bf16 rounding of O never enters (and O is not read at all).
 constexpr int BWD_STAGES = 2;
 constexpr int BWD_STAGE_BYTES = 4 * TILE_BYTES;  // Q', K, V', dO
-constexpr int BWD_SMEM = BWD_STAGES * BWD_STAGE_BYTES + 2 * P_BYTES + 256 + 1024;
+constexpr int BWD_STAGING_BYTES = 2 * TILE_BYTES;  // two [128 rows][64] bf16 boxes for the token-major gradient stores
+constexpr int BWD_SMEM = BWD_STAGES * BWD_STAGE_BYTES + 2 * P_BYTES + BWD_STAGING_BYTES + 256 + 1024;
 constexpr int BWD_THREADS = 320;  // WG0 (4 warps) + WG1 (4 warps) + TMA warp + MMA warp
 
 struct BwdParams {
@@ -326,19 +330,21 @@ struct BwdParams {
 template <int PACK>
 __global__ void __launch_bounds__(BWD_THREADS, 1)
 attn_bwd_tc_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant__ CUtensorMap tm_k,
-                   const __grid_constant__ CUtensorMap tm_v, const __grid_constant__ CUtensorMap tm_do, BwdParams p) {
+                   const __grid_constant__ CUtensorMap tm_v, const __grid_constant__ CUtensorMap tm_do,
+                   const __grid_constant__ CUtensorMap tm_dqkv, BwdParams p) {
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   uint8_t* sP = smem + BWD_STAGES * BWD_STAGE_BYTES;
   uint8_t* sdS = sP + P_BYTES;
-  uint64_t* bars = reinterpret_cast<uint64_t*>(sdS + P_BYTES);
-  uint64_t* full = bars;                 // [BWD_STAGES]
-  uint64_t* empty = full + BWD_STAGES;   // [BWD_STAGES]
-  uint64_t* s_full = empty + BWD_STAGES; // MMA1 done
-  uint64_t* pds_full = s_full + 1;       // WG0 wrote P, dS
-  uint64_t* o2_full = pds_full + 1;      // MMA2 done
-  uint64_t* o2_empty = o2_full + 1;      // WG1 drained dQ/dK/dV
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(o2_empty + 1);
+  uint8_t* stg = sdS + P_BYTES;
+  uint64_t* bars = reinterpret_cast<uint64_t*>(stg + BWD_STAGING_BYTES);
+  uint64_t* full = bars;                  // [BWD_STAGES]
+  uint64_t* empty = full + BWD_STAGES;    // [BWD_STAGES]
+  uint64_t* s_full = empty + BWD_STAGES;  // [2]  MMA1 done (per TMEM set)
+  uint64_t* pds_full = s_full + 2;        // WG0 wrote P, dS (128 arrivals)
+  uint64_t* o2_full = pds_full + 1;       // [2]  MMA2 done (per TMEM set)
+  uint64_t* o2_empty = o2_full + 2;       // [2]  WG1 read dQ/dK/dV out of the set (128 arrivals)
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(o2_empty + 2);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int L = p.L;
@@ -351,8 +357,10 @@ attn_bwd_tc_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_consta
   }
   if (warp == 8 && lane == 0) {
     tma_prefetch_desc(&tm_q); tma_prefetch_desc(&tm_k); tma_prefetch_desc(&tm_v); tma_prefetch_desc(&tm_do);
+    tma_prefetch_desc(&tm_dqkv);
     for (int s = 0; s < BWD_STAGES; ++s) { mbar_init(&full[s], 1); mbar_init(&empty[s], 1); }
-    mbar_init(s_full, 1); mbar_init(pds_full, 128); mbar_init(o2_full, 1); mbar_init(o2_empty, 128);
+    for (int b = 0; b < 2; ++b) { mbar_init(&s_full[b], 1); mbar_init(&o2_full[b], 1); mbar_init(&o2_empty[b], 128); }
+    mbar_init(pds_full, 128);
     fence_mbar_init();
   }
   if (warp == 9) {
@@ -408,6 +416,7 @@ attn_bwd_tc_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_consta
     constexpr uint32_t idesc_q = umma_idesc_bf16(128, 64) | IDESC_B_MN;
     auto issue_mma1 = [&](int it) {
       const int s = it % BWD_STAGES;
+      const uint32_t set = tmem_base + (it & 1) * 256;
       mbar_wait(&full[s], (it / BWD_STAGES) & 1);
       tc_fence_after();
       if (lane == 0) {
@@ -415,42 +424,46 @@ attn_bwd_tc_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_consta
         const uint64_t dq = umma_desc_kmajor_sw128(st), dk = umma_desc_kmajor_sw128(st + TILE_BYTES);
         const uint64_t dv = umma_desc_kmajor_sw128(st + 2 * TILE_BYTES), ddo = umma_desc_kmajor_sw128(st + 3 * TILE_BYTES);
 #pragma unroll
-        for (int k = 0; k < 4; ++k) umma_bf16_ss(tmem_base, dq + 2 * k, dk + 2 * k, idesc_s, k != 0);
+        for (int k = 0; k < 4; ++k) umma_bf16_ss(set, dq + 2 * k, dk + 2 * k, idesc_s, k != 0);
 #pragma unroll
-        for (int k = 0; k < 4; ++k) umma_bf16_ss(tmem_base + 128, ddo + 2 * k, dv + 2 * k, idesc_s, k != 0);
-        umma_commit(s_full);
+        for (int k = 0; k < 4; ++k) umma_bf16_ss(set + 128, ddo + 2 * k, dv + 2 * k, idesc_s, k != 0);
+        umma_commit(&s_full[it & 1]);
       }
       __syncwarp();
     };
     if (n_local > 0) issue_mma1(0);
     for (int it = 0; it < n_local; ++it) {
       const int s = it % BWD_STAGES;
-      mbar_wait(pds_full, it & 1);
-      mbar_wait(o2_empty, (it & 1) ^ 1);
+      const uint32_t set = tmem_base + (it & 1) * 256;
+      mbar_wait(pds_full, it & 1);  // P, dS are in smem; S / dP of this set have been consumed
       tc_fence_after();
       if (lane == 0) {
         const uint32_t st = smem_u32(smem + s * BWD_STAGE_BYTES);
         const uint32_t aP = smem_u32(sP), aS = smem_u32(sdS);
 #pragma unroll
         for (int k = 0; k < 8; ++k) {  // dV' = P^T dO   (K = query rows, 16 per step)
-          umma_bf16_ss(tmem_base + 256, umma_desc_mnmajor_sw128(aP + k * 2048, TILE_BYTES),
+          umma_bf16_ss(set, umma_desc_mnmajor_sw128(aP + k * 2048, TILE_BYTES),
                        umma_desc_mnmajor_sw128(st + 3 * TILE_BYTES + k * 2048, TILE_BYTES), idesc_t, k != 0);
         }
 #pragma unroll
         for (int k = 0; k < 8; ++k) {  // dK = dS^T Q'
-          umma_bf16_ss(tmem_base + 320, umma_desc_mnmajor_sw128(aS + k * 2048, TILE_BYTES),
+          umma_bf16_ss(set + 64, umma_desc_mnmajor_sw128(aS + k * 2048, TILE_BYTES),
                        umma_desc_mnmajor_sw128(st + k * 2048, TILE_BYTES), idesc_t, k != 0);
         }
 #pragma unroll
         for (int k = 0; k < 8; ++k) {  // dQ' = dS K     (K = keys)
-          umma_bf16_ss(tmem_base + 384, umma_desc_kmajor_sw128(aS + (k >> 2) * TILE_BYTES) + 2 * (k & 3),
+          umma_bf16_ss(set + 128, umma_desc_kmajor_sw128(aS + (k >> 2) * TILE_BYTES) + 2 * (k & 3),
                        umma_desc_mnmajor_sw128(st + TILE_BYTES + k * 2048, TILE_BYTES), idesc_q, k != 0);
         }
-        umma_commit(o2_full);
+        umma_commit(&o2_full[it & 1]);
         umma_commit(&empty[s]);
       }
       __syncwarp();
-      if (it + 1 < n_local) issue_mma1(it + 1);
+      if (it + 1 < n_local) {
+        // tile it+1 reuses the column set of tile it-1: its gradients must have been read out
+        if (it >= 1) mbar_wait(&o2_empty[(it + 1) & 1], ((it - 1) >> 1) & 1);
+        issue_mma1(it + 1);
+      }
     }
   } else {
     const int wg = warp >> 2, quad = warp & 3;
@@ -459,7 +472,6 @@ attn_bwd_tc_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_consta
     const int l = PACK == 2 ? (row & 63) : row;
     const int col0 = PACK == 2 ? slot * 64 : 0;
     constexpr int NCOL = PACK == 2 ? 64 : 128;
-    const uint32_t t_lane = tmem_base + (static_cast<uint32_t>(quad * 32) << 16);
     if (wg == 0) {
       // ---------------------------------------------------------- WG0: P, delta, dS
       auto load_lse = [&](int it_) -> float {
@@ -473,8 +485,9 @@ attn_bwd_tc_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_consta
         const bool valid = (l < L) && (g < p.heads_total);
         const float lse_s = lse_next * LOG2E;
         lse_next = load_lse(it + 1);
-        mbar_wait(s_full, it & 1);
+        mbar_wait(&s_full[it & 1], (it >> 1) & 1);
         tc_fence_after();
+        const uint32_t t_lane = tmem_base + (static_cast<uint32_t>(quad * 32) << 16) + (it & 1) * 256;
         if constexpr (PACK == 2) {
           // one pass: the row's 64 scores and 64 dP values stay in registers between delta and dS
           float pr[64], dp[64];
@@ -496,7 +509,7 @@ attn_bwd_tc_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_consta
 #pragma unroll
           for (int j = 0; j < 64; ++j) d4[j & 3] = fmaf(pr[j], dp[j], d4[j & 3]);
           const float delta = (d4[0] + d4[1]) + (d4[2] + d4[3]);
-          if (it > 0) mbar_wait(o2_full, (it - 1) & 1);  // MMA2 of the previous tile is done reading P / dS
+          if (it > 0) mbar_wait(&o2_full[(it - 1) & 1], ((it - 1) >> 1) & 1);  // MMA2 of the previous tile is done reading P / dS
 #pragma unroll
           for (int q = 0; q < 8; ++q) {
             const int kc = (col0 >> 3) + q;
@@ -525,9 +538,7 @@ attn_bwd_tc_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_consta
               delta = fmaf(pj, __uint_as_float(dv[j]), delta);
             }
           }
-          if (it > 0) {  // MMA2 of the previous tile must be done reading the P / dS tiles
-            mbar_wait(o2_full, (it - 1) & 1);
-          }
+          if (it > 0) mbar_wait(&o2_full[(it - 1) & 1], ((it - 1) >> 1) & 1);  // MMA2 of the previous tile done reading P / dS
 #pragma unroll 1
           for (int c = 0; c < NCOL; c += 32) {
             uint32_t sv[32], dv[32];
@@ -562,44 +573,69 @@ attn_bwd_tc_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_consta
     } else {
       // ---------------------------------------------------------- WG1: gradients out
       const size_t plane = static_cast<size_t>(p.heads_total) * L * 64;
+      const bool elected = (threadIdx.x == 128);
+      int pc = 0;  // parts stored so far (staging box = pc & 1)
       for (int it = 0; it < n_local; ++it) {
         const int tile = blockIdx.x + it * gridDim.x;
         const int g = tile * PACK + slot;
         const bool valid = (l < L) && (g < p.heads_total);
-        const int n = g / p.H, h = g - n * p.H;
-        bf16* tok = p.dqkv + (static_cast<size_t>(l) * p.NB + n) * p.ld + h * 64;
         bf16* hm = p.ddelta != nullptr ? p.ddelta + (static_cast<size_t>(g) * L + l) * 64 : nullptr;
-        mbar_wait(o2_full, it & 1);
+        const uint32_t t_lane = tmem_base + (static_cast<uint32_t>(quad * 32) << 16) + (it & 1) * 256;
+        mbar_wait(&o2_full[it & 1], (it >> 1) & 1);
         tc_fence_after();
 #pragma unroll 1
-        for (int part = 0; part < 3; ++part) {   // 0: dV', 1: dK, 2: dQ'
-          const float sc = part == 2 ? 0.125f : 1.f;
-          bf16* dst_tok = tok + (part == 0 ? 2 * p.D : (part == 1 ? p.D : 0));
-          bf16* dst_hm = (hm != nullptr && part != 1) ? hm + (part == 0 ? plane : 0) : nullptr;
+        for (int part = 0; part < 3; ++part, ++pc) {   // 0: dV' (columns 2D..), 1: dK (D..), 2: dQ' (0.., scaled 1/8)
+          uint32_t v[64];
+          tmem_ld_32x32(t_lane + part * 64, *reinterpret_cast<uint32_t(*)[32]>(&v[0]));
+          tmem_ld_32x32(t_lane + part * 64 + 32, *reinterpret_cast<uint32_t(*)[32]>(&v[32]));
+          tmem_ld_wait();
+          if (part == 2) {  // the set's last columns are in registers: MMA1 of tile it+2 may overwrite it
+            tc_fence_before();
+            mbar_arrive(&o2_empty[it & 1]);
+          }
+          // head-major d(delta) planes (dQ' -> plane 0, dV' -> plane 1): contiguous per head, stored directly
+          if (valid && hm != nullptr && part != 1) {
+            bf16* dst = hm + (part == 0 ? plane : 0);
 #pragma unroll
-          for (int c = 0; c < 64; c += 32) {
-            uint32_t v[32];
-            tmem_ld_32x32(t_lane + 256 + part * 64 + c, v);
-            tmem_ld_wait();
-            if (valid) {
+            for (int j = 0; j < 64; j += 8)
+              *reinterpret_cast<uint4*>(dst + j) =
+                  make_uint4(pack_bf16(__uint_as_float(v[j]), __uint_as_float(v[j + 1])),
+                             pack_bf16(__uint_as_float(v[j + 2]), __uint_as_float(v[j + 3])),
+                             pack_bf16(__uint_as_float(v[j + 4]), __uint_as_float(v[j + 5])),
+                             pack_bf16(__uint_as_float(v[j + 6]), __uint_as_float(v[j + 7])));
+          }
+          // token-major dqkv rows: staged [row][64] (swizzled) and TMA-stored per head
+          uint8_t* box = stg + (pc & 1) * TILE_BYTES;
+          if (elected) tma_store_wait_read<1>();  // the store that last used this box (two parts ago) has drained
+          named_bar_sync(2, 128);
+          if (valid) {
+            const float sc = part == 2 ? 0.125f : 1.f;
+            uint8_t* rp = box + row * 128;
 #pragma unroll
-              for (int j = 0; j < 32; j += 8) {
-                float f[8];
+            for (int q = 0; q < 8; ++q)
+              *reinterpret_cast<uint4*>(rp + ((q ^ (row & 7)) << 4)) =
+                  make_uint4(pack_bf16(__uint_as_float(v[8 * q]) * sc, __uint_as_float(v[8 * q + 1]) * sc),
+                             pack_bf16(__uint_as_float(v[8 * q + 2]) * sc, __uint_as_float(v[8 * q + 3]) * sc),
+                             pack_bf16(__uint_as_float(v[8 * q + 4]) * sc, __uint_as_float(v[8 * q + 5]) * sc),
+                             pack_bf16(__uint_as_float(v[8 * q + 6]) * sc, __uint_as_float(v[8 * q + 7]) * sc));
+          }
+          fence_proxy_async_smem();
+          named_bar_sync(2, 128);
+          if (elected) {
+            const int hbase = part == 0 ? 2 * p.H : (part == 1 ? p.H : 0);  // dqkv columns: [dq | dk | dv] heads
 #pragma unroll
-                for (int t = 0; t < 8; ++t) f[t] = __uint_as_float(v[j + t]);
-                *reinterpret_cast<uint4*>(dst_tok + c + j) =
-                    make_uint4(pack_bf16(f[0] * sc, f[1] * sc), pack_bf16(f[2] * sc, f[3] * sc),
-                               pack_bf16(f[4] * sc, f[5] * sc), pack_bf16(f[6] * sc, f[7] * sc));
-                if (dst_hm != nullptr)
-                  *reinterpret_cast<uint4*>(dst_hm + c + j) = make_uint4(pack_bf16(f[0], f[1]), pack_bf16(f[2], f[3]),
-                                                                         pack_bf16(f[4], f[5]), pack_bf16(f[6], f[7]));
+            for (int j = 0; j < PACK; ++j) {
+              const int gj = tile * PACK + j;
+              if (gj < p.heads_total) {
+                const int n = gj / p.H, h = gj - n * p.H;
+                tma_store_4d(&tm_dqkv, box + j * 8192, 0, hbase + h, n, 0);
               }
             }
+            tma_store_commit();
           }
         }
-        tc_fence_before();
-        mbar_arrive(o2_empty);
       }
+      if (elected) tma_store_wait_all<0>();
     }
   }
 
@@ -656,15 +692,17 @@ int attn_bwd_tc(cudaStream_t s, const AttnShape& a, const bf16* q, const bf16* k
   if (make_tmap_bf16_2d(&tk, k, rows, 64, 64, a.L, 64) != 0) return -1;
   if (make_tmap_bf16_2d(&tv, v, rows, 64, 64, a.L, 64) != 0) return -1;
   if (make_tmap_bf16_tok_heads(&tdo, do_tok, a.L, a.NB, a.H, a.D, a.L) != 0) return -1;
+  CUtensorMap tdq;  // dqkv rows viewed as 3H heads of 64 columns (the low-rank columns beyond 3D are not covered)
+  if (make_tmap_bf16_tok_heads(&tdq, dqkv, a.L, a.NB, 3 * a.H, ld_dqkv, a.L) != 0) return -1;
   BwdParams p{a.L, a.NB, a.H, a.D, heads, tiles, ld_dqkv, lse, dqkv, ddelta};
   const int grid = tiles < sm_count() ? tiles : sm_count();
   ProfScope prof(s, PC_ATTN_BWD);
   if (pack == 2) {
     PEVIT_CHECK_CUDA(cudaFuncSetAttribute(attn_bwd_tc_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, BWD_SMEM));
-    PEVIT_CHECK_CUDA(launch_kernel(attn_bwd_tc_kernel<2>, dim3(grid), dim3(BWD_THREADS), BWD_SMEM, s, 1, tq, tk, tv, tdo, p));
+    PEVIT_CHECK_CUDA(launch_kernel(attn_bwd_tc_kernel<2>, dim3(grid), dim3(BWD_THREADS), BWD_SMEM, s, 1, tq, tk, tv, tdo, tdq, p));
   } else {
     PEVIT_CHECK_CUDA(cudaFuncSetAttribute(attn_bwd_tc_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, BWD_SMEM));
-    PEVIT_CHECK_CUDA(launch_kernel(attn_bwd_tc_kernel<1>, dim3(grid), dim3(BWD_THREADS), BWD_SMEM, s, 1, tq, tk, tv, tdo, p));
+    PEVIT_CHECK_CUDA(launch_kernel(attn_bwd_tc_kernel<1>, dim3(grid), dim3(BWD_THREADS), BWD_SMEM, s, 1, tq, tk, tv, tdo, tdq, p));
   }
   PEVIT_CHECK_LAUNCH();
   return 0;
