@@ -148,6 +148,10 @@ typedef struct pevit_block_desc {
   int32_t save;        /* 1: fill `saved` for a later pevit_block_bwd */
   int32_t attn_impl;   /* 0 default (delta GEMM + tcgen05 attention), 1 CUDA-core kernel with in-kernel delta */
   int32_t need_dx;     /* bwd: 0 skips the input gradient (first layer: nothing upstream trains) */
+  int32_t out_rows;    /* 0: all L*NB token rows of y are produced.  > 0: only the leading out_rows rows (LND order,
+                        * a multiple of NB = whole token indices) are needed -- the last ViT block feeds only
+                        * ln_post(x[0]) (model.py:1046), so its out-projection, MLP and their dgrads run on NB rows.
+                        * y / dy then hold out_rows rows; attention still sees every key. */
 } pevit_block_desc;
 
 typedef struct pevit_block_weights {

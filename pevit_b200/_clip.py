@@ -230,11 +230,13 @@ class ResidualAttentionBlock(nn.Module):
         mask = self.attn_mask.to(dtype=x.dtype, device=x.device) if self.attn_mask is not None else None
         return self.attn(x, x, x, need_weights=False, attn_mask=mask)[0]
 
-    def forward(self, x: torch.Tensor) -> torch.Tensor:
+    def forward(self, x: torch.Tensor, out_tokens: int = 0) -> torch.Tensor:
+        """``out_tokens`` > 0 (fused blocks only): return just the first ``out_tokens`` token positions."""
         if self.fused:
-            return ops.block_forward(self, x, self.method, self.peft_tensors(), self.attn_impl).to(x.dtype)
+            return ops.block_forward(self, x, self.method, self.peft_tensors(), self.attn_impl, out_tokens).to(x.dtype)
         x = x + self.attention(self.ln_1(x))
-        return x + self.mlp(self.ln_2(x))
+        x = x + self.mlp(self.ln_2(x))
+        return x[:out_tokens] if out_tokens else x
 
 
 class Transformer(nn.Module):
@@ -296,7 +298,14 @@ class VisionTransformer(nn.Module):
             cls = self.class_embedding.to(x.dtype).expand(x.shape[0], 1, -1)
             x = torch.cat([cls, x], dim=1) + self.positional_embedding.to(x.dtype)
             x = self.ln_pre(x).transpose(0, 1).contiguous()      # (L, N, D) rows, as the reference (model.py:1042)
-        x = self.transformer(x)
+        blocks = self.transformer.resblocks
+        if x.is_cuda and len(blocks) > 0 and all(getattr(b, "fused", False) for b in blocks):
+            # only x[0] feeds ln_post (model.py:1046): the last block produces the class-token rows alone
+            for blk in blocks[:-1]:
+                x = blk(x)
+            x = blocks[-1](x, out_tokens=1)
+        else:
+            x = self.transformer(x)
         x = self.ln_post(x[0])                                   # class token of every image
         if self.proj is not None:
             x = x @ self.proj

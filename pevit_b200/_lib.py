@@ -44,6 +44,7 @@ class BlockDesc(C.Structure):
     _fields_ = [
         ("L", c_int32), ("NB", c_int32), ("D", c_int32), ("H", c_int32), ("method", c_int32),
         ("r", c_int32), ("alpha", c_float), ("save", c_int32), ("attn_impl", c_int32), ("need_dx", c_int32),
+        ("out_rows", c_int32),
     ]
 
 

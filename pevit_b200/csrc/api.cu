@@ -105,6 +105,8 @@ int check_desc(const pevit_block_desc* d) {
     PEVIT_REQUIRE(d->r > 0 && d->r <= 32 && (2 * d->r) % 8 == 0, "low-rank width r=%d unsupported", d->r);
   else
     PEVIT_REQUIRE(d->r == 0, "r must be 0 for method %d", d->method);
+  PEVIT_REQUIRE(d->out_rows >= 0 && d->out_rows <= d->L * d->NB && d->out_rows % d->NB == 0,
+                "out_rows=%d must be a multiple of NB=%d within L*NB", d->out_rows, d->NB);
   return 0;
 }
 
@@ -280,6 +282,7 @@ int pevit_block_fwd(const pevit_block_desc* desc, const pevit_block_weights* w, 
   const pevit_block_desc& d = *desc;
   cudaStream_t s = as_stream(stream);
   const int M = d.L * d.NB, D = d.D, r2 = 2 * d.r, W3 = 3 * D + r2;
+  const int Mo = d.out_rows > 0 ? d.out_rows : M;  // rows whose output is needed (everything after attention)
   Saved sv = carve_saved(d, saved);
   Work wk = carve_work(d, workspace);
   const size_t plane = static_cast<size_t>(M) * D;
@@ -320,22 +323,22 @@ int pevit_block_fwd(const pevit_block_desc* desc, const pevit_block_weights* w, 
     GemmEpilogue ep;
     ep.bias = w->b_o; ep.resid = x; ep.out_f32 = sv.x1; ep.ld_out = D;
     prof_set_tag(PC_GEMM_OUT);
-    TRY(gemm_tn(s, sv.o_tok, D, static_cast<const bf16*>(w->w_o), D, M, D, D, EPI_F32, ep));
+    TRY(gemm_tn(s, sv.o_tok, D, static_cast<const bf16*>(w->w_o), D, Mo, D, D, EPI_F32, ep));
   }
   // ln_2, c_fc + QuickGELU
-  TRY(layernorm_fwd(s, sv.x1, w->ln2_g, w->ln2_b, wk.xn2, nullptr, sv.mean2, sv.rstd2, M, D));
+  TRY(layernorm_fwd(s, sv.x1, w->ln2_g, w->ln2_b, wk.xn2, nullptr, sv.mean2, sv.rstd2, Mo, D));
   {
     GemmEpilogue ep;
     ep.bias = w->b_fc; ep.out_bf16 = wk.h; ep.out2_bf16 = d.save ? sv.z : nullptr; ep.ld_out = 4 * D;
     ep.act = ACT_QUICKGELU;
     prof_set_tag(PC_GEMM_FC);
-    TRY(gemm_tn(s, wk.xn2, D, static_cast<const bf16*>(w->w_fc), D, M, 4 * D, D, EPI_ACT, ep));
+    TRY(gemm_tn(s, wk.xn2, D, static_cast<const bf16*>(w->w_fc), D, Mo, 4 * D, D, EPI_ACT, ep));
   }
   if (!has_bottleneck(d)) {
     GemmEpilogue ep;
     ep.bias = w->b_proj; ep.resid = sv.x1; ep.out_f32 = y; ep.ld_out = D;
     prof_set_tag(PC_GEMM_PROJ);
-    TRY(gemm_tn(s, wk.h, 4 * D, static_cast<const bf16*>(w->w_proj), 4 * D, M, D, 4 * D, EPI_F32, ep));
+    TRY(gemm_tn(s, wk.h, 4 * D, static_cast<const bf16*>(w->w_proj), 4 * D, Mo, D, 4 * D, EPI_F32, ep));
     return 0;
   }
   // bottleneck: y = x1 + m + up(act(down(LN_a(m)))), m = mlp output  (adapter_model.py:264-282, F8)
@@ -343,21 +346,21 @@ int pevit_block_fwd(const pevit_block_desc* desc, const pevit_block_weights* w, 
     GemmEpilogue ep;
     ep.bias = w->b_proj; ep.out_f32 = sv.m; ep.ld_out = D;
     prof_set_tag(PC_GEMM_PROJ);
-    TRY(gemm_tn(s, wk.h, 4 * D, static_cast<const bf16*>(w->w_proj), 4 * D, M, D, 4 * D, EPI_F32, ep));
+    TRY(gemm_tn(s, wk.h, 4 * D, static_cast<const bf16*>(w->w_proj), 4 * D, Mo, D, 4 * D, EPI_F32, ep));
   }
-  TRY(layernorm_fwd(s, sv.m, w->lna_g, w->lna_b, sv.a_n, nullptr, sv.mean_a, sv.rstd_a, M, D));
+  TRY(layernorm_fwd(s, sv.m, w->lna_g, w->lna_b, sv.a_n, nullptr, sv.mean_a, sv.rstd_a, Mo, D));
   {
     GemmEpilogue ep;
     ep.bias = w->b_down; ep.out_bf16 = sv.u; ep.out2_bf16 = sv.zd; ep.ld_out = 64;
     ep.act = d.method == PEVIT_ADAPTER ? ACT_RELU : ACT_GELU_NEW;
     prof_set_tag(PC_GEMM_BOTTLENECK);
-    TRY(gemm_tn(s, sv.a_n, D, static_cast<const bf16*>(w->w_down), D, M, 64, D, EPI_ACT, ep));
+    TRY(gemm_tn(s, sv.a_n, D, static_cast<const bf16*>(w->w_down), D, Mo, 64, D, EPI_ACT, ep));
   }
   {
     GemmEpilogue ep;
     ep.bias = w->b_up; ep.resid = sv.x1; ep.resid2 = sv.m; ep.out_f32 = y; ep.ld_out = D;
     prof_set_tag(PC_GEMM_BOTTLENECK);
-    TRY(gemm_tn(s, sv.u, 64, static_cast<const bf16*>(w->w_up), 64, M, D, 64, EPI_F32, ep));
+    TRY(gemm_tn(s, sv.u, 64, static_cast<const bf16*>(w->w_up), 64, Mo, D, 64, EPI_F32, ep));
   }
   return 0;
 }
@@ -373,6 +376,7 @@ int pevit_block_bwd(const pevit_block_desc* desc, const pevit_block_weights* w, 
   const pevit_block_desc& d = *desc;
   cudaStream_t s = as_stream(stream);
   const int M = d.L * d.NB, D = d.D, r = d.r, r2 = 2 * r, W3 = 3 * D + r2;
+  const int Mo = d.out_rows > 0 ? d.out_rows : M;  // dy holds Mo rows; the rows beyond carry no gradient
   Saved sv = carve_saved(d, const_cast<void*>(saved));
   Work wk = carve_work(d, workspace);
   const size_t plane = static_cast<size_t>(M) * D;
@@ -380,33 +384,33 @@ int pevit_block_bwd(const pevit_block_desc* desc, const pevit_block_weights* w, 
   // bf16 copy of dy (A operand of the first dgrad GEMM): handed over by the block above when it produced one
   const bf16* dyb = static_cast<const bf16*>(dy_bf16);
   if (dyb == nullptr) {
-    TRY(cast_f32_to_bf16(s, dy, wk.dy_bf16, plane));
+    TRY(cast_f32_to_bf16(s, dy, wk.dy_bf16, static_cast<size_t>(Mo) * D));
     dyb = wk.dy_bf16;
   }
   const bf16* dmlp_bf16 = dyb;  // gradient w.r.t. the MLP output m
   if (has_bottleneck(d)) {
     const int act = d.method == PEVIT_ADAPTER ? ACT_RELU : ACT_GELU_NEW;
     // up projection: dW_up = dy^T u, db_up = colsum(dy), du = dy W_up, dzd = du * act'(zd)
-    if (g->d_w_up) TRY(atb_tc(s, dyb, D, sv.u, 64, 64, M, D, 0, 64, 1.f, g->d_w_up, 64));
-    if (g->d_b_up) TRY(colsum_bf16(s, dyb, nullptr, D, M, D, g->d_b_up));
+    if (g->d_w_up) TRY(atb_tc(s, dyb, D, sv.u, 64, 64, Mo, D, 0, 64, 1.f, g->d_w_up, 64));
+    if (g->d_b_up) TRY(colsum_bf16(s, dyb, nullptr, D, Mo, D, g->d_b_up));
     {
       GemmEpilogue ep;
       ep.out_bf16 = wk.dzd; ep.aux_bf16 = sv.zd; ep.ld_out = 64; ep.act = act;
       prof_set_tag(PC_GEMM_BOTTLENECK);
-      TRY(gemm_tn(s, dyb, D, static_cast<const bf16*>(w->w_up_t), D, M, 64, D, EPI_DACT, ep));
+      TRY(gemm_tn(s, dyb, D, static_cast<const bf16*>(w->w_up_t), D, Mo, 64, D, EPI_DACT, ep));
     }
     // down projection: dW_down^T = a_n^T dzd, db_down = colsum(dzd), da_n = dzd W_down
-    if (g->d_w_down) TRY(atb_tc(s, sv.a_n, D, wk.dzd, 64, 64, M, D, 0, 64, 1.f, g->d_w_down, 64));
-    if (g->d_b_down) TRY(colsum_bf16(s, wk.dzd, nullptr, 64, M, 64, g->d_b_down));
+    if (g->d_w_down) TRY(atb_tc(s, sv.a_n, D, wk.dzd, 64, 64, Mo, D, 0, 64, 1.f, g->d_w_down, 64));
+    if (g->d_b_down) TRY(colsum_bf16(s, wk.dzd, nullptr, 64, Mo, 64, g->d_b_down));
     {
       GemmEpilogue ep;
       ep.out_f32 = wk.dxn; ep.ld_out = D;
       prof_set_tag(PC_GEMM_BOTTLENECK);
-      TRY(gemm_tn(s, wk.dzd, 64, static_cast<const bf16*>(w->w_down_t), 64, M, D, 64, EPI_F32, ep));
+      TRY(gemm_tn(s, wk.dzd, 64, static_cast<const bf16*>(w->w_down_t), 64, Mo, D, 64, EPI_F32, ep));
     }
     // adapter LayerNorm backward (+ the direct `+ m` path: dres = dy), with its affine grads
     TRY(layernorm_bwd(s, wk.dxn, sv.m, w->lna_g, sv.mean_a, sv.rstd_a, dy, nullptr, wk.dm_bf16, g->d_lna_g, g->d_lna_b,
-                      M, D));
+                      Mo, D));
     dmlp_bf16 = wk.dm_bf16;
   }
   // c_proj dgrad fused with QuickGELU': dz = (dm W_proj) * g'(z)
@@ -414,23 +418,27 @@ int pevit_block_bwd(const pevit_block_desc* desc, const pevit_block_weights* w, 
     GemmEpilogue ep;
     ep.out_bf16 = wk.dz; ep.aux_bf16 = sv.z; ep.ld_out = 4 * D; ep.act = ACT_QUICKGELU;
     prof_set_tag(PC_GEMM_DPROJ);
-    TRY(gemm_tn(s, dmlp_bf16, D, static_cast<const bf16*>(w->w_proj_t), D, M, 4 * D, D, EPI_DACT, ep));
+    TRY(gemm_tn(s, dmlp_bf16, D, static_cast<const bf16*>(w->w_proj_t), D, Mo, 4 * D, D, EPI_DACT, ep));
   }
   // c_fc dgrad -> d ln_2 output
   {
     GemmEpilogue ep;
     ep.out_f32 = wk.dxn; ep.ld_out = D;
     prof_set_tag(PC_GEMM_DFC);
-    TRY(gemm_tn(s, wk.dz, 4 * D, static_cast<const bf16*>(w->w_fc_t), 4 * D, M, D, 4 * D, EPI_F32, ep));
+    TRY(gemm_tn(s, wk.dz, 4 * D, static_cast<const bf16*>(w->w_fc_t), 4 * D, Mo, D, 4 * D, EPI_F32, ep));
   }
   // ln_2 backward + residual path
-  TRY(layernorm_bwd(s, wk.dxn, sv.x1, w->ln2_g, sv.mean2, sv.rstd2, dy, wk.dx1, wk.dx1_bf16, nullptr, nullptr, M, D));
+  TRY(layernorm_bwd(s, wk.dxn, sv.x1, w->ln2_g, sv.mean2, sv.rstd2, dy, wk.dx1, wk.dx1_bf16, nullptr, nullptr, Mo, D));
   // out-proj dgrad -> dO (token rows)
   {
     GemmEpilogue ep;
     ep.out_bf16 = wk.do_tok; ep.ld_out = D;
     prof_set_tag(PC_GEMM_DOUT);
-    TRY(gemm_tn(s, wk.dx1_bf16, D, static_cast<const bf16*>(w->w_o_t), D, M, D, D, EPI_BF16, ep));
+    TRY(gemm_tn(s, wk.dx1_bf16, D, static_cast<const bf16*>(w->w_o_t), D, Mo, D, D, EPI_BF16, ep));
+    // query rows beyond out_rows received no gradient: their dO is exactly zero (they still act as keys)
+    if (Mo < M)
+      PEVIT_CHECK_CUDA(cudaMemsetAsync(wk.do_tok + static_cast<size_t>(Mo) * D, 0,
+                                       static_cast<size_t>(M - Mo) * D * sizeof(bf16), s));
   }
   // attention backward
   {
@@ -468,7 +476,7 @@ int pevit_block_bwd(const pevit_block_desc* desc, const pevit_block_weights* w, 
   }
   // ln_1 backward + residual path
   TRY(layernorm_bwd(s, wk.dxn, x, w->ln1_g, sv.mean1, sv.rstd1, wk.dx1, dx, static_cast<bf16*>(dx_bf16), nullptr, nullptr,
-                    M, D));
+                    M, D, Mo));
   return 0;
 }
 

@@ -35,10 +35,11 @@ int gemm_tn(cudaStream_t stream, const bf16* A, int lda, const bf16* B, int ldb,
 int layernorm_fwd(cudaStream_t s, const float* x, const float* gamma, const float* beta, bf16* y_bf16, float* y_f32,
                   float* mean, float* rstd, int M, int D);
 // dx = LN'(dy_n) [+ dres]; dy_n given as fp32.  gamma frozen unless dgamma/dbeta non-null
-// (adapter LayerNorm: atomically accumulated, caller zeroes).
+// (adapter LayerNorm: atomically accumulated, caller zeroes).  dres_rows >= 0: only the first dres_rows rows of dres
+// exist (the residual gradient of the remaining rows is zero); -1: all M rows.
 int layernorm_bwd(cudaStream_t s, const float* dyn, const float* x, const float* gamma, const float* mean,
                   const float* rstd, const float* dres, float* dx, bf16* dx_bf16, float* dgamma, float* dbeta, int M,
-                  int D);
+                  int D, int dres_rows = -1);
 
 // ------------------------------------------------------------------ attention_ref.cu
 struct AttnShape {

@@ -70,7 +70,7 @@ __global__ void __launch_bounds__(LN_THREADS)
 ln_bwd_kernel(const float* __restrict__ dyn, const float* __restrict__ x, const float* __restrict__ gamma,
               const float* __restrict__ mean_in, const float* __restrict__ rstd_in, const float* __restrict__ dres,
               float* __restrict__ dx, bf16* __restrict__ dx_bf16, float* __restrict__ dgamma,
-              float* __restrict__ dbeta, int M, int D) {
+              float* __restrict__ dbeta, int M, int D, int dres_rows) {
   pdl_launch_dependents();
   pdl_wait();
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -90,7 +90,8 @@ ln_bwd_kernel(const float* __restrict__ dyn, const float* __restrict__ x, const 
     // all loads of the row are issued before the first use
 #pragma unroll
     for (int i = 0; i < NV; ++i) { g[i] = dr[lane + 32 * i]; xh[i] = xr[lane + 32 * i]; }
-    if (dres != nullptr) {
+    const bool has_res = dres != nullptr && row < dres_rows;
+    if (has_res) {
 #pragma unroll
       for (int i = 0; i < NV; ++i) res[i] = rr[lane + 32 * i];
     }
@@ -119,7 +120,7 @@ ln_bwd_kernel(const float* __restrict__ dyn, const float* __restrict__ x, const 
       o.y = rstd * (g[i].y - m1 - xh[i].y * m2);
       o.z = rstd * (g[i].z - m1 - xh[i].z * m2);
       o.w = rstd * (g[i].w - m1 - xh[i].w * m2);
-      if (dres != nullptr) { o.x += res[i].x; o.y += res[i].y; o.z += res[i].z; o.w += res[i].w; }
+      if (has_res) { o.x += res[i].x; o.y += res[i].y; o.z += res[i].z; o.w += res[i].w; }
       if (dx != nullptr) reinterpret_cast<float4*>(dx + base)[c] = o;
       if (dx_bf16 != nullptr)
         reinterpret_cast<uint2*>(dx_bf16 + base)[c] = make_uint2(pack_bf16(o.x, o.y), pack_bf16(o.z, o.w));
@@ -160,13 +161,13 @@ int launch_fwd(cudaStream_t s, const float* x, const float* gamma, const float* 
 template <int NV>
 int launch_bwd(cudaStream_t s, const float* dyn, const float* x, const float* gamma, const float* mean,
                const float* rstd, const float* dres, float* dx, bf16* dx_bf16, float* dgamma, float* dbeta, int M,
-               int D) {
+               int D, int dres_rows) {
   if (dgamma != nullptr)
     launch_kernel(ln_bwd_kernel<NV, true>, dim3(ln_grid(M, 2)), dim3(LN_THREADS), 0, s, 1, dyn, x, gamma, mean, rstd, dres, dx,
-                  dx_bf16, dgamma, dbeta, M, D);
+                  dx_bf16, dgamma, dbeta, M, D, dres_rows);
   else
     launch_kernel(ln_bwd_kernel<NV, false>, dim3(ln_grid(M, 4)), dim3(LN_THREADS), 0, s, 1, dyn, x, gamma, mean, rstd, dres, dx,
-                  dx_bf16, static_cast<float*>(nullptr), static_cast<float*>(nullptr), M, D);
+                  dx_bf16, static_cast<float*>(nullptr), static_cast<float*>(nullptr), M, D, dres_rows);
   return 0;
 }
 
@@ -193,19 +194,20 @@ int layernorm_fwd(cudaStream_t s, const float* x, const float* gamma, const floa
 
 int layernorm_bwd(cudaStream_t s, const float* dyn, const float* x, const float* gamma, const float* mean,
                   const float* rstd, const float* dres, float* dx, bf16* dx_bf16, float* dgamma, float* dbeta, int M,
-                  int D) {
+                  int D, int dres_rows) {
   PEVIT_REQUIRE(D % 128 == 0 && D <= 128 * MAXV, "layernorm: D=%d must be a multiple of 128 and <= %d", D, 128 * MAXV);
   PEVIT_REQUIRE(dgamma == nullptr || dbeta != nullptr, "layernorm_bwd: dgamma without dbeta");
+  if (dres_rows < 0) dres_rows = M;
   ProfScope prof(s, PC_LN_BWD);
   switch (D / 128) {
-    case 1: launch_bwd<1>(s, dyn, x, gamma, mean, rstd, dres, dx, dx_bf16, dgamma, dbeta, M, D); break;
-    case 2: launch_bwd<2>(s, dyn, x, gamma, mean, rstd, dres, dx, dx_bf16, dgamma, dbeta, M, D); break;
-    case 3: launch_bwd<3>(s, dyn, x, gamma, mean, rstd, dres, dx, dx_bf16, dgamma, dbeta, M, D); break;
-    case 4: launch_bwd<4>(s, dyn, x, gamma, mean, rstd, dres, dx, dx_bf16, dgamma, dbeta, M, D); break;
-    case 5: launch_bwd<5>(s, dyn, x, gamma, mean, rstd, dres, dx, dx_bf16, dgamma, dbeta, M, D); break;
-    case 6: launch_bwd<6>(s, dyn, x, gamma, mean, rstd, dres, dx, dx_bf16, dgamma, dbeta, M, D); break;
-    case 7: launch_bwd<7>(s, dyn, x, gamma, mean, rstd, dres, dx, dx_bf16, dgamma, dbeta, M, D); break;
-    default: launch_bwd<8>(s, dyn, x, gamma, mean, rstd, dres, dx, dx_bf16, dgamma, dbeta, M, D); break;
+    case 1: launch_bwd<1>(s, dyn, x, gamma, mean, rstd, dres, dx, dx_bf16, dgamma, dbeta, M, D, dres_rows); break;
+    case 2: launch_bwd<2>(s, dyn, x, gamma, mean, rstd, dres, dx, dx_bf16, dgamma, dbeta, M, D, dres_rows); break;
+    case 3: launch_bwd<3>(s, dyn, x, gamma, mean, rstd, dres, dx, dx_bf16, dgamma, dbeta, M, D, dres_rows); break;
+    case 4: launch_bwd<4>(s, dyn, x, gamma, mean, rstd, dres, dx, dx_bf16, dgamma, dbeta, M, D, dres_rows); break;
+    case 5: launch_bwd<5>(s, dyn, x, gamma, mean, rstd, dres, dx, dx_bf16, dgamma, dbeta, M, D, dres_rows); break;
+    case 6: launch_bwd<6>(s, dyn, x, gamma, mean, rstd, dres, dx, dx_bf16, dgamma, dbeta, M, D, dres_rows); break;
+    case 7: launch_bwd<7>(s, dyn, x, gamma, mean, rstd, dres, dx, dx_bf16, dgamma, dbeta, M, D, dres_rows); break;
+    default: launch_bwd<8>(s, dyn, x, gamma, mean, rstd, dres, dx, dx_bf16, dgamma, dbeta, M, D, dres_rows); break;
   }
   PEVIT_CHECK_LAUNCH();
   return 0;

@@ -144,7 +144,7 @@ class _BlockFn(torch.autograd.Function):
     """y = ResidualAttentionBlock(x); differentiable w.r.t. x and the PEFT tensors only."""
 
     @staticmethod
-    def forward(ctx, x, pack: BlockPack, attn_impl: int, *peft):
+    def forward(ctx, x, pack: BlockPack, attn_impl: int, out_tokens: int, *peft):
         lib = L.lib()
         method = pack.method
         Lt, NB, D = x.shape
@@ -170,10 +170,10 @@ class _BlockFn(torch.autograd.Function):
             pack.cast(w_up, pack.w_up); pack.transpose(w_up, pack.w_up_t, D)
         need_grad = any(ctx.needs_input_grad)
         desc = L.BlockDesc(Lt, NB, D, pack.H, METHOD_IDS[method], pack.r, pack.alpha, int(need_grad), attn_impl,
-                           int(ctx.needs_input_grad[0]))
+                           int(ctx.needs_input_grad[0]), out_tokens * NB)
         saved = torch.empty(lib.pevit_block_saved_bytes(C.byref(desc)), dtype=torch.uint8, device=x.device)
         ws = workspace(x.device, lib.pevit_block_workspace_bytes(C.byref(desc)))
-        y = torch.empty_like(x)
+        y = torch.empty_like(x) if out_tokens == 0 else torch.empty(out_tokens, NB, D, dtype=x.dtype, device=x.device)
         w = pack.weights_struct(delta_bias, lna, b_down, b_up)
         L.check(lib.pevit_block_fwd(C.byref(desc), C.byref(w), _ptr(x), _ptr(y), _ptr(saved), _ptr(ws), st),
                 "pevit_block_fwd")
@@ -233,10 +233,13 @@ class _BlockFn(torch.autograd.Function):
             grads = (d_pmat[:, :r].t().contiguous(), d_qmat[0], d_pmat[:, r:].t().contiguous(), d_qmat[1])
         else:
             grads = (d_lna_g, d_lna_b, d_w_down_t.t().contiguous(), d_b_down, d_w_up, d_b_up)
-        return (dx, None, None, *grads)
+        return (dx, None, None, None, *grads)
 
 
-def block_forward(block, x: torch.Tensor, method: str, peft: tuple, attn_impl: int = 0) -> torch.Tensor:
+def block_forward(block, x: torch.Tensor, method: str, peft: tuple, attn_impl: int = 0,
+                  out_tokens: int = 0) -> torch.Tensor:
+    """``out_tokens`` > 0: only the first ``out_tokens`` token positions of the output are produced (shape
+    (out_tokens, N, D)); the last ViT block passes 1 because only ``x[0]`` feeds ``ln_post`` (model.py:1046)."""
     if not x.is_cuda:
         raise RuntimeError("pevit_b200 blocks run on CUDA (sm_100a) only; there is no CPU fallback")
     if block.training and method == "kadaptation":
@@ -256,7 +259,9 @@ def block_forward(block, x: torch.Tensor, method: str, peft: tuple, attn_impl: i
                                "weights (the reference Classifier does, kadaptation_clip.py:104-122) or run under "
                                "torch.no_grad()")
     pack = get_pack(block, method)
-    return _BlockFn.apply(x, pack, attn_impl, *peft)
+    if not 0 <= out_tokens <= x.shape[0]:
+        raise ValueError(f"out_tokens={out_tokens} outside 0..{x.shape[0]}")
+    return _BlockFn.apply(x, pack, attn_impl, out_tokens, *peft)
 
 
 class StemPack:

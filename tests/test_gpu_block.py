@@ -181,3 +181,34 @@ def test_train_mode_is_rejected_and_no_cpu_fallback():
     model.eval().cpu()
     with pytest.raises(RuntimeError):
         model.encode_image(torch.randn(2, 3, 32, 32))
+
+
+@pytest.mark.parametrize("method", METHODS)
+def test_last_block_class_token_rows_only(method):
+    """out_tokens=1 (what VisionTransformer passes to its last block: only x[0] feeds ln_post, model.py:1046) must
+    give the same class-token rows and the same gradients as the full block followed by [0]."""
+    shape = synth.VIT_TINY
+    sd = synth.clip_state_dict(shape, seed=7)
+    model = BUILDERS[method](dict(sd))
+    synth.randomize_adapters(model.named_parameters(), seed=8)
+    model = model.cuda()
+    freeze_like_reference(model, method)
+    blk = model.visual.transformer.resblocks[-1]
+    Lt, NB, D = shape.tokens, 6, shape.vision_width
+    g = torch.Generator(device="cuda").manual_seed(9)
+    x0 = torch.randn(Lt, NB, D, device="cuda", generator=g)
+    w = torch.randn(NB, D, device="cuda", generator=g)
+    outs, grads = [], []
+    for out_tokens in (0, 1):
+        model.zero_grad(set_to_none=True)
+        x = x0.clone().requires_grad_(True)
+        y = blk(x, out_tokens=out_tokens)
+        assert y.shape == ((Lt, NB, D) if out_tokens == 0 else (1, NB, D))
+        (y[0] * w).sum().backward()
+        outs.append(y[0].detach().clone())
+        grads.append({"x": x.grad.clone(), **{n: p.grad.clone() for n, p in model.named_parameters()
+                                                if p.grad is not None}})
+    assert rel_inf(outs[1], outs[0]) < 1e-6
+    assert grads[0].keys() == grads[1].keys() and len(grads[0]) > 1
+    for name in grads[0]:
+        assert rel_inf(grads[1][name], grads[0][name]) < 2e-3, name
