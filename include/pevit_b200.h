@@ -123,6 +123,12 @@ int pevit_colsum_bf16(const void* x, int32_t m, int32_t d, float* out, void* str
 int pevit_kad_factor_grads(const float* dP, const float* dQ, const float* u1, const float* v1, const float* u2,
                            const float* v2, const float* s, const float* t, int32_t d, float* du1, float* dv1,
                            float* du2, float* dv2, float* ds, float* dt, void* stream);
+/* Same contractions ADDED onto du1..dt (the caller's .grad buffers): what autograd's AccumulateGrad would do with
+ * the result of pevit_kad_factor_grads, without the temporaries and the add kernels (the shared phm_rule tensors
+ * receive one contribution per block, kadaptation_clip.py:352 loss.backward()). */
+int pevit_kad_factor_grads_acc(const float* dP, const float* dQ, const float* u1, const float* v1, const float* u2,
+                               const float* v2, const float* s, const float* t, int32_t d, float* du1, float* dv1,
+                               float* du2, float* dv2, float* ds, float* dt, void* stream);
 /* weight packing: fp32 [rows][cols] -> bf16 (same layout / transposed with leading dim ldd) */
 int pevit_cast_bf16(const float* src, void* dst, size_t n, void* stream);
 int pevit_transpose_bf16(const float* src, int32_t rows, int32_t cols, void* dst, int32_t ldd, void* stream);

@@ -88,6 +88,7 @@ _SIGNATURES = {
                                c_float, c_void_p, c_int32, c_void_p]),
     "pevit_colsum_bf16": (c_int32, [c_void_p, c_int32, c_int32, c_void_p, c_void_p]),
     "pevit_kad_factor_grads": (c_int32, [c_void_p] * 8 + [c_int32] + [c_void_p] * 7),
+    "pevit_kad_factor_grads_acc": (c_int32, [c_void_p] * 8 + [c_int32] + [c_void_p] * 7),
     "pevit_cast_bf16": (c_int32, [c_void_p, c_void_p, c_size_t, c_void_p]),
     "pevit_transpose_bf16": (c_int32, [c_void_p, c_int32, c_int32, c_void_p, c_int32, c_void_p]),
     "pevit_patch_embed_workspace_bytes": (c_size_t, [c_int32] * 4),

@@ -229,7 +229,13 @@ int pevit_colsum_bf16(const void* x, int32_t m, int32_t d, float* out, void* str
 int pevit_kad_factor_grads(const float* dP, const float* dQ, const float* u1, const float* v1, const float* u2,
                            const float* v2, const float* s, const float* t, int32_t d, float* du1, float* dv1,
                            float* du2, float* dv2, float* ds, float* dt, void* stream) {
-  return kad_factor_grads(as_stream(stream), dP, dQ, u1, v1, u2, v2, s, t, d, du1, dv1, du2, dv2, ds, dt);
+  return kad_factor_grads(as_stream(stream), dP, dQ, u1, v1, u2, v2, s, t, d, du1, dv1, du2, dv2, ds, dt, false);
+}
+
+int pevit_kad_factor_grads_acc(const float* dP, const float* dQ, const float* u1, const float* v1, const float* u2,
+                               const float* v2, const float* s, const float* t, int32_t d, float* du1, float* dv1,
+                               float* du2, float* dv2, float* ds, float* dt, void* stream) {
+  return kad_factor_grads(as_stream(stream), dP, dQ, u1, v1, u2, v2, s, t, d, du1, dv1, du2, dv2, ds, dt, true);
 }
 
 int pevit_cast_bf16(const float* src, void* dst, size_t n, void* stream) {

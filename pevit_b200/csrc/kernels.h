@@ -96,10 +96,10 @@ int atb_tc(cudaStream_t s, const bf16* A, int lda, const bf16* B, int ldb, int n
 // column sums of one or two (X1 nullable) bf16 [M][ld] matrices (first D columns), atomically accumulated into
 // out[D] (caller zeroes).
 int colsum_bf16(cudaStream_t s, const bf16* X0, const bf16* X1, int ld, int M, int D, float* out);
-// KAdaptation factor gradients from dP [D][64] (q|v) and dQ [2][D][32].
+// KAdaptation factor gradients from dP [D][64] (q|v) and dQ [2][D][32]; accumulate: += instead of =.
 int kad_factor_grads(cudaStream_t s, const float* dP, const float* dQ, const float* u1, const float* v1, const float* u2,
                      const float* v2, const float* sfac, const float* tfac, int D, float* du1, float* dv1, float* du2,
-                     float* dv2, float* dsfac, float* dtfac);
+                     float* dv2, float* dsfac, float* dtfac, bool accumulate);
 // dT (fp32 [M][r2 cols starting at col0]) -> bf16 into dqkv_ext[:, 3D+col0 ...]
 int cast_f32_to_bf16_2d(cudaStream_t s, const float* src, int lds, bf16* dst, int ldd, int rows, int cols);
 

@@ -176,7 +176,7 @@ kad_factor_grads_kernel(const float* __restrict__ dP, const float* __restrict__ 
                         const float* __restrict__ v1, const float* __restrict__ u2, const float* __restrict__ v2,
                         const float* __restrict__ sf, const float* __restrict__ tf, int D, float* __restrict__ du1,
                         float* __restrict__ dv1, float* __restrict__ du2, float* __restrict__ dv2,
-                        float* __restrict__ dsf, float* __restrict__ dtf) {
+                        float* __restrict__ dsf, float* __restrict__ dtf, int accumulate) {
   pdl_launch_dependents();
   pdl_wait();
   extern __shared__ float sm[];  // [4][D]: dPq, dPv, dQq, dQv columns i; then s, t, u1, u2, v1, v2 rows i
@@ -205,15 +205,15 @@ kad_factor_grads_kernel(const float* __restrict__ dP, const float* __restrict__ 
       const float* fac = which < 2 ? ss : tt;
       for (int k = 0; k < F; ++k) g = fmaf(col[a * F + k], fac[k], g);
       float* dst = which == 0 ? du1 : (which == 1 ? du2 : (which == 2 ? dv1 : dv2));
-      dst[i * 32 + a] = g;
+      dst[i * 32 + a] = accumulate ? dst[i * 32 + a] + g : g;
     } else if (o < 128 + F) {
       const int k = o - 128;
       for (int a = 0; a < 32; ++a) g = fmaf(cPq[a * F + k], a1[a], fmaf(cPv[a * F + k], a2[a], g));
-      dsf[i * F + k] = g;
+      dsf[i * F + k] = accumulate ? dsf[i * F + k] + g : g;
     } else {
       const int k = o - 128 - F;
       for (int a = 0; a < 32; ++a) g = fmaf(cQq[a * F + k], b1[a], fmaf(cQv[a * F + k], b2[a], g));
-      dtf[i * F + k] = g;
+      dtf[i * F + k] = accumulate ? dtf[i * F + k] + g : g;
     }
   }
 }
@@ -320,11 +320,11 @@ int colsum_bf16(cudaStream_t s, const bf16* X0, const bf16* X1, int ld, int M, i
 
 int kad_factor_grads(cudaStream_t s, const float* dP, const float* dQ, const float* u1, const float* v1, const float* u2,
                      const float* v2, const float* sfac, const float* tfac, int D, float* du1, float* dv1, float* du2,
-                     float* dv2, float* dsfac, float* dtfac) {
+                     float* dv2, float* dsfac, float* dtfac, bool accumulate) {
   ProfScope prof(s, PC_FACTOR_GRADS);
   const size_t smem = (4 * static_cast<size_t>(D) + 2 * (D / 32) + 128) * sizeof(float);
   PEVIT_CHECK_CUDA(launch_kernel(kad_factor_grads_kernel, dim3(32), dim3(256), smem, s, 1, dP, dQ, u1, v1, u2, v2, sfac, tfac, D,
-                                 du1, dv1, du2, dv2, dsfac, dtfac));
+                                 du1, dv1, du2, dv2, dsfac, dtfac, accumulate ? 1 : 0));
   PEVIT_CHECK_LAUNCH();
   return 0;
 }

@@ -13,7 +13,7 @@ import torch.distributed as dist
 import torch.nn.functional as F
 from torch import nn
 
-from . import _clip, synth
+from . import _clip, ops, synth
 
 BUILD = {"kadaptation": _clip.KAD, "lora": _clip.LORA, "adapter": _clip.ADAPTER, "compacter": _clip.COMPACTER}
 
@@ -82,6 +82,8 @@ class FineTuner(nn.Module):
         self.grads = FlatGrads(self.used, device)
         self.flat_grad = self.grads.flat
         self.opt = torch.optim.SGD(self.used, lr=lr, momentum=momentum, weight_decay=weight_decay)
+        # every trainable .grad is a persistent view into the flat buffer: let the block kernels add into it directly
+        ops.set_direct_grad_accumulation(True)
 
     def forward(self, images: torch.Tensor) -> torch.Tensor:
         return self.head(self.backbone.encode_image(images).float())

@@ -37,6 +37,17 @@ def _f32c(t: torch.Tensor) -> torch.Tensor:
     return t.contiguous()
 
 
+# Opt-in (engine.FineTuner turns it on): KAdaptation blocks add their PEFT gradients straight into the parameters'
+# existing ``.grad`` buffers from inside the kernels -- the arithmetic of autograd's AccumulateGrad without the ~100
+# temporaries, zero-fills and add kernels per step.  Parameter hooks do not fire for gradients delivered this way,
+# so the default stays the plain autograd contract.
+_direct_grads = [False]
+
+
+def set_direct_grad_accumulation(on: bool) -> None:
+    _direct_grads[0] = bool(on)
+
+
 _workspace: Dict[Tuple[int, int], torch.Tensor] = {}
 # bf16 shadow of the most recent block input-gradient: (data_ptr, version, shape) of the fp32 dx -> bf16 copy.
 # The block below receives that very tensor as its dy, so it can skip re-casting it (one slot is enough).
@@ -93,7 +104,14 @@ class BlockPack:
         if method in ("adapter", "compacter"):
             self.w_down, self.w_down_t = torch.empty(BOTTLENECK, D, **bf), torch.empty(D, BOTTLENECK, **bf)
             self.w_up, self.w_up_t = torch.empty(D, BOTTLENECK, **bf), torch.empty(BOTTLENECK, D, **bf)
+        self._grad_scratch = None
         self.key = self.signature(block)
+
+    def grad_scratch(self) -> torch.Tensor:
+        """fp32 [D*2r + 2*D*r]: dP | dQ accumulators of one backward (direct-accumulation mode)."""
+        if self._grad_scratch is None:
+            self._grad_scratch = torch.zeros(4 * self.D * self.r, dtype=torch.float32, device=self.w_o.device)
+        return self._grad_scratch
 
     @staticmethod
     def cast(src: torch.Tensor, dst: torch.Tensor) -> None:
@@ -178,6 +196,7 @@ class _BlockFn(torch.autograd.Function):
         L.check(lib.pevit_block_fwd(C.byref(desc), C.byref(w), _ptr(x), _ptr(y), _ptr(saved), _ptr(ws), st),
                 "pevit_block_fwd")
         ctx.pack, ctx.desc = pack, desc
+        ctx.live = peft if (_direct_grads[0] and method == "kadaptation") else None
         ctx.save_for_backward(x, saved, *peft_c)
         return y
 
@@ -200,12 +219,21 @@ class _BlockFn(torch.autograd.Function):
             dy16 = shadow[1]
         g = L.BlockGrads()
         delta_bias = lna = b_down = b_up = None
+        live = ctx.live
+        direct = live is not None and all(
+            t.requires_grad and t.grad is not None and t.grad.is_contiguous() and t.grad.dtype == torch.float32
+            and t.grad.device == dev for t in live)
         if method in ("kadaptation", "lora"):
-            d_pmat = torch.zeros(D, 2 * r, **f32)
-            d_qmat = torch.zeros(2, D, r, **f32)
+            if direct:  # one persistent scratch buffer for dP | dQ, zeroed by a single fill
+                scratch = pack.grad_scratch()
+                scratch.zero_()
+                d_pmat, d_qmat = scratch[:D * 2 * r].view(D, 2 * r), scratch[D * 2 * r:].view(2, D, r)
+            else:
+                d_pmat = torch.zeros(D, 2 * r, **f32)
+                d_qmat = torch.zeros(2, D, r, **f32)
             g.d_pmat, g.d_qmat = _ptr(d_pmat), _ptr(d_qmat)
             if method == "kadaptation":
-                d_bias = torch.zeros(D, **f32)
+                d_bias = live[6].grad if direct else torch.zeros(D, **f32)   # colsum accumulates atomically
                 g.d_bias = _ptr(d_bias)
                 delta_bias = peft_c[6]
         else:
@@ -221,7 +249,13 @@ class _BlockFn(torch.autograd.Function):
                                     C.byref(g), _ptr(saved), _ptr(ws), st), "pevit_block_bwd")
         if dx is not None:
             _dx_shadow[0] = ((dx.data_ptr(), dx._version, tuple(dx.shape)), dx16)
-        if method == "kadaptation":
+        if method == "kadaptation" and direct:
+            u1, v1, u2, v2, s, t, _ = peft_c
+            L.check(lib.pevit_kad_factor_grads_acc(_ptr(d_pmat), _ptr(d_qmat), _ptr(u1), _ptr(v1), _ptr(u2), _ptr(v2),
+                                                   _ptr(s), _ptr(t), D, *(_ptr(p.grad) for p in live[:6]), st),
+                    "pevit_kad_factor_grads_acc")
+            grads = (None,) * 7
+        elif method == "kadaptation":
             u1, v1, u2, v2, s, t, _ = peft_c
             outs = [torch.empty_like(p) for p in (u1, v1, u2, v2, s, t)]
             L.check(lib.pevit_kad_factor_grads(_ptr(d_pmat), _ptr(d_qmat), _ptr(u1), _ptr(v1), _ptr(u2), _ptr(v2),

@@ -39,7 +39,7 @@ def test_ctypes_binding_covers_the_header(built):
 
 def test_struct_layouts_match_the_header():
     # sizes computed from the C declarations (LP64): pointers 8 B, int32/float 4 B, natural alignment
-    assert ctypes.sizeof(L.BlockDesc) == 10 * 4
+    assert ctypes.sizeof(L.BlockDesc) == 11 * 4
     assert ctypes.sizeof(L.BlockWeights) == 28 * 8
     assert ctypes.sizeof(L.BlockGrads) == 9 * 8
     assert ctypes.sizeof(L.GemmArgs) == 152

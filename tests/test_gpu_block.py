@@ -212,3 +212,24 @@ def test_last_block_class_token_rows_only(method):
     assert grads[0].keys() == grads[1].keys() and len(grads[0]) > 1
     for name in grads[0]:
         assert rel_inf(grads[1][name], grads[0][name]) < 2e-3, name
+
+
+def test_direct_grad_accumulation_matches_autograd():
+    """engine.FineTuner lets the KAdaptation kernels add into the flat .grad buffer; the result must equal the plain
+    autograd path (fresh gradient tensors + AccumulateGrad), including the rules shared by all blocks."""
+    from pevit_b200 import engine, ops
+    shape = synth.VIT_TINY
+    tuner = engine.FineTuner("kadaptation", shape, device="cuda", seed=3)
+    img = synth.images(6, shape.image_resolution, seed=11).cuda()
+    lab = synth.labels(6, 10, seed=12).cuda()
+    flats = []
+    try:
+        for direct in (True, False):
+            ops.set_direct_grad_accumulation(direct)
+            tuner.grads.zero_()
+            F.cross_entropy(tuner(img), lab).backward()
+            flats.append(tuner.flat_grad.clone())
+    finally:
+        ops.set_direct_grad_accumulation(False)
+    assert flats[0].abs().max() > 0
+    assert rel_inf(flats[0], flats[1]) < 1e-5
