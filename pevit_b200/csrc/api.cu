@@ -386,6 +386,7 @@ int pevit_block_bwd(const pevit_block_desc* desc, const pevit_block_weights* w, 
   Saved sv = carve_saved(d, const_cast<void*>(saved));
   Work wk = carve_work(d, workspace);
   const size_t plane = static_cast<size_t>(M) * D;
+  bf16* dxn16 = reinterpret_cast<bf16*>(wk.dxn);  // dgrad GEMM -> LayerNorm backward hand-over (bf16 view of dxn)
 
   // bf16 copy of dy (A operand of the first dgrad GEMM): handed over by the block above when it produced one
   const bf16* dyb = static_cast<const bf16*>(dy_bf16);
@@ -429,12 +430,13 @@ int pevit_block_bwd(const pevit_block_desc* desc, const pevit_block_weights* w, 
   // c_fc dgrad -> d ln_2 output
   {
     GemmEpilogue ep;
-    ep.out_f32 = wk.dxn; ep.ld_out = D;
+    ep.out_bf16 = dxn16; ep.ld_out = D;  // handed to the LayerNorm backward in bf16 (fp32 accumulate, one rounding)
     prof_set_tag(PC_GEMM_DFC);
-    TRY(gemm_tn(s, wk.dz, 4 * D, static_cast<const bf16*>(w->w_fc_t), 4 * D, Mo, D, 4 * D, EPI_F32, ep));
+    TRY(gemm_tn(s, wk.dz, 4 * D, static_cast<const bf16*>(w->w_fc_t), 4 * D, Mo, D, 4 * D, EPI_BF16, ep));
   }
   // ln_2 backward + residual path
-  TRY(layernorm_bwd(s, wk.dxn, sv.x1, w->ln2_g, sv.mean2, sv.rstd2, dy, wk.dx1, wk.dx1_bf16, nullptr, nullptr, Mo, D));
+  TRY(layernorm_bwd(s, nullptr, sv.x1, w->ln2_g, sv.mean2, sv.rstd2, dy, wk.dx1, wk.dx1_bf16, nullptr, nullptr, Mo, D, -1,
+                    dxn16));
   // out-proj dgrad -> dO (token rows)
   {
     GemmEpilogue ep;
@@ -476,13 +478,13 @@ int pevit_block_bwd(const pevit_block_desc* desc, const pevit_block_weights* w, 
   // in-projection dgrad (K = 3D + 2r: the low-rank columns ride along)
   {
     GemmEpilogue ep;
-    ep.out_f32 = wk.dxn; ep.ld_out = D;
+    ep.out_bf16 = dxn16; ep.ld_out = D;
     prof_set_tag(PC_GEMM_DQKV);
-    TRY(gemm_tn(s, wk.dqkv, W3, static_cast<const bf16*>(w->w_qkv_ext_t), W3, M, D, W3, EPI_F32, ep));
+    TRY(gemm_tn(s, wk.dqkv, W3, static_cast<const bf16*>(w->w_qkv_ext_t), W3, M, D, W3, EPI_BF16, ep));
   }
   // ln_1 backward + residual path
-  TRY(layernorm_bwd(s, wk.dxn, x, w->ln1_g, sv.mean1, sv.rstd1, wk.dx1, dx, static_cast<bf16*>(dx_bf16), nullptr, nullptr,
-                    M, D, Mo));
+  TRY(layernorm_bwd(s, nullptr, x, w->ln1_g, sv.mean1, sv.rstd1, wk.dx1, dx, static_cast<bf16*>(dx_bf16), nullptr, nullptr,
+                    M, D, Mo, dxn16));
   return 0;
 }
 

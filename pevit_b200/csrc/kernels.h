@@ -36,10 +36,11 @@ int layernorm_fwd(cudaStream_t s, const float* x, const float* gamma, const floa
                   float* mean, float* rstd, int M, int D);
 // dx = LN'(dy_n) [+ dres]; dy_n given as fp32.  gamma frozen unless dgamma/dbeta non-null
 // (adapter LayerNorm: atomically accumulated, caller zeroes).  dres_rows >= 0: only the first dres_rows rows of dres
-// exist (the residual gradient of the remaining rows is zero); -1: all M rows.
+// exist (the residual gradient of the remaining rows is zero); -1: all M rows.  dyn_bf16 (frozen gamma only): dy_n
+// as the bf16 output of the dgrad GEMM, used instead of dyn.
 int layernorm_bwd(cudaStream_t s, const float* dyn, const float* x, const float* gamma, const float* mean,
                   const float* rstd, const float* dres, float* dx, bf16* dx_bf16, float* dgamma, float* dbeta, int M,
-                  int D, int dres_rows = -1);
+                  int D, int dres_rows = -1, const bf16* dyn_bf16 = nullptr);
 
 // ------------------------------------------------------------------ attention_ref.cu
 struct AttnShape {

@@ -65,7 +65,8 @@ ln_fwd_kernel(const float* __restrict__ x, const float* __restrict__ gamma, cons
 }
 
 // dx = rstd * (g - mean(g) - xhat * mean(g * xhat)) [+ dres],  g = dyn * gamma, xhat = (x-mean)*rstd
-template <int NV, bool kParamGrads>
+// kBf16In: dyn is the bf16 output of the dgrad GEMM that produced it (half the traffic of an fp32 hand-over)
+template <int NV, bool kParamGrads, bool kBf16In>
 __global__ void __launch_bounds__(LN_THREADS)
 ln_bwd_kernel(const float* __restrict__ dyn, const float* __restrict__ x, const float* __restrict__ gamma,
               const float* __restrict__ mean_in, const float* __restrict__ rstd_in, const float* __restrict__ dres,
@@ -84,12 +85,22 @@ ln_bwd_kernel(const float* __restrict__ dyn, const float* __restrict__ x, const 
   for (int row = blockIdx.x * LN_ROWS + warp; row < M; row += gridDim.x * LN_ROWS) {
     const size_t base = static_cast<size_t>(row) * D;
     const float4* dr = reinterpret_cast<const float4*>(dyn + base);
+    const uint2* dr16 = reinterpret_cast<const uint2*>(reinterpret_cast<const bf16*>(dyn) + base);
     const float4* xr = reinterpret_cast<const float4*>(x + base);
     const float4* rr = reinterpret_cast<const float4*>(dres + base);
     float4 g[NV], xh[NV], res[NV];
     // all loads of the row are issued before the first use
 #pragma unroll
-    for (int i = 0; i < NV; ++i) { g[i] = dr[lane + 32 * i]; xh[i] = xr[lane + 32 * i]; }
+    for (int i = 0; i < NV; ++i) {
+      if constexpr (kBf16In) {
+        const uint2 u = dr16[lane + 32 * i];
+        const float2 lo = unpack_bf16(u.x), hi = unpack_bf16(u.y);
+        g[i] = make_float4(lo.x, lo.y, hi.x, hi.y);
+      } else {
+        g[i] = dr[lane + 32 * i];
+      }
+      xh[i] = xr[lane + 32 * i];
+    }
     const bool has_res = dres != nullptr && row < dres_rows;
     if (has_res) {
 #pragma unroll
@@ -161,12 +172,15 @@ int launch_fwd(cudaStream_t s, const float* x, const float* gamma, const float* 
 template <int NV>
 int launch_bwd(cudaStream_t s, const float* dyn, const float* x, const float* gamma, const float* mean,
                const float* rstd, const float* dres, float* dx, bf16* dx_bf16, float* dgamma, float* dbeta, int M,
-               int D, int dres_rows) {
-  if (dgamma != nullptr)
-    launch_kernel(ln_bwd_kernel<NV, true>, dim3(ln_grid(M, 2)), dim3(LN_THREADS), 0, s, 1, dyn, x, gamma, mean, rstd, dres, dx,
+               int D, int dres_rows, bool bf16_in) {
+  if (bf16_in)
+    launch_kernel(ln_bwd_kernel<NV, false, true>, dim3(ln_grid(M, 4)), dim3(LN_THREADS), 0, s, 1, dyn, x, gamma, mean, rstd, dres,
+                  dx, dx_bf16, static_cast<float*>(nullptr), static_cast<float*>(nullptr), M, D, dres_rows);
+  else if (dgamma != nullptr)
+    launch_kernel(ln_bwd_kernel<NV, true, false>, dim3(ln_grid(M, 2)), dim3(LN_THREADS), 0, s, 1, dyn, x, gamma, mean, rstd, dres, dx,
                   dx_bf16, dgamma, dbeta, M, D, dres_rows);
   else
-    launch_kernel(ln_bwd_kernel<NV, false>, dim3(ln_grid(M, 4)), dim3(LN_THREADS), 0, s, 1, dyn, x, gamma, mean, rstd, dres, dx,
+    launch_kernel(ln_bwd_kernel<NV, false, false>, dim3(ln_grid(M, 4)), dim3(LN_THREADS), 0, s, 1, dyn, x, gamma, mean, rstd, dres, dx,
                   dx_bf16, static_cast<float*>(nullptr), static_cast<float*>(nullptr), M, D, dres_rows);
   return 0;
 }
@@ -194,20 +208,23 @@ int layernorm_fwd(cudaStream_t s, const float* x, const float* gamma, const floa
 
 int layernorm_bwd(cudaStream_t s, const float* dyn, const float* x, const float* gamma, const float* mean,
                   const float* rstd, const float* dres, float* dx, bf16* dx_bf16, float* dgamma, float* dbeta, int M,
-                  int D, int dres_rows) {
+                  int D, int dres_rows, const bf16* dyn_bf16) {
   PEVIT_REQUIRE(D % 128 == 0 && D <= 128 * MAXV, "layernorm: D=%d must be a multiple of 128 and <= %d", D, 128 * MAXV);
   PEVIT_REQUIRE(dgamma == nullptr || dbeta != nullptr, "layernorm_bwd: dgamma without dbeta");
+  PEVIT_REQUIRE(dyn_bf16 == nullptr || dgamma == nullptr, "layernorm_bwd: bf16 dyn is for frozen-gamma LayerNorms only");
+  const bool bf16_in = dyn_bf16 != nullptr;
+  if (bf16_in) dyn = reinterpret_cast<const float*>(dyn_bf16);
   if (dres_rows < 0) dres_rows = M;
   ProfScope prof(s, PC_LN_BWD);
   switch (D / 128) {
-    case 1: launch_bwd<1>(s, dyn, x, gamma, mean, rstd, dres, dx, dx_bf16, dgamma, dbeta, M, D, dres_rows); break;
-    case 2: launch_bwd<2>(s, dyn, x, gamma, mean, rstd, dres, dx, dx_bf16, dgamma, dbeta, M, D, dres_rows); break;
-    case 3: launch_bwd<3>(s, dyn, x, gamma, mean, rstd, dres, dx, dx_bf16, dgamma, dbeta, M, D, dres_rows); break;
-    case 4: launch_bwd<4>(s, dyn, x, gamma, mean, rstd, dres, dx, dx_bf16, dgamma, dbeta, M, D, dres_rows); break;
-    case 5: launch_bwd<5>(s, dyn, x, gamma, mean, rstd, dres, dx, dx_bf16, dgamma, dbeta, M, D, dres_rows); break;
-    case 6: launch_bwd<6>(s, dyn, x, gamma, mean, rstd, dres, dx, dx_bf16, dgamma, dbeta, M, D, dres_rows); break;
-    case 7: launch_bwd<7>(s, dyn, x, gamma, mean, rstd, dres, dx, dx_bf16, dgamma, dbeta, M, D, dres_rows); break;
-    default: launch_bwd<8>(s, dyn, x, gamma, mean, rstd, dres, dx, dx_bf16, dgamma, dbeta, M, D, dres_rows); break;
+    case 1: launch_bwd<1>(s, dyn, x, gamma, mean, rstd, dres, dx, dx_bf16, dgamma, dbeta, M, D, dres_rows, bf16_in); break;
+    case 2: launch_bwd<2>(s, dyn, x, gamma, mean, rstd, dres, dx, dx_bf16, dgamma, dbeta, M, D, dres_rows, bf16_in); break;
+    case 3: launch_bwd<3>(s, dyn, x, gamma, mean, rstd, dres, dx, dx_bf16, dgamma, dbeta, M, D, dres_rows, bf16_in); break;
+    case 4: launch_bwd<4>(s, dyn, x, gamma, mean, rstd, dres, dx, dx_bf16, dgamma, dbeta, M, D, dres_rows, bf16_in); break;
+    case 5: launch_bwd<5>(s, dyn, x, gamma, mean, rstd, dres, dx, dx_bf16, dgamma, dbeta, M, D, dres_rows, bf16_in); break;
+    case 6: launch_bwd<6>(s, dyn, x, gamma, mean, rstd, dres, dx, dx_bf16, dgamma, dbeta, M, D, dres_rows, bf16_in); break;
+    case 7: launch_bwd<7>(s, dyn, x, gamma, mean, rstd, dres, dx, dx_bf16, dgamma, dbeta, M, D, dres_rows, bf16_in); break;
+    default: launch_bwd<8>(s, dyn, x, gamma, mean, rstd, dres, dx, dx_bf16, dgamma, dbeta, M, D, dres_rows, bf16_in); break;
   }
   PEVIT_CHECK_LAUNCH();
   return 0;
