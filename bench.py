@@ -337,9 +337,9 @@ def run_b200(args):
     if clocks is not None:
         clocks.stop()
     if rank != 0:
-        if world > 1:
-            dist.destroy_process_group()
-        return
+        tuner.release_graph()
+        torch.cuda.synchronize()
+        finish(world)
 
     ms_step = ms_total / args.steps
     value = N * world * args.steps / (ms_total / 1e3)
@@ -399,11 +399,32 @@ def run_b200(args):
     if world == 1 and not args.no_cpu_baseline:
         line["cpu_baseline"] = cpu_baseline(args, shape)
     print(json.dumps(line), flush=True)
+    tuner.release_graph()
+    torch.cuda.synchronize()
+    finish(world)
+
+
+def finish(world: int) -> None:
+    """Leave without hanging: the step graph holds NCCL work, and tearing the communicator down while it is alive
+    has been seen to block forever.  Results are already printed; give destroy a bounded chance, then exit."""
+    sys.stdout.flush()
+    sys.stderr.flush()
     if world > 1:
-        dist.destroy_process_group()
+        import torch.distributed as dist
+        t = threading.Thread(target=lambda: dist.is_initialized() and dist.destroy_process_group(), daemon=True)
+        t.start()
+        t.join(10.0)
+    os._exit(0)
 
 
 def main():
+    import signal
+
+    def on_alarm(signum, frame):  # never hang a GPU box: a stuck collective or teardown ends the process instead
+        print("[bench] watchdog: run exceeded 25 minutes, aborting", file=sys.stderr, flush=True)
+        os._exit(3)
+    signal.signal(signal.SIGALRM, on_alarm)
+    signal.alarm(1500)
     args = parse()
     if args.impl == "reference":
         run_reference(args)

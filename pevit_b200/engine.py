@@ -127,5 +127,13 @@ class FineTuner(nn.Module):
         self.graph.replay()
         return self.static_loss
 
+    def release_graph(self) -> None:
+        """Drop the captured step (and the NCCL work it holds) before the process group is torn down."""
+        graph = getattr(self, "graph", None)
+        if graph is not None:
+            torch.cuda.synchronize()
+            graph.reset()
+            self.graph = None
+
     def trainable_numel(self) -> int:
         return sum(p.numel() for p in self.params)
