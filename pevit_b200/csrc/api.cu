@@ -466,13 +466,21 @@ int pevit_block_bwd(const pevit_block_desc* desc, const pevit_block_weights* w, 
       ep.out_bf16 = wk.dqkv + 3 * D + which * r; ep.ld_out = W3;
       prof_set_tag(PC_GEMM_DT);
       TRY(gemm_tn(s, dd, D, qmat_t + static_cast<size_t>(which) * r * D, D, M, r, D, EPI_BF16, ep));
-      // dQ = alpha * dDelta^T T
-      if (g->d_qmat)
-        TRY(atb_tc(s, dd, D, sv.T, r2, r2, M, D, which * r, r, d.alpha, g->d_qmat + static_cast<size_t>(which) * D * r, r));
+    }
+    // the three weight-gradient shaped products of the layer in one launch:
+    //   dQ_q = alpha dDelta_q^T T_q,  dQ_v = alpha dDelta_v^T T_v,  dP = X^T dT  ([D][2r], q | v)
+    {
+      AtbProblem probs[3];
+      int n = 0;
+      if (g->d_qmat) {
+        for (int which = 0; which < 2; ++which)
+          probs[n++] = AtbProblem{wk.ddelta + which * plane, D, sv.T, r2, r2, which * r, r, d.alpha,
+                                  g->d_qmat + static_cast<size_t>(which) * D * r, r};
+      }
+      if (g->d_pmat) probs[n++] = AtbProblem{sv.xn1, D, wk.dqkv + 3 * D, W3, r2, 0, r2, 1.f, g->d_pmat, r2};
+      if (n > 0) TRY(atb_tc_batch(s, probs, n, M, D));
     }
     if (d.method == PEVIT_KADAPTATION && g->d_bias) TRY(colsum_bf16(s, wk.ddelta, wk.ddelta + plane, D, M, D, g->d_bias));
-    // dP = X^T dT  ([D][2r], q | v)
-    if (g->d_pmat) TRY(atb_tc(s, sv.xn1, D, wk.dqkv + 3 * D, W3, r2, M, D, 0, r2, 1.f, g->d_pmat, r2));
   }
   if (!d.need_dx) return 0;  // first layer: nothing upstream of this block trains
   // in-projection dgrad (K = 3D + 2r: the low-rank columns ride along)

@@ -23,8 +23,19 @@ struct AtbParams {
   float* C;
 };
 
+constexpr int ATB_MAX_BATCH = 3;
+struct AtbBatch {
+  CUtensorMap tm_a[ATB_MAX_BATCH], tm_b[ATB_MAX_BATCH];
+  AtbParams p[ATB_MAX_BATCH];
+};
+
+// blockIdx.z selects one of up to three independent products (same M): the block backward has three of them per
+// layer (dQ_q, dQ_v, dP), each far too short to fill the GPU or amortise a launch on its own.
 __global__ void __launch_bounds__(ATB_THREADS)
-atb_tc_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant__ CUtensorMap tm_b, AtbParams p) {
+atb_tc_kernel(const __grid_constant__ AtbBatch batch) {
+  const CUtensorMap& tm_a = batch.tm_a[blockIdx.z];
+  const CUtensorMap& tm_b = batch.tm_b[blockIdx.z];
+  const AtbParams& p = batch.p[blockIdx.z];
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   uint64_t* full = reinterpret_cast<uint64_t*>(smem + ATB_STAGES * ATB_STAGE_BYTES);
@@ -130,23 +141,27 @@ atb_tc_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant__ 
 
 // A: bf16 [M][lda] (uses Kc columns).  B: bf16 [M][ldb] with nb_cols (<= 64) columns visible; columns
 // [n_lo, n_lo + n_cnt) of the product are accumulated into C[kc][0 .. n_cnt) (row stride ldc).
-int atb_tc(cudaStream_t s, const bf16* A, int lda, const bf16* B, int ldb, int nb_cols, int M, int Kc, int n_lo,
-           int n_cnt, float scale, float* C, int ldc) {
-  PEVIT_REQUIRE(nb_cols >= 1 && nb_cols <= 64 && n_lo >= 0 && n_lo + n_cnt <= nb_cols,
-                "atb_tc: column window [%d,%d) outside the %d visible columns", n_lo, n_lo + n_cnt, nb_cols);
-  PEVIT_REQUIRE(lda % 8 == 0 && ldb % 8 == 0 && (reinterpret_cast<uintptr_t>(A) & 15) == 0 &&
-                    (reinterpret_cast<uintptr_t>(B) & 15) == 0,
-                "atb_tc: operands need 16-byte aligned rows (lda=%d ldb=%d)", lda, ldb);
-  CUtensorMap ta, tb;
-  if (make_tmap_bf16_2d(&ta, A, M, Kc, lda, ATB_BK, 64) != 0) return -1;
-  if (make_tmap_bf16_2d(&tb, B, M, nb_cols, ldb, ATB_BK, 64) != 0) return -1;
+int atb_tc_batch(cudaStream_t s, const AtbProblem* probs, int count, int M, int Kc) {
+  PEVIT_REQUIRE(count >= 1 && count <= ATB_MAX_BATCH, "atb_tc_batch: %d problems (1..%d)", count, ATB_MAX_BATCH);
   const int gx = (Kc + 127) / 128;
-  int splits = (sm_count() + gx - 1) / gx;  // ~one CTA per SM: fewer partial tiles to reduce with atomics
+  int splits = (sm_count() + gx * count - 1) / (gx * count);  // ~one CTA per SM over the whole batch
+  if (splits < 8) splits = 8;
   int rps = (M + splits - 1) / splits;
   rps = ((rps + ATB_BK - 1) / ATB_BK) * ATB_BK;
   splits = (M + rps - 1) / rps;
-  const int vec4 = (n_lo % 4 == 0 && n_cnt % 4 == 0 && ldc % 4 == 0 && (reinterpret_cast<uintptr_t>(C) & 15) == 0) ? 1 : 0;
-  AtbParams p{M, Kc, n_lo, n_cnt, ldc, rps, vec4, scale, C};
+  AtbBatch batch;
+  for (int i = 0; i < count; ++i) {
+    const AtbProblem& q = probs[i];
+    PEVIT_REQUIRE(q.nb_cols >= 1 && q.nb_cols <= 64 && q.n_lo >= 0 && q.n_lo + q.n_cnt <= q.nb_cols,
+                  "atb_tc: column window [%d,%d) outside the %d visible columns", q.n_lo, q.n_lo + q.n_cnt, q.nb_cols);
+    PEVIT_REQUIRE(q.lda % 8 == 0 && q.ldb % 8 == 0 && (reinterpret_cast<uintptr_t>(q.A) & 15) == 0 &&
+                      (reinterpret_cast<uintptr_t>(q.B) & 15) == 0,
+                  "atb_tc: operands need 16-byte aligned rows (lda=%d ldb=%d)", q.lda, q.ldb);
+    if (make_tmap_bf16_2d(&batch.tm_a[i], q.A, M, Kc, q.lda, ATB_BK, 64) != 0) return -1;
+    if (make_tmap_bf16_2d(&batch.tm_b[i], q.B, M, q.nb_cols, q.ldb, ATB_BK, 64) != 0) return -1;
+    const int vec4 = (q.n_lo % 4 == 0 && q.n_cnt % 4 == 0 && q.ldc % 4 == 0 && (reinterpret_cast<uintptr_t>(q.C) & 15) == 0) ? 1 : 0;
+    batch.p[i] = AtbParams{M, Kc, q.n_lo, q.n_cnt, q.ldc, rps, vec4, q.scale, q.C};
+  }
   static bool configured[64] = {};
   int dev = 0;
   PEVIT_CHECK_CUDA(cudaGetDevice(&dev));
@@ -155,9 +170,15 @@ int atb_tc(cudaStream_t s, const bf16* A, int lda, const bf16* B, int ldb, int n
     configured[dev & 63] = true;
   }
   ProfScope prof(s, PC_ATB);
-  PEVIT_CHECK_CUDA(launch_kernel(atb_tc_kernel, dim3(gx, splits), dim3(ATB_THREADS), ATB_SMEM, s, 1, ta, tb, p));
+  PEVIT_CHECK_CUDA(launch_kernel(atb_tc_kernel, dim3(gx, splits, count), dim3(ATB_THREADS), ATB_SMEM, s, 1, batch));
   PEVIT_CHECK_LAUNCH();
   return 0;
+}
+
+int atb_tc(cudaStream_t s, const bf16* A, int lda, const bf16* B, int ldb, int nb_cols, int M, int Kc, int n_lo,
+           int n_cnt, float scale, float* C, int ldc) {
+  const AtbProblem q{A, lda, B, ldb, nb_cols, n_lo, n_cnt, scale, C, ldc};
+  return atb_tc_batch(s, &q, 1, M, Kc);
 }
 
 }  // namespace pevit

@@ -406,6 +406,10 @@ gemm_tn_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
             if (nt + j * BOXCOLS < N) tma_prefetch_l2_2d(&tmap_aux, nt + j * BOXCOLS, m0);
         }
         for (int kb = 0; kb < num_kb; ++kb) {
+          // A (activations, tens of MB, read once per N tile) mostly misses L2; the ring buffers ~1 us of mainloop,
+          // less than an HBM round trip under load -- pull the A box of a later k-block into L2 now (B, the frozen
+          // weights, stays L2-resident on its own)
+          if (ep.a_prefetch > 0 && kb + ep.a_prefetch < num_kb) tma_prefetch_l2_2d(&tmap_a, (kb + ep.a_prefetch) * BK, m0);
           mbar_wait(&empty_bar[stage], phase ^ 1);
           uint8_t* sa = smem + stage * Cfg::STAGE_BYTES;
           if constexpr (CTA2) {
@@ -725,7 +729,10 @@ int pick_tile(int M, int N, int forced, bool allow_pair, bool* pair) {
 }  // namespace
 
 int gemm_tn(cudaStream_t stream, const bf16* A, int lda, const bf16* B, int ldb, int M, int N, int K, int epi,
-            const GemmEpilogue& ep, int force_bn) {
+            const GemmEpilogue& ep_in, int force_bn) {
+  static const int a_prefetch = getenv("PEVIT_GEMM_APF") ? atoi(getenv("PEVIT_GEMM_APF")) : 0;
+  GemmEpilogue ep = ep_in;
+  ep.a_prefetch = a_prefetch;
   PEVIT_REQUIRE(M > 0 && N > 0 && K > 0, "gemm_tn: empty problem %d x %d x %d", M, N, K);
   PEVIT_REQUIRE(K % 8 == 0 && lda % 8 == 0 && ldb % 8 == 0,
                 "gemm_tn: K, lda, ldb must be multiples of 8 (16-byte TMA strides): K=%d lda=%d ldb=%d", K, lda, ldb);

@@ -24,6 +24,7 @@ struct GemmEpilogue {
   bf16* qkv_hm = nullptr;          // [3][NB*H][L][64] head-major q (pre-scaled 1/8), k, v
   bf16* t_out = nullptr;           // [M][r2] low-rank activations T = X P (bf16: A operand of the delta GEMM)
   int L = 0, NB = 0, H = 0, D = 0, r2 = 0;
+  int a_prefetch = 0;  // k-blocks ahead of the ring at which the producer pulls A boxes into L2 (0 = off)
   int debug = 0;  // diagnostics only (tools/gemm_bench.py): 1 = no TMA loads, 2 = no MMAs, 4 = no epilogue stores
 };
 
@@ -94,6 +95,14 @@ int atb_accumulate(cudaStream_t s, const void* A, int a_is_bf16, int lda, const 
 // B exposes nb_cols (<= 64) columns; columns [n_lo, n_lo+n_cnt) of A^T B go to C[kc][0..n_cnt) (row stride ldc).
 int atb_tc(cudaStream_t s, const bf16* A, int lda, const bf16* B, int ldb, int nb_cols, int M, int Kc, int n_lo,
            int n_cnt, float scale, float* C, int ldc);
+// up to three such products over the same M rows and Kc columns in ONE launch (blockIdx.z = problem)
+struct AtbProblem {
+  const bf16* A; int lda;
+  const bf16* B; int ldb, nb_cols, n_lo, n_cnt;
+  float scale;
+  float* C; int ldc;
+};
+int atb_tc_batch(cudaStream_t s, const AtbProblem* probs, int count, int M, int Kc);
 // column sums of one or two (X1 nullable) bf16 [M][ld] matrices (first D columns), atomically accumulated into
 // out[D] (caller zeroes).
 int colsum_bf16(cudaStream_t s, const bf16* X0, const bf16* X1, int ld, int M, int D, float* out);
