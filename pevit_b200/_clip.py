@@ -290,6 +290,10 @@ class VisionTransformer(nn.Module):
         return not (torch.is_grad_enabled() and any(p.requires_grad for p in ps))
 
     def forward(self, x: torch.Tensor) -> torch.Tensor:
+        blocks = self.transformer.resblocks
+        fused = x.is_cuda and len(blocks) > 0 and all(getattr(b, "fused", False) for b in blocks)
+        if fused:
+            ops.expand_ahead(list(blocks), blocks[0].method)     # factor expansions overlap the stem (side stream)
         if x.is_cuda and not x.requires_grad and self._stem_is_frozen() and x.shape[-1] % self.conv1.kernel_size[0] == 0:
             x = ops.stem_forward(self, x)                        # fused stem -> (L, N, D)
         else:  # stem parameters being trained (not a PEViT setting): stock ops keep autograd semantics
@@ -298,8 +302,8 @@ class VisionTransformer(nn.Module):
             cls = self.class_embedding.to(x.dtype).expand(x.shape[0], 1, -1)
             x = torch.cat([cls, x], dim=1) + self.positional_embedding.to(x.dtype)
             x = self.ln_pre(x).transpose(0, 1).contiguous()      # (L, N, D) rows, as the reference (model.py:1042)
-        blocks = self.transformer.resblocks
-        if x.is_cuda and len(blocks) > 0 and all(getattr(b, "fused", False) for b in blocks):
+        if fused:
+            ops.join_side_stream(x.device)
             # only x[0] feeds ln_post (model.py:1046): the last block produces the class-token rows alone
             for blk in blocks[:-1]:
                 x = blk(x)

@@ -138,14 +138,23 @@ ln_bwd_kernel(const float* __restrict__ dyn, const float* __restrict__ x, const 
     }
   }
   if (kParamGrads) {
-    // every lane owns fixed columns; one atomic per (warp, column)
+    // every lane owns fixed columns: the CTA's warps first combine in shared memory, then ONE global atomic per
+    // (CTA, column) -- per-warp global atomics put thousands of contenders on each of the 2*D addresses
+    __shared__ float sacc[2 * 128 * MAXV];
+    for (int c = threadIdx.x; c < 2 * D; c += LN_THREADS) sacc[c] = 0.f;
+    __syncthreads();
 #pragma unroll
     for (int i = 0; i < NV; ++i) {
       const int c = (lane + 32 * i) * 4;
-      atomicAdd(dgamma + c, accg[i].x); atomicAdd(dgamma + c + 1, accg[i].y);
-      atomicAdd(dgamma + c + 2, accg[i].z); atomicAdd(dgamma + c + 3, accg[i].w);
-      atomicAdd(dbeta + c, accb[i].x); atomicAdd(dbeta + c + 1, accb[i].y);
-      atomicAdd(dbeta + c + 2, accb[i].z); atomicAdd(dbeta + c + 3, accb[i].w);
+      atomicAdd(&sacc[c], accg[i].x); atomicAdd(&sacc[c + 1], accg[i].y);
+      atomicAdd(&sacc[c + 2], accg[i].z); atomicAdd(&sacc[c + 3], accg[i].w);
+      atomicAdd(&sacc[D + c], accb[i].x); atomicAdd(&sacc[D + c + 1], accb[i].y);
+      atomicAdd(&sacc[D + c + 2], accb[i].z); atomicAdd(&sacc[D + c + 3], accb[i].w);
+    }
+    __syncthreads();
+    for (int c = threadIdx.x; c < D; c += LN_THREADS) {
+      atomicAdd(dgamma + c, sacc[c]);
+      atomicAdd(dbeta + c, sacc[D + c]);
     }
   }
 }

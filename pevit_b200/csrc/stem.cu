@@ -11,6 +11,9 @@ namespace pevit {
 namespace {
 
 // patches[(n*G + gy)*G + gx][c*p*p + i*p + j] = img[n][c][gy*p + i][gx*p + j]   (bf16, K padded with zeros)
+// One block per patch.  p % 4 == 0 (every CLIP ViT: 32, 16; not 14): a thread converts 4 consecutive pixels of one
+// patch row (16-byte load, 8-byte store); otherwise element by element.
+template <bool kVec4>
 __global__ void im2col_kernel(const float* __restrict__ img, bf16* __restrict__ patches, int NB, int R, int p, int G,
                               int K, int Kpad) {
   pdl_launch_dependents();
@@ -21,14 +24,25 @@ __global__ void im2col_kernel(const float* __restrict__ img, bf16* __restrict__ 
   const float* src = img + (static_cast<size_t>(n) * 3 * R + gy * p) * R + gx * p;
   bf16* dst = patches + static_cast<size_t>(row) * Kpad;
   const int pp = p * p;
-  for (int k = threadIdx.x; k < Kpad; k += blockDim.x) {
-    float v = 0.f;
-    if (k < K) {
-      const int c = k / pp, rem = k - c * pp;
-      const int i = rem / p, j = rem - i * p;
-      v = __ldg(src + (static_cast<size_t>(c) * R + i) * R + j);
+  if constexpr (kVec4) {
+    const int p4 = p >> 2;
+    for (int q = threadIdx.x; q < (K >> 2); q += blockDim.x) {  // q = (c, i, j/4)
+      const int ci = q / p4, j4 = q - ci * p4;
+      const int c = ci / p, i = ci - c * p;
+      const float4 v = __ldg(reinterpret_cast<const float4*>(src + (static_cast<size_t>(c) * R + i) * R) + j4);
+      *reinterpret_cast<uint2*>(dst + 4 * q) = make_uint2(pack_bf16(v.x, v.y), pack_bf16(v.z, v.w));
     }
-    dst[k] = __float2bfloat16(v);
+    for (int k = K + threadIdx.x; k < Kpad; k += blockDim.x) dst[k] = __float2bfloat16(0.f);
+  } else {
+    for (int k = threadIdx.x; k < Kpad; k += blockDim.x) {
+      float v = 0.f;
+      if (k < K) {
+        const int c = k / pp, rem = k - c * pp;
+        const int i = rem / p, j = rem - i * p;
+        v = __ldg(src + (static_cast<size_t>(c) * R + i) * R + j);
+      }
+      dst[k] = __float2bfloat16(v);
+    }
   }
 }
 
@@ -98,7 +112,12 @@ int patch_embed(cudaStream_t s, const float* img, const bf16* w_patch, const flo
                                         ((static_cast<size_t>(rows) * Kpad * sizeof(bf16) + 255) & ~size_t(255)));
   {
     ProfScope prof(s, PC_STEM);
-    PEVIT_CHECK_CUDA(launch_kernel(im2col_kernel, dim3(rows), dim3(256), 0, s, 1, img, patches, NB, R, p, G, K, Kpad));
+    // 16-byte loads need p % 4 == 0, R % 4 == 0 and an aligned image base
+    const bool vec4 = p % 4 == 0 && R % 4 == 0 && (reinterpret_cast<uintptr_t>(img) & 15) == 0;
+    if (vec4)
+      PEVIT_CHECK_CUDA(launch_kernel(im2col_kernel<true>, dim3(rows), dim3(256), 0, s, 1, img, patches, NB, R, p, G, K, Kpad));
+    else
+      PEVIT_CHECK_CUDA(launch_kernel(im2col_kernel<false>, dim3(rows), dim3(256), 0, s, 1, img, patches, NB, R, p, G, K, Kpad));
     PEVIT_CHECK_LAUNCH();
   }
   GemmEpilogue ep;

@@ -105,6 +105,7 @@ class BlockPack:
             self.w_down, self.w_down_t = torch.empty(BOTTLENECK, D, **bf), torch.empty(D, BOTTLENECK, **bf)
             self.w_up, self.w_up_t = torch.empty(D, BOTTLENECK, **bf), torch.empty(BOTTLENECK, D, **bf)
         self._grad_scratch = None
+        self.expanded_ahead = False
         self.key = self.signature(block)
 
     def grad_scratch(self) -> torch.Tensor:
@@ -158,6 +159,50 @@ def get_pack(block, method: str) -> BlockPack:
     return pack
 
 
+def _expand_factors(pack: BlockPack, peft_c: tuple, st: int) -> None:
+    """Write the expanded low-rank operands (P^T rows of the in-projection, Q, alpha*Q) of one block."""
+    lib, D = L.lib(), pack.D
+    if pack.method == "kadaptation":
+        u1, v1, u2, v2, s, t = peft_c[:6]
+        L.check(lib.pevit_kad_expand(_ptr(u1), _ptr(v1), _ptr(u2), _ptr(v2), _ptr(s), _ptr(t), D, pack.alpha,
+                                     _ptr(pack.w_qkv_ext), _ptr(pack.w_qkv_ext_t), _ptr(pack.qmat),
+                                     _ptr(pack.qmat_t), _ptr(pack.delta_w), st), "pevit_kad_expand")
+    else:
+        aq, bq, av, bv = peft_c
+        L.check(lib.pevit_lora_expand(_ptr(aq), _ptr(av), _ptr(bq), _ptr(bv), D, pack.r, pack.alpha,
+                                      _ptr(pack.w_qkv_ext), _ptr(pack.w_qkv_ext_t), _ptr(pack.qmat),
+                                      _ptr(pack.qmat_t), _ptr(pack.delta_w), st), "pevit_lora_expand")
+
+
+_side_streams: Dict[int, torch.cuda.Stream] = {}
+
+
+def expand_ahead(blocks, method: str) -> None:
+    """Run the factor expansions of ALL blocks now, on a side stream, so that these twelve latency-bound launches
+    overlap the stem instead of sitting one by one on the critical path in front of every block.  The caller joins
+    with ``join_side_stream()`` before the first block runs.  Each pack is flagged so the block skips its own."""
+    if method not in ("kadaptation", "lora") or not blocks:
+        return
+    dev = blocks[0].attn.in_proj_weight.device
+    main = torch.cuda.current_stream(dev)
+    side = _side_streams.get(dev.index or 0)
+    if side is None:
+        side = _side_streams[dev.index or 0] = torch.cuda.Stream(device=dev)
+    side.wait_stream(main)  # earlier work on the main stream (previous backward) may still read the packs
+    with torch.cuda.stream(side):
+        st = side.cuda_stream
+        for blk in blocks:
+            pack = get_pack(blk, method)
+            _expand_factors(pack, tuple(_f32c(t.detach()) for t in blk.peft_tensors()), st)
+            pack.expanded_ahead = True
+
+
+def join_side_stream(device) -> None:
+    side = _side_streams.get(device.index or 0)
+    if side is not None:
+        torch.cuda.current_stream(device).wait_stream(side)
+
+
 class _BlockFn(torch.autograd.Function):
     """y = ResidualAttentionBlock(x); differentiable w.r.t. x and the PEFT tensors only."""
 
@@ -170,17 +215,13 @@ class _BlockFn(torch.autograd.Function):
         x = _f32c(x)
         peft_c = tuple(_f32c(t.detach()) for t in peft)
         delta_bias = lna = b_down = b_up = None
-        if method == "kadaptation":
-            u1, v1, u2, v2, s, t, b = peft_c
-            L.check(lib.pevit_kad_expand(_ptr(u1), _ptr(v1), _ptr(u2), _ptr(v2), _ptr(s), _ptr(t), D, pack.alpha,
-                                         _ptr(pack.w_qkv_ext), _ptr(pack.w_qkv_ext_t), _ptr(pack.qmat),
-                                         _ptr(pack.qmat_t), _ptr(pack.delta_w), st), "pevit_kad_expand")
-            delta_bias = b
-        elif method == "lora":
-            aq, bq, av, bv = peft_c
-            L.check(lib.pevit_lora_expand(_ptr(aq), _ptr(av), _ptr(bq), _ptr(bv), D, pack.r, pack.alpha,
-                                          _ptr(pack.w_qkv_ext), _ptr(pack.w_qkv_ext_t), _ptr(pack.qmat),
-                                          _ptr(pack.qmat_t), _ptr(pack.delta_w), st), "pevit_lora_expand")
+        if method in ("kadaptation", "lora"):
+            if pack.expanded_ahead:      # expand_ahead() already wrote this pack's factor operands on the side stream
+                pack.expanded_ahead = False
+            else:
+                _expand_factors(pack, peft_c, st)
+            if method == "kadaptation":
+                delta_bias = peft_c[6]
         elif method in ("adapter", "compacter"):
             g, bta, w_down, b_down, w_up, b_up = peft_c   # w_down [64][D], w_up [D][64] dense
             lna = (g, bta)
