@@ -129,6 +129,20 @@ int pevit_kad_factor_grads(const float* dP, const float* dQ, const float* u1, co
 int pevit_kad_factor_grads_acc(const float* dP, const float* dQ, const float* u1, const float* v1, const float* u2,
                                const float* v2, const float* s, const float* t, int32_t d, float* du1, float* dv1,
                                float* du2, float* dv2, float* ds, float* dt, void* stream);
+/* ------------------------------------------------------------------ step tail
+ * Linear head + CrossEntropyLoss (kadaptation_clip.py:176-185, :350): logits = feat W^T + b, *loss += mean over the
+ * n samples of (logsumexp - logit[label]) (caller zeroes loss), dlogits = (softmax - onehot) / n.  fp32 throughout. */
+int pevit_head_ce_fwd(const float* feat, const float* w, const float* b, const int64_t* labels, int32_t n, int32_t e,
+                      int32_t c, float* logits, float* dlogits, float* loss, void* stream);
+/* gscale: device scalar multiplying every gradient (autograd's grad_output; NULL = 1).  dfeat_bf16 [n][e] (nullable):
+ * gradient w.r.t. the features, bf16 = A operand of the projection dgrad GEMM; dw [c][e], db [c] (nullable):
+ * accumulate != 0 adds onto them. */
+int pevit_head_ce_bwd(const float* dlogits, const float* feat, const float* w, const float* gscale, int32_t n, int32_t e,
+                      int32_t c, void* dfeat_bf16, float* dw, float* db, int32_t accumulate, void* stream);
+/* torch.optim.SGD(momentum, weight_decay; dampening 0, no Nesterov; optim/build.py:18-127) over flat buffers:
+ * g' = grad_scale * g + wd * p; m = momentum * m + g'; p -= lr * m.  grad_scale folds 1/world_size in. */
+int pevit_sgd_momentum(float* p, const float* g, float* m, size_t n, float lr, float momentum, float weight_decay,
+                       float grad_scale, void* stream);
 /* weight packing: fp32 [rows][cols] -> bf16 (same layout / transposed with leading dim ldd) */
 int pevit_cast_bf16(const float* src, void* dst, size_t n, void* stream);
 int pevit_transpose_bf16(const float* src, int32_t rows, int32_t cols, void* dst, int32_t ldd, void* stream);

@@ -290,6 +290,13 @@ class VisionTransformer(nn.Module):
         return not (torch.is_grad_enabled() and any(p.requires_grad for p in ps))
 
     def forward(self, x: torch.Tensor) -> torch.Tensor:
+        x = self.ln_post(self.forward_cls_tokens(x))             # class token of every image
+        if self.proj is not None:
+            x = x @ self.proj
+        return x
+
+    def forward_cls_tokens(self, x: torch.Tensor) -> torch.Tensor:
+        """Class-token rows (N, D) of the last block, before ln_post (what the fused step tail consumes)."""
         blocks = self.transformer.resblocks
         fused = x.is_cuda and len(blocks) > 0 and all(getattr(b, "fused", False) for b in blocks)
         if fused:
@@ -310,10 +317,7 @@ class VisionTransformer(nn.Module):
             x = blocks[-1](x, out_tokens=1)
         else:
             x = self.transformer(x)
-        x = self.ln_post(x[0])                                   # class token of every image
-        if self.proj is not None:
-            x = x @ self.proj
-        return x
+        return x[0]
 
 
 class CLIP(nn.Module):

@@ -246,6 +246,23 @@ int pevit_transpose_bf16(const float* src, int32_t rows, int32_t cols, void* dst
   return transpose_f32_to_bf16(as_stream(stream), src, rows, cols, static_cast<bf16*>(dst), ldd);
 }
 
+int pevit_head_ce_fwd(const float* feat, const float* w, const float* b, const int64_t* labels, int32_t n, int32_t e,
+                      int32_t c, float* logits, float* dlogits, float* loss, void* stream) {
+  PEVIT_REQUIRE(feat && w && labels && logits && dlogits && loss, "pevit_head_ce_fwd: null pointer");
+  return head_ce_fwd(as_stream(stream), feat, w, b, reinterpret_cast<const long long*>(labels), n, e, c, logits, dlogits, loss);
+}
+
+int pevit_head_ce_bwd(const float* dlogits, const float* feat, const float* w, const float* gscale, int32_t n, int32_t e,
+                      int32_t c, void* dfeat_bf16, float* dw, float* db, int32_t accumulate, void* stream) {
+  PEVIT_REQUIRE(dlogits && feat && w, "pevit_head_ce_bwd: null pointer");
+  return head_ce_bwd(as_stream(stream), dlogits, feat, w, gscale, n, e, c, static_cast<bf16*>(dfeat_bf16), dw, db, accumulate);
+}
+
+int pevit_sgd_momentum(float* p, const float* g, float* m, size_t n, float lr, float momentum, float weight_decay,
+                       float grad_scale, void* stream) {
+  return sgd_momentum(as_stream(stream), p, g, m, n, lr, momentum, weight_decay, grad_scale);
+}
+
 int pevit_prof_enable(int32_t on) { return prof_enable(on); }
 int pevit_prof_reset(void) { return prof_reset(); }
 int pevit_prof_num_classes(void) { return PC_COUNT; }

@@ -120,6 +120,18 @@ size_t patch_embed_workspace_bytes(int NB, int R, int p, int D);
 int patch_embed(cudaStream_t s, const float* img, const bf16* w_patch, const float* cls, const float* pos,
                 const float* ln_g, const float* ln_b, float* x, void* workspace, int NB, int R, int p, int D);
 
+// ------------------------------------------------------------------ tail.cu
+// Linear head + cross-entropy (mean over N): logits [N][C], dlogits = (softmax - 1hot)/N, *loss += mean loss
+// (caller zeroes loss).  labels are int64.
+int head_ce_fwd(cudaStream_t s, const float* feat, const float* W, const float* b, const long long* labels, int N, int E,
+                int C, float* logits, float* dlogits, float* loss);
+// gscale: device scalar multiplying every gradient (autograd's grad_output; null = 1).  dfeat bf16 [N][E] (nullable),
+// dW [C][E] / db [C] (nullable; accumulate: += instead of =).
+int head_ce_bwd(cudaStream_t s, const float* dlogits, const float* feat, const float* W, const float* gscale, int N, int E,
+                int C, bf16* dfeat, float* dW, float* db, int accumulate);
+// torch.optim.SGD(momentum, weight_decay) over flat buffers; gscale folds 1/world_size of the gradient all-reduce in.
+int sgd_momentum(cudaStream_t s, float* p, const float* g, float* m, size_t n, float lr, float mu, float wd, float gscale);
+
 // ------------------------------------------------------------------ elementwise.cu
 int cast_f32_to_bf16(cudaStream_t s, const float* src, bf16* dst, size_t n);
 // dst[c][r] = src[r][c]  (fp32 -> bf16 transpose; weight prep for dgrad GEMMs)

@@ -27,6 +27,23 @@ def trainable_by_name(name: str, method: str) -> bool:
     return "adapter" in name or "phm_rule" in name or "attn.b" in name
 
 
+class FlatParams:
+    """Re-points every parameter's storage into one flat fp32 buffer (same values), so the optimizer update is a
+    single kernel over (flat_p, flat_g, flat_m)."""
+
+    def __init__(self, params, device=None):
+        self.params = list(params)
+        device = device if device is not None else self.params[0].device
+        self.flat = torch.zeros(sum(p.numel() for p in self.params), dtype=torch.float32, device=device)
+        off = 0
+        with torch.no_grad():
+            for p in self.params:
+                view = self.flat[off:off + p.numel()].view_as(p)
+                view.copy_(p.data)
+                p.data = view
+                off += p.numel()
+
+
 class FlatGrads:
     """One flat fp32 buffer holding every trainable gradient; each ``p.grad`` is a view into it, so the
     data-parallel exchange is ONE collective per step regardless of how many PEFT tensors there are."""
@@ -49,13 +66,19 @@ class FlatGrads:
             dist.all_reduce(self.flat, group=group)
             self.flat.div_(world)
 
+    def all_reduce_sum(self, group=None) -> None:
+        """Sum only: the 1/world factor is folded into the fused optimizer kernel."""
+        if dist.get_world_size(group) > 1:
+            dist.all_reduce(self.flat, group=group)
+
 
 class FineTuner(nn.Module):
     """Backbone (frozen CLIP visual tower + PEFT tensors) and a linear head, stepped with SGD(momentum)."""
 
     def __init__(self, method: str, shape: synth.ClipShape, num_classes: int = 10, device="cuda", lr: float = 1e-3,
                  momentum: float = 0.9, weight_decay: float = 0.0, seed: int = 0, randomize: bool = True,
-                 process_group: Optional[dist.ProcessGroup] = None, distributed: bool = False):
+                 process_group: Optional[dist.ProcessGroup] = None, distributed: bool = False,
+                 fused_tail: Optional[bool] = None):
         super().__init__()
         self.method = method
         sd = synth.clip_state_dict(shape, seed=seed)
@@ -82,6 +105,13 @@ class FineTuner(nn.Module):
         self.grads = FlatGrads(self.used, device)
         self.flat_grad = self.grads.flat
         self.opt = torch.optim.SGD(self.used, lr=lr, momentum=momentum, weight_decay=weight_decay)
+        # step tail on this library's kernels (ln_post + projection GEMM + head/CE kernel; one SGD kernel over flat
+        # parameter / gradient / momentum buffers) instead of ~30 small PyTorch launches; CUDA only
+        self.fused_tail = (torch.device(device).type == "cuda") if fused_tail is None else fused_tail
+        self.hyper = (lr, momentum, weight_decay)
+        if self.fused_tail:
+            self.flat_params = FlatParams(self.used, device)
+            self.flat_momentum = torch.zeros_like(self.flat_params.flat)
         # every trainable .grad is a persistent view into the flat buffer: let the block kernels add into it directly
         ops.set_direct_grad_accumulation(True)
 
@@ -91,6 +121,16 @@ class FineTuner(nn.Module):
     def step(self, images: torch.Tensor, labels: torch.Tensor) -> torch.Tensor:
         """One fine-tune step on this rank's local batch; returns the (device) loss."""
         self.grads.zero_()
+        if self.fused_tail:
+            visual = self.backbone.visual
+            x_cls = visual.forward_cls_tokens(images.type(self.backbone.dtype))
+            loss, _ = ops.tail_loss(visual, self.head, x_cls, labels)
+            loss.backward()
+            if self.distributed:
+                self.grads.all_reduce_sum(self.group)
+            lr, mu, wd = self.hyper
+            ops.sgd_momentum_(self.flat_params.flat, self.flat_grad, self.flat_momentum, lr, mu, wd, 1.0 / self.world)
+            return loss.detach()
         loss = F.cross_entropy(self.forward(images), labels)
         loss.backward()
         if self.distributed:

@@ -378,3 +378,118 @@ def stem_forward(visual, images: torch.Tensor) -> torch.Tensor:
     L.check(lib.pevit_patch_embed(_ptr(images), _ptr(pack.w), *(_ptr(t) for t in small), _ptr(x), _ptr(ws), NB, R, p, D,
                                   _stream()), "pevit_patch_embed")
     return x
+
+
+# ----------------------------------------------------------------------------- step tail
+class TailPack:
+    """Frozen operands of the tail: ln_post affine (fp32) and the visual projection as bf16 GEMM operands."""
+
+    def __init__(self, visual):
+        proj = visual.proj.detach()                      # (D, E)
+        self.D, self.E = proj.shape
+        dev = proj.device
+        self.proj = torch.empty(self.D, self.E, dtype=torch.bfloat16, device=dev)     # B of the dgrad  [D][E]
+        self.proj_t = torch.empty(self.E, self.D, dtype=torch.bfloat16, device=dev)   # B of the forward [E][D]
+        BlockPack.cast(proj, self.proj)
+        BlockPack.transpose(proj, self.proj_t, self.D)
+        self.ln_w, self.ln_b = _f32c(visual.ln_post.weight.detach()), _f32c(visual.ln_post.bias.detach())
+        self.key = self.signature(visual)
+
+    @staticmethod
+    def signature(visual) -> tuple:
+        ts = (visual.proj, visual.ln_post.weight, visual.ln_post.bias)
+        return tuple((t.data_ptr(), t._version, str(t.device)) for t in ts)
+
+
+def _gemm_f32(a: torch.Tensor, b: torch.Tensor, out: torch.Tensor) -> None:
+    """out[M][N] (fp32) = a[M][K] (bf16) @ b[N][K]^T (bf16) through pevit_gemm_tn."""
+    args = L.GemmArgs()
+    args.a, args.lda, args.b, args.ldb = a.data_ptr(), a.stride(0), b.data_ptr(), b.stride(0)
+    args.m, args.n, args.k, args.epilogue = a.shape[0], b.shape[0], a.shape[1], L.EPI_F32
+    args.out_f32, args.ld_out = out.data_ptr(), out.stride(0)
+    L.check(L.lib().pevit_gemm_tn(C.byref(args), _stream()), "pevit_gemm_tn")
+
+
+class _TailFn(torch.autograd.Function):
+    """loss, logits = CE(Linear(ln_post(x_cls) @ proj)); differentiable w.r.t. x_cls and the head."""
+
+    @staticmethod
+    def forward(ctx, x_cls, labels, head_w, head_b, pack: TailPack):
+        lib, st = L.lib(), _stream()
+        x = _f32c(x_cls).view(-1, pack.D)
+        N, D, E, Cn = x.shape[0], pack.D, pack.E, head_w.shape[0]
+        dev = x.device
+        f32 = dict(dtype=torch.float32, device=dev)
+        xn = torch.empty(N, D, dtype=torch.bfloat16, device=dev)
+        mean, rstd = torch.empty(N, **f32), torch.empty(N, **f32)
+        L.check(lib.pevit_layernorm_fwd(_ptr(x), _ptr(pack.ln_w), _ptr(pack.ln_b), _ptr(xn), None, _ptr(mean), _ptr(rstd),
+                                        N, D, st), "pevit_layernorm_fwd")
+        feat = torch.empty(N, E, **f32)
+        _gemm_f32(xn, pack.proj_t, feat)
+        w, b = _f32c(head_w.detach()), (None if head_b is None else _f32c(head_b.detach()))
+        logits, dlogits = torch.empty(N, Cn, **f32), torch.empty(N, Cn, **f32)
+        loss = torch.zeros((), **f32)
+        labels = labels.to(torch.int64).contiguous()
+        L.check(lib.pevit_head_ce_fwd(_ptr(feat), _ptr(w), _ptr(b), _ptr(labels), N, E, Cn, _ptr(logits), _ptr(dlogits),
+                                      _ptr(loss), st), "pevit_head_ce_fwd")
+        ctx.pack, ctx.shape = pack, tuple(x_cls.shape)
+        ctx.live = (head_w, head_b) if _direct_grads[0] else None
+        ctx.save_for_backward(x, mean, rstd, feat, dlogits, w)
+        ctx.mark_non_differentiable(logits)
+        return loss, logits
+
+    @staticmethod
+    def backward(ctx, g_loss, _g_logits):
+        lib, st = L.lib(), _stream()
+        pack = ctx.pack
+        x, mean, rstd, feat, dlogits, w = ctx.saved_tensors
+        N, D, E, Cn = x.shape[0], pack.D, pack.E, w.shape[0]
+        dev = x.device
+        g = _f32c(g_loss)
+        live = ctx.live
+        direct = live is not None and all(t is None or (t.requires_grad and t.grad is not None and t.grad.is_contiguous()
+                                                        and t.grad.dtype == torch.float32) for t in live)
+        need_w = ctx.needs_input_grad[2]
+        if direct:
+            dW, db = live[0].grad, (None if live[1] is None else live[1].grad)
+        else:
+            dW = torch.empty(Cn, E, dtype=torch.float32, device=dev) if need_w else None
+            db = torch.empty(Cn, dtype=torch.float32, device=dev) if ctx.needs_input_grad[3] else None
+        dfeat = torch.empty(N, E, dtype=torch.bfloat16, device=dev) if ctx.needs_input_grad[0] else None
+        L.check(lib.pevit_head_ce_bwd(_ptr(dlogits), _ptr(feat), _ptr(w), _ptr(g), N, E, Cn, _ptr(dfeat), _ptr(dW), _ptr(db),
+                                      int(direct), st), "pevit_head_ce_bwd")
+        dx = None
+        if dfeat is not None:
+            dln = torch.empty(N, D, dtype=torch.float32, device=dev)
+            _gemm_f32(dfeat, pack.proj, dln)                       # d ln_post output = dfeat @ proj^T
+            dx = torch.empty(N, D, dtype=torch.float32, device=dev)
+            L.check(lib.pevit_layernorm_bwd(_ptr(dln), _ptr(x), _ptr(pack.ln_w), _ptr(mean), _ptr(rstd), None, _ptr(dx), None,
+                                            None, None, N, D, st), "pevit_layernorm_bwd")
+            dx = dx.view(ctx.shape)
+        if direct:
+            return dx, None, None, None, None
+        return dx, None, dW, db, None
+
+
+def tail_loss(visual, head, x_cls: torch.Tensor, labels: torch.Tensor):
+    """Cross-entropy of ``head(ln_post(x_cls) @ visual.proj)`` (model.py:1046-1049, kadaptation_clip.py:176-185, :350)
+    in three launches forward / four backward.  ``x_cls``: class-token rows (N, D) or (1, N, D) of the last block.
+    Requires a frozen ln_post / proj (the PEViT setting).  Returns (loss, logits)."""
+    if not x_cls.is_cuda:
+        raise RuntimeError("pevit_b200 tail runs on CUDA (sm_100a) only; there is no CPU fallback")
+    if visual.proj is None or visual.proj.requires_grad or visual.ln_post.weight.requires_grad:
+        raise RuntimeError("tail_loss needs a frozen ln_post and visual.proj")
+    pack = getattr(visual, "_pevit_tail", None)
+    if pack is None or pack.key != TailPack.signature(visual):
+        pack = TailPack(visual)
+        object.__setattr__(visual, "_pevit_tail", pack)
+    return _TailFn.apply(x_cls, labels, head.weight, head.bias, pack)
+
+
+def sgd_momentum_(flat_p: torch.Tensor, flat_g: torch.Tensor, flat_m: torch.Tensor, lr: float, momentum: float,
+                  weight_decay: float, grad_scale: float = 1.0) -> None:
+    """One launch of torch.optim.SGD(momentum, weight_decay) arithmetic over flat fp32 buffers (optim/build.py:18-127)."""
+    assert flat_p.is_contiguous() and flat_g.is_contiguous() and flat_m.is_contiguous()
+    assert flat_p.dtype == flat_g.dtype == flat_m.dtype == torch.float32 and flat_p.numel() == flat_g.numel() == flat_m.numel()
+    L.check(L.lib().pevit_sgd_momentum(_ptr(flat_p), _ptr(flat_g), _ptr(flat_m), flat_p.numel(), lr, momentum, weight_decay,
+                                       grad_scale, _stream()), "pevit_sgd_momentum")

@@ -233,3 +233,24 @@ def test_direct_grad_accumulation_matches_autograd():
         ops.set_direct_grad_accumulation(False)
     assert flats[0].abs().max() > 0
     assert rel_inf(flats[0], flats[1]) < 1e-5
+
+
+def test_fused_tail_step_matches_pytorch_tail():
+    """FineTuner with the fused tail (ln_post/proj/head/CE kernels + one SGD kernel over flat buffers) against the same
+    step with the PyTorch tail and torch.optim.SGD: same loss, same parameters after two steps."""
+    from pevit_b200 import engine, ops
+    shape = synth.VIT_TINY
+    img = synth.images(6, shape.image_resolution, seed=21).cuda()
+    lab = synth.labels(6, 10, seed=22).cuda()
+    out = {}
+    try:
+        for fused in (True, False):
+            tuner = engine.FineTuner("kadaptation", shape, device="cuda", seed=4, lr=0.05, weight_decay=1e-3,
+                                     fused_tail=fused)
+            losses = [tuner.step(img, lab).item() for _ in range(2)]
+            out[fused] = (losses, torch.cat([p.detach().flatten().clone() for p in tuner.used]))
+    finally:
+        ops.set_direct_grad_accumulation(False)
+    for a, b in zip(out[True][0], out[False][0]):
+        assert abs(a - b) < 5e-3 * max(1.0, abs(b))
+    assert rel_inf(out[True][1], out[False][1]) < 5e-3

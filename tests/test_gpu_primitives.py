@@ -380,3 +380,55 @@ def test_patch_embed_stem(lib, NB, R, p, D):
     torch.cuda.synchronize()
     assert got.shape == ref.shape
     assert rel_inf(got, ref) < 1e-2
+
+
+@pytest.mark.parametrize("N,D,E,Cn", [(256, 768, 512, 10), (7, 128, 64, 3), (64, 1024, 768, 100)])
+def test_tail_loss_matches_torch(lib, N, D, E, Cn):
+    """ln_post -> projection -> Linear head -> CrossEntropy on this library's kernels against the PyTorch fp32 ops."""
+    import torch.nn.functional as F
+    from pevit_b200 import ops
+
+    class V(torch.nn.Module):
+        def __init__(self):
+            super().__init__()
+            self.ln_post = torch.nn.LayerNorm(D)
+            self.proj = torch.nn.Parameter(torch.randn(D, E) * D ** -0.5, requires_grad=False)
+    g = torch.Generator().manual_seed(N + D)
+    visual = V()
+    with torch.no_grad():
+        visual.ln_post.weight.copy_(1 + 0.1 * torch.randn(D, generator=g))
+        visual.ln_post.bias.copy_(0.1 * torch.randn(D, generator=g))
+    visual = visual.cuda().requires_grad_(False)
+    head = torch.nn.Linear(E, Cn).cuda()
+    x = torch.randn(1, N, D, generator=g).cuda().requires_grad_(True)
+    labels = torch.randint(0, Cn, (N,), generator=g).cuda()
+    loss, logits = ops.tail_loss(visual, head, x, labels)
+    (loss * 3.0).backward()
+    got = (loss.detach().clone(), logits.clone(), x.grad.clone(), head.weight.grad.clone(), head.bias.grad.clone())
+    x.grad = None
+    head.zero_grad(set_to_none=True)
+    ref_logits = head(visual.ln_post(x[0]) @ visual.proj)
+    ref_loss = F.cross_entropy(ref_logits, labels)
+    (ref_loss * 3.0).backward()
+    assert abs(got[0].item() - ref_loss.item()) < 3e-3 * max(1.0, abs(ref_loss.item()))
+    assert rel_inf(got[1], ref_logits.detach()) < 1e-2
+    assert rel_inf(got[2], x.grad) < 2e-2
+    assert rel_inf(got[3], head.weight.grad) < 1e-2
+    assert rel_inf(got[4], head.bias.grad) < 1e-2
+
+
+def test_sgd_momentum_matches_torch(lib):
+    from pevit_b200 import ops
+    n = 55306
+    g = torch.Generator().manual_seed(5)
+    p0 = torch.randn(n, generator=g).cuda()
+    p_ref = p0.clone().requires_grad_(True)
+    opt = torch.optim.SGD([p_ref], lr=0.05, momentum=0.9, weight_decay=1e-2)
+    p, m = p0.clone(), torch.zeros(n, device="cuda")
+    for step in range(4):
+        grad = torch.randn(n, generator=g).cuda()
+        p_ref.grad = grad.clone() * 0.5          # grad_scale 0.5 folded into the kernel (1 / world_size)
+        opt.step()
+        ops.sgd_momentum_(p, grad, m, 0.05, 0.9, 1e-2, 0.5)
+        torch.cuda.synchronize()
+        assert rel_inf(p, p_ref.detach()) < 1e-6, step
