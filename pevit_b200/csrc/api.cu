@@ -325,13 +325,24 @@ int pevit_block_fwd(const pevit_block_desc* desc, const pevit_block_weights* w, 
     // q' = q + scr(alpha T_q Q_q^T + b), v' = v + scr(alpha T_v Q_v^T + b): F4 makes scr() the identity on the
     // flat head-major buffer viewed as [M][D], so the delta is a rank-2r GEMM accumulated in place (model.py:796-799)
     const bf16* dw = static_cast<const bf16*>(w->delta_w);
-    for (int which = 0; which < 2; ++which) {
-      bf16* dst = sv.qkv_hm + (which == 0 ? 0 : 2) * plane;
+    if (M % 256 == 0) {
+      // both deltas in ONE launch: batch 0 -> q plane, batch 1 -> v plane (two planes further down the same tensor);
+      // T is read once per tile pair, delta_w[which] are consecutive row blocks of one [2D][2r] matrix
       GemmEpilogue ep;
       ep.bias = d.method == PEVIT_KADAPTATION ? w->delta_bias : nullptr;
-      ep.out_bf16 = dst; ep.resid_bf16 = dst; ep.ld_out = D;
+      ep.out_bf16 = sv.qkv_hm; ep.resid_bf16 = sv.qkv_hm; ep.ld_out = D;
+      ep.batch = 2; ep.b_batch_rows = D; ep.c_batch_rows = 2 * M;
       prof_set_tag(PC_GEMM_DELTA);
-      TRY(gemm_tn(s, sv.T, r2, dw + static_cast<size_t>(which) * D * r2, r2, M, D, r2, EPI_BF16, ep));
+      TRY(gemm_tn(s, sv.T, r2, dw, r2, M, D, r2, EPI_BF16, ep));
+    } else {
+      for (int which = 0; which < 2; ++which) {
+        bf16* dst = sv.qkv_hm + (which == 0 ? 0 : 2) * plane;
+        GemmEpilogue ep;
+        ep.bias = d.method == PEVIT_KADAPTATION ? w->delta_bias : nullptr;
+        ep.out_bf16 = dst; ep.resid_bf16 = dst; ep.ld_out = D;
+        prof_set_tag(PC_GEMM_DELTA);
+        TRY(gemm_tn(s, sv.T, r2, dw + static_cast<size_t>(which) * D * r2, r2, M, D, r2, EPI_BF16, ep));
+      }
     }
   }
   // attention core
@@ -476,13 +487,15 @@ int pevit_block_bwd(const pevit_block_desc* desc, const pevit_block_weights* w, 
   }
   if (has_lowrank(d)) {
     const bf16* qmat_t = static_cast<const bf16*>(w->qmat_t);
-    for (int which = 0; which < 2; ++which) {
-      const bf16* dd = wk.ddelta + which * plane;  // d(delta) viewed as [M][D] in LND rows (F4)
-      // dT = alpha * dDelta * Q  -> bf16 straight into the extra K columns of the QKV dgrad operand
+    {
+      // dT = alpha * dDelta * Q  -> bf16 straight into the extra K columns of the QKV dgrad operand; q and v in one
+      // launch: batch b reads plane b of d(delta) ([M][D] in LND rows, F4) and rows [b r, +r) of qmat_t, and writes
+      // columns 3D + b r of dqkv
       GemmEpilogue ep;
-      ep.out_bf16 = wk.dqkv + 3 * D + which * r; ep.ld_out = W3;
+      ep.out_bf16 = wk.dqkv + 3 * D; ep.ld_out = W3;
+      ep.batch = 2; ep.a_batch_rows = M; ep.b_batch_rows = r; ep.c_batch_elems = r;
       prof_set_tag(PC_GEMM_DT);
-      TRY(gemm_tn(s, dd, D, qmat_t + static_cast<size_t>(which) * r * D, D, M, r, D, EPI_BF16, ep));
+      TRY(gemm_tn(s, wk.ddelta, D, qmat_t, D, M, r, D, EPI_BF16, ep));
     }
     // the three weight-gradient shaped products of the layer in one launch:
     //   dQ_q = alpha dDelta_q^T T_q,  dQ_v = alpha dDelta_v^T T_v,  dP = X^T dT  ([D][2r], q | v)

@@ -348,11 +348,18 @@ gemm_tn_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
   const int lane = threadIdx.x & 31;
   const int tiles_n = (N + BN - 1) / BN;
   const int tiles_m = (M + TILE_M - 1) / TILE_M;
-  const int num_tiles = tiles_m * tiles_n;
+  const int tiles_per_batch = tiles_m * tiles_n;
+  const int num_tiles = tiles_per_batch * ep.batch;
   const int num_kb = (K + BK - 1) / BK;
   const uint32_t cta_rank = CTA2 ? cluster_ctarank() : 0u;       // 0 = leader (issues the MMAs)
   const int first_tile = CTA2 ? static_cast<int>(blockIdx.x >> 1) : static_cast<int>(blockIdx.x);
   const int tile_step = CTA2 ? static_cast<int>(gridDim.x >> 1) : static_cast<int>(gridDim.x);
+  // Batched launch (ep.batch > 1): several products that share shapes run as one grid; tile index = batch-major.
+  // Operands / outputs of batch b sit at fixed ROW offsets of the same 2-D tensors (plus a pointer offset for the
+  // direct-store epilogue).
+  auto tile_batch = [&](int tile) { return tile / tiles_per_batch; };
+  auto tile_m0 = [&](int tile) { return ((tile % tiles_per_batch) / tiles_n) * TILE_M + static_cast<int>(cta_rank) * BM; };
+  auto tile_n0 = [&](int tile) { return ((tile % tiles_per_batch) % tiles_n) * BN; };
   // auxiliary epilogue operand that is TMA-loaded into the boxes (staged epilogue only)
   const bool has_aux = TS && (kF32 ? ep.resid != nullptr
                                    : (epi_base(EPI) == EPI_BF16 ? ep.resid_bf16 != nullptr : epi_base(EPI) == EPI_DACT));
@@ -396,14 +403,15 @@ gemm_tn_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
       int stage = 0;
       uint32_t phase = 0;
       for (int tile = first_tile; tile < num_tiles; tile += tile_step) {
-        const int m0 = (tile / tiles_n) * TILE_M + static_cast<int>(cta_rank) * BM;
-        const int n0 = (tile % tiles_n) * BN + static_cast<int>(cta_rank) * Cfg::B_ROWS * (CTA2 ? 1 : 0);
+        const int bidx = tile_batch(tile);
+        const int m0 = tile_m0(tile) + bidx * ep.a_batch_rows;
+        const int n0 = tile_n0(tile) + static_cast<int>(cta_rank) * Cfg::B_ROWS * (CTA2 ? 1 : 0) + bidx * ep.b_batch_rows;
         if (has_aux) {
           // pull this tile's auxiliary boxes into L2 a whole mainloop ahead of the epilogue that consumes them
-          const int nt = (tile % tiles_n) * BN;
+          const int nt = tile_n0(tile);
 #pragma unroll 1
           for (int j = 0; j < NBOXES; ++j)
-            if (nt + j * BOXCOLS < N) tma_prefetch_l2_2d(&tmap_aux, nt + j * BOXCOLS, m0);
+            if (nt + j * BOXCOLS < N) tma_prefetch_l2_2d(&tmap_aux, nt + j * BOXCOLS, tile_m0(tile) + bidx * ep.c_batch_rows);
         }
         for (int kb = 0; kb < num_kb; ++kb) {
           // A (activations, tens of MB, read once per N tile) mostly misses L2; the ring buffers ~1 us of mainloop,
@@ -478,9 +486,11 @@ gemm_tn_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
       for (int tile = first_tile; tile < num_tiles; tile += tile_step, ++it) {
         const int acc = it & 1;
         const uint32_t acc_phase = (it >> 1) & 1;
-        const int m_base = (tile / tiles_n) * TILE_M + static_cast<int>(cta_rank) * BM;
+        const int m_base = tile_m0(tile);
         const int m = m_base + quad * 32 + lane;
-        const int n0 = (tile % tiles_n) * BN;
+        const int n0 = tile_n0(tile);
+        GemmEpilogue epb = ep;  // batch b writes at a fixed element offset of the same output
+        if (ep.batch > 1 && epb.out_bf16 != nullptr) epb.out_bf16 += static_cast<size_t>(tile_batch(tile)) * ep.c_batch_elems;
         mbar_wait(&tfull_bar[acc], acc_phase);
         tc_fence_after();
         const uint32_t t_row = tmem_base + (static_cast<uint32_t>(quad * 32) << 16) + acc * BN;
@@ -489,7 +499,7 @@ gemm_tn_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
           uint32_t v[32];
           tmem_ld_32x32(t_row + c, v);
           tmem_ld_wait();
-          if (m < M && n0 + c < N) epilogue_chunk<EPI>(ep, m, n0 + c, v, N);
+          if (m < M && n0 + c < N) epilogue_chunk<EPI>(epb, m, n0 + c, v, N);
         }
         tc_fence_before();
         __syncwarp();
@@ -518,7 +528,7 @@ gemm_tn_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
         for (;;) {
           const int tile_ = first_tile + la_it * tile_step;
           if (tile_ >= num_tiles) return false;
-          if (la_j < NBOXES && (tile_ % tiles_n) * BN + la_j * BOXCOLS < N) return true;
+          if (la_j < NBOXES && tile_n0(tile_) + la_j * BOXCOLS < N) return true;
           ++la_it;
           la_j = first_j(la_it);
         }
@@ -526,8 +536,8 @@ gemm_tn_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
       auto la_issue = [&](int slot) {  // elected only
         if (!la_seek()) return;
         const int tile_ = first_tile + la_it * tile_step;
-        const int m0_ = (tile_ / tiles_n) * TILE_M + static_cast<int>(cta_rank) * BM;
-        const int c0_ = (tile_ % tiles_n) * BN + la_j * BOXCOLS;
+        const int m0_ = tile_m0(tile_) + tile_batch(tile_) * ep.c_batch_rows;
+        const int c0_ = tile_n0(tile_) + la_j * BOXCOLS;
         mbar_expect_tx(&my_aux[slot], BOX_BYTES);
         tma_load_2d(my_boxes + slot * BOX_BYTES, &tmap_aux, &my_aux[slot], c0_, m0_);
         la_j += 2;
@@ -539,8 +549,8 @@ gemm_tn_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
       for (int tile = first_tile; tile < num_tiles; tile += tile_step, ++it) {
         const int acc = it & 1;
         const uint32_t acc_phase = (it >> 1) & 1;
-        const int m0 = (tile / tiles_n) * TILE_M + static_cast<int>(cta_rank) * BM;
-        const int n0 = (tile % tiles_n) * BN;
+        const int m0 = tile_m0(tile) + tile_batch(tile) * ep.c_batch_rows;  // output / aux rows (QKV: batch == 1)
+        const int n0 = tile_n0(tile);
         mbar_wait(&tfull_bar[acc], acc_phase);
         tc_fence_after();
         const uint32_t t_row = tmem_base + (static_cast<uint32_t>(quad * 32) << 16) + acc * BN;
@@ -643,7 +653,7 @@ int launch_impl(cudaStream_t stream, const CUtensorMap& ta, const CUtensorMap& t
     configured[dev & 63] = true;
   }
   const int tile_m = CTA2 ? 2 * BM : BM;
-  const int tiles = ((M + tile_m - 1) / tile_m) * ((N + BN - 1) / BN);
+  const int tiles = ((M + tile_m - 1) / tile_m) * ((N + BN - 1) / BN) * ep.batch;
   ProfScope prof(stream, PC_GEMM_OTHER);
   int grid;
   if constexpr (CTA2) {
@@ -748,9 +758,12 @@ int gemm_tn(cudaStream_t stream, const bf16* A, int lda, const bf16* B, int ldb,
   static const bool pair_disabled = getenv("PEVIT_GEMM_NO_PAIR") != nullptr;
   const int bn = pick_tile(M, N, force_bn, !pair_disabled, &pair);
   g_use_pair = pair;
+  PEVIT_REQUIRE(ep.batch >= 1 && (ep.batch == 1 || epi == EPI_BF16),
+                "gemm_tn: batched launches are supported for the bf16 epilogue only (batch=%d, epilogue %d)", ep.batch, epi);
+  const int nbm1 = ep.batch - 1;
   Tmaps t;
-  if (make_tmap_bf16_2d(&t.a, A, M, K, lda, BM, BK) != 0) return -1;
-  if (make_tmap_bf16_2d(&t.b, B, N, K, ldb, pair ? bn / 2 : bn, BK) != 0) return -1;
+  if (make_tmap_bf16_2d(&t.a, A, static_cast<uint64_t>(nbm1) * ep.a_batch_rows + M, K, lda, BM, BK) != 0) return -1;
+  if (make_tmap_bf16_2d(&t.b, B, static_cast<uint64_t>(nbm1) * ep.b_batch_rows + N, K, ldb, pair ? bn / 2 : bn, BK) != 0) return -1;
   t.c = t.a;
   t.c2 = t.a;
   t.aux = t.a;
@@ -775,11 +788,20 @@ int gemm_tn(cudaStream_t stream, const bf16* A, int lda, const bf16* B, int ldb,
     const bool act_plain = !((epi == EPI_ACT || epi == EPI_DACT) && ep.act != ACT_QUICKGELU);  // bottleneck acts: direct
     ts = act_plain && N % 64 == 0 && out != nullptr && aligned16(out) && aligned16(aux) && ep.resid2 == nullptr &&
          (static_cast<size_t>(ep.ld_out) * elt) % 16 == 0 && aligned16(ep.out2_bf16) && force_bn >= 0;
+    if (ep.batch > 1) {
+      // staged: batches are ROW blocks of one output tensor, so a tile must not straddle two of them;
+      // direct: batches are element offsets of the same rows
+      const int tile_m = pair ? 2 * BM : BM;
+      if (ts) PEVIT_REQUIRE(ep.c_batch_elems == 0 && ep.c_batch_rows >= M && M % tile_m == 0,
+                            "gemm_tn: batched staged epilogue needs M %% %d == 0 and row-block outputs (M=%d)", tile_m, M);
+      else PEVIT_REQUIRE(ep.c_batch_rows == 0, "gemm_tn: batched direct epilogue takes c_batch_elems, not c_batch_rows");
+    }
+    const uint64_t out_rows = static_cast<uint64_t>(nbm1) * ep.c_batch_rows + M;
     if (ts) {
-      if (make_tmap_out_2d(&t.c, out, M, N, ep.ld_out, BM, elt) != 0) return -1;
+      if (make_tmap_out_2d(&t.c, out, out_rows, N, ep.ld_out, BM, elt) != 0) return -1;
       if (epi == EPI_ACT && ep.out2_bf16 != nullptr && make_tmap_out_2d(&t.c2, ep.out2_bf16, M, N, ep.ld_out, BM, 2) != 0)
         return -1;
-      if (aux != nullptr && make_tmap_out_2d(&t.aux, aux, M, N, ep.ld_out, BM, elt) != 0) return -1;
+      if (aux != nullptr && make_tmap_out_2d(&t.aux, aux, out_rows, N, ep.ld_out, BM, elt) != 0) return -1;
     }
   }
   switch (bn) {

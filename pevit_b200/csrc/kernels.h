@@ -24,6 +24,11 @@ struct GemmEpilogue {
   bf16* qkv_hm = nullptr;          // [3][NB*H][L][64] head-major q (pre-scaled 1/8), k, v
   bf16* t_out = nullptr;           // [M][r2] low-rank activations T = X P (bf16: A operand of the delta GEMM)
   int L = 0, NB = 0, H = 0, D = 0, r2 = 0;
+  // batched launch (EPI_BF16 only): `batch` products of identical shape in one grid.  Batch b reads A rows
+  // [b * a_batch_rows, +M) and B rows [b * b_batch_rows, +N) of the same 2-D operands, and writes either row block
+  // b * c_batch_rows of the output / residual tensor (staged epilogue) or the same rows at element offset
+  // b * c_batch_elems (direct epilogue: column windows of one wide matrix).
+  int batch = 1, a_batch_rows = 0, b_batch_rows = 0, c_batch_rows = 0, c_batch_elems = 0;
   int a_prefetch = 0;  // k-blocks ahead of the ring at which the producer pulls A boxes into L2 (0 = off)
   int debug = 0;  // diagnostics only (tools/gemm_bench.py): 1 = no TMA loads, 2 = no MMAs, 4 = no epilogue stores
 };

@@ -254,3 +254,37 @@ def test_fused_tail_step_matches_pytorch_tail():
     for a, b in zip(out[True][0], out[False][0]):
         assert abs(a - b) < 5e-3 * max(1.0, abs(b))
     assert rel_inf(out[True][1], out[False][1]) < 5e-3
+
+
+@pytest.mark.parametrize("method", ["kadaptation", "lora"])
+def test_batched_delta_launch_vs_in_kernel_delta(method):
+    """L*N a multiple of 256: the q and v deltas are applied by ONE batched GEMM launch (and dT_q / dT_v by another).
+    The CUDA-core cross-check path (attn_impl=1) expands the delta inside the attention kernel instead -- no delta
+    GEMM at all -- so agreement checks the batched row / column offsets end to end."""
+    shape = synth.VIT_TINY
+    sd = synth.clip_state_dict(shape, seed=13)
+    model = BUILDERS[method](dict(sd))
+    synth.randomize_adapters(model.named_parameters(), seed=14)
+    model = model.cuda()
+    freeze_like_reference(model, method)
+    blk = model.visual.transformer.resblocks[1]
+    Lt, NB, D = shape.tokens, 256, shape.vision_width
+    assert (Lt * NB) % 256 == 0
+    g = torch.Generator(device="cuda").manual_seed(15)
+    x0 = torch.randn(Lt, NB, D, device="cuda", generator=g)
+    w = torch.randn(Lt, NB, D, device="cuda", generator=g)
+    res = []
+    for impl in (0, 1):
+        blk.attn_impl = impl
+        model.zero_grad(set_to_none=True)
+        x = x0.clone().requires_grad_(True)
+        y = blk(x)
+        (y * w).sum().backward()
+        res.append((y.detach().clone(), x.grad.clone(),
+                    {n: p.grad.clone() for n, p in model.named_parameters() if p.grad is not None}))
+    blk.attn_impl = 0
+    assert rel_inf(res[0][0], res[1][0]) < 1e-2
+    assert rel_inf(res[0][1], res[1][1]) < 2e-2
+    assert len(res[0][2]) > 0
+    for name in res[0][2]:
+        assert rel_inf(res[0][2][name], res[1][2][name]) < 3e-2, name
