@@ -139,15 +139,20 @@ class FineTuner(nn.Module):
         return loss.detach()
 
     # ------------------------------------------------------------------ CUDA-graph replay of the whole step
-    def capture(self, images: torch.Tensor, labels: torch.Tensor, warmup: int = 3) -> None:
+    def capture(self, images: torch.Tensor, labels: torch.Tensor, warmup: int = 3, slots: int = 1) -> None:
         """Capture zero_grad + forward + loss + backward + (all-reduce) + SGD into one CUDA graph.
 
-        A step enqueues ~500 kernels; at ~11 ms of device time the host can barely keep up launching them, so
+        A step enqueues ~250 kernels; at ~7 ms of device time the host can barely keep up launching them, so
         the step is replayed from a graph with static input buffers instead (B200 guidance: graphs, not a tracing
         compiler).  Every address in the step is static: packs, flat gradient buffer, momentum buffers, and the
         activations live in the graph's private pool.
+
+        ``slots`` > 1 captures that many graphs over ONE memory pool, each bound to its own static input buffers
+        (``input_buffers(slot)``): a host pipeline can then H2D-copy batch i+1 straight into the other slot's
+        buffers while batch i runs, with no device-to-device staging copy in front of the replay.
         """
-        self.static_images, self.static_labels = images.clone(), labels.clone()
+        self.static_inputs = [(images.clone(), labels.clone()) for _ in range(slots)]
+        self.static_images, self.static_labels = self.static_inputs[0]
         side = torch.cuda.Stream(device=images.device)
         side.wait_stream(torch.cuda.current_stream())
         with torch.cuda.stream(side):   # warm up on a side stream: momentum buffers, packs, workspaces exist
@@ -155,25 +160,37 @@ class FineTuner(nn.Module):
                 self.step(self.static_images, self.static_labels)
         torch.cuda.current_stream().wait_stream(side)
         torch.cuda.synchronize()
-        self.graph = torch.cuda.CUDAGraph()
-        with torch.cuda.graph(self.graph):
-            self.static_loss = self.step(self.static_images, self.static_labels)
+        self.graphs, self.static_losses, pool = [], [], None
+        for img, lab in self.static_inputs:
+            graph = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(graph, pool=pool):
+                loss = self.step(img, lab)
+            pool = graph.pool()
+            self.graphs.append(graph)
+            self.static_losses.append(loss)
+        self.graph, self.static_loss = self.graphs[0], self.static_losses[0]
 
-    def step_graphed(self, images: Optional[torch.Tensor] = None, labels: Optional[torch.Tensor] = None) -> torch.Tensor:
-        """Replay the captured step (optionally on a new batch copied into the static input buffers)."""
+    def input_buffers(self, slot: int = 0):
+        """The (images, labels) device buffers graph ``slot`` reads: fill them, then ``step_graphed(slot=slot)``."""
+        return self.static_inputs[slot]
+
+    def step_graphed(self, images: Optional[torch.Tensor] = None, labels: Optional[torch.Tensor] = None,
+                     slot: int = 0) -> torch.Tensor:
+        """Replay the captured step (optionally on a new batch copied into the slot's static input buffers)."""
         if images is not None:
-            self.static_images.copy_(images, non_blocking=True)
-            self.static_labels.copy_(labels, non_blocking=True)
-        self.graph.replay()
-        return self.static_loss
+            self.static_inputs[slot][0].copy_(images, non_blocking=True)
+            self.static_inputs[slot][1].copy_(labels, non_blocking=True)
+        self.graphs[slot].replay()
+        return self.static_losses[slot]
 
     def release_graph(self) -> None:
         """Drop the captured step (and the NCCL work it holds) before the process group is torn down."""
-        graph = getattr(self, "graph", None)
-        if graph is not None:
+        graphs = getattr(self, "graphs", None)
+        if graphs:
             torch.cuda.synchronize()
-            graph.reset()
-            self.graph = None
+            for graph in graphs:
+                graph.reset()
+            self.graphs, self.graph = [], None
 
     def trainable_numel(self) -> int:
         return sum(p.numel() for p in self.params)
