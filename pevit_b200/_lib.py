@@ -10,6 +10,7 @@ import os
 
 _PKG = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_PKG, "lib", "libpevit_b200.so")
+LIB_PATH = os.environ.get("PEVIT_LIB", LIB_PATH)  # diagnostics: load an alternative build of the same ABI
 
 c_void_p, c_int32, c_float, c_size_t = C.c_void_p, C.c_int32, C.c_float, C.c_size_t
 

@@ -21,9 +21,11 @@ constexpr int BM = 128;
 constexpr int BK = 64;  // 64 bf16 = one 128-byte swizzle row
 constexpr int GEMM_THREADS = 320;  // TMA warp, MMA warp, 2 x 4 epilogue warps
 
-// boxes per epilogue warpgroup: epilogues that may TMA-load an auxiliary operand run a 3-deep ring (load two boxes
-// ahead), the others a 2-deep one
-constexpr int epi_ring(int epi) { return (epi == EPI_F32 || epi == EPI_BF16 || epi == EPI_DACT) ? 3 : 2; }
+// Boxes per epilogue warpgroup (RING): 3 = auxiliary operands are TMA-loaded two boxes ahead (short-K GEMMs whose
+// epilogue is the critical path: out-proj + residual, c_proj dgrad x act'(z), the in-place delta); 2 = one box
+// ahead / store ring only, which leaves 32 KB more shared memory for mainloop stages (measured: every stage is worth
+// ~5 % on the K = 3072 GEMMs).  The host picks per launch (ring_for).
+constexpr bool epi_has_ring3(int epi) { return epi == EPI_F32 || epi == EPI_BF16 || epi == EPI_DACT; }
 
 template <int BN, bool CTA2, bool TS, int RING>
 struct TileCfg {
@@ -34,7 +36,10 @@ struct TileCfg {
   static constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
   static constexpr int STAGING_BYTES = TS ? 2 * RING * 16384 : 0;  // staged epilogue: 2 warpgroups x RING [128 rows][128 B] boxes
   static constexpr int STAGES_FIT = (227 * 1024 - STAGING_BYTES - 2048) / STAGE_BYTES;
-  static constexpr int STAGES = STAGES_FIT > 8 ? 8 : STAGES_FIT;
+#ifndef PEVIT_GEMM_MAX_STAGES
+#define PEVIT_GEMM_MAX_STAGES 8
+#endif
+  static constexpr int STAGES = STAGES_FIT > PEVIT_GEMM_MAX_STAGES ? PEVIT_GEMM_MAX_STAGES : STAGES_FIT;
   static constexpr int TMEM_COLS = 2 * BN <= 32 ? 32 : (2 * BN <= 64 ? 64 : (2 * BN <= 128 ? 128 : (2 * BN <= 256 ? 256 : 512)));  // two accumulator stages, power of two
   static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + STAGING_BYTES + 256 + 1024;  // + barriers + align slack
 };
@@ -319,12 +324,12 @@ __device__ __forceinline__ void box_half(const BiasRegs& br, bool has_aux, uint8
   }
 }
 
-template <int BN, int EPI, bool TS, bool CTA2>
+template <int BN, int EPI, bool TS, bool CTA2, int RING>
 __global__ void __launch_bounds__(GEMM_THREADS, 1)
 gemm_tn_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_b,
                const __grid_constant__ CUtensorMap tmap_c, const __grid_constant__ CUtensorMap tmap_c2,
                const __grid_constant__ CUtensorMap tmap_aux, int M, int N, int K, GemmEpilogue ep) {
-  using Cfg = TileCfg<BN, CTA2, TS, epi_ring(epi_base(EPI))>;
+  using Cfg = TileCfg<BN, CTA2, TS, RING>;
   constexpr int STAGES = Cfg::STAGES;
   constexpr int TILE_M = CTA2 ? 2 * BM : BM;  // rows of C covered by one (pair of) CTA(s) per tile
   // staged epilogue geometry (see box_half): columns per box, boxes per tile
@@ -515,7 +520,6 @@ gemm_tn_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
       // RING = 3 (aux-capable epilogues): the aux load of box g+2 is issued right after the store of box g, once
       // the store of box g-1 (same buffer) has drained.  RING = 2: the elected thread drains the previous store
       // before the barrier, so the other buffer is free for the next box.
-      constexpr int RING = epi_ring(epi_base(EPI));
       uint8_t* my_boxes = staging + wg * RING * BOX_BYTES;
       uint64_t* my_aux = aux_bar + wg * 3;
       const int row = quad * 32 + lane, r7 = row & 7;
@@ -542,7 +546,10 @@ gemm_tn_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
         tma_load_2d(my_boxes + slot * BOX_BYTES, &tmap_aux, &my_aux[slot], c0_, m0_);
         la_j += 2;
       };
-      if (has_aux && elected) { la_issue(0); la_issue(1); }
+      if (has_aux && elected) {
+#pragma unroll
+        for (int q = 0; q < RING - 1; ++q) la_issue(q);
+      }
       int slot = 0;            // (boxes processed by this warpgroup) % RING
       uint32_t aux_phase = 0;  // (boxes processed / RING) & 1
       int it = 0;
@@ -609,11 +616,9 @@ gemm_tn_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
               if constexpr (kTwo) { if (ep.out2_bf16 != nullptr) tma_store_2d(&tmap_c2, box + BOX_BYTES, c0, m0); }
             }
             tma_store_commit();
-            if constexpr (RING == 3) {
-              if (has_aux) {
-                tma_store_wait_read<1>();  // store of box g-1 drained: its buffer takes the aux operand of box g+2
-                la_issue(slot == 0 ? 2 : slot - 1);
-              }
+            if (has_aux) {
+              tma_store_wait_read<1>();  // store of box g-1 drained: its buffer takes the aux operand of box g+RING-1
+              la_issue(slot == 0 ? RING - 1 : slot - 1);
             }
           }
           if (++slot == RING) { slot = 0; aux_phase ^= 1; }
@@ -639,13 +644,13 @@ gemm_tn_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
   }
 }
 
-template <int BN, int EPI, bool TS, bool CTA2>
+template <int BN, int EPI, bool TS, bool CTA2, int RING>
 int launch_impl(cudaStream_t stream, const CUtensorMap& ta, const CUtensorMap& tb, const CUtensorMap& tc,
                 const CUtensorMap& tc2, const CUtensorMap& taux, int M, int N, int K, const GemmEpilogue& ep) {
-  using Cfg = TileCfg<BN, CTA2, TS, epi_ring(epi_base(EPI))>;
+  using Cfg = TileCfg<BN, CTA2, TS, RING>;
   static_assert(Cfg::STAGES >= 2, "pipeline too shallow");
   static bool configured[64] = {};  // per instantiation and device (the attribute is per context)
-  auto kern = gemm_tn_kernel<BN, EPI, TS, CTA2>;
+  auto kern = gemm_tn_kernel<BN, EPI, TS, CTA2, RING>;
   int dev = 0;
   PEVIT_CHECK_CUDA(cudaGetDevice(&dev));
   if (!configured[dev & 63]) {
@@ -673,14 +678,24 @@ thread_local bool g_use_pair = false;
 
 struct Tmaps { CUtensorMap a, b, c, c2, aux; };
 
+thread_local int g_ring = 2;
+
 template <int BN, int EPI, bool TS_REQ>
 int launch(cudaStream_t stream, const Tmaps& t, int M, int N, int K, const GemmEpilogue& ep) {
   // a tile narrower than one box (32 fp32 / 64 bf16 columns) cannot use the staged epilogue
   constexpr bool TS = TS_REQ && BN >= (epi_base(EPI) == EPI_F32 ? 32 : 64);
-  if constexpr (BN >= 128) {
-    if (g_use_pair) return launch_impl<BN, EPI, TS, true>(stream, t.a, t.b, t.c, t.c2, t.aux, M, N, K, ep);
+  if constexpr (TS && epi_has_ring3(epi_base(EPI))) {
+    if (g_ring == 3) {
+      if constexpr (BN >= 128) {
+        if (g_use_pair) return launch_impl<BN, EPI, TS, true, 3>(stream, t.a, t.b, t.c, t.c2, t.aux, M, N, K, ep);
+      }
+      return launch_impl<BN, EPI, TS, false, 3>(stream, t.a, t.b, t.c, t.c2, t.aux, M, N, K, ep);
+    }
   }
-  return launch_impl<BN, EPI, TS, false>(stream, t.a, t.b, t.c, t.c2, t.aux, M, N, K, ep);
+  if constexpr (BN >= 128) {
+    if (g_use_pair) return launch_impl<BN, EPI, TS, true, 2>(stream, t.a, t.b, t.c, t.c2, t.aux, M, N, K, ep);
+  }
+  return launch_impl<BN, EPI, TS, false, 2>(stream, t.a, t.b, t.c, t.c2, t.aux, M, N, K, ep);
 }
 
 template <int BN>
@@ -803,6 +818,9 @@ int gemm_tn(cudaStream_t stream, const bf16* A, int lda, const bf16* B, int ldb,
         return -1;
       if (aux != nullptr && make_tmap_out_2d(&t.aux, aux, out_rows, N, ep.ld_out, BM, elt) != 0) return -1;
     }
+    // deep aux ring only where the epilogue is the critical path (short K); long-K GEMMs get the stages instead
+    static const int ring3_max_k = getenv("PEVIT_GEMM_RING3_MAXK") ? atoi(getenv("PEVIT_GEMM_RING3_MAXK")) : 1024;
+    g_ring = (aux != nullptr && K <= ring3_max_k) ? 3 : 2;
   }
   switch (bn) {
     case 32: return dispatch_epi<32>(epi, ts, stream, t, M, N, K, ep);

@@ -71,7 +71,9 @@ def full_captures(tag):
         except ValueError:
             continue
         k = rec["kernel"]
-        if "attn_fwd_tc" in k:
+        if rec["report"].startswith("one_"):   # tools/one_gemm.py captures: one GEMM class per report
+            traffic["gemm_" + rec["report"][4:].split(".")[0]] = b
+        elif "attn_fwd_tc" in k:
             traffic["attn_fwd"] = b
         elif "attn_bwd_tc" in k:
             traffic["attn_bwd"] = b
