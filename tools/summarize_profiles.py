@@ -48,9 +48,18 @@ def launches(tag):
 
 def full_captures(tag):
     out_rows, traffic = [], {}
-    for rep in sorted(f for f in os.listdir(OUT) if f.endswith(".ncu-rep")):
-        res = subprocess.run(["ncu", "-i", os.path.join(OUT, rep), "--page", "raw", "--csv"], capture_output=True, text=True)
-        rows = list(csv.reader(res.stdout.splitlines()))
+    # either the reports themselves or their raw pages exported on the GPU box (`ncu -i x.ncu-rep --page raw --csv >
+    # x.raw.csv`: a report embeds the whole cubin, ~16 MB each, and gpurun returns at most 64 MiB)
+    names = sorted(f for f in os.listdir(OUT) if f.endswith(".raw.csv") or
+                   (f.endswith(".ncu-rep") and not os.path.exists(os.path.join(OUT, f[:-8] + ".raw.csv"))))
+    for rep in names:
+        if rep.endswith(".raw.csv"):
+            text = open(os.path.join(OUT, rep)).read()
+            rep = rep[:-8] + ".ncu-rep"
+        else:
+            text = subprocess.run(["ncu", "-i", os.path.join(OUT, rep), "--page", "raw", "--csv"], capture_output=True,
+                                  text=True).stdout
+        rows = list(csv.reader(text.splitlines()))
         if len(rows) < 3:
             continue
         hdr = rows[0]
