@@ -57,9 +57,10 @@ def shape_of(name):
 
 
 def workload(args, shape):
+    # names the workload (tier contract: a "workload" description, not the ML-style model / seq_len keys)
     return {"workload": f"{args.model} CLIP + {args.method} fine-tune step, synthetic 224x224, "
-                        f"batch {args.batch}/GPU", "model": args.model, "method": args.method,
-            "per_gpu_batch": args.batch, "global_batch": args.batch * args.gpus, "tokens": shape.tokens,
+                        f"batch {args.batch}/GPU", "backbone": args.model, "peft": args.method,
+            "images_per_gpu_step": args.batch, "images_per_step": args.batch * args.gpus, "tokens": shape.tokens,
             "width": shape.vision_width, "layers": shape.vision_layers, "parallelism": f"dp{args.gpus}",
             "l2_policy": "inputs larger than L2 (154 MB fp32 image batch, >3 GB of saved activations per step)"}
 
