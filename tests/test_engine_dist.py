@@ -84,3 +84,59 @@ def test_single_process_is_a_no_op_collective():
 ])
 def test_name_based_freezing_matches_the_reference_drivers(name, method, expect):
     assert trainable_by_name(name, method) is expect
+
+
+def test_flat_params_share_storage_and_keep_values():
+    """engine.FlatParams re-points every parameter into one flat buffer (the fused SGD kernel's view of the model):
+    values survive, later in-place updates of the flat buffer are what the modules see, .grad views stay intact."""
+    from pevit_b200.engine import FlatParams
+    torch.manual_seed(0)
+    lin = torch.nn.Linear(7, 3)
+    extra = torch.nn.Parameter(torch.randn(4, 5, 1))
+    params = [lin.weight, lin.bias, extra]
+    before = [p.detach().clone() for p in params]
+    grads = FlatGrads(params)
+    flat = FlatParams(params)
+    assert flat.flat.numel() == sum(p.numel() for p in params)
+    for p, b in zip(params, before):
+        assert torch.equal(p.detach(), b)
+        assert p.data.untyped_storage().data_ptr() == flat.flat.untyped_storage().data_ptr()
+        assert p.grad._base is grads.flat
+    flat.flat.add_(1.0)                                  # what the SGD kernel does: update through the flat view
+    for p, b in zip(params, before):
+        assert torch.equal(p.detach(), b + 1.0)
+    x = torch.randn(2, 7)
+    assert torch.allclose(lin(x), torch.nn.functional.linear(x, before[0] + 1.0, before[1] + 1.0))
+
+
+def test_sum_allreduce_plus_scaled_update_equals_mean_allreduce():
+    """The fused step folds 1/world into the optimizer kernel (all_reduce_sum + grad_scale) -- same update as
+    all_reduce_mean + unscaled SGD, here with the reference arithmetic of pevit_sgd_momentum on CPU."""
+    g = torch.Generator().manual_seed(1)
+    world, n = 4, 100
+    local = [torch.randn(n, generator=g) for _ in range(world)]
+    p0 = torch.randn(n, generator=g)
+    mean_path = p0.clone().requires_grad_(True)
+    opt = torch.optim.SGD([mean_path], lr=0.1, momentum=0.9, weight_decay=1e-2)
+    p, m = p0.clone(), torch.zeros(n)
+    for _ in range(3):
+        mean_path.grad = torch.stack(local).mean(0)
+        opt.step()
+        gsum = torch.stack(local).sum(0)
+        gi = gsum * (1.0 / world) + 1e-2 * p             # pevit_sgd_momentum: g' = grad_scale * g + wd * p
+        m = 0.9 * m + gi
+        p = p - 0.1 * m
+        local = [t * 0.5 + 0.1 for t in local]
+    assert torch.allclose(p, mean_path.detach(), atol=1e-6)
+
+
+def test_non_fused_block_honours_out_tokens_on_cpu():
+    """Text-tower style blocks (stock PyTorch path) accept out_tokens too: first token positions of the full output."""
+    from pevit_b200 import _clip
+    torch.manual_seed(0)
+    blk = _clip.ResidualAttentionBlock(64, 1).eval()
+    x = torch.randn(5, 2, 64)
+    with torch.no_grad():
+        full = blk(x)
+        first = blk(x, out_tokens=1)
+    assert first.shape == (1, 2, 64) and torch.equal(first, full[:1])
