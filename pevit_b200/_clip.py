@@ -311,10 +311,13 @@ class VisionTransformer(nn.Module):
             x = self.ln_pre(x).transpose(0, 1).contiguous()      # (L, N, D) rows, as the reference (model.py:1042)
         if fused:
             ops.join_side_stream(x.device)
-            # only x[0] feeds ln_post (model.py:1046): the last block produces the class-token rows alone
-            for blk in blocks[:-1]:
-                x = blk(x)
-            x = blocks[-1](x, out_tokens=1)
+            try:
+                # only x[0] feeds ln_post (model.py:1046): the last block produces the class-token rows alone
+                for blk in blocks[:-1]:
+                    x = blk(x)
+                x = blocks[-1](x, out_tokens=1)
+            finally:
+                ops.clear_expanded_ahead(blocks)   # an aborted forward must not leave "already expanded" marks behind
         else:
             x = self.transformer(x)
         return x[0]

@@ -197,6 +197,13 @@ def expand_ahead(blocks, method: str) -> None:
             pack.expanded_ahead = True
 
 
+def clear_expanded_ahead(blocks) -> None:
+    for blk in blocks:
+        pack = getattr(blk, "_pevit_pack", None)
+        if pack is not None:
+            pack.expanded_ahead = False
+
+
 def join_side_stream(device) -> None:
     side = _side_streams.get(device.index or 0)
     if side is not None:
