@@ -7,6 +7,11 @@ import numpy as np
 import torch
 
 GOLDEN = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
+# (fixture file, method): one Transformer layer at a BASELINE configuration's shape, produced by the reference
+BLOCK_FIXTURES = [("b32blk_kadaptation.npz", "kadaptation"), ("b32blk_lora.npz", "lora"),
+                  ("b32blk_adapter.npz", "adapter"), ("b32blk_compacter.npz", "compacter"),
+                  ("b16blk_lora.npz", "lora"),                  # configs[2]: ViT-B/16, L = 197
+                  ("l14blk_kadaptation.npz", "kadaptation")]   # configs[4]: ViT-L/14, L = 257, D = 1024
 METHODS = ("kadaptation", "lora", "adapter", "compacter")
 
 

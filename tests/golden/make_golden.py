@@ -17,6 +17,9 @@ Fixtures
   b32blk_<method>.npz       one ViT-B/32-shaped Transformer layer (D=768, H=12, L=50, N=8): weights are
                             regenerated from the seed at test time (checksum stored), output sub-sampled,
                             adapter grads stored in full.
+  b16blk_lora.npz           the same for BASELINE configs[2]'s shape: ViT-B/16 (D=768, H=12, L=197, N=4), LoRA
+  l14blk_kadaptation.npz    and configs[4]'s: ViT-L/14 (D=1024, H=16, L=257, N=2), KAdaptation
+                            (both exercise the L > 128 attention kernels at block level)
 """
 from __future__ import annotations
 
@@ -97,7 +100,10 @@ def block_weights(D: int, seed: int) -> dict:
 
 
 def b32_block(method: str) -> dict:
-    D, H, L, N = 768, 12, 50, 8
+    return shaped_block(method, 768, 12, 50, 8)
+
+
+def shaped_block(method: str, D: int, H: int, L: int, N: int) -> dict:
     mod = ref_import.load({"kadaptation": "model", "lora": "lora_model", "adapter": "adapter_model",
                            "compacter": "compacter_model"}[method])
     torch.manual_seed(99)
@@ -149,6 +155,8 @@ def main() -> None:
         for case in ("R", "Z"):
             save(f"tiny_{m}_{case}.npz", tiny_case(m, case, sd))
         save(f"b32blk_{m}.npz", b32_block(m))
+    save("b16blk_lora.npz", shaped_block("lora", 768, 12, 197, 4))
+    save("l14blk_kadaptation.npz", shaped_block("kadaptation", 1024, 16, 257, 2))
     import json
     with open(os.path.join(HERE, "surface.json"), "w") as fh:
         json.dump({m: surface(m, sd) for m in METHODS}, fh, indent=0)

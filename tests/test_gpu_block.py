@@ -18,7 +18,7 @@ import pevit_b200
 from oracle import pevit_oracle as O
 from pevit_b200 import _clip, synth
 from tests._report import Parity
-from tests._util import METHODS, bf16_floor_block, bf16_floor_step, load_npz, rel_inf, rel_l2, tiny_params
+from tests._util import BLOCK_FIXTURES, METHODS, bf16_floor_block, bf16_floor_step, load_npz, rel_inf, rel_l2, tiny_params
 
 pytestmark = pytest.mark.gpu
 TOL = 1e-2
@@ -97,9 +97,9 @@ def test_tiny_model_step_vs_reference_fixture(method, case):
     rep.finish()
 
 
-@pytest.mark.parametrize("method", METHODS)
-def test_b32_block_vs_reference_fixture_and_oracle(method):
-    fix = load_npz(f"b32blk_{method}.npz")
+@pytest.mark.parametrize("fixture,method", BLOCK_FIXTURES, ids=[f[0][:-4] for f in BLOCK_FIXTURES])
+def test_block_vs_reference_fixture_and_oracle(fixture, method):
+    fix = load_npz(fixture)
     D, H, Lt, NB = (int(v) for v in fix["shape"])
     g = torch.Generator().manual_seed(10)
     w: dict = {}
@@ -129,7 +129,7 @@ def test_b32_block_vs_reference_fixture_and_oracle(method):
         if k.startswith("param:"):
             p[k[6:]] = v
     floor = bf16_floor_block(fix, p, x, wy, H, method)
-    rep = Parity(f"b32_block[{method}]")
+    rep = Parity(f"{fixture[:-4]}[{method}]")
     rep.add("y (fixture)", rel_inf(y.detach().cpu()[:, :, ::8], fix["y_sub"]), TOL, note=f"bf16 floor {floor['y']:.2e}")
     rep.add("dx (fixture)", rel_inf(xc.grad.cpu()[:, :, ::8], fix["dx_sub"]), max(GRAD_TOL, 1.5 * floor["dx"]),
             rel_l2(xc.grad.cpu()[:, :, ::8], fix["dx_sub"]), note=f"bf16 floor {floor['dx']:.2e}")

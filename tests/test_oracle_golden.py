@@ -9,7 +9,7 @@ import torch
 from oracle import pevit_oracle as O
 from oracle import ref_import
 from pevit_b200 import synth
-from tests._util import METHODS, load_npz, rel_inf, tiny_params
+from tests._util import BLOCK_FIXTURES, METHODS, load_npz, rel_inf, tiny_params
 
 OUT_TOL, GRAD_TOL = 2e-5, 1e-4
 
@@ -46,9 +46,9 @@ def test_tiny_step_matches_reference_fixture(method, case):
         assert any("v_proj_adapter1_left" in n for n in none)
 
 
-@pytest.mark.parametrize("method", METHODS)
-def test_b32_block_matches_reference_fixture(method):
-    fix = load_npz(f"b32blk_{method}.npz")
+@pytest.mark.parametrize("fixture,method", BLOCK_FIXTURES, ids=[f[0][:-4] for f in BLOCK_FIXTURES])
+def test_block_matches_reference_fixture(fixture, method):
+    fix = load_npz(fixture)
     D, H, L, N = (int(v) for v in fix["shape"])
     g = torch.Generator().manual_seed(10)
     w: dict = {}
