@@ -55,7 +55,6 @@ std::vector<ProfEvent> g_pool;     // reusable pairs
 std::mutex g_prof_mu;
 bool g_prof_on = false;
 std::atomic<long long> g_launches{0};
-long long g_class_launches[PC_COUNT] = {};
 thread_local int g_tag = -1;
 const char* const kClassNames[PC_COUNT] = {
     "gemm_qkv", "gemm_out", "gemm_fc", "gemm_proj", "gemm_dproj", "gemm_dfc", "gemm_dout", "gemm_dqkv", "gemm_dT",
