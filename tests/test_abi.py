@@ -57,3 +57,19 @@ def test_size_queries_need_no_gpu(built):
     bad = L.BlockDesc(50, 256, 700, 12, L.KADAPTATION, 32, 160.0, 1, 0, 1)
     assert lib.pevit_block_saved_bytes(ctypes.byref(bad)) == 0
     assert b"head_dim" in lib.pevit_last_error()
+
+
+def test_sass_shows_tcgen05_tmem_and_tma(built):
+    """The built library really is tcgen05 / TMEM / TMA code for sm_100a (B200_PROFILING.md's SASS mnemonics):
+    UTCHMMA (tcgen05.mma, incl. the 2-CTA form), LDTM (tcgen05.ld), UTMALDG / UTMASTG (TMA load / store),
+    UTMAPF (TMA L2 prefetch).  No GPU needed: cuobjdump reads the cubin."""
+    import shutil
+    import subprocess
+    tool = shutil.which("cuobjdump") or "/usr/local/cuda/bin/cuobjdump"
+    if not os.path.exists(tool):
+        pytest.skip("cuobjdump not available")
+    res = subprocess.run([tool, "-sass", L.LIB_PATH], capture_output=True, text=True, timeout=300)
+    assert res.returncode == 0, res.stderr[-500:]
+    assert "EF_CUDA_SM100" in res.stdout
+    for mnemonic in ("UTCHMMA", "UTCHMMA.2CTA", "LDTM", "UTMALDG", "UTMASTG", "UTMAPF"):
+        assert mnemonic in res.stdout, f"{mnemonic} missing from the SASS"
