@@ -1,0 +1,42 @@
+"""The bench line's shape (driver contract): checked on the committed headline line and on the reference arm run live
+on CPU with a tiny sample."""
+import json
+import os
+import subprocess
+import sys
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+BASE_KEYS = {"metric", "value", "unit", "n_gpus", "steps", "warmup", "ms_per_step", "higher_is_better", "scaling",
+             "vs_baseline", "dtype", "data", "config", "e2e", "gpu_launches", "cpu_baseline"}
+
+
+def test_committed_headline_line_has_every_contract_key():
+    with open(os.path.join(ROOT, "profiles", "r01_bench_c2_1gpu.json")) as fh:
+        line = json.load(fh)
+    with open(os.path.join(ROOT, "BASELINE.json")) as fh:
+        base = json.load(fh)
+    assert BASE_KEYS | {"roofline", "clocks"} <= set(line)
+    assert line["metric"] == base["metric"] and line["unit"] == "images/s" and line["higher_is_better"] is True
+    assert line["warmup"] >= 3 and line["n_gpus"] == 1 and line["scaling"] == "weak" and line["vs_baseline"] is None
+    assert "workload" in line["config"] and "model" not in line["config"] and "l2_policy" in line["config"]
+    assert {"value", "unit", "h2d_bytes_per_step", "d2h_bytes_per_step"} <= set(line["e2e"])
+    assert line["e2e"]["h2d_bytes_per_step"] >= 256 * 3 * 224 * 224 * 4 and line["e2e"]["d2h_bytes_per_step"] > 0
+    assert line["e2e"]["value"] <= line["value"] * 1.02          # e2e includes the copies: never faster than resident
+    roof = line["roofline"]
+    assert {"bound", "achieved", "peak", "unit", "frac", "traffic"} <= set(roof) and roof["bound"] in ("hbm", "tensor")
+    assert abs(roof["frac"] - roof["achieved"] / roof["peak"]) < 1e-9 and 0 < roof["frac"] < 1
+    assert {"value", "unit", "cores", "kind", "sample"} <= set(line["cpu_baseline"]) and line["cpu_baseline"]["kind"] == "port"
+    assert {"sm_mhz", "sm_max_mhz", "reasons"} <= set(line["clocks"])
+    assert not {"hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown"} & set(line["clocks"]["reasons"])
+    assert line["gpu_launches"] > 0
+
+
+def test_reference_arm_prints_the_contract_line_on_cpu():
+    res = subprocess.run([sys.executable, "bench.py", "--impl", "reference", "--steps", "1", "--warmup", "0",
+                          "--cpu-batch", "2"], cwd=ROOT, capture_output=True, text=True, timeout=600)
+    assert res.returncode == 0, res.stderr[-2000:]
+    line = json.loads(res.stdout.strip().splitlines()[-1])
+    assert line["impl"] == "reference" and BASE_KEYS <= set(line)
+    assert line["e2e"] == {"value": line["value"], "unit": line["unit"], "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}
+    assert line["cpu_baseline"]["value"] == line["value"] and line["cpu_baseline"]["cores"] >= 1
+    assert line["gpu_launches"] == 0 and "workload" in line["config"]
