@@ -45,7 +45,14 @@ def parse():
     ap.add_argument("--method", default="kadaptation", choices=["kadaptation", "lora", "adapter", "compacter"])
     ap.add_argument("--model", default="vit_b32", choices=["vit_b32", "vit_b16", "vit_l14"])
     ap.add_argument("--batch", type=int, default=256, help="images per GPU per step")
-    ap.add_argument("--cpu-batch", type=int, default=32, help="images per CPU-baseline step (bounded sample)")
+    ap.add_argument("--cpu-batch", type=int, default=0,
+                    help="images per CPU-baseline step (0 = the full --batch: same configuration as the GPU arm)")
+    ap.add_argument("--ref-device", default="cpu", choices=["cpu", "cuda"],
+                    help="--impl reference: cpu = the bench contract's CPU arm; cuda = the same reference algorithm as "
+                         "eager PyTorch on one B200 (north_star's >=5x denominator; diagnostics, not the contract arm)")
+    ap.add_argument("--ref-autocast", action="store_true", help="--ref-device cuda under torch.autocast(bfloat16)")
+    ap.add_argument("--no-gpu-eager-baseline", action="store_true")
+    ap.add_argument("--no-parity-probe", action="store_true")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-graph", action="store_true", help="time the eager step instead of the CUDA-graph replay")
     return ap.parse_args()
@@ -126,34 +133,91 @@ def use_all_host_threads() -> int:
     return torch.get_num_threads()
 
 
-def oracle_step_fn(args, shape):
+def oracle_step_fn(args, shape, device="cpu", autocast=False):
+    """One fwd + CE + bwd step of the reference algorithm (oracle/pevit_oracle.py: materialised Kronecker sums, dense
+    delta -- kadaptation_clip.py:347-352) on `device`; returns seconds per call (device-synchronised)."""
     from oracle import pevit_oracle as O
     use_all_host_threads()
     from pevit_b200 import synth
+    dev = torch.device(device)
     p = dict(synth.clip_state_dict(shape, seed=0))
     O.init_adapters(p, args.method, seed=0)
     synth.randomize_adapters(p.items(), seed=1)
+    p = {k: v.to(dev) for k, v in p.items()}
     g = torch.Generator().manual_seed(4)
-    hw = torch.randn(10, shape.embed_dim, generator=g) * shape.embed_dim ** -0.5
-    hb = torch.zeros(10)
+    hw = (torch.randn(10, shape.embed_dim, generator=g) * shape.embed_dim ** -0.5).to(dev)
+    hb = torch.zeros(10, device=dev)
 
     def step(n, seed):
-        img, lab = synth.images(n, shape.image_resolution, seed=seed), synth.labels(n, 10, seed=seed + 1)
+        img = synth.images(n, shape.image_resolution, seed=seed).to(dev)
+        lab = synth.labels(n, 10, seed=seed + 1).to(dev)
+        if dev.type == "cuda":
+            torch.cuda.synchronize(dev)
         t0 = time.perf_counter()
-        O.train_step_grads(img, lab, p, hw, hb, args.method)
+        with torch.autocast(dev.type, dtype=torch.bfloat16, enabled=autocast):
+            _, loss, _ = O.train_step_grads(img, lab, p, hw, hb, args.method)
+        float(loss)  # the reference reads the loss back every step (kadaptation_clip.py:354)
+        if dev.type == "cuda":
+            torch.cuda.synchronize(dev)
         return time.perf_counter() - t0
     return step
 
 
+def cpu_batch_of(args) -> int:
+    return args.cpu_batch if args.cpu_batch > 0 else args.batch
+
+
 def cpu_baseline(args, shape, steps=2, warmup=1) -> dict:
     step = oracle_step_fn(args, shape)
+    nb = cpu_batch_of(args)
     for i in range(warmup):
-        step(min(4, args.cpu_batch), 100 + i)
-    ts = [step(args.cpu_batch, 200 + i) for i in range(steps)]
-    return {"value": args.cpu_batch / statistics.median(ts), "unit": "images/s", "cores": torch.get_num_threads(),
-            "kind": "port", "host_cpus": os.cpu_count(),
-            "sample": f"{steps} fwd+bwd step(s) of {args.cpu_batch} images, {args.model} {args.method}, fp32, "
+        step(min(4, nb), 100 + i)
+    ts = [step(nb, 200 + i) for i in range(steps)]
+    return {"value": nb / statistics.median(ts), "unit": "images/s", "cores": torch.get_num_threads(),
+            "kind": "port", "host_cpus": os.cpu_count(), "same_config": nb == args.batch,
+            "sample": f"{steps} fwd+bwd step(s) of {nb} images, {args.model} {args.method}, fp32, "
                       "oracle/pevit_oracle.py (reference algorithm: materialised Kronecker sums)"}
+
+
+def gpu_eager_baseline(args, shape, dev, steps=3, warmup=2) -> dict:
+    """north_star's denominator ("the reference's own 1-GPU images/sec"): the reference ALGORITHM as eager PyTorch on
+    this B200 -- fp32 with TF32 off (the reference's default) and under autocast(bf16).  The Python reference itself
+    cannot travel to the GPU box; the oracle is its restatement (same op sequence, same intermediates)."""
+    out = {"kind": "port (oracle/pevit_oracle.py as eager PyTorch on cuda)", "images_per_step": args.batch,
+           "steps": steps, "unit": "images/s"}
+    tf32 = (torch.backends.cuda.matmul.allow_tf32, torch.backends.cudnn.allow_tf32)
+    torch.backends.cuda.matmul.allow_tf32 = torch.backends.cudnn.allow_tf32 = False
+    try:
+        for key, autocast in (("fp32", False), ("autocast_bf16", True)):
+            step = oracle_step_fn(args, shape, device=dev, autocast=autocast)
+            for i in range(warmup):
+                step(args.batch, 100 + i)
+            ts = [step(args.batch, 200 + i) for i in range(steps)]
+            out[key] = args.batch / statistics.median(ts)
+            del step
+            torch.cuda.empty_cache()
+    finally:
+        torch.backends.cuda.matmul.allow_tf32, torch.backends.cudnn.allow_tf32 = tf32
+    return out
+
+
+def parity_probe(args, shape, tuner, dev, n=16) -> dict:
+    """BASELINE.json's second metric: logits max-abs-err of this path vs the reference algorithm (oracle, fp32, CPU) on
+    the same weights and the same n-image batch (F4 couples the samples of a batch, so both sides see the same n)."""
+    from oracle import pevit_oracle as O
+    from pevit_b200 import synth
+    use_all_host_threads()
+    p = {k: v.detach().float().cpu() for k, v in tuner.backbone.named_parameters()}
+    p.update({k: v.detach().float().cpu() for k, v in tuner.backbone.named_buffers()})
+    hw, hb = tuner.head.weight.detach().float().cpu(), tuner.head.bias.detach().float().cpu()
+    img = synth.images(n, shape.image_resolution, seed=77)
+    with torch.no_grad():
+        ref = O.classifier_logits(img, p, hw, hb, args.method)
+        got = tuner(img.to(dev)).float().cpu()
+    err = (got - ref).abs().max().item()
+    return {"max_abs_err": err, "rel_err": err / ref.abs().max().item(), "ref_max_abs": ref.abs().max().item(),
+            "sample": f"{n} images, trained-state weights of this run, oracle fp32 on CPU vs bf16 CUDA path",
+            "tolerance": "1e-2 relative (bf16, north_star)"}
 
 
 def run_reference(args):
@@ -161,21 +225,30 @@ def run_reference(args):
     if rank != 0:
         return
     shape = shape_of(args.model)
-    step = oracle_step_fn(args, shape)
+    nb = cpu_batch_of(args)
+    on_gpu = args.ref_device == "cuda"
+    if on_gpu:
+        torch.backends.cuda.matmul.allow_tf32 = torch.backends.cudnn.allow_tf32 = False  # reference default
+    step = oracle_step_fn(args, shape, device=args.ref_device, autocast=args.ref_autocast)
     for i in range(args.warmup):
-        step(args.cpu_batch, 100 + i)
-    ts = [step(args.cpu_batch, 200 + i) for i in range(args.steps)]
+        step(nb, 100 + i)
+    ts = [step(nb, 200 + i) for i in range(args.steps)]
     total = sum(ts)
-    ips = args.cpu_batch * args.steps / total
+    ips = nb * args.steps / total
     cfg = workload(args, shape)
-    cfg["sample"] = f"each step = {args.cpu_batch} images (bounded sample of the {args.batch}-image batch)"
+    cfg["sample"] = (f"each step = the full {nb}-image batch" if nb == args.batch else
+                     f"each step = {nb} images (bounded sample of the {args.batch}-image batch)")
+    cfg["reference_device"] = ("cuda eager PyTorch, " + ("autocast bf16" if args.ref_autocast else "fp32, TF32 off")
+                               if on_gpu else "host CPU")
     line = {"impl": "reference", "metric": METRIC, "value": ips, "unit": "images/s", "n_gpus": args.gpus,
             "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * total / args.steps,
-            "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "dtype": "bf16-autocast" if (on_gpu and args.ref_autocast) else "f32", "data": "synthetic",
             "config": cfg,
             "cpu_baseline": {"value": ips, "unit": "images/s", "cores": torch.get_num_threads(), "kind": "port",
-                             "host_cpus": os.cpu_count(),
-                             "sample": f"{args.steps} fwd+bwd steps of {args.cpu_batch} images on the host CPU, "
+                             "host_cpus": os.cpu_count(), "same_config": nb == args.batch,
+                             "sample": f"{args.steps} fwd+bwd steps of {nb} images on "
+                                       f"{'one B200 (eager PyTorch)' if on_gpu else 'the host CPU'}, "
                                        "oracle/pevit_oracle.py (the Python reference cannot travel to the GPU box)"},
             "e2e": {"value": ips, "unit": "images/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
             "gpu_launches": 0}
@@ -344,6 +417,7 @@ def run_b200(args):
         tuner.release_graph()
         torch.cuda.synchronize()
         finish(world)
+        return
 
     ms_step = ms_total / args.steps
     value = N * world * args.steps / (ms_total / 1e3)
@@ -361,7 +435,15 @@ def run_b200(args):
     own_ms = sum(k["ms_per_step"] for k in kernels.values())
     ms_step_eager = ms_eager / args.steps
     for k in kernels.values():
-        k["share_of_step"] = k["ms_per_step"] / ms_step_eager
+        # per-launch event brackets add a little to every class (own_ms > ms_step): the share against the TIMED step
+        # is an upper bound, the share of the summed kernel time is the distribution
+        k["share_of_step"] = k["ms_per_step"] / ms_step
+        k["share_of_kernel_time"] = k["ms_per_step"] / own_ms
+    traffic_file = os.path.join(ROOT, "profiles", "ncu_traffic.json")
+    traffic = {}
+    if os.path.exists(traffic_file):
+        with open(traffic_file) as fh:
+            traffic = json.load(fh).get(f"{args.model}_{args.method}_b{args.batch}", {})
 
     def roofline_of(name):
         k = kernels[name]
@@ -373,17 +455,22 @@ def run_b200(args):
             alg = gemm_flops(name, M, D, 2 * r)
             ach, peak, unit, bound = alg / sec / 1e12, pk.get("bf16_tflops_sustained", pk["bf16_tflops"]), "TFLOP/s", "tensor"
         return {"kernel": name, "bound": bound, "achieved": ach, "peak": peak, "unit": unit, "frac": ach / peak,
-                "traffic": None, "algorithmic_per_launch": alg, "avg_launch_us": k["avg_us"],
+                "traffic": traffic.get(name), "algorithmic_per_launch": alg, "avg_launch_us": k["avg_us"],
                 "share_of_step": k["share_of_step"], "peak_source": pk_src}
 
     rated = [n for n in kernels if n.startswith("attn") or (n.startswith("gemm") and n not in
                                                               ("gemm_other", "gemm_bottleneck"))]
     dominant = max(rated, key=lambda n: kernels[n]["ms_per_step"])
     roof = roofline_of(dominant)
-    traffic_file = os.path.join(ROOT, "profiles", "ncu_traffic.json")
-    if os.path.exists(traffic_file):
-        with open(traffic_file) as fh:
-            roof["traffic"] = json.load(fh).get(dominant)
+    # whole step against the tensor roofline: SURVEY 8(d) algorithmic FLOPs per image (dense base path, dgrad only)
+    p_, E_ = shape.vision_patch_size, shape.embed_dim
+    fwd_flops = shape.vision_layers * (24 * L_ * D * D + 4 * L_ * L_ * D) + 2 * (L_ - 1) * 3 * p_ * p_ * D + 2 * D * E_
+    bwd_flops = shape.vision_layers * (24 * L_ * D * D + 10 * L_ * L_ * D) + 2 * D * E_
+    sustained = pk.get("bf16_tflops_sustained", pk["bf16_tflops"])
+    step_tflops = (fwd_flops + bwd_flops) * N / (ms_step * 1e-3) / 1e12
+    whole_step = {"flops_per_image": fwd_flops + bwd_flops, "achieved_tflops": step_tflops, "peak_tflops": sustained,
+                  "frac": step_tflops / sustained, "peak_source": pk_src,
+                  "ceiling_images_per_s_per_gpu": sustained * 1e12 / (fwd_flops + bwd_flops)}
     line = {
         "metric": METRIC, "value": value, "unit": "images/s", "n_gpus": world, "steps": args.steps,
         "warmup": max(args.warmup, 3), "ms_per_step": ms_step, "higher_is_better": True, "scaling": "weak",
@@ -395,30 +482,51 @@ def run_b200(args):
         "gpu_launches": int(launches),  # this library's kernels per K steps (counted in the eager pass; the graph replays the same launches)
         "roofline": roof,
         "roofline_attn": {n: roofline_of(n) for n in ("attn_fwd", "attn_bwd") if n in kernels},
+        "whole_step_tensor_frac": whole_step["frac"], "whole_step": whole_step,
         "kernels": kernels, "own_kernel_ms_per_step": own_ms,
         "trainable_params": tuner.trainable_numel(), "host_enqueue_ms_per_step": cpu_ms_per_step,
         "cuda_graph": graphed, "eager_profiled_ms_per_step": ms_step_eager,
         "kernel_timing": "per-launch CUDA events in a separate eager pass of the same K steps right after the timed region",
     }
+    tuner.release_graph()
+    torch.cuda.synchronize()
+    if world == 1 and not args.no_parity_probe:
+        probe = parity_probe(args, shape, tuner, dev)
+        line["logits_max_abs_err"] = probe["max_abs_err"]
+        line["logits_parity"] = probe
+    if world == 1 and not args.no_gpu_eager_baseline:
+        del tuner
+        torch.cuda.empty_cache()
+        try:
+            line["gpu_eager_baseline"] = gpu_eager_baseline(args, shape, dev)
+            line["gpu_eager_baseline"]["speedup_vs_fp32"] = value / line["gpu_eager_baseline"]["fp32"]
+            line["gpu_eager_baseline"]["speedup_vs_autocast_bf16"] = value / line["gpu_eager_baseline"]["autocast_bf16"]
+        except Exception as exc:  # pragma: no cover - e.g. out of memory at a large configuration
+            line["gpu_eager_baseline"] = {"unavailable": repr(exc)[:200]}
+            torch.cuda.empty_cache()
     if world == 1 and not args.no_cpu_baseline:
         line["cpu_baseline"] = cpu_baseline(args, shape)
     print(json.dumps(line), flush=True)
-    tuner.release_graph()
-    torch.cuda.synchronize()
     finish(world)
 
 
 def finish(world: int) -> None:
-    """Leave without hanging: the step graph holds NCCL work, and tearing the communicator down while it is alive
-    has been seen to block forever.  Results are already printed; give destroy a bounded chance, then exit."""
+    """Leave through the NORMAL interpreter exit (atexit handlers and the driver's process hooks must run).  With
+    N > 1 the step graph held NCCL work and tearing the communicator down has been seen to block: the graphs are
+    already reset, destroy gets a bounded chance, and a daemon watchdog ends the process only if the regular shutdown
+    that follows is still stuck a minute later (results are printed by then)."""
     sys.stdout.flush()
     sys.stderr.flush()
     if world > 1:
         import torch.distributed as dist
         t = threading.Thread(target=lambda: dist.is_initialized() and dist.destroy_process_group(), daemon=True)
         t.start()
-        t.join(10.0)
-    os._exit(0)
+        t.join(20.0)
+
+        def watchdog():
+            time.sleep(60.0)
+            os._exit(0)
+        threading.Thread(target=watchdog, daemon=True).start()
 
 
 def main():

@@ -150,11 +150,13 @@ int pevit_transpose_bf16(const float* src, int32_t rows, int32_t cols, void* dst
 /* ------------------------------------------------------------------ stem
  * VisionTransformer.forward up to the first block (model.py:1034-1042): stride-p conv1 as im2col + tcgen05
  * GEMM, class token, positional embedding, ln_pre, NLD -> LND.  images fp32 (N,3,R,R) -> x fp32 (L,N,D).
- * w_patch: bf16 [D][ceil8(3 p^2)] flattened conv1.weight, zero padded along K.  Frozen parameters: no backward. */
+ * w_patch: bf16 [D][ceil8(3 p^2)] flattened conv1.weight, zero padded along K.  Frozen parameters: no backward.
+ * pos_rows: rows of the positional embedding; must equal (resolution/patch)^2 + 1 (the reference fails with a
+ * broadcast error otherwise, model.py:1040). */
 size_t pevit_patch_embed_workspace_bytes(int32_t nb, int32_t resolution, int32_t patch, int32_t d);
 int pevit_patch_embed(const float* images, const void* w_patch, const float* cls, const float* pos, const float* ln_g,
                       const float* ln_b, float* x, void* workspace, int32_t nb, int32_t resolution, int32_t patch,
-                      int32_t d, void* stream);
+                      int32_t d, int32_t pos_rows, void* stream);
 
 /* ------------------------------------------------------------------ block level
  * One ResidualAttentionBlock forward / backward (model.py:947-975, lora_model.py,

@@ -96,7 +96,7 @@ _SIGNATURES = {
     "pevit_cast_bf16": (c_int32, [c_void_p, c_void_p, c_size_t, c_void_p]),
     "pevit_transpose_bf16": (c_int32, [c_void_p, c_int32, c_int32, c_void_p, c_int32, c_void_p]),
     "pevit_patch_embed_workspace_bytes": (c_size_t, [c_int32] * 4),
-    "pevit_patch_embed": (c_int32, [c_void_p] * 8 + [c_int32] * 4 + [c_void_p]),
+    "pevit_patch_embed": (c_int32, [c_void_p] * 8 + [c_int32] * 5 + [c_void_p]),
     "pevit_block_saved_bytes": (c_size_t, [_P(BlockDesc)]),
     "pevit_block_workspace_bytes": (c_size_t, [_P(BlockDesc)]),
     "pevit_block_fwd": (c_int32, [_P(BlockDesc), _P(BlockWeights), c_void_p, c_void_p, c_void_p, c_void_p, c_void_p]),

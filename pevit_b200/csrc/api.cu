@@ -279,8 +279,11 @@ size_t pevit_patch_embed_workspace_bytes(int32_t nb, int32_t resolution, int32_t
 
 int pevit_patch_embed(const float* images, const void* w_patch, const float* cls, const float* pos, const float* ln_g,
                       const float* ln_b, float* x, void* workspace, int32_t nb, int32_t resolution, int32_t patch,
-                      int32_t d, void* stream) {
+                      int32_t d, int32_t pos_rows, void* stream) {
   PEVIT_REQUIRE(images && w_patch && cls && pos && ln_g && ln_b && x && workspace, "pevit_patch_embed: null pointer");
+  PEVIT_REQUIRE(patch > 0 && resolution % patch == 0 && pos_rows == (resolution / patch) * (resolution / patch) + 1,
+                "pevit_patch_embed: positional embedding has %d rows, resolution %d / patch %d needs %d", pos_rows,
+                resolution, patch, patch > 0 ? (resolution / patch) * (resolution / patch) + 1 : 0);
   return patch_embed(as_stream(stream), images, static_cast<const bf16*>(w_patch), cls, pos, ln_g, ln_b, x, workspace, nb,
                      resolution, patch, d);
 }

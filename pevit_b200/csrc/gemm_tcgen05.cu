@@ -208,7 +208,7 @@ __device__ __forceinline__ void epilogue_chunk(const GemmEpilogue& ep, int m, in
   } else if constexpr (epi_base(EPI) == EPI_QKV) {
     // rows are tokens in LND order (m = l*NB + n).  Columns [0,3D): q|k|v -> head-major bf16
     // tiles [which][n*H+h][l][64] with q pre-scaled by 1/sqrt(64) (exact: power of two);
-    // columns [3D, 3D+r2): low-rank activations T = X*P kept in fp32, row-major [M][r2].
+    // columns [3D, 3D+r2): low-rank activations T = X*P, stored bf16 row-major [M][r2] (A operand of the delta GEMM).
     const int l = m / ep.NB, n = m - l * ep.NB;
     const int threeD = 3 * ep.D;
     if (c0 < threeD) {

@@ -40,14 +40,18 @@ head_ce_fwd_kernel(const float* __restrict__ feat, const float* __restrict__ W, 
     for (int c = lane; c < C; c += 32) se += __expf(sl[c] - mx);
     se = warp_sum(se);
     const float lse = mx + __logf(se);
-    const int y = static_cast<int>(labels[n]);
+    const long long y64 = labels[n];
+    // PyTorch's CrossEntropyLoss raises on a class index outside [0, C) (device assert): same contract -- fail the
+    // launch loudly instead of dropping the loss term while still emitting a gradient
+    if (y64 < 0 || y64 >= C) __trap();
+    const int y = static_cast<int>(y64);
     const float inv_n = 1.f / N;
     for (int c = lane; c < C; c += 32) {
       const float p = __expf(sl[c] - lse);
       logits[static_cast<size_t>(n) * C + c] = sl[c];
       dlogits[static_cast<size_t>(n) * C + c] = (p - (c == y ? 1.f : 0.f)) * inv_n;
     }
-    if (lane == 0 && y >= 0 && y < C) atomicAdd(loss, (lse - sl[y]) * inv_n);
+    if (lane == 0) atomicAdd(loss, (lse - sl[y]) * inv_n);
   }
 }
 
@@ -83,7 +87,7 @@ head_wgrad_kernel(const float* __restrict__ dlogits, const float* __restrict__ f
     if (e < E) acc = fmaf(d, feat[static_cast<size_t>(n) * E + e], acc);
     accb += d;
   }
-  if (e < E) {
+  if (dW != nullptr && e < E) {
     float* dst = dW + static_cast<size_t>(c) * E + e;
     *dst = accumulate ? *dst + g * acc : g * acc;
   }
@@ -127,9 +131,10 @@ int head_ce_bwd(cudaStream_t s, const float* dlogits, const float* feat, const f
                                    N, E, C, dfeat));
     PEVIT_CHECK_LAUNCH();
   }
-  if (dW != nullptr) {
+  if (dW != nullptr || db != nullptr) {  // a frozen weight with a trainable bias still needs db
     ProfScope prof(s, PC_TAIL);
-    PEVIT_CHECK_CUDA(launch_kernel(head_wgrad_kernel, dim3((E + HEAD_THREADS - 1) / HEAD_THREADS, C), dim3(HEAD_THREADS), 0, s, 1,
+    const int gx = dW != nullptr ? (E + HEAD_THREADS - 1) / HEAD_THREADS : 1;
+    PEVIT_CHECK_CUDA(launch_kernel(head_wgrad_kernel, dim3(gx, C), dim3(HEAD_THREADS), 0, s, 1,
                                    dlogits, feat, gscale, N, E, C, dW, db, accumulate));
     PEVIT_CHECK_LAUNCH();
   }

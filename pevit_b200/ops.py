@@ -27,7 +27,26 @@ def _ptr(t: Optional[torch.Tensor]) -> Optional[int]:
 
 
 def _stream() -> int:
+    """Raw handle of the CURRENT device's current stream.  Every entry point below first makes its tensors' device
+    current (``torch.cuda.device``): the library encodes tensor maps, reads the SM count and sets kernel attributes in
+    the current CUDA context, so a model on cuda:1 must not be driven from device 0's context."""
     return torch.cuda.current_stream().cuda_stream
+
+
+def _on_device_of(arg_index: int):
+    """Decorator: run the wrapped function with the device of its ``arg_index``-th tensor argument current."""
+    def deco(fn):
+        import functools
+
+        @functools.wraps(fn)
+        def wrapped(*args, **kwargs):
+            t = args[arg_index]
+            if isinstance(t, torch.Tensor) and t.is_cuda:
+                with torch.cuda.device(t.device):
+                    return fn(*args, **kwargs)
+            return fn(*args, **kwargs)
+        return wrapped
+    return deco
 
 
 def _f32c(t: torch.Tensor) -> torch.Tensor:
@@ -68,6 +87,10 @@ class BlockPack:
     """bf16 operand copies of one block's frozen weights (+ slots for the expanded factors)."""
 
     def __init__(self, block, method: str):
+        with torch.cuda.device(block.attn.in_proj_weight.device):
+            self._build(block, method)
+
+    def _build(self, block, method: str):
         self.method = method
         attn = block.attn
         w_in = attn.in_proj_weight.detach()
@@ -189,7 +212,7 @@ def expand_ahead(blocks, method: str) -> None:
     if side is None:
         side = _side_streams[dev.index or 0] = torch.cuda.Stream(device=dev)
     side.wait_stream(main)  # earlier work on the main stream (previous backward) may still read the packs
-    with torch.cuda.stream(side):
+    with torch.cuda.device(dev), torch.cuda.stream(side):
         st = side.cuda_stream
         for blk in blocks:
             pack = get_pack(blk, method)
@@ -214,6 +237,7 @@ class _BlockFn(torch.autograd.Function):
     """y = ResidualAttentionBlock(x); differentiable w.r.t. x and the PEFT tensors only."""
 
     @staticmethod
+    @_on_device_of(1)
     def forward(ctx, x, pack: BlockPack, attn_impl: int, out_tokens: int, *peft):
         lib = L.lib()
         method = pack.method
@@ -249,6 +273,7 @@ class _BlockFn(torch.autograd.Function):
         return y
 
     @staticmethod
+    @_on_device_of(1)
     def backward(ctx, dy):
         lib = L.lib()
         pack, desc = ctx.pack, ctx.desc
@@ -350,6 +375,10 @@ class StemPack:
     """bf16 [D][Kpad] copy of the (frozen) patch-embedding conv weight."""
 
     def __init__(self, visual):
+        with torch.cuda.device(visual.conv1.weight.device):
+            self._build(visual)
+
+    def _build(self, visual):
         w = visual.conv1.weight.detach()
         D, K = w.shape[0], w[0].numel()
         self.Kpad = (K + 7) // 8 * 8
@@ -365,16 +394,24 @@ class StemPack:
         return (w.data_ptr(), w._version, str(w.device))
 
 
+@_on_device_of(1)
 def stem_forward(visual, images: torch.Tensor) -> torch.Tensor:
     """conv1 + class token + positional embedding + ln_pre -> (L, N, D) fp32 (model.py:1034-1042)."""
     lib = L.lib()
+    p = visual.conv1.kernel_size[0]
+    if images.dim() != 4 or images.shape[1] != 3 or images.shape[2] != images.shape[3] or images.shape[2] % p != 0:
+        raise ValueError(f"stem_forward expects (N, 3, R, R) images with R a multiple of the patch size {p}, "
+                         f"got {tuple(images.shape)}")
+    if (images.shape[2] // p) ** 2 + 1 != visual.positional_embedding.shape[0]:
+        # the reference fails here with a broadcast error (model.py:1040): same contract, clearer message
+        raise ValueError(f"resolution {images.shape[2]} gives {(images.shape[2] // p) ** 2 + 1} tokens but the "
+                         f"checkpoint's positional embedding has {visual.positional_embedding.shape[0]} rows")
     pack = getattr(visual, "_pevit_stem", None)
     if pack is None or pack.key != StemPack.signature(visual):
         pack = StemPack(visual)
         object.__setattr__(visual, "_pevit_stem", pack)
     images = _f32c(images)
     NB, _, R, _ = images.shape
-    p = visual.conv1.kernel_size[0]
     D = visual.conv1.out_channels
     Lt = (R // p) ** 2 + 1
     x = torch.empty(Lt, NB, D, dtype=torch.float32, device=images.device)
@@ -383,7 +420,7 @@ def stem_forward(visual, images: torch.Tensor) -> torch.Tensor:
     small = [_f32c(t.detach()) for t in (visual.class_embedding, visual.positional_embedding, visual.ln_pre.weight,
                                          visual.ln_pre.bias)]
     L.check(lib.pevit_patch_embed(_ptr(images), _ptr(pack.w), *(_ptr(t) for t in small), _ptr(x), _ptr(ws), NB, R, p, D,
-                                  _stream()), "pevit_patch_embed")
+                                  small[1].shape[0], _stream()), "pevit_patch_embed")
     return x
 
 
@@ -392,6 +429,10 @@ class TailPack:
     """Frozen operands of the tail: ln_post affine (fp32) and the visual projection as bf16 GEMM operands."""
 
     def __init__(self, visual):
+        with torch.cuda.device(visual.proj.device):
+            self._build(visual)
+
+    def _build(self, visual):
         proj = visual.proj.detach()                      # (D, E)
         self.D, self.E = proj.shape
         dev = proj.device
@@ -421,6 +462,7 @@ class _TailFn(torch.autograd.Function):
     """loss, logits = CE(Linear(ln_post(x_cls) @ proj)); differentiable w.r.t. x_cls and the head."""
 
     @staticmethod
+    @_on_device_of(1)
     def forward(ctx, x_cls, labels, head_w, head_b, pack: TailPack):
         lib, st = L.lib(), _stream()
         x = _f32c(x_cls).view(-1, pack.D)
@@ -446,6 +488,7 @@ class _TailFn(torch.autograd.Function):
         return loss, logits
 
     @staticmethod
+    @_on_device_of(1)
     def backward(ctx, g_loss, _g_logits):
         lib, st = L.lib(), _stream()
         pack = ctx.pack
@@ -484,7 +527,8 @@ def tail_loss(visual, head, x_cls: torch.Tensor, labels: torch.Tensor):
     Requires a frozen ln_post / proj (the PEViT setting).  Returns (loss, logits)."""
     if not x_cls.is_cuda:
         raise RuntimeError("pevit_b200 tail runs on CUDA (sm_100a) only; there is no CPU fallback")
-    if visual.proj is None or visual.proj.requires_grad or visual.ln_post.weight.requires_grad:
+    if (visual.proj is None or visual.proj.requires_grad or visual.ln_post.weight.requires_grad
+            or visual.ln_post.bias.requires_grad):
         raise RuntimeError("tail_loss needs a frozen ln_post and visual.proj")
     pack = getattr(visual, "_pevit_tail", None)
     if pack is None or pack.key != TailPack.signature(visual):
@@ -493,6 +537,7 @@ def tail_loss(visual, head, x_cls: torch.Tensor, labels: torch.Tensor):
     return _TailFn.apply(x_cls, labels, head.weight, head.bias, pack)
 
 
+@_on_device_of(0)
 def sgd_momentum_(flat_p: torch.Tensor, flat_g: torch.Tensor, flat_m: torch.Tensor, lr: float, momentum: float,
                   weight_decay: float, grad_scale: float = 1.0) -> None:
     """One launch of torch.optim.SGD(momentum, weight_decay) arithmetic over flat fp32 buffers (optim/build.py:18-127)."""
