@@ -101,7 +101,7 @@ typedef struct pevit_attn_args {
   const void* do_tok;                /* bwd in : bf16 [L*NB][D] */
   void* dqkv; int32_t ld_dqkv;       /* bwd out: bf16 [L*NB][ld], cols dq/8 | dk | dv */
   void* ddelta;                      /* bwd out: bf16 [2][NB*H][L][64] (nullable) */
-  int32_t impl;                      /* 0 = default, 1 = CUDA-core cross-check kernel */
+  int32_t impl;                      /* 0 = default, 1 = CUDA-core cross-check kernel, 2 = pair-streaming kernels for L > 128 */
 } pevit_attn_args;
 int pevit_attn_fwd(const pevit_attn_args* args, void* stream);
 int pevit_attn_bwd(const pevit_attn_args* args, void* stream);
@@ -168,7 +168,8 @@ typedef struct pevit_block_desc {
   int32_t r;           /* 32 (KAdaptation), 4 (LoRA), 0 otherwise */
   float alpha;         /* 160 (KAdaptation), 32 (LoRA) */
   int32_t save;        /* 1: fill `saved` for a later pevit_block_bwd */
-  int32_t attn_impl;   /* 0 default (delta GEMM + tcgen05 attention), 1 CUDA-core kernel with in-kernel delta */
+  int32_t attn_impl;   /* 0 default (delta GEMM + tcgen05 attention), 1 CUDA-core kernel with in-kernel delta,
+                        * 2 like 0 with the pair-streaming attention kernels for L > 128 */
   int32_t need_dx;     /* bwd: 0 skips the input gradient (first layer: nothing upstream trains) */
   int32_t out_rows;    /* 0: all L*NB token rows of y are produced.  > 0: only the leading out_rows rows (LND order,
                         * a multiple of NB = whole token indices) are needed -- the last ViT block feeds only

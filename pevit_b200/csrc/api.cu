@@ -112,16 +112,21 @@ int check_desc(const pevit_block_desc* d) {
 
 int attn_fwd_dispatch(cudaStream_t s, const AttnShape& a, int impl, const bf16* q, const bf16* k, const bf16* v,
                       const bf16* T, const float* qmat, const float* bias, bf16* o_tok, float* lse) {
-  if (impl == 0 && attn_tc_supported(a)) return attn_fwd_tc(s, a, q, k, v, o_tok, lse);
-  if (impl == 0 && attn_tc_long_supported(a)) return attn_fwd_tc_long(s, a, q, k, v, o_tok, lse);
+  // impl 0: tcgen05 kernels (L <= 128: one tile per head or two heads per tile; longer: head-resident); impl 2: the
+  // round-1 pair-streaming kernels for 128 < L <= 384 (kept as a second implementation and for shapes whose
+  // operands do not fit in shared memory); impl 1: CUDA-core cross-check with the delta expanded in-kernel
+  if (impl != 1 && attn_tc_supported(a)) return attn_fwd_tc(s, a, q, k, v, o_tok, lse);
+  if (impl == 0 && attn_hr_supported(a)) return attn_fwd_hr(s, a, q, k, v, o_tok, lse);
+  if (impl != 1 && attn_tc_long_supported(a)) return attn_fwd_tc_long(s, a, q, k, v, o_tok, lse);
   return attn_delta_fwd_ref(s, a, q, k, v, T, qmat, bias, o_tok, lse);
 }
 
 int attn_bwd_dispatch(cudaStream_t s, const AttnShape& a, int impl, const bf16* q, const bf16* k, const bf16* v,
                       const bf16* T, const float* qmat, const float* bias, const bf16* o_tok, const bf16* do_tok,
                       const float* lse, bf16* dqkv, int ld, bf16* ddelta) {
-  if (impl == 0 && attn_tc_supported(a)) return attn_bwd_tc(s, a, q, k, v, do_tok, lse, dqkv, ld, ddelta);
-  if (impl == 0 && attn_tc_long_supported(a)) return attn_bwd_tc_long(s, a, q, k, v, o_tok, do_tok, lse, dqkv, ld, ddelta);
+  if (impl != 1 && attn_tc_supported(a)) return attn_bwd_tc(s, a, q, k, v, do_tok, lse, dqkv, ld, ddelta);
+  if (impl == 0 && attn_bwd_hr_supported(a)) return attn_bwd_hr(s, a, q, k, v, o_tok, do_tok, lse, dqkv, ld, ddelta);
+  if (impl != 1 && attn_tc_long_supported(a)) return attn_bwd_tc_long(s, a, q, k, v, o_tok, do_tok, lse, dqkv, ld, ddelta);
   return attn_delta_bwd_ref(s, a, q, k, v, T, qmat, bias, o_tok, do_tok, lse, dqkv, ld, ddelta);
 }
 

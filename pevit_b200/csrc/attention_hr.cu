@@ -1,0 +1,795 @@
+// "Head-resident" attention core on tcgen05 / TMEM for sequences longer than one 128-row tile (ViT-B/16: L = 197,
+// ViT-L/14: L = 257; any 128 < L <= 384).  Reference: evaluation/model.py:803-815 (bmm(q, k^T), softmax, bmm(p, v),
+// head merge) and its autograd; q', k, v' are head-major bf16 with the low-rank delta already applied.
+//
+// Work item = ONE (image, head): its Q, K, V (and dO, O in the backward) are brought into shared memory ONCE by
+// TMA -- full 128-row tiles plus a tail tile of ceil16(L mod 128) rows, so HBM traffic is the algorithmic minimum and
+// the padded part of the last tile costs no exponentials and almost no MMA columns -- and every (query tile, key
+// block) pair of the head is computed from there.
+//
+//   forward   two stages of head operands (the next head loads while this one computes).  Per pair: S = Q_t K_j^T in
+//             TMEM, one softmax thread per query row computes the block-local statistics (m_j, l_j) and writes the
+//             bf16 probabilities BACK INTO TMEM over the S columns it has just read; O_j = P V_j is then a tcgen05.mma
+//             with the A operand taken from TMEM (no shared-memory round trip, no proxy fence), one accumulator per
+//             key block.  A third warpgroup merges the blocks exactly (O = sum_j e^{m_j-m} O_j / sum_j e^{m_j-m} l_j),
+//             so the softmax warpgroups never wait for an epilogue.  Nothing is rescaled in TMEM, no partial touches HBM.
+//   backward  see the second half of this file.
+#include "common.cuh"
+#include "kernels.h"
+
+namespace pevit {
+namespace {
+
+constexpr int TILE_BYTES = 128 * 128;  // 128 rows x 64 bf16, 128B-swizzled
+constexpr float LOG2E = 1.4426950408889634f;
+constexpr int HR_MAXT = 3;             // tiles per head (L <= 384)
+
+__device__ __forceinline__ float fast_exp2(float x) {
+  float y;
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+  return y;
+}
+
+// Geometry of one head's operands in shared memory: nt tiles, the last one `tail` valid rows stored as tail16 rows.
+struct HrGeom {
+  int L, NB, H, D, heads, nt, tail, tail16;
+  int tensor_bytes;  // (nt - 1) * TILE_BYTES + tail16 * 128
+};
+__host__ __device__ inline int hr_rows(const HrGeom& g, int t) { return t == g.nt - 1 ? g.tail : 128; }      // valid rows
+__host__ __device__ inline int hr_rows16(const HrGeom& g, int t) { return t == g.nt - 1 ? g.tail16 : 128; }  // stored rows
+
+HrGeom make_geom(const AttnShape& a) {
+  HrGeom g{};
+  g.L = a.L; g.NB = a.NB; g.H = a.H; g.D = a.D; g.heads = a.NB * a.H;
+  g.nt = (a.L + 127) / 128;
+  g.tail = a.L - 128 * (g.nt - 1);
+  g.tail16 = (g.tail + 15) / 16 * 16;
+  g.tensor_bytes = (g.nt - 1) * TILE_BYTES + g.tail16 * 128;
+  return g;
+}
+
+// ===================================================================================================== forward
+constexpr int HF_THREADS = 448;  // softmax WG0, softmax WG1, merge WG, TMA warp, MMA warp
+constexpr int HF_STATS_BYTES = 2 * HR_MAXT * 128 * 8;
+
+struct FwdHrParams {
+  HrGeom g;
+  int nstage;
+  bf16* o_tok;
+  float* lse;
+};
+
+// one 32- or 16-column chunk of a score row: running max
+template <int W, bool MASK>
+__device__ __forceinline__ void chunk_max(uint32_t taddr, int c, int valid, float (&m4)[4]) {
+  uint32_t v[W];
+  if constexpr (W == 32) tmem_ld_32x32(taddr + c, v); else tmem_ld_32x16(taddr + c, v);
+  tmem_ld_wait();
+#pragma unroll
+  for (int i = 0; i < W; ++i) {
+    const float s = __uint_as_float(v[i]);
+    if (!MASK || c + i < valid) m4[i & 3] = fmaxf(m4[i & 3], s);
+  }
+}
+// one chunk: p = exp2(s * log2e - mxs), row sum, bf16 probabilities written back to TMEM at column pbase + c / 2
+template <int W, bool MASK>
+__device__ __forceinline__ void chunk_exp(uint32_t taddr, uint32_t pbase, int c, int valid, float mxs, float (&s4)[4]) {
+  uint32_t v[W];
+  if constexpr (W == 32) tmem_ld_32x32(taddr + c, v); else tmem_ld_32x16(taddr + c, v);
+  tmem_ld_wait();
+  uint32_t pk[W / 2];
+#pragma unroll
+  for (int i = 0; i < W; i += 2) {
+    float e0 = fast_exp2(fmaf(__uint_as_float(v[i]), LOG2E, -mxs));
+    float e1 = fast_exp2(fmaf(__uint_as_float(v[i + 1]), LOG2E, -mxs));
+    if (MASK) {
+      e0 = c + i < valid ? e0 : 0.f;
+      e1 = c + i + 1 < valid ? e1 : 0.f;
+    }
+    s4[i & 3] += e0;
+    s4[(i + 1) & 3] += e1;
+    pk[i >> 1] = pack_bf16(e0, e1);
+  }
+  if constexpr (W == 32) tmem_st_32x16(pbase + (c >> 1), pk); else tmem_st_32x8(pbase + (c >> 1), pk);
+}
+
+__global__ void __launch_bounds__(HF_THREADS, 1)
+attn_fwd_hr_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant__ CUtensorMap tm_k,
+                   const __grid_constant__ CUtensorMap tm_v, const __grid_constant__ CUtensorMap tm_qt,
+                   const __grid_constant__ CUtensorMap tm_kt, const __grid_constant__ CUtensorMap tm_vt, FwdHrParams p) {
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  const HrGeom& G = p.g;
+  const int stage_bytes = 3 * G.tensor_bytes;
+  float2* stats = reinterpret_cast<float2*>(smem + p.nstage * stage_bytes);  // [tile parity][block j][row] = (max, sum)
+  uint64_t* bars = reinterpret_cast<uint64_t*>(reinterpret_cast<uint8_t*>(stats) + HF_STATS_BYTES);
+  uint64_t* full = bars;             // [2] head operands landed
+  uint64_t* empty = full + 2;        // [2] every MMA of the head has completed
+  uint64_t* s_full = empty + 2;      // [2] S_b ready (MMA -> softmax warpgroup b)
+  uint64_t* p_full = s_full + 2;     // [2] P_b written back to TMEM (128 arrivals)
+  uint64_t* o_full = p_full + 2;     // every O_j of the query tile accumulated
+  uint64_t* o_empty = o_full + 1;    // merge warpgroup has read the O_j (128 arrivals)
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(o_empty + 1);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int nt = G.nt, L = G.L;
+  const int n_local = (G.heads - static_cast<int>(blockIdx.x) + static_cast<int>(gridDim.x) - 1) /
+                      static_cast<int>(gridDim.x);
+  const int pairs_per_item = nt * nt;
+  const int n_pairs = n_local * pairs_per_item;
+
+  // Rows of the tail tile beyond tail16 are never written by TMA but are read by the M = 128 MMAs: they must hold
+  // finite values (their results are discarded), so the operand area starts out as zeros.
+  {
+    uint4* z = reinterpret_cast<uint4*>(smem);
+    const int n16 = p.nstage * stage_bytes / 16;
+    for (int i = threadIdx.x; i < n16; i += HF_THREADS) z[i] = make_uint4(0, 0, 0, 0);
+  }
+  if (warp == 12 && lane == 0) {
+    tma_prefetch_desc(&tm_q); tma_prefetch_desc(&tm_k); tma_prefetch_desc(&tm_v);
+    tma_prefetch_desc(&tm_qt); tma_prefetch_desc(&tm_kt); tma_prefetch_desc(&tm_vt);
+    for (int s = 0; s < 2; ++s) {
+      mbar_init(&full[s], 1); mbar_init(&empty[s], 1);
+      mbar_init(&s_full[s], 1); mbar_init(&p_full[s], 128);
+    }
+    mbar_init(o_full, 1);
+    mbar_init(o_empty, 128);
+    fence_mbar_init();
+  }
+  if (warp == 13) {
+    tmem_alloc(tmem_slot, 512);
+    tmem_relinquish();
+  }
+  fence_proxy_async_smem();
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+  pdl_launch_dependents();
+  pdl_wait();
+  // TMEM columns: S0 [0,128)  S1 [128,256)  (P_b: bf16 pairs over the first 64 columns of S_b)  O_j [256 + 64 j, +64)
+
+  if (warp == 12) {
+    // ------------------------------------------------------------ TMA producer: one head per stage
+    if (lane == 0) {
+      auto prefetch_head = [&](int k_) {
+        if (k_ >= n_local) return;
+        const int g_ = blockIdx.x + k_ * gridDim.x;
+        for (int i = 0; i < nt - 1; ++i) {
+          tma_prefetch_l2_3d(&tm_q, 0, i * 128, g_); tma_prefetch_l2_3d(&tm_k, 0, i * 128, g_);
+          tma_prefetch_l2_3d(&tm_v, 0, i * 128, g_);
+        }
+        tma_prefetch_l2_3d(&tm_qt, 0, (nt - 1) * 128, g_); tma_prefetch_l2_3d(&tm_kt, 0, (nt - 1) * 128, g_);
+        tma_prefetch_l2_3d(&tm_vt, 0, (nt - 1) * 128, g_);
+      };
+      for (int k_ = p.nstage; k_ < p.nstage + 2; ++k_) prefetch_head(k_);
+      for (int k = 0; k < n_local; ++k) {
+        const int g = blockIdx.x + k * gridDim.x;
+        const int s = k % p.nstage;
+        prefetch_head(k + p.nstage + 2);
+        mbar_wait(&empty[s], ((k / p.nstage) & 1) ^ 1);
+        uint8_t* st = smem + s * stage_bytes;
+        mbar_expect_tx(&full[s], static_cast<uint32_t>(stage_bytes));
+        // first pair's operands first
+        for (int i = 0; i < nt; ++i) {
+          const bool tl = i == nt - 1;
+          tma_load_3d(st + i * TILE_BYTES, tl ? &tm_qt : &tm_q, &full[s], 0, i * 128, g);
+          tma_load_3d(st + G.tensor_bytes + i * TILE_BYTES, tl ? &tm_kt : &tm_k, &full[s], 0, i * 128, g);
+          tma_load_3d(st + 2 * G.tensor_bytes + i * TILE_BYTES, tl ? &tm_vt : &tm_v, &full[s], 0, i * 128, g);
+        }
+      }
+    }
+  } else if (warp == 13) {
+    // ------------------------------------------------------------ MMA issuer
+    auto issue_s = [&](int pi) {
+      const int k = pi / pairs_per_item, r = pi - k * pairs_per_item;
+      const int t = r / nt, j = r - t * nt;
+      const int s = k % p.nstage, b = pi & 1;
+      if (r == 0) mbar_wait(&full[s], (k / p.nstage) & 1);
+      tc_fence_after();
+      if (lane == 0) {
+        const uint32_t st = smem_u32(smem + s * stage_bytes);
+        const uint64_t dq = umma_desc_kmajor_sw128(st + t * TILE_BYTES);
+        const uint64_t dk = umma_desc_kmajor_sw128(st + G.tensor_bytes + j * TILE_BYTES);
+        const uint32_t idesc = umma_idesc_bf16(128, hr_rows16(G, j));
+#pragma unroll
+        for (int kk = 0; kk < 4; ++kk) umma_bf16_ss(tmem_base + b * 128, dq + 2 * kk, dk + 2 * kk, idesc, kk != 0);
+        umma_commit(&s_full[b]);
+      }
+      __syncwarp();
+    };
+    auto issue_pv = [&](int pi) {
+      const int k = pi / pairs_per_item, r = pi - k * pairs_per_item;
+      const int t = r / nt, j = r - t * nt;
+      const int s = k % p.nstage, b = pi & 1;
+      const int tc = k * nt + t;
+      mbar_wait(&p_full[b], (pi >> 1) & 1);
+      if (j == 0) mbar_wait(o_empty, (tc & 1) ^ 1);  // the merge warpgroup has drained the previous tile's O_j
+      tc_fence_after();
+      if (lane == 0) {
+        const uint32_t sv = smem_u32(smem + s * stage_bytes + 2 * G.tensor_bytes + j * TILE_BYTES);
+        constexpr uint32_t idesc = umma_idesc_bf16(128, 64) | IDESC_B_MN;
+        const int ksteps = hr_rows16(G, j) >> 4;
+        for (int kk = 0; kk < ksteps; ++kk)  // A = P_b: 16 keys = 8 TMEM columns per step; B = V_j (64 d contiguous per key)
+          umma_bf16_ts(tmem_base + 256 + j * 64, tmem_base + b * 128 + kk * 8,
+                       umma_desc_mnmajor_sw128(sv + kk * 2048, TILE_BYTES), idesc, kk != 0);
+        if (j == nt - 1) umma_commit(o_full);
+        if (r == pairs_per_item - 1) umma_commit(&empty[s]);
+      }
+      __syncwarp();
+    };
+    // S runs one pair ahead of P V (S_(b^1)'s previous reader, the P V product of pair pi-1, is already issued).  With
+    // a single operand stage the look-ahead must not cross into the next head: its load only starts once this
+    // head's last MMA has completed.
+    for (int pi = 0; pi < n_pairs; ++pi) {
+      const bool first_of_item = pi % pairs_per_item == 0;
+      if (first_of_item && (pi == 0 || p.nstage == 1)) issue_s(pi);
+      const int nx = pi + 1;
+      if (nx < n_pairs && !(p.nstage == 1 && nx % pairs_per_item == 0)) issue_s(nx);
+      issue_pv(pi);
+    }
+  } else if (warp < 8) {
+    // ------------------------------------------------------------ softmax warpgroups (alternate pairs)
+    const int grp = warp >> 2, quad = warp & 3;
+    const int row = quad * 32 + lane;
+    const uint32_t t_row = tmem_base + (static_cast<uint32_t>(quad * 32) << 16) + grp * 128;
+    for (int pi = grp; pi < n_pairs; pi += 2) {
+      const int k = pi / pairs_per_item, r = pi - k * pairs_per_item;
+      const int t = r / nt, j = r - t * nt;
+      const int tc = k * nt + t;
+      const int kw = hr_rows16(G, j), valid = hr_rows(G, j);
+      const bool active = quad * 32 < hr_rows(G, t);  // warp-uniform: some row of this warp is a real query
+      mbar_wait(&s_full[grp], (pi >> 1) & 1);
+      tc_fence_after();
+      if (active) {
+        float m4[4] = {-INFINITY, -INFINITY, -INFINITY, -INFINITY};
+        int c = 0;
+        for (; c + 32 <= kw; c += 32) {
+          if (c + 32 <= valid) chunk_max<32, false>(t_row, c, valid, m4);
+          else chunk_max<32, true>(t_row, c, valid, m4);
+        }
+        if (c < kw) {
+          if (c + 16 <= valid) chunk_max<16, false>(t_row, c, valid, m4);
+          else chunk_max<16, true>(t_row, c, valid, m4);
+        }
+        const float mx = fmaxf(fmaxf(m4[0], m4[1]), fmaxf(m4[2], m4[3]));
+        const float mxs = mx * LOG2E;
+        float s4[4] = {0.f, 0.f, 0.f, 0.f};
+        for (c = 0; c + 32 <= kw; c += 32) {
+          if (c + 32 <= valid) chunk_exp<32, false>(t_row, t_row, c, valid, mxs, s4);
+          else chunk_exp<32, true>(t_row, t_row, c, valid, mxs, s4);
+        }
+        if (c < kw) {
+          if (c + 16 <= valid) chunk_exp<16, false>(t_row, t_row, c, valid, mxs, s4);
+          else chunk_exp<16, true>(t_row, t_row, c, valid, mxs, s4);
+        }
+        stats[((tc & 1) * HR_MAXT + j) * 128 + row] = make_float2(mx, (s4[0] + s4[1]) + (s4[2] + s4[3]));
+        tmem_st_wait();
+      }
+      tc_fence_before();
+      mbar_arrive(&p_full[grp]);
+    }
+  } else {
+    // ------------------------------------------------------------ merge warpgroup: O = sum_j w_j O_j / l
+    const int quad = warp & 3;
+    const int row = quad * 32 + lane;
+    const uint32_t t_row = tmem_base + (static_cast<uint32_t>(quad * 32) << 16) + 256;
+    const int n_tiles = n_local * nt;
+    for (int tc = 0; tc < n_tiles; ++tc) {
+      const int k = tc / nt, t = tc - k * nt;
+      const int g = blockIdx.x + k * gridDim.x;
+      const bool active = quad * 32 < hr_rows(G, t);
+      const int lq = t * 128 + row;
+      mbar_wait(o_full, tc & 1);
+      tc_fence_after();
+      if (active) {
+        const float2* st = stats + (tc & 1) * HR_MAXT * 128 + row;
+        float mj[HR_MAXT], w[HR_MAXT], m = -INFINITY, l = 0.f;
+#pragma unroll
+        for (int j = 0; j < HR_MAXT; ++j) {
+          mj[j] = -INFINITY; w[j] = 0.f;
+          if (j < nt) { mj[j] = st[j * 128].x; m = fmaxf(m, mj[j]); }
+        }
+#pragma unroll
+        for (int j = 0; j < HR_MAXT; ++j)
+          if (j < nt) { w[j] = fast_exp2((mj[j] - m) * LOG2E); l = fmaf(w[j], st[j * 128].y, l); }
+        const float inv = 1.f / l;
+        const bool valid = lq < L;
+        const int n = g / G.H, h = g - n * G.H;
+        bf16* orow = p.o_tok + (static_cast<size_t>(valid ? lq : 0) * G.NB + n) * G.D + h * 64;
+#pragma unroll
+        for (int half = 0; half < 2; ++half) {
+          float acc[32];
+#pragma unroll
+          for (int c = 0; c < 32; ++c) acc[c] = 0.f;
+#pragma unroll
+          for (int j = 0; j < HR_MAXT; ++j) {
+            if (j < nt) {
+              uint32_t v[32];
+              tmem_ld_32x32(t_row + j * 64 + half * 32, v);
+              tmem_ld_wait();
+              const float wj = w[j] * inv;
+#pragma unroll
+              for (int c = 0; c < 32; ++c) acc[c] = fmaf(wj, __uint_as_float(v[c]), acc[c]);
+            }
+          }
+          if (half == 1) {  // every O_j of this tile is in registers: the next tile's P V products may overwrite them
+            tc_fence_before();
+            mbar_arrive(o_empty);
+          }
+          if (valid) {
+#pragma unroll
+            for (int c = 0; c < 32; c += 8)
+              *reinterpret_cast<uint4*>(orow + half * 32 + c) =
+                  make_uint4(pack_bf16(acc[c], acc[c + 1]), pack_bf16(acc[c + 2], acc[c + 3]),
+                             pack_bf16(acc[c + 4], acc[c + 5]), pack_bf16(acc[c + 6], acc[c + 7]));
+          }
+        }
+        if (valid) p.lse[static_cast<size_t>(g) * L + lq] = m + __logf(l);
+      } else {
+        tc_fence_before();
+        mbar_arrive(o_empty);
+      }
+    }
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 13) {
+    tc_fence_after();
+    tmem_dealloc(tmem_base, 512);
+  }
+}
+
+
+// ===================================================================================================== backward
+// Operands Q', K, V', dO of the head stay resident (one stage; O visits the P / dS area at the start of the head, only
+// to form delta = rowsum(dO o O)).  Per (query tile t, key block j) pair, non-transposed orientation:
+//   MMA1  S = Q_t K_j^T -> TMEM [0,128),  dP = dO_t V_j^T -> TMEM [128,256)          (N = stored keys of block j)
+//   WG0/1 P = exp(S - lse), dS = P o (dP - delta): the two warpgroups split the key columns (64 each), bf16 tiles in smem
+//   MMA2  dV_j += P^T dO_t, dK_j += dS^T Q_t (K steps = stored rows of tile t), dQ_t += dS K_j (K steps = stored keys)
+//   WG2   drains dV_j / dK_j after the last tile of the group and dQ_t after the last key block
+// Query tiles are processed in groups of two (TMEM: 256 + 128 + 2 x 64 columns); a second group (L > 256) adds its
+// dK / dV contribution onto the first group's output (same thread, same rows).
+constexpr int HB_THREADS = 448;  // WG0, WG1 (P / dS), WG2 (gradients out), TMA warp, MMA warp
+constexpr int HB_VEC_BYTES = 2 * 2 * 128 * HR_MAXT * 4;  // [head parity][delta | lse * log2e][384] fp32
+
+struct BwdHrParams {
+  HrGeom g;
+  int ld;
+  const float* lse;
+  bf16* dqkv;
+  bf16* ddelta;  // nullable
+};
+
+__device__ __forceinline__ void add_bf16x8(float (&f)[8], const uint4& x) {
+  const uint32_t w[4] = {x.x, x.y, x.z, x.w};
+#pragma unroll
+  for (int t = 0; t < 4; ++t) {
+    const float2 a = unpack_bf16(w[t]);
+    f[2 * t] += a.x;
+    f[2 * t + 1] += a.y;
+  }
+}
+
+// W columns [c, c + W) of one query row: P and dS as bf16 into the swizzled [128][128] tiles
+template <int W>
+__device__ __forceinline__ void pds_chunk(uint32_t t_row, uint8_t* sP, uint8_t* sdS, int row, int c, int ncols_valid,
+                                          bool row_valid, float lse_s, float delta) {
+  uint32_t sv[W], dv[W];
+  if constexpr (W == 32) { tmem_ld_32x32(t_row + c, sv); tmem_ld_32x32(t_row + 128 + c, dv); }
+  else { tmem_ld_32x16(t_row + c, sv); tmem_ld_32x16(t_row + 128 + c, dv); }
+  tmem_ld_wait();
+#pragma unroll
+  for (int q = 0; q < W / 8; ++q) {
+    float pj[8], ds[8];
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+      const int col = c + 8 * q + i;
+      const float e = (row_valid && col < ncols_valid) ? fast_exp2(fmaf(__uint_as_float(sv[8 * q + i]), LOG2E, -lse_s)) : 0.f;
+      pj[i] = e;
+      ds[i] = e * (__uint_as_float(dv[8 * q + i]) - delta);
+    }
+    const int kc = (c >> 3) + q;
+    const int off = (kc >> 3) * TILE_BYTES + row * 128 + (((kc & 7) ^ (row & 7)) << 4);
+    *reinterpret_cast<uint4*>(sP + off) = make_uint4(pack_bf16(pj[0], pj[1]), pack_bf16(pj[2], pj[3]),
+                                                     pack_bf16(pj[4], pj[5]), pack_bf16(pj[6], pj[7]));
+    *reinterpret_cast<uint4*>(sdS + off) = make_uint4(pack_bf16(ds[0], ds[1]), pack_bf16(ds[2], ds[3]),
+                                                      pack_bf16(ds[4], ds[5]), pack_bf16(ds[6], ds[7]));
+  }
+}
+
+__global__ void __launch_bounds__(HB_THREADS, 1)
+attn_bwd_hr_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant__ CUtensorMap tm_k,
+                   const __grid_constant__ CUtensorMap tm_v, const __grid_constant__ CUtensorMap tm_do,
+                   const __grid_constant__ CUtensorMap tm_o, const __grid_constant__ CUtensorMap tm_qt,
+                   const __grid_constant__ CUtensorMap tm_kt, const __grid_constant__ CUtensorMap tm_vt,
+                   const __grid_constant__ CUtensorMap tm_dot, const __grid_constant__ CUtensorMap tm_ot, BwdHrParams p) {
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  const HrGeom& G = p.g;
+  const int TB = G.tensor_bytes;
+  uint8_t* sQ = smem;
+  uint8_t* sK = smem + TB;
+  uint8_t* sV = smem + 2 * TB;
+  uint8_t* sdO = smem + 3 * TB;
+  uint8_t* sP = smem + 4 * TB;       // [128 query rows][128 keys] bf16 as two [128][64] half tiles
+  uint8_t* sdS = sP + 2 * TILE_BYTES;
+  uint8_t* sO = sP;                  // O tiles of the head, only until delta is formed
+  float* vecs = reinterpret_cast<float*>(sdS + 2 * TILE_BYTES);  // [parity][0: delta, 1: lse * log2e][384]
+  uint64_t* bars = reinterpret_cast<uint64_t*>(reinterpret_cast<uint8_t*>(vecs) + HB_VEC_BYTES);
+  uint64_t* full = bars;               // head operands landed
+  uint64_t* empty = full + 1;          // every MMA of the head has completed
+  uint64_t* s_full = empty + 1;        // MMA1 (S, dP) of a pair done
+  uint64_t* pds_full = s_full + 1;     // P, dS written (256 arrivals)
+  uint64_t* mma2_done = pds_full + 1;  // MMA2 of a pair done reading P, dS
+  uint64_t* kv_full = mma2_done + 1;   // dK_j, dV_j complete (all tiles of the group)
+  uint64_t* kv_empty = kv_full + 1;    // WG2 drained dK_j, dV_j (128 arrivals)
+  uint64_t* dq_full = kv_empty + 1;    // dQ of the group's tiles complete (all key blocks)
+  uint64_t* dq_empty = dq_full + 1;    // WG2 drained dQ (128 arrivals)
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(dq_empty + 1);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int nt = G.nt, L = G.L;
+  const int ngroups = (nt + 1) / 2;
+  const int n_local = (G.heads - static_cast<int>(blockIdx.x) + static_cast<int>(gridDim.x) - 1) /
+                      static_cast<int>(gridDim.x);
+  auto tiles_in_group = [&](int tg) { return min(2, nt - 2 * tg); };
+
+  {
+    uint4* z = reinterpret_cast<uint4*>(smem);
+    const int n16 = (4 * TB + 4 * TILE_BYTES) / 16;
+    for (int i = threadIdx.x; i < n16; i += HB_THREADS) z[i] = make_uint4(0, 0, 0, 0);
+  }
+  if (warp == 12 && lane == 0) {
+    tma_prefetch_desc(&tm_q); tma_prefetch_desc(&tm_k); tma_prefetch_desc(&tm_v); tma_prefetch_desc(&tm_do);
+    tma_prefetch_desc(&tm_o); tma_prefetch_desc(&tm_qt); tma_prefetch_desc(&tm_kt); tma_prefetch_desc(&tm_vt);
+    tma_prefetch_desc(&tm_dot); tma_prefetch_desc(&tm_ot);
+    mbar_init(full, 1); mbar_init(empty, 1);
+    mbar_init(s_full, 1); mbar_init(pds_full, 256); mbar_init(mma2_done, 1);
+    mbar_init(kv_full, 1); mbar_init(kv_empty, 128); mbar_init(dq_full, 1); mbar_init(dq_empty, 128);
+    fence_mbar_init();
+  }
+  if (warp == 13) {
+    tmem_alloc(tmem_slot, 512);
+    tmem_relinquish();
+  }
+  fence_proxy_async_smem();
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+  pdl_launch_dependents();
+  pdl_wait();
+  // TMEM columns: S [0,128) dP [128,256) dV_j [256,320) dK_j [320,384) dQ_tt [384 + 64 tt, +64)
+
+  if (warp == 12) {
+    // ------------------------------------------------------------ TMA producer
+    if (lane == 0) {
+      auto prefetch_head = [&](int k_) {  // pull the next head into L2 while this one computes
+        if (k_ >= n_local) return;
+        const int g_ = blockIdx.x + k_ * gridDim.x;
+        const int n_ = g_ / G.H, h_ = g_ - n_ * G.H;
+        for (int i = 0; i < nt; ++i) {
+          const bool tl = i == nt - 1;
+          tma_prefetch_l2_3d(tl ? &tm_qt : &tm_q, 0, i * 128, g_);
+          tma_prefetch_l2_3d(tl ? &tm_kt : &tm_k, 0, i * 128, g_);
+          tma_prefetch_l2_3d(tl ? &tm_vt : &tm_v, 0, i * 128, g_);
+          tma_prefetch_l2_4d(tl ? &tm_dot : &tm_do, 0, h_, n_, i * 128);
+          tma_prefetch_l2_4d(tl ? &tm_ot : &tm_o, 0, h_, n_, i * 128);
+        }
+      };
+      prefetch_head(1);
+      for (int k = 0; k < n_local; ++k) {
+        const int g = blockIdx.x + k * gridDim.x;
+        const int n = g / G.H, h = g - n * G.H;
+        prefetch_head(k + 2);
+        mbar_wait(empty, (k & 1) ^ 1);
+        mbar_expect_tx(full, static_cast<uint32_t>(5 * TB));
+        for (int i = 0; i < nt; ++i) {
+          const bool tl = i == nt - 1;
+          tma_load_4d(sO + i * TILE_BYTES, tl ? &tm_ot : &tm_o, full, 0, h, n, i * 128);
+          tma_load_4d(sdO + i * TILE_BYTES, tl ? &tm_dot : &tm_do, full, 0, h, n, i * 128);
+          tma_load_3d(sQ + i * TILE_BYTES, tl ? &tm_qt : &tm_q, full, 0, i * 128, g);
+          tma_load_3d(sK + i * TILE_BYTES, tl ? &tm_kt : &tm_k, full, 0, i * 128, g);
+          tma_load_3d(sV + i * TILE_BYTES, tl ? &tm_vt : &tm_v, full, 0, i * 128, g);
+        }
+      }
+    }
+  } else if (warp == 13) {
+    // ------------------------------------------------------------ MMA issuer
+    constexpr uint32_t idesc_t = umma_idesc_bf16(128, 64) | IDESC_A_MN | IDESC_B_MN;  // A^T B forms
+    constexpr uint32_t idesc_q = umma_idesc_bf16(128, 64) | IDESC_B_MN;
+    const uint32_t aQ = smem_u32(sQ), aK = smem_u32(sK), aV = smem_u32(sV), aDO = smem_u32(sdO);
+    const uint32_t aP = smem_u32(sP), aS = smem_u32(sdS);
+    auto issue_mma1 = [&](int t, int j) {
+      if (lane == 0) {
+        const uint32_t idesc_s = umma_idesc_bf16(128, hr_rows16(G, j));
+        const uint64_t dq = umma_desc_kmajor_sw128(aQ + t * TILE_BYTES), dk = umma_desc_kmajor_sw128(aK + j * TILE_BYTES);
+        const uint64_t dv = umma_desc_kmajor_sw128(aV + j * TILE_BYTES), ddo = umma_desc_kmajor_sw128(aDO + t * TILE_BYTES);
+#pragma unroll
+        for (int kk = 0; kk < 4; ++kk) umma_bf16_ss(tmem_base, dq + 2 * kk, dk + 2 * kk, idesc_s, kk != 0);
+#pragma unroll
+        for (int kk = 0; kk < 4; ++kk) umma_bf16_ss(tmem_base + 128, ddo + 2 * kk, dv + 2 * kk, idesc_s, kk != 0);
+        umma_commit(s_full);
+      }
+      __syncwarp();
+    };
+    int bp = 0, kvc = 0, gc = 0;
+    for (int k = 0; k < n_local; ++k) {
+      mbar_wait(full, k & 1);
+      tc_fence_after();
+      issue_mma1(0, 0);
+      for (int tg = 0; tg < ngroups; ++tg, ++gc) {
+        const int ntg = tiles_in_group(tg);
+        for (int j = 0; j < nt; ++j, ++kvc) {
+          for (int tt = 0; tt < ntg; ++tt, ++bp) {
+            const int t = 2 * tg + tt;
+            mbar_wait(pds_full, bp & 1);
+            if (tt == 0) mbar_wait(kv_empty, (kvc & 1) ^ 1);          // dK / dV accumulators drained (previous block)
+            if (j == 0 && tt == 0) mbar_wait(dq_empty, (gc & 1) ^ 1);  // dQ accumulators drained (previous group)
+            tc_fence_after();
+            const bool last_tt = tt == ntg - 1;
+            const bool last_of_head = last_tt && j == nt - 1 && tg == ngroups - 1;
+            if (lane == 0) {
+              const int qsteps = hr_rows16(G, t) >> 4, ksteps = hr_rows16(G, j) >> 4;
+              for (int kk = 0; kk < qsteps; ++kk)  // dV_j (+)= P^T dO_t   (K = query rows, 16 per step)
+                umma_bf16_ss(tmem_base + 256, umma_desc_mnmajor_sw128(aP + kk * 2048, TILE_BYTES),
+                             umma_desc_mnmajor_sw128(aDO + t * TILE_BYTES + kk * 2048, TILE_BYTES), idesc_t, (tt | kk) != 0);
+              for (int kk = 0; kk < qsteps; ++kk)  // dK_j (+)= dS^T Q_t
+                umma_bf16_ss(tmem_base + 320, umma_desc_mnmajor_sw128(aS + kk * 2048, TILE_BYTES),
+                             umma_desc_mnmajor_sw128(aQ + t * TILE_BYTES + kk * 2048, TILE_BYTES), idesc_t, (tt | kk) != 0);
+              for (int kk = 0; kk < ksteps; ++kk)  // dQ_t (+)= dS K_j     (K = keys)
+                umma_bf16_ss(tmem_base + 384 + tt * 64, umma_desc_kmajor_sw128(aS + (kk >> 2) * TILE_BYTES) + 2 * (kk & 3),
+                             umma_desc_mnmajor_sw128(aK + j * TILE_BYTES + kk * 2048, TILE_BYTES), idesc_q, (j | kk) != 0);
+              umma_commit(mma2_done);
+              if (last_tt) umma_commit(kv_full);
+              if (last_tt && j == nt - 1) umma_commit(dq_full);
+              if (last_of_head) umma_commit(empty);
+            }
+            __syncwarp();
+            if (!last_of_head) {  // S / dP of the next pair: both TMEM regions were consumed before pds_full
+              int t2 = t + 1, j2 = j, tg2 = tg;
+              if (tt == ntg - 1) { j2 = j + 1; t2 = 2 * tg; if (j2 == nt) { j2 = 0; tg2 = tg + 1; t2 = 2 * tg2; } }
+              issue_mma1(t2, j2);
+            }
+          }
+        }
+      }
+    }
+  } else if (warp < 8) {
+    // ------------------------------------------------------------ WG0 / WG1: delta, then P and dS of every pair
+    const int wg = warp >> 2, quad = warp & 3;
+    const int row = quad * 32 + lane;
+    const int tid = threadIdx.x;  // 0..255
+    const uint32_t t_row = tmem_base + (static_cast<uint32_t>(quad * 32) << 16);
+    int bp = 0;
+    for (int k = 0; k < n_local; ++k) {
+      const int g = blockIdx.x + k * gridDim.x;
+      float* vdelta = vecs + (k & 1) * 2 * 128 * HR_MAXT;
+      float* vlse = vdelta + 128 * HR_MAXT;
+      float lse_r[2];
+#pragma unroll
+      for (int i = 0; i < 2; ++i) {
+        const int l = tid + i * 256;
+        lse_r[i] = l < L ? p.lse[static_cast<size_t>(g) * L + l] * LOG2E : 0.f;
+      }
+      mbar_wait(full, k & 1);
+      // delta[l] = sum_d dO[l][d] * O[l][d]: both tiles share the swizzle, so matching physical chunks pair up
+#pragma unroll
+      for (int i = 0; i < 2; ++i) {
+        const int l = tid + i * 256;
+        if (l < L) {
+          const uint8_t* pdo = sdO + (l >> 7) * TILE_BYTES + (l & 127) * 128;
+          const uint8_t* po = sO + (l >> 7) * TILE_BYTES + (l & 127) * 128;
+          float d = 0.f;
+#pragma unroll
+          for (int c = 0; c < 8; ++c) {
+            const uint4 a = *reinterpret_cast<const uint4*>(pdo + c * 16);
+            const uint4 b = *reinterpret_cast<const uint4*>(po + c * 16);
+            const uint32_t aw[4] = {a.x, a.y, a.z, a.w}, bw[4] = {b.x, b.y, b.z, b.w};
+#pragma unroll
+            for (int q = 0; q < 4; ++q) {
+              const float2 fa = unpack_bf16(aw[q]), fb = unpack_bf16(bw[q]);
+              d = fmaf(fa.x, fb.x, fmaf(fa.y, fb.y, d));
+            }
+          }
+          vdelta[l] = d;
+          vlse[l] = lse_r[i];
+        }
+      }
+      named_bar_sync(1, 256);  // delta / lse of the head visible to both warpgroups; the O tiles may now be overwritten
+      for (int tg = 0; tg < ngroups; ++tg) {
+        const int ntg = tiles_in_group(tg);
+        for (int j = 0; j < nt; ++j) {
+          const int kw = hr_rows16(G, j), kvalid = hr_rows(G, j);
+          for (int tt = 0; tt < ntg; ++tt, ++bp) {
+            const int t = 2 * tg + tt;
+            const int lq = t * 128 + row;
+            const bool active = quad * 32 < hr_rows16(G, t);  // warp holds rows the MMAs read (real or zero padding)
+            const bool row_valid = row < hr_rows(G, t);
+            const float lse_s = row_valid ? vlse[lq] : 0.f;
+            const float delta = row_valid ? vdelta[lq] : 0.f;
+            mbar_wait(s_full, bp & 1);
+            tc_fence_after();
+            if (bp > 0) mbar_wait(mma2_done, (bp - 1) & 1);  // MMA2 of the previous pair is done reading P / dS
+            if (active) {
+              for (int c = wg * 64; c < min(kw, wg * 64 + 64); c += 32) {
+                if (c + 32 <= kw) pds_chunk<32>(t_row, sP, sdS, row, c, kvalid, row_valid, lse_s, delta);
+                else pds_chunk<16>(t_row, sP, sdS, row, c, kvalid, row_valid, lse_s, delta);
+              }
+            }
+            fence_proxy_async_smem();
+            tc_fence_before();
+            mbar_arrive(pds_full);
+          }
+        }
+      }
+    }
+  } else {
+    // ------------------------------------------------------------ WG2: gradients out
+    const int quad = warp & 3;
+    const int row = quad * 32 + lane;
+    const uint32_t t_row = tmem_base + (static_cast<uint32_t>(quad * 32) << 16);
+    const size_t plane = static_cast<size_t>(G.heads) * L * 64;
+    int kvc = 0, gc = 0;
+    for (int k = 0; k < n_local; ++k) {
+      const int g = blockIdx.x + k * gridDim.x;
+      const int n = g / G.H, h = g - n * G.H;
+      for (int tg = 0; tg < ngroups; ++tg, ++gc) {
+        const int ntg = tiles_in_group(tg);
+        const bool add_prev = tg > 0;  // a previous group of this head already wrote its dK / dV share
+        for (int j = 0; j < nt; ++j, ++kvc) {
+          const int lk = j * 128 + row;
+          const bool valid = row < hr_rows(G, j);
+          const bool active = quad * 32 < hr_rows(G, j);
+          bf16* tok = p.dqkv + (static_cast<size_t>(valid ? lk : 0) * G.NB + n) * p.ld + h * 64;
+          bf16* hm = p.ddelta != nullptr ? p.ddelta + plane + (static_cast<size_t>(g) * L + (valid ? lk : 0)) * 64 : nullptr;
+          mbar_wait(kv_full, kvc & 1);
+          tc_fence_after();
+          if (active) {
+#pragma unroll 1
+            for (int part = 0; part < 2; ++part) {  // 0: dV', 1: dK
+              bf16* dst_tok = tok + (part == 0 ? 2 * G.D : G.D);
+#pragma unroll
+              for (int c = 0; c < 64; c += 32) {
+                uint32_t v[32];
+                tmem_ld_32x32(t_row + 256 + part * 64 + c, v);
+                tmem_ld_wait();
+                if (valid) {
+#pragma unroll
+                  for (int jj = 0; jj < 32; jj += 8) {
+                    float f[8];
+#pragma unroll
+                    for (int t8 = 0; t8 < 8; ++t8) f[t8] = __uint_as_float(v[jj + t8]);
+                    if (add_prev) add_bf16x8(f, *reinterpret_cast<const uint4*>(dst_tok + c + jj));
+                    const uint4 o = make_uint4(pack_bf16(f[0], f[1]), pack_bf16(f[2], f[3]), pack_bf16(f[4], f[5]),
+                                               pack_bf16(f[6], f[7]));
+                    *reinterpret_cast<uint4*>(dst_tok + c + jj) = o;
+                    if (part == 0 && hm != nullptr) *reinterpret_cast<uint4*>(hm + c + jj) = o;
+                  }
+                }
+              }
+            }
+          }
+          tc_fence_before();
+          mbar_arrive(kv_empty);
+        }
+        mbar_wait(dq_full, gc & 1);
+        tc_fence_after();
+        for (int tt = 0; tt < ntg; ++tt) {
+          const int t = 2 * tg + tt;
+          const int lq = t * 128 + row;
+          const bool valid = row < hr_rows(G, t);
+          if (quad * 32 < hr_rows(G, t)) {
+            bf16* dst_tok = p.dqkv + (static_cast<size_t>(valid ? lq : 0) * G.NB + n) * p.ld + h * 64;
+            bf16* dst_hm = p.ddelta != nullptr ? p.ddelta + (static_cast<size_t>(g) * L + (valid ? lq : 0)) * 64 : nullptr;
+#pragma unroll
+            for (int c = 0; c < 64; c += 32) {
+              uint32_t v[32];
+              tmem_ld_32x32(t_row + 384 + tt * 64 + c, v);
+              tmem_ld_wait();
+              if (valid) {
+#pragma unroll
+                for (int jj = 0; jj < 32; jj += 8) {
+                  float f[8];
+#pragma unroll
+                  for (int t8 = 0; t8 < 8; ++t8) f[t8] = __uint_as_float(v[jj + t8]);
+                  *reinterpret_cast<uint4*>(dst_tok + c + jj) =
+                      make_uint4(pack_bf16(f[0] * 0.125f, f[1] * 0.125f), pack_bf16(f[2] * 0.125f, f[3] * 0.125f),
+                                 pack_bf16(f[4] * 0.125f, f[5] * 0.125f), pack_bf16(f[6] * 0.125f, f[7] * 0.125f));
+                  if (dst_hm != nullptr)
+                    *reinterpret_cast<uint4*>(dst_hm + c + jj) = make_uint4(pack_bf16(f[0], f[1]), pack_bf16(f[2], f[3]),
+                                                                           pack_bf16(f[4], f[5]), pack_bf16(f[6], f[7]));
+                }
+              }
+            }
+          }
+        }
+        tc_fence_before();
+        mbar_arrive(dq_empty);
+      }
+    }
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 13) {
+    tc_fence_after();
+    tmem_dealloc(tmem_base, 512);
+  }
+}
+
+}  // namespace
+
+bool attn_hr_supported(const AttnShape& a) { return a.r == 0 && a.L > 128 && a.L <= 128 * HR_MAXT && a.H * 64 == a.D; }
+
+int attn_fwd_hr(cudaStream_t s, const AttnShape& a, const bf16* q, const bf16* k, const bf16* v, bf16* o_tok, float* lse) {
+  PEVIT_REQUIRE(attn_hr_supported(a), "attn_fwd_hr: unsupported shape L=%d D=%d H=%d r=%d", a.L, a.D, a.H, a.r);
+  const HrGeom g = make_geom(a);
+  CUtensorMap tq, tk, tv, tqt, tkt, tvt;
+  if (make_tmap_bf16_hm3d(&tq, q, a.L, g.heads, 128) != 0) return -1;
+  if (make_tmap_bf16_hm3d(&tk, k, a.L, g.heads, 128) != 0) return -1;
+  if (make_tmap_bf16_hm3d(&tv, v, a.L, g.heads, 128) != 0) return -1;
+  if (make_tmap_bf16_hm3d(&tqt, q, a.L, g.heads, g.tail16) != 0) return -1;
+  if (make_tmap_bf16_hm3d(&tkt, k, a.L, g.heads, g.tail16) != 0) return -1;
+  if (make_tmap_bf16_hm3d(&tvt, v, a.L, g.heads, g.tail16) != 0) return -1;
+  const int stage_bytes = 3 * g.tensor_bytes;
+  const int fixed = HF_STATS_BYTES + 256 + 1024;
+  const int nstage = (227 * 1024 - fixed) / stage_bytes >= 2 ? 2 : 1;
+  const int smem_bytes = nstage * stage_bytes + fixed;
+  FwdHrParams p{g, nstage, o_tok, lse};
+  const int grid = g.heads < sm_count() ? g.heads : sm_count();
+  static int configured[64] = {};
+  int dev = 0;
+  PEVIT_CHECK_CUDA(cudaGetDevice(&dev));
+  if (configured[dev & 63] < smem_bytes) {
+    PEVIT_CHECK_CUDA(cudaFuncSetAttribute(attn_fwd_hr_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+    configured[dev & 63] = 227 * 1024;
+  }
+  ProfScope prof(s, PC_ATTN_FWD);
+  PEVIT_CHECK_CUDA(launch_kernel(attn_fwd_hr_kernel, dim3(grid), dim3(HF_THREADS), smem_bytes, s, 1, tq, tk, tv, tqt, tkt, tvt, p));
+  PEVIT_CHECK_LAUNCH();
+  return 0;
+}
+
+bool attn_bwd_hr_supported(const AttnShape& a) {
+  if (!attn_hr_supported(a)) return false;
+  const HrGeom g = make_geom(a);
+  return 4 * g.tensor_bytes + 4 * TILE_BYTES + HB_VEC_BYTES + 256 + 1024 <= 227 * 1024 && a.L <= 512;
+}
+
+int attn_bwd_hr(cudaStream_t s, const AttnShape& a, const bf16* q, const bf16* k, const bf16* v, const bf16* o_tok,
+                const bf16* do_tok, const float* lse, bf16* dqkv, int ld_dqkv, bf16* ddelta) {
+  PEVIT_REQUIRE(attn_bwd_hr_supported(a), "attn_bwd_hr: unsupported shape L=%d D=%d H=%d r=%d", a.L, a.D, a.H, a.r);
+  PEVIT_REQUIRE(ld_dqkv % 8 == 0, "attn_bwd_hr: ld_dqkv=%d must be a multiple of 8", ld_dqkv);
+  const HrGeom g = make_geom(a);
+  CUtensorMap tq, tk, tv, tdo, to, tqt, tkt, tvt, tdot, tot;
+  if (make_tmap_bf16_hm3d(&tq, q, a.L, g.heads, 128) != 0) return -1;
+  if (make_tmap_bf16_hm3d(&tk, k, a.L, g.heads, 128) != 0) return -1;
+  if (make_tmap_bf16_hm3d(&tv, v, a.L, g.heads, 128) != 0) return -1;
+  if (make_tmap_bf16_hm3d(&tqt, q, a.L, g.heads, g.tail16) != 0) return -1;
+  if (make_tmap_bf16_hm3d(&tkt, k, a.L, g.heads, g.tail16) != 0) return -1;
+  if (make_tmap_bf16_hm3d(&tvt, v, a.L, g.heads, g.tail16) != 0) return -1;
+  if (make_tmap_bf16_tok_heads(&tdo, do_tok, a.L, a.NB, a.H, a.D, 128) != 0) return -1;
+  if (make_tmap_bf16_tok_heads(&to, o_tok, a.L, a.NB, a.H, a.D, 128) != 0) return -1;
+  if (make_tmap_bf16_tok_heads(&tdot, do_tok, a.L, a.NB, a.H, a.D, g.tail16) != 0) return -1;
+  if (make_tmap_bf16_tok_heads(&tot, o_tok, a.L, a.NB, a.H, a.D, g.tail16) != 0) return -1;
+  const int smem_bytes = 4 * g.tensor_bytes + 4 * TILE_BYTES + HB_VEC_BYTES + 256 + 1024;
+  BwdHrParams p{g, ld_dqkv, lse, dqkv, ddelta};
+  const int grid = g.heads < sm_count() ? g.heads : sm_count();
+  static bool configured[64] = {};
+  int dev = 0;
+  PEVIT_CHECK_CUDA(cudaGetDevice(&dev));
+  if (!configured[dev & 63]) {
+    PEVIT_CHECK_CUDA(cudaFuncSetAttribute(attn_bwd_hr_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+    configured[dev & 63] = true;
+  }
+  ProfScope prof(s, PC_ATTN_BWD);
+  PEVIT_CHECK_CUDA(launch_kernel(attn_bwd_hr_kernel, dim3(grid), dim3(HB_THREADS), smem_bytes, s, 1, tq, tk, tv, tdo, to, tqt,
+                                 tkt, tvt, tdot, tot, p));
+  PEVIT_CHECK_LAUNCH();
+  return 0;
+}
+
+}  // namespace pevit

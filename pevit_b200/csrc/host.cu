@@ -224,6 +224,27 @@ int make_tmap_qkv_hm_5d(CUtensorMap* out, const void* base, int L, int NB, int H
   return 0;
 }
 
+int make_tmap_bf16_hm3d(CUtensorMap* out, const void* base, int L, int heads, uint32_t box_l) {
+  const TmapKey key{base, static_cast<uint64_t>(L), static_cast<uint64_t>(heads), 0, box_l, 0, 5};
+  TmapSlot* slot = nullptr;
+  if (tmap_lookup(key, out, &slot)) return 0;
+  CUtensorMap dummy;
+  if (g_encode == nullptr && make_tmap_bf16_2d(&dummy, base, 8, 64, 64, 8, 64) != 0) return -2;  // resolves g_encode
+  const cuuint64_t gdim[3] = {64, static_cast<cuuint64_t>(L), static_cast<cuuint64_t>(heads)};
+  const cuuint64_t gstride[2] = {128, static_cast<cuuint64_t>(L) * 128};
+  const cuuint32_t box[3] = {64, box_l, 1};
+  const cuuint32_t estride[3] = {1, 1, 1};
+  CUresult r = g_encode(out, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 3, const_cast<void*>(base), gdim, gstride, box, estride,
+                        CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                        CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) {
+    set_error("cuTensorMapEncodeTiled(3d) failed (%d): base=%p L=%d heads=%d box_l=%u", (int)r, base, L, heads, box_l);
+    return -2;
+  }
+  tmap_store(slot, key, *out);
+  return 0;
+}
+
 int make_tmap_bf16_tok_heads(CUtensorMap* out, const void* base, int L, int NB, int H, uint64_t row_stride_elems,
                              uint32_t box_l) {
   const TmapKey key{base, static_cast<uint64_t>(L), static_cast<uint64_t>(NB), row_stride_elems, static_cast<uint32_t>(H),

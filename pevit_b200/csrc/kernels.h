@@ -80,6 +80,14 @@ int attn_fwd_tc_long(cudaStream_t s, const AttnShape& a, const bf16* q, const bf
 int attn_bwd_tc_long(cudaStream_t s, const AttnShape& a, const bf16* q, const bf16* k, const bf16* v, const bf16* o_tok,
                      const bf16* do_tok, const float* lse, bf16* dqkv, int ld_dqkv, bf16* ddelta);
 
+// attention_hr.cu: the same range of L with each head's operands resident in shared memory (loaded once, tail tile of
+// ceil16(L mod 128) rows) and, in the forward, the probabilities kept in TMEM as the A operand of P V.
+bool attn_hr_supported(const AttnShape& a);
+int attn_fwd_hr(cudaStream_t s, const AttnShape& a, const bf16* q, const bf16* k, const bf16* v, bf16* o_tok, float* lse);
+bool attn_bwd_hr_supported(const AttnShape& a);  // additionally: Q, K, V, dO of one head + the P / dS tiles fit in shared memory
+int attn_bwd_hr(cudaStream_t s, const AttnShape& a, const bf16* q, const bf16* k, const bf16* v, const bf16* o_tok,
+                const bf16* do_tok, const float* lse, bf16* dqkv, int ld_dqkv, bf16* ddelta);
+
 // ------------------------------------------------------------------ lowrank.cu
 // KAdaptation factor expansion: from u1,u2 (rule*_left [32][32]), v1,v2 (rule*_right),
 // s (q_proj_adapter1_left [32][D/32]), t (q_proj_adapter1_right [32][D/32]) build

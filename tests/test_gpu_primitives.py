@@ -202,11 +202,18 @@ def torch_attention(q, k, v, T, qmat, bias, alpha, Lt, NB, H, D, r):
                                                 # L > 128: tcgen05 kernels composed over (query tile, key block) pairs
                                                 (197, 3, 768, 0, False), (257, 2, 1024, 0, False), (129, 2, 128, 0, False),
                                                 (256, 2, 128, 0, False), (300, 1, 128, 0, False), (384, 1, 128, 0, False),
-                                                (197, 40, 768, 0, False), (257, 20, 128, 0, False)])
-@pytest.mark.parametrize("impl", [0, 1])
+                                                (197, 40, 768, 0, False), (257, 20, 128, 0, False),
+                                                # tail tile of exactly 16 rows / a multiple of 16 (unmasked tail path),
+                                                # forward head-resident with ONE operand stage (L = 320: the backward
+                                                # operands no longer fit -> pair-streaming backward), many heads per CTA
+                                                (144, 2, 128, 0, False), (272, 3, 128, 0, False), (320, 2, 128, 0, False),
+                                                (208, 2, 128, 0, False), (257, 80, 128, 0, False)])
+@pytest.mark.parametrize("impl", [0, 1, 2])
 def test_attention_fwd_bwd(lib, Lt, NB, D, r, use_bias, impl):
-    if impl == 0 and r:
-        pytest.skip("impl 0 takes q', v' with the delta already applied (delta GEMM); covered by the block tests")
+    if impl != 1 and r:
+        pytest.skip("impl 0 / 2 take q', v' with the delta already applied (delta GEMM); covered by the block tests")
+    if impl == 2 and Lt <= 128:
+        pytest.skip("impl 2 differs from impl 0 only for L > 128 (pair-streaming instead of head-resident kernels)")
     if impl == 1 and Lt > 288:
         pytest.skip("the CUDA-core cross-check kernel keeps a whole score row in shared memory (L <= 288)")
     H, M = D // 64, Lt * NB
