@@ -129,6 +129,24 @@ int pevit_kad_factor_grads(const float* dP, const float* dQ, const float* u1, co
 int pevit_kad_factor_grads_acc(const float* dP, const float* dQ, const float* u1, const float* v1, const float* u2,
                                const float* v2, const float* s, const float* t, int32_t d, float* du1, float* dv1,
                                float* du2, float* dv2, float* ds, float* dt, void* stream);
+/* Compacter PHM layers (compacter_model.py:196-308, :302-308 the per-call einsum): both layers of one block expanded
+ * on the device into the bf16 operands of the bottleneck GEMMs -- W = H^T with H = sum_i kron(rule_i, left_i right_i).
+ * rule fp32 [n][n][n]; down: left [n][d/n], right [n][bottleneck/n]; up: left [n][bottleneck/n], right [n][d/n].
+ * Outputs bf16: w_down [bottleneck][d], w_down_t [d][bottleneck], w_up [d][bottleneck], w_up_t [bottleneck][d]. */
+int pevit_phm_expand(const float* rule, int32_t n, const float* down_left, const float* down_right, const float* up_left,
+                     const float* up_right, int32_t d, int32_t bottleneck, void* w_down, void* w_down_t, void* w_up,
+                     void* w_up_t, void* stream);
+/* Factor gradients (what autograd derives through the einsum) from pevit_block_bwd's dense d_w_down / d_w_up
+ * ([d][bottleneck] each).  d_rule (nullable: the shared rule is frozen in the reference driver, compacter_clip.py:122)
+ * is accumulated with atomics -- caller zeroes it or passes the .grad buffer; accumulate != 0: += on the others. */
+int pevit_phm_factor_grads(const float* d_w_down, const float* d_w_up, const float* rule, int32_t n, const float* down_left,
+                           const float* down_right, const float* up_left, const float* up_right, int32_t d,
+                           int32_t bottleneck, float* d_rule, float* d_down_left, float* d_down_right, float* d_up_left,
+                           float* d_up_right, int32_t accumulate, void* stream);
+/* Adapter (adapter_model.py:204-295): dense fp32 down [bottleneck][d] / up [d][bottleneck] -> the same four operands. */
+int pevit_bottleneck_pack(const float* w_down, const float* w_up, int32_t d, int32_t bottleneck, void* w_down_bf16,
+                          void* w_down_t, void* w_up_bf16, void* w_up_t, void* stream);
+
 /* ------------------------------------------------------------------ step tail
  * Linear head + CrossEntropyLoss (kadaptation_clip.py:176-185, :350): logits = feat W^T + b, *loss += mean over the
  * n samples of (logsumexp - logit[label]) (caller zeroes loss), dlogits = (softmax - onehot) / n.  fp32 throughout. */

@@ -154,8 +154,8 @@ class PHMLinear(nn.Module):
     def dense_weight(self) -> torch.Tensor:
         """H^T with H = sum_i kron(rule_i, left_i right_i)  (in x out), returned as (out, in).
 
-        A few hundred kB of host-side plumbing per layer; differentiable, so the factor gradients
-        come from autograd on the dense dH the block kernel returns.
+        Reference statement of compacter_model.py:302-308 for tests and inspection; the fused block does NOT call
+        it (``pevit_phm_expand`` builds the bf16 operands on the device).
         """
         n = self.phm_dim
         h = torch.einsum("iac,ik,ip->akcp", self.phm_rule, self.W_left[:, :, 0], self.W_right[:, 0, :])
@@ -183,9 +183,11 @@ class HyperComplexAdapter(nn.Module):
         self.adapter_down.apply(_bert_init)
 
     def peft_tensors(self) -> tuple:
-        down = self.adapter_down[1]
-        return (self.adapter_norm_before.weight, self.adapter_norm_before.bias, down.dense_weight(), down.b,
-                self.adapter_up.dense_weight(), self.adapter_up.b)
+        """LN affine, the shared rule and the raw PHM factors: the dense weights are expanded (and the factor
+        gradients contracted) on the device, ``pevit_phm_expand`` / ``pevit_phm_factor_grads``."""
+        down, up = self.adapter_down[1], self.adapter_up
+        return (self.adapter_norm_before.weight, self.adapter_norm_before.bias, down.phm_rule,
+                down.W_left, down.W_right, down.b, up.W_left, up.W_right, up.b)
 
 
 # --------------------------------------------------------------------------- blocks and towers

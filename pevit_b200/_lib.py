@@ -90,6 +90,10 @@ _SIGNATURES = {
     "pevit_colsum_bf16": (c_int32, [c_void_p, c_int32, c_int32, c_void_p, c_void_p]),
     "pevit_kad_factor_grads": (c_int32, [c_void_p] * 8 + [c_int32] + [c_void_p] * 7),
     "pevit_kad_factor_grads_acc": (c_int32, [c_void_p] * 8 + [c_int32] + [c_void_p] * 7),
+    "pevit_phm_expand": (c_int32, [c_void_p, c_int32] + [c_void_p] * 4 + [c_int32, c_int32] + [c_void_p] * 5),
+    "pevit_phm_factor_grads": (c_int32, [c_void_p] * 3 + [c_int32] + [c_void_p] * 4 + [c_int32, c_int32] + [c_void_p] * 5
+                               + [c_int32, c_void_p]),
+    "pevit_bottleneck_pack": (c_int32, [c_void_p, c_void_p, c_int32, c_int32] + [c_void_p] * 5),
     "pevit_head_ce_fwd": (c_int32, [c_void_p] * 4 + [c_int32] * 3 + [c_void_p] * 4),
     "pevit_head_ce_bwd": (c_int32, [c_void_p] * 4 + [c_int32] * 3 + [c_void_p] * 3 + [c_int32, c_void_p]),
     "pevit_sgd_momentum": (c_int32, [c_void_p] * 3 + [c_size_t] + [c_float] * 4 + [c_void_p]),

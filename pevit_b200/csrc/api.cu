@@ -243,6 +243,33 @@ int pevit_kad_factor_grads_acc(const float* dP, const float* dQ, const float* u1
   return kad_factor_grads(as_stream(stream), dP, dQ, u1, v1, u2, v2, s, t, d, du1, dv1, du2, dv2, ds, dt, true);
 }
 
+int pevit_phm_expand(const float* rule, int32_t n, const float* down_left, const float* down_right, const float* up_left,
+                     const float* up_right, int32_t d, int32_t bottleneck, void* w_down, void* w_down_t, void* w_up,
+                     void* w_up_t, void* stream) {
+  PEVIT_REQUIRE(rule && down_left && down_right && up_left && up_right && w_down && w_down_t && w_up && w_up_t,
+                "pevit_phm_expand: null pointer");
+  return phm_expand(as_stream(stream), rule, n, down_left, down_right, up_left, up_right, d, bottleneck,
+                    static_cast<bf16*>(w_down), static_cast<bf16*>(w_down_t), static_cast<bf16*>(w_up),
+                    static_cast<bf16*>(w_up_t));
+}
+
+int pevit_phm_factor_grads(const float* d_w_down, const float* d_w_up, const float* rule, int32_t n, const float* down_left,
+                           const float* down_right, const float* up_left, const float* up_right, int32_t d,
+                           int32_t bottleneck, float* d_rule, float* d_down_left, float* d_down_right, float* d_up_left,
+                           float* d_up_right, int32_t accumulate, void* stream) {
+  PEVIT_REQUIRE(d_w_down && d_w_up && rule && down_left && down_right && up_left && up_right && d_down_left &&
+                    d_down_right && d_up_left && d_up_right, "pevit_phm_factor_grads: null pointer");
+  return phm_factor_grads(as_stream(stream), d_w_down, d_w_up, rule, n, down_left, down_right, up_left, up_right, d,
+                          bottleneck, d_rule, d_down_left, d_down_right, d_up_left, d_up_right, accumulate != 0);
+}
+
+int pevit_bottleneck_pack(const float* w_down, const float* w_up, int32_t d, int32_t bottleneck, void* w_down_bf16,
+                          void* w_down_t, void* w_up_bf16, void* w_up_t, void* stream) {
+  PEVIT_REQUIRE(w_down && w_up && w_down_bf16 && w_down_t && w_up_bf16 && w_up_t, "pevit_bottleneck_pack: null pointer");
+  return bottleneck_pack(as_stream(stream), w_down, w_up, d, bottleneck, static_cast<bf16*>(w_down_bf16),
+                         static_cast<bf16*>(w_down_t), static_cast<bf16*>(w_up_bf16), static_cast<bf16*>(w_up_t));
+}
+
 int pevit_cast_bf16(const float* src, void* dst, size_t n, void* stream) {
   return cast_f32_to_bf16(as_stream(stream), src, static_cast<bf16*>(dst), n);
 }

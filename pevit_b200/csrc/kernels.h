@@ -126,6 +126,22 @@ int kad_factor_grads(cudaStream_t s, const float* dP, const float* dQ, const flo
 // dT (fp32 [M][r2 cols starting at col0]) -> bf16 into dqkv_ext[:, 3D+col0 ...]
 int cast_f32_to_bf16_2d(cudaStream_t s, const float* src, int lds, bf16* dst, int ldd, int rows, int cols);
 
+// ------------------------------------------------------------------ phm.cu
+// Compacter: expand both PHM layers of a block (down: D -> B, up: B -> D; rule [n][n][n], left [n][in/n], right
+// [n][out/n]) into the bf16 GEMM operands w_down [B][D], w_down_t [D][B], w_up [D][B], w_up_t [B][D].
+int phm_expand(cudaStream_t s, const float* rule, int n, const float* down_left, const float* down_right,
+               const float* up_left, const float* up_right, int D, int B, bf16* w_down, bf16* w_down_t, bf16* w_up,
+               bf16* w_up_t);
+// Factor gradients from the dense gradients of pevit_block_bwd (d_w_down [D][B] = dH_down, d_w_up [D][B] = dW_up);
+// d_rule (nullable) is accumulated atomically (shared by both layers and by every block); accumulate: += for the rest.
+int phm_factor_grads(cudaStream_t s, const float* d_w_down, const float* d_w_up, const float* rule, int n,
+                     const float* down_left, const float* down_right, const float* up_left, const float* up_right, int D,
+                     int B, float* d_rule, float* d_down_left, float* d_down_right, float* d_up_left, float* d_up_right,
+                     bool accumulate);
+// Adapter: fp32 dense down [B][D] / up [D][B] -> the same four bf16 operands.
+int bottleneck_pack(cudaStream_t s, const float* w_down, const float* w_up, int D, int B, bf16* o_down, bf16* o_down_t,
+                    bf16* o_up, bf16* o_up_t);
+
 // ------------------------------------------------------------------ stem.cu
 // Patch embedding + class token + positional embedding + ln_pre -> x (L, N, D) fp32 (model.py:1034-1042).
 // w_patch: bf16 [D][Kpad], Kpad = ceil8(3 p^2), the flattened conv1 weight zero-padded along K.

@@ -1,0 +1,172 @@
+// Bottleneck weight preparation for Adapter / Compacter, on the device.
+//
+// Compacter's PHMLinear (reference evaluation/compacter_model.py:196-308) builds its dense weight every call as
+//   H = sum_{i<n} kron(rule_i, left_i right_i),   H[a K + k][c P + p] = sum_i rule[i][a][c] left[i][k] right[i][p]
+// (n = 4, rank 1: left_i is (in/n) x 1, right_i is 1 x (out/n)) with a torch.einsum, and autograd walks back through
+// it.  Here one launch expands both PHM layers of a block straight into the bf16 operand layouts the bottleneck
+// GEMMs read (W = H^T as [out][in] and its transpose), and one launch contracts the dense gradients the block
+// backward produces into the factor gradients:
+//   dleft[i][k]  = sum_{a,c,p} dH[aK+k][cP+p] rule[i][a][c] right[i][p]
+//   dright[i][p] = sum_{a,c,k} dH[aK+k][cP+p] rule[i][a][c] left[i][k]
+//   drule[i][a][c] = sum_{k,p} dH[aK+k][cP+p] left[i][k] right[i][p]
+// The Adapter's dense down / up weights (adapter_model.py:204-295) only need the bf16 copies + transposes: one launch.
+#include "common.cuh"
+#include "kernels.h"
+
+namespace pevit {
+namespace {
+
+constexpr int PHM_MAXN = 8;
+
+struct PhmLayer {
+  const float* left;   // [n][in / n]
+  const float* right;  // [n][out / n]
+  int in_f, out_f;
+  bf16* w;             // [out][in]  = H^T   (B operand of y = x H)
+  bf16* w_t;           // [in][out]  = H     (B operand of the dgrad)
+};
+
+__global__ void __launch_bounds__(256)
+phm_expand_kernel(const float* __restrict__ rule, int n, PhmLayer l0, PhmLayer l1) {
+  pdl_launch_dependents();
+  pdl_wait();
+  const PhmLayer& l = blockIdx.y == 0 ? l0 : l1;
+  __shared__ float srule[PHM_MAXN * PHM_MAXN * PHM_MAXN];
+  for (int i = threadIdx.x; i < n * n * n; i += blockDim.x) srule[i] = rule[i];
+  __syncthreads();
+  const int K = l.in_f / n, P = l.out_f / n;
+  const int total = l.in_f * l.out_f;
+  for (int idx = blockIdx.x * blockDim.x + threadIdx.x; idx < total; idx += gridDim.x * blockDim.x) {
+    const int row = idx / l.out_f, col = idx - row * l.out_f;  // H[row][col]: row over in, col over out
+    const int a = row / K, k = row - a * K, c = col / P, p = col - c * P;
+    float h = 0.f;
+    for (int i = 0; i < n; ++i) h = fmaf(srule[(i * n + a) * n + c] * l.left[i * K + k], l.right[i * P + p], h);
+    const bf16 hb = __float2bfloat16(h);
+    l.w_t[static_cast<size_t>(row) * l.out_f + col] = hb;
+    l.w[static_cast<size_t>(col) * l.in_f + row] = hb;
+  }
+}
+
+struct PhmGradLayer {
+  const float* dh;     // dense gradient, see dh_out_in
+  int dh_out_in;       // 0: dh is dH [in][out];  1: dh is dW = dH^T [out][in]
+  const float* left;
+  const float* right;
+  int in_f, out_f;
+  float* dleft;
+  float* dright;
+};
+
+// one warp per output scalar; tasks of a layer: n K (dleft), n P (dright), n^3 (drule)
+__global__ void __launch_bounds__(256)
+phm_factor_grads_kernel(const float* __restrict__ rule, int n, PhmGradLayer l0, PhmGradLayer l1, float* __restrict__ drule,
+                        int accumulate) {
+  pdl_launch_dependents();
+  pdl_wait();
+  const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
+  const int K0 = l0.in_f / n, P0 = l0.out_f / n, K1 = l1.in_f / n, P1 = l1.out_f / n;
+  const int n3 = drule != nullptr ? n * n * n : 0;
+  const int tasks0 = n * K0 + n * P0 + n3, tasks1 = n * K1 + n * P1 + n3;
+  if (warp >= tasks0 + tasks1) return;
+  const bool second = warp >= tasks0;
+  const PhmGradLayer& l = second ? l1 : l0;
+  const int task = second ? warp - tasks0 : warp;
+  const int K = l.in_f / n, P = l.out_f / n;
+  auto dh_at = [&](int row, int col) {
+    return l.dh_out_in ? l.dh[static_cast<size_t>(col) * l.in_f + row] : l.dh[static_cast<size_t>(row) * l.out_f + col];
+  };
+  float g = 0.f;
+  if (task < n * K) {
+    const int i = task / K, k = task - i * K;
+    for (int e = lane; e < n * n * P; e += 32) {
+      const int a = e / (n * P), c = (e / P) % n, p = e % P;
+      g = fmaf(dh_at(a * K + k, c * P + p), rule[(i * n + a) * n + c] * l.right[i * P + p], g);
+    }
+    g = warp_sum(g);
+    if (lane == 0) l.dleft[task] = accumulate ? l.dleft[task] + g : g;
+  } else if (task < n * K + n * P) {
+    const int t2 = task - n * K;
+    const int i = t2 / P, p = t2 - i * P;
+    for (int e = lane; e < n * n * K; e += 32) {
+      const int a = e / (n * K), c = (e / K) % n, k = e % K;
+      g = fmaf(dh_at(a * K + k, c * P + p), rule[(i * n + a) * n + c] * l.left[i * K + k], g);
+    }
+    g = warp_sum(g);
+    if (lane == 0) l.dright[t2] = accumulate ? l.dright[t2] + g : g;
+  } else {
+    const int t3 = task - n * K - n * P;
+    const int i = t3 / (n * n), a = (t3 / n) % n, c = t3 % n;
+    for (int e = lane; e < K * P; e += 32) {
+      const int k = e / P, p = e - k * P;
+      g = fmaf(dh_at(a * K + k, c * P + p), l.left[i * K + k] * l.right[i * P + p], g);
+    }
+    g = warp_sum(g);
+    if (lane == 0) atomicAdd(drule + t3, g);  // both layers (and every block of the model) add into the shared rule
+  }
+}
+
+// Adapter: dense fp32 down [B][D] / up [D][B] -> bf16 operands and their transposes in one launch
+__global__ void __launch_bounds__(256)
+bottleneck_pack_kernel(const float* __restrict__ w_down, const float* __restrict__ w_up, int D, int B, bf16* __restrict__ o_down,
+                       bf16* __restrict__ o_down_t, bf16* __restrict__ o_up, bf16* __restrict__ o_up_t) {
+  pdl_launch_dependents();
+  pdl_wait();
+  const int total = D * B;
+  for (int idx = blockIdx.x * blockDim.x + threadIdx.x; idx < 2 * total; idx += gridDim.x * blockDim.x) {
+    if (idx < total) {  // w_down[b][d]
+      const int b = idx / D, d = idx - b * D;
+      const bf16 v = __float2bfloat16(w_down[idx]);
+      o_down[idx] = v;
+      o_down_t[static_cast<size_t>(d) * B + b] = v;
+    } else {            // w_up[d][b]
+      const int j = idx - total;
+      const int d = j / B, b = j - d * B;
+      const bf16 v = __float2bfloat16(w_up[j]);
+      o_up[j] = v;
+      o_up_t[static_cast<size_t>(b) * D + d] = v;
+    }
+  }
+}
+
+}  // namespace
+
+int phm_expand(cudaStream_t s, const float* rule, int n, const float* down_left, const float* down_right,
+               const float* up_left, const float* up_right, int D, int B, bf16* w_down, bf16* w_down_t, bf16* w_up,
+               bf16* w_up_t) {
+  PEVIT_REQUIRE(n >= 1 && n <= PHM_MAXN && D % n == 0 && B % n == 0, "phm_expand: n=%d must divide D=%d and %d", n, D, B);
+  PhmLayer dn{down_left, down_right, D, B, w_down, w_down_t};
+  PhmLayer up{up_left, up_right, B, D, w_up, w_up_t};
+  const int grid = (D * B + 255) / 256;
+  ProfScope prof(s, PC_EXPAND);
+  PEVIT_CHECK_CUDA(launch_kernel(phm_expand_kernel, dim3(grid, 2), dim3(256), 0, s, 1, rule, n, dn, up));
+  PEVIT_CHECK_LAUNCH();
+  return 0;
+}
+
+int phm_factor_grads(cudaStream_t s, const float* d_w_down, const float* d_w_up, const float* rule, int n,
+                     const float* down_left, const float* down_right, const float* up_left, const float* up_right, int D,
+                     int B, float* d_rule, float* d_down_left, float* d_down_right, float* d_up_left, float* d_up_right,
+                     bool accumulate) {
+  PEVIT_REQUIRE(n >= 1 && n <= PHM_MAXN && D % n == 0 && B % n == 0, "phm_factor_grads: n=%d must divide D=%d and %d", n, D, B);
+  // block backward layouts: d_w_down is [D][B] = dH_down ([in][out]); d_w_up is [D][B] = dW_up = dH_up^T ([out][in])
+  PhmGradLayer dn{d_w_down, 0, down_left, down_right, D, B, d_down_left, d_down_right};
+  PhmGradLayer up{d_w_up, 1, up_left, up_right, B, D, d_up_left, d_up_right};
+  const int n3 = d_rule != nullptr ? n * n * n : 0;
+  const int tasks = 2 * (n * (D / n) + n * (B / n) + n3);
+  ProfScope prof(s, PC_FACTOR_GRADS);
+  PEVIT_CHECK_CUDA(launch_kernel(phm_factor_grads_kernel, dim3((tasks + 7) / 8), dim3(256), 0, s, 1, rule, n, dn, up, d_rule,
+                                 accumulate ? 1 : 0));
+  PEVIT_CHECK_LAUNCH();
+  return 0;
+}
+
+int bottleneck_pack(cudaStream_t s, const float* w_down, const float* w_up, int D, int B, bf16* o_down, bf16* o_down_t,
+                    bf16* o_up, bf16* o_up_t) {
+  ProfScope prof(s, PC_EXPAND);
+  PEVIT_CHECK_CUDA(launch_kernel(bottleneck_pack_kernel, dim3((2 * D * B + 255) / 256), dim3(256), 0, s, 1, w_down, w_up, D, B,
+                                 o_down, o_down_t, o_up, o_up_t));
+  PEVIT_CHECK_LAUNCH();
+  return 0;
+}
+
+}  // namespace pevit

@@ -131,6 +131,12 @@ class BlockPack:
         self.expanded_ahead = False
         self.key = self.signature(block)
 
+    def dense_grad_scratch(self) -> torch.Tensor:
+        """fp32 [2][D][64]: dense dH_down | dW_up of one backward, contracted into the PHM factor gradients."""
+        if getattr(self, "_dense_scratch", None) is None:
+            self._dense_scratch = torch.zeros(2, self.D, BOTTLENECK, dtype=torch.float32, device=self.w_o.device)
+        return self._dense_scratch
+
     def grad_scratch(self) -> torch.Tensor:
         """fp32 [D*2r + 2*D*r]: dP | dQ accumulators of one backward (direct-accumulation mode)."""
         if self._grad_scratch is None:
@@ -183,9 +189,19 @@ def get_pack(block, method: str) -> BlockPack:
 
 
 def _expand_factors(pack: BlockPack, peft_c: tuple, st: int) -> None:
-    """Write the expanded low-rank operands (P^T rows of the in-projection, Q, alpha*Q) of one block."""
+    """Write the per-step operands derived from the PEFT tensors of one block: the expanded low-rank operands (P^T
+    rows of the in-projection, Q, alpha*Q) or the bf16 bottleneck weights (Compacter: PHM expansion)."""
     lib, D = L.lib(), pack.D
-    if pack.method == "kadaptation":
+    if pack.method == "compacter":
+        _, _, rule, dl, dr, _, ul, ur, _ = peft_c
+        L.check(lib.pevit_phm_expand(_ptr(rule), rule.shape[0], _ptr(dl), _ptr(dr), _ptr(ul), _ptr(ur), D, BOTTLENECK,
+                                     _ptr(pack.w_down), _ptr(pack.w_down_t), _ptr(pack.w_up), _ptr(pack.w_up_t), st),
+                "pevit_phm_expand")
+    elif pack.method == "adapter":
+        w_down, w_up = peft_c[2], peft_c[4]
+        L.check(lib.pevit_bottleneck_pack(_ptr(w_down), _ptr(w_up), D, BOTTLENECK, _ptr(pack.w_down), _ptr(pack.w_down_t),
+                                          _ptr(pack.w_up), _ptr(pack.w_up_t), st), "pevit_bottleneck_pack")
+    elif pack.method == "kadaptation":
         u1, v1, u2, v2, s, t = peft_c[:6]
         L.check(lib.pevit_kad_expand(_ptr(u1), _ptr(v1), _ptr(u2), _ptr(v2), _ptr(s), _ptr(t), D, pack.alpha,
                                      _ptr(pack.w_qkv_ext), _ptr(pack.w_qkv_ext_t), _ptr(pack.qmat),
@@ -204,7 +220,7 @@ def expand_ahead(blocks, method: str) -> None:
     """Run the factor expansions of ALL blocks now, on a side stream, so that these twelve latency-bound launches
     overlap the stem instead of sitting one by one on the critical path in front of every block.  The caller joins
     with ``join_side_stream()`` before the first block runs.  Each pack is flagged so the block skips its own."""
-    if method not in ("kadaptation", "lora") or not blocks:
+    if method not in ("kadaptation", "lora", "adapter", "compacter") or not blocks:
         return
     dev = blocks[0].attn.in_proj_weight.device
     main = torch.cuda.current_stream(dev)
@@ -246,18 +262,17 @@ class _BlockFn(torch.autograd.Function):
         x = _f32c(x)
         peft_c = tuple(_f32c(t.detach()) for t in peft)
         delta_bias = lna = b_down = b_up = None
-        if method in ("kadaptation", "lora"):
-            if pack.expanded_ahead:      # expand_ahead() already wrote this pack's factor operands on the side stream
+        if method != "plain":
+            if pack.expanded_ahead:      # expand_ahead() already wrote this pack's derived operands on the side stream
                 pack.expanded_ahead = False
             else:
                 _expand_factors(pack, peft_c, st)
-            if method == "kadaptation":
-                delta_bias = peft_c[6]
-        elif method in ("adapter", "compacter"):
-            g, bta, w_down, b_down, w_up, b_up = peft_c   # w_down [64][D], w_up [D][64] dense
-            lna = (g, bta)
-            pack.cast(w_down, pack.w_down); pack.transpose(w_down, pack.w_down_t, BOTTLENECK)
-            pack.cast(w_up, pack.w_up); pack.transpose(w_up, pack.w_up_t, D)
+        if method == "kadaptation":
+            delta_bias = peft_c[6]
+        elif method == "adapter":
+            lna, b_down, b_up = (peft_c[0], peft_c[1]), peft_c[3], peft_c[5]
+        elif method == "compacter":
+            lna, b_down, b_up = (peft_c[0], peft_c[1]), peft_c[5], peft_c[8]
         need_grad = any(ctx.needs_input_grad)
         desc = L.BlockDesc(Lt, NB, D, pack.H, METHOD_IDS[method], pack.r, pack.alpha, int(need_grad), attn_impl,
                            int(ctx.needs_input_grad[0]), out_tokens * NB)
@@ -268,7 +283,7 @@ class _BlockFn(torch.autograd.Function):
         L.check(lib.pevit_block_fwd(C.byref(desc), C.byref(w), _ptr(x), _ptr(y), _ptr(saved), _ptr(ws), st),
                 "pevit_block_fwd")
         ctx.pack, ctx.desc = pack, desc
-        ctx.live = peft if (_direct_grads[0] and method == "kadaptation") else None
+        ctx.live = peft if (_direct_grads[0] and method in ("kadaptation", "compacter")) else None
         ctx.save_for_backward(x, saved, *peft_c)
         return y
 
@@ -293,9 +308,13 @@ class _BlockFn(torch.autograd.Function):
         g = L.BlockGrads()
         delta_bias = lna = b_down = b_up = None
         live = ctx.live
-        direct = live is not None and all(
-            t.requires_grad and t.grad is not None and t.grad.is_contiguous() and t.grad.dtype == torch.float32
-            and t.grad.device == dev for t in live)
+
+        def _ready(t):
+            return (t.requires_grad and t.grad is not None and t.grad.is_contiguous() and t.grad.dtype == torch.float32
+                    and t.grad.device == dev)
+        # Compacter's shared rule (index 2) is frozen in the reference driver (F9): it only has to be ready if it trains
+        direct = live is not None and all(_ready(t) for i, t in enumerate(live)
+                                          if not (method == "compacter" and i == 2 and not t.requires_grad))
         if method in ("kadaptation", "lora"):
             if direct:  # one persistent scratch buffer for dP | dQ, zeroed by a single fill
                 scratch = pack.grad_scratch()
@@ -310,10 +329,22 @@ class _BlockFn(torch.autograd.Function):
                 g.d_bias = _ptr(d_bias)
                 delta_bias = peft_c[6]
         else:
-            lna = (peft_c[0], peft_c[1]); b_down, b_up = peft_c[3], peft_c[5]
-            d_lna_g, d_lna_b = torch.zeros(D, **f32), torch.zeros(D, **f32)
-            d_w_down_t, d_b_down = torch.zeros(D, BOTTLENECK, **f32), torch.zeros(BOTTLENECK, **f32)
-            d_w_up, d_b_up = torch.zeros(D, BOTTLENECK, **f32), torch.zeros(D, **f32)
+            compacter = method == "compacter"
+            lna = (peft_c[0], peft_c[1])
+            b_down, b_up = (peft_c[5], peft_c[8]) if compacter else (peft_c[3], peft_c[5])
+            # Compacter's rule is frozen in the reference driver (F9); a trainable rule is honoured
+            rule_live = live[2] if (direct and compacter) else None
+            need_rule = compacter and ctx.needs_input_grad[4 + 2]
+            if direct:   # every kernel below accumulates (atomics / +=): hand it the .grad buffers themselves
+                i_bd, i_bu = (5, 8)
+                d_lna_g, d_lna_b, d_b_down, d_b_up = live[0].grad, live[1].grad, live[i_bd].grad, live[i_bu].grad
+                scratch = pack.dense_grad_scratch()
+                scratch.zero_()
+                d_w_down_t, d_w_up = scratch[0], scratch[1]
+            else:
+                d_lna_g, d_lna_b = torch.zeros(D, **f32), torch.zeros(D, **f32)
+                d_w_down_t, d_b_down = torch.zeros(D, BOTTLENECK, **f32), torch.zeros(BOTTLENECK, **f32)
+                d_w_up, d_b_up = torch.zeros(D, BOTTLENECK, **f32), torch.zeros(D, **f32)
             g.d_lna_g, g.d_lna_b = _ptr(d_lna_g), _ptr(d_lna_b)
             g.d_w_down, g.d_b_down, g.d_w_up, g.d_b_up = _ptr(d_w_down_t), _ptr(d_b_down), _ptr(d_w_up), _ptr(d_b_up)
         w = pack.weights_struct(delta_bias, lna, b_down, b_up)
@@ -338,6 +369,19 @@ class _BlockFn(torch.autograd.Function):
         elif method == "lora":
             # P = A^T, Q = B  ->  dA = dP^T, dB = dQ   (lora_model.py:490-514)
             grads = (d_pmat[:, :r].t().contiguous(), d_qmat[0], d_pmat[:, r:].t().contiguous(), d_qmat[1])
+        elif method == "compacter":
+            # dense dH -> PHM factor gradients (compacter_model.py:302-308 differentiated)
+            _, _, rule, dl, dr, _, ul, ur, _ = peft_c
+            if direct:
+                outs = [live[i].grad for i in (3, 4, 6, 7)]
+                d_rule = rule_live.grad if need_rule else None
+            else:
+                outs = [torch.empty_like(t) for t in (dl, dr, ul, ur)]
+                d_rule = torch.zeros_like(rule) if need_rule else None
+            L.check(lib.pevit_phm_factor_grads(_ptr(d_w_down_t), _ptr(d_w_up), _ptr(rule), rule.shape[0], _ptr(dl), _ptr(dr),
+                                               _ptr(ul), _ptr(ur), D, BOTTLENECK, _ptr(d_rule), *(_ptr(o) for o in outs),
+                                               int(direct), st), "pevit_phm_factor_grads")
+            grads = (None,) * 9 if direct else (d_lna_g, d_lna_b, d_rule, outs[0], outs[1], d_b_down, outs[2], outs[3], d_b_up)
         else:
             grads = (d_lna_g, d_lna_b, d_w_down_t.t().contiguous(), d_b_down, d_w_up, d_b_up)
         return (dx, None, None, None, *grads)

@@ -439,3 +439,57 @@ def test_sgd_momentum_matches_torch(lib):
         ops.sgd_momentum_(p, grad, m, 0.05, 0.9, 1e-2, 0.5)
         torch.cuda.synchronize()
         assert rel_inf(p, p_ref.detach()) < 1e-6, step
+
+
+@pytest.mark.parametrize("D,B,n", [(768, 64, 4), (128, 64, 4), (1024, 64, 4), (96, 32, 2)])
+def test_phm_expand_and_factor_grads(lib, D, B, n):
+    """Compacter PHM layers (compacter_model.py:302-308: H = sum_i kron(rule_i, left_i right_i), per-call einsum +
+    autograd) against the device expansion and the factor-gradient contraction of the dense gradients."""
+    dev = "cuda"
+    g = torch.Generator(device=dev).manual_seed(D + B)
+    rule = (torch.rand(n, n, n, device=dev, generator=g) * 2 - 1).requires_grad_(True)
+    dl = torch.randn(n, D // n, 1, device=dev, generator=g).requires_grad_(True)
+    dr = torch.randn(n, 1, B // n, device=dev, generator=g).requires_grad_(True)
+    ul = torch.randn(n, B // n, 1, device=dev, generator=g).requires_grad_(True)
+    ur = torch.randn(n, 1, D // n, device=dev, generator=g).requires_grad_(True)
+
+    def dense(left, right, fin, fout):  # H (in x out), the reference einsum
+        return torch.einsum("iac,ik,ip->akcp", rule, left[:, :, 0], right[:, 0, :]).reshape(fin, fout)
+    h_down, h_up = dense(dl, dr, D, B), dense(ul, ur, B, D)
+    w_down, w_down_t = torch.empty(B, D, dtype=torch.bfloat16, device=dev), torch.empty(D, B, dtype=torch.bfloat16, device=dev)
+    w_up, w_up_t = torch.empty(D, B, dtype=torch.bfloat16, device=dev), torch.empty(B, D, dtype=torch.bfloat16, device=dev)
+    L.check(lib.pevit_phm_expand(rule.data_ptr(), n, dl.data_ptr(), dr.data_ptr(), ul.data_ptr(), ur.data_ptr(), D, B,
+                                 w_down.data_ptr(), w_down_t.data_ptr(), w_up.data_ptr(), w_up_t.data_ptr(), st()), "phm_expand")
+    torch.cuda.synchronize()
+    # one bf16 rounding of an fp32 sum whose order differs from the einsum's: half a bf16 ulp
+    assert rel_inf(w_down_t.float(), h_down.detach()) < 4e-3 and torch.equal(w_down, w_down_t.t().contiguous())
+    assert rel_inf(w_up_t.float(), h_up.detach()) < 4e-3 and torch.equal(w_up, w_up_t.t().contiguous())
+    # factor gradients from dense gradients in the layouts pevit_block_bwd produces
+    gd, gu = torch.randn(D, B, device=dev, generator=g), torch.randn(D, B, device=dev, generator=g)  # dH_down, dW_up
+    ((h_down * gd).sum() + (h_up * gu.t()).sum()).backward()
+    d_rule = torch.zeros(n, n, n, device=dev)
+    outs = [torch.empty_like(t) for t in (dl, dr, ul, ur)]
+    L.check(lib.pevit_phm_factor_grads(gd.data_ptr(), gu.data_ptr(), rule.data_ptr(), n, dl.data_ptr(), dr.data_ptr(),
+                                       ul.data_ptr(), ur.data_ptr(), D, B, d_rule.data_ptr(), *(o.data_ptr() for o in outs),
+                                       0, st()), "phm_factor_grads")
+    torch.cuda.synchronize()
+    for got, ref in zip([d_rule] + outs, (rule, dl, dr, ul, ur)):
+        assert rel_inf(got, ref.grad) < 2e-5
+    # accumulate form (+=) with a frozen rule (NULL d_rule)
+    acc = [torch.ones_like(t) for t in (dl, dr, ul, ur)]
+    L.check(lib.pevit_phm_factor_grads(gd.data_ptr(), gu.data_ptr(), rule.data_ptr(), n, dl.data_ptr(), dr.data_ptr(),
+                                       ul.data_ptr(), ur.data_ptr(), D, B, None, *(o.data_ptr() for o in acc), 1, st()),
+            "phm_factor_grads")
+    torch.cuda.synchronize()
+    for got, ref in zip(acc, (dl, dr, ul, ur)):
+        assert rel_inf(got - 1.0, ref.grad) < 2e-5
+
+
+def test_bottleneck_pack(lib):
+    D, B, dev = 768, 64, "cuda"
+    w_down, w_up = torch.randn(B, D, device=dev), torch.randn(D, B, device=dev)
+    o = [torch.empty(s, dtype=torch.bfloat16, device=dev) for s in ((B, D), (D, B), (D, B), (B, D))]
+    L.check(lib.pevit_bottleneck_pack(w_down.data_ptr(), w_up.data_ptr(), D, B, *(t.data_ptr() for t in o), st()), "pack")
+    torch.cuda.synchronize()
+    assert torch.equal(o[0], bf(w_down)) and torch.equal(o[1], bf(w_down.t().contiguous()))
+    assert torch.equal(o[2], bf(w_up)) and torch.equal(o[3], bf(w_up.t().contiguous()))
