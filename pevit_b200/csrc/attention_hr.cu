@@ -14,6 +14,8 @@
 //             key block.  A third warpgroup merges the blocks exactly (O = sum_j e^{m_j-m} O_j / sum_j e^{m_j-m} l_j),
 //             so the softmax warpgroups never wait for an epilogue.  Nothing is rescaled in TMEM, no partial touches HBM.
 //   backward  see the second half of this file.
+#include <cstdlib>
+
 #include "common.cuh"
 #include "kernels.h"
 
@@ -50,7 +52,8 @@ HrGeom make_geom(const AttnShape& a) {
 
 // ===================================================================================================== forward
 constexpr int HF_THREADS = 448;  // softmax WG0, softmax WG1, merge WG, TMA warp, MMA warp
-constexpr int HF_STATS_BYTES = 2 * HR_MAXT * 128 * 8;
+constexpr int HF_STATS_BYTES = 2 * HR_MAXT * 2 * 128 * 8;  // [tile parity][key block][warpgroup][row] (max, partial sum)
+constexpr int HF_XMAX_BYTES = 2 * 2 * 128 * 4;          // [S buffer][warpgroup][row] partial row maxima
 
 struct FwdHrParams {
   HrGeom g;
@@ -59,38 +62,45 @@ struct FwdHrParams {
   float* lse;
 };
 
-// one 32- or 16-column chunk of a score row: running max
-template <int W, bool MASK>
-__device__ __forceinline__ void chunk_max(uint32_t taddr, int c, int valid, float (&m4)[4]) {
-  uint32_t v[W];
-  if constexpr (W == 32) tmem_ld_32x32(taddr + c, v); else tmem_ld_32x16(taddr + c, v);
+// The <= 64 score columns one softmax thread owns (FULL: exactly 64, all valid).  One TMEM read per score: the row
+// statistics and the probabilities come out of registers (TMEM reads, 64 B/clk per SM, are this kernel's floor).
+template <bool FULL>
+__device__ __forceinline__ void load_scores(uint32_t taddr, int ncols, uint32_t (&v)[64]) {
+  if (FULL || ncols >= 32) tmem_ld_32x32(taddr, *reinterpret_cast<uint32_t(*)[32]>(&v[0]));
+  else if (ncols >= 16) tmem_ld_32x16(taddr, *reinterpret_cast<uint32_t(*)[16]>(&v[0]));
+  if (FULL || ncols == 64) tmem_ld_32x32(taddr + 32, *reinterpret_cast<uint32_t(*)[32]>(&v[32]));
+  else if (ncols == 48) tmem_ld_32x16(taddr + 32, *reinterpret_cast<uint32_t(*)[16]>(&v[32]));
   tmem_ld_wait();
-#pragma unroll
-  for (int i = 0; i < W; ++i) {
-    const float s = __uint_as_float(v[i]);
-    if (!MASK || c + i < valid) m4[i & 3] = fmaxf(m4[i & 3], s);
-  }
 }
-// one chunk: p = exp2(s * log2e - mxs), row sum, bf16 probabilities written back to TMEM at column pbase + c / 2
-template <int W, bool MASK>
-__device__ __forceinline__ void chunk_exp(uint32_t taddr, uint32_t pbase, int c, int valid, float mxs, float (&s4)[4]) {
-  uint32_t v[W];
-  if constexpr (W == 32) tmem_ld_32x32(taddr + c, v); else tmem_ld_32x16(taddr + c, v);
-  tmem_ld_wait();
-  uint32_t pk[W / 2];
+template <bool FULL>
+__device__ __forceinline__ float local_max(const uint32_t (&v)[64], int nvalid) {
+  float m4[4] = {-INFINITY, -INFINITY, -INFINITY, -INFINITY};
 #pragma unroll
-  for (int i = 0; i < W; i += 2) {
+  for (int i = 0; i < 64; ++i)
+    if (FULL || i < nvalid) m4[i & 3] = fmaxf(m4[i & 3], __uint_as_float(v[i]));
+  return fmaxf(fmaxf(m4[0], m4[1]), fmaxf(m4[2], m4[3]));
+}
+// p = exp2(s * log2e - mxs) packed to bf16 pairs and written back to TMEM at pbase; returns the row sum of this part
+template <bool FULL>
+__device__ __forceinline__ float exp_store(uint32_t pbase, int ncols, int nvalid, float mxs, const uint32_t (&v)[64]) {
+  float s4[4] = {0.f, 0.f, 0.f, 0.f};
+  uint32_t pk[32];
+#pragma unroll
+  for (int i = 0; i < 64; i += 2) {
     float e0 = fast_exp2(fmaf(__uint_as_float(v[i]), LOG2E, -mxs));
     float e1 = fast_exp2(fmaf(__uint_as_float(v[i + 1]), LOG2E, -mxs));
-    if (MASK) {
-      e0 = c + i < valid ? e0 : 0.f;
-      e1 = c + i + 1 < valid ? e1 : 0.f;
+    if (!FULL) {
+      e0 = i < nvalid ? e0 : 0.f;
+      e1 = i + 1 < nvalid ? e1 : 0.f;
     }
-    s4[i & 3] += e0;
-    s4[(i + 1) & 3] += e1;
+    s4[(i >> 1) & 3] += e0 + e1;
     pk[i >> 1] = pack_bf16(e0, e1);
   }
-  if constexpr (W == 32) tmem_st_32x16(pbase + (c >> 1), pk); else tmem_st_32x8(pbase + (c >> 1), pk);
+  if (FULL || ncols >= 32) tmem_st_32x16(pbase, *reinterpret_cast<const uint32_t(*)[16]>(&pk[0]));
+  else if (ncols >= 16) tmem_st_32x8(pbase, *reinterpret_cast<const uint32_t(*)[8]>(&pk[0]));
+  if (FULL || ncols == 64) tmem_st_32x16(pbase + 16, *reinterpret_cast<const uint32_t(*)[16]>(&pk[16]));
+  else if (ncols == 48) tmem_st_32x8(pbase + 16, *reinterpret_cast<const uint32_t(*)[8]>(&pk[16]));
+  return (s4[0] + s4[1]) + (s4[2] + s4[3]);
 }
 
 __global__ void __launch_bounds__(HF_THREADS, 1)
@@ -101,12 +111,13 @@ attn_fwd_hr_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_consta
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   const HrGeom& G = p.g;
   const int stage_bytes = 3 * G.tensor_bytes;
-  float2* stats = reinterpret_cast<float2*>(smem + p.nstage * stage_bytes);  // [tile parity][block j][row] = (max, sum)
-  uint64_t* bars = reinterpret_cast<uint64_t*>(reinterpret_cast<uint8_t*>(stats) + HF_STATS_BYTES);
+  float2* stats = reinterpret_cast<float2*>(smem + p.nstage * stage_bytes);
+  float* xmax = reinterpret_cast<float*>(reinterpret_cast<uint8_t*>(stats) + HF_STATS_BYTES);
+  uint64_t* bars = reinterpret_cast<uint64_t*>(reinterpret_cast<uint8_t*>(xmax) + HF_XMAX_BYTES);
   uint64_t* full = bars;             // [2] head operands landed
   uint64_t* empty = full + 2;        // [2] every MMA of the head has completed
   uint64_t* s_full = empty + 2;      // [2] S_b ready (MMA -> softmax warpgroup b)
-  uint64_t* p_full = s_full + 2;     // [2] P_b written back to TMEM (128 arrivals)
+  uint64_t* p_full = s_full + 2;     // [2] P_b written back to TMEM (256 arrivals)
   uint64_t* o_full = p_full + 2;     // every O_j of the query tile accumulated
   uint64_t* o_empty = o_full + 1;    // merge warpgroup has read the O_j (128 arrivals)
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(o_empty + 1);
@@ -130,7 +141,7 @@ attn_fwd_hr_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_consta
     tma_prefetch_desc(&tm_qt); tma_prefetch_desc(&tm_kt); tma_prefetch_desc(&tm_vt);
     for (int s = 0; s < 2; ++s) {
       mbar_init(&full[s], 1); mbar_init(&empty[s], 1);
-      mbar_init(&s_full[s], 1); mbar_init(&p_full[s], 128);
+      mbar_init(&s_full[s], 1); mbar_init(&p_full[s], 256);
     }
     mbar_init(o_full, 1);
     mbar_init(o_empty, 128);
@@ -147,7 +158,8 @@ attn_fwd_hr_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_consta
   const uint32_t tmem_base = *tmem_slot;
   pdl_launch_dependents();
   pdl_wait();
-  // TMEM columns: S0 [0,128)  S1 [128,256)  (P_b: bf16 pairs over the first 64 columns of S_b)  O_j [256 + 64 j, +64)
+  // TMEM columns: S0 [0,128)  S1 [128,256)  O_j [256 + 64 j, +64).  P_b: bf16 pairs written by each softmax warpgroup over
+  // the start of ITS OWN half of S_b (keys 0..63 -> S_b + [0,32), keys 64..127 -> S_b + 64 + [0,32))
 
   if (warp == 12) {
     // ------------------------------------------------------------ TMA producer: one head per stage
@@ -162,11 +174,12 @@ attn_fwd_hr_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_consta
         tma_prefetch_l2_3d(&tm_qt, 0, (nt - 1) * 128, g_); tma_prefetch_l2_3d(&tm_kt, 0, (nt - 1) * 128, g_);
         tma_prefetch_l2_3d(&tm_vt, 0, (nt - 1) * 128, g_);
       };
-      for (int k_ = p.nstage; k_ < p.nstage + 2; ++k_) prefetch_head(k_);
+      // one head beyond the shared-memory stages: measured with 4 heads ahead, the ~60 MB of prefetched operands in
+      // flight across 148 CTAs thrashed L2 (DRAM reads 1.8x the algorithmic bytes)
       for (int k = 0; k < n_local; ++k) {
         const int g = blockIdx.x + k * gridDim.x;
         const int s = k % p.nstage;
-        prefetch_head(k + p.nstage + 2);
+        prefetch_head(k + p.nstage);
         mbar_wait(&empty[s], ((k / p.nstage) & 1) ^ 1);
         uint8_t* st = smem + s * stage_bytes;
         mbar_expect_tx(&full[s], static_cast<uint32_t>(stage_bytes));
@@ -211,7 +224,7 @@ attn_fwd_hr_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_consta
         constexpr uint32_t idesc = umma_idesc_bf16(128, 64) | IDESC_B_MN;
         const int ksteps = hr_rows16(G, j) >> 4;
         for (int kk = 0; kk < ksteps; ++kk)  // A = P_b: 16 keys = 8 TMEM columns per step; B = V_j (64 d contiguous per key)
-          umma_bf16_ts(tmem_base + 256 + j * 64, tmem_base + b * 128 + kk * 8,
+          umma_bf16_ts(tmem_base + 256 + j * 64, tmem_base + b * 128 + (kk >> 2) * 64 + (kk & 3) * 8,
                        umma_desc_mnmajor_sw128(sv + kk * 2048, TILE_BYTES), idesc, kk != 0);
         if (j == nt - 1) umma_commit(o_full);
         if (r == pairs_per_item - 1) umma_commit(&empty[s]);
@@ -229,45 +242,41 @@ attn_fwd_hr_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_consta
       issue_pv(pi);
     }
   } else if (warp < 8) {
-    // ------------------------------------------------------------ softmax warpgroups (alternate pairs)
+    // ------------------------------------------------------------ softmax: both warpgroups on every pair, 64 keys each
     const int grp = warp >> 2, quad = warp & 3;
     const int row = quad * 32 + lane;
-    const uint32_t t_row = tmem_base + (static_cast<uint32_t>(quad * 32) << 16) + grp * 128;
-    for (int pi = grp; pi < n_pairs; pi += 2) {
+    for (int pi = 0; pi < n_pairs; ++pi) {
       const int k = pi / pairs_per_item, r = pi - k * pairs_per_item;
       const int t = r / nt, j = r - t * nt;
-      const int tc = k * nt + t;
-      const int kw = hr_rows16(G, j), valid = hr_rows(G, j);
+      const int tc = k * nt + t, b = pi & 1;
+      const int kw = hr_rows16(G, j), kvalid = hr_rows(G, j);
+      const int ncols = max(0, min(64, kw - 64 * grp)), nvalid = max(0, min(64, kvalid - 64 * grp));
       const bool active = quad * 32 < hr_rows(G, t);  // warp-uniform: some row of this warp is a real query
-      mbar_wait(&s_full[grp], (pi >> 1) & 1);
+      const uint32_t t_row = tmem_base + (static_cast<uint32_t>(quad * 32) << 16) + b * 128 + grp * 64;
+      float* xm = xmax + b * 256;
+      mbar_wait(&s_full[b], (pi >> 1) & 1);
       tc_fence_after();
+      uint32_t v[64];
+      float mloc = -INFINITY;
+      const bool full = nvalid == 64;
+      if (active && ncols > 0) {
+        if (full) { load_scores<true>(t_row, ncols, v); mloc = local_max<true>(v, nvalid); }
+        else { load_scores<false>(t_row, ncols, v); mloc = local_max<false>(v, nvalid); }
+      }
+      xm[grp * 128 + row] = mloc;
+      named_bar_sync(1, 256);  // the other warpgroup's half of every row maximum
       if (active) {
-        float m4[4] = {-INFINITY, -INFINITY, -INFINITY, -INFINITY};
-        int c = 0;
-        for (; c + 32 <= kw; c += 32) {
-          if (c + 32 <= valid) chunk_max<32, false>(t_row, c, valid, m4);
-          else chunk_max<32, true>(t_row, c, valid, m4);
+        const float mx = fmaxf(mloc, xm[(grp ^ 1) * 128 + row]);
+        float sum = 0.f;
+        if (ncols > 0) {
+          if (full) sum = exp_store<true>(t_row, ncols, nvalid, mx * LOG2E, v);
+          else sum = exp_store<false>(t_row, ncols, nvalid, mx * LOG2E, v);
         }
-        if (c < kw) {
-          if (c + 16 <= valid) chunk_max<16, false>(t_row, c, valid, m4);
-          else chunk_max<16, true>(t_row, c, valid, m4);
-        }
-        const float mx = fmaxf(fmaxf(m4[0], m4[1]), fmaxf(m4[2], m4[3]));
-        const float mxs = mx * LOG2E;
-        float s4[4] = {0.f, 0.f, 0.f, 0.f};
-        for (c = 0; c + 32 <= kw; c += 32) {
-          if (c + 32 <= valid) chunk_exp<32, false>(t_row, t_row, c, valid, mxs, s4);
-          else chunk_exp<32, true>(t_row, t_row, c, valid, mxs, s4);
-        }
-        if (c < kw) {
-          if (c + 16 <= valid) chunk_exp<16, false>(t_row, t_row, c, valid, mxs, s4);
-          else chunk_exp<16, true>(t_row, t_row, c, valid, mxs, s4);
-        }
-        stats[((tc & 1) * HR_MAXT + j) * 128 + row] = make_float2(mx, (s4[0] + s4[1]) + (s4[2] + s4[3]));
+        stats[(((tc & 1) * HR_MAXT + j) * 2 + grp) * 128 + row] = make_float2(mx, sum);
         tmem_st_wait();
       }
       tc_fence_before();
-      mbar_arrive(&p_full[grp]);
+      mbar_arrive(&p_full[b]);
     }
   } else {
     // ------------------------------------------------------------ merge warpgroup: O = sum_j w_j O_j / l
@@ -283,16 +292,16 @@ attn_fwd_hr_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_consta
       mbar_wait(o_full, tc & 1);
       tc_fence_after();
       if (active) {
-        const float2* st = stats + (tc & 1) * HR_MAXT * 128 + row;
+        const float2* st = stats + (tc & 1) * HR_MAXT * 256 + row;  // [j][warpgroup][row]
         float mj[HR_MAXT], w[HR_MAXT], m = -INFINITY, l = 0.f;
 #pragma unroll
         for (int j = 0; j < HR_MAXT; ++j) {
           mj[j] = -INFINITY; w[j] = 0.f;
-          if (j < nt) { mj[j] = st[j * 128].x; m = fmaxf(m, mj[j]); }
+          if (j < nt) { mj[j] = st[j * 256].x; m = fmaxf(m, mj[j]); }
         }
 #pragma unroll
         for (int j = 0; j < HR_MAXT; ++j)
-          if (j < nt) { w[j] = fast_exp2((mj[j] - m) * LOG2E); l = fmaf(w[j], st[j * 128].y, l); }
+          if (j < nt) { w[j] = fast_exp2((mj[j] - m) * LOG2E); l = fmaf(w[j], st[j * 256].y + st[j * 256 + 128].y, l); }
         const float inv = 1.f / l;
         const bool valid = lq < L;
         const int n = g / G.H, h = g - n * G.H;
@@ -479,11 +488,10 @@ attn_bwd_hr_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_consta
           tma_prefetch_l2_4d(tl ? &tm_ot : &tm_o, 0, h_, n_, i * 128);
         }
       };
-      prefetch_head(1);
       for (int k = 0; k < n_local; ++k) {
         const int g = blockIdx.x + k * gridDim.x;
         const int n = g / G.H, h = g - n * G.H;
-        prefetch_head(k + 2);
+        prefetch_head(k + 1);  // one head ahead only: deeper prefetching thrashed L2 (see the forward kernel)
         mbar_wait(empty, (k & 1) ^ 1);
         mbar_expect_tx(full, static_cast<uint32_t>(5 * TB));
         for (int i = 0; i < nt; ++i) {
@@ -720,6 +728,407 @@ attn_bwd_hr_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_consta
   }
 }
 
+
+// ===================================================================================================== backward, v2
+// Same residency and the same accumulators as above, but in the TRANSPOSED orientation and in half-tile units, so that
+// the exponentials of one unit overlap the tensor work of the previous one and the probabilities never visit shared
+// memory:
+//   unit  = (query tile t, 64-row half h, key block j).  TMEM buffer b = unit & 1 (two of them: 2 x 128 columns):
+//   MMA1  S^T = K_j Q_{t,h}^T -> b*128 + [0,64),  dP^T = V_j dO_{t,h}^T -> b*128 + [64,128)   (M = 128 keys, N = <= 64 rows)
+//   WG0/1 one thread per KEY lane, the warpgroups split the 64 query columns: P^T = exp(S^T - lse_q),
+//         dS^T = P^T o (dP^T - delta_q); both written back into TMEM over the columns just read (bf16 pairs), dS^T also
+//         into a [128 keys][128 rows] shared-memory tile
+//   MMA2  dV_j += P^T dO_{t,h}, dK_j += dS^T Q_{t,h}: tcgen05.mma with the A operand in TMEM; after the tile's last half
+//         dQ_t += dS_t K_j from the shared-memory tile (A read MN-major)
+// While the warpgroups work on unit u+1 (TMEM-read bound: 64 KB per unit at 64 B/clk), the tensor pipe runs MMA2(u) and
+// MMA1(u+2); v1 above serialises the two phases.
+struct HrUnit { int t, j, tt, h, nq, flags, pair, pad; };
+enum { U_FIRST_KV = 1, U_LAST_KV = 2, U_FIRST_GRP = 4, U_LAST_GRP = 8, U_LAST_HALF = 16, U_LAST = 32 };
+constexpr int HB2_MAX_UNITS = 24;
+
+__global__ void __launch_bounds__(HB_THREADS, 1)
+attn_bwd_hr2_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant__ CUtensorMap tm_k,
+                    const __grid_constant__ CUtensorMap tm_v, const __grid_constant__ CUtensorMap tm_do,
+                    const __grid_constant__ CUtensorMap tm_o, const __grid_constant__ CUtensorMap tm_qt,
+                    const __grid_constant__ CUtensorMap tm_kt, const __grid_constant__ CUtensorMap tm_vt,
+                    const __grid_constant__ CUtensorMap tm_dot, const __grid_constant__ CUtensorMap tm_ot, BwdHrParams p) {
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  const HrGeom& G = p.g;
+  const int TB = G.tensor_bytes;
+  uint8_t* sQ = smem;
+  uint8_t* sK = smem + TB;
+  uint8_t* sV = smem + 2 * TB;
+  uint8_t* sdO = smem + 3 * TB;
+  uint8_t* sDS = smem + 4 * TB;      // [pair parity][q half][128 key rows][64 query cols] bf16: dS^T of the current pairs
+  uint8_t* sO = sDS;                 // O tiles of the head, only until delta is formed
+  float* vecs = reinterpret_cast<float*>(sDS + 4 * TILE_BYTES);  // [parity][0: delta, 1: lse * log2e][384]
+  HrUnit* units = reinterpret_cast<HrUnit*>(reinterpret_cast<uint8_t*>(vecs) + HB_VEC_BYTES);
+  uint64_t* bars = reinterpret_cast<uint64_t*>(units + HB2_MAX_UNITS);
+  uint64_t* full = bars;               // head operands landed
+  uint64_t* empty = full + 1;          // every MMA of the head has completed
+  uint64_t* s_full = empty + 1;        // [2] MMA1 of a unit done
+  uint64_t* pds_full = s_full + 2;     // [2] P^T, dS^T of a unit written (256 arrivals)
+  uint64_t* ds_free = pds_full + 2;    // [2] dQ MMA of a pair done reading its dS^T tile
+  uint64_t* kv_full = ds_free + 2;     // dK_j, dV_j complete (all tiles of the group)
+  uint64_t* kv_empty = kv_full + 1;    // WG2 drained dK_j, dV_j (128 arrivals)
+  uint64_t* dq_full = kv_empty + 1;    // dQ of the group's tiles complete (all key blocks)
+  uint64_t* dq_empty = dq_full + 1;    // WG2 drained dQ (128 arrivals)
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(dq_empty + 1);
+  int* n_units_s = reinterpret_cast<int*>(tmem_slot + 1);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int nt = G.nt, L = G.L;
+  const int ngroups = (nt + 1) / 2;
+  const int n_local = (G.heads - static_cast<int>(blockIdx.x) + static_cast<int>(gridDim.x) - 1) /
+                      static_cast<int>(gridDim.x);
+  auto tiles_in_group = [&](int tg) { return min(2, nt - 2 * tg); };
+
+  {
+    uint4* z = reinterpret_cast<uint4*>(smem);
+    const int n16 = (4 * TB + 4 * TILE_BYTES) / 16;
+    for (int i = threadIdx.x; i < n16; i += HB_THREADS) z[i] = make_uint4(0, 0, 0, 0);
+  }
+  if (threadIdx.x == 0) {  // the unit sequence of one head (identical for every head)
+    int n = 0, pair = 0;
+    for (int tg = 0; tg < ngroups; ++tg) {
+      const int ntg = tiles_in_group(tg);
+      for (int j = 0; j < nt; ++j) {
+        for (int tt = 0; tt < ntg; ++tt, ++pair) {
+          const int t = 2 * tg + tt;
+          const int r16 = hr_rows16(G, t);
+          const int nh = r16 > 64 ? 2 : 1;
+          for (int h = 0; h < nh; ++h, ++n) {
+            HrUnit u{t, j, tt, h, min(64, r16 - 64 * h), 0, pair, 0};
+            if (tt == 0 && h == 0) u.flags |= U_FIRST_KV;
+            if (tt == ntg - 1 && h == nh - 1) u.flags |= U_LAST_KV;
+            if (j == 0 && tt == 0 && h == 0) u.flags |= U_FIRST_GRP;
+            if (j == nt - 1 && tt == ntg - 1 && h == nh - 1) u.flags |= U_LAST_GRP;
+            if (h == nh - 1) u.flags |= U_LAST_HALF;
+            if (tg == ngroups - 1 && j == nt - 1 && tt == ntg - 1 && h == nh - 1) u.flags |= U_LAST;
+            units[n] = u;
+          }
+        }
+      }
+    }
+    *n_units_s = n;
+  }
+  if (warp == 12 && lane == 0) {
+    tma_prefetch_desc(&tm_q); tma_prefetch_desc(&tm_k); tma_prefetch_desc(&tm_v); tma_prefetch_desc(&tm_do);
+    tma_prefetch_desc(&tm_o); tma_prefetch_desc(&tm_qt); tma_prefetch_desc(&tm_kt); tma_prefetch_desc(&tm_vt);
+    tma_prefetch_desc(&tm_dot); tma_prefetch_desc(&tm_ot);
+    mbar_init(full, 1); mbar_init(empty, 1);
+    for (int b = 0; b < 2; ++b) { mbar_init(&s_full[b], 1); mbar_init(&pds_full[b], 256); mbar_init(&ds_free[b], 1); }
+    mbar_init(kv_full, 1); mbar_init(kv_empty, 128); mbar_init(dq_full, 1); mbar_init(dq_empty, 128);
+    fence_mbar_init();
+  }
+  if (warp == 13) {
+    tmem_alloc(tmem_slot, 512);
+    tmem_relinquish();
+  }
+  fence_proxy_async_smem();
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+  const int n_units = *n_units_s;
+  const int pairs_per_head = units[n_units - 1].pair + 1;
+  pdl_launch_dependents();
+  pdl_wait();
+  // TMEM columns: buffer b: S^T [128 b, +64), dP^T [128 b + 64, +64);  dV_j [256,320) dK_j [320,384) dQ_tt [384 + 64 tt, +64)
+
+  if (warp == 12) {
+    // ------------------------------------------------------------ TMA producer
+    if (lane == 0) {
+      auto prefetch_head = [&](int k_) {
+        if (k_ >= n_local) return;
+        const int g_ = blockIdx.x + k_ * gridDim.x;
+        const int n_ = g_ / G.H, h_ = g_ - n_ * G.H;
+        for (int i = 0; i < nt; ++i) {
+          const bool tl = i == nt - 1;
+          tma_prefetch_l2_3d(tl ? &tm_qt : &tm_q, 0, i * 128, g_);
+          tma_prefetch_l2_3d(tl ? &tm_kt : &tm_k, 0, i * 128, g_);
+          tma_prefetch_l2_3d(tl ? &tm_vt : &tm_v, 0, i * 128, g_);
+          tma_prefetch_l2_4d(tl ? &tm_dot : &tm_do, 0, h_, n_, i * 128);
+          tma_prefetch_l2_4d(tl ? &tm_ot : &tm_o, 0, h_, n_, i * 128);
+        }
+      };
+      for (int k = 0; k < n_local; ++k) {
+        const int g = blockIdx.x + k * gridDim.x;
+        const int n = g / G.H, h = g - n * G.H;
+        prefetch_head(k + 1);
+        mbar_wait(empty, (k & 1) ^ 1);
+        mbar_expect_tx(full, static_cast<uint32_t>(5 * TB));
+        for (int i = 0; i < nt; ++i) {
+          const bool tl = i == nt - 1;
+          tma_load_4d(sO + i * TILE_BYTES, tl ? &tm_ot : &tm_o, full, 0, h, n, i * 128);
+          tma_load_4d(sdO + i * TILE_BYTES, tl ? &tm_dot : &tm_do, full, 0, h, n, i * 128);
+          tma_load_3d(sQ + i * TILE_BYTES, tl ? &tm_qt : &tm_q, full, 0, i * 128, g);
+          tma_load_3d(sK + i * TILE_BYTES, tl ? &tm_kt : &tm_k, full, 0, i * 128, g);
+          tma_load_3d(sV + i * TILE_BYTES, tl ? &tm_vt : &tm_v, full, 0, i * 128, g);
+        }
+      }
+    }
+  } else if (warp == 13) {
+    // ------------------------------------------------------------ MMA issuer
+    constexpr uint32_t idesc_ts = umma_idesc_bf16(128, 64) | IDESC_B_MN;               // A in TMEM, B = [rows][64 d]
+    constexpr uint32_t idesc_dq = umma_idesc_bf16(128, 64) | IDESC_A_MN | IDESC_B_MN;  // A = dS^T tile read transposed
+    const uint32_t aQ = smem_u32(sQ), aK = smem_u32(sK), aV = smem_u32(sV), aDO = smem_u32(sdO), aDS = smem_u32(sDS);
+    long long ug = 0;  // units issued (MMA1) so far, over all heads
+    auto issue_mma1 = [&](const HrUnit& u, long long idx) {
+      const int b = static_cast<int>(idx & 1);
+      if (lane == 0) {
+        const uint32_t idesc = umma_idesc_bf16(128, u.nq);
+        const uint32_t roff = u.t * TILE_BYTES + u.h * 64 * 128;
+        const uint64_t dk = umma_desc_kmajor_sw128(aK + u.j * TILE_BYTES), dv = umma_desc_kmajor_sw128(aV + u.j * TILE_BYTES);
+        const uint64_t dq = umma_desc_kmajor_sw128(aQ + roff), ddo = umma_desc_kmajor_sw128(aDO + roff);
+#pragma unroll
+        for (int kk = 0; kk < 4; ++kk) umma_bf16_ss(tmem_base + b * 128, dk + 2 * kk, dq + 2 * kk, idesc, kk != 0);
+#pragma unroll
+        for (int kk = 0; kk < 4; ++kk) umma_bf16_ss(tmem_base + b * 128 + 64, dv + 2 * kk, ddo + 2 * kk, idesc, kk != 0);
+        umma_commit(&s_full[b]);
+      }
+      __syncwarp();
+    };
+    long long uc = 0;   // units completed (MMA2 issued)
+    int kvc = 0, gc = 0;
+    for (int k = 0; k < n_local; ++k) {
+      mbar_wait(full, k & 1);
+      tc_fence_after();
+      issue_mma1(units[0], ug++);
+      if (n_units > 1) issue_mma1(units[1], ug++);
+      for (int ui = 0; ui < n_units; ++ui, ++uc) {
+        const HrUnit u = units[ui];
+        const int b = static_cast<int>(uc & 1);
+        const long long pg = static_cast<long long>(k) * pairs_per_head + u.pair;  // pair counter over all heads
+        mbar_wait(&pds_full[b], static_cast<uint32_t>((uc >> 1) & 1));
+        if (u.flags & U_FIRST_KV) mbar_wait(kv_empty, (kvc & 1) ^ 1);   // dK / dV accumulators drained (previous block)
+        if (u.flags & U_FIRST_GRP) mbar_wait(dq_empty, (gc & 1) ^ 1);   // dQ accumulators drained (previous group)
+        tc_fence_after();
+        if (lane == 0) {
+          const uint32_t rows = u.t * TILE_BYTES + u.h * 64 * 128;  // first row of this half inside dO / Q
+          const int qsteps = u.nq >> 4;
+          for (int kk = 0; kk < qsteps; ++kk)   // dV_j (+)= P^T dO_{t,h}   (K = query rows of the half, 16 per step)
+            umma_bf16_ts(tmem_base + 256, tmem_base + b * 128 + (kk >> 1) * 32 + (kk & 1) * 8,
+                         umma_desc_mnmajor_sw128(aDO + rows + kk * 2048, TILE_BYTES), idesc_ts,
+                         (!(u.flags & U_FIRST_KV) || kk != 0) ? 1u : 0u);
+          for (int kk = 0; kk < qsteps; ++kk)   // dK_j (+)= dS^T Q_{t,h}
+            umma_bf16_ts(tmem_base + 320, tmem_base + b * 128 + 64 + (kk >> 1) * 32 + (kk & 1) * 8,
+                         umma_desc_mnmajor_sw128(aQ + rows + kk * 2048, TILE_BYTES), idesc_ts,
+                         (!(u.flags & U_FIRST_KV) || kk != 0) ? 1u : 0u);
+          if (u.flags & U_LAST_HALF) {          // dQ_t (+)= dS_t K_j       (K = stored keys of block j)
+            const uint32_t ds = aDS + static_cast<uint32_t>(pg & 1) * 2 * TILE_BYTES;
+            const int ksteps = hr_rows16(G, u.j) >> 4;
+            for (int kk = 0; kk < ksteps; ++kk)
+              umma_bf16_ss(tmem_base + 384 + u.tt * 64, umma_desc_mnmajor_sw128(ds + kk * 2048, TILE_BYTES),
+                           umma_desc_mnmajor_sw128(aK + u.j * TILE_BYTES + kk * 2048, TILE_BYTES), idesc_dq,
+                           (u.j | kk) != 0 ? 1u : 0u);
+            umma_commit(&ds_free[pg & 1]);
+          }
+          if (u.flags & U_LAST_KV) umma_commit(kv_full);
+          if (u.flags & U_LAST_GRP) umma_commit(dq_full);
+          if (u.flags & U_LAST) umma_commit(empty);
+        }
+        __syncwarp();
+        if (u.flags & U_LAST_KV) ++kvc;
+        if (u.flags & U_LAST_GRP) ++gc;
+        if (ui + 2 < n_units) issue_mma1(units[ui + 2], ug++);  // into the buffer this unit has just released (in order)
+      }
+    }
+  } else if (warp < 8) {
+    // ------------------------------------------------------------ WG0 / WG1: delta, then P^T and dS^T of every unit
+    const int wg = warp >> 2, quad = warp & 3;
+    const int row = quad * 32 + lane;  // key lane
+    const int tid = threadIdx.x;       // 0..255
+    const uint32_t t_lane = tmem_base + (static_cast<uint32_t>(quad * 32) << 16);
+    long long uc = 0;
+    for (int k = 0; k < n_local; ++k) {
+      const int g = blockIdx.x + k * gridDim.x;
+      float* vdelta = vecs + (k & 1) * 2 * 128 * HR_MAXT;
+      float* vlse = vdelta + 128 * HR_MAXT;
+      float lse_r[2];
+#pragma unroll
+      for (int i = 0; i < 2; ++i) {
+        const int l = tid + i * 256;
+        lse_r[i] = l < L ? p.lse[static_cast<size_t>(g) * L + l] * LOG2E : 0.f;
+      }
+      mbar_wait(full, k & 1);
+#pragma unroll
+      for (int i = 0; i < 2; ++i) {
+        const int l = tid + i * 256;
+        if (l < 128 * HR_MAXT) {
+          float d = 0.f;
+          if (l < L) {
+            const uint8_t* pdo = sdO + (l >> 7) * TILE_BYTES + (l & 127) * 128;
+            const uint8_t* po = sO + (l >> 7) * TILE_BYTES + (l & 127) * 128;
+#pragma unroll
+            for (int c = 0; c < 8; ++c) {
+              const uint4 a = *reinterpret_cast<const uint4*>(pdo + c * 16);
+              const uint4 bq = *reinterpret_cast<const uint4*>(po + c * 16);
+              const uint32_t aw[4] = {a.x, a.y, a.z, a.w}, bw[4] = {bq.x, bq.y, bq.z, bq.w};
+#pragma unroll
+              for (int q = 0; q < 4; ++q) {
+                const float2 fa = unpack_bf16(aw[q]), fb = unpack_bf16(bw[q]);
+                d = fmaf(fa.x, fb.x, fmaf(fa.y, fb.y, d));
+              }
+            }
+          }
+          vdelta[l] = d;                       // rows at or beyond L: zeros (their probabilities are masked anyway)
+          vlse[l] = l < L ? lse_r[i] : 0.f;
+        }
+      }
+      named_bar_sync(1, 256);  // delta / lse of the head visible to both warpgroups; the O tiles may now be overwritten
+      for (int ui = 0; ui < n_units; ++ui, ++uc) {
+        const HrUnit u = units[ui];
+        const int b = static_cast<int>(uc & 1);
+        const long long pg = static_cast<long long>(k) * pairs_per_head + u.pair;
+        const int kw = hr_rows16(G, u.j), kvalid = hr_rows(G, u.j);
+        const bool active = quad * 32 < kw;       // warp holds key lanes the dQ product reads (real or zero padding)
+        const bool key_valid = row < kvalid;
+        const int q0 = u.h * 64 + wg * 32;         // first query row (within the tile) of this thread's columns
+        const int ncols = max(0, min(32, u.nq - wg * 32));
+        const int qvalid = hr_rows(G, u.t) - q0;   // columns < qvalid are real query rows
+        mbar_wait(&s_full[b], static_cast<uint32_t>((uc >> 1) & 1));
+        tc_fence_after();
+        // the dS^T tile of this pair was last read by the dQ product two pairs ago
+        if (u.h == 0) mbar_wait(&ds_free[pg & 1], static_cast<uint32_t>(((pg >> 1) & 1) ^ 1));
+        if (active && ncols > 0) {
+          const uint32_t ts = t_lane + b * 128 + wg * 32, tdp = ts + 64;
+          uint32_t sv[32], dv[32];
+          if (ncols == 32) { tmem_ld_32x32(ts, sv); tmem_ld_32x32(tdp, dv); }
+          else { tmem_ld_32x16(ts, *reinterpret_cast<uint32_t(*)[16]>(&sv[0])); tmem_ld_32x16(tdp, *reinterpret_cast<uint32_t(*)[16]>(&dv[0])); }
+          tmem_ld_wait();
+          const float* pl = vlse + u.t * 128 + q0;
+          const float* pd = vdelta + u.t * 128 + q0;
+          uint32_t pp[16], pds[16];
+          uint8_t* srow = sDS + static_cast<uint32_t>(pg & 1) * 2 * TILE_BYTES + u.h * TILE_BYTES + row * 128;
+#pragma unroll
+          for (int q = 0; q < 4; ++q) {
+            if (q * 8 < ncols) {
+              const float4 l0 = *reinterpret_cast<const float4*>(pl + 8 * q), l1 = *reinterpret_cast<const float4*>(pl + 8 * q + 4);
+              const float4 d0 = *reinterpret_cast<const float4*>(pd + 8 * q), d1 = *reinterpret_cast<const float4*>(pd + 8 * q + 4);
+              const float ls[8] = {l0.x, l0.y, l0.z, l0.w, l1.x, l1.y, l1.z, l1.w};
+              const float dl[8] = {d0.x, d0.y, d0.z, d0.w, d1.x, d1.y, d1.z, d1.w};
+              float pj[8], ds[8];
+#pragma unroll
+              for (int i = 0; i < 8; ++i) {
+                const int c = 8 * q + i;
+                const float e = (key_valid && c < qvalid) ? fast_exp2(fmaf(__uint_as_float(sv[c]), LOG2E, -ls[i])) : 0.f;
+                pj[i] = e;
+                ds[i] = e * (__uint_as_float(dv[c]) - dl[i]);
+              }
+#pragma unroll
+              for (int i = 0; i < 4; ++i) {
+                pp[4 * q + i] = pack_bf16(pj[2 * i], pj[2 * i + 1]);
+                pds[4 * q + i] = pack_bf16(ds[2 * i], ds[2 * i + 1]);
+              }
+              const int ch = wg * 4 + q;  // 16-byte chunk of the 64 query columns of this half
+              *reinterpret_cast<uint4*>(srow + ((ch ^ (row & 7)) << 4)) = make_uint4(pds[4 * q], pds[4 * q + 1], pds[4 * q + 2], pds[4 * q + 3]);
+            }
+          }
+          if (ncols == 32) { tmem_st_32x16(ts, pp); tmem_st_32x16(tdp, pds); }
+          else { tmem_st_32x8(ts, *reinterpret_cast<const uint32_t(*)[8]>(&pp[0])); tmem_st_32x8(tdp, *reinterpret_cast<const uint32_t(*)[8]>(&pds[0])); }
+          tmem_st_wait();
+        }
+        fence_proxy_async_smem();
+        tc_fence_before();
+        mbar_arrive(&pds_full[b]);
+      }
+    }
+  } else {
+    // ------------------------------------------------------------ WG2: gradients out (same accumulators as v1)
+    const int quad = warp & 3;
+    const int row = quad * 32 + lane;
+    const uint32_t t_row = tmem_base + (static_cast<uint32_t>(quad * 32) << 16);
+    const size_t plane = static_cast<size_t>(G.heads) * L * 64;
+    int kvc = 0, gc = 0;
+    for (int k = 0; k < n_local; ++k) {
+      const int g = blockIdx.x + k * gridDim.x;
+      const int n = g / G.H, h = g - n * G.H;
+      for (int tg = 0; tg < ngroups; ++tg, ++gc) {
+        const int ntg = tiles_in_group(tg);
+        const bool add_prev = tg > 0;
+        for (int j = 0; j < nt; ++j, ++kvc) {
+          const int lk = j * 128 + row;
+          const bool valid = row < hr_rows(G, j);
+          const bool active = quad * 32 < hr_rows(G, j);
+          bf16* tok = p.dqkv + (static_cast<size_t>(valid ? lk : 0) * G.NB + n) * p.ld + h * 64;
+          bf16* hm = p.ddelta != nullptr ? p.ddelta + plane + (static_cast<size_t>(g) * L + (valid ? lk : 0)) * 64 : nullptr;
+          mbar_wait(kv_full, kvc & 1);
+          tc_fence_after();
+          if (active) {
+#pragma unroll 1
+            for (int part = 0; part < 2; ++part) {  // 0: dV', 1: dK
+              bf16* dst_tok = tok + (part == 0 ? 2 * G.D : G.D);
+#pragma unroll
+              for (int c = 0; c < 64; c += 32) {
+                uint32_t v[32];
+                tmem_ld_32x32(t_row + 256 + part * 64 + c, v);
+                tmem_ld_wait();
+                if (valid) {
+#pragma unroll
+                  for (int jj = 0; jj < 32; jj += 8) {
+                    float f[8];
+#pragma unroll
+                    for (int t8 = 0; t8 < 8; ++t8) f[t8] = __uint_as_float(v[jj + t8]);
+                    if (add_prev) add_bf16x8(f, *reinterpret_cast<const uint4*>(dst_tok + c + jj));
+                    const uint4 o = make_uint4(pack_bf16(f[0], f[1]), pack_bf16(f[2], f[3]), pack_bf16(f[4], f[5]),
+                                               pack_bf16(f[6], f[7]));
+                    *reinterpret_cast<uint4*>(dst_tok + c + jj) = o;
+                    if (part == 0 && hm != nullptr) *reinterpret_cast<uint4*>(hm + c + jj) = o;
+                  }
+                }
+              }
+            }
+          }
+          tc_fence_before();
+          mbar_arrive(kv_empty);
+        }
+        mbar_wait(dq_full, gc & 1);
+        tc_fence_after();
+        for (int tt = 0; tt < ntg; ++tt) {
+          const int t = 2 * tg + tt;
+          const int lq = t * 128 + row;
+          const bool valid = row < hr_rows(G, t);
+          if (quad * 32 < hr_rows(G, t)) {
+            bf16* dst_tok = p.dqkv + (static_cast<size_t>(valid ? lq : 0) * G.NB + n) * p.ld + h * 64;
+            bf16* dst_hm = p.ddelta != nullptr ? p.ddelta + (static_cast<size_t>(g) * L + (valid ? lq : 0)) * 64 : nullptr;
+#pragma unroll
+            for (int c = 0; c < 64; c += 32) {
+              uint32_t v[32];
+              tmem_ld_32x32(t_row + 384 + tt * 64 + c, v);
+              tmem_ld_wait();
+              if (valid) {
+#pragma unroll
+                for (int jj = 0; jj < 32; jj += 8) {
+                  float f[8];
+#pragma unroll
+                  for (int t8 = 0; t8 < 8; ++t8) f[t8] = __uint_as_float(v[jj + t8]);
+                  *reinterpret_cast<uint4*>(dst_tok + c + jj) =
+                      make_uint4(pack_bf16(f[0] * 0.125f, f[1] * 0.125f), pack_bf16(f[2] * 0.125f, f[3] * 0.125f),
+                                 pack_bf16(f[4] * 0.125f, f[5] * 0.125f), pack_bf16(f[6] * 0.125f, f[7] * 0.125f));
+                  if (dst_hm != nullptr)
+                    *reinterpret_cast<uint4*>(dst_hm + c + jj) = make_uint4(pack_bf16(f[0], f[1]), pack_bf16(f[2], f[3]),
+                                                                           pack_bf16(f[4], f[5]), pack_bf16(f[6], f[7]));
+                }
+              }
+            }
+          }
+        }
+        tc_fence_before();
+        mbar_arrive(dq_empty);
+      }
+    }
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 13) {
+    tc_fence_after();
+    tmem_dealloc(tmem_base, 512);
+  }
+}
+
 }  // namespace
 
 bool attn_hr_supported(const AttnShape& a) { return a.r == 0 && a.L > 128 && a.L <= 128 * HR_MAXT && a.H * 64 == a.D; }
@@ -735,7 +1144,7 @@ int attn_fwd_hr(cudaStream_t s, const AttnShape& a, const bf16* q, const bf16* k
   if (make_tmap_bf16_hm3d(&tkt, k, a.L, g.heads, g.tail16) != 0) return -1;
   if (make_tmap_bf16_hm3d(&tvt, v, a.L, g.heads, g.tail16) != 0) return -1;
   const int stage_bytes = 3 * g.tensor_bytes;
-  const int fixed = HF_STATS_BYTES + 256 + 1024;
+  const int fixed = HF_STATS_BYTES + HF_XMAX_BYTES + 256 + 1024;
   const int nstage = (227 * 1024 - fixed) / stage_bytes >= 2 ? 2 : 1;
   const int smem_bytes = nstage * stage_bytes + fixed;
   FwdHrParams p{g, nstage, o_tok, lse};
@@ -756,7 +1165,8 @@ int attn_fwd_hr(cudaStream_t s, const AttnShape& a, const bf16* q, const bf16* k
 bool attn_bwd_hr_supported(const AttnShape& a) {
   if (!attn_hr_supported(a)) return false;
   const HrGeom g = make_geom(a);
-  return 4 * g.tensor_bytes + 4 * TILE_BYTES + HB_VEC_BYTES + 256 + 1024 <= 227 * 1024 && a.L <= 512;
+  return 4 * g.tensor_bytes + 4 * TILE_BYTES + HB_VEC_BYTES + HB2_MAX_UNITS * static_cast<int>(sizeof(HrUnit)) + 256 + 1024 <= 227 * 1024 &&
+         a.L <= 384;
 }
 
 int attn_bwd_hr(cudaStream_t s, const AttnShape& a, const bf16* q, const bf16* k, const bf16* v, const bf16* o_tok,
@@ -775,19 +1185,21 @@ int attn_bwd_hr(cudaStream_t s, const AttnShape& a, const bf16* q, const bf16* k
   if (make_tmap_bf16_tok_heads(&to, o_tok, a.L, a.NB, a.H, a.D, 128) != 0) return -1;
   if (make_tmap_bf16_tok_heads(&tdot, do_tok, a.L, a.NB, a.H, a.D, g.tail16) != 0) return -1;
   if (make_tmap_bf16_tok_heads(&tot, o_tok, a.L, a.NB, a.H, a.D, g.tail16) != 0) return -1;
-  const int smem_bytes = 4 * g.tensor_bytes + 4 * TILE_BYTES + HB_VEC_BYTES + 256 + 1024;
+  const int smem_bytes = 4 * g.tensor_bytes + 4 * TILE_BYTES + HB_VEC_BYTES + HB2_MAX_UNITS * static_cast<int>(sizeof(HrUnit)) + 256 + 1024;
   BwdHrParams p{g, ld_dqkv, lse, dqkv, ddelta};
+  static const bool use_v1 = getenv("PEVIT_ATTN_BWD_V1") != nullptr;  // diagnostics: the serialised first version
   const int grid = g.heads < sm_count() ? g.heads : sm_count();
   static bool configured[64] = {};
   int dev = 0;
   PEVIT_CHECK_CUDA(cudaGetDevice(&dev));
   if (!configured[dev & 63]) {
     PEVIT_CHECK_CUDA(cudaFuncSetAttribute(attn_bwd_hr_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+    PEVIT_CHECK_CUDA(cudaFuncSetAttribute(attn_bwd_hr2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
     configured[dev & 63] = true;
   }
   ProfScope prof(s, PC_ATTN_BWD);
-  PEVIT_CHECK_CUDA(launch_kernel(attn_bwd_hr_kernel, dim3(grid), dim3(HB_THREADS), smem_bytes, s, 1, tq, tk, tv, tdo, to, tqt,
-                                 tkt, tvt, tdot, tot, p));
+  PEVIT_CHECK_CUDA(launch_kernel(use_v1 ? attn_bwd_hr_kernel : attn_bwd_hr2_kernel, dim3(grid), dim3(HB_THREADS), smem_bytes, s, 1,
+                                 tq, tk, tv, tdo, to, tqt, tkt, tvt, tdot, tot, p));
   PEVIT_CHECK_LAUNCH();
   return 0;
 }

@@ -1,13 +1,16 @@
 #!/usr/bin/env python
 """Top stall sites of an ncu report's SASS source page (one section per captured kernel).
-usage: sass_stalls.py report.ncu-rep [topN]"""
+usage: sass_stalls.py report.ncu-rep|source_page.csv [topN]"""
 import csv
 import subprocess
 import sys
 
 rep = sys.argv[1]
 topn = int(sys.argv[2]) if len(sys.argv) > 2 else 40
-out = subprocess.run(["ncu", "-i", rep, "--page", "source", "--csv", "--print-source", "sass"], capture_output=True, text=True).stdout
+if rep.endswith(".csv"):   # an already exported source page (tools/r02_*.sh export it on the box: reports are ~16 MB each)
+    out = open(rep).read()
+else:
+    out = subprocess.run(["ncu", "-i", rep, "--page", "source", "--csv", "--print-source", "sass"], capture_output=True, text=True).stdout
 rows = list(csv.reader(out.splitlines()))
 sections, cur = [], None
 for r in rows:
