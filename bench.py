@@ -45,6 +45,9 @@ def parse():
     ap.add_argument("--method", default="kadaptation", choices=["kadaptation", "lora", "adapter", "compacter"])
     ap.add_argument("--model", default="vit_b32", choices=["vit_b32", "vit_b16", "vit_l14"])
     ap.add_argument("--batch", type=int, default=256, help="images per GPU per step")
+    ap.add_argument("--global-batch", type=int, default=0,
+                    help="strong scaling: fixed images per step over ALL GPUs (per-GPU batch = global / N); 0 = weak "
+                         "scaling with --batch images per GPU (the driver's default)")
     ap.add_argument("--cpu-batch", type=int, default=0,
                     help="images per CPU-baseline step (0 = the full --batch: same configuration as the GPU arm)")
     ap.add_argument("--ref-device", default="cpu", choices=["cpu", "cuda"],
@@ -69,7 +72,8 @@ def workload(args, shape):
                         f"batch {args.batch}/GPU", "backbone": args.model, "peft": args.method,
             "images_per_gpu_step": args.batch, "images_per_step": args.batch * args.gpus, "tokens": shape.tokens,
             "width": shape.vision_width, "layers": shape.vision_layers, "parallelism": f"dp{args.gpus}",
-            "l2_policy": "inputs larger than L2 (154 MB fp32 image batch, >3 GB of saved activations per step)"}
+            "l2_policy": f"inputs larger than L2 ({args.batch * 3 * shape.image_resolution ** 2 * 4 / 1e6:.0f} MB fp32 image "
+                         "batch and GBs of saved activations per step stream through the 126 MB L2)"}
 
 
 # ----------------------------------------------------------------------------- clocks
@@ -253,7 +257,7 @@ def run_reference(args):
                                if on_gpu else "host CPU")
     line = {"impl": "reference", "metric": METRIC, "value": ips, "unit": "images/s", "n_gpus": args.gpus,
             "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * total / args.steps,
-            "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "higher_is_better": True, "scaling": args.scaling, "vs_baseline": None,
             "dtype": "bf16-autocast" if (on_gpu and args.ref_autocast) else "f32", "data": "synthetic",
             "config": cfg,
             "cpu_baseline": {"value": ips, "unit": "images/s", "cores": torch.get_num_threads(), "kind": "port",
@@ -484,7 +488,7 @@ def run_b200(args):
                   "ceiling_images_per_s_per_gpu": sustained * 1e12 / (fwd_flops + bwd_flops)}
     line = {
         "metric": METRIC, "value": value, "unit": "images/s", "n_gpus": world, "steps": args.steps,
-        "warmup": max(args.warmup, 3), "ms_per_step": ms_step, "higher_is_better": True, "scaling": "weak",
+        "warmup": max(args.warmup, 3), "ms_per_step": ms_step, "higher_is_better": True, "scaling": args.scaling,
         "vs_baseline": None, "dtype": "bf16", "data": "synthetic", "config": workload(args, shape),
         "clocks": clocks.summary(t_wall0, t_wall2) if clocks else None,
         "e2e": {"value": e2e_value, "unit": "images/s", "ms_per_step": ms_e2e / args.steps,
@@ -540,6 +544,16 @@ def finish(world: int) -> None:
         threading.Thread(target=watchdog, daemon=True).start()
 
 
+def resolve_scaling(args) -> None:
+    """--global-batch G: strong scaling (global 2048 on ViT-B/32, N = G / world per GPU)."""
+    args.scaling = "weak"
+    if args.global_batch > 0:
+        if args.global_batch % args.gpus:
+            raise SystemExit(f"--global-batch {args.global_batch} is not divisible by --gpus {args.gpus}")
+        args.batch = args.global_batch // args.gpus
+        args.scaling = "strong"
+
+
 def main():
     import signal
 
@@ -549,6 +563,7 @@ def main():
     signal.signal(signal.SIGALRM, on_alarm)
     signal.alarm(1500)
     args = parse()
+    resolve_scaling(args)
     if args.impl == "reference":
         run_reference(args)
     else:

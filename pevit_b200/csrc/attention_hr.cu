@@ -14,6 +14,7 @@
 //             key block.  A third warpgroup merges the blocks exactly (O = sum_j e^{m_j-m} O_j / sum_j e^{m_j-m} l_j),
 //             so the softmax warpgroups never wait for an epilogue.  Nothing is rescaled in TMEM, no partial touches HBM.
 //   backward  see the second half of this file.
+#include <cstdio>
 #include <cstdlib>
 
 #include "common.cuh"
@@ -31,6 +32,46 @@ __device__ __forceinline__ float fast_exp2(float x) {
   asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
   return y;
 }
+
+// Diagnostics (PEVIT_ATTN_TRACE=<file>): CTA 0 records (clock64 << 8 | event id) per warp into a global buffer that the
+// host dumps after the launch; tools/attn_trace.py turns it into a per-role timeline.  Null pointer = off (one
+// predictable branch per event).
+constexpr int TRACE_EVENTS = 1024;  // per warp
+struct Tracer {
+  unsigned long long* buf;
+  int n;
+  __device__ __forceinline__ Tracer(unsigned long long* base, int warp)
+      : buf(base != nullptr && blockIdx.x == 0 && (threadIdx.x & 31) == 0 ? base + warp * TRACE_EVENTS : nullptr), n(0) {}
+  __device__ __forceinline__ void operator()(int id) {
+    if (buf != nullptr && n < TRACE_EVENTS) buf[n++] = (static_cast<unsigned long long>(clock64()) << 8) | static_cast<unsigned>(id);
+  }
+};
+struct TraceHost {
+  unsigned long long* dev = nullptr;
+  const char* path = nullptr;
+  int warps = 0;
+  unsigned long long* begin(int nwarps) {
+    path = getenv("PEVIT_ATTN_TRACE");
+    if (path == nullptr) return nullptr;
+    warps = nwarps;
+    if (cudaMalloc(&dev, sizeof(unsigned long long) * TRACE_EVENTS * nwarps) != cudaSuccess) return dev = nullptr;
+    cudaMemset(dev, 0, sizeof(unsigned long long) * TRACE_EVENTS * nwarps);
+    return dev;
+  }
+  void end(cudaStream_t s, const char* tag) {
+    if (dev == nullptr) return;
+    cudaStreamSynchronize(s);
+    const size_t n = static_cast<size_t>(TRACE_EVENTS) * warps;
+    unsigned long long* host = static_cast<unsigned long long*>(malloc(n * sizeof(unsigned long long)));
+    cudaMemcpy(host, dev, n * sizeof(unsigned long long), cudaMemcpyDeviceToHost);
+    char name[512];
+    snprintf(name, sizeof(name), "%s.%s.bin", path, tag);
+    if (FILE* f = fopen(name, "wb")) { fwrite(&warps, sizeof(int), 1, f); fwrite(host, sizeof(unsigned long long), n, f); fclose(f); }
+    free(host);
+    cudaFree(dev);
+    dev = nullptr;
+  }
+};
 
 // Geometry of one head's operands in shared memory: nt tiles, the last one `tail` valid rows stored as tail16 rows.
 struct HrGeom {
@@ -60,6 +101,7 @@ struct FwdHrParams {
   int nstage;
   bf16* o_tok;
   float* lse;
+  unsigned long long* trace;
 };
 
 // The <= 64 score columns one softmax thread owns (FULL: exactly 64, all valid).  One TMEM read per score: the row
@@ -128,6 +170,7 @@ attn_fwd_hr_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_consta
                       static_cast<int>(gridDim.x);
   const int pairs_per_item = nt * nt;
   const int n_pairs = n_local * pairs_per_item;
+  Tracer tr(p.trace, warp);
 
   // Rows of the tail tile beyond tail16 are never written by TMA but are read by the M = 128 MMAs: they must hold
   // finite values (their results are discarded), so the operand area starts out as zeros.
@@ -181,6 +224,7 @@ attn_fwd_hr_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_consta
         const int s = k % p.nstage;
         prefetch_head(k + p.nstage);
         mbar_wait(&empty[s], ((k / p.nstage) & 1) ^ 1);
+        tr(30);
         uint8_t* st = smem + s * stage_bytes;
         mbar_expect_tx(&full[s], static_cast<uint32_t>(stage_bytes));
         // first pair's operands first
@@ -198,8 +242,9 @@ attn_fwd_hr_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_consta
       const int k = pi / pairs_per_item, r = pi - k * pairs_per_item;
       const int t = r / nt, j = r - t * nt;
       const int s = k % p.nstage, b = pi & 1;
-      if (r == 0) mbar_wait(&full[s], (k / p.nstage) & 1);
+      if (r == 0) { mbar_wait(&full[s], (k / p.nstage) & 1); tr(1); }
       tc_fence_after();
+      tr(2);
       if (lane == 0) {
         const uint32_t st = smem_u32(smem + s * stage_bytes);
         const uint64_t dq = umma_desc_kmajor_sw128(st + t * TILE_BYTES);
@@ -217,7 +262,8 @@ attn_fwd_hr_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_consta
       const int s = k % p.nstage, b = pi & 1;
       const int tc = k * nt + t;
       mbar_wait(&p_full[b], (pi >> 1) & 1);
-      if (j == 0) mbar_wait(o_empty, (tc & 1) ^ 1);  // the merge warpgroup has drained the previous tile's O_j
+      tr(3);
+      if (j == 0) { mbar_wait(o_empty, (tc & 1) ^ 1); tr(5); }  // the merge warpgroup has drained the previous tile's O_j
       tc_fence_after();
       if (lane == 0) {
         const uint32_t sv = smem_u32(smem + s * stage_bytes + 2 * G.tensor_bytes + j * TILE_BYTES);
@@ -230,6 +276,7 @@ attn_fwd_hr_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_consta
         if (r == pairs_per_item - 1) umma_commit(&empty[s]);
       }
       __syncwarp();
+      tr(4);
     };
     // S runs one pair ahead of P V (S_(b^1)'s previous reader, the P V product of pair pi-1, is already issued).  With
     // a single operand stage the look-ahead must not cross into the next head: its load only starts once this
@@ -256,6 +303,7 @@ attn_fwd_hr_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_consta
       float* xm = xmax + b * 256;
       mbar_wait(&s_full[b], (pi >> 1) & 1);
       tc_fence_after();
+      tr(10);
       uint32_t v[64];
       float mloc = -INFINITY;
       const bool full = nvalid == 64;
@@ -264,7 +312,9 @@ attn_fwd_hr_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_consta
         else { load_scores<false>(t_row, ncols, v); mloc = local_max<false>(v, nvalid); }
       }
       xm[grp * 128 + row] = mloc;
+      tr(11);
       named_bar_sync(1, 256);  // the other warpgroup's half of every row maximum
+      tr(12);
       if (active) {
         const float mx = fmaxf(mloc, xm[(grp ^ 1) * 128 + row]);
         float sum = 0.f;
@@ -273,10 +323,12 @@ attn_fwd_hr_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_consta
           else sum = exp_store<false>(t_row, ncols, nvalid, mx * LOG2E, v);
         }
         stats[(((tc & 1) * HR_MAXT + j) * 2 + grp) * 128 + row] = make_float2(mx, sum);
+        tr(13);
         tmem_st_wait();
       }
       tc_fence_before();
       mbar_arrive(&p_full[b]);
+      tr(14);
     }
   } else {
     // ------------------------------------------------------------ merge warpgroup: O = sum_j w_j O_j / l
@@ -291,6 +343,7 @@ attn_fwd_hr_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_consta
       const int lq = t * 128 + row;
       mbar_wait(o_full, tc & 1);
       tc_fence_after();
+      tr(20);
       if (active) {
         const float2* st = stats + (tc & 1) * HR_MAXT * 256 + row;  // [j][warpgroup][row]
         float mj[HR_MAXT], w[HR_MAXT], m = -INFINITY, l = 0.f;
@@ -335,6 +388,7 @@ attn_fwd_hr_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_consta
           }
         }
         if (valid) p.lse[static_cast<size_t>(g) * L + lq] = m + __logf(l);
+        tr(22);
       } else {
         tc_fence_before();
         mbar_arrive(o_empty);
@@ -369,6 +423,7 @@ struct BwdHrParams {
   const float* lse;
   bf16* dqkv;
   bf16* ddelta;  // nullable
+  unsigned long long* trace;
 };
 
 __device__ __forceinline__ void add_bf16x8(float (&f)[8], const uint4& x) {
@@ -783,6 +838,7 @@ attn_bwd_hr2_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_const
   const int n_local = (G.heads - static_cast<int>(blockIdx.x) + static_cast<int>(gridDim.x) - 1) /
                       static_cast<int>(gridDim.x);
   auto tiles_in_group = [&](int tg) { return min(2, nt - 2 * tg); };
+  Tracer tr(p.trace, warp);
 
   {
     uint4* z = reinterpret_cast<uint4*>(smem);
@@ -858,6 +914,7 @@ attn_bwd_hr2_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_const
         const int n = g / G.H, h = g - n * G.H;
         prefetch_head(k + 1);
         mbar_wait(empty, (k & 1) ^ 1);
+        tr(30);
         mbar_expect_tx(full, static_cast<uint32_t>(5 * TB));
         for (int i = 0; i < nt; ++i) {
           const bool tl = i == nt - 1;
@@ -895,6 +952,7 @@ attn_bwd_hr2_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_const
     for (int k = 0; k < n_local; ++k) {
       mbar_wait(full, k & 1);
       tc_fence_after();
+      tr(1);
       issue_mma1(units[0], ug++);
       if (n_units > 1) issue_mma1(units[1], ug++);
       for (int ui = 0; ui < n_units; ++ui, ++uc) {
@@ -902,8 +960,9 @@ attn_bwd_hr2_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_const
         const int b = static_cast<int>(uc & 1);
         const long long pg = static_cast<long long>(k) * pairs_per_head + u.pair;  // pair counter over all heads
         mbar_wait(&pds_full[b], static_cast<uint32_t>((uc >> 1) & 1));
-        if (u.flags & U_FIRST_KV) mbar_wait(kv_empty, (kvc & 1) ^ 1);   // dK / dV accumulators drained (previous block)
-        if (u.flags & U_FIRST_GRP) mbar_wait(dq_empty, (gc & 1) ^ 1);   // dQ accumulators drained (previous group)
+        tr(3);
+        if (u.flags & U_FIRST_KV) { mbar_wait(kv_empty, (kvc & 1) ^ 1); tr(5); }   // dK / dV accumulators drained (previous block)
+        if (u.flags & U_FIRST_GRP) { mbar_wait(dq_empty, (gc & 1) ^ 1); tr(6); }   // dQ accumulators drained (previous group)
         tc_fence_after();
         if (lane == 0) {
           const uint32_t rows = u.t * TILE_BYTES + u.h * 64 * 128;  // first row of this half inside dO / Q
@@ -932,7 +991,9 @@ attn_bwd_hr2_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_const
         __syncwarp();
         if (u.flags & U_LAST_KV) ++kvc;
         if (u.flags & U_LAST_GRP) ++gc;
+        tr(4);
         if (ui + 2 < n_units) issue_mma1(units[ui + 2], ug++);  // into the buffer this unit has just released (in order)
+        tr(2);
       }
     }
   } else if (warp < 8) {
@@ -953,6 +1014,7 @@ attn_bwd_hr2_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_const
         lse_r[i] = l < L ? p.lse[static_cast<size_t>(g) * L + l] * LOG2E : 0.f;
       }
       mbar_wait(full, k & 1);
+      tr(9);
 #pragma unroll
       for (int i = 0; i < 2; ++i) {
         const int l = tid + i * 256;
@@ -990,14 +1052,16 @@ attn_bwd_hr2_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_const
         const int qvalid = hr_rows(G, u.t) - q0;   // columns < qvalid are real query rows
         mbar_wait(&s_full[b], static_cast<uint32_t>((uc >> 1) & 1));
         tc_fence_after();
+        tr(10);
         // the dS^T tile of this pair was last read by the dQ product two pairs ago
-        if (u.h == 0) mbar_wait(&ds_free[pg & 1], static_cast<uint32_t>(((pg >> 1) & 1) ^ 1));
+        if (u.h == 0) { mbar_wait(&ds_free[pg & 1], static_cast<uint32_t>(((pg >> 1) & 1) ^ 1)); tr(15); }
         if (active && ncols > 0) {
           const uint32_t ts = t_lane + b * 128 + wg * 32, tdp = ts + 64;
           uint32_t sv[32], dv[32];
           if (ncols == 32) { tmem_ld_32x32(ts, sv); tmem_ld_32x32(tdp, dv); }
           else { tmem_ld_32x16(ts, *reinterpret_cast<uint32_t(*)[16]>(&sv[0])); tmem_ld_32x16(tdp, *reinterpret_cast<uint32_t(*)[16]>(&dv[0])); }
           tmem_ld_wait();
+          tr(11);
           const float* pl = vlse + u.t * 128 + q0;
           const float* pd = vdelta + u.t * 128 + q0;
           uint32_t pp[16], pds[16];
@@ -1028,11 +1092,13 @@ attn_bwd_hr2_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_const
           }
           if (ncols == 32) { tmem_st_32x16(ts, pp); tmem_st_32x16(tdp, pds); }
           else { tmem_st_32x8(ts, *reinterpret_cast<const uint32_t(*)[8]>(&pp[0])); tmem_st_32x8(tdp, *reinterpret_cast<const uint32_t(*)[8]>(&pds[0])); }
+          tr(13);
           tmem_st_wait();
         }
         fence_proxy_async_smem();
         tc_fence_before();
         mbar_arrive(&pds_full[b]);
+        tr(14);
       }
     }
   } else {
@@ -1056,6 +1122,7 @@ attn_bwd_hr2_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_const
           bf16* hm = p.ddelta != nullptr ? p.ddelta + plane + (static_cast<size_t>(g) * L + (valid ? lk : 0)) * 64 : nullptr;
           mbar_wait(kv_full, kvc & 1);
           tc_fence_after();
+          tr(20);
           if (active) {
 #pragma unroll 1
             for (int part = 0; part < 2; ++part) {  // 0: dV', 1: dK
@@ -1083,9 +1150,11 @@ attn_bwd_hr2_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_const
           }
           tc_fence_before();
           mbar_arrive(kv_empty);
+          tr(21);
         }
         mbar_wait(dq_full, gc & 1);
         tc_fence_after();
+        tr(23);
         for (int tt = 0; tt < ntg; ++tt) {
           const int t = 2 * tg + tt;
           const int lq = t * 128 + row;
@@ -1117,6 +1186,7 @@ attn_bwd_hr2_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_const
         }
         tc_fence_before();
         mbar_arrive(dq_empty);
+        tr(24);
       }
     }
   }
@@ -1147,7 +1217,8 @@ int attn_fwd_hr(cudaStream_t s, const AttnShape& a, const bf16* q, const bf16* k
   const int fixed = HF_STATS_BYTES + HF_XMAX_BYTES + 256 + 1024;
   const int nstage = (227 * 1024 - fixed) / stage_bytes >= 2 ? 2 : 1;
   const int smem_bytes = nstage * stage_bytes + fixed;
-  FwdHrParams p{g, nstage, o_tok, lse};
+  TraceHost trace;
+  FwdHrParams p{g, nstage, o_tok, lse, trace.begin(HF_THREADS / 32)};
   const int grid = g.heads < sm_count() ? g.heads : sm_count();
   static int configured[64] = {};
   int dev = 0;
@@ -1159,6 +1230,7 @@ int attn_fwd_hr(cudaStream_t s, const AttnShape& a, const bf16* q, const bf16* k
   ProfScope prof(s, PC_ATTN_FWD);
   PEVIT_CHECK_CUDA(launch_kernel(attn_fwd_hr_kernel, dim3(grid), dim3(HF_THREADS), smem_bytes, s, 1, tq, tk, tv, tqt, tkt, tvt, p));
   PEVIT_CHECK_LAUNCH();
+  trace.end(s, "fwd");
   return 0;
 }
 
@@ -1186,7 +1258,8 @@ int attn_bwd_hr(cudaStream_t s, const AttnShape& a, const bf16* q, const bf16* k
   if (make_tmap_bf16_tok_heads(&tdot, do_tok, a.L, a.NB, a.H, a.D, g.tail16) != 0) return -1;
   if (make_tmap_bf16_tok_heads(&tot, o_tok, a.L, a.NB, a.H, a.D, g.tail16) != 0) return -1;
   const int smem_bytes = 4 * g.tensor_bytes + 4 * TILE_BYTES + HB_VEC_BYTES + HB2_MAX_UNITS * static_cast<int>(sizeof(HrUnit)) + 256 + 1024;
-  BwdHrParams p{g, ld_dqkv, lse, dqkv, ddelta};
+  TraceHost trace;
+  BwdHrParams p{g, ld_dqkv, lse, dqkv, ddelta, trace.begin(HB_THREADS / 32)};
   static const bool use_v1 = getenv("PEVIT_ATTN_BWD_V1") != nullptr;  // diagnostics: the serialised first version
   const int grid = g.heads < sm_count() ? g.heads : sm_count();
   static bool configured[64] = {};
@@ -1201,6 +1274,7 @@ int attn_bwd_hr(cudaStream_t s, const AttnShape& a, const bf16* q, const bf16* k
   PEVIT_CHECK_CUDA(launch_kernel(use_v1 ? attn_bwd_hr_kernel : attn_bwd_hr2_kernel, dim3(grid), dim3(HB_THREADS), smem_bytes, s, 1,
                                  tq, tk, tv, tdo, to, tqt, tkt, tvt, tdot, tot, p));
   PEVIT_CHECK_LAUNCH();
+  trace.end(s, "bwd");
   return 0;
 }
 
