@@ -92,58 +92,47 @@ HrGeom make_geom(const AttnShape& a) {
 }
 
 // ===================================================================================================== forward
-constexpr int HF_THREADS = 448;  // softmax WG0, softmax WG1, merge WG, TMA warp, MMA warp
-constexpr int HF_STATS_BYTES = 2 * HR_MAXT * 2 * 128 * 8;  // [tile parity][key block][warpgroup][row] (max, partial sum)
-constexpr int HF_XMAX_BYTES = 2 * 2 * 128 * 4;          // [S buffer][warpgroup][row] partial row maxima
+// Unit = (query tile t, key block jb).  The stored keys of a head (L16 = ceil16(L)) are cut into nkb = ceil(L16 / 112) blocks
+// of <= 112 keys -- ViT-B/16: 112 + 96, ViT-L/14: 96 + 96 + 80 -- and each block is ONE MMA shape (N = block width), so
+// the key tail costs neither a unit nor exponentials.
+//   * Unit u belongs to softmax warpgroup u & 1, ALONE: one thread per query row reads the row's <= 112 scores from
+//     TMEM once (a warp reads TMEM at ~48 B/clk however many loads are in flight, so a second pass would cost as much as
+//     the exponentials), keeps them in registers (setmaxnreg moves registers from the other roles to the softmax
+//     warpgroups), and writes the bf16 probabilities back over the scores.  No barrier couples the two warpgroups, so
+//     their load / MUFU / store phases interleave on every SM sub-partition.
+//   * Up to three score buffers rotate over the units (u % nbuf): the scores of unit u+2 are computed while the
+//     warpgroups work on units u and u+1, which hides the MMA round trip.
+//   * One accumulator O_jb per key block, merged exactly by a third warpgroup (O = sum_jb e^{m_jb - m} O_jb / l): nothing
+//     is rescaled in TMEM and no partial result touches HBM.
+constexpr int HF_THREADS = 512;  // softmax WG0, softmax WG1, merge WG, [TMA warp, MMA warp, two idle warps]
+constexpr int HF_MAXKB = 4;      // key blocks per head
+constexpr int HF_MAXCOLS = 112;  // keys per block = score columns per softmax thread
+constexpr int HF_MAXBUF = 3;     // score buffers in TMEM
+constexpr int HF_STATS_BYTES = 2 * HF_MAXKB * 128 * 8;  // [tile parity][key block][row] (max, sum)
 
 struct FwdHrParams {
   HrGeom g;
   int nstage;
+  int nkb;       // key blocks per head
+  int kwa, kwl;  // stored keys (multiple of 16, <= 112) of the blocks jb < nkb - 1 / of the last block; block jb starts at jb * kwa
+  int nbuf;      // score buffers of kwa TMEM columns each; the accumulators follow them
   bf16* o_tok;
   float* lse;
   unsigned long long* trace;
 };
 
-// The <= 64 score columns one softmax thread owns (FULL: exactly 64, all valid).  One TMEM read per score: the row
-// statistics and the probabilities come out of registers (TMEM reads, 64 B/clk per SM, are this kernel's floor).
-template <bool FULL>
-__device__ __forceinline__ void load_scores(uint32_t taddr, int ncols, uint32_t (&v)[64]) {
-  if (FULL || ncols >= 32) tmem_ld_32x32(taddr, *reinterpret_cast<uint32_t(*)[32]>(&v[0]));
-  else if (ncols >= 16) tmem_ld_32x16(taddr, *reinterpret_cast<uint32_t(*)[16]>(&v[0]));
-  if (FULL || ncols == 64) tmem_ld_32x32(taddr + 32, *reinterpret_cast<uint32_t(*)[32]>(&v[32]));
-  else if (ncols == 48) tmem_ld_32x16(taddr + 32, *reinterpret_cast<uint32_t(*)[16]>(&v[32]));
-  tmem_ld_wait();
-}
-template <bool FULL>
-__device__ __forceinline__ float local_max(const uint32_t (&v)[64], int nvalid) {
-  float m4[4] = {-INFINITY, -INFINITY, -INFINITY, -INFINITY};
-#pragma unroll
-  for (int i = 0; i < 64; ++i)
-    if (FULL || i < nvalid) m4[i & 3] = fmaxf(m4[i & 3], __uint_as_float(v[i]));
-  return fmaxf(fmaxf(m4[0], m4[1]), fmaxf(m4[2], m4[3]));
-}
-// p = exp2(s * log2e - mxs) packed to bf16 pairs and written back to TMEM at pbase; returns the row sum of this part
-template <bool FULL>
-__device__ __forceinline__ float exp_store(uint32_t pbase, int ncols, int nvalid, float mxs, const uint32_t (&v)[64]) {
-  float s4[4] = {0.f, 0.f, 0.f, 0.f};
-  uint32_t pk[32];
-#pragma unroll
-  for (int i = 0; i < 64; i += 2) {
-    float e0 = fast_exp2(fmaf(__uint_as_float(v[i]), LOG2E, -mxs));
-    float e1 = fast_exp2(fmaf(__uint_as_float(v[i + 1]), LOG2E, -mxs));
-    if (!FULL) {
-      e0 = i < nvalid ? e0 : 0.f;
-      e1 = i + 1 < nvalid ? e1 : 0.f;
-    }
-    s4[(i >> 1) & 3] += e0 + e1;
-    pk[i >> 1] = pack_bf16(e0, e1);
+template <int N>
+__device__ __forceinline__ uint32_t (&sub(uint32_t (&v)[HF_MAXCOLS], int i))[N] { return *reinterpret_cast<uint32_t(*)[N]>(&v[i]); }
+
+// position of a unit in the CTA's sequence, advanced without divisions
+struct HfUnit {
+  int u, k, t, jb, buf, par;  // index, local head, query tile, key block, score buffer, phase parity of the buffer's barriers
+  __device__ __forceinline__ void next(int nt, int nkb, int nbuf) {
+    ++u;
+    if (++jb == nkb) { jb = 0; if (++t == nt) { t = 0; ++k; } }
+    if (++buf == nbuf) { buf = 0; par ^= 1; }
   }
-  if (FULL || ncols >= 32) tmem_st_32x16(pbase, *reinterpret_cast<const uint32_t(*)[16]>(&pk[0]));
-  else if (ncols >= 16) tmem_st_32x8(pbase, *reinterpret_cast<const uint32_t(*)[8]>(&pk[0]));
-  if (FULL || ncols == 64) tmem_st_32x16(pbase + 16, *reinterpret_cast<const uint32_t(*)[16]>(&pk[16]));
-  else if (ncols == 48) tmem_st_32x8(pbase + 16, *reinterpret_cast<const uint32_t(*)[8]>(&pk[16]));
-  return (s4[0] + s4[1]) + (s4[2] + s4[3]);
-}
+};
 
 __global__ void __launch_bounds__(HF_THREADS, 1)
 attn_fwd_hr_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant__ CUtensorMap tm_k,
@@ -154,23 +143,26 @@ attn_fwd_hr_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_consta
   const HrGeom& G = p.g;
   const int stage_bytes = 3 * G.tensor_bytes;
   float2* stats = reinterpret_cast<float2*>(smem + p.nstage * stage_bytes);
-  float* xmax = reinterpret_cast<float*>(reinterpret_cast<uint8_t*>(stats) + HF_STATS_BYTES);
-  uint64_t* bars = reinterpret_cast<uint64_t*>(reinterpret_cast<uint8_t*>(xmax) + HF_XMAX_BYTES);
-  uint64_t* full = bars;             // [2] head operands landed
-  uint64_t* empty = full + 2;        // [2] every MMA of the head has completed
-  uint64_t* s_full = empty + 2;      // [2] S_b ready (MMA -> softmax warpgroup b)
-  uint64_t* p_full = s_full + 2;     // [2] P_b written back to TMEM (256 arrivals)
-  uint64_t* o_full = p_full + 2;     // every O_j of the query tile accumulated
-  uint64_t* o_empty = o_full + 1;    // merge warpgroup has read the O_j (128 arrivals)
+  uint64_t* bars = reinterpret_cast<uint64_t*>(reinterpret_cast<uint8_t*>(stats) + HF_STATS_BYTES);
+  uint64_t* full = bars;                 // [2] head operands landed
+  uint64_t* empty = full + 2;            // [2] every MMA of the head has completed
+  uint64_t* s_full = empty + 2;          // [HF_MAXBUF] S_buf ready (MMA -> the unit's softmax warpgroup)
+  uint64_t* p_full = s_full + HF_MAXBUF; // [HF_MAXBUF] P written back over S_buf (4 warp arrivals)
+  uint64_t* o_full = p_full + HF_MAXBUF; // every O_jb of the query tile accumulated
+  uint64_t* o_empty = o_full + 1;        // merge warpgroup has read the O_jb (4 warp arrivals)
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(o_empty + 1);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int nt = G.nt, L = G.L;
+  const int nt = G.nt, L = G.L, nkb = p.nkb, nbuf = p.nbuf;
   const int n_local = (G.heads - static_cast<int>(blockIdx.x) + static_cast<int>(gridDim.x) - 1) /
                       static_cast<int>(gridDim.x);
-  const int pairs_per_item = nt * nt;
-  const int n_pairs = n_local * pairs_per_item;
+  const int U = nt * nkb;            // units per head
+  const int n_units = n_local * U;
   Tracer tr(p.trace, warp);
+  auto block_keys = [&](int jb) { return jb == nkb - 1 ? p.kwl : p.kwa; };   // stored keys of block jb
+  const bool two_stages = p.nstage == 2;                                    // (no divisions on the issue paths)
+  auto stage_of = [&](int k) { return two_stages ? (k & 1) : 0; };
+  auto stage_par = [&](int k) { return two_stages ? ((k >> 1) & 1) : (k & 1); };
 
   // Rows of the tail tile beyond tail16 are never written by TMA but are read by the M = 128 MMAs: they must hold
   // finite values (their results are discarded), so the operand area starts out as zeros.
@@ -182,12 +174,10 @@ attn_fwd_hr_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_consta
   if (warp == 12 && lane == 0) {
     tma_prefetch_desc(&tm_q); tma_prefetch_desc(&tm_k); tma_prefetch_desc(&tm_v);
     tma_prefetch_desc(&tm_qt); tma_prefetch_desc(&tm_kt); tma_prefetch_desc(&tm_vt);
-    for (int s = 0; s < 2; ++s) {
-      mbar_init(&full[s], 1); mbar_init(&empty[s], 1);
-      mbar_init(&s_full[s], 1); mbar_init(&p_full[s], 256);
-    }
+    for (int s = 0; s < 2; ++s) { mbar_init(&full[s], 1); mbar_init(&empty[s], 1); }
+    for (int s = 0; s < HF_MAXBUF; ++s) { mbar_init(&s_full[s], 1); mbar_init(&p_full[s], 4); }
     mbar_init(o_full, 1);
-    mbar_init(o_empty, 128);
+    mbar_init(o_empty, 4);
     fence_mbar_init();
   }
   if (warp == 13) {
@@ -201,12 +191,90 @@ attn_fwd_hr_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_consta
   const uint32_t tmem_base = *tmem_slot;
   pdl_launch_dependents();
   pdl_wait();
-  // TMEM columns: S0 [0,128)  S1 [128,256)  O_j [256 + 64 j, +64).  P_b: bf16 pairs written by each softmax warpgroup over
-  // the start of ITS OWN half of S_b (keys 0..63 -> S_b + [0,32), keys 64..127 -> S_b + 64 + [0,32))
+  // TMEM columns: S_i [i kwa, +kwa) for i < nbuf, then O_jb [nbuf kwa + 64 jb, +64).  P: bf16 pairs over the first half of S_i
+  const uint32_t t_o = tmem_base + nbuf * p.kwa;
 
-  if (warp == 12) {
+  if (warp < 8) {
+    // ------------------------------------------------------------ softmax: warpgroup w owns the units u = w (mod 2)
+    setmaxnreg_inc<168>();
+    const int wg = warp >> 2, quad = warp & 3;
+    const int row = quad * 32 + lane;
+    HfUnit it{0, 0, 0, 0, 0, 0};
+    if (wg == 1 && n_units > 1) it.next(nt, nkb, nbuf);
+    for (; it.u < n_units; it.next(nt, nkb, nbuf), it.next(nt, nkb, nbuf)) {
+      const int tc = it.k * nt + it.t, jb = it.jb;
+      const int kw = block_keys(jb), nv = min(kw, L - jb * p.kwa);  // my columns / of which real keys
+      const bool active = quad * 32 < hr_rows(G, it.t);  // warp-uniform: some row of this warp is a real query
+      const uint32_t t_row = tmem_base + (static_cast<uint32_t>(quad * 32) << 16) + it.buf * p.kwa;
+      mbar_wait(&s_full[it.buf], it.par);
+      tc_fence_after();
+      tr(10);
+      if (active) {
+        uint32_t v[HF_MAXCOLS];
+        if (kw >= 32) tmem_ld_32x32(t_row, sub<32>(v, 0)); else tmem_ld_32x16(t_row, sub<16>(v, 0));
+        if (kw >= 64) tmem_ld_32x32(t_row + 32, sub<32>(v, 32)); else if (kw >= 48) tmem_ld_32x16(t_row + 32, sub<16>(v, 32));
+        if (kw >= 96) tmem_ld_32x32(t_row + 64, sub<32>(v, 64)); else if (kw >= 80) tmem_ld_32x16(t_row + 64, sub<16>(v, 64));
+        if (kw >= 112) tmem_ld_32x16(t_row + 96, sub<16>(v, 96));
+        tmem_ld_wait();
+        // Padding keys (only the last 16 columns of the head's last block can hold any) become -inf: they drop out of
+        // the maximum and their probabilities are exact zeros, so the hot loops below need no masked variant (the
+        // kernel is instruction-cache bound: every unrolled variant costs fetch stalls in all roles).
+        if (nv < kw) {
+#pragma unroll
+          for (int c = 0; c < HF_MAXCOLS; c += 16) {
+            if (c + 16 == kw) {
+#pragma unroll
+              for (int i = 0; i < 16; ++i)
+                if (c + i >= nv) v[c + i] = 0xff800000u;
+            }
+          }
+        }
+        float m4[4] = {-INFINITY, -INFINITY, -INFINITY, -INFINITY};
+#pragma unroll
+        for (int c = 0; c < HF_MAXCOLS; c += 16) {
+          if (c < kw) {
+#pragma unroll
+            for (int i = 0; i < 16; ++i) m4[i & 3] = fmaxf(m4[i & 3], __uint_as_float(v[c + i]));
+          }
+        }
+        const float mx = fmaxf(fmaxf(m4[0], m4[1]), fmaxf(m4[2], m4[3]));
+        const float mxs = mx * LOG2E;
+        tr(11);
+        float s4[4] = {0.f, 0.f, 0.f, 0.f};
+        // 32 scores -> 16 packed bf16 pairs, written back over the first half of the columns (all of them are in registers)
+#pragma unroll
+        for (int c = 0; c < HF_MAXCOLS; c += 32) {
+          if (c < kw) {
+            uint32_t pk[16];
+#pragma unroll
+            for (int h = 0; h < 32 && c + h < HF_MAXCOLS; h += 16) {
+              if (c + h < kw) {
+#pragma unroll
+                for (int i = 0; i < 16; i += 2) {
+                  const float e0 = fast_exp2(fmaf(__uint_as_float(v[c + h + i]), LOG2E, -mxs));
+                  const float e1 = fast_exp2(fmaf(__uint_as_float(v[c + h + i + 1]), LOG2E, -mxs));
+                  s4[(i >> 1) & 3] += e0 + e1;
+                  pk[(h + i) >> 1] = pack_bf16(e0, e1);
+                }
+              }
+            }
+            if (c + 32 <= kw) tmem_st_32x16(t_row + (c >> 1), pk);
+            else tmem_st_32x8(t_row + (c >> 1), *reinterpret_cast<const uint32_t(*)[8]>(&pk[0]));
+          }
+        }
+        stats[((tc & 1) * HF_MAXKB + jb) * 128 + row] = make_float2(mx, (s4[0] + s4[1]) + (s4[2] + s4[3]));
+        tr(13);
+        tmem_st_wait();
+      }
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&p_full[it.buf]);
+      tr(14);
+    }
+  } else if (warp == 12) {
+    setmaxnreg_dec<56>();
     // ------------------------------------------------------------ TMA producer: one head per stage
-    if (lane == 0) {
+    if (elect_one()) {
       auto prefetch_head = [&](int k_) {
         if (k_ >= n_local) return;
         const int g_ = blockIdx.x + k_ * gridDim.x;
@@ -221,13 +289,12 @@ attn_fwd_hr_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_consta
       // flight across 148 CTAs thrashed L2 (DRAM reads 1.8x the algorithmic bytes)
       for (int k = 0; k < n_local; ++k) {
         const int g = blockIdx.x + k * gridDim.x;
-        const int s = k % p.nstage;
+        const int s = stage_of(k);
         prefetch_head(k + p.nstage);
-        mbar_wait(&empty[s], ((k / p.nstage) & 1) ^ 1);
+        mbar_wait(&empty[s], stage_par(k) ^ 1);
         tr(30);
         uint8_t* st = smem + s * stage_bytes;
         mbar_expect_tx(&full[s], static_cast<uint32_t>(stage_bytes));
-        // first pair's operands first
         for (int i = 0; i < nt; ++i) {
           const bool tl = i == nt - 1;
           tma_load_3d(st + i * TILE_BYTES, tl ? &tm_qt : &tm_q, &full[s], 0, i * 128, g);
@@ -237,107 +304,63 @@ attn_fwd_hr_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_consta
       }
     }
   } else if (warp == 13) {
+    setmaxnreg_dec<56>();
     // ------------------------------------------------------------ MMA issuer
-    auto issue_s = [&](int pi) {
-      const int k = pi / pairs_per_item, r = pi - k * pairs_per_item;
-      const int t = r / nt, j = r - t * nt;
-      const int s = k % p.nstage, b = pi & 1;
-      if (r == 0) { mbar_wait(&full[s], (k / p.nstage) & 1); tr(1); }
+    auto issue_s = [&](const HfUnit x) {
+      const int s = stage_of(x.k);
+      if (x.t == 0 && x.jb == 0) { mbar_wait(&full[s], stage_par(x.k)); tr(1); }
       tc_fence_after();
       tr(2);
-      if (lane == 0) {
+      if (elect_one()) {
         const uint32_t st = smem_u32(smem + s * stage_bytes);
-        const uint64_t dq = umma_desc_kmajor_sw128(st + t * TILE_BYTES);
-        const uint64_t dk = umma_desc_kmajor_sw128(st + G.tensor_bytes + j * TILE_BYTES);
-        const uint32_t idesc = umma_idesc_bf16(128, hr_rows16(G, j));
+        const uint64_t dq = umma_desc_kmajor_sw128(st + x.t * TILE_BYTES);
+        const uint64_t dk = umma_desc_kmajor_sw128(st + G.tensor_bytes + x.jb * p.kwa * 128);
+        const uint32_t idesc = umma_idesc_bf16(128, block_keys(x.jb));
 #pragma unroll
-        for (int kk = 0; kk < 4; ++kk) umma_bf16_ss(tmem_base + b * 128, dq + 2 * kk, dk + 2 * kk, idesc, kk != 0);
-        umma_commit(&s_full[b]);
+        for (int kk = 0; kk < 4; ++kk) umma_bf16_ss(tmem_base + x.buf * p.kwa, dq + 2 * kk, dk + 2 * kk, idesc, kk != 0);
+        umma_commit(&s_full[x.buf]);
       }
       __syncwarp();
     };
-    auto issue_pv = [&](int pi) {
-      const int k = pi / pairs_per_item, r = pi - k * pairs_per_item;
-      const int t = r / nt, j = r - t * nt;
-      const int s = k % p.nstage, b = pi & 1;
-      const int tc = k * nt + t;
-      mbar_wait(&p_full[b], (pi >> 1) & 1);
+    auto issue_pv = [&](const HfUnit x) {
+      const int s = stage_of(x.k);
+      const int tc = x.k * nt + x.t;
+      mbar_wait(&p_full[x.buf], x.par);
       tr(3);
-      if (j == 0) { mbar_wait(o_empty, (tc & 1) ^ 1); tr(5); }  // the merge warpgroup has drained the previous tile's O_j
+      if (x.jb == 0) { mbar_wait(o_empty, (tc & 1) ^ 1); tr(5); }  // the merge warpgroup has drained the previous tile's O_jb
       tc_fence_after();
-      if (lane == 0) {
-        const uint32_t sv = smem_u32(smem + s * stage_bytes + 2 * G.tensor_bytes + j * TILE_BYTES);
+      if (elect_one()) {
+        const uint32_t sv = smem_u32(smem + s * stage_bytes + 2 * G.tensor_bytes + x.jb * p.kwa * 128);
         constexpr uint32_t idesc = umma_idesc_bf16(128, 64) | IDESC_B_MN;
-        const int ksteps = hr_rows16(G, j) >> 4;
-        for (int kk = 0; kk < ksteps; ++kk)  // A = P_b: 16 keys = 8 TMEM columns per step; B = V_j (64 d contiguous per key)
-          umma_bf16_ts(tmem_base + 256 + j * 64, tmem_base + b * 128 + (kk >> 2) * 64 + (kk & 3) * 8,
-                       umma_desc_mnmajor_sw128(sv + kk * 2048, TILE_BYTES), idesc, kk != 0);
-        if (j == nt - 1) umma_commit(o_full);
-        if (r == pairs_per_item - 1) umma_commit(&empty[s]);
+        const int ksteps = block_keys(x.jb) >> 4;
+        const uint32_t pa = tmem_base + x.buf * p.kwa;
+        for (int kk = 0; kk < ksteps; ++kk)  // A = P: 16 keys = 8 TMEM columns per step; B = V rows (64 d contiguous per key)
+          umma_bf16_ts(t_o + x.jb * 64, pa + kk * 8, umma_desc_mnmajor_sw128(sv + kk * 2048, TILE_BYTES), idesc, kk != 0);
+        if (x.jb == nkb - 1) umma_commit(o_full);
+        if (x.t == nt - 1 && x.jb == nkb - 1) umma_commit(&empty[s]);
       }
       __syncwarp();
       tr(4);
     };
-    // S runs one pair ahead of P V (S_(b^1)'s previous reader, the P V product of pair pi-1, is already issued).  With
-    // a single operand stage the look-ahead must not cross into the next head: its load only starts once this
-    // head's last MMA has completed.
-    for (int pi = 0; pi < n_pairs; ++pi) {
-      const bool first_of_item = pi % pairs_per_item == 0;
-      if (first_of_item && (pi == 0 || p.nstage == 1)) issue_s(pi);
-      const int nx = pi + 1;
-      if (nx < n_pairs && !(p.nstage == 1 && nx % pairs_per_item == 0)) issue_s(nx);
-      issue_pv(pi);
+    // S_u goes into the buffer whose previous reader, P V of unit u - nbuf, has been issued (the tensor pipe runs in
+    // order).  With a single operand stage the scores of the next head must not be issued before this head's last
+    // P V: its operands only load once that product has completed.
+    HfUnit xs{0, 0, 0, 0, 0, 0}, xp{0, 0, 0, 0, 0, 0};
+    for (;;) {  // xp.u = number of P V products issued so far
+      while (xs.u < n_units && xs.u < xp.u + nbuf && (p.nstage >= 2 || xs.k * U <= xp.u)) { issue_s(xs); xs.next(nt, nkb, nbuf); }
+      if (xp.u >= n_units) break;
+      issue_pv(xp);
+      xp.next(nt, nkb, nbuf);
     }
-  } else if (warp < 8) {
-    // ------------------------------------------------------------ softmax: both warpgroups on every pair, 64 keys each
-    const int grp = warp >> 2, quad = warp & 3;
-    const int row = quad * 32 + lane;
-    for (int pi = 0; pi < n_pairs; ++pi) {
-      const int k = pi / pairs_per_item, r = pi - k * pairs_per_item;
-      const int t = r / nt, j = r - t * nt;
-      const int tc = k * nt + t, b = pi & 1;
-      const int kw = hr_rows16(G, j), kvalid = hr_rows(G, j);
-      const int ncols = max(0, min(64, kw - 64 * grp)), nvalid = max(0, min(64, kvalid - 64 * grp));
-      const bool active = quad * 32 < hr_rows(G, t);  // warp-uniform: some row of this warp is a real query
-      const uint32_t t_row = tmem_base + (static_cast<uint32_t>(quad * 32) << 16) + b * 128 + grp * 64;
-      float* xm = xmax + b * 256;
-      mbar_wait(&s_full[b], (pi >> 1) & 1);
-      tc_fence_after();
-      tr(10);
-      uint32_t v[64];
-      float mloc = -INFINITY;
-      const bool full = nvalid == 64;
-      if (active && ncols > 0) {
-        if (full) { load_scores<true>(t_row, ncols, v); mloc = local_max<true>(v, nvalid); }
-        else { load_scores<false>(t_row, ncols, v); mloc = local_max<false>(v, nvalid); }
-      }
-      xm[grp * 128 + row] = mloc;
-      tr(11);
-      named_bar_sync(1, 256);  // the other warpgroup's half of every row maximum
-      tr(12);
-      if (active) {
-        const float mx = fmaxf(mloc, xm[(grp ^ 1) * 128 + row]);
-        float sum = 0.f;
-        if (ncols > 0) {
-          if (full) sum = exp_store<true>(t_row, ncols, nvalid, mx * LOG2E, v);
-          else sum = exp_store<false>(t_row, ncols, nvalid, mx * LOG2E, v);
-        }
-        stats[(((tc & 1) * HR_MAXT + j) * 2 + grp) * 128 + row] = make_float2(mx, sum);
-        tr(13);
-        tmem_st_wait();
-      }
-      tc_fence_before();
-      mbar_arrive(&p_full[b]);
-      tr(14);
-    }
-  } else {
-    // ------------------------------------------------------------ merge warpgroup: O = sum_j w_j O_j / l
+  } else if (warp < 12) {
+    setmaxnreg_dec<112>();
+    // ------------------------------------------------------------ merge warpgroup: O = sum_jb w_jb O_jb / l
     const int quad = warp & 3;
     const int row = quad * 32 + lane;
-    const uint32_t t_row = tmem_base + (static_cast<uint32_t>(quad * 32) << 16) + 256;
+    const uint32_t t_row = t_o + (static_cast<uint32_t>(quad * 32) << 16);
+    int k = 0, t = 0;
     const int n_tiles = n_local * nt;
     for (int tc = 0; tc < n_tiles; ++tc) {
-      const int k = tc / nt, t = tc - k * nt;
       const int g = blockIdx.x + k * gridDim.x;
       const bool active = quad * 32 < hr_rows(G, t);
       const int lq = t * 128 + row;
@@ -345,55 +368,61 @@ attn_fwd_hr_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_consta
       tc_fence_after();
       tr(20);
       if (active) {
-        const float2* st = stats + (tc & 1) * HR_MAXT * 256 + row;  // [j][warpgroup][row]
-        float mj[HR_MAXT], w[HR_MAXT], m = -INFINITY, l = 0.f;
+        const float2* st = stats + (tc & 1) * HF_MAXKB * 128 + row;  // [jb][row]
+        float w[HF_MAXKB], m = -INFINITY, l = 0.f;
+        float2 ms[HF_MAXKB];
 #pragma unroll
-        for (int j = 0; j < HR_MAXT; ++j) {
-          mj[j] = -INFINITY; w[j] = 0.f;
-          if (j < nt) { mj[j] = st[j * 256].x; m = fmaxf(m, mj[j]); }
+        for (int j = 0; j < HF_MAXKB; ++j) {
+          ms[j] = make_float2(-INFINITY, 0.f);
+          if (j < nkb) { ms[j] = st[j * 128]; m = fmaxf(m, ms[j].x); }
         }
 #pragma unroll
-        for (int j = 0; j < HR_MAXT; ++j)
-          if (j < nt) { w[j] = fast_exp2((mj[j] - m) * LOG2E); l = fmaf(w[j], st[j * 256].y + st[j * 256 + 128].y, l); }
+        for (int j = 0; j < HF_MAXKB; ++j) {
+          w[j] = j < nkb ? fast_exp2((ms[j].x - m) * LOG2E) : 0.f;
+          l = fmaf(w[j], ms[j].y, l);
+        }
         const float inv = 1.f / l;
         const bool valid = lq < L;
         const int n = g / G.H, h = g - n * G.H;
         bf16* orow = p.o_tok + (static_cast<size_t>(valid ? lq : 0) * G.NB + n) * G.D + h * 64;
+        float acc[64];
 #pragma unroll
-        for (int half = 0; half < 2; ++half) {
-          float acc[32];
+        for (int c = 0; c < 64; ++c) acc[c] = 0.f;
+#pragma unroll 1
+        for (int j = 0; j < nkb; ++j) {  // not unrolled: code size (see above)
+          const float wj = (j == 0 ? w[0] : j == 1 ? w[1] : j == 2 ? w[2] : w[3]) * inv;
 #pragma unroll
-          for (int c = 0; c < 32; ++c) acc[c] = 0.f;
+          for (int half = 0; half < 2; ++half) {
+            uint32_t v[32];
+            tmem_ld_32x32(t_row + j * 64 + half * 32, v);
+            tmem_ld_wait();
 #pragma unroll
-          for (int j = 0; j < HR_MAXT; ++j) {
-            if (j < nt) {
-              uint32_t v[32];
-              tmem_ld_32x32(t_row + j * 64 + half * 32, v);
-              tmem_ld_wait();
-              const float wj = w[j] * inv;
-#pragma unroll
-              for (int c = 0; c < 32; ++c) acc[c] = fmaf(wj, __uint_as_float(v[c]), acc[c]);
-            }
+            for (int c = 0; c < 32; ++c) acc[half * 32 + c] = fmaf(wj, __uint_as_float(v[c]), acc[half * 32 + c]);
           }
-          if (half == 1) {  // every O_j of this tile is in registers: the next tile's P V products may overwrite them
-            tc_fence_before();
-            mbar_arrive(o_empty);
-          }
-          if (valid) {
+        }
+        // every O_jb of this tile is in registers: the next tile's P V products may overwrite them (before the slow,
+        // row-strided global stores)
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(o_empty);
+        if (valid) {
 #pragma unroll
-            for (int c = 0; c < 32; c += 8)
-              *reinterpret_cast<uint4*>(orow + half * 32 + c) =
-                  make_uint4(pack_bf16(acc[c], acc[c + 1]), pack_bf16(acc[c + 2], acc[c + 3]),
-                             pack_bf16(acc[c + 4], acc[c + 5]), pack_bf16(acc[c + 6], acc[c + 7]));
-          }
+          for (int c = 0; c < 64; c += 8)
+            *reinterpret_cast<uint4*>(orow + c) =
+                make_uint4(pack_bf16(acc[c], acc[c + 1]), pack_bf16(acc[c + 2], acc[c + 3]),
+                           pack_bf16(acc[c + 4], acc[c + 5]), pack_bf16(acc[c + 6], acc[c + 7]));
         }
         if (valid) p.lse[static_cast<size_t>(g) * L + lq] = m + __logf(l);
         tr(22);
       } else {
         tc_fence_before();
-        mbar_arrive(o_empty);
+        __syncwarp();
+        if (lane == 0) mbar_arrive(o_empty);
       }
+      if (++t == nt) { t = 0; ++k; }
     }
+  } else {
+    setmaxnreg_dec<56>();  // warps 14, 15: complete the fourth warpgroup for setmaxnreg, no work
   }
 
   tc_fence_before();
@@ -529,7 +558,7 @@ attn_bwd_hr_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_consta
 
   if (warp == 12) {
     // ------------------------------------------------------------ TMA producer
-    if (lane == 0) {
+    if (elect_one()) {
       auto prefetch_head = [&](int k_) {  // pull the next head into L2 while this one computes
         if (k_ >= n_local) return;
         const int g_ = blockIdx.x + k_ * gridDim.x;
@@ -566,7 +595,7 @@ attn_bwd_hr_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_consta
     const uint32_t aQ = smem_u32(sQ), aK = smem_u32(sK), aV = smem_u32(sV), aDO = smem_u32(sdO);
     const uint32_t aP = smem_u32(sP), aS = smem_u32(sdS);
     auto issue_mma1 = [&](int t, int j) {
-      if (lane == 0) {
+      if (elect_one()) {
         const uint32_t idesc_s = umma_idesc_bf16(128, hr_rows16(G, j));
         const uint64_t dq = umma_desc_kmajor_sw128(aQ + t * TILE_BYTES), dk = umma_desc_kmajor_sw128(aK + j * TILE_BYTES);
         const uint64_t dv = umma_desc_kmajor_sw128(aV + j * TILE_BYTES), ddo = umma_desc_kmajor_sw128(aDO + t * TILE_BYTES);
@@ -594,7 +623,7 @@ attn_bwd_hr_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_consta
             tc_fence_after();
             const bool last_tt = tt == ntg - 1;
             const bool last_of_head = last_tt && j == nt - 1 && tg == ngroups - 1;
-            if (lane == 0) {
+            if (elect_one()) {
               const int qsteps = hr_rows16(G, t) >> 4, ksteps = hr_rows16(G, j) >> 4;
               for (int kk = 0; kk < qsteps; ++kk)  // dV_j (+)= P^T dO_t   (K = query rows, 16 per step)
                 umma_bf16_ss(tmem_base + 256, umma_desc_mnmajor_sw128(aP + kk * 2048, TILE_BYTES),
@@ -895,7 +924,7 @@ attn_bwd_hr2_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_const
 
   if (warp == 12) {
     // ------------------------------------------------------------ TMA producer
-    if (lane == 0) {
+    if (elect_one()) {
       auto prefetch_head = [&](int k_) {
         if (k_ >= n_local) return;
         const int g_ = blockIdx.x + k_ * gridDim.x;
@@ -934,7 +963,7 @@ attn_bwd_hr2_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_const
     long long ug = 0;  // units issued (MMA1) so far, over all heads
     auto issue_mma1 = [&](const HrUnit& u, long long idx) {
       const int b = static_cast<int>(idx & 1);
-      if (lane == 0) {
+      if (elect_one()) {
         const uint32_t idesc = umma_idesc_bf16(128, u.nq);
         const uint32_t roff = u.t * TILE_BYTES + u.h * 64 * 128;
         const uint64_t dk = umma_desc_kmajor_sw128(aK + u.j * TILE_BYTES), dv = umma_desc_kmajor_sw128(aV + u.j * TILE_BYTES);
@@ -964,17 +993,20 @@ attn_bwd_hr2_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_const
         if (u.flags & U_FIRST_KV) { mbar_wait(kv_empty, (kvc & 1) ^ 1); tr(5); }   // dK / dV accumulators drained (previous block)
         if (u.flags & U_FIRST_GRP) { mbar_wait(dq_empty, (gc & 1) ^ 1); tr(6); }   // dQ accumulators drained (previous group)
         tc_fence_after();
-        if (lane == 0) {
+        tr(42);
+        if (elect_one()) {
           const uint32_t rows = u.t * TILE_BYTES + u.h * 64 * 128;  // first row of this half inside dO / Q
           const int qsteps = u.nq >> 4;
           for (int kk = 0; kk < qsteps; ++kk)   // dV_j (+)= P^T dO_{t,h}   (K = query rows of the half, 16 per step)
             umma_bf16_ts(tmem_base + 256, tmem_base + b * 128 + (kk >> 1) * 32 + (kk & 1) * 8,
                          umma_desc_mnmajor_sw128(aDO + rows + kk * 2048, TILE_BYTES), idesc_ts,
                          (!(u.flags & U_FIRST_KV) || kk != 0) ? 1u : 0u);
+          tr(43);
           for (int kk = 0; kk < qsteps; ++kk)   // dK_j (+)= dS^T Q_{t,h}
             umma_bf16_ts(tmem_base + 320, tmem_base + b * 128 + 64 + (kk >> 1) * 32 + (kk & 1) * 8,
                          umma_desc_mnmajor_sw128(aQ + rows + kk * 2048, TILE_BYTES), idesc_ts,
                          (!(u.flags & U_FIRST_KV) || kk != 0) ? 1u : 0u);
+          tr(44);
           if (u.flags & U_LAST_HALF) {          // dQ_t (+)= dS_t K_j       (K = stored keys of block j)
             const uint32_t ds = aDS + static_cast<uint32_t>(pg & 1) * 2 * TILE_BYTES;
             const int ksteps = hr_rows16(G, u.j) >> 4;
@@ -982,6 +1014,7 @@ attn_bwd_hr2_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_const
               umma_bf16_ss(tmem_base + 384 + u.tt * 64, umma_desc_mnmajor_sw128(ds + kk * 2048, TILE_BYTES),
                            umma_desc_mnmajor_sw128(aK + u.j * TILE_BYTES + kk * 2048, TILE_BYTES), idesc_dq,
                            (u.j | kk) != 0 ? 1u : 0u);
+            tr(45);
             umma_commit(&ds_free[pg & 1]);
           }
           if (u.flags & U_LAST_KV) umma_commit(kv_full);
@@ -1214,11 +1247,20 @@ int attn_fwd_hr(cudaStream_t s, const AttnShape& a, const bf16* q, const bf16* k
   if (make_tmap_bf16_hm3d(&tkt, k, a.L, g.heads, g.tail16) != 0) return -1;
   if (make_tmap_bf16_hm3d(&tvt, v, a.L, g.heads, g.tail16) != 0) return -1;
   const int stage_bytes = 3 * g.tensor_bytes;
-  const int fixed = HF_STATS_BYTES + HF_XMAX_BYTES + 256 + 1024;
+  const int fixed = HF_STATS_BYTES + 256 + 1024;
   const int nstage = (227 * 1024 - fixed) / stage_bytes >= 2 ? 2 : 1;
   const int smem_bytes = nstage * stage_bytes + fixed;
   TraceHost trace;
-  FwdHrParams p{g, nstage, o_tok, lse, trace.begin(HF_THREADS / 32)};
+  FwdHrParams p{};
+  p.g = g; p.nstage = nstage; p.o_tok = o_tok; p.lse = lse;
+  const int l16 = (g.nt - 1) * 128 + g.tail16;  // stored keys of a head
+  p.nkb = (l16 + HF_MAXCOLS - 1) / HF_MAXCOLS;
+  p.kwa = p.nkb == 1 ? l16 : ((l16 + p.nkb - 1) / p.nkb + 15) / 16 * 16;
+  p.kwl = l16 - (p.nkb - 1) * p.kwa;
+  p.nbuf = (512 - 64 * p.nkb) / p.kwa < HF_MAXBUF ? (512 - 64 * p.nkb) / p.kwa : HF_MAXBUF;
+  PEVIT_REQUIRE(p.nkb <= HF_MAXKB && p.kwl >= 16 && p.kwl <= p.kwa && p.kwa <= HF_MAXCOLS && p.nbuf >= 2,
+                "attn_fwd_hr: L=%d does not fit (key blocks %d x %d + %d, %d score buffers)", a.L, p.nkb - 1, p.kwa, p.kwl, p.nbuf);
+  p.trace = trace.begin(HF_THREADS / 32);
   const int grid = g.heads < sm_count() ? g.heads : sm_count();
   static int configured[64] = {};
   int dev = 0;

@@ -17,6 +17,20 @@
 namespace pevit {
 namespace {
 
+// Which single-lane guard each role of the backward kernel uses (overridable for A/B builds).  Measured on B200 at
+// L = 50, N = 256: issuing the MMAs from `lane == 0` (ptxas then wraps every UTCHMMA in a ~100-cycle waterfall loop, i.e. the
+// 24 MMA2 instructions trickle out over ~3000 cycles) is FASTER than the back-to-back issue elect.sync allows, 55.3 vs
+// 61.4 us: the burst saturates shared-memory bandwidth exactly when WG0 stores P / dS of the next tile.
+#ifndef BWD_TMA_ONE
+#define BWD_TMA_ONE elect_one()
+#endif
+#ifndef BWD_MMA_ONE
+#define BWD_MMA_ONE (lane == 0)
+#endif
+#ifndef BWD_WG1_ONE
+#define BWD_WG1_ONE elect_one()
+#endif
+
 constexpr int TC_STAGES = 3;
 constexpr int ATTN_PREFETCH = 5;  // tiles pulled into L2 beyond the shared-memory ring
 constexpr int TILE_BYTES = 128 * 128;  // 128 rows x 64 bf16
@@ -99,7 +113,7 @@ attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_consta
 
   if (warp == 8) {
     // ------------------------------------------------------------ TMA producer
-    if (lane == 0) {
+    if (elect_one()) {
       // The ring holds three tiles, but a tile's HBM latency is several tile-times: pull the operands of the tiles
       // further ahead into L2 now, so that the ring's own loads are L2 hits.
       auto prefetch_tile = [&](int it_) {
@@ -139,7 +153,7 @@ attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_consta
       const int s = it % TC_STAGES, b = it & 1;
       mbar_wait(&full[s], (it / TC_STAGES) & 1);
       tc_fence_after();
-      if (lane == 0) {
+      if (elect_one()) {
         const uint32_t sq = smem_u32(smem + s * STAGE_BYTES);
         const uint64_t dq = umma_desc_kmajor_sw128(sq);
         const uint64_t dk = umma_desc_kmajor_sw128(sq + TILE_BYTES);
@@ -155,7 +169,7 @@ attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_consta
       mbar_wait(&p_full[b], ph);
       mbar_wait(&o_empty[b], ph ^ 1);  // the epilogue warpgroup has read O_b of tile it-2
       tc_fence_after();
-      if (lane == 0) {
+      if (elect_one()) {
         const uint32_t sp = smem_u32(sP + b * P_BYTES);
         const uint32_t sv = smem_u32(smem + s * STAGE_BYTES + 2 * TILE_BYTES);
 #pragma unroll
@@ -238,11 +252,11 @@ attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_consta
       // The normalised O rows are staged in the part of P_b this row's softmax thread rewrites every tile anyway
       // (P_b is dead once O_b is complete) and leave as one TMA store per head: [L tokens][64] -> o_tok rows
       // (l * NB + n), columns h * 64.., coalesced instead of 128 scattered 16-byte stores per warp.
-      const bool elected = (threadIdx.x == 128);
+      auto elected = [&]() { return warp == 4 && elect_one(); };  // one lane of the warpgroup's first warp, the same every time
       for (int it = 0; it < n_local; ++it) {
         const int tile = blockIdx.x + it * gridDim.x;
         const int b = it & 1;
-        if (elected && it > 0) {  // previous tile's store has read its staging buffer: hand P_(b^1) back to the softmax
+        if (elected() && it > 0) {  // previous tile's store has read its staging buffer: hand P_(b^1) back to the softmax
           tma_store_wait_read<0>();
           mbar_arrive(&p_free[b ^ 1]);
         }
@@ -278,7 +292,7 @@ attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_consta
         }
         fence_proxy_async_smem();
         named_bar_sync(1, 128);
-        if (elected && !(p.debug & 4)) {
+        if (elected() && !(p.debug & 4)) {
 #pragma unroll
           for (int j = 0; j < PACK; ++j) {
             const int gj = tile * PACK + j;
@@ -290,7 +304,7 @@ attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_consta
           tma_store_commit();
         }
       }
-      if (elected) tma_store_wait_all<0>();
+      if (elected()) tma_store_wait_all<0>();
     }
   }
 
@@ -377,7 +391,7 @@ attn_bwd_tc_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_consta
 
   if (warp == 8) {
     // ------------------------------------------------------------ TMA producer
-    if (lane == 0) {
+    if (BWD_TMA_ONE) {
       auto prefetch_tile = [&](int it_) {  // see the forward kernel: L2 prefetch beyond the two-stage ring
         if (it_ >= n_local) return;
         const int g0_ = (blockIdx.x + it_ * gridDim.x) * PACK;
@@ -419,7 +433,7 @@ attn_bwd_tc_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_consta
       const uint32_t set = tmem_base + (it & 1) * 256;
       mbar_wait(&full[s], (it / BWD_STAGES) & 1);
       tc_fence_after();
-      if (lane == 0) {
+      if (BWD_MMA_ONE) {
         const uint32_t st = smem_u32(smem + s * BWD_STAGE_BYTES);
         const uint64_t dq = umma_desc_kmajor_sw128(st), dk = umma_desc_kmajor_sw128(st + TILE_BYTES);
         const uint64_t dv = umma_desc_kmajor_sw128(st + 2 * TILE_BYTES), ddo = umma_desc_kmajor_sw128(st + 3 * TILE_BYTES);
@@ -437,7 +451,7 @@ attn_bwd_tc_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_consta
       const uint32_t set = tmem_base + (it & 1) * 256;
       mbar_wait(pds_full, it & 1);  // P, dS are in smem; S / dP of this set have been consumed
       tc_fence_after();
-      if (lane == 0) {
+      if (BWD_MMA_ONE) {
         const uint32_t st = smem_u32(smem + s * BWD_STAGE_BYTES);
         const uint32_t aP = smem_u32(sP), aS = smem_u32(sdS);
 #pragma unroll
@@ -573,7 +587,7 @@ attn_bwd_tc_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_consta
     } else {
       // ---------------------------------------------------------- WG1: gradients out
       const size_t plane = static_cast<size_t>(p.heads_total) * L * 64;
-      const bool elected = (threadIdx.x == 128);
+      auto elected = [&]() { return warp == 4 && BWD_WG1_ONE; };  // one lane of the warpgroup's first warp, the same every time
       int pc = 0;  // parts stored so far (staging box = pc & 1)
       for (int it = 0; it < n_local; ++it) {
         const int tile = blockIdx.x + it * gridDim.x;
@@ -606,7 +620,7 @@ attn_bwd_tc_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_consta
           }
           // token-major dqkv rows: staged [row][64] (swizzled) and TMA-stored per head
           uint8_t* box = stg + (pc & 1) * TILE_BYTES;
-          if (elected) tma_store_wait_read<1>();  // the store that last used this box (two parts ago) has drained
+          if (elected()) tma_store_wait_read<1>();  // the store that last used this box (two parts ago) has drained
           named_bar_sync(2, 128);
           if (valid) {
             const float sc = part == 2 ? 0.125f : 1.f;
@@ -621,7 +635,7 @@ attn_bwd_tc_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_consta
           }
           fence_proxy_async_smem();
           named_bar_sync(2, 128);
-          if (elected) {
+          if (elected()) {
             const int hbase = part == 0 ? 2 * p.H : (part == 1 ? p.H : 0);  // dqkv columns: [dq | dk | dv] heads
 #pragma unroll
             for (int j = 0; j < PACK; ++j) {
@@ -635,7 +649,7 @@ attn_bwd_tc_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_consta
           }
         }
       }
-      if (elected) tma_store_wait_all<0>();
+      if (elected()) tma_store_wait_all<0>();
     }
   }
 

@@ -89,7 +89,7 @@ attn_fwd_long_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_cons
 
   if (warp == 8) {
     // ------------------------------------------------------------ TMA producer
-    if (lane == 0) {
+    if (elect_one()) {
       for (int bi = 0; bi < n_blocks; ++bi) {
         const int k = bi / nkv, j = bi - k * nkv;
         const int item = blockIdx.x + k * gridDim.x;
@@ -111,7 +111,7 @@ attn_fwd_long_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_cons
       const int s = bi % FL_STAGES, b = bi & 1;
       mbar_wait(&full[s], (bi / FL_STAGES) & 1);
       tc_fence_after();
-      if (lane == 0) {
+      if (elect_one()) {
         const uint32_t sq = smem_u32(smem + s * FL_STAGE_BYTES);
         const uint64_t dq = umma_desc_kmajor_sw128(sq);
         const uint64_t dk = umma_desc_kmajor_sw128(sq + TILE_BYTES);
@@ -127,7 +127,7 @@ attn_fwd_long_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_cons
       mbar_wait(&p_full[b], (bi >> 1) & 1);
       if (j == 0) mbar_wait(o_empty, (k & 1) ^ 1);  // the previous item's epilogue has drained the O buffers
       tc_fence_after();
-      if (lane == 0) {
+      if (elect_one()) {
         const uint32_t sp = smem_u32(sP + b * FL_P_BYTES);
         const uint32_t sv = smem_u32(smem + s * FL_STAGE_BYTES + 2 * TILE_BYTES);
 #pragma unroll
@@ -330,7 +330,7 @@ attn_bwd_long_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_cons
 
   if (warp == 8) {
     // ------------------------------------------------------------ TMA producer
-    if (lane == 0) {
+    if (elect_one()) {
       int bp = 0;
       for (int k = 0; k < n_local; ++k) {
         const int g = head_of(k), tg = k % p.ngroups;
@@ -363,7 +363,7 @@ attn_bwd_long_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_cons
       const int s = bp % BL_STAGES;
       mbar_wait(&full[s], (bp / BL_STAGES) & 1);
       tc_fence_after();
-      if (lane == 0) {
+      if (elect_one()) {
         const uint32_t st = smem_u32(smem + s * BL_STAGE_BYTES);
         const uint64_t dq = umma_desc_kmajor_sw128(st), dk = umma_desc_kmajor_sw128(st + TILE_BYTES);
         const uint64_t dv = umma_desc_kmajor_sw128(st + 2 * TILE_BYTES), ddo = umma_desc_kmajor_sw128(st + 3 * TILE_BYTES);
@@ -386,7 +386,7 @@ attn_bwd_long_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_cons
           if (tt == 0) mbar_wait(kv_empty, (kvc & 1) ^ 1);            // dK / dV accumulators drained (previous block)
           if (j == 0 && tt == 0) mbar_wait(dq_empty, (k & 1) ^ 1);    // dQ accumulators drained (previous item)
           tc_fence_after();
-          if (lane == 0) {
+          if (elect_one()) {
             const uint32_t st = smem_u32(smem + s * BL_STAGE_BYTES);
             const uint32_t aP = smem_u32(sP), aS = smem_u32(sdS);
 #pragma unroll

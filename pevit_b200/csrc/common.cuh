@@ -129,6 +129,9 @@ __device__ __forceinline__ void pdl_launch_dependents() {
 #endif
 }
 
+// One lane of a fully converged warp, chosen by the hardware.  Unlike `lane == 0`, ptxas knows that exactly one lane
+// runs the guarded code, so the register -> uniform-register moves that UTCHMMA / UTMALDG operands need are single
+// R2URs instead of a per-lane waterfall loop (ELECT / R2UR.BROADCAST / BRA.U.ANY, ~100 cycles per MMA issued).
 __device__ __forceinline__ bool elect_one() {
   uint32_t pred = 0;
   asm volatile(
@@ -138,6 +141,11 @@ __device__ __forceinline__ bool elect_one() {
       : "=r"(pred));
   return pred != 0;
 }
+
+// Register reallocation between the warpgroups of a CTA (all four warps of a warpgroup execute the same one): the kernel
+// is compiled for 65536 / threads registers per thread; roles that need fewer release them, the hot role takes them.
+template <int N> __device__ __forceinline__ void setmaxnreg_inc() { asm volatile("setmaxnreg.inc.sync.aligned.u32 %0;" ::"n"(N)); }
+template <int N> __device__ __forceinline__ void setmaxnreg_dec() { asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" ::"n"(N)); }
 
 __device__ __forceinline__ float warp_sum(float v) {
 #pragma unroll

@@ -66,7 +66,7 @@ atb_tc_kernel(const __grid_constant__ AtbBatch batch) {
   pdl_wait();
 
   if (warp == 0) {
-    if (lane == 0) {
+    if (elect_one()) {
       for (int kb = 0; kb < num_kb; ++kb) {
         const int s = kb % ATB_STAGES;
         mbar_wait(&empty[s], ((kb / ATB_STAGES) & 1) ^ 1);
@@ -84,7 +84,7 @@ atb_tc_kernel(const __grid_constant__ AtbBatch batch) {
       const int s = kb % ATB_STAGES;
       mbar_wait(&full[s], (kb / ATB_STAGES) & 1);
       tc_fence_after();
-      if (lane == 0) {
+      if (elect_one()) {
         const uint32_t st = smem_u32(smem + s * ATB_STAGE_BYTES);
 #pragma unroll
         for (int k = 0; k < ATB_BK / 16; ++k)

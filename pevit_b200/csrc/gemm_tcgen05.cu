@@ -404,7 +404,7 @@ gemm_tn_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
 
   if (warp == 0) {
     // ------------------------------------------------------------ TMA producer
-    if (lane == 0) {
+    if (elect_one()) {
       int stage = 0;
       uint32_t phase = 0;
       for (int tile = first_tile; tile < num_tiles; tile += tile_step) {
@@ -456,7 +456,7 @@ gemm_tn_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
       for (int kb = 0; kb < num_kb; ++kb) {
         mbar_wait(&full_bar[stage], phase);
         tc_fence_after();
-        if (lane == 0) {
+        if (elect_one()) {
           const uint32_t sa = smem_u32(smem + stage * Cfg::STAGE_BYTES);
           const uint64_t da = umma_desc_kmajor_sw128(sa);
           const uint64_t db = umma_desc_kmajor_sw128(sa + Cfg::A_BYTES);
@@ -523,7 +523,11 @@ gemm_tn_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
       uint8_t* my_boxes = staging + wg * RING * BOX_BYTES;
       uint64_t* my_aux = aux_bar + wg * 3;
       const int row = quad * 32 + lane, r7 = row & 7;
-      const bool elected = (threadIdx.x == 64 + wg * 128);
+      // One thread of the warpgroup's first warp owns the box traffic (bulk groups are per thread).  elect.sync picks the
+      // same lane for the same mask every time, and tells ptxas that the guarded code runs on ONE lane (plain R2URs for
+      // the TMA operands instead of a waterfall loop per instruction).
+      const bool first_warp = warp == 2 + 4 * wg;
+      auto elected = [&]() { return first_warp && elect_one(); };
       const int bar_id = 1 + wg;
       auto first_j = [&](int it_) { return (wg ^ ((it_ * NBOXES) & 1)) & 1; };
       // cursor over this warpgroup's boxes, ahead of the consumer (aux prefetch)
@@ -546,7 +550,7 @@ gemm_tn_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
         tma_load_2d(my_boxes + slot * BOX_BYTES, &tmap_aux, &my_aux[slot], c0_, m0_);
         la_j += 2;
       };
-      if (has_aux && elected) {
+      if (has_aux && elected()) {
 #pragma unroll
         for (int q = 0; q < RING - 1; ++q) la_issue(q);
       }
@@ -578,7 +582,7 @@ gemm_tn_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
               tmem_ld_wait();
               act_half_compute<EPI>(br, v, hp, zp);
               if (sub == 0) {  // both buffers are about to be rewritten: the previous h / z stores must have drained
-                if (elected) tma_store_wait_read<0>();
+                if (elected()) tma_store_wait_read<0>();
                 named_bar_sync(bar_id, 128);
               }
               act_half_store(rowp, rowp2, r7, sub, hp, zp);
@@ -600,10 +604,10 @@ gemm_tn_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
           fence_proxy_async_smem();
           if constexpr (!kTwo) {
             // the buffer of the NEXT box must be free once the barrier below is passed
-            if (elected) tma_store_wait_read<RING - 2>();
+            if (elected()) tma_store_wait_read<RING - 2>();
           }
           named_bar_sync(bar_id, 128);
-          if (elected) {
+          if (elected()) {
             if constexpr (kQKV) {
               if (c0 < 3 * ep.D) {
                 const int which = c0 / ep.D, h = (c0 - which * ep.D) >> 6;
@@ -630,7 +634,7 @@ gemm_tn_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
           else mbar_arrive(&tempty_bar[acc]);
         }
       }
-      if (elected) tma_store_wait_all<0>();  // smem must outlive the last stores
+      if (elected()) tma_store_wait_all<0>();  // smem must outlive the last stores
     }
   }
 

@@ -11,7 +11,8 @@ NAMES = {1: "mma:operands landed", 2: "mma:S/MMA1 issued", 3: "mma:P ready (p_fu
          5: "mma:acc drained (o_empty/kv_empty)", 6: "mma:dq drained", 9: "wg:head operands landed",
          10: "wg:S ready", 11: "wg:loaded+max", 12: "wg:after named barrier", 13: "wg:exp done, st issued",
          14: "wg:arrived", 15: "wg:ds_free", 20: "out:acc full", 21: "out:kv drained", 22: "out:stored",
-         23: "out:dq full", 24: "out:dq drained", 30: "tma:stage free, loads issued"}
+         23: "out:dq full", 24: "out:dq drained", 30: "tma:stage free, loads issued", 40: "mma:S mmas issued", 41: "mma:S committed",
+         42: "mma:fence done", 43: "mma:PV/dV mmas issued", 44: "mma:dK mmas issued", 45: "mma:dQ mmas issued"}
 
 
 def main():
