@@ -835,7 +835,9 @@ attn_bwd_hr2_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_const
                     const __grid_constant__ CUtensorMap tm_v, const __grid_constant__ CUtensorMap tm_do,
                     const __grid_constant__ CUtensorMap tm_o, const __grid_constant__ CUtensorMap tm_qt,
                     const __grid_constant__ CUtensorMap tm_kt, const __grid_constant__ CUtensorMap tm_vt,
-                    const __grid_constant__ CUtensorMap tm_dot, const __grid_constant__ CUtensorMap tm_ot, BwdHrParams p) {
+                    const __grid_constant__ CUtensorMap tm_dot, const __grid_constant__ CUtensorMap tm_ot,
+                    const __grid_constant__ CUtensorMap tm_g, const __grid_constant__ CUtensorMap tm_gt,
+                    const __grid_constant__ CUtensorMap tm_h, const __grid_constant__ CUtensorMap tm_ht, BwdHrParams p) {
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   const HrGeom& G = p.g;
@@ -846,18 +848,19 @@ attn_bwd_hr2_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_const
   uint8_t* sdO = smem + 3 * TB;
   uint8_t* sDS = smem + 4 * TB;      // [pair parity][q half][128 key rows][64 query cols] bf16: dS^T of the current pairs
   uint8_t* sO = sDS;                 // O tiles of the head, only until delta is formed
-  float* vecs = reinterpret_cast<float*>(sDS + 4 * TILE_BYTES);  // [parity][0: delta, 1: lse * log2e][384]
+  uint8_t* stg = sDS + 4 * TILE_BYTES;  // [128 rows][64] bf16 box the gradients leave through (TMA store)
+  float* vecs = reinterpret_cast<float*>(stg + TILE_BYTES);  // [parity][0: delta, 1: lse * log2e][384]
   HrUnit* units = reinterpret_cast<HrUnit*>(reinterpret_cast<uint8_t*>(vecs) + HB_VEC_BYTES);
   uint64_t* bars = reinterpret_cast<uint64_t*>(units + HB2_MAX_UNITS);
   uint64_t* full = bars;               // head operands landed
   uint64_t* empty = full + 1;          // every MMA of the head has completed
   uint64_t* s_full = empty + 1;        // [2] MMA1 of a unit done
-  uint64_t* pds_full = s_full + 2;     // [2] P^T, dS^T of a unit written (256 arrivals)
+  uint64_t* pds_full = s_full + 2;     // [2] P^T, dS^T of a unit written (8 warp arrivals)
   uint64_t* ds_free = pds_full + 2;    // [2] dQ MMA of a pair done reading its dS^T tile
   uint64_t* kv_full = ds_free + 2;     // dK_j, dV_j complete (all tiles of the group)
-  uint64_t* kv_empty = kv_full + 1;    // WG2 drained dK_j, dV_j (128 arrivals)
+  uint64_t* kv_empty = kv_full + 1;    // WG2 drained dK_j, dV_j (4 warp arrivals)
   uint64_t* dq_full = kv_empty + 1;    // dQ of the group's tiles complete (all key blocks)
-  uint64_t* dq_empty = dq_full + 1;    // WG2 drained dQ (128 arrivals)
+  uint64_t* dq_empty = dq_full + 1;    // WG2 drained dQ (4 warp arrivals)
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(dq_empty + 1);
   int* n_units_s = reinterpret_cast<int*>(tmem_slot + 1);
 
@@ -902,9 +905,10 @@ attn_bwd_hr2_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_const
     tma_prefetch_desc(&tm_q); tma_prefetch_desc(&tm_k); tma_prefetch_desc(&tm_v); tma_prefetch_desc(&tm_do);
     tma_prefetch_desc(&tm_o); tma_prefetch_desc(&tm_qt); tma_prefetch_desc(&tm_kt); tma_prefetch_desc(&tm_vt);
     tma_prefetch_desc(&tm_dot); tma_prefetch_desc(&tm_ot);
+    tma_prefetch_desc(&tm_g); tma_prefetch_desc(&tm_gt); tma_prefetch_desc(&tm_h); tma_prefetch_desc(&tm_ht);
     mbar_init(full, 1); mbar_init(empty, 1);
-    for (int b = 0; b < 2; ++b) { mbar_init(&s_full[b], 1); mbar_init(&pds_full[b], 256); mbar_init(&ds_free[b], 1); }
-    mbar_init(kv_full, 1); mbar_init(kv_empty, 128); mbar_init(dq_full, 1); mbar_init(dq_empty, 128);
+    for (int b = 0; b < 2; ++b) { mbar_init(&s_full[b], 1); mbar_init(&pds_full[b], 8); mbar_init(&ds_free[b], 1); }
+    mbar_init(kv_full, 1); mbar_init(kv_empty, 4); mbar_init(dq_full, 1); mbar_init(dq_empty, 4);
     fence_mbar_init();
   }
   if (warp == 13) {
@@ -1130,59 +1134,80 @@ attn_bwd_hr2_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_const
         }
         fence_proxy_async_smem();
         tc_fence_before();
-        mbar_arrive(&pds_full[b]);
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&pds_full[b]);
         tr(14);
       }
     }
   } else {
     // ------------------------------------------------------------ WG2: gradients out (same accumulators as v1)
+    // Every gradient tile leaves as bulk TMA stores out of ONE swizzled [rows][64] staging box: token-major into dqkv
+    // (4-D map: rows l * NB + n, head column block) and, for dV' / dQ', head-major into d(delta).  Per-thread 16-byte
+    // stores of row-strided data cost 32 LSU wavefronts per instruction and kept the MIO queue of every sub-partition
+    // busy for ~16 k cycles per head (and the next head's first MMAs waiting behind them).
     const int quad = warp & 3;
     const int row = quad * 32 + lane;
     const uint32_t t_row = tmem_base + (static_cast<uint32_t>(quad * 32) << 16);
-    const size_t plane = static_cast<size_t>(G.heads) * L * 64;
+    uint8_t* rp = stg + row * 128;
+    const int r7 = row & 7;
+    const bool has_hm = p.ddelta != nullptr;
+    auto leader = [&]() { return warp == 8 && elect_one(); };
+    // TMEM columns [col, col + 64) of this thread's lane -> its row of the staging box, scaled
+    auto stage_rows = [&](uint32_t col, float sc, bool active) {
+      if (leader()) tma_store_wait_read<0>();   // the previous stores have read the box
+      named_bar_sync(3, 128);
+      if (active) {
+#pragma unroll
+        for (int c = 0; c < 64; c += 32) {
+          uint32_t v[32];
+          tmem_ld_32x32(t_row + col + c, v);
+          tmem_ld_wait();
+#pragma unroll
+          for (int q = 0; q < 4; ++q)
+            *reinterpret_cast<uint4*>(rp + ((((c >> 3) + q) ^ r7) << 4)) =
+                make_uint4(pack_bf16(__uint_as_float(v[8 * q]) * sc, __uint_as_float(v[8 * q + 1]) * sc),
+                           pack_bf16(__uint_as_float(v[8 * q + 2]) * sc, __uint_as_float(v[8 * q + 3]) * sc),
+                           pack_bf16(__uint_as_float(v[8 * q + 4]) * sc, __uint_as_float(v[8 * q + 5]) * sc),
+                           pack_bf16(__uint_as_float(v[8 * q + 6]) * sc, __uint_as_float(v[8 * q + 7]) * sc));
+        }
+      }
+    };
     int kvc = 0, gc = 0;
     for (int k = 0; k < n_local; ++k) {
       const int g = blockIdx.x + k * gridDim.x;
       const int n = g / G.H, h = g - n * G.H;
       for (int tg = 0; tg < ngroups; ++tg, ++gc) {
         const int ntg = tiles_in_group(tg);
-        const bool add_prev = tg > 0;
+        const bool add_prev = tg > 0;  // a previous group of this head already stored its dK / dV share: reduce-add
         for (int j = 0; j < nt; ++j, ++kvc) {
-          const int lk = j * 128 + row;
-          const bool valid = row < hr_rows(G, j);
-          const bool active = quad * 32 < hr_rows(G, j);
-          bf16* tok = p.dqkv + (static_cast<size_t>(valid ? lk : 0) * G.NB + n) * p.ld + h * 64;
-          bf16* hm = p.ddelta != nullptr ? p.ddelta + plane + (static_cast<size_t>(g) * L + (valid ? lk : 0)) * 64 : nullptr;
+          const bool tail = j == nt - 1;
+          const bool active = quad * 32 < hr_rows16(G, j);
           mbar_wait(kv_full, kvc & 1);
           tc_fence_after();
           tr(20);
-          if (active) {
 #pragma unroll 1
-            for (int part = 0; part < 2; ++part) {  // 0: dV', 1: dK
-              bf16* dst_tok = tok + (part == 0 ? 2 * G.D : G.D);
-#pragma unroll
-              for (int c = 0; c < 64; c += 32) {
-                uint32_t v[32];
-                tmem_ld_32x32(t_row + 256 + part * 64 + c, v);
-                tmem_ld_wait();
-                if (valid) {
-#pragma unroll
-                  for (int jj = 0; jj < 32; jj += 8) {
-                    float f[8];
-#pragma unroll
-                    for (int t8 = 0; t8 < 8; ++t8) f[t8] = __uint_as_float(v[jj + t8]);
-                    if (add_prev) add_bf16x8(f, *reinterpret_cast<const uint4*>(dst_tok + c + jj));
-                    const uint4 o = make_uint4(pack_bf16(f[0], f[1]), pack_bf16(f[2], f[3]), pack_bf16(f[4], f[5]),
-                                               pack_bf16(f[6], f[7]));
-                    *reinterpret_cast<uint4*>(dst_tok + c + jj) = o;
-                    if (part == 0 && hm != nullptr) *reinterpret_cast<uint4*>(hm + c + jj) = o;
-                  }
-                }
+          for (int part = 0; part < 2; ++part) {  // 0: dV', 1: dK
+            stage_rows(256 + part * 64, 1.f, active);
+            if (part == 1) {  // both accumulators are in registers / the box: the next key block may overwrite them
+              tc_fence_before();
+              __syncwarp();
+              if (lane == 0) mbar_arrive(kv_empty);
+            }
+            fence_proxy_async_smem();
+            named_bar_sync(3, 128);
+            if (leader()) {
+              const int hb = (part == 0 ? 2 * G.H : G.H) + h;  // dqkv column blocks: [dq | dk | dv] heads
+              if (add_prev) {
+                tma_store_wait_all<0>();  // the first group's stores of these rows have landed
+                tma_reduce_add_4d(tail ? &tm_gt : &tm_g, stg, 0, hb, n, j * 128);
+                if (part == 0 && has_hm) tma_reduce_add_3d(tail ? &tm_ht : &tm_h, stg, 0, j * 128, G.heads + g);
+              } else {
+                tma_store_4d(tail ? &tm_gt : &tm_g, stg, 0, hb, n, j * 128);
+                if (part == 0 && has_hm) tma_store_3d(tail ? &tm_ht : &tm_h, stg, 0, j * 128, G.heads + g);
               }
+              tma_store_commit();
             }
           }
-          tc_fence_before();
-          mbar_arrive(kv_empty);
           tr(21);
         }
         mbar_wait(dq_full, gc & 1);
@@ -1190,38 +1215,29 @@ attn_bwd_hr2_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_const
         tr(23);
         for (int tt = 0; tt < ntg; ++tt) {
           const int t = 2 * tg + tt;
-          const int lq = t * 128 + row;
-          const bool valid = row < hr_rows(G, t);
-          if (quad * 32 < hr_rows(G, t)) {
-            bf16* dst_tok = p.dqkv + (static_cast<size_t>(valid ? lq : 0) * G.NB + n) * p.ld + h * 64;
-            bf16* dst_hm = p.ddelta != nullptr ? p.ddelta + (static_cast<size_t>(g) * L + (valid ? lq : 0)) * 64 : nullptr;
-#pragma unroll
-            for (int c = 0; c < 64; c += 32) {
-              uint32_t v[32];
-              tmem_ld_32x32(t_row + 384 + tt * 64 + c, v);
-              tmem_ld_wait();
-              if (valid) {
-#pragma unroll
-                for (int jj = 0; jj < 32; jj += 8) {
-                  float f[8];
-#pragma unroll
-                  for (int t8 = 0; t8 < 8; ++t8) f[t8] = __uint_as_float(v[jj + t8]);
-                  *reinterpret_cast<uint4*>(dst_tok + c + jj) =
-                      make_uint4(pack_bf16(f[0] * 0.125f, f[1] * 0.125f), pack_bf16(f[2] * 0.125f, f[3] * 0.125f),
-                                 pack_bf16(f[4] * 0.125f, f[5] * 0.125f), pack_bf16(f[6] * 0.125f, f[7] * 0.125f));
-                  if (dst_hm != nullptr)
-                    *reinterpret_cast<uint4*>(dst_hm + c + jj) = make_uint4(pack_bf16(f[0], f[1]), pack_bf16(f[2], f[3]),
-                                                                           pack_bf16(f[4], f[5]), pack_bf16(f[6], f[7]));
-                }
-              }
+          const bool tail = t == nt - 1;
+          const bool active = quad * 32 < hr_rows16(G, t);
+          // token-major dQ = dQ' / 8 (q' = q / 8), head-major d(delta_q) = dQ': two passes over the same accumulator
+          for (int pass = 0; pass < (has_hm ? 2 : 1); ++pass) {
+            stage_rows(384 + tt * 64, pass == 0 ? 0.125f : 1.f, active);
+            if (tt == ntg - 1 && pass == (has_hm ? 1 : 0)) {
+              tc_fence_before();
+              __syncwarp();
+              if (lane == 0) mbar_arrive(dq_empty);
+            }
+            fence_proxy_async_smem();
+            named_bar_sync(3, 128);
+            if (leader()) {
+              if (pass == 0) tma_store_4d(tail ? &tm_gt : &tm_g, stg, 0, h, n, t * 128);
+              else tma_store_3d(tail ? &tm_ht : &tm_h, stg, 0, t * 128, g);
+              tma_store_commit();
             }
           }
         }
-        tc_fence_before();
-        mbar_arrive(dq_empty);
         tr(24);
       }
     }
+    if (leader()) tma_store_wait_all<0>();  // shared memory must outlive the last stores
   }
 
   tc_fence_before();
@@ -1279,7 +1295,7 @@ int attn_fwd_hr(cudaStream_t s, const AttnShape& a, const bf16* q, const bf16* k
 bool attn_bwd_hr_supported(const AttnShape& a) {
   if (!attn_hr_supported(a)) return false;
   const HrGeom g = make_geom(a);
-  return 4 * g.tensor_bytes + 4 * TILE_BYTES + HB_VEC_BYTES + HB2_MAX_UNITS * static_cast<int>(sizeof(HrUnit)) + 256 + 1024 <= 227 * 1024 &&
+  return 4 * g.tensor_bytes + 5 * TILE_BYTES + HB_VEC_BYTES + HB2_MAX_UNITS * static_cast<int>(sizeof(HrUnit)) + 256 + 1024 <= 227 * 1024 &&
          a.L <= 384;
 }
 
@@ -1299,7 +1315,16 @@ int attn_bwd_hr(cudaStream_t s, const AttnShape& a, const bf16* q, const bf16* k
   if (make_tmap_bf16_tok_heads(&to, o_tok, a.L, a.NB, a.H, a.D, 128) != 0) return -1;
   if (make_tmap_bf16_tok_heads(&tdot, do_tok, a.L, a.NB, a.H, a.D, g.tail16) != 0) return -1;
   if (make_tmap_bf16_tok_heads(&tot, o_tok, a.L, a.NB, a.H, a.D, g.tail16) != 0) return -1;
-  const int smem_bytes = 4 * g.tensor_bytes + 4 * TILE_BYTES + HB_VEC_BYTES + HB2_MAX_UNITS * static_cast<int>(sizeof(HrUnit)) + 256 + 1024;
+  // gradient stores: token-major dqkv as [64][3 H column blocks][NB][L], head-major d(delta) as [64][L][2 planes x heads]
+  CUtensorMap tg_, tgt, th, tht;
+  if (make_tmap_bf16_tok_heads(&tg_, dqkv, a.L, a.NB, 3 * a.H, ld_dqkv, 128) != 0) return -1;
+  if (make_tmap_bf16_tok_heads(&tgt, dqkv, a.L, a.NB, 3 * a.H, ld_dqkv, g.tail16) != 0) return -1;
+  th = tg_; tht = tgt;
+  if (ddelta != nullptr) {
+    if (make_tmap_bf16_hm3d(&th, ddelta, a.L, 2 * g.heads, 128) != 0) return -1;
+    if (make_tmap_bf16_hm3d(&tht, ddelta, a.L, 2 * g.heads, g.tail16) != 0) return -1;
+  }
+  const int smem_bytes = 4 * g.tensor_bytes + 5 * TILE_BYTES + HB_VEC_BYTES + HB2_MAX_UNITS * static_cast<int>(sizeof(HrUnit)) + 256 + 1024;
   TraceHost trace;
   BwdHrParams p{g, ld_dqkv, lse, dqkv, ddelta, trace.begin(HB_THREADS / 32)};
   static const bool use_v1 = getenv("PEVIT_ATTN_BWD_V1") != nullptr;  // diagnostics: the serialised first version
@@ -1313,8 +1338,12 @@ int attn_bwd_hr(cudaStream_t s, const AttnShape& a, const bf16* q, const bf16* k
     configured[dev & 63] = true;
   }
   ProfScope prof(s, PC_ATTN_BWD);
-  PEVIT_CHECK_CUDA(launch_kernel(use_v1 ? attn_bwd_hr_kernel : attn_bwd_hr2_kernel, dim3(grid), dim3(HB_THREADS), smem_bytes, s, 1,
-                                 tq, tk, tv, tdo, to, tqt, tkt, tvt, tdot, tot, p));
+  if (use_v1)
+    PEVIT_CHECK_CUDA(launch_kernel(attn_bwd_hr_kernel, dim3(grid), dim3(HB_THREADS), smem_bytes, s, 1,
+                                   tq, tk, tv, tdo, to, tqt, tkt, tvt, tdot, tot, p));
+  else
+    PEVIT_CHECK_CUDA(launch_kernel(attn_bwd_hr2_kernel, dim3(grid), dim3(HB_THREADS), smem_bytes, s, 1,
+                                   tq, tk, tv, tdo, to, tqt, tkt, tvt, tdot, tot, tg_, tgt, th, tht, p));
   PEVIT_CHECK_LAUNCH();
   trace.end(s, "bwd");
   return 0;
