@@ -139,7 +139,7 @@ attn_fwd_hr_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_consta
                    const __grid_constant__ CUtensorMap tm_v, const __grid_constant__ CUtensorMap tm_qt,
                    const __grid_constant__ CUtensorMap tm_kt, const __grid_constant__ CUtensorMap tm_vt, FwdHrParams p) {
   extern __shared__ uint8_t smem_raw[];
-  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  uint8_t* smem = smem_align1024(smem_raw);
   const HrGeom& G = p.g;
   const int stage_bytes = 3 * G.tensor_bytes;
   float2* stats = reinterpret_cast<float2*>(smem + p.nstage * stage_bytes);
@@ -499,7 +499,7 @@ attn_bwd_hr_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_consta
                    const __grid_constant__ CUtensorMap tm_kt, const __grid_constant__ CUtensorMap tm_vt,
                    const __grid_constant__ CUtensorMap tm_dot, const __grid_constant__ CUtensorMap tm_ot, BwdHrParams p) {
   extern __shared__ uint8_t smem_raw[];
-  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  uint8_t* smem = smem_align1024(smem_raw);
   const HrGeom& G = p.g;
   const int TB = G.tensor_bytes;
   uint8_t* sQ = smem;
@@ -839,7 +839,7 @@ attn_bwd_hr2_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_const
                     const __grid_constant__ CUtensorMap tm_g, const __grid_constant__ CUtensorMap tm_gt,
                     const __grid_constant__ CUtensorMap tm_h, const __grid_constant__ CUtensorMap tm_ht, BwdHrParams p) {
   extern __shared__ uint8_t smem_raw[];
-  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  uint8_t* smem = smem_align1024(smem_raw);
   const HrGeom& G = p.g;
   const int TB = G.tensor_bytes;
   uint8_t* sQ = smem;
@@ -987,7 +987,9 @@ attn_bwd_hr2_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_const
       tc_fence_after();
       tr(1);
       issue_mma1(units[0], ug++);
+      tr(46);
       if (n_units > 1) issue_mma1(units[1], ug++);
+      tr(47);
       for (int ui = 0; ui < n_units; ++ui, ++uc) {
         const HrUnit u = units[ui];
         const int b = static_cast<int>(uc & 1);
@@ -1076,7 +1078,9 @@ attn_bwd_hr2_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_const
           vlse[l] = l < L ? lse_r[i] : 0.f;
         }
       }
+      tr(16);
       named_bar_sync(1, 256);  // delta / lse of the head visible to both warpgroups; the O tiles may now be overwritten
+      tr(17);
       for (int ui = 0; ui < n_units; ++ui, ++uc) {
         const HrUnit u = units[ui];
         const int b = static_cast<int>(uc & 1);

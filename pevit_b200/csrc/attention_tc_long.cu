@@ -49,7 +49,7 @@ __global__ void __launch_bounds__(FL_THREADS, 1)
 attn_fwd_long_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant__ CUtensorMap tm_k,
                      const __grid_constant__ CUtensorMap tm_v, FwdLongParams p) {
   extern __shared__ uint8_t smem_raw[];
-  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  uint8_t* smem = smem_align1024(smem_raw);
   uint8_t* sP = smem + FL_STAGES * FL_STAGE_BYTES;
   float2* stats = reinterpret_cast<float2*>(sP + 2 * FL_P_BYTES);  // [item parity][block j][row] = (max, sum)
   uint64_t* bars = reinterpret_cast<uint64_t*>(reinterpret_cast<uint8_t*>(stats) + FL_STATS_BYTES);
@@ -283,7 +283,7 @@ attn_bwd_long_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_cons
                      const __grid_constant__ CUtensorMap tm_v, const __grid_constant__ CUtensorMap tm_do,
                      const __grid_constant__ CUtensorMap tm_o, BwdLongParams p) {
   extern __shared__ uint8_t smem_raw[];
-  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  uint8_t* smem = smem_align1024(smem_raw);
   uint8_t* sP = smem + BL_STAGES * BL_STAGE_BYTES;
   uint8_t* sdS = sP + BL_P_BYTES;
   uint64_t* bars = reinterpret_cast<uint64_t*>(sdS + BL_P_BYTES);

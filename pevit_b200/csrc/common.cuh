@@ -200,6 +200,12 @@ __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
     }
   }
 }
+// First 1024-byte aligned address of the dynamic shared memory, as POINTER ARITHMETIC on the __shared__ array: an
+// integer round trip (uintptr_t + mask) makes the compiler forget the address space, and every access through the
+// result becomes a generic LD / ST (the local/global pipe, "lg" stalls) instead of LDS / STS.
+__device__ __forceinline__ uint8_t* smem_align1024(uint8_t* raw) {
+  return raw + ((1024u - (static_cast<uint32_t>(__cvta_generic_to_shared(raw)) & 1023u)) & 1023u);
+}
 // generic-proxy writes to smem -> visible to the async proxy (UMMA / TMA reads)
 __device__ __forceinline__ void fence_proxy_async_smem() {
   asm volatile("fence.proxy.async.shared::cta;" ::: "memory");

@@ -37,7 +37,7 @@ atb_tc_kernel(const __grid_constant__ AtbBatch batch) {
   const CUtensorMap& tm_b = batch.tm_b[blockIdx.z];
   const AtbParams& p = batch.p[blockIdx.z];
   extern __shared__ uint8_t smem_raw[];
-  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  uint8_t* smem = smem_align1024(smem_raw);
   uint64_t* full = reinterpret_cast<uint64_t*>(smem + ATB_STAGES * ATB_STAGE_BYTES);
   uint64_t* empty = full + ATB_STAGES;
   uint64_t* done = empty + ATB_STAGES;

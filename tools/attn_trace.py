@@ -12,7 +12,8 @@ NAMES = {1: "mma:operands landed", 2: "mma:S/MMA1 issued", 3: "mma:P ready (p_fu
          10: "wg:S ready", 11: "wg:loaded+max", 12: "wg:after named barrier", 13: "wg:exp done, st issued",
          14: "wg:arrived", 15: "wg:ds_free", 20: "out:acc full", 21: "out:kv drained", 22: "out:stored",
          23: "out:dq full", 24: "out:dq drained", 30: "tma:stage free, loads issued", 40: "mma:S mmas issued", 41: "mma:S committed",
-         42: "mma:fence done", 43: "mma:PV/dV mmas issued", 44: "mma:dK mmas issued", 45: "mma:dQ mmas issued"}
+         42: "mma:fence done", 43: "mma:PV/dV mmas issued", 44: "mma:dK mmas issued", 45: "mma:dQ mmas issued", 16: "wg:delta computed", 17: "wg:delta barrier passed",
+         46: "mma:first MMA1 of head issued", 47: "mma:second MMA1 of head issued"}
 
 
 def main():
