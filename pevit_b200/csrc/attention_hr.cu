@@ -108,7 +108,12 @@ constexpr int HF_THREADS = 512;  // softmax WG0, softmax WG1, merge WG, [TMA war
 constexpr int HF_MAXKB = 4;      // key blocks per head
 constexpr int HF_MAXCOLS = 112;  // keys per block = score columns per softmax thread
 constexpr int HF_MAXBUF = 3;     // score buffers in TMEM
-constexpr int HF_STATS_BYTES = 2 * HF_MAXKB * 128 * 8;  // [tile parity][key block][row] (max, sum)
+// Row statistics of the tiles in flight.  The softmax warpgroups run up to nbuf - 1 units ahead of the P V pointer, which
+// itself waits for the merge warpgroup at every tile boundary: while the merge reads tile T-1 the softmax may already
+// be writing tile T+1, so two slots are NOT enough (compute-sanitizer racecheck found exactly that; a perturbed run
+// produced wrong rows).  Four slots, indexed by the tile counter & 3.
+constexpr int HF_STATS_SLOTS = 4;
+constexpr int HF_STATS_BYTES = HF_STATS_SLOTS * HF_MAXKB * 128 * 8;  // [tile & 3][key block][row] (max, sum)
 
 struct FwdHrParams {
   HrGeom g;
@@ -262,7 +267,7 @@ attn_fwd_hr_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_consta
             else tmem_st_32x8(t_row + (c >> 1), *reinterpret_cast<const uint32_t(*)[8]>(&pk[0]));
           }
         }
-        stats[((tc & 1) * HF_MAXKB + jb) * 128 + row] = make_float2(mx, (s4[0] + s4[1]) + (s4[2] + s4[3]));
+        stats[((tc & (HF_STATS_SLOTS - 1)) * HF_MAXKB + jb) * 128 + row] = make_float2(mx, (s4[0] + s4[1]) + (s4[2] + s4[3]));
         tr(13);
         tmem_st_wait();
       }
@@ -368,7 +373,7 @@ attn_fwd_hr_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_consta
       tc_fence_after();
       tr(20);
       if (active) {
-        const float2* st = stats + (tc & 1) * HF_MAXKB * 128 + row;  // [jb][row]
+        const float2* st = stats + (tc & (HF_STATS_SLOTS - 1)) * HF_MAXKB * 128 + row;  // [jb][row]
         float w[HF_MAXKB], m = -INFINITY, l = 0.f;
         float2 ms[HF_MAXKB];
 #pragma unroll
@@ -1159,32 +1164,25 @@ attn_bwd_hr2_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_const
     const int r7 = row & 7;
     const bool has_hm = p.ddelta != nullptr;
     auto leader = [&]() { return warp == 8 && elect_one(); };
-    // TMEM columns [col, col + 64) of this thread's lane -> 32 registers of bf16 pairs (scaled).  The accumulators are
-    // handed back to the MMA warp as soon as they are in registers; the box rounds below then run at the TMA store's
-    // pace (~1200 cycles per 128 row-strided rows) without holding up the tensor pipe.
-    auto load_pack = [&](uint32_t col, float sc, bool active, uint32_t (&pk)[32]) {
-      if (!active) return;
-#pragma unroll
-      for (int c = 0; c < 64; c += 32) {
-        uint32_t v[32];
-        tmem_ld_32x32(t_row + col + c, v);
-        tmem_ld_wait();
-#pragma unroll
-        for (int i = 0; i < 16; ++i)
-          pk[(c >> 1) + i] = pack_bf16(__uint_as_float(v[2 * i]) * sc, __uint_as_float(v[2 * i + 1]) * sc);
-      }
-    };
-    // 32 packed registers -> this thread's row of the staging box (once the previous stores have read it) -> visible to TMA
-    auto fill_box = [&](const uint32_t (&pk)[32], bool active) {
-      if (leader()) tma_store_wait_read<0>();
+    // TMEM columns [col, col + 64) of this thread's lane -> its row of the staging box, scaled
+    auto stage_rows = [&](uint32_t col, float sc, bool active) {
+      if (leader()) tma_store_wait_read<0>();   // the previous stores have read the box
       named_bar_sync(3, 128);
       if (active) {
 #pragma unroll
-        for (int q = 0; q < 8; ++q)
-          *reinterpret_cast<uint4*>(rp + ((q ^ r7) << 4)) = make_uint4(pk[4 * q], pk[4 * q + 1], pk[4 * q + 2], pk[4 * q + 3]);
+        for (int c = 0; c < 64; c += 32) {
+          uint32_t v[32];
+          tmem_ld_32x32(t_row + col + c, v);
+          tmem_ld_wait();
+#pragma unroll
+          for (int q = 0; q < 4; ++q)
+            *reinterpret_cast<uint4*>(rp + ((((c >> 3) + q) ^ r7) << 4)) =
+                make_uint4(pack_bf16(__uint_as_float(v[8 * q]) * sc, __uint_as_float(v[8 * q + 1]) * sc),
+                           pack_bf16(__uint_as_float(v[8 * q + 2]) * sc, __uint_as_float(v[8 * q + 3]) * sc),
+                           pack_bf16(__uint_as_float(v[8 * q + 4]) * sc, __uint_as_float(v[8 * q + 5]) * sc),
+                           pack_bf16(__uint_as_float(v[8 * q + 6]) * sc, __uint_as_float(v[8 * q + 7]) * sc));
+        }
       }
-      fence_proxy_async_smem();
-      named_bar_sync(3, 128);
     };
     int kvc = 0, gc = 0;
     for (int k = 0; k < n_local; ++k) {
@@ -1196,17 +1194,19 @@ attn_bwd_hr2_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_const
         for (int j = 0; j < nt; ++j, ++kvc) {
           const bool tail = j == nt - 1;
           const bool active = quad * 32 < hr_rows16(G, j);
-          uint32_t pv[32], pk_[32];
           mbar_wait(kv_full, kvc & 1);
           tc_fence_after();
           tr(20);
-          load_pack(256, 1.f, active, pv);   // dV'
-          load_pack(320, 1.f, active, pk_);  // dK
-          tc_fence_before();
-          __syncwarp();
-          if (lane == 0) mbar_arrive(kv_empty);
-          tr(21);
-          auto store_kv = [&](int part) {  // 0: dV', 1: dK (the box has just been filled)
+#pragma unroll 1
+          for (int part = 0; part < 2; ++part) {  // 0: dV', 1: dK
+            stage_rows(256 + part * 64, 1.f, active);
+            if (part == 1) {  // both accumulators are in registers / the box: the next key block may overwrite them
+              tc_fence_before();
+              __syncwarp();
+              if (lane == 0) mbar_arrive(kv_empty);
+            }
+            fence_proxy_async_smem();
+            named_bar_sync(3, 128);
             if (leader()) {
               const int hb = (part == 0 ? 2 * G.H : G.H) + h;  // dqkv column blocks: [dq | dk | dv] heads
               if (add_prev) {
@@ -1219,11 +1219,8 @@ attn_bwd_hr2_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_const
               }
               tma_store_commit();
             }
-          };
-          fill_box(pv, active);
-          store_kv(0);
-          fill_box(pk_, active);
-          store_kv(1);
+          }
+          tr(21);
         }
         mbar_wait(dq_full, gc & 1);
         tc_fence_after();
@@ -1232,23 +1229,24 @@ attn_bwd_hr2_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_const
           const int t = 2 * tg + tt;
           const bool tail = t == nt - 1;
           const bool active = quad * 32 < hr_rows16(G, t);
-          // token-major dQ = dQ' / 8 (q' = q / 8), head-major d(delta_q) = dQ'
-          uint32_t ps[32], pu[32];
-          load_pack(384 + tt * 64, 0.125f, active, ps);
-          if (has_hm) load_pack(384 + tt * 64, 1.f, active, pu);
-          if (tt == ntg - 1) {
-            tc_fence_before();
-            __syncwarp();
-            if (lane == 0) mbar_arrive(dq_empty);
-            tr(24);
-          }
-          fill_box(ps, active);
-          if (leader()) { tma_store_4d(tail ? &tm_gt : &tm_g, stg, 0, h, n, t * 128); tma_store_commit(); }
-          if (has_hm) {
-            fill_box(pu, active);
-            if (leader()) { tma_store_3d(tail ? &tm_ht : &tm_h, stg, 0, t * 128, g); tma_store_commit(); }
+          // token-major dQ = dQ' / 8 (q' = q / 8), head-major d(delta_q) = dQ': two passes over the same accumulator
+          for (int pass = 0; pass < (has_hm ? 2 : 1); ++pass) {
+            stage_rows(384 + tt * 64, pass == 0 ? 0.125f : 1.f, active);
+            if (tt == ntg - 1 && pass == (has_hm ? 1 : 0)) {
+              tc_fence_before();
+              __syncwarp();
+              if (lane == 0) mbar_arrive(dq_empty);
+            }
+            fence_proxy_async_smem();
+            named_bar_sync(3, 128);
+            if (leader()) {
+              if (pass == 0) tma_store_4d(tail ? &tm_gt : &tm_g, stg, 0, h, n, t * 128);
+              else tma_store_3d(tail ? &tm_ht : &tm_h, stg, 0, t * 128, g);
+              tma_store_commit();
+            }
           }
         }
+        tr(24);
       }
     }
     if (leader()) tma_store_wait_all<0>();  // shared memory must outlive the last stores

@@ -17,15 +17,14 @@
 namespace pevit {
 namespace {
 
-// Which single-lane guard each role of the backward kernel uses (overridable for A/B builds).  Measured on B200 at
-// L = 50, N = 256: issuing the MMAs from `lane == 0` (ptxas then wraps every UTCHMMA in a ~100-cycle waterfall loop, i.e. the
-// 24 MMA2 instructions trickle out over ~3000 cycles) is FASTER than the back-to-back issue elect.sync allows, 55.3 vs
-// 61.4 us: the burst saturates shared-memory bandwidth exactly when WG0 stores P / dS of the next tile.
+// Which single-lane guard each role of the backward kernel uses (overridable for A/B builds).  History: while the P / dS
+// staging stores were still generic ST (see smem_align1024), back-to-back MMA issue through elect.sync measured SLOWER
+// than `lane == 0` here (61.4 vs 55.3 us at L = 50, N = 256); with shared-space stores both measure 53.2 us.
 #ifndef BWD_TMA_ONE
 #define BWD_TMA_ONE elect_one()
 #endif
 #ifndef BWD_MMA_ONE
-#define BWD_MMA_ONE (lane == 0)
+#define BWD_MMA_ONE elect_one()
 #endif
 #ifndef BWD_WG1_ONE
 #define BWD_WG1_ONE elect_one()
