@@ -454,6 +454,7 @@ constexpr int HB_VEC_BYTES = 2 * 2 * 128 * HR_MAXT * 4;  // [head parity][delta 
 struct BwdHrParams {
   HrGeom g;
   int ld;
+  int nbox;      // staging boxes for the gradient stores (v2): 2 when shared memory allows, else 1
   const float* lse;
   bf16* dqkv;
   bf16* ddelta;  // nullable
@@ -854,8 +855,8 @@ attn_bwd_hr2_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_const
   uint8_t* sdO = smem + 3 * TB;
   uint8_t* sDS = smem + 4 * TB;      // [pair parity][q half][128 key rows][64 query cols] bf16: dS^T of the current pairs
   uint8_t* sO = sDS;                 // O tiles of the head, only until delta is formed
-  uint8_t* stg = sDS + 4 * TILE_BYTES;  // [128 rows][64] bf16 box the gradients leave through (TMA store)
-  float* vecs = reinterpret_cast<float*>(stg + TILE_BYTES);  // [parity][0: delta, 1: lse * log2e][384]
+  uint8_t* stg = sDS + 4 * TILE_BYTES;  // nbox x [128 rows][64] bf16 boxes the gradients leave through (TMA store)
+  float* vecs = reinterpret_cast<float*>(stg + p.nbox * TILE_BYTES);  // [parity][0: delta, 1: lse * log2e][384]
   HrUnit* units = reinterpret_cast<HrUnit*>(reinterpret_cast<uint8_t*>(vecs) + HB_VEC_BYTES);
   uint64_t* bars = reinterpret_cast<uint64_t*>(units + HB2_MAX_UNITS);
   uint64_t* full = bars;               // head operands landed
@@ -1104,6 +1105,9 @@ attn_bwd_hr2_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_const
         tr(10);
         // the dS^T tile of this pair was last read by the dQ product two pairs ago
         if (u.h == 0) { mbar_wait(&ds_free[pg & 1], static_cast<uint32_t>(((pg >> 1) & 1) ^ 1)); tr(15); }
+        // (measured: giving each warpgroup its own unit -- all 64 columns, no shared unit -- is SLOWER, 581 vs 563 us at
+        // L = 197: the MMA warp issues ~20 instructions per unit at ~65 cycles each (A-operand fetch bound), so a
+        // warpgroup that owns a buffer alone waits ~1800 cycles for its next scores; sharing every unit halves that.)
         if (active && ncols > 0) {
           const uint32_t ts = t_lane + b * 128 + wg * 32, tdp = ts + 64;
           uint32_t sv[32], dv[32];
@@ -1160,13 +1164,21 @@ attn_bwd_hr2_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_const
     const int quad = warp & 3;
     const int row = quad * 32 + lane;
     const uint32_t t_row = tmem_base + (static_cast<uint32_t>(quad * 32) << 16);
-    uint8_t* rp = stg + row * 128;
     const int r7 = row & 7;
     const bool has_hm = p.ddelta != nullptr;
+    const bool two_boxes = p.nbox == 2;
+    uint8_t* box = stg;                 // the box being filled / stored (alternates when there are two)
+    uint8_t* rp = box + row * 128;
     auto leader = [&]() { return warp == 8 && elect_one(); };
     // TMEM columns [col, col + 64) of this thread's lane -> its row of the staging box, scaled
     auto stage_rows = [&](uint32_t col, float sc, bool active) {
-      if (leader()) tma_store_wait_read<0>();   // the previous stores have read the box
+      if (two_boxes) {                          // the stores out of THIS box (two rounds ago) have read it
+        box = box == stg ? stg + TILE_BYTES : stg;
+        rp = box + row * 128;
+        if (leader()) tma_store_wait_read<1>();
+      } else if (leader()) {
+        tma_store_wait_read<0>();               // the previous stores have read the box
+      }
       named_bar_sync(3, 128);
       if (active) {
 #pragma unroll
@@ -1211,11 +1223,11 @@ attn_bwd_hr2_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_const
               const int hb = (part == 0 ? 2 * G.H : G.H) + h;  // dqkv column blocks: [dq | dk | dv] heads
               if (add_prev) {
                 tma_store_wait_all<0>();  // the first group's stores of these rows have landed
-                tma_reduce_add_4d(tail ? &tm_gt : &tm_g, stg, 0, hb, n, j * 128);
-                if (part == 0 && has_hm) tma_reduce_add_3d(tail ? &tm_ht : &tm_h, stg, 0, j * 128, G.heads + g);
+                tma_reduce_add_4d(tail ? &tm_gt : &tm_g, box, 0, hb, n, j * 128);
+                if (part == 0 && has_hm) tma_reduce_add_3d(tail ? &tm_ht : &tm_h, box, 0, j * 128, G.heads + g);
               } else {
-                tma_store_4d(tail ? &tm_gt : &tm_g, stg, 0, hb, n, j * 128);
-                if (part == 0 && has_hm) tma_store_3d(tail ? &tm_ht : &tm_h, stg, 0, j * 128, G.heads + g);
+                tma_store_4d(tail ? &tm_gt : &tm_g, box, 0, hb, n, j * 128);
+                if (part == 0 && has_hm) tma_store_3d(tail ? &tm_ht : &tm_h, box, 0, j * 128, G.heads + g);
               }
               tma_store_commit();
             }
@@ -1240,8 +1252,8 @@ attn_bwd_hr2_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_const
             fence_proxy_async_smem();
             named_bar_sync(3, 128);
             if (leader()) {
-              if (pass == 0) tma_store_4d(tail ? &tm_gt : &tm_g, stg, 0, h, n, t * 128);
-              else tma_store_3d(tail ? &tm_ht : &tm_h, stg, 0, t * 128, g);
+              if (pass == 0) tma_store_4d(tail ? &tm_gt : &tm_g, box, 0, h, n, t * 128);
+              else tma_store_3d(tail ? &tm_ht : &tm_h, box, 0, t * 128, g);
               tma_store_commit();
             }
           }
@@ -1336,9 +1348,11 @@ int attn_bwd_hr(cudaStream_t s, const AttnShape& a, const bf16* q, const bf16* k
     if (make_tmap_bf16_hm3d(&th, ddelta, a.L, 2 * g.heads, 128) != 0) return -1;
     if (make_tmap_bf16_hm3d(&tht, ddelta, a.L, 2 * g.heads, g.tail16) != 0) return -1;
   }
-  const int smem_bytes = 4 * g.tensor_bytes + 5 * TILE_BYTES + HB_VEC_BYTES + HB2_MAX_UNITS * static_cast<int>(sizeof(HrUnit)) + 256 + 1024;
+  const int smem_1box = 4 * g.tensor_bytes + 5 * TILE_BYTES + HB_VEC_BYTES + HB2_MAX_UNITS * static_cast<int>(sizeof(HrUnit)) + 256 + 1024;
+  const int nbox = smem_1box + TILE_BYTES <= 227 * 1024 ? 2 : 1;
+  const int smem_bytes = smem_1box + (nbox - 1) * TILE_BYTES;
   TraceHost trace;
-  BwdHrParams p{g, ld_dqkv, lse, dqkv, ddelta, trace.begin(HB_THREADS / 32)};
+  BwdHrParams p{g, ld_dqkv, nbox, lse, dqkv, ddelta, trace.begin(HB_THREADS / 32)};
   static const bool use_v1 = getenv("PEVIT_ATTN_BWD_V1") != nullptr;  // diagnostics: the serialised first version
   const int grid = g.heads < sm_count() ? g.heads : sm_count();
   static bool configured[64] = {};

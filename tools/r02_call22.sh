@@ -1,0 +1,11 @@
+#!/bin/bash
+set -u
+mkdir -p gpurun_out
+O=gpurun_out
+timeout 900 python -m pytest tests/test_gpu_primitives.py -m gpu -q -k "attention" -p no:cacheprovider 2>&1 | tail -3
+for shape in "197 512 768" "257 256 1024" "384 128 768" "129 256 768"; do
+  ATTN_IMPL=0 timeout 180 python tools/attn_bench.py $shape 2>&1 | grep bwd
+done
+PEVIT_ATTN_TRACE=gpurun_out/c22_trace_L197 ATTN_ONCE=1 timeout 120 python tools/attn_bench.py 197 512 768
+PEVIT_ATTN_TRACE=gpurun_out/c22_trace_L257 ATTN_ONCE=1 timeout 120 python tools/attn_bench.py 257 256 1024
+timeout 600 python -m pytest tests/test_gpu_block.py -m gpu -q -p no:cacheprovider -k "b16blk or l14blk" 2>&1 | tail -3
