@@ -70,7 +70,7 @@ attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_consta
   uint64_t* full = bars;                   // [TC_STAGES]
   uint64_t* empty = full + TC_STAGES;      // [TC_STAGES]
   uint64_t* s_full = empty + TC_STAGES;    // [2]
-  uint64_t* p_full = s_full + 2;           // [2]  128 arrivals
+  uint64_t* p_full = s_full + 2;           // [2]  4 warp arrivals
   uint64_t* o_full = p_full + 2;           // [2]
   uint64_t* o_empty = o_full + 2;          // [2]  4 warp arrivals
   uint64_t* p_free = o_empty + 2;          // [2]  the O tile staged in P_b has left through TMA
@@ -92,7 +92,7 @@ attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_consta
     tma_prefetch_desc(&tm_q); tma_prefetch_desc(&tm_k); tma_prefetch_desc(&tm_v); tma_prefetch_desc(&tm_o);
     for (int s = 0; s < TC_STAGES; ++s) { mbar_init(&full[s], 1); mbar_init(&empty[s], 1); }
     for (int b = 0; b < 2; ++b) {
-      mbar_init(&s_full[b], 1); mbar_init(&p_full[b], 128); mbar_init(&o_full[b], 1); mbar_init(&o_empty[b], 4);
+      mbar_init(&s_full[b], 1); mbar_init(&p_full[b], 4); mbar_init(&o_full[b], 1); mbar_init(&o_empty[b], 4);
       mbar_init(&p_free[b], 1);
     }
     fence_mbar_init();
@@ -244,7 +244,8 @@ attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_consta
         stats[(it & 3) * 128 + row] = make_float2(mx, sum);  // read by the epilogue warpgroup after o_full
         fence_proxy_async_smem();
         tc_fence_before();
-        mbar_arrive(&p_full[b]);
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&p_full[b]);  // one arrival per warp: 128 arrivals on one mbarrier serialise (~600 cycles)
       }
     } else {
       // ---------------------------------------------------------- epilogue warpgroup
@@ -354,9 +355,9 @@ attn_bwd_tc_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_consta
   uint64_t* full = bars;                  // [BWD_STAGES]
   uint64_t* empty = full + BWD_STAGES;    // [BWD_STAGES]
   uint64_t* s_full = empty + BWD_STAGES;  // [2]  MMA1 done (per TMEM set)
-  uint64_t* pds_full = s_full + 2;        // WG0 wrote P, dS (128 arrivals)
+  uint64_t* pds_full = s_full + 2;        // WG0 wrote P, dS (4 warp arrivals)
   uint64_t* o2_full = pds_full + 1;       // [2]  MMA2 done (per TMEM set)
-  uint64_t* o2_empty = o2_full + 2;       // [2]  WG1 read dQ/dK/dV out of the set (128 arrivals)
+  uint64_t* o2_empty = o2_full + 2;       // [2]  WG1 read dQ/dK/dV out of the set (4 warp arrivals)
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(o2_empty + 2);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -372,8 +373,8 @@ attn_bwd_tc_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_consta
     tma_prefetch_desc(&tm_q); tma_prefetch_desc(&tm_k); tma_prefetch_desc(&tm_v); tma_prefetch_desc(&tm_do);
     tma_prefetch_desc(&tm_dqkv);
     for (int s = 0; s < BWD_STAGES; ++s) { mbar_init(&full[s], 1); mbar_init(&empty[s], 1); }
-    for (int b = 0; b < 2; ++b) { mbar_init(&s_full[b], 1); mbar_init(&o2_full[b], 1); mbar_init(&o2_empty[b], 128); }
-    mbar_init(pds_full, 128);
+    for (int b = 0; b < 2; ++b) { mbar_init(&s_full[b], 1); mbar_init(&o2_full[b], 1); mbar_init(&o2_empty[b], 4); }
+    mbar_init(pds_full, 4);
     fence_mbar_init();
   }
   if (warp == 9) {
@@ -581,7 +582,8 @@ attn_bwd_tc_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_consta
         }
         fence_proxy_async_smem();
         tc_fence_before();
-        mbar_arrive(pds_full);
+        __syncwarp();
+        if (lane == 0) mbar_arrive(pds_full);
       }
     } else {
       // ---------------------------------------------------------- WG1: gradients out
@@ -604,7 +606,8 @@ attn_bwd_tc_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_consta
           tmem_ld_wait();
           if (part == 2) {  // the set's last columns are in registers: MMA1 of tile it+2 may overwrite it
             tc_fence_before();
-            mbar_arrive(&o2_empty[it & 1]);
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&o2_empty[it & 1]);
           }
           // head-major d(delta) planes (dQ' -> plane 0, dV' -> plane 1): contiguous per head, stored directly
           if (valid && hm != nullptr && part != 1) {
