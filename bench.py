@@ -205,6 +205,27 @@ def gpu_eager_baseline(args, shape, dev, steps=3, warmup=2) -> dict:
     return out
 
 
+def inference_throughput(args, tuner, images, iters=10, warmup=3) -> dict:
+    """the validate / feature-extraction path (kadaptation_clip.py:376-410 ``validate``; feature.py): the
+    same fused blocks under ``torch.no_grad()`` -- ``save = 0`` in the block descriptor, no activation is kept."""
+    with torch.no_grad():
+        for _ in range(warmup):
+            tuner(images)
+        torch.cuda.synchronize()
+        mem0 = torch.cuda.memory_allocated()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(iters):
+            out = tuner(images)
+        e1.record()
+        torch.cuda.synchronize()
+        kept = torch.cuda.memory_allocated() - mem0
+    ms = e0.elapsed_time(e1) / iters
+    return {"images_per_s": images.shape[0] / ms * 1e3, "ms_per_batch": ms, "batch": int(images.shape[0]),
+            "bytes_kept_after_forward": int(kept), "logits_bytes": int(out.numel() * out.element_size()),
+            "what": "Classifier forward (backbone.encode_image + head) under torch.no_grad(), eager launches"}
+
+
 def parity_probe(args, shape, tuner, dev, n=16) -> dict:
     """BASELINE.json's second metric: logits max-abs-err of this path vs the reference algorithm (oracle, fp32, CPU) on
     the same weights and the same n-image batch (F4 couples the samples of a batch, so both sides see the same n)."""
@@ -505,6 +526,8 @@ def run_b200(args):
     }
     tuner.release_graph()
     torch.cuda.synchronize()
+    if world == 1:
+        line["inference"] = inference_throughput(args, tuner, images)
     if world == 1 and not args.no_parity_probe:
         probe = parity_probe(args, shape, tuner, dev)
         line["logits_max_abs_err"] = probe["max_abs_err"]

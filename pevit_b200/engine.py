@@ -78,7 +78,7 @@ class FineTuner(nn.Module):
     def __init__(self, method: str, shape: synth.ClipShape, num_classes: int = 10, device="cuda", lr: float = 1e-3,
                  momentum: float = 0.9, weight_decay: float = 0.0, seed: int = 0, randomize: bool = True,
                  process_group: Optional[dist.ProcessGroup] = None, distributed: bool = False,
-                 fused_tail: Optional[bool] = None):
+                 fused_tail: Optional[bool] = None, without_wd=("bias", "ln")):
         super().__init__()
         self.method = method
         sd = synth.clip_state_dict(shape, seed=seed)
@@ -100,11 +100,24 @@ class FineTuner(nn.Module):
         # flat gradient buffer; every trainable .grad is a view into it
         self.params = [p for p in self.parameters() if p.requires_grad]
         # F2: KAdaptation's v_proj_adapter1_* are trainable by name but never receive a gradient
-        self.used = [p for n, p in self.named_parameters()
-                     if p.requires_grad and not (method == "kadaptation" and "v_proj_adapter1_" in n)]
+        used = [(n, p) for n, p in self.named_parameters()
+                if p.requires_grad and not (method == "kadaptation" and "v_proj_adapter1_" in n)]
+        # Weight-decay groups of the reference's optimizer builder (optim/build.py:18-86 ``_set_wd``): parameters of
+        # LayerNorm modules ('ln') and parameters named *.bias ('bias') go to a zero-weight-decay group.  The flat
+        # buffers keep the decayed parameters first, so the fused update is two launches over two contiguous ranges.
+        ln_params = {id(q) for m in self.modules() if isinstance(m, nn.LayerNorm) for q in m.parameters(recurse=False)}
+        no_wd = [(n, p) for n, p in used if ("ln" in without_wd and id(p) in ln_params) or
+                 ("bias" in without_wd and n.endswith(".bias"))]
+        no_wd_ids = {id(p) for _, p in no_wd}
+        decayed = [(n, p) for n, p in used if id(p) not in no_wd_ids]
+        self.used = [p for _, p in decayed] + [p for _, p in no_wd]
+        self.used_names = [n for n, _ in decayed] + [n for n, _ in no_wd]
+        self.n_decayed = sum(p.numel() for _, p in decayed)
         self.grads = FlatGrads(self.used, device)
         self.flat_grad = self.grads.flat
-        self.opt = torch.optim.SGD(self.used, lr=lr, momentum=momentum, weight_decay=weight_decay)
+        self.opt = torch.optim.SGD([{"params": [p for _, p in decayed]},
+                                    {"params": [p for _, p in no_wd], "weight_decay": 0.0}],
+                                   lr=lr, momentum=momentum, weight_decay=weight_decay)
         # step tail on this library's kernels (ln_post + projection GEMM + head/CE kernel; one SGD kernel over flat
         # parameter / gradient / momentum buffers) instead of ~30 small PyTorch launches; CUDA only
         self.fused_tail = (torch.device(device).type == "cuda") if fused_tail is None else fused_tail
@@ -129,7 +142,13 @@ class FineTuner(nn.Module):
             if self.distributed:
                 self.grads.all_reduce_sum(self.group)
             lr, mu, wd = self.hyper
-            ops.sgd_momentum_(self.flat_params.flat, self.flat_grad, self.flat_momentum, lr, mu, wd, 1.0 / self.world)
+            fp, fg, fm, nd = self.flat_params.flat, self.flat_grad, self.flat_momentum, self.n_decayed
+            if wd == 0.0 or nd == fp.numel():
+                ops.sgd_momentum_(fp, fg, fm, lr, mu, wd, 1.0 / self.world)
+            else:  # decayed range, then the zero-weight-decay group
+                if nd > 0:
+                    ops.sgd_momentum_(fp[:nd], fg[:nd], fm[:nd], lr, mu, wd, 1.0 / self.world)
+                ops.sgd_momentum_(fp[nd:], fg[nd:], fm[nd:], lr, mu, 0.0, 1.0 / self.world)
             return loss.detach()
         loss = F.cross_entropy(self.forward(images), labels)
         loss.backward()

@@ -284,3 +284,44 @@ def test_batched_delta_launch_vs_in_kernel_delta(method):
     assert len(res[0][2]) > 0
     for name in res[0][2]:
         assert rel_inf(res[0][2][name], res[1][2][name]) < 3e-2, name
+
+
+@pytest.mark.parametrize("method", METHODS)
+def test_inference_path_saves_nothing(method):
+    """SURVEY 8f #3 (validate / feature extraction, kadaptation_clip.py:376-410): under ``torch.no_grad()`` the block runs
+    with ``save = 0`` -- the C ABI asks for less than half the buffer of the training forward (forward-internal scratch
+    only), no autograd graph is built, nothing but the output stays allocated, and the features equal those of the training-mode forward."""
+    import ctypes as C
+    from pevit_b200 import _lib as L, ops
+    shape = synth.VIT_TINY
+    sd = synth.clip_state_dict(shape, seed=17)
+    model = BUILDERS[method](dict(sd))
+    synth.randomize_adapters(model.named_parameters(), seed=18)
+    model = model.cuda()
+    freeze_like_reference(model, method)
+    img = synth.images(6, shape.image_resolution, seed=19).cuda()
+    feat_train = model.encode_image(img)
+    assert feat_train.requires_grad
+    del feat_train
+    with torch.no_grad():
+        model.encode_image(img)   # workspaces / packs exist
+        torch.cuda.synchronize()
+        m0 = torch.cuda.memory_allocated()
+        feat = model.encode_image(img)
+        torch.cuda.synchronize()
+        kept = torch.cuda.memory_allocated() - m0
+    assert not feat.requires_grad and feat.grad_fn is None
+    assert kept <= 2 * feat.numel() * feat.element_size() + 4096, f"{kept} bytes stay allocated after a no_grad forward"
+    with torch.enable_grad():
+        ref = model.encode_image(img)
+    assert rel_inf(feat, ref.detach()) < 1e-6
+    blk = model.visual.transformer.resblocks[0]
+    pack = ops.get_pack(blk, blk.method)
+    sizes = {}
+    for save in (0, 1):
+        desc = L.BlockDesc(shape.tokens, 6, shape.vision_width, pack.H, ops.METHOD_IDS[pack.method], pack.r, pack.alpha,
+                           save, 0, save, 0)
+        sizes[save] = L.lib().pevit_block_saved_bytes(C.byref(desc))
+    # save = 0 keeps only what the forward itself passes between its kernels (q/k/v, o, lse: scratch the caller may free
+    # right after the call); the activations the backward needs (x_1, LN outputs, MLP pre-activation, ...) are not kept
+    assert sizes[0] < sizes[1] / 2, sizes
