@@ -15,14 +15,15 @@ import subprocess
 import sys
 
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
-OUT = os.path.join(ROOT, "gpurun_out")
+OUT = os.path.join(ROOT, os.environ.get("PROF_IN", "gpurun_out"))   # PROF_IN: directory the captures were written to
 PROF = os.path.join(ROOT, "profiles")
 METRICS = ["gpu__time_duration.sum", "dram__bytes_read.sum", "dram__bytes_write.sum",
            "sm__pipe_tensor_cycles_active.avg.pct_of_peak_sustained_active",
            "gpu__dram_throughput.avg.pct_of_peak_sustained_elapsed",
            "lts__throughput.avg.pct_of_peak_sustained_elapsed", "l1tex__m_xbar2l1tex_read_bytes.sum",
            "sm__warps_active.avg.pct_of_peak_sustained_active", "launch__registers_per_thread", "launch__grid_size",
-           "launch__block_size", "sm__throughput.avg.pct_of_peak_sustained_elapsed"]
+           "launch__block_size", "sm__throughput.avg.pct_of_peak_sustained_elapsed",
+           "sm__inst_executed_pipe_xu.avg.pct_of_peak_sustained_active", "smsp__issue_active.avg.pct_of_peak_sustained_active"]
 
 
 def launches(tag):
@@ -74,21 +75,23 @@ def full_captures(tag):
         w = csv.DictWriter(fh, fieldnames=["report", "kernel"] + METRICS)
         w.writeheader()
         w.writerows(out_rows)
-    for rec in out_rows:  # dram traffic per launch, keyed like bench.py's kernel classes where unambiguous
+    # DRAM traffic per launch, keyed by bench configuration (model_method_bN) and bench.py's kernel class
+    cfgs = {"c2": "vit_b32_kadaptation_b256", "L197": "vit_b16_lora_b512", "L257": "vit_l14_kadaptation_b256"}
+    for rec in out_rows:
         try:
             b = (float(rec["dram__bytes_read.sum"]) + float(rec["dram__bytes_write.sum"])) * 1e6
         except ValueError:
             continue
-        k = rec["kernel"]
-        if rec["report"].startswith("one_"):   # tools/one_gemm.py captures: one GEMM class per report
-            traffic["gemm_" + rec["report"][4:].split(".")[0]] = b
+        k, rep = rec["kernel"], rec["report"]
+        if rep.startswith("one_"):   # tools/one_gemm.py captures: one GEMM class per report, C2 shapes
+            traffic.setdefault(cfgs["c2"], {})["gemm_" + rep[4:].split(".")[0]] = b
+        elif rep.startswith("hr_"):  # tools/attn_bench.py captures of the head-resident kernels: hr_<fwd|bwd>_L<L>
+            _, kern, ltag = rep.split(".")[0].split("_")
+            traffic.setdefault(cfgs[ltag], {})["attn_" + kern] = b
         elif "attn_fwd_tc" in k:
-            traffic["attn_fwd"] = b
+            traffic.setdefault(cfgs["c2"], {})["attn_fwd"] = b
         elif "attn_bwd_tc" in k:
-            traffic["attn_bwd"] = b
-    extra = os.path.join(OUT, "gemm_class_traffic.json")
-    if os.path.exists(extra):
-        traffic.update(json.load(open(extra)))
+            traffic.setdefault(cfgs["c2"], {})["attn_bwd"] = b
     with open(os.path.join(PROF, "ncu_traffic.json"), "w") as fh:
         json.dump(traffic, fh, indent=1, sort_keys=True)
     print(f"full captures: {len(out_rows)} kernels")
