@@ -63,11 +63,18 @@ def full_captures(tag):
         rows = list(csv.reader(text.splitlines()))
         if len(rows) < 3:
             continue
-        hdr = rows[0]
+        hdr, units = rows[0], rows[1]
+        scale = {"byte": 1e-6, "Kbyte": 1e-3, "Mbyte": 1.0, "Gbyte": 1e3, "ns": 1e-3, "us": 1.0, "ms": 1e3}  # -> MB / us
         for r in rows[2:]:
             rec = {"report": rep, "kernel": r[hdr.index("Kernel Name")]}
             for m in METRICS:
-                rec[m] = r[hdr.index(m)] if m in hdr else ""
+                if m not in hdr:
+                    rec[m] = ""
+                    continue
+                v, u = r[hdr.index(m)], units[hdr.index(m)]
+                if (m.startswith("dram__bytes") or m.startswith("l1tex__m_xbar") or m == "gpu__time_duration.sum") and u in scale:
+                    v = f"{float(v.replace(',', '')) * scale[u]:.3f}"   # normalised: MB and microseconds
+                rec[m] = v
             out_rows.append(rec)
     if not out_rows:
         return
