@@ -1016,10 +1016,14 @@ attn_bwd_hr2_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_const
                          umma_desc_mnmajor_sw128(aDO + rows + kk * 2048, TILE_BYTES), idesc_ts,
                          (!(u.flags & U_FIRST_KV) || kk != 0) ? 1u : 0u);
           tr(43);
-          for (int kk = 0; kk < qsteps; ++kk)   // dK_j (+)= dS^T Q_{t,h}
-            umma_bf16_ts(tmem_base + 320, tmem_base + b * 128 + 64 + (kk >> 1) * 32 + (kk & 1) * 8,
-                         umma_desc_mnmajor_sw128(aQ + rows + kk * 2048, TILE_BYTES), idesc_ts,
-                         (!(u.flags & U_FIRST_KV) || kk != 0) ? 1u : 0u);
+          {                                     // dK_j (+)= dS^T Q_{t,h}: A = the shared-memory dS^T half tile (K-major: 64
+            // query columns per key row).  From TMEM the A operand of an N = 64 product costs 64 cycles (4 KB at 64 B/clk),
+            // twice the math; shared memory delivers it at 128 B/clk, and the warpgroups no longer write dS^T back to TMEM.
+            const uint64_t dds = umma_desc_kmajor_sw128(aDS + static_cast<uint32_t>(pg & 1) * 2 * TILE_BYTES + u.h * TILE_BYTES);
+            for (int kk = 0; kk < qsteps; ++kk)
+              umma_bf16_ss(tmem_base + 320, dds + 2 * kk, umma_desc_mnmajor_sw128(aQ + rows + kk * 2048, TILE_BYTES), idesc_ts,
+                           (!(u.flags & U_FIRST_KV) || kk != 0) ? 1u : 0u);
+          }
           tr(44);
           if (u.flags & U_LAST_HALF) {          // dQ_t (+)= dS_t K_j       (K = stored keys of block j)
             const uint32_t ds = aDS + static_cast<uint32_t>(pg & 1) * 2 * TILE_BYTES;
@@ -1144,8 +1148,8 @@ attn_bwd_hr2_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_const
               *reinterpret_cast<uint4*>(srow + ((ch ^ (row & 7)) << 4)) = make_uint4(pds[4 * q], pds[4 * q + 1], pds[4 * q + 2], pds[4 * q + 3]);
             }
           }
-          if (ncols == 32) { tmem_st_32x16(ts, pp); tmem_st_32x16(tdp, pds); }
-          else { tmem_st_32x8(ts, *reinterpret_cast<const uint32_t(*)[8]>(&pp[0])); tmem_st_32x8(tdp, *reinterpret_cast<const uint32_t(*)[8]>(&pds[0])); }
+          if (ncols == 32) tmem_st_32x16(ts, pp);   // P^T stays in TMEM (A operand of dV); dS^T is read from shared memory
+          else tmem_st_32x8(ts, *reinterpret_cast<const uint32_t(*)[8]>(&pp[0]));
           tr(13);
           tmem_st_wait();
         }
