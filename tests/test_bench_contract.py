@@ -11,7 +11,7 @@ BASE_KEYS = {"metric", "value", "unit", "n_gpus", "steps", "warmup", "ms_per_ste
 
 
 def test_committed_headline_line_has_every_contract_key():
-    with open(os.path.join(ROOT, "profiles", "r01_bench_c2_1gpu.json")) as fh:
+    with open(os.path.join(ROOT, "profiles", "r02_bench_c2_run2.json")) as fh:
         line = json.load(fh)
     with open(os.path.join(ROOT, "BASELINE.json")) as fh:
         base = json.load(fh)
@@ -29,6 +29,13 @@ def test_committed_headline_line_has_every_contract_key():
     assert {"sm_mhz", "sm_max_mhz", "reasons"} <= set(line["clocks"])
     assert not {"hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown"} & set(line["clocks"]["reasons"])
     assert line["gpu_launches"] > 0
+    # round 2: the line also carries north_star's denominators and BASELINE.json's second metric
+    assert line["cpu_baseline"]["same_config"] is True
+    eager = line["gpu_eager_baseline"]
+    assert eager["fp32"] > 0 and eager["autocast_bf16"] > 0 and eager["speedup_vs_autocast_bf16"] >= 5.0
+    assert 0 < line["logits_max_abs_err"] < 5e-2 and line["logits_parity"]["ratio_to_reference_bf16_floor"] < 1.0
+    assert line["inference"]["images_per_s"] > line["value"] and line["inference"]["bytes_kept_after_forward"] <= 4 * line["inference"]["logits_bytes"]
+    assert 0 < line["whole_step_tensor_frac"] < 1 and line["roofline"]["traffic"] is not None
 
 
 def test_reference_arm_prints_the_contract_line_on_cpu():
