@@ -13,6 +13,7 @@ NAMES = {1: "mma:operands landed", 2: "mma:S/MMA1 issued", 3: "mma:P ready (p_fu
          14: "wg:arrived", 15: "wg:ds_free", 20: "out:acc full", 21: "out:kv drained", 22: "out:stored",
          23: "out:dq full", 24: "out:dq drained", 30: "tma:stage free, loads issued", 40: "mma:S mmas issued", 41: "mma:S committed",
          42: "mma:fence done", 43: "mma:PV/dV mmas issued", 44: "mma:dK mmas issued", 45: "mma:dQ mmas issued", 16: "wg:delta computed", 17: "wg:delta barrier passed",
+         50: "kernel entry", 51: "prologue done", 52: "role done", 21: "out:accumulators released",
          46: "mma:first MMA1 of head issued", 47: "mma:second MMA1 of head issued"}
 
 
