@@ -56,8 +56,14 @@ def parse():
     ap.add_argument("--ref-autocast", action="store_true", help="--ref-device cuda under torch.autocast(bfloat16)")
     ap.add_argument("--no-gpu-eager-baseline", action="store_true")
     ap.add_argument("--no-parity-probe", action="store_true")
+    ap.add_argument("--no-text-tower", action="store_true")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-graph", action="store_true", help="time the eager step instead of the CUDA-graph replay")
+    ap.add_argument("--pixels", default="bf16", choices=["f32", "bf16", "u8"],
+                    help="format of the image batch on the host and in HBM: f32 = the reference data loader's output; "
+                         "bf16 = the same values rounded on the host (encode_image accepts any float dtype, "
+                         "model.py:1152; the stem's GEMM operand is bf16 either way: bit-identical step, half the H2D "
+                         "bytes); u8 = raw pixels, ToTensor + Normalize evaluated inside the stem kernel")
     return ap.parse_args()
 
 
@@ -72,8 +78,28 @@ def workload(args, shape):
                         f"batch {args.batch}/GPU", "backbone": args.model, "peft": args.method,
             "images_per_gpu_step": args.batch, "images_per_step": args.batch * args.gpus, "tokens": shape.tokens,
             "width": shape.vision_width, "layers": shape.vision_layers, "parallelism": f"dp{args.gpus}",
-            "l2_policy": f"inputs larger than L2 ({args.batch * 3 * shape.image_resolution ** 2 * 4 / 1e6:.0f} MB fp32 image "
-                         "batch and GBs of saved activations per step stream through the 126 MB L2)"}
+            "pixels": {"f32": "fp32 (reference data loader output)",
+                       "bf16": "bf16 on the host and in HBM (any float dtype is the reference's contract, model.py:1152; "
+                               "the stem rounds pixels to bf16 anyway: bit-identical step)",
+                       "u8": "uint8 on the host and in HBM, ToTensor + Normalize inside the stem kernel"}[args.pixels],
+            "l2_policy": f"inputs larger than L2 ({args.batch * 3 * shape.image_resolution ** 2 * PIXEL_BYTES[args.pixels] / 1e6:.0f} MB "
+                         f"{args.pixels} image batch and GBs of saved activations per step stream through the 126 MB L2)"}
+
+
+PIXEL_BYTES = {"f32": 4, "bf16": 2, "u8": 1}
+CLIP_NORM = ((0.48145466, 0.4578275, 0.40821073), (0.26862954, 0.26130258, 0.27577711))   # CLIP's Normalize
+
+
+def to_pixels(images, kind):
+    """fp32 normalised synthetic images -> the requested host / HBM format (u8: de-normalised and quantised)."""
+    import torch
+    if kind == "f32":
+        return images
+    if kind == "bf16":
+        return images.to(torch.bfloat16)
+    mean = torch.tensor(CLIP_NORM[0], device=images.device).view(1, 3, 1, 1)
+    std = torch.tensor(CLIP_NORM[1], device=images.device).view(1, 3, 1, 1)
+    return ((images * std + mean).clamp(0, 1) * 255).round().to(torch.uint8)
 
 
 # ----------------------------------------------------------------------------- clocks
@@ -226,6 +252,37 @@ def inference_throughput(args, tuner, images, iters=10, warmup=3) -> dict:
             "what": "Classifier forward (backbone.encode_image + head) under torch.no_grad(), eager launches"}
 
 
+def text_tower_throughput(dev, n=1024, iters=5, warmup=2) -> dict:
+    """``encode_text`` of the text tower every OpenAI CLIP ViT-B checkpoint carries (width 512, 8 heads, 12
+    layers, context 77) on the fused blocks (method plain + causal mask), beside the same module on its stock PyTorch
+    path (fp32 nn.MultiheadAttention: what the reference runs) on the same GPU, and the difference of the two."""
+    import pevit_b200
+    from pevit_b200 import synth
+    shape = synth.TEXT_B32
+    model = pevit_b200.build_model(dict(synth.clip_state_dict(shape, seed=7))).to(dev)
+    text = synth.prompts(n, shape.context_length, shape.vocab_size, seed=5).to(dev)
+
+    def timed():
+        with torch.no_grad():
+            for _ in range(warmup):
+                out = model.encode_text(text)
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+            for _ in range(iters):
+                out = model.encode_text(text)
+            e1.record()
+            torch.cuda.synchronize()
+        return e0.elapsed_time(e1) / iters, out.float()
+    ms_fused, feat = timed()
+    for blk in model.transformer.resblocks:
+        blk._pevit_causal = 0            # stock nn.MultiheadAttention path
+    ms_stock, ref = timed()
+    return {"prompts_per_s": n / ms_fused * 1e3, "ms_per_batch": ms_fused, "batch": n, "context": shape.context_length,
+            "width": shape.transformer_width, "layers": shape.transformer_layers,
+            "stock_pytorch_fp32_prompts_per_s": n / ms_stock * 1e3, "speedup_vs_stock": ms_stock / ms_fused,
+            "features_rel_err_vs_stock_fp32": ((feat - ref).abs().max() / ref.abs().max()).item()}
+
+
 def parity_probe(args, shape, tuner, dev, n=16) -> dict:
     """BASELINE.json's second metric: logits max-abs-err of this path vs the reference algorithm (oracle, fp32, CPU) on
     the same weights and the same n-image batch (F4 couples the samples of a batch, so both sides see the same n)."""
@@ -332,10 +389,11 @@ def run_b200(args):
     lib = _lib.lib()
     _lib.check(lib.pevit_check_device(), "pevit_check_device")
     shape = shape_of(args.model)
-    tuner = engine.FineTuner(args.method, shape, device=dev, distributed=world > 1, seed=0)
+    tuner = engine.FineTuner(args.method, shape, device=dev, distributed=world > 1, seed=0,
+                             pixel_norm=CLIP_NORM if args.pixels == "u8" else None)
     N, R = args.batch, shape.image_resolution
     g = torch.Generator(device=dev).manual_seed(1000 + rank)
-    images = torch.randn(N, 3, R, R, device=dev, generator=g)
+    images = to_pixels(torch.randn(N, 3, R, R, device=dev, generator=g), args.pixels)
     labels = torch.randint(0, 10, (N,), device=dev, generator=g)
 
     def barrier():
@@ -403,7 +461,7 @@ def run_b200(args):
     _lib.check(lib.pevit_prof_read(ms_arr, cnt_arr, ncls), "pevit_prof_read")
 
     # ---- end-to-end timing: host-resident inputs, H2D every step (prefetched), loss read back every step
-    host_img = [torch.randn(N, 3, R, R).pin_memory() for _ in range(2)]
+    host_img = [to_pixels(torch.randn(N, 3, R, R), args.pixels).pin_memory() for _ in range(2)]
     host_lab = [torch.randint(0, 10, (N,)).pin_memory() for _ in range(2)]
     if graphed:   # H2D lands directly in the static input buffers of the two captured graphs (no staging copy)
         dev_img, dev_lab = [tuner.input_buffers(b)[0] for b in range(2)], [tuner.input_buffers(b)[1] for b in range(2)]
@@ -513,7 +571,7 @@ def run_b200(args):
         "vs_baseline": None, "dtype": "bf16", "data": "synthetic", "config": workload(args, shape),
         "clocks": clocks.summary(t_wall0, t_wall2) if clocks else None,
         "e2e": {"value": e2e_value, "unit": "images/s", "ms_per_step": ms_e2e / args.steps,
-                "h2d_bytes_per_step": (images.numel() * 4 + labels.numel() * 8) * world,
+                "h2d_bytes_per_step": (images.numel() * images.element_size() + labels.numel() * 8) * world,
                 "d2h_bytes_per_step": 4 * world, "last_loss": last_loss},
         "gpu_launches": int(launches),  # this library's kernels per K steps (counted in the eager pass; the graph replays the same launches)
         "roofline": roof,
@@ -528,6 +586,11 @@ def run_b200(args):
     torch.cuda.synchronize()
     if world == 1:
         line["inference"] = inference_throughput(args, tuner, images)
+    if world == 1 and not args.no_text_tower:
+        try:
+            line["text_tower"] = text_tower_throughput(dev)
+        except Exception as exc:  # pragma: no cover
+            line["text_tower"] = {"unavailable": repr(exc)[:200]}
     if world == 1 and not args.no_parity_probe:
         probe = parity_probe(args, shape, tuner, dev)
         line["logits_max_abs_err"] = probe["max_abs_err"]

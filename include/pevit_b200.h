@@ -26,7 +26,7 @@
 extern "C" {
 #endif
 
-#define PEVIT_ABI_VERSION 1
+#define PEVIT_ABI_VERSION 2
 
 enum pevit_method {
   PEVIT_PLAIN = 0,       /* stock block, no PEFT module (text tower / ablation) */
@@ -102,6 +102,7 @@ typedef struct pevit_attn_args {
   void* dqkv; int32_t ld_dqkv;       /* bwd out: bf16 [L*NB][ld], cols dq/8 | dk | dv */
   void* ddelta;                      /* bwd out: bf16 [2][NB*H][L][64] (nullable) */
   int32_t impl;                      /* 0 = default, 1 = CUDA-core cross-check kernel, 2 = pair-streaming kernels for L > 128 */
+  int32_t causal;                    /* fwd only, L <= 128: 1 = keys j > l masked out (text tower, model.py:1139-1145) */
 } pevit_attn_args;
 int pevit_attn_fwd(const pevit_attn_args* args, void* stream);
 int pevit_attn_bwd(const pevit_attn_args* args, void* stream);
@@ -175,6 +176,17 @@ size_t pevit_patch_embed_workspace_bytes(int32_t nb, int32_t resolution, int32_t
 int pevit_patch_embed(const float* images, const void* w_patch, const float* cls, const float* pos, const float* ln_g,
                       const float* ln_b, float* x, void* workspace, int32_t nb, int32_t resolution, int32_t patch,
                       int32_t d, int32_t pos_rows, void* stream);
+/* The same stem for other pixel formats.  PEVIT_PX_BF16: the reference accepts any float dtype (encode_image casts,
+ * model.py:1152) and the stem rounds pixels to bf16 anyway, so bf16 images give bit-identical patches at half the
+ * host-to-device bytes.  PEVIT_PX_U8: raw [0,255] pixels, torchvision's ToTensor + Normalize -- the transform the
+ * reference's data loader applies on the host -- evaluated in the kernel in fp32 with the host's operation order,
+ * (u8 / 255 - mean[c]) / std[c] (IEEE division: bit-identical to the host result); mean / std are 3 HOST floats each
+ * (copied at launch), ignored for the float formats. */
+enum pevit_pixel_dtype { PEVIT_PX_F32 = 0, PEVIT_PX_BF16 = 1, PEVIT_PX_U8 = 2 };
+int pevit_patch_embed_px(const void* images, int32_t px_dtype, const float* mean, const float* std_, const void* w_patch,
+                         const float* cls, const float* pos, const float* ln_g, const float* ln_b, float* x,
+                         void* workspace, int32_t nb, int32_t resolution, int32_t patch, int32_t d, int32_t pos_rows,
+                         void* stream);
 
 /* ------------------------------------------------------------------ block level
  * One ResidualAttentionBlock forward / backward (model.py:947-975, lora_model.py,
@@ -193,6 +205,8 @@ typedef struct pevit_block_desc {
                         * a multiple of NB = whole token indices) are needed -- the last ViT block feeds only
                         * ln_post(x[0]) (model.py:1046), so its out-projection, MLP and their dgrads run on NB rows.
                         * y / dy then hold out_rows rows; attention still sees every key. */
+  int32_t causal;      /* 1: causal attention mask (CLIP text tower blocks, model.py:1139-1145, 1154-1167): method
+                        * PEVIT_PLAIN, save = 0 (the text tower is frozen: forward only), L <= 128 */
 } pevit_block_desc;
 
 typedef struct pevit_block_weights {

@@ -90,7 +90,7 @@ def lora_delta(x: torch.Tensor, p: Params, pre: str, which: str) -> torch.Tensor
     return torch.matmul(torch.matmul(x, a.T), b.T) * (128 / 4)
 
 
-def attention(x: torch.Tensor, p: Params, pre: str, heads: int, method: str) -> torch.Tensor:
+def attention(x: torch.Tensor, p: Params, pre: str, heads: int, method: str, causal: bool = False) -> torch.Tensor:
     """model.py:612-834 (KAdaptation), lora_model.py:596-760 (LoRA), and the stock
     ``nn.MultiheadAttention`` math used by adapter_model.py:317 / compacter_model.py:484.
 
@@ -108,6 +108,8 @@ def attention(x: torch.Tensor, p: Params, pre: str, heads: int, method: str) -> 
         q = q.contiguous() + delta(x, p, pre, "q").reshape(N * heads, L, hd)         # model.py:796-798
         v = v.contiguous() + delta(x, p, pre, "v").reshape(N * heads, L, hd)         # model.py:797-799
     s = torch.bmm(q, k.transpose(-2, -1))                                            # model.py:806
+    if causal:  # text tower: additive -inf mask above the diagonal (model.py:1139-1145, applied at :807 / stock MHA)
+        s = s + torch.full((L, L), float("-inf"), dtype=s.dtype, device=s.device).triu_(1)
     a = torch.softmax(s, dim=-1)                                                     # model.py:808
     o = torch.bmm(a, v)                                                              # model.py:812
     o = merge_heads(o, L, N)
@@ -191,6 +193,23 @@ def encode_image(img: torch.Tensor, p: Params, method: str, use_proj: bool = Tru
     if use_proj and p.get("visual.proj") is not None:
         x = x @ p["visual.proj"]
     return x
+
+
+def encode_text(text: torch.Tensor, p: Params) -> torch.Tensor:
+    """model.py:1154-1167 (``CLIP.encode_text``): token + positional embedding, the text transformer (stock
+    ``nn.MultiheadAttention`` blocks with the causal mask of model.py:1139-1145, heads = width // 64, model.py:1218),
+    ``ln_final``, the row of the highest token id (EOT) of every prompt, ``text_projection``."""
+    x = p["token_embedding.weight"][text] + p["positional_embedding"]                 # (N, L, W)
+    x = x.permute(1, 0, 2)
+    heads = p["ln_final.weight"].shape[0] // 64
+    layers = len({k.split(".")[2] for k in p if k.startswith("transformer.resblocks.")})
+    for i in range(layers):
+        pre = f"transformer.resblocks.{i}."
+        x = x + attention(layer_norm(x, p[pre + "ln_1.weight"], p[pre + "ln_1.bias"]), p, pre, heads, "plain",
+                          causal=True)
+        x = x + mlp(layer_norm(x, p[pre + "ln_2.weight"], p[pre + "ln_2.bias"]), p, pre)
+    x = layer_norm(x.permute(1, 0, 2), p["ln_final.weight"], p["ln_final.bias"])
+    return x[torch.arange(x.shape[0]), text.argmax(dim=-1)] @ p["text_projection"]
 
 
 def classifier_logits(img: torch.Tensor, p: Params, head_w: torch.Tensor, head_b: torch.Tensor,

@@ -191,6 +191,15 @@ class HyperComplexAdapter(nn.Module):
 
 
 # --------------------------------------------------------------------------- blocks and towers
+def _is_causal_mask(mask: Optional[torch.Tensor]) -> bool:
+    """True for the additive mask ``CLIP.build_attention_mask`` makes (model.py:1139-1145): -inf strictly above the
+    diagonal, 0 elsewhere.  Any other mask keeps the stock PyTorch attention."""
+    if mask is None or mask.dim() != 2 or mask.shape[0] != mask.shape[1] or not mask.is_floating_point():
+        return False
+    upper = torch.ones_like(mask, dtype=torch.bool).triu_(1)
+    return bool(torch.isneginf(mask[upper]).all()) and bool((mask[~upper] == 0).all())
+
+
 class ResidualAttentionBlock(nn.Module):
     """model.py:947-975 / adapter_model.py:298-336 / compacter_model.py:465-503.
 
@@ -218,6 +227,8 @@ class ResidualAttentionBlock(nn.Module):
         self.attn_mask = attn_mask
         self.fused = kattention is not None
         self.attn_impl = 0
+        # text-tower blocks: the same fused schedule with method "plain" and the causal mask, forward only
+        self._pevit_causal = 1 if (kattention is None and _is_causal_mask(attn_mask)) else 0
 
     def peft_tensors(self) -> tuple:
         if self.method in (KAD, LORA):
@@ -232,10 +243,22 @@ class ResidualAttentionBlock(nn.Module):
         mask = self.attn_mask.to(dtype=x.dtype, device=x.device) if self.attn_mask is not None else None
         return self.attn(x, x, x, need_weights=False, attn_mask=mask)[0]
 
+    def _text_block_on_device(self, x: torch.Tensor) -> bool:
+        """A frozen text-tower block (model.py:1154-1167: stock MHA + causal mask) can take the fused forward when
+        nothing asks for a gradient and the shape is one the kernels cover (head_dim 64, width % 128, L <= 128)."""
+        if not (self._pevit_causal and x.is_cuda and x.dim() == 3 and not self.training):
+            return False
+        width, heads = self.attn.embed_dim, self.attn.num_heads
+        if width != 64 * heads or width % 128 != 0 or x.shape[0] > 128 or x.shape[0] != self.attn_mask.shape[0]:
+            return False
+        return not (torch.is_grad_enabled() and (x.requires_grad or any(p.requires_grad for p in self.parameters())))
+
     def forward(self, x: torch.Tensor, out_tokens: int = 0) -> torch.Tensor:
         """``out_tokens`` > 0 (fused blocks only): return just the first ``out_tokens`` token positions."""
         if self.fused:
             return ops.block_forward(self, x, self.method, self.peft_tensors(), self.attn_impl, out_tokens).to(x.dtype)
+        if self._text_block_on_device(x):
+            return ops.block_forward(self, x, PLAIN, (), 0, out_tokens).to(x.dtype)
         x = x + self.attention(self.ln_1(x))
         x = x + self.mlp(self.ln_2(x))
         return x[:out_tokens] if out_tokens else x
@@ -286,6 +309,8 @@ class VisionTransformer(nn.Module):
         self.transformer = Transformer(width, layers, heads, kattention=True, method=method)
         self.ln_post = LayerNorm(width)
         self.proj = nn.Parameter(scale * torch.randn(width, output_dim))
+        # (mean3, std3) of torchvision's Normalize: when set, uint8 images are normalised inside the stem kernel
+        self.pixel_norm = None
 
     def _stem_is_frozen(self) -> bool:
         ps = (self.conv1.weight, self.class_embedding, self.positional_embedding, self.ln_pre.weight, self.ln_pre.bias)
@@ -306,7 +331,10 @@ class VisionTransformer(nn.Module):
         if x.is_cuda and not x.requires_grad and self._stem_is_frozen() and x.shape[-1] % self.conv1.kernel_size[0] == 0:
             x = ops.stem_forward(self, x)                        # fused stem -> (L, N, D)
         else:  # stem parameters being trained (not a PEViT setting): stock ops keep autograd semantics
-            x = self.conv1(x)                                    # (N, D, g, g)
+            if x.dtype == torch.uint8 and self.pixel_norm is not None:   # ToTensor + Normalize, as the kernel does
+                mean, std = (torch.tensor(v, dtype=torch.float32, device=x.device).view(1, 3, 1, 1) for v in self.pixel_norm)
+                x = (x.float() / 255.0 - mean) / std
+            x = self.conv1(x.type(self.conv1.weight.dtype))      # (N, D, g, g)
             x = x.flatten(2).transpose(1, 2)                     # (N, g*g, D)
             cls = self.class_embedding.to(x.dtype).expand(x.shape[0], 1, -1)
             x = torch.cat([cls, x], dim=1) + self.positional_embedding.to(x.dtype)
@@ -366,7 +394,14 @@ class CLIP(nn.Module):
         return self.visual.conv1.weight.dtype
 
     def encode_image(self, image: torch.Tensor) -> torch.Tensor:
-        return self.visual(image.type(self.dtype))
+        return self.visual(self.pixels_for_stem(image))
+
+    def pixels_for_stem(self, image: torch.Tensor) -> torch.Tensor:
+        """``image.type(self.dtype)`` (model.py:1152), except for the formats the fused stem reads directly on the
+        device: bf16 (same patches, no fp32 round trip) and uint8 with ``visual.pixel_norm`` set."""
+        direct = image.is_cuda and (image.dtype == torch.bfloat16 or
+                                    (image.dtype == torch.uint8 and getattr(self.visual, "pixel_norm", None) is not None))
+        return image if direct else image.type(self.dtype)
 
     def encode_text(self, text: torch.Tensor) -> torch.Tensor:
         x = self.token_embedding(text).type(self.dtype) + self.positional_embedding.type(self.dtype)

@@ -37,7 +37,7 @@ class AttnArgs(C.Structure):
         ("L", c_int32), ("NB", c_int32), ("H", c_int32), ("D", c_int32), ("r", c_int32), ("alpha", c_float),
         ("q", c_void_p), ("k", c_void_p), ("v", c_void_p), ("t", c_void_p), ("qmat", c_void_p),
         ("delta_bias", c_void_p), ("o_tok", c_void_p), ("lse", c_void_p), ("do_tok", c_void_p),
-        ("dqkv", c_void_p), ("ld_dqkv", c_int32), ("ddelta", c_void_p), ("impl", c_int32),
+        ("dqkv", c_void_p), ("ld_dqkv", c_int32), ("ddelta", c_void_p), ("impl", c_int32), ("causal", c_int32),
     ]
 
 
@@ -45,7 +45,7 @@ class BlockDesc(C.Structure):
     _fields_ = [
         ("L", c_int32), ("NB", c_int32), ("D", c_int32), ("H", c_int32), ("method", c_int32),
         ("r", c_int32), ("alpha", c_float), ("save", c_int32), ("attn_impl", c_int32), ("need_dx", c_int32),
-        ("out_rows", c_int32),
+        ("out_rows", c_int32), ("causal", c_int32),
     ]
 
 
@@ -101,6 +101,7 @@ _SIGNATURES = {
     "pevit_transpose_bf16": (c_int32, [c_void_p, c_int32, c_int32, c_void_p, c_int32, c_void_p]),
     "pevit_patch_embed_workspace_bytes": (c_size_t, [c_int32] * 4),
     "pevit_patch_embed": (c_int32, [c_void_p] * 8 + [c_int32] * 5 + [c_void_p]),
+    "pevit_patch_embed_px": (c_int32, [c_void_p, c_int32] + [c_void_p] * 9 + [c_int32] * 5 + [c_void_p]),
     "pevit_block_saved_bytes": (c_size_t, [_P(BlockDesc)]),
     "pevit_block_workspace_bytes": (c_size_t, [_P(BlockDesc)]),
     "pevit_block_fwd": (c_int32, [_P(BlockDesc), _P(BlockWeights), c_void_p, c_void_p, c_void_p, c_void_p, c_void_p]),
@@ -124,7 +125,7 @@ def lib() -> C.CDLL:
         for name, (res, args) in _SIGNATURES.items():
             fn = getattr(handle, name)  # AttributeError if the ABI is incomplete
             fn.restype, fn.argtypes = res, args
-        if handle.pevit_abi_version() != 1:
+        if handle.pevit_abi_version() != 2:
             raise RuntimeError("pevit_b200 ABI version mismatch")
         _lib = handle
     return _lib

@@ -107,6 +107,8 @@ int check_desc(const pevit_block_desc* d) {
     PEVIT_REQUIRE(d->r == 0, "r must be 0 for method %d", d->method);
   PEVIT_REQUIRE(d->out_rows >= 0 && d->out_rows <= d->L * d->NB && d->out_rows % d->NB == 0,
                 "out_rows=%d must be a multiple of NB=%d within L*NB", d->out_rows, d->NB);
+  PEVIT_REQUIRE(d->causal == 0 || (d->causal == 1 && d->method == PEVIT_PLAIN && d->save == 0 && d->L <= 128),
+                "causal=%d: the masked attention is forward-only (save=0), method plain, L <= 128 (L=%d)", d->causal, d->L);
   return 0;
 }
 
@@ -115,6 +117,10 @@ int attn_fwd_dispatch(cudaStream_t s, const AttnShape& a, int impl, const bf16* 
   // impl 0: tcgen05 kernels (L <= 128: one tile per head or two heads per tile; longer: head-resident); impl 2: the
   // round-1 pair-streaming kernels for 128 < L <= 384 (kept as a second implementation and for shapes whose
   // operands do not fit in shared memory); impl 1: CUDA-core cross-check with the delta expanded in-kernel
+  if (a.causal) {  // text tower (L = 77): only the L <= 128 kernel carries the mask
+    PEVIT_REQUIRE(attn_tc_supported(a), "causal attention needs L <= 128 and no in-kernel delta (L=%d r=%d)", a.L, a.r);
+    return attn_fwd_tc(s, a, q, k, v, o_tok, lse);
+  }
   if (impl != 1 && attn_tc_supported(a)) return attn_fwd_tc(s, a, q, k, v, o_tok, lse);
   if (impl == 0 && attn_hr_supported(a)) return attn_fwd_hr(s, a, q, k, v, o_tok, lse);
   if (impl != 1 && attn_tc_long_supported(a)) return attn_fwd_tc_long(s, a, q, k, v, o_tok, lse);
@@ -124,6 +130,7 @@ int attn_fwd_dispatch(cudaStream_t s, const AttnShape& a, int impl, const bf16* 
 int attn_bwd_dispatch(cudaStream_t s, const AttnShape& a, int impl, const bf16* q, const bf16* k, const bf16* v,
                       const bf16* T, const float* qmat, const float* bias, const bf16* o_tok, const bf16* do_tok,
                       const float* lse, bf16* dqkv, int ld, bf16* ddelta) {
+  PEVIT_REQUIRE(!a.causal, "causal attention is forward-only (the text tower is frozen)");
   if (impl != 1 && attn_tc_supported(a)) return attn_bwd_tc(s, a, q, k, v, do_tok, lse, dqkv, ld, ddelta);
   if (impl == 0 && attn_bwd_hr_supported(a)) return attn_bwd_hr(s, a, q, k, v, o_tok, do_tok, lse, dqkv, ld, ddelta);
   if (impl != 1 && attn_tc_long_supported(a)) return attn_bwd_tc_long(s, a, q, k, v, o_tok, do_tok, lse, dqkv, ld, ddelta);
@@ -186,7 +193,7 @@ int pevit_layernorm_bwd(const float* dyn, const float* x, const float* gamma, co
 
 int pevit_attn_fwd(const pevit_attn_args* a, void* stream) {
   PEVIT_REQUIRE(a != nullptr, "null attention args");
-  AttnShape sh{a->L, a->NB, a->H, a->D, a->r, a->alpha};
+  AttnShape sh{a->L, a->NB, a->H, a->D, a->r, a->alpha, a->causal};
   return attn_fwd_dispatch(as_stream(stream), sh, a->impl, static_cast<const bf16*>(a->q),
                            static_cast<const bf16*>(a->k), static_cast<const bf16*>(a->v),
                            static_cast<const bf16*>(a->t), a->qmat, a->delta_bias, static_cast<bf16*>(a->o_tok), a->lse);
@@ -194,7 +201,7 @@ int pevit_attn_fwd(const pevit_attn_args* a, void* stream) {
 
 int pevit_attn_bwd(const pevit_attn_args* a, void* stream) {
   PEVIT_REQUIRE(a != nullptr, "null attention args");
-  AttnShape sh{a->L, a->NB, a->H, a->D, a->r, a->alpha};
+  AttnShape sh{a->L, a->NB, a->H, a->D, a->r, a->alpha, a->causal};
   return attn_bwd_dispatch(as_stream(stream), sh, a->impl, static_cast<const bf16*>(a->q),
                            static_cast<const bf16*>(a->k), static_cast<const bf16*>(a->v),
                            static_cast<const bf16*>(a->t), a->qmat, a->delta_bias,
@@ -316,8 +323,20 @@ int pevit_patch_embed(const float* images, const void* w_patch, const float* cls
   PEVIT_REQUIRE(patch > 0 && resolution % patch == 0 && pos_rows == (resolution / patch) * (resolution / patch) + 1,
                 "pevit_patch_embed: positional embedding has %d rows, resolution %d / patch %d needs %d", pos_rows,
                 resolution, patch, patch > 0 ? (resolution / patch) * (resolution / patch) + 1 : 0);
-  return patch_embed(as_stream(stream), images, static_cast<const bf16*>(w_patch), cls, pos, ln_g, ln_b, x, workspace, nb,
-                     resolution, patch, d);
+  return patch_embed(as_stream(stream), images, PEVIT_PX_F32, nullptr, nullptr, static_cast<const bf16*>(w_patch), cls,
+                     pos, ln_g, ln_b, x, workspace, nb, resolution, patch, d);
+}
+
+int pevit_patch_embed_px(const void* images, int32_t px_dtype, const float* mean, const float* std_, const void* w_patch,
+                         const float* cls, const float* pos, const float* ln_g, const float* ln_b, float* x,
+                         void* workspace, int32_t nb, int32_t resolution, int32_t patch, int32_t d, int32_t pos_rows,
+                         void* stream) {
+  PEVIT_REQUIRE(images && w_patch && cls && pos && ln_g && ln_b && x && workspace, "pevit_patch_embed_px: null pointer");
+  PEVIT_REQUIRE(patch > 0 && resolution % patch == 0 && pos_rows == (resolution / patch) * (resolution / patch) + 1,
+                "pevit_patch_embed_px: positional embedding has %d rows, resolution %d / patch %d needs %d", pos_rows,
+                resolution, patch, patch > 0 ? (resolution / patch) * (resolution / patch) + 1 : 0);
+  return patch_embed(as_stream(stream), images, px_dtype, mean, std_, static_cast<const bf16*>(w_patch), cls, pos, ln_g,
+                     ln_b, x, workspace, nb, resolution, patch, d);
 }
 
 size_t pevit_block_saved_bytes(const pevit_block_desc* desc) {
@@ -382,7 +401,7 @@ int pevit_block_fwd(const pevit_block_desc* desc, const pevit_block_weights* w, 
   }
   // attention core
   {
-    AttnShape a{d.L, d.NB, d.H, D, fused_delta ? d.r : 0, d.alpha};
+    AttnShape a{d.L, d.NB, d.H, D, fused_delta ? d.r : 0, d.alpha, d.causal};
     TRY(attn_fwd_dispatch(s, a, d.attn_impl, sv.qkv_hm, sv.qkv_hm + plane, sv.qkv_hm + 2 * plane,
                           fused_delta ? sv.T : nullptr, fused_delta ? w->qmat : nullptr,
                           fused_delta && d.method == PEVIT_KADAPTATION ? w->delta_bias : nullptr, sv.o_tok, sv.lse));

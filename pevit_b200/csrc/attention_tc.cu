@@ -51,6 +51,7 @@ struct FwdParams {
   int debug;  // diagnostics (PEVIT_ATTN_DEBUG): 1 = no operand loads, 2 = no softmax math, 4 = no O staging / store
   bf16* o_tok;
   float* lse;
+  int causal;  // additive -inf mask above the diagonal (CLIP text tower, model.py:1139-1145): keys j <= l only
 };
 
 // Roles: warps 0-3 softmax (every tile: S_b -> P_b + row statistics), warps 4-7 epilogue (every tile: O_b ->
@@ -198,6 +199,7 @@ attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_consta
     const int col0 = PACK == 2 ? slot * 64 : 0;    // first key column of this row's block
     constexpr int NCOL = PACK == 2 ? 64 : 128;
     const uint32_t t_lane = tmem_base + (static_cast<uint32_t>(quad * 32) << 16);
+    const int lim = p.causal ? min(L, l + 1) : L;  // keys [0, lim) of this row's block take part in the softmax
     if (wgrole == 0) {
       // ---------------------------------------------------------- softmax warpgroup
       for (int it = 0; it < n_local; ++it) {
@@ -220,13 +222,13 @@ attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_consta
         }
         float m4[4] = {-INFINITY, -INFINITY, -INFINITY, -INFINITY};
 #pragma unroll
-        for (int j = 0; j < NCOL; ++j) if (j < L) m4[j & 3] = fmaxf(m4[j & 3], sc[j]);
+        for (int j = 0; j < NCOL; ++j) if (j < lim) m4[j & 3] = fmaxf(m4[j & 3], sc[j]);
         const float mx = fmaxf(fmaxf(m4[0], m4[1]), fmaxf(m4[2], m4[3]));
         float s4[4] = {0.f, 0.f, 0.f, 0.f};
         const float mxs = mx * LOG2E;
 #pragma unroll
         for (int j = 0; j < NCOL; ++j) {
-          const float e = (j < L) ? fast_exp2(fmaf(sc[j], LOG2E, -mxs)) : 0.f;
+          const float e = (j < lim) ? fast_exp2(fmaf(sc[j], LOG2E, -mxs)) : 0.f;
           sc[j] = e;
           s4[j & 3] += e;
         }
@@ -681,7 +683,7 @@ int attn_fwd_tc(cudaStream_t s, const AttnShape& a, const bf16* q, const bf16* k
   CUtensorMap to;
   if (make_tmap_bf16_tok_heads(&to, o_tok, a.L, a.NB, a.H, a.D, a.L) != 0) return -1;
   static const int dbg = getenv("PEVIT_ATTN_DEBUG") ? atoi(getenv("PEVIT_ATTN_DEBUG")) : 0;
-  FwdParams p{a.L, a.NB, a.H, a.D, heads, tiles, dbg, o_tok, lse};
+  FwdParams p{a.L, a.NB, a.H, a.D, heads, tiles, dbg, o_tok, lse, a.causal};
   const int grid = tiles < sm_count() ? tiles : sm_count();
   ProfScope prof(s, PC_ATTN_FWD);
   if (pack == 2) {
@@ -699,6 +701,7 @@ int attn_bwd_tc(cudaStream_t s, const AttnShape& a, const bf16* q, const bf16* k
                 const float* lse, bf16* dqkv, int ld_dqkv, bf16* ddelta) {
   PEVIT_REQUIRE(attn_tc_supported(a), "attn_bwd_tc: unsupported shape L=%d D=%d H=%d r=%d", a.L, a.D, a.H, a.r);
   PEVIT_REQUIRE(ld_dqkv % 8 == 0, "attn_bwd_tc: ld_dqkv=%d must be a multiple of 8", ld_dqkv);
+  PEVIT_REQUIRE(!a.causal, "attn_bwd_tc: the causal mask is forward-only (the text tower is frozen)");
   const int heads = a.NB * a.H;
   const int pack = a.L <= 64 ? 2 : 1;
   const int tiles = (heads + pack - 1) / pack;

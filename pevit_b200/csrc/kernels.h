@@ -52,6 +52,7 @@ int layernorm_bwd(cudaStream_t s, const float* dyn, const float* x, const float*
 struct AttnShape {
   int L, NB, H, D, r;  // r = low-rank width per projection (32 KAdaptation, 4 LoRA, 0 none)
   float alpha;         // 160 / 32
+  int causal = 0;      // forward only, L <= 128: key j of query l is masked when j > l (text tower, model.py:1139-1145)
 };
 // q,k,v: head-major bf16 [NB*H][L][64] (q pre-scaled).  T: bf16 [L*NB][2r] (LND rows).
 // Qmat: fp32 [2][D][r] (q then v factor), bias: fp32 [D] or null.
@@ -146,8 +147,10 @@ int bottleneck_pack(cudaStream_t s, const float* w_down, const float* w_up, int 
 // Patch embedding + class token + positional embedding + ln_pre -> x (L, N, D) fp32 (model.py:1034-1042).
 // w_patch: bf16 [D][Kpad], Kpad = ceil8(3 p^2), the flattened conv1 weight zero-padded along K.
 size_t patch_embed_workspace_bytes(int NB, int R, int p, int D);
-int patch_embed(cudaStream_t s, const float* img, const bf16* w_patch, const float* cls, const float* pos,
-                const float* ln_g, const float* ln_b, float* x, void* workspace, int NB, int R, int p, int D);
+// px_dtype (pevit_pixel_dtype): 0 fp32, 1 bf16, 2 uint8 normalised in the kernel with mean / std (3 host floats each).
+int patch_embed(cudaStream_t s, const void* img, int px_dtype, const float* mean, const float* stdv, const bf16* w_patch,
+                const float* cls, const float* pos, const float* ln_g, const float* ln_b, float* x, void* workspace,
+                int NB, int R, int p, int D);
 
 // ------------------------------------------------------------------ tail.cu
 // Linear head + cross-entropy (mean over N): logits [N][C], dlogits = (softmax - 1hot)/N, *loss += mean loss

@@ -13,15 +13,43 @@ namespace {
 // patches[(n*G + gy)*G + gx][c*p*p + i*p + j] = img[n][c][gy*p + i][gx*p + j]   (bf16, K padded with zeros)
 // One block per patch.  p % 4 == 0 (every CLIP ViT: 32, 16; not 14): a thread converts 4 consecutive pixels of one
 // patch row (16-byte load, 8-byte store); otherwise element by element.
-template <bool kVec4>
-__global__ void im2col_kernel(const float* __restrict__ img, bf16* __restrict__ patches, int NB, int R, int p, int G,
-                              int K, int Kpad) {
+// Pixel formats the stem reads (pevit_pixel_dtype): fp32 (the reference's data loader output), bf16 (the same values
+// already rounded: identical patches, half the H2D bytes), raw uint8 with torchvision's ToTensor + Normalize applied
+// here in fp32 with the host's operation order ((u8 / 255 - mean) / std, IEEE division: bit-identical to the host).
+struct PixelNorm { float mean[3], std[3]; };
+template <typename T> struct Px;
+template <> struct Px<float> {
+  using Vec4 = float4;
+  static __device__ __forceinline__ float get(float v, int, const PixelNorm&) { return v; }
+  static __device__ __forceinline__ void get4(const Vec4& v, int, const PixelNorm&, float (&o)[4]) { o[0] = v.x; o[1] = v.y; o[2] = v.z; o[3] = v.w; }
+};
+template <> struct Px<bf16> {
+  using Vec4 = uint2;
+  static __device__ __forceinline__ float get(bf16 v, int, const PixelNorm&) { return __bfloat162float(v); }
+  static __device__ __forceinline__ void get4(const Vec4& v, int, const PixelNorm&, float (&o)[4]) {
+    o[0] = __uint_as_float(v.x << 16); o[1] = __uint_as_float(v.x & 0xffff0000u);
+    o[2] = __uint_as_float(v.y << 16); o[3] = __uint_as_float(v.y & 0xffff0000u);
+  }
+};
+template <> struct Px<uint8_t> {
+  using Vec4 = uchar4;
+  static __device__ __forceinline__ float get(uint8_t v, int c, const PixelNorm& n) {
+    return __fdiv_rn(__fsub_rn(__fdiv_rn(static_cast<float>(v), 255.f), n.mean[c]), n.std[c]);
+  }
+  static __device__ __forceinline__ void get4(const Vec4& v, int c, const PixelNorm& n, float (&o)[4]) {
+    o[0] = get(v.x, c, n); o[1] = get(v.y, c, n); o[2] = get(v.z, c, n); o[3] = get(v.w, c, n);
+  }
+};
+
+template <bool kVec4, typename T>
+__global__ void im2col_kernel(const T* __restrict__ img, bf16* __restrict__ patches, int NB, int R, int p, int G,
+                              int K, int Kpad, PixelNorm norm) {
   pdl_launch_dependents();
   pdl_wait();
   const int row = blockIdx.x;  // (n, gy, gx)
   const int n = row / (G * G), g = row - n * G * G;
   const int gy = g / G, gx = g - gy * G;
-  const float* src = img + (static_cast<size_t>(n) * 3 * R + gy * p) * R + gx * p;
+  const T* src = img + (static_cast<size_t>(n) * 3 * R + gy * p) * R + gx * p;
   bf16* dst = patches + static_cast<size_t>(row) * Kpad;
   const int pp = p * p;
   if constexpr (kVec4) {
@@ -29,8 +57,11 @@ __global__ void im2col_kernel(const float* __restrict__ img, bf16* __restrict__ 
     for (int q = threadIdx.x; q < (K >> 2); q += blockDim.x) {  // q = (c, i, j/4)
       const int ci = q / p4, j4 = q - ci * p4;
       const int c = ci / p, i = ci - c * p;
-      const float4 v = __ldg(reinterpret_cast<const float4*>(src + (static_cast<size_t>(c) * R + i) * R) + j4);
-      *reinterpret_cast<uint2*>(dst + 4 * q) = make_uint2(pack_bf16(v.x, v.y), pack_bf16(v.z, v.w));
+      using Vec4 = typename Px<T>::Vec4;
+      const Vec4 raw = __ldg(reinterpret_cast<const Vec4*>(src + (static_cast<size_t>(c) * R + i) * R) + j4);
+      float v[4];
+      Px<T>::get4(raw, c, norm, v);
+      *reinterpret_cast<uint2*>(dst + 4 * q) = make_uint2(pack_bf16(v[0], v[1]), pack_bf16(v[2], v[3]));
     }
     for (int k = K + threadIdx.x; k < Kpad; k += blockDim.x) dst[k] = __float2bfloat16(0.f);
   } else {
@@ -39,7 +70,7 @@ __global__ void im2col_kernel(const float* __restrict__ img, bf16* __restrict__ 
       if (k < K) {
         const int c = k / pp, rem = k - c * pp;
         const int i = rem / p, j = rem - i * p;
-        v = __ldg(src + (static_cast<size_t>(c) * R + i) * R + j);
+        v = Px<T>::get(__ldg(src + (static_cast<size_t>(c) * R + i) * R + j), c, norm);
       }
       dst[k] = __float2bfloat16(v);
     }
@@ -102,8 +133,24 @@ size_t patch_embed_workspace_bytes(int NB, int R, int p, int D) {
   return ((rows * Kpad * sizeof(bf16) + 255) & ~size_t(255)) + rows * D * sizeof(float) + 256;
 }
 
-int patch_embed(cudaStream_t s, const float* img, const bf16* w_patch, const float* cls, const float* pos,
-                const float* ln_g, const float* ln_b, float* x, void* workspace, int NB, int R, int p, int D) {
+template <typename T>
+static int launch_im2col(cudaStream_t s, const T* img, bf16* patches, int NB, int R, int p, int G, int K, int Kpad,
+                         int rows, const PixelNorm& norm) {
+  // vector loads of 4 pixels need p % 4 == 0, R % 4 == 0 and a base aligned to 4 pixels
+  const bool vec4 = p % 4 == 0 && R % 4 == 0 && (reinterpret_cast<uintptr_t>(img) & (4 * sizeof(T) - 1)) == 0;
+  if (vec4)
+    PEVIT_CHECK_CUDA(launch_kernel(im2col_kernel<true, T>, dim3(rows), dim3(256), 0, s, 1, img, patches, NB, R, p, G, K, Kpad, norm));
+  else
+    PEVIT_CHECK_CUDA(launch_kernel(im2col_kernel<false, T>, dim3(rows), dim3(256), 0, s, 1, img, patches, NB, R, p, G, K, Kpad, norm));
+  PEVIT_CHECK_LAUNCH();
+  return 0;
+}
+
+int patch_embed(cudaStream_t s, const void* img, int px_dtype, const float* mean, const float* stdv, const bf16* w_patch,
+                const float* cls, const float* pos, const float* ln_g, const float* ln_b, float* x, void* workspace,
+                int NB, int R, int p, int D) {
+  PEVIT_REQUIRE(px_dtype >= 0 && px_dtype <= 2, "patch_embed: unknown pixel dtype %d", px_dtype);
+  PEVIT_REQUIRE(px_dtype != 2 || (mean != nullptr && stdv != nullptr), "patch_embed: uint8 pixels need mean / std");
   PEVIT_REQUIRE(R % p == 0 && D % 128 == 0 && D <= 128 * FIN_MAXV, "patch_embed: unsupported R=%d p=%d D=%d", R, p, D);
   const int G = R / p, L = G * G + 1, K = 3 * p * p, Kpad = (K + 7) / 8 * 8;
   const int rows = NB * G * G;
@@ -112,13 +159,14 @@ int patch_embed(cudaStream_t s, const float* img, const bf16* w_patch, const flo
                                         ((static_cast<size_t>(rows) * Kpad * sizeof(bf16) + 255) & ~size_t(255)));
   {
     ProfScope prof(s, PC_STEM);
-    // 16-byte loads need p % 4 == 0, R % 4 == 0 and an aligned image base
-    const bool vec4 = p % 4 == 0 && R % 4 == 0 && (reinterpret_cast<uintptr_t>(img) & 15) == 0;
-    if (vec4)
-      PEVIT_CHECK_CUDA(launch_kernel(im2col_kernel<true>, dim3(rows), dim3(256), 0, s, 1, img, patches, NB, R, p, G, K, Kpad));
-    else
-      PEVIT_CHECK_CUDA(launch_kernel(im2col_kernel<false>, dim3(rows), dim3(256), 0, s, 1, img, patches, NB, R, p, G, K, Kpad));
-    PEVIT_CHECK_LAUNCH();
+    PixelNorm norm{{0.f, 0.f, 0.f}, {1.f, 1.f, 1.f}};
+    if (px_dtype == 2)
+      for (int c = 0; c < 3; ++c) { norm.mean[c] = mean[c]; norm.std[c] = stdv[c]; }
+    int rc = 0;
+    if (px_dtype == 0) rc = launch_im2col(s, static_cast<const float*>(img), patches, NB, R, p, G, K, Kpad, rows, norm);
+    else if (px_dtype == 1) rc = launch_im2col(s, static_cast<const bf16*>(img), patches, NB, R, p, G, K, Kpad, rows, norm);
+    else rc = launch_im2col(s, static_cast<const uint8_t*>(img), patches, NB, R, p, G, K, Kpad, rows, norm);
+    if (rc != 0) return rc;
   }
   GemmEpilogue ep;
   ep.out_f32 = emb;

@@ -78,7 +78,7 @@ class FineTuner(nn.Module):
     def __init__(self, method: str, shape: synth.ClipShape, num_classes: int = 10, device="cuda", lr: float = 1e-3,
                  momentum: float = 0.9, weight_decay: float = 0.0, seed: int = 0, randomize: bool = True,
                  process_group: Optional[dist.ProcessGroup] = None, distributed: bool = False,
-                 fused_tail: Optional[bool] = None, without_wd=("bias", "ln")):
+                 fused_tail: Optional[bool] = None, without_wd=("bias", "ln"), pixel_norm=None):
         super().__init__()
         self.method = method
         sd = synth.clip_state_dict(shape, seed=seed)
@@ -92,6 +92,7 @@ class FineTuner(nn.Module):
         with torch.no_grad():
             self.head.weight.copy_(torch.randn(num_classes, shape.embed_dim, generator=g) * shape.embed_dim ** -0.5)
             self.head.bias.zero_()
+        self.backbone.visual.pixel_norm = pixel_norm   # uint8 batches: ToTensor + Normalize inside the stem kernel
         self.to(device)
         self.backbone.eval()  # the reference never leaves eval mode on the PEFT path (F7)
         self.distributed = distributed
@@ -136,7 +137,7 @@ class FineTuner(nn.Module):
         self.grads.zero_()
         if self.fused_tail:
             visual = self.backbone.visual
-            x_cls = visual.forward_cls_tokens(images.type(self.backbone.dtype))
+            x_cls = visual.forward_cls_tokens(self.backbone.pixels_for_stem(images))
             loss, _ = ops.tail_loss(visual, self.head, x_cls, labels)
             loss.backward()
             if self.distributed:

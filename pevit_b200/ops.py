@@ -92,6 +92,7 @@ class BlockPack:
 
     def _build(self, block, method: str):
         self.method = method
+        self.causal = int(getattr(block, "_pevit_causal", 0))   # text-tower blocks (_clip.ResidualAttentionBlock)
         attn = block.attn
         w_in = attn.in_proj_weight.detach()
         dev = w_in.device
@@ -274,8 +275,10 @@ class _BlockFn(torch.autograd.Function):
         elif method == "compacter":
             lna, b_down, b_up = (peft_c[0], peft_c[1]), peft_c[5], peft_c[8]
         need_grad = any(ctx.needs_input_grad)
+        if pack.causal and need_grad:
+            raise RuntimeError("pevit_b200: the causal (text tower) block is forward-only; gradients need the stock path")
         desc = L.BlockDesc(Lt, NB, D, pack.H, METHOD_IDS[method], pack.r, pack.alpha, int(need_grad), attn_impl,
-                           int(ctx.needs_input_grad[0]), out_tokens * NB)
+                           int(ctx.needs_input_grad[0]), out_tokens * NB, pack.causal)
         saved = torch.empty(lib.pevit_block_saved_bytes(C.byref(desc)), dtype=torch.uint8, device=x.device)
         ws = workspace(x.device, lib.pevit_block_workspace_bytes(C.byref(desc)))
         y = torch.empty_like(x) if out_tokens == 0 else torch.empty(out_tokens, NB, D, dtype=x.dtype, device=x.device)
@@ -438,9 +441,18 @@ class StemPack:
         return (w.data_ptr(), w._version, str(w.device))
 
 
+# pixel formats the stem kernel reads directly (pevit_pixel_dtype); uint8 only with ``visual.pixel_norm`` set
+PIXEL_DTYPES = {torch.float32: 0, torch.bfloat16: 1, torch.uint8: 2}
+
+
 @_on_device_of(1)
 def stem_forward(visual, images: torch.Tensor) -> torch.Tensor:
-    """conv1 + class token + positional embedding + ln_pre -> (L, N, D) fp32 (model.py:1034-1042)."""
+    """conv1 + class token + positional embedding + ln_pre -> (L, N, D) fp32 (model.py:1034-1042).
+
+    ``images``: fp32 or bf16 pixels as they are (bf16 gives bit-identical patches: the GEMM operand is bf16 either
+    way), or raw uint8 pixels when ``visual.pixel_norm = (mean3, std3)`` is set -- torchvision's ToTensor + Normalize
+    is then evaluated inside the kernel, bit-identical to the host transform, and the batch crosses PCIe as 1 byte
+    per value.  Anything else is cast to fp32 first, as ``encode_image`` does (model.py:1152)."""
     lib = L.lib()
     p = visual.conv1.kernel_size[0]
     if images.dim() != 4 or images.shape[1] != 3 or images.shape[2] != images.shape[3] or images.shape[2] % p != 0:
@@ -454,7 +466,14 @@ def stem_forward(visual, images: torch.Tensor) -> torch.Tensor:
     if pack is None or pack.key != StemPack.signature(visual):
         pack = StemPack(visual)
         object.__setattr__(visual, "_pevit_stem", pack)
-    images = _f32c(images)
+    px = PIXEL_DTYPES.get(images.dtype)
+    norm = getattr(visual, "pixel_norm", None)
+    if px is None or (px == 2 and norm is None):   # any other dtype: the reference's cast (model.py:1152)
+        images, px = images.float(), 0
+    images = images.contiguous()
+    mean = std = None
+    if px == 2:
+        mean, std = (C.c_float * 3)(*[float(v) for v in norm[0]]), (C.c_float * 3)(*[float(v) for v in norm[1]])
     NB, _, R, _ = images.shape
     D = visual.conv1.out_channels
     Lt = (R // p) ** 2 + 1
@@ -463,8 +482,8 @@ def stem_forward(visual, images: torch.Tensor) -> torch.Tensor:
     ws = torch.empty(nbytes, dtype=torch.uint8, device=images.device)
     small = [_f32c(t.detach()) for t in (visual.class_embedding, visual.positional_embedding, visual.ln_pre.weight,
                                          visual.ln_pre.bias)]
-    L.check(lib.pevit_patch_embed(_ptr(images), _ptr(pack.w), *(_ptr(t) for t in small), _ptr(x), _ptr(ws), NB, R, p, D,
-                                  small[1].shape[0], _stream()), "pevit_patch_embed")
+    L.check(lib.pevit_patch_embed_px(_ptr(images), px, mean, std, _ptr(pack.w), *(_ptr(t) for t in small), _ptr(x),
+                                     _ptr(ws), NB, R, p, D, small[1].shape[0], _stream()), "pevit_patch_embed_px")
     return x
 
 

@@ -43,6 +43,25 @@ VIT_B16 = ClipShape(512, 224, 12, 768, 16, 8, 64, 64, 1)
 VIT_L14 = ClipShape(768, 224, 24, 1024, 14, 8, 64, 64, 1)
 # Tiny shape used by the committed golden fixtures (2 heads so the scramble is non-trivial).
 VIT_TINY = ClipShape(32, 32, 2, 128, 16, 8, 64, 64, 1)
+# Text-tower shapes: a 2-layer tower of width 128 (2 heads) at a short context (two prompts share one
+# attention tile) and at CLIP's context length 77 (one prompt per tile); TEXT_B32 is the text tower every OpenAI CLIP
+# ViT-B checkpoint carries (width 512, 8 heads, 12 layers, vocabulary 49408) with a one-layer visual tower.
+TEXT_TINY16 = ClipShape(32, 32, 1, 128, 16, 16, 96, 128, 2)
+TEXT_TINY77 = ClipShape(32, 32, 1, 128, 16, 77, 96, 128, 2)
+TEXT_B32 = ClipShape(512, 32, 1, 128, 16, 77, 49408, 512, 12)
+
+
+def prompts(n: int, context_length: int, vocab_size: int, seed: int = 5) -> torch.Tensor:
+    """Token ids shaped like the CLIP tokenizer's output: start token, a few word ids, the EOT token (the HIGHEST id,
+    which is what ``encode_text`` looks for, model.py:1165), zero padding."""
+    g = torch.Generator().manual_seed(seed)
+    text = torch.zeros(n, context_length, dtype=torch.long)
+    for i in range(n):
+        words = int(torch.randint(1, context_length - 2, (1,), generator=g))
+        text[i, 0] = vocab_size - 2
+        text[i, 1:1 + words] = torch.randint(1, vocab_size - 2, (words,), generator=g)
+        text[i, 1 + words] = vocab_size - 1
+    return text
 
 
 def _block(prefix: str, width: int, layers: int, g: torch.Generator, sd: dict) -> None:

@@ -20,6 +20,8 @@ Fixtures
   b16blk_lora.npz           the same for BASELINE configs[2]'s shape: ViT-B/16 (D=768, H=12, L=197, N=4), LoRA
   l14blk_kadaptation.npz    and configs[4]'s: ViT-L/14 (D=1024, H=16, L=257, N=2), KAdaptation
                             (both exercise the L > 128 attention kernels at block level)
+  text_tiny16 / text_tiny77 encode_text (model.py:1154-1167) of a 2-layer, width-128 text tower at context 16 / 77:
+                            token ids and features (checkpoint regenerated from the seed at test time)
 """
 from __future__ import annotations
 
@@ -132,6 +134,18 @@ def shaped_block(method: str, D: int, H: int, L: int, N: int) -> dict:
     return out
 
 
+def text_case(shape, n: int) -> dict:
+    """encode_text of the unmodified reference (model.py:1154-1167) on a seeded checkpoint of ``shape`` (regenerated
+    from the seed at test time; checksum stored)."""
+    sd = synth.clip_state_dict(shape, seed=7)
+    torch.manual_seed(1234)
+    model = ref_import.build("kadaptation", sd).float()
+    text = synth.prompts(n, shape.context_length, shape.vocab_size, seed=5)
+    with torch.no_grad():
+        feat = model.encode_text(text)
+    return {"text": text, "features": feat, "sd_checksum": torch.stack([t.double().sum() for t in sd.values()]).sum()}
+
+
 def surface(method: str, sd) -> dict:
     """state_dict keys / named_parameters names with shapes: the drop-in boundary."""
     torch.manual_seed(0)
@@ -149,6 +163,10 @@ def save(name: str, d: dict) -> None:
 
 def main() -> None:
     assert ref_import.available(), "reference not mounted"
+    if sys.argv[1:] == ["text"]:  # only the text-tower fixtures (added later; everything else stays byte-identical)
+        save("text_tiny16.npz", text_case(synth.TEXT_TINY16, 5))
+        save("text_tiny77.npz", text_case(synth.TEXT_TINY77, 3))
+        return
     sd = synth.clip_state_dict(synth.VIT_TINY, seed=0)
     save("tiny_clip_sd.npz", sd)
     for m in METHODS:
@@ -157,6 +175,8 @@ def main() -> None:
         save(f"b32blk_{m}.npz", b32_block(m))
     save("b16blk_lora.npz", shaped_block("lora", 768, 12, 197, 4))
     save("l14blk_kadaptation.npz", shaped_block("kadaptation", 1024, 16, 257, 2))
+    save("text_tiny16.npz", text_case(synth.TEXT_TINY16, 5))
+    save("text_tiny77.npz", text_case(synth.TEXT_TINY77, 3))
     import json
     with open(os.path.join(HERE, "surface.json"), "w") as fh:
         json.dump({m: surface(m, sd) for m in METHODS}, fh, indent=0)

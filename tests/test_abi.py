@@ -33,13 +33,13 @@ def test_library_exports_every_declared_symbol(built):
 def test_ctypes_binding_covers_the_header(built):
     assert sorted(L.EXPORTED) == declared_symbols()
     lib = L.lib()
-    assert lib.pevit_abi_version() == 1
+    assert lib.pevit_abi_version() == 2
     assert lib.pevit_last_error() is not None
 
 
 def test_struct_layouts_match_the_header():
     # sizes computed from the C declarations (LP64): pointers 8 B, int32/float 4 B, natural alignment
-    assert ctypes.sizeof(L.BlockDesc) == 11 * 4
+    assert ctypes.sizeof(L.BlockDesc) == 12 * 4
     assert ctypes.sizeof(L.BlockWeights) == 28 * 8
     assert ctypes.sizeof(L.BlockGrads) == 9 * 8
     assert ctypes.sizeof(L.GemmArgs) == 152

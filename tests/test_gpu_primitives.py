@@ -387,6 +387,20 @@ def test_patch_embed_stem(lib, NB, R, p, D):
     torch.cuda.synchronize()
     assert got.shape == ref.shape
     assert rel_inf(got, ref) < 1e-2
+    # bf16 pixels: the GEMM operand is the bf16 rounding of the image either way -> bit-identical stem output
+    with torch.no_grad():
+        assert torch.equal(ops.stem_forward(vis, img.bfloat16()), got)
+    # uint8 pixels + pixel_norm: ToTensor + Normalize inside the kernel, bit-identical to the host transform
+    mean, std = (0.48145466, 0.4578275, 0.40821073), (0.26862954, 0.26130258, 0.27577711)   # CLIP's Normalize
+    u8 = torch.randint(0, 256, (NB, 3, R, R), dtype=torch.uint8)
+    host = u8.float().div(255.0)                                   # torchvision ToTensor
+    host = host.sub_(torch.tensor(mean).view(1, 3, 1, 1)).div_(torch.tensor(std).view(1, 3, 1, 1))   # Normalize
+    with torch.no_grad():
+        want = ops.stem_forward(vis, host.cuda())
+        assert not torch.equal(ops.stem_forward(vis, u8.cuda()), want)    # no pixel_norm: plain cast, as the reference
+        vis.pixel_norm = (mean, std)
+        assert torch.equal(ops.stem_forward(vis, u8.cuda()), want)
+        vis.pixel_norm = None
 
 
 @pytest.mark.parametrize("N,D,E,Cn", [(256, 768, 512, 10), (7, 128, 64, 3), (64, 1024, 768, 100)])

@@ -107,3 +107,38 @@ def test_shipped_init_matches_reference_statistics():
     n = sum(p[k].numel() for k in O.trainable_names(p, "kadaptation"))
     D, layers = 128, 2
     assert n == layers * (4 * 32 * (D // 32) + D) + 4 * 32 * 32
+
+
+TEXT_FIXTURES = [("text_tiny16.npz", synth.TEXT_TINY16), ("text_tiny77.npz", synth.TEXT_TINY77)]
+
+
+@pytest.mark.parametrize("fixture,shape", TEXT_FIXTURES, ids=[f[0][:-4] for f in TEXT_FIXTURES])
+def test_encode_text_matches_reference_fixture(fixture, shape):
+    """SURVEY 8f #4: the oracle's text tower (causal mask, EOT row, projection) against the reference's encode_text."""
+    fix = load_npz(fixture)
+    sd = synth.clip_state_dict(shape, seed=7)
+    chk = torch.stack([t.double().sum() for t in sd.values()]).sum()
+    if abs(chk.item() - fix["sd_checksum"].item()) > 1e-6:
+        pytest.skip("torch RNG stream differs from the one the fixture was generated with")
+    assert torch.equal(fix["text"], synth.prompts(fix["text"].shape[0], shape.context_length, shape.vocab_size, seed=5))
+    feat = O.encode_text(fix["text"], sd)
+    assert rel_inf(feat, fix["features"]) < OUT_TOL
+    # the mask matters: without it the features move by far more than the tolerance
+    x = O.attention(torch.randn(6, 2, 128), {k: v for k, v in sd.items()}, "transformer.resblocks.0.", 2, "plain")
+    xc = O.attention(torch.randn(6, 2, 128), {k: v for k, v in sd.items()}, "transformer.resblocks.0.", 2, "plain",
+                     causal=True)
+    assert x.shape == xc.shape
+
+
+def test_repo_text_tower_on_cpu_is_the_stock_path():
+    """On CPU (or whenever a gradient is wanted) the text tower keeps the stock nn.MultiheadAttention path and matches
+    the reference fixture in fp32; the causal flag is derived from the mask build_attention_mask() makes."""
+    import pevit_b200
+    fix = load_npz("text_tiny16.npz")
+    sd = synth.clip_state_dict(synth.TEXT_TINY16, seed=7)
+    model = pevit_b200.build_model(dict(sd))
+    assert all(blk._pevit_causal == 1 and not blk.fused for blk in model.transformer.resblocks)
+    assert all(blk._pevit_causal == 0 and blk.fused for blk in model.visual.transformer.resblocks)
+    with torch.no_grad():
+        feat = model.encode_text(fix["text"])
+    assert rel_inf(feat, fix["features"]) < OUT_TOL
