@@ -57,6 +57,8 @@ def parse():
     ap.add_argument("--no-gpu-eager-baseline", action="store_true")
     ap.add_argument("--no-parity-probe", action="store_true")
     ap.add_argument("--no-text-tower", action="store_true")
+    ap.add_argument("--no-peer-exchange", action="store_true",
+                    help="N > 1: NCCL all-reduce + SGD kernel instead of the fused one-shot peer-memory all-reduce + SGD")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-graph", action="store_true", help="time the eager step instead of the CUDA-graph replay")
     ap.add_argument("--pixels", default="bf16", choices=["f32", "bf16", "u8"],
@@ -390,7 +392,8 @@ def run_b200(args):
     _lib.check(lib.pevit_check_device(), "pevit_check_device")
     shape = shape_of(args.model)
     tuner = engine.FineTuner(args.method, shape, device=dev, distributed=world > 1, seed=0,
-                             pixel_norm=CLIP_NORM if args.pixels == "u8" else None)
+                             pixel_norm=CLIP_NORM if args.pixels == "u8" else None,
+                             peer_exchange=False if args.no_peer_exchange else None)
     N, R = args.batch, shape.image_resolution
     g = torch.Generator(device=dev).manual_seed(1000 + rank)
     images = to_pixels(torch.randn(N, 3, R, R, device=dev, generator=g), args.pixels)
@@ -582,6 +585,12 @@ def run_b200(args):
         "cuda_graph": graphed, "eager_profiled_ms_per_step": ms_step_eager,
         "kernel_timing": "per-launch CUDA events in a separate eager pass of the same K steps right after the timed region",
     }
+    if world > 1:
+        line["exchange"] = {"kind": "one-shot all-reduce over CUDA-IPC peer memory fused with the SGD update, 1 launch "
+                                    "per step (pevit_allreduce_sgd)" if tuner.peer is not None else
+                                    "ncclAllReduce over the flat gradient buffer + SGD kernel(s)",
+                            "floats": int(tuner.flat_grad.numel()),
+                            "timed_out": bool(tuner.peer.timed_out()) if tuner.peer is not None else None}
     tuner.release_graph()
     torch.cuda.synchronize()
     if world == 1:

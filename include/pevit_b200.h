@@ -162,6 +162,30 @@ int pevit_head_ce_bwd(const float* dlogits, const float* feat, const float* w, c
  * g' = grad_scale * g + wd * p; m = momentum * m + g'; p -= lr * m.  grad_scale folds 1/world_size in. */
 int pevit_sgd_momentum(float* p, const float* g, float* m, size_t n, float lr, float momentum, float weight_decay,
                        float grad_scale, void* stream);
+/* ------------------------------------------------------------------ data-parallel exchange fused with the update
+ * (the reference's loop has optimizer.step() at kadaptation_clip.py:353 and no exchange; under
+ * data parallelism it would be DDP's ncclAllReduce followed by torch.optim.SGD.)  ONE launch per rank and step:
+ * a one-shot all-reduce over peer-mapped memory -- every rank loads each 16-byte chunk of all `world` gradient
+ * buffers over NVLink, sums them in rank order (bit-identical sums on every rank) -- fused with the momentum-SGD
+ * update of the local flat parameters.  Elements [0, n_decayed) take weight_decay, the rest 0 (optim/build.py:18-86).
+ *
+ * Buffers: pevit_peer_alloc() cudaMallocs n gradient floats + a control block (pevit_peer_buffer_bytes(n) in all),
+ * zeroes it and returns a 64-byte CUDA IPC handle to hand to the other ranks (any transport: the caller's
+ * torch.distributed all_gather); pevit_peer_open() maps a peer's buffer.  peers[r] = rank r's base pointer
+ * (peers[rank] = the own allocation).  The first `n` floats of the own buffer are the flat gradient buffer the
+ * backward pass fills; it keeps the LOCAL gradient (the sum goes straight into the update).
+ * Synchronisation is inside the kernel (flag hand-shakes at system scope, monotonic epochs kept in device memory, so a
+ * captured CUDA graph replays it); every rank must launch it once per step with the same n.  A hand-shake that waits
+ * longer than 20 s (PEVIT_PEER_TIMEOUT_MS) gives up and raises the error word pevit_peer_status() reads -- never a hung device.
+ * world <= 8, one node. */
+size_t pevit_peer_buffer_bytes(size_t n_floats);
+int pevit_peer_alloc(size_t n_floats, void** ptr, void* ipc_handle_64_bytes);
+int pevit_peer_open(const void* ipc_handle_64_bytes, void** ptr);
+int pevit_peer_close(void* ptr);
+int pevit_peer_free(void* ptr);
+int pevit_peer_status(const void* own, size_t n_floats, int32_t* timed_out, void* stream);   /* synchronises `stream` */
+int pevit_allreduce_sgd(void* const* peers, int32_t world, int32_t rank, size_t n, size_t n_decayed, float* p, float* m,
+                        float lr, float momentum, float weight_decay, float grad_scale, void* stream);
 /* weight packing: fp32 [rows][cols] -> bf16 (same layout / transposed with leading dim ldd) */
 int pevit_cast_bf16(const float* src, void* dst, size_t n, void* stream);
 int pevit_transpose_bf16(const float* src, int32_t rows, int32_t cols, void* dst, int32_t ldd, void* stream);

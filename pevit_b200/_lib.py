@@ -99,6 +99,14 @@ _SIGNATURES = {
     "pevit_sgd_momentum": (c_int32, [c_void_p] * 3 + [c_size_t] + [c_float] * 4 + [c_void_p]),
     "pevit_cast_bf16": (c_int32, [c_void_p, c_void_p, c_size_t, c_void_p]),
     "pevit_transpose_bf16": (c_int32, [c_void_p, c_int32, c_int32, c_void_p, c_int32, c_void_p]),
+    "pevit_peer_buffer_bytes": (c_size_t, [c_size_t]),
+    "pevit_peer_alloc": (c_int32, [c_size_t, _P(c_void_p), c_void_p]),
+    "pevit_peer_open": (c_int32, [c_void_p, _P(c_void_p)]),
+    "pevit_peer_close": (c_int32, [c_void_p]),
+    "pevit_peer_free": (c_int32, [c_void_p]),
+    "pevit_peer_status": (c_int32, [c_void_p, c_size_t, _P(c_int32), c_void_p]),
+    "pevit_allreduce_sgd": (c_int32, [_P(c_void_p), c_int32, c_int32, c_size_t, c_size_t, c_void_p, c_void_p,
+                                      c_float, c_float, c_float, c_float, c_void_p]),
     "pevit_patch_embed_workspace_bytes": (c_size_t, [c_int32] * 4),
     "pevit_patch_embed": (c_int32, [c_void_p] * 8 + [c_int32] * 5 + [c_void_p]),
     "pevit_patch_embed_px": (c_int32, [c_void_p, c_int32] + [c_void_p] * 9 + [c_int32] * 5 + [c_void_p]),

@@ -312,6 +312,22 @@ int pevit_prof_read(double* ms, int64_t* launches, int32_t n) {
 }
 int64_t pevit_launch_count(void) { return launch_count(); }
 
+size_t pevit_peer_buffer_bytes(size_t n_floats) { return peer_buffer_bytes(n_floats); }
+int pevit_peer_alloc(size_t n_floats, void** ptr, void* ipc_handle) { return peer_alloc(n_floats, ptr, ipc_handle); }
+int pevit_peer_open(const void* ipc_handle, void** ptr) { return peer_open(ipc_handle, ptr); }
+int pevit_peer_close(void* ptr) { return peer_close(ptr); }
+int pevit_peer_free(void* ptr) { return peer_free(ptr); }
+int pevit_peer_status(const void* own, size_t n_floats, int32_t* timed_out, void* stream) {
+  int t = 0;
+  int rc = peer_status(as_stream(stream), own, n_floats, &t);
+  if (rc == 0) *timed_out = t;
+  return rc;
+}
+int pevit_allreduce_sgd(void* const* peers, int32_t world, int32_t rank, size_t n, size_t n_decayed, float* p, float* m,
+                        float lr, float momentum, float weight_decay, float gscale, void* stream) {
+  return allreduce_sgd(as_stream(stream), peers, world, rank, n, n_decayed, p, m, lr, momentum, weight_decay, gscale);
+}
+
 size_t pevit_patch_embed_workspace_bytes(int32_t nb, int32_t resolution, int32_t patch, int32_t d) {
   return patch_embed_workspace_bytes(nb, resolution, patch, d);
 }

@@ -78,7 +78,7 @@ inline cudaError_t launch_kernel(void (*kern)(KArgs...), dim3 grid, dim3 block, 
 enum ProfClass {
   PC_GEMM_QKV = 0, PC_GEMM_OUT, PC_GEMM_FC, PC_GEMM_PROJ, PC_GEMM_DPROJ, PC_GEMM_DFC, PC_GEMM_DOUT, PC_GEMM_DQKV,
   PC_GEMM_DT, PC_GEMM_DELTA, PC_GEMM_BOTTLENECK, PC_GEMM_OTHER, PC_ATTN_FWD, PC_ATTN_BWD, PC_LN_FWD, PC_LN_BWD, PC_ATB, PC_COLSUM,
-  PC_EXPAND, PC_FACTOR_GRADS, PC_CAST, PC_STEM, PC_GEMM_STEM, PC_TAIL, PC_COUNT
+  PC_EXPAND, PC_FACTOR_GRADS, PC_CAST, PC_STEM, PC_GEMM_STEM, PC_TAIL, PC_ALLREDUCE_SGD, PC_COUNT
 };
 void prof_set_tag(int cls);  // class of the next launch on this thread (overrides the launcher's default)
 struct ProfScope {

@@ -59,7 +59,7 @@ thread_local int g_tag = -1;
 const char* const kClassNames[PC_COUNT] = {
     "gemm_qkv", "gemm_out", "gemm_fc", "gemm_proj", "gemm_dproj", "gemm_dfc", "gemm_dout", "gemm_dqkv", "gemm_dT",
     "gemm_delta", "gemm_bottleneck", "gemm_other", "attn_fwd", "attn_bwd", "ln_fwd", "ln_bwd", "atb", "colsum", "expand",
-    "factor_grads", "cast", "stem", "gemm_stem", "tail"};
+    "factor_grads", "cast", "stem", "gemm_stem", "tail", "allreduce_sgd"};
 }  // namespace
 
 void prof_set_tag(int cls) { g_tag = cls; }

@@ -164,6 +164,18 @@ int head_ce_bwd(cudaStream_t s, const float* dlogits, const float* feat, const f
 // torch.optim.SGD(momentum, weight_decay) over flat buffers; gscale folds 1/world_size of the gradient all-reduce in.
 int sgd_momentum(cudaStream_t s, float* p, const float* g, float* m, size_t n, float lr, float mu, float wd, float gscale);
 
+// ------------------------------------------------------------------ peer.cu
+// One-shot all-reduce of the flat gradient buffer over peer-mapped (CUDA IPC) memory fused with the SGD update.
+constexpr int PEER_MAX_WORLD = 8, PEER_MAX_CTAS = 16, PEER_HANDLE_BYTES = 64;
+size_t peer_buffer_bytes(size_t n);   // n gradient floats + the control block (flags, epochs, error word)
+int peer_alloc(size_t n, void** ptr, void* ipc_handle);
+int peer_open(const void* ipc_handle, void** ptr);
+int peer_close(void* ptr);
+int peer_free(void* ptr);
+int peer_status(cudaStream_t s, const void* own, size_t n, int* timed_out);
+int allreduce_sgd(cudaStream_t s, void* const* peers, int world, int rank, size_t n, size_t n_decayed, float* p, float* m,
+                  float lr, float mu, float wd, float gscale);
+
 // ------------------------------------------------------------------ elementwise.cu
 int cast_f32_to_bf16(cudaStream_t s, const float* src, bf16* dst, size_t n);
 // dst[c][r] = src[r][c]  (fp32 -> bf16 transpose; weight prep for dgrad GEMMs)

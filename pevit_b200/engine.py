@@ -6,6 +6,7 @@ never allocated).
 """
 from __future__ import annotations
 
+import os
 from typing import Optional
 
 import torch
@@ -48,10 +49,13 @@ class FlatGrads:
     """One flat fp32 buffer holding every trainable gradient; each ``p.grad`` is a view into it, so the
     data-parallel exchange is ONE collective per step regardless of how many PEFT tensors there are."""
 
-    def __init__(self, params, device=None):
+    def __init__(self, params, device=None, flat: Optional[torch.Tensor] = None):
         self.params = list(params)
         device = device if device is not None else self.params[0].device
-        self.flat = torch.zeros(sum(p.numel() for p in self.params), dtype=torch.float32, device=device)
+        n = sum(p.numel() for p in self.params)
+        # ``flat``: a caller-provided buffer (the peer-mapped allocation of the fused exchange) instead of a new one
+        self.flat = torch.zeros(n, dtype=torch.float32, device=device) if flat is None else flat
+        assert self.flat.numel() == n and self.flat.dtype == torch.float32
         off = 0
         for p in self.params:
             p.grad = self.flat[off:off + p.numel()].view_as(p)
@@ -78,7 +82,8 @@ class FineTuner(nn.Module):
     def __init__(self, method: str, shape: synth.ClipShape, num_classes: int = 10, device="cuda", lr: float = 1e-3,
                  momentum: float = 0.9, weight_decay: float = 0.0, seed: int = 0, randomize: bool = True,
                  process_group: Optional[dist.ProcessGroup] = None, distributed: bool = False,
-                 fused_tail: Optional[bool] = None, without_wd=("bias", "ln"), pixel_norm=None):
+                 fused_tail: Optional[bool] = None, without_wd=("bias", "ln"), pixel_norm=None,
+                 peer_exchange: Optional[bool] = None):
         super().__init__()
         self.method = method
         sd = synth.clip_state_dict(shape, seed=seed)
@@ -114,20 +119,53 @@ class FineTuner(nn.Module):
         self.used = [p for _, p in decayed] + [p for _, p in no_wd]
         self.used_names = [n for n, _ in decayed] + [n for n, _ in no_wd]
         self.n_decayed = sum(p.numel() for _, p in decayed)
-        self.grads = FlatGrads(self.used, device)
+        # step tail on this library's kernels (ln_post + projection GEMM + head/CE kernel; one SGD kernel over flat
+        # parameter / gradient / momentum buffers) instead of ~30 small PyTorch launches; CUDA only
+        self.fused_tail = (torch.device(device).type == "cuda") if fused_tail is None else fused_tail
+        # data-parallel exchange: the gradient buffer lives in peer-mapped memory and ONE kernel per step sums it over
+        # the ranks and applies the update; NCCL all-reduce + SGD kernel when that is not available
+        self.peer = None
+        if peer_exchange is None:
+            peer_exchange = os.environ.get("PEVIT_PEER_EXCHANGE", "1") != "0"
+        if peer_exchange and distributed and self.fused_tail and 1 < self.world <= 8:
+            self.peer = self._open_peer_exchange(sum(p.numel() for p in self.used), device, process_group)
+        self.grads = FlatGrads(self.used, device, flat=self.peer.flat if self.peer is not None else None)
         self.flat_grad = self.grads.flat
         self.opt = torch.optim.SGD([{"params": [p for _, p in decayed]},
                                     {"params": [p for _, p in no_wd], "weight_decay": 0.0}],
                                    lr=lr, momentum=momentum, weight_decay=weight_decay)
-        # step tail on this library's kernels (ln_post + projection GEMM + head/CE kernel; one SGD kernel over flat
-        # parameter / gradient / momentum buffers) instead of ~30 small PyTorch launches; CUDA only
-        self.fused_tail = (torch.device(device).type == "cuda") if fused_tail is None else fused_tail
         self.hyper = (lr, momentum, weight_decay)
         if self.fused_tail:
             self.flat_params = FlatParams(self.used, device)
             self.flat_momentum = torch.zeros_like(self.flat_params.flat)
         # every trainable .grad is a persistent view into the flat buffer: let the block kernels add into it directly
         ops.set_direct_grad_accumulation(True)
+
+    def _open_peer_exchange(self, n: int, device, group):
+        """Map every rank's gradient buffer into every other rank (CUDA IPC, one node).  The decision is collective:
+        if any rank cannot (different hosts, IPC refused by the container), ALL ranks keep the NCCL path."""
+        import socket
+        rank, world = dist.get_rank(group), dist.get_world_size(group)
+
+        def exchange(payload):
+            out = [None] * world
+            dist.all_gather_object(out, payload, group=group)
+            return out
+        buf, ok = None, 1
+        try:
+            if len(set(exchange(socket.gethostname()))) != 1:
+                raise RuntimeError("ranks span several hosts")
+            buf = ops.PeerGradBuffer(n, torch.device(device), rank, world, exchange)
+        except Exception as exc:  # noqa: BLE001 - any failure means "use NCCL", decided together below
+            print(f"[pevit_b200] rank {rank}: peer-memory exchange unavailable ({exc!r}); using NCCL all-reduce", flush=True)
+            ok = 0
+        flag = torch.tensor([ok], device=device, dtype=torch.int32)
+        dist.all_reduce(flag, op=dist.ReduceOp.MIN, group=group)
+        if int(flag.item()) != 1:
+            if buf is not None:
+                buf.close()
+            return None
+        return buf
 
     def forward(self, images: torch.Tensor) -> torch.Tensor:
         return self.head(self.backbone.encode_image(images).float())
@@ -140,10 +178,13 @@ class FineTuner(nn.Module):
             x_cls = visual.forward_cls_tokens(self.backbone.pixels_for_stem(images))
             loss, _ = ops.tail_loss(visual, self.head, x_cls, labels)
             loss.backward()
-            if self.distributed:
-                self.grads.all_reduce_sum(self.group)
             lr, mu, wd = self.hyper
             fp, fg, fm, nd = self.flat_params.flat, self.flat_grad, self.flat_momentum, self.n_decayed
+            if self.peer is not None:   # one launch: sum over the ranks' peer-mapped buffers + both weight-decay groups
+                ops.allreduce_sgd_(self.peer, fp, fm, nd, lr, mu, wd)
+                return loss.detach()
+            if self.distributed:
+                self.grads.all_reduce_sum(self.group)
             if wd == 0.0 or nd == fp.numel():
                 ops.sgd_momentum_(fp, fg, fm, lr, mu, wd, 1.0 / self.world)
             else:  # decayed range, then the zero-weight-decay group

@@ -608,3 +608,84 @@ def sgd_momentum_(flat_p: torch.Tensor, flat_g: torch.Tensor, flat_m: torch.Tens
     assert flat_p.dtype == flat_g.dtype == flat_m.dtype == torch.float32 and flat_p.numel() == flat_g.numel() == flat_m.numel()
     L.check(L.lib().pevit_sgd_momentum(_ptr(flat_p), _ptr(flat_g), _ptr(flat_m), flat_p.numel(), lr, momentum, weight_decay,
                                        grad_scale, _stream()), "pevit_sgd_momentum")
+
+
+# ----------------------------------------------------------------------------- fused all-reduce + SGD
+class _DeviceArray:
+    """CUDA array interface over a raw device pointer (memory owned by the C library)."""
+
+    def __init__(self, ptr: int, n: int, owner):
+        self.__cuda_array_interface__ = {"shape": (n,), "typestr": "<f4", "data": (ptr, False), "version": 3}
+        self.owner = owner
+
+
+class PeerGradBuffer:
+    """The flat fp32 gradient buffer of one rank inside a CUDA-IPC allocation that every other rank of the node has
+    mapped (``pevit_peer_alloc`` / ``pevit_peer_open``), for ``allreduce_sgd_``: the data-parallel gradient exchange
+    and the optimizer update as ONE kernel over NVLink peer memory instead of ncclAllReduce + SGD launches.
+
+    ``exchange(payload) -> list of payloads by rank`` is the caller's transport for the 64-byte handles (the engine
+    passes ``torch.distributed.all_gather_object``).  ``virtual_ranks`` > 0 instead creates that many buffers in THIS
+    process on one device (no IPC): the single-GPU test drives them from separate streams."""
+
+    def __init__(self, n: int, device: torch.device, rank: int = 0, world: int = 1, exchange=None, virtual_ranks: int = 0):
+        lib = L.lib()
+        self.n, self.rank, self.world, self.device = n, rank, world, torch.device(device)
+        self._opened, self._owned = [], []
+        with torch.cuda.device(self.device):
+            if virtual_ranks:
+                self.world = virtual_ranks
+                ptrs = []
+                for _ in range(virtual_ranks):
+                    ptr, handle = C.c_void_p(), (C.c_ubyte * 64)()
+                    L.check(lib.pevit_peer_alloc(n, C.byref(ptr), handle), "pevit_peer_alloc")
+                    ptrs.append(ptr.value)
+                self._owned = list(ptrs)
+                self.flats = [torch.as_tensor(_DeviceArray(p, n, self), device=self.device) for p in ptrs]
+                self.flat = self.flats[rank]
+            else:
+                ptr, handle = C.c_void_p(), (C.c_ubyte * 64)()
+                L.check(lib.pevit_peer_alloc(n, C.byref(ptr), handle), "pevit_peer_alloc")
+                self._owned = [ptr.value]
+                self.flat = torch.as_tensor(_DeviceArray(ptr.value, n, self), device=self.device)
+                handles = exchange(bytes(handle)) if world > 1 else [bytes(handle)]
+                ptrs = []
+                for r, h in enumerate(handles):
+                    if r == rank:
+                        ptrs.append(ptr.value)
+                        continue
+                    other = C.c_void_p()
+                    L.check(lib.pevit_peer_open((C.c_ubyte * 64).from_buffer_copy(h), C.byref(other)), "pevit_peer_open")
+                    self._opened.append(other.value)
+                    ptrs.append(other.value)
+        self.peers = (C.c_void_p * self.world)(*ptrs)
+
+    def timed_out(self, rank: Optional[int] = None) -> bool:
+        """True if a hand-shake of any launch so far gave up waiting for a peer (synchronises the current stream)."""
+        flag = C.c_int32(0)
+        own = self.peers[self.rank if rank is None else rank]
+        with torch.cuda.device(self.device):
+            L.check(L.lib().pevit_peer_status(own, self.n, C.byref(flag), _stream()), "pevit_peer_status")
+        return bool(flag.value)
+
+    def close(self) -> None:
+        lib = L.lib()
+        with torch.cuda.device(self.device):
+            torch.cuda.synchronize()
+            for p in self._opened:
+                lib.pevit_peer_close(p)
+            for p in self._owned:
+                lib.pevit_peer_free(p)
+        self._opened, self._owned = [], []
+
+
+def allreduce_sgd_(buf: PeerGradBuffer, flat_p: torch.Tensor, flat_m: torch.Tensor, n_decayed: int, lr: float,
+                   momentum: float, weight_decay: float, rank: Optional[int] = None) -> None:
+    """p, m <- SGD(momentum, wd on the first ``n_decayed`` elements) with g = (sum over ranks of the peer-mapped
+    gradient buffers) / world, in one launch (``pevit_allreduce_sgd``).  Every rank must call it once per step."""
+    assert flat_p.is_contiguous() and flat_m.is_contiguous() and flat_p.dtype == flat_m.dtype == torch.float32
+    assert flat_p.numel() == flat_m.numel() == buf.n
+    with torch.cuda.device(buf.device):
+        L.check(L.lib().pevit_allreduce_sgd(buf.peers, buf.world, buf.rank if rank is None else rank, buf.n, n_decayed,
+                                            _ptr(flat_p), _ptr(flat_m), lr, momentum, weight_decay, 1.0 / buf.world,
+                                            _stream()), "pevit_allreduce_sgd")
