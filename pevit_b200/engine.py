@@ -138,8 +138,8 @@ class FineTuner(nn.Module):
         if self.fused_tail:
             self.flat_params = FlatParams(self.used, device)
             self.flat_momentum = torch.zeros_like(self.flat_params.flat)
-        # every trainable .grad is a persistent view into the flat buffer: let the block kernels add into it directly
-        ops.set_direct_grad_accumulation(True)
+        # every trainable .grad is a persistent view into the flat buffer: step() lets the block kernels add into it
+        # directly (scoped to the step: ops.direct_grad_accumulation; nothing process-global is switched on)
 
     def _open_peer_exchange(self, n: int, device, group):
         """Map every rank's gradient buffer into every other rank (CUDA IPC, one node).  The decision is collective:
@@ -172,6 +172,10 @@ class FineTuner(nn.Module):
 
     def step(self, images: torch.Tensor, labels: torch.Tensor) -> torch.Tensor:
         """One fine-tune step on this rank's local batch; returns the (device) loss."""
+        with ops.direct_grad_accumulation(True):
+            return self._step(images, labels)
+
+    def _step(self, images: torch.Tensor, labels: torch.Tensor) -> torch.Tensor:
         self.grads.zero_()
         if self.fused_tail:
             visual = self.backbone.visual

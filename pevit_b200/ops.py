@@ -7,7 +7,9 @@ autograd inputs, so frozen-backbone gradients are never allocated.
 """
 from __future__ import annotations
 
+import contextlib
 import ctypes as C
+import weakref
 from typing import Dict, Optional, Tuple
 
 import torch
@@ -65,6 +67,19 @@ _direct_grads = [False]
 
 def set_direct_grad_accumulation(on: bool) -> None:
     _direct_grads[0] = bool(on)
+
+
+@contextlib.contextmanager
+def direct_grad_accumulation(on: bool = True):
+    """Scope the direct-accumulation mode to the caller's own forward / backward (``engine.FineTuner.step``) instead
+    of switching it on for every block of the process: outside the scope autograd's plain contract holds
+    (AccumulateGrad, hooks, ``torch.autograd.grad``)."""
+    prev = _direct_grads[0]
+    _direct_grads[0] = bool(on)
+    try:
+        yield
+    finally:
+        _direct_grads[0] = prev
 
 
 _workspace: Dict[Tuple[int, int], torch.Tensor] = {}
@@ -130,6 +145,7 @@ class BlockPack:
             self.w_up, self.w_up_t = torch.empty(D, BOTTLENECK, **bf), torch.empty(BOTTLENECK, D, **bf)
         self._grad_scratch = None
         self.expanded_ahead = False
+        self.stamp = 0   # bumped by every factor expansion
         self.key = self.signature(block)
 
     def dense_grad_scratch(self) -> torch.Tensor:
@@ -193,6 +209,7 @@ def _expand_factors(pack: BlockPack, peft_c: tuple, st: int) -> None:
     """Write the per-step operands derived from the PEFT tensors of one block: the expanded low-rank operands (P^T
     rows of the in-projection, Q, alpha*Q) or the bf16 bottleneck weights (Compacter: PHM expansion)."""
     lib, D = L.lib(), pack.D
+    pack.stamp += 1   # the derived operands below now belong to THIS set of PEFT values (checked in backward)
     if pack.method == "compacter":
         _, _, rule, dl, dr, _, ul, ur, _ = peft_c
         L.check(lib.pevit_phm_expand(_ptr(rule), rule.shape[0], _ptr(dl), _ptr(dr), _ptr(ul), _ptr(ur), D, BOTTLENECK,
@@ -285,7 +302,7 @@ class _BlockFn(torch.autograd.Function):
         w = pack.weights_struct(delta_bias, lna, b_down, b_up)
         L.check(lib.pevit_block_fwd(C.byref(desc), C.byref(w), _ptr(x), _ptr(y), _ptr(saved), _ptr(ws), st),
                 "pevit_block_fwd")
-        ctx.pack, ctx.desc = pack, desc
+        ctx.pack, ctx.desc, ctx.stamp = pack, desc, pack.stamp
         ctx.live = peft if (_direct_grads[0] and method in ("kadaptation", "compacter")) else None
         ctx.save_for_backward(x, saved, *peft_c)
         return y
@@ -301,13 +318,21 @@ class _BlockFn(torch.autograd.Function):
         dev = x.device
         st = _stream()
         dy = _f32c(dy)
+        if pack.stamp != ctx.stamp and method != "plain":
+            # another forward (or expand_ahead) re-wrote this block's derived operands since the forward this backward
+            # belongs to: rebuild them from the PEFT tensors that forward saved instead of using the newer factors
+            _expand_factors(pack, tuple(peft_c), st)
+            pack.expanded_ahead = False
+            ctx.stamp = pack.stamp
         f32 = dict(dtype=torch.float32, device=dev)
         dx = torch.empty_like(x) if desc.need_dx else None
         dx16 = torch.empty(x.shape, dtype=torch.bfloat16, device=dev) if desc.need_dx else None
         shadow, _dx_shadow[0] = _dx_shadow[0], None
         dy16 = None
-        if shadow is not None and shadow[0] == (dy.data_ptr(), dy._version, tuple(dy.shape)):
-            dy16 = shadow[1]
+        # the shadow is keyed on the tensor OBJECT (weak reference) as well as its address / version / shape: a freed
+        # dx whose address the caching allocator hands to an unrelated dy of the same shape must not match
+        if shadow is not None and shadow[0]() is dy and shadow[1] == (dy.data_ptr(), dy._version, tuple(dy.shape)):
+            dy16 = shadow[2]
         g = L.BlockGrads()
         delta_bias = lna = b_down = b_up = None
         live = ctx.live
@@ -355,7 +380,7 @@ class _BlockFn(torch.autograd.Function):
         L.check(lib.pevit_block_bwd(C.byref(desc), C.byref(w), _ptr(x), _ptr(dy), _ptr(dy16), _ptr(dx), _ptr(dx16),
                                     C.byref(g), _ptr(saved), _ptr(ws), st), "pevit_block_bwd")
         if dx is not None:
-            _dx_shadow[0] = ((dx.data_ptr(), dx._version, tuple(dx.shape)), dx16)
+            _dx_shadow[0] = (weakref.ref(dx), (dx.data_ptr(), dx._version, tuple(dx.shape)), dx16)
         if method == "kadaptation" and direct:
             u1, v1, u2, v2, s, t, _ = peft_c
             L.check(lib.pevit_kad_factor_grads_acc(_ptr(d_pmat), _ptr(d_qmat), _ptr(u1), _ptr(v1), _ptr(u2), _ptr(v2),

@@ -324,3 +324,36 @@ def test_inference_path_saves_nothing(method):
     # the size query is an upper bound the caller allocates and may free right after a save = 0 call (KAdaptation / LoRA
     # ask for the forward-internal scratch only; the bottleneck methods report one size for both modes)
     assert sizes[0] <= sizes[1], sizes
+
+
+@pytest.mark.gpu
+def test_backward_uses_the_factors_of_its_own_forward():
+    """The per-block operand pack is shared by every forward of that block.  A second forward with OTHER PEFT values
+    (here: a clone of the block's parameters, changed) between a forward and its backward must not leak its factors
+    into that backward: the pack is re-expanded from the tensors the first forward saved (version stamp)."""
+    from pevit_b200 import _clip, ops
+    torch.manual_seed(5)
+    tower = _clip.Transformer(128, 1, 2, kattention=True, method=_clip.KAD).cuda().eval()
+    synth.randomize_adapters(tower.named_parameters(), seed=6)
+    for name, prm in tower.named_parameters():
+        prm.requires_grad_("adapter" in name or "phm_rule" in name or name.endswith("attn.b"))
+    blk = tower.resblocks[0]
+    x = torch.randn(5, 3, 128, device="cuda")
+    wy = torch.randn(5, 3, 128, device="cuda")
+
+    def grads_of(interleave: bool):
+        for p in tower.parameters():
+            p.grad = None
+        xx = x.clone().requires_grad_(True)
+        y = blk(xx)
+        if interleave:   # same block, same pack, different factor values (out-of-place copies: no version error)
+            other = tuple(t.detach() * 1.7 + 0.01 for t in blk.peft_tensors())
+            with torch.no_grad():
+                ops.block_forward(blk, x, blk.method, other, 0, 0)
+        (y * wy).sum().backward()
+        return [xx.grad.clone()] + [p.grad.clone() for p in tower.parameters() if p.requires_grad and p.grad is not None]
+    ref = grads_of(False)
+    got = grads_of(True)
+    assert len(ref) == len(got) and len(ref) > 4
+    for a, b in zip(got, ref):
+        assert torch.equal(a, b)
