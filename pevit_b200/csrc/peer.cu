@@ -76,7 +76,8 @@ __device__ __forceinline__ void peer_barrier(const PeerArgs& a, PeerCtl* mine, i
   if (threadIdx.x < a.world) {
     const int r = threadIdx.x;
     PeerCtl* theirs = reinterpret_cast<PeerCtl*>(reinterpret_cast<uint8_t*>(a.peers[r]) + ctl_offset(a.n));
-    __threadfence_system();
+    // release at system scope is cumulative: it orders the gradients earlier kernels of this stream wrote (visible to
+    // this thread since the kernel boundary) and, through the bar.sync above, this CTA's completed peer loads
     st_release_sys(&theirs->flag[phase][b][a.rank], e);
     const uint32_t* f = &mine->flag[phase][b][r];
     const unsigned long long t0 = global_ns();
