@@ -166,7 +166,7 @@ int sgd_momentum(cudaStream_t s, float* p, const float* g, float* m, size_t n, f
 
 // ------------------------------------------------------------------ peer.cu
 // One-shot all-reduce of the flat gradient buffer over peer-mapped (CUDA IPC) memory fused with the SGD update.
-constexpr int PEER_MAX_WORLD = 8, PEER_MAX_CTAS = 16, PEER_HANDLE_BYTES = 64;
+constexpr int PEER_MAX_WORLD = 8, PEER_MAX_CTAS = 32, PEER_HANDLE_BYTES = 64;
 size_t peer_buffer_bytes(size_t n);   // n gradient floats + the control block (flags, epochs, error word)
 int peer_alloc(size_t n, void** ptr, void* ipc_handle);
 int peer_open(const void* ipc_handle, void** ptr);

@@ -104,11 +104,16 @@ allreduce_sgd_kernel(PeerArgs a) {
   const size_t per = (n4 + gridDim.x - 1) / gridDim.x;
   const size_t lo = per * b, hi = lo + per < n4 ? lo + per : n4;
   for (size_t c = lo + threadIdx.x; c < hi; c += PEER_THREADS) {
-    float4 g = ld_sys_f4(a.peers[0] + 4 * c);
-    for (int r = 1; r < W; ++r) {
-      const float4 t = ld_sys_f4(a.peers[r] + 4 * c);
-      g.x += t.x; g.y += t.y; g.z += t.z; g.w += t.w;
-    }
+    // all W peer loads of the chunk are in flight together (one NVLink round trip, not W dependent ones) ...
+    float4 v[PEER_MAX_WORLD];
+#pragma unroll
+    for (int r = 0; r < PEER_MAX_WORLD; ++r)
+      if (r < W) v[r] = ld_sys_f4(a.peers[r] + 4 * c);
+    // ... and are added in rank order
+    float4 g = v[0];
+#pragma unroll
+    for (int r = 1; r < PEER_MAX_WORLD; ++r)
+      if (r < W) { g.x += v[r].x; g.y += v[r].y; g.z += v[r].z; g.w += v[r].w; }
     float4 pv = *reinterpret_cast<float4*>(a.p + 4 * c), mv = *reinterpret_cast<float4*>(a.m + 4 * c);
     const float gs[4] = {g.x, g.y, g.z, g.w};
     float ps[4] = {pv.x, pv.y, pv.z, pv.w}, ms[4] = {mv.x, mv.y, mv.z, mv.w};
@@ -207,7 +212,7 @@ int allreduce_sgd(cudaStream_t s, void* const* peers, int world, int rank, size_
   a.timeout_ns = static_cast<unsigned long long>(timeout_ms > 0 ? timeout_ms : 20000) * 1000000ull;
   // latency-bound: a few CTAs (all co-resident with every other rank's CTAs of the same index by construction: the
   // grid is far smaller than the SM count), each owning a contiguous slice
-  size_t grid = (n / 4 + PEER_THREADS * 4 - 1) / (PEER_THREADS * 4);
+  size_t grid = (n / 4 + PEER_THREADS - 1) / PEER_THREADS;   // about one 16-byte chunk per thread
   if (grid < 1) grid = 1;
   if (grid > PEER_MAX_CTAS) grid = PEER_MAX_CTAS;
   ProfScope prof(s, PC_ALLREDUCE_SGD);
