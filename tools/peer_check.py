@@ -49,10 +49,33 @@ def main():
     lab = torch.randint(0, 10, (6,), device=dev, generator=g)
     peer.capture(img, lab)
     nccl.capture(img, lab)
-    for _ in range(5):
+    # Every replay is checked against the update recomputed from the ranks' LOCAL gradients (the kernel leaves them in
+    # place): sum in rank order, torch.optim.SGD arithmetic, from the parameters / momentum before the replay.  This is
+    # exact bookkeeping of one step -- unlike the comparison with the NCCL tuner, which drifts once a 1-ulp parameter
+    # difference flips a bf16 rounding somewhere in the next forward.
+    lr, mu, wd = peer.hyper
+    nd, worst_step = peer.n_decayed, 0.0
+    for _ in range(8):
+        p0, m0 = peer.flat_params.flat.clone(), peer.flat_momentum.clone()
         peer.step_graphed()
         nccl.step_graphed()
-    torch.cuda.synchronize()
+        torch.cuda.synchronize()
+        grads = [torch.empty_like(peer.flat_grad) for _ in range(world)]
+        dist.all_gather(grads, peer.flat_grad.clone())
+        total = grads[0].clone()
+        for r in range(1, world):
+            total += grads[r]
+        wdv = torch.zeros_like(p0)
+        wdv[:nd] = wd
+        g = total / world + wdv * p0
+        m1 = mu * m0 + g
+        p1 = p0 - lr * m1
+        worst_step = max(worst_step, ((peer.flat_params.flat - p1).abs().max() / p1.abs().max()).item(),
+                         ((peer.flat_momentum - m1).abs().max() / m1.abs().max().clamp_min(1e-30)).item())
+    out["graph_max_rel_diff_vs_recomputed_update"] = worst_step
+    gathered = [torch.empty_like(peer.flat_params.flat) for _ in range(world)]
+    dist.all_gather(gathered, peer.flat_params.flat)
+    out["graph_identical_across_ranks"] = all(torch.equal(t, gathered[0]) for t in gathered)
     a, b = peer.flat_params.flat, nccl.flat_params.flat
     out["graph_max_rel_diff_vs_nccl_path"] = ((a - b).abs().max() / b.abs().max()).item()
     # cost of the exchange alone: replay-timed difference is in the bench; here the kernel is timed directly
