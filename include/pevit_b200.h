@@ -130,6 +130,13 @@ int pevit_kad_factor_grads(const float* dP, const float* dQ, const float* u1, co
 int pevit_kad_factor_grads_acc(const float* dP, const float* dQ, const float* u1, const float* v1, const float* u2,
                                const float* v2, const float* s, const float* t, int32_t d, float* du1, float* dv1,
                                float* du2, float* dv2, float* ds, float* dt, void* stream);
+/* The same accumulation for all `count` (<= 48) layers of one backward pass in ONE launch: dP / dQ / s / t / ds / dt are
+ * HOST arrays of `count` device pointers (one per layer); the rule factors u1, v1, u2, v2 and their gradient buffers
+ * are the tensors all layers share (model.py:1003-1010), their per-layer contributions are added atomically. */
+int pevit_kad_factor_grads_acc_batch(int32_t count, const float* const* dP, const float* const* dQ, const float* const* s,
+                                     const float* const* t, float* const* ds, float* const* dt, const float* u1,
+                                     const float* v1, const float* u2, const float* v2, int32_t d, float* du1, float* dv1,
+                                     float* du2, float* dv2, void* stream);
 /* Compacter PHM layers (compacter_model.py:196-308, :302-308 the per-call einsum): both layers of one block expanded
  * on the device into the bf16 operands of the bottleneck GEMMs -- W = H^T with H = sum_i kron(rule_i, left_i right_i).
  * rule fp32 [n][n][n]; down: left [n][d/n], right [n][bottleneck/n]; up: left [n][bottleneck/n], right [n][d/n].

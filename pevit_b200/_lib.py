@@ -90,6 +90,7 @@ _SIGNATURES = {
     "pevit_colsum_bf16": (c_int32, [c_void_p, c_int32, c_int32, c_void_p, c_void_p]),
     "pevit_kad_factor_grads": (c_int32, [c_void_p] * 8 + [c_int32] + [c_void_p] * 7),
     "pevit_kad_factor_grads_acc": (c_int32, [c_void_p] * 8 + [c_int32] + [c_void_p] * 7),
+    "pevit_kad_factor_grads_acc_batch": (c_int32, [c_int32] + [c_void_p] * 10 + [c_int32] + [c_void_p] * 5),
     "pevit_phm_expand": (c_int32, [c_void_p, c_int32] + [c_void_p] * 4 + [c_int32, c_int32] + [c_void_p] * 5),
     "pevit_phm_factor_grads": (c_int32, [c_void_p] * 3 + [c_int32] + [c_void_p] * 4 + [c_int32, c_int32] + [c_void_p] * 5
                                + [c_int32, c_void_p]),

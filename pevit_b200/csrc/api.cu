@@ -250,6 +250,15 @@ int pevit_kad_factor_grads_acc(const float* dP, const float* dQ, const float* u1
   return kad_factor_grads(as_stream(stream), dP, dQ, u1, v1, u2, v2, s, t, d, du1, dv1, du2, dv2, ds, dt, true);
 }
 
+int pevit_kad_factor_grads_acc_batch(int32_t count, const float* const* dP, const float* const* dQ, const float* const* s,
+                                     const float* const* t, float* const* ds, float* const* dt, const float* u1,
+                                     const float* v1, const float* u2, const float* v2, int32_t d, float* du1, float* dv1,
+                                     float* du2, float* dv2, void* stream) {
+  PEVIT_REQUIRE(dP && dQ && s && t && ds && dt && u1 && v1 && u2 && v2 && du1 && dv1 && du2 && dv2,
+                "pevit_kad_factor_grads_acc_batch: null pointer");
+  return kad_factor_grads_batch(as_stream(stream), count, dP, dQ, s, t, ds, dt, u1, v1, u2, v2, d, du1, dv1, du2, dv2);
+}
+
 int pevit_phm_expand(const float* rule, int32_t n, const float* down_left, const float* down_right, const float* up_left,
                      const float* up_right, int32_t d, int32_t bottleneck, void* w_down, void* w_down_t, void* w_up,
                      void* w_up_t, void* stream) {
@@ -578,9 +587,13 @@ int pevit_block_bwd(const pevit_block_desc* desc, const pevit_block_weights* w, 
                                   g->d_qmat + static_cast<size_t>(which) * D * r, r};
       }
       if (g->d_pmat) probs[n++] = AtbProblem{sv.xn1, D, wk.dqkv + 3 * D, W3, r2, 0, r2, 1.f, g->d_pmat, r2};
-      if (n > 0) TRY(atb_tc_batch(s, probs, n, M, D));
+      // KAdaptation's shared bias gradient colsum(dDelta_q) + colsum(dDelta_v) rides in the same launch
+      const bool want_bias = d.method == PEVIT_KADAPTATION && g->d_bias != nullptr;
+      const AtbColsum cs{wk.ddelta, wk.ddelta + plane, D, M, D, g->d_bias};
+      const bool ride = want_bias && n > 0 && atb_colsum_rider_supported(D, D);
+      if (n > 0) TRY(atb_tc_batch(s, probs, n, M, D, ride ? &cs : nullptr));
+      if (want_bias && !ride) TRY(colsum_bf16(s, wk.ddelta, wk.ddelta + plane, D, M, D, g->d_bias));
     }
-    if (d.method == PEVIT_KADAPTATION && g->d_bias) TRY(colsum_bf16(s, wk.ddelta, wk.ddelta + plane, D, M, D, g->d_bias));
   }
   if (!d.need_dx) return 0;  // first layer: nothing upstream of this block trains
   // in-projection dgrad (K = 3D + 2r: the low-rank columns ride along)

@@ -24,15 +24,67 @@ struct AtbParams {
 };
 
 constexpr int ATB_MAX_BATCH = 3;
+constexpr int ATB_CS_SLICES = 2;  // z-slices of the grid that run the column-sum job
 struct AtbBatch {
   CUtensorMap tm_a[ATB_MAX_BATCH], tm_b[ATB_MAX_BATCH];
   AtbParams p[ATB_MAX_BATCH];
+  int count;
+  AtbColsum cs;  // optional rider: out[c] += sum_m X0[m][c] + X1[m][c]  (cs.out == nullptr: none)
 };
+
+// The column-sum rider (KAdaptation's shared bias gradient, colsum(dDelta_q) + colsum(dDelta_v), model.py:583): the same
+// d(delta) planes the products above read, summed by the CTAs of the extra z-slices while the products run -- one launch
+// and one pass through L2 instead of a second kernel behind this one.  192 threads = (D / 8 column groups of one
+// 16-byte load) x row lanes; a CTA owns a contiguous slice of rows; row lanes meet in shared memory, then one atomic per
+// column per CTA.
+__device__ __forceinline__ void colsum_rider(const AtbColsum& cs, float* red, int cta, int nctas) {
+  const int ncg = cs.D >> 3;                      // host guarantees D % 8 == 0 and ncg <= ATB_THREADS
+  const int lanes = ATB_THREADS / ncg;            // row lanes per CTA
+  const int cg = threadIdx.x % ncg, rl = threadIdx.x / ncg;
+  const int rows_per = (cs.M + nctas - 1) / nctas;
+  const int m_begin = cta * rows_per, m_end = min(cs.M, m_begin + rows_per);
+  float acc[8];
+#pragma unroll
+  for (int j = 0; j < 8; ++j) acc[j] = 0.f;
+  if (rl < lanes) {
+#pragma unroll 4
+    for (int m = m_begin + rl; m < m_end; m += lanes) {
+      const uint4 a = __ldg(reinterpret_cast<const uint4*>(cs.X0 + static_cast<size_t>(m) * cs.ld) + cg);
+      const uint4 b = cs.X1 != nullptr ? __ldg(reinterpret_cast<const uint4*>(cs.X1 + static_cast<size_t>(m) * cs.ld) + cg)
+                                       : make_uint4(0, 0, 0, 0);
+      const uint32_t w[4] = {a.x, a.y, a.z, a.w}, u[4] = {b.x, b.y, b.z, b.w};
+#pragma unroll
+      for (int t = 0; t < 4; ++t) {
+        const float2 f = unpack_bf16(w[t]), h = unpack_bf16(u[t]);
+        acc[2 * t] += f.x + h.x;
+        acc[2 * t + 1] += f.y + h.y;
+      }
+    }
+#pragma unroll
+    for (int j = 0; j < 8; ++j) red[rl * cs.D + cg * 8 + j] = acc[j];
+  }
+  __syncthreads();
+  for (int c = threadIdx.x; c < cs.D; c += ATB_THREADS) {
+    float t = 0.f;
+    for (int r = 0; r < lanes; ++r) t += red[r * cs.D + c];
+    atomicAdd(cs.out + c, t);
+  }
+}
 
 // blockIdx.z selects one of up to three independent products (same M): the block backward has three of them per
 // layer (dQ_q, dQ_v, dP), each far too short to fill the GPU or amortise a launch on its own.
 __global__ void __launch_bounds__(ATB_THREADS)
 atb_tc_kernel(const __grid_constant__ AtbBatch batch) {
+  if (static_cast<int>(blockIdx.z) >= batch.count) {   // column-sum rider slices (whole CTAs: no barrier is shared)
+    extern __shared__ uint8_t smem_cs[];
+    pdl_launch_dependents();
+    pdl_wait();
+    const int per_slice = gridDim.x * gridDim.y;
+    colsum_rider(batch.cs, reinterpret_cast<float*>(smem_cs),
+                 (static_cast<int>(blockIdx.z) - batch.count) * per_slice + blockIdx.y * gridDim.x + blockIdx.x,
+                 per_slice * ATB_CS_SLICES);
+    return;
+  }
   const CUtensorMap& tm_a = batch.tm_a[blockIdx.z];
   const CUtensorMap& tm_b = batch.tm_b[blockIdx.z];
   const AtbParams& p = batch.p[blockIdx.z];
@@ -141,8 +193,16 @@ atb_tc_kernel(const __grid_constant__ AtbBatch batch) {
 
 // A: bf16 [M][lda] (uses Kc columns).  B: bf16 [M][ldb] with nb_cols (<= 64) columns visible; columns
 // [n_lo, n_lo + n_cnt) of the product are accumulated into C[kc][0 .. n_cnt) (row stride ldc).
-int atb_tc_batch(cudaStream_t s, const AtbProblem* probs, int count, int M, int Kc) {
+bool atb_colsum_rider_supported(int D, int ld) { return D % 8 == 0 && D / 8 <= ATB_THREADS && D >= 8 && ld % 8 == 0; }
+
+int atb_tc_batch(cudaStream_t s, const AtbProblem* probs, int count, int M, int Kc, const AtbColsum* colsum) {
   PEVIT_REQUIRE(count >= 1 && count <= ATB_MAX_BATCH, "atb_tc_batch: %d problems (1..%d)", count, ATB_MAX_BATCH);
+  if (colsum != nullptr)
+    PEVIT_REQUIRE(colsum->X0 != nullptr && colsum->out != nullptr && atb_colsum_rider_supported(colsum->D, colsum->ld) &&
+                      (reinterpret_cast<uintptr_t>(colsum->X0) & 15) == 0 && (reinterpret_cast<uintptr_t>(colsum->X1) & 15) == 0 &&
+                      static_cast<size_t>(ATB_THREADS / (colsum->D / 8)) * colsum->D * sizeof(float) <= ATB_SMEM,
+                  "atb_tc_batch: column-sum rider needs 16-byte rows and D / 8 <= %d (D=%d ld=%d)", ATB_THREADS, colsum->D,
+                  colsum->ld);
   const int gx = (Kc + 127) / 128;
   int splits = (sm_count() + gx * count - 1) / (gx * count);  // ~one CTA per SM over the whole batch
   if (splits < 8) splits = 8;
@@ -150,6 +210,8 @@ int atb_tc_batch(cudaStream_t s, const AtbProblem* probs, int count, int M, int 
   rps = ((rps + ATB_BK - 1) / ATB_BK) * ATB_BK;
   splits = (M + rps - 1) / rps;
   AtbBatch batch;
+  batch.count = count;
+  batch.cs = colsum != nullptr ? *colsum : AtbColsum{nullptr, nullptr, 0, 0, 0, nullptr};
   for (int i = 0; i < count; ++i) {
     const AtbProblem& q = probs[i];
     PEVIT_REQUIRE(q.nb_cols >= 1 && q.nb_cols <= 64 && q.n_lo >= 0 && q.n_lo + q.n_cnt <= q.nb_cols,
@@ -170,7 +232,8 @@ int atb_tc_batch(cudaStream_t s, const AtbProblem* probs, int count, int M, int 
     configured[dev & 63] = true;
   }
   ProfScope prof(s, PC_ATB);
-  PEVIT_CHECK_CUDA(launch_kernel(atb_tc_kernel, dim3(gx, splits, count), dim3(ATB_THREADS), ATB_SMEM, s, 1, batch));
+  PEVIT_CHECK_CUDA(launch_kernel(atb_tc_kernel, dim3(gx, splits, count + (colsum != nullptr ? ATB_CS_SLICES : 0)),
+                                 dim3(ATB_THREADS), ATB_SMEM, s, 1, batch));
   PEVIT_CHECK_LAUNCH();
   return 0;
 }
@@ -178,7 +241,7 @@ int atb_tc_batch(cudaStream_t s, const AtbProblem* probs, int count, int M, int 
 int atb_tc(cudaStream_t s, const bf16* A, int lda, const bf16* B, int ldb, int nb_cols, int M, int Kc, int n_lo,
            int n_cnt, float scale, float* C, int ldc) {
   const AtbProblem q{A, lda, B, ldb, nb_cols, n_lo, n_cnt, scale, C, ldc};
-  return atb_tc_batch(s, &q, 1, M, Kc);
+  return atb_tc_batch(s, &q, 1, M, Kc, nullptr);
 }
 
 }  // namespace pevit

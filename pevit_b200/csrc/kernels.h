@@ -116,7 +116,14 @@ struct AtbProblem {
   float scale;
   float* C; int ldc;
 };
-int atb_tc_batch(cudaStream_t s, const AtbProblem* probs, int count, int M, int Kc);
+// optional rider of the same launch: out[c] += sum_m X0[m][c] (+ X1[m][c]) over bf16 [M][ld] matrices (first D columns);
+// extra CTAs of the grid compute it while the products run (the shared bias gradient reads the same d(delta) planes)
+struct AtbColsum {
+  const bf16* X0; const bf16* X1; int ld, M, D;
+  float* out;
+};
+bool atb_colsum_rider_supported(int D, int ld);
+int atb_tc_batch(cudaStream_t s, const AtbProblem* probs, int count, int M, int Kc, const AtbColsum* colsum = nullptr);
 // column sums of one or two (X1 nullable) bf16 [M][ld] matrices (first D columns), atomically accumulated into
 // out[D] (caller zeroes).
 int colsum_bf16(cudaStream_t s, const bf16* X0, const bf16* X1, int ld, int M, int D, float* out);
@@ -124,6 +131,13 @@ int colsum_bf16(cudaStream_t s, const bf16* X0, const bf16* X1, int ld, int M, i
 int kad_factor_grads(cudaStream_t s, const float* dP, const float* dQ, const float* u1, const float* v1, const float* u2,
                      const float* v2, const float* sfac, const float* tfac, int D, float* du1, float* dv1, float* du2,
                      float* dv2, float* dsfac, float* dtfac, bool accumulate);
+// ... for up to KAD_MAX_LAYERS layers in ONE launch, added onto the gradient buffers: per-layer arrays (host pointers to
+// `count` device pointers each) of dP, dQ, s, t, ds, dt; the rule factors and their gradients are shared by all layers.
+constexpr int KAD_MAX_LAYERS = 48;
+int kad_factor_grads_batch(cudaStream_t s, int count, const float* const* dP, const float* const* dQ,
+                           const float* const* sfac, const float* const* tfac, float* const* dsfac, float* const* dtfac,
+                           const float* u1, const float* v1, const float* u2, const float* v2, int D, float* du1, float* dv1,
+                           float* du2, float* dv2);
 // dT (fp32 [M][r2 cols starting at col0]) -> bf16 into dqkv_ext[:, 3D+col0 ...]
 int cast_f32_to_bf16_2d(cudaStream_t s, const float* src, int lds, bf16* dst, int ldd, int rows, int cols);
 

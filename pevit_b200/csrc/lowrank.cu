@@ -218,6 +218,61 @@ kad_factor_grads_kernel(const float* __restrict__ dP, const float* __restrict__ 
   }
 }
 
+// The same contractions for ALL layers of a backward pass in one launch (blockIdx.y = layer), added onto the callers'
+// gradient buffers: ds / dt are per layer (plain +=, each element has one writer), du1 / dv1 / du2 / dv2 belong to the rule
+// tensors every layer shares (model.py:1003-1010), so the layers' contributions meet there through atomicAdd.
+struct KadLayers {
+  const float* dP[KAD_MAX_LAYERS]; const float* dQ[KAD_MAX_LAYERS];
+  const float* sf[KAD_MAX_LAYERS]; const float* tf[KAD_MAX_LAYERS];
+  float* dsf[KAD_MAX_LAYERS]; float* dtf[KAD_MAX_LAYERS];
+};
+__global__ void __launch_bounds__(256)
+kad_factor_grads_batch_kernel(const __grid_constant__ KadLayers ly, const float* __restrict__ u1, const float* __restrict__ v1,
+                              const float* __restrict__ u2, const float* __restrict__ v2, int D, float* __restrict__ du1,
+                              float* __restrict__ dv1, float* __restrict__ du2, float* __restrict__ dv2) {
+  pdl_launch_dependents();
+  pdl_wait();
+  extern __shared__ float sm[];
+  const int i = blockIdx.x, layer = blockIdx.y;
+  const int F = D / 32;
+  const float* dP = ly.dP[layer]; const float* dQ = ly.dQ[layer];
+  const float* sf = ly.sf[layer]; const float* tf = ly.tf[layer];
+  float* dsf = ly.dsf[layer]; float* dtf = ly.dtf[layer];
+  float* cPq = sm; float* cPv = sm + D; float* cQq = sm + 2 * D; float* cQv = sm + 3 * D;
+  float* ss = sm + 4 * D; float* tt = ss + F; float* a1 = tt + F; float* a2 = a1 + 32; float* b1 = a2 + 32; float* b2 = b1 + 32;
+  for (int c = threadIdx.x; c < D; c += blockDim.x) {
+    cPq[c] = dP[static_cast<size_t>(c) * 64 + i];
+    cPv[c] = dP[static_cast<size_t>(c) * 64 + 32 + i];
+    cQq[c] = dQ[static_cast<size_t>(c) * 32 + i];
+    cQv[c] = dQ[static_cast<size_t>(D + c) * 32 + i];
+  }
+  for (int k = threadIdx.x; k < F; k += blockDim.x) { ss[k] = sf[i * F + k]; tt[k] = tf[i * F + k]; }
+  if (threadIdx.x < 32) {
+    a1[threadIdx.x] = u1[i * 32 + threadIdx.x]; a2[threadIdx.x] = u2[i * 32 + threadIdx.x];
+    b1[threadIdx.x] = v1[i * 32 + threadIdx.x]; b2[threadIdx.x] = v2[i * 32 + threadIdx.x];
+  }
+  __syncthreads();
+  for (int o = threadIdx.x; o < 128 + 2 * F; o += blockDim.x) {
+    float g = 0.f;
+    if (o < 128) {
+      const int which = o >> 5, a = o & 31;
+      const float* col = which == 0 ? cPq : (which == 1 ? cPv : (which == 2 ? cQq : cQv));
+      const float* fac = which < 2 ? ss : tt;
+      for (int k = 0; k < F; ++k) g = fmaf(col[a * F + k], fac[k], g);
+      float* dst = which == 0 ? du1 : (which == 1 ? du2 : (which == 2 ? dv1 : dv2));
+      atomicAdd(dst + i * 32 + a, g);
+    } else if (o < 128 + F) {
+      const int k = o - 128;
+      for (int a = 0; a < 32; ++a) g = fmaf(cPq[a * F + k], a1[a], fmaf(cPv[a * F + k], a2[a], g));
+      dsf[i * F + k] += g;
+    } else {
+      const int k = o - 128 - F;
+      for (int a = 0; a < 32; ++a) g = fmaf(cQq[a * F + k], b1[a], fmaf(cQv[a * F + k], b2[a], g));
+      dtf[i * F + k] += g;
+    }
+  }
+}
+
 __global__ void cast2d_kernel(const float* __restrict__ src, int lds, bf16* __restrict__ dst, int ldd, int rows,
                               int cols) {
   pdl_launch_dependents();
@@ -325,6 +380,25 @@ int kad_factor_grads(cudaStream_t s, const float* dP, const float* dQ, const flo
   const size_t smem = (4 * static_cast<size_t>(D) + 2 * (D / 32) + 128) * sizeof(float);
   PEVIT_CHECK_CUDA(launch_kernel(kad_factor_grads_kernel, dim3(32), dim3(256), smem, s, 1, dP, dQ, u1, v1, u2, v2, sfac, tfac, D,
                                  du1, dv1, du2, dv2, dsfac, dtfac, accumulate ? 1 : 0));
+  PEVIT_CHECK_LAUNCH();
+  return 0;
+}
+
+int kad_factor_grads_batch(cudaStream_t s, int count, const float* const* dP, const float* const* dQ,
+                           const float* const* sfac, const float* const* tfac, float* const* dsfac, float* const* dtfac,
+                           const float* u1, const float* v1, const float* u2, const float* v2, int D, float* du1, float* dv1,
+                           float* du2, float* dv2) {
+  PEVIT_REQUIRE(count >= 1 && count <= KAD_MAX_LAYERS, "kad_factor_grads_batch: %d layers (1..%d)", count, KAD_MAX_LAYERS);
+  PEVIT_REQUIRE(D % 32 == 0, "kad_factor_grads_batch: D=%d not divisible by phm_dim 32", D);
+  KadLayers ly{};
+  for (int l = 0; l < count; ++l) {
+    PEVIT_REQUIRE(dP[l] && dQ[l] && sfac[l] && tfac[l] && dsfac[l] && dtfac[l], "kad_factor_grads_batch: null pointer in layer %d", l);
+    ly.dP[l] = dP[l]; ly.dQ[l] = dQ[l]; ly.sf[l] = sfac[l]; ly.tf[l] = tfac[l]; ly.dsf[l] = dsfac[l]; ly.dtf[l] = dtfac[l];
+  }
+  ProfScope prof(s, PC_FACTOR_GRADS);
+  const size_t smem = (4 * static_cast<size_t>(D) + 2 * (D / 32) + 128) * sizeof(float);
+  PEVIT_CHECK_CUDA(launch_kernel(kad_factor_grads_batch_kernel, dim3(32, count), dim3(256), smem, s, 1, ly, u1, v1, u2, v2, D,
+                                 du1, dv1, du2, dv2));
   PEVIT_CHECK_LAUNCH();
   return 0;
 }

@@ -135,6 +135,7 @@ class FineTuner(nn.Module):
                                     {"params": [p for _, p in no_wd], "weight_decay": 0.0}],
                                    lr=lr, momentum=momentum, weight_decay=weight_decay)
         self.hyper = (lr, momentum, weight_decay)
+        self._scratch_pool = self._scratch_packs = None
         if self.fused_tail:
             self.flat_params = FlatParams(self.used, device)
             self.flat_momentum = torch.zeros_like(self.flat_params.flat)
@@ -172,16 +173,32 @@ class FineTuner(nn.Module):
 
     def step(self, images: torch.Tensor, labels: torch.Tensor) -> torch.Tensor:
         """One fine-tune step on this rank's local batch; returns the (device) loss."""
-        with ops.direct_grad_accumulation(True):
+        with ops.direct_grad_accumulation(True, defer_factor_grads=True):
             return self._step(images, labels)
+
+    def _clear_block_scratch(self) -> None:
+        """One fill for the gradient accumulators of ALL blocks (views of one pool) instead of one per block inside
+        the backward pass; the pool is (re)built when the blocks' operand packs exist / have been rebuilt."""
+        blocks = self.backbone.visual.transformer.resblocks
+        packs = [getattr(b, "_pevit_pack", None) for b in blocks]
+        if any(p is None for p in packs):
+            return                      # first step: the packs are built by the forward that follows
+        if self._scratch_packs is None or any(a is not b for a, b in zip(packs, self._scratch_packs)):
+            self._scratch_pool, self._scratch_packs = ops.pool_grad_scratch(packs), packs
+        if self._scratch_pool is not None:
+            self._scratch_pool.zero_()
+            for p in packs:
+                p.scratch_clean = True
 
     def _step(self, images: torch.Tensor, labels: torch.Tensor) -> torch.Tensor:
         self.grads.zero_()
+        self._clear_block_scratch()
         if self.fused_tail:
             visual = self.backbone.visual
             x_cls = visual.forward_cls_tokens(self.backbone.pixels_for_stem(images))
             loss, _ = ops.tail_loss(visual, self.head, x_cls, labels)
             loss.backward()
+            ops.flush_factor_grads()   # KAdaptation: all layers' factor gradients in one launch
             lr, mu, wd = self.hyper
             fp, fg, fm, nd = self.flat_params.flat, self.flat_grad, self.flat_momentum, self.n_decayed
             if self.peer is not None:   # one launch: sum over the ranks' peer-mapped buffers + both weight-decay groups
@@ -198,6 +215,7 @@ class FineTuner(nn.Module):
             return loss.detach()
         loss = F.cross_entropy(self.forward(images), labels)
         loss.backward()
+        ops.flush_factor_grads()
         if self.distributed:
             self.grads.all_reduce_mean(self.group)
         self.opt.step()

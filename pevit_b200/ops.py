@@ -70,16 +70,68 @@ def set_direct_grad_accumulation(on: bool) -> None:
 
 
 @contextlib.contextmanager
-def direct_grad_accumulation(on: bool = True):
+def direct_grad_accumulation(on: bool = True, defer_factor_grads: bool = False):
     """Scope the direct-accumulation mode to the caller's own forward / backward (``engine.FineTuner.step``) instead
     of switching it on for every block of the process: outside the scope autograd's plain contract holds
-    (AccumulateGrad, hooks, ``torch.autograd.grad``)."""
-    prev = _direct_grads[0]
-    _direct_grads[0] = bool(on)
+    (AccumulateGrad, hooks, ``torch.autograd.grad``).
+
+    ``defer_factor_grads``: KAdaptation blocks leave their dP / dQ in the pack's scratch and only register themselves;
+    ``flush_factor_grads()`` (called by the owner after ``backward()``, and in any case when the scope ends) then
+    contracts ALL layers into the factor gradients with one launch instead of one per layer."""
+    prev = (_direct_grads[0], _defer_kad[0])
+    _direct_grads[0], _defer_kad[0] = bool(on), bool(on and defer_factor_grads)
     try:
         yield
     finally:
-        _direct_grads[0] = prev
+        try:
+            flush_factor_grads()
+        finally:
+            _direct_grads[0], _defer_kad[0] = prev
+
+
+_defer_kad = [False]
+_pending_kad: list = []   # (device, D, shared (u1, v1, u2, v2), shared grads, per-layer (dP, dQ, s, t, ds, dt))
+
+
+def flush_factor_grads() -> None:
+    """Contract the registered layers' dP / dQ into the KAdaptation factor gradients: one launch per group of layers
+    that share their rule tensors (a model has one such group)."""
+    pending, _pending_kad[:] = list(_pending_kad), []
+    groups: Dict[tuple, list] = {}
+    for dev, D, shared, shared_g, layer in pending:
+        groups.setdefault((dev, D, tuple(_ptr(t) for t in shared), tuple(_ptr(t) for t in shared_g)), []).append(
+            (shared, shared_g, layer))
+    lib = L.lib()
+    for (dev, D, _, _), items in groups.items():
+        shared, shared_g = items[0][0], items[0][1]
+        with torch.cuda.device(dev):
+            for lo in range(0, len(items), 48):
+                chunk = [it[2] for it in items[lo:lo + 48]]
+                cols = [(C.c_void_p * len(chunk))(*[_ptr(layer[k]) for layer in chunk]) for k in range(6)]
+                L.check(lib.pevit_kad_factor_grads_acc_batch(len(chunk), *cols, *(_ptr(t) for t in shared), D,
+                                                             *(_ptr(t) for t in shared_g), _stream()),
+                        "pevit_kad_factor_grads_acc_batch")
+
+
+def pool_grad_scratch(packs) -> Optional[torch.Tensor]:
+    """Make the per-block gradient accumulators (KAdaptation / LoRA: dP | dQ; Compacter: dense dH_down | dW_up) views of
+    ONE buffer, so that the owner clears all of them with a single fill per step and marks them clean
+    (``pack.scratch_clean = True``) instead of one fill launch per block inside the backward pass."""
+    packs = [p for p in packs if p is not None]
+    if not packs:
+        return None
+    sizes = [4 * p.D * p.r if p.r else (2 * p.D * BOTTLENECK if p.method == "compacter" else 0) for p in packs]
+    if sum(sizes) == 0:
+        return None
+    pool = torch.zeros(sum(sizes), dtype=torch.float32, device=packs[0].w_o.device)
+    off = 0
+    for p, n in zip(packs, sizes):
+        if n and p.r:
+            p._grad_scratch = pool[off:off + n]
+        elif n:
+            p._dense_scratch = pool[off:off + n].view(2, p.D, BOTTLENECK)
+        off += n
+    return pool
 
 
 _workspace: Dict[Tuple[int, int], torch.Tensor] = {}
@@ -146,6 +198,7 @@ class BlockPack:
         self._grad_scratch = None
         self.expanded_ahead = False
         self.stamp = 0   # bumped by every factor expansion
+        self.scratch_clean = False   # the owner of a pooled scratch cleared it for the coming backward (pool_grad_scratch)
         self.key = self.signature(block)
 
     def dense_grad_scratch(self) -> torch.Tensor:
@@ -346,7 +399,10 @@ class _BlockFn(torch.autograd.Function):
         if method in ("kadaptation", "lora"):
             if direct:  # one persistent scratch buffer for dP | dQ, zeroed by a single fill
                 scratch = pack.grad_scratch()
-                scratch.zero_()
+                if pack.scratch_clean:
+                    pack.scratch_clean = False   # cleared by the pool's single fill at the start of the step
+                else:
+                    scratch.zero_()
                 d_pmat, d_qmat = scratch[:D * 2 * r].view(D, 2 * r), scratch[D * 2 * r:].view(2, D, r)
             else:
                 d_pmat = torch.zeros(D, 2 * r, **f32)
@@ -367,7 +423,10 @@ class _BlockFn(torch.autograd.Function):
                 i_bd, i_bu = (5, 8)
                 d_lna_g, d_lna_b, d_b_down, d_b_up = live[0].grad, live[1].grad, live[i_bd].grad, live[i_bu].grad
                 scratch = pack.dense_grad_scratch()
-                scratch.zero_()
+                if pack.scratch_clean:
+                    pack.scratch_clean = False
+                else:
+                    scratch.zero_()
                 d_w_down_t, d_w_up = scratch[0], scratch[1]
             else:
                 d_lna_g, d_lna_b = torch.zeros(D, **f32), torch.zeros(D, **f32)
@@ -381,7 +440,12 @@ class _BlockFn(torch.autograd.Function):
                                     C.byref(g), _ptr(saved), _ptr(ws), st), "pevit_block_bwd")
         if dx is not None:
             _dx_shadow[0] = (weakref.ref(dx), (dx.data_ptr(), dx._version, tuple(dx.shape)), dx16)
-        if method == "kadaptation" and direct:
+        if method == "kadaptation" and direct and _defer_kad[0]:
+            u1, v1, u2, v2, s, t, _ = peft_c   # contracted with all other layers by flush_factor_grads()
+            _pending_kad.append((dev, D, (u1, v1, u2, v2), tuple(p.grad for p in live[:4]),
+                                 (d_pmat, d_qmat, s, t, live[4].grad, live[5].grad)))
+            grads = (None,) * 7
+        elif method == "kadaptation" and direct:
             u1, v1, u2, v2, s, t, _ = peft_c
             L.check(lib.pevit_kad_factor_grads_acc(_ptr(d_pmat), _ptr(d_qmat), _ptr(u1), _ptr(v1), _ptr(u2), _ptr(v2),
                                                    _ptr(s), _ptr(t), D, *(_ptr(p.grad) for p in live[:6]), st),
