@@ -505,8 +505,14 @@ int pevit_block_bwd(const pevit_block_desc* desc, const pevit_block_weights* w, 
   if (has_bottleneck(d)) {
     const int act = d.method == PEVIT_ADAPTER ? ACT_RELU : ACT_GELU_NEW;
     // up projection: dW_up = dy^T u, db_up = colsum(dy), du = dy W_up, dzd = du * act'(zd)
-    if (g->d_w_up) TRY(atb_tc(s, dyb, D, sv.u, 64, 64, Mo, D, 0, 64, 1.f, g->d_w_up, 64));
-    if (g->d_b_up) TRY(colsum_bf16(s, dyb, nullptr, D, Mo, D, g->d_b_up));
+    // (the bias gradient's column sum reads the same dy rows: it rides in the A^T B launch as extra CTAs)
+    {
+      const AtbColsum cs{dyb, nullptr, D, Mo, D, g->d_b_up};
+      const bool ride = g->d_w_up && g->d_b_up && atb_colsum_rider_supported(D, D);
+      const AtbProblem q{dyb, D, sv.u, 64, 64, 0, 64, 1.f, g->d_w_up, 64};
+      if (g->d_w_up) TRY(atb_tc_batch(s, &q, 1, Mo, D, ride ? &cs : nullptr));
+      if (g->d_b_up && !ride) TRY(colsum_bf16(s, dyb, nullptr, D, Mo, D, g->d_b_up));
+    }
     {
       GemmEpilogue ep;
       ep.out_bf16 = wk.dzd; ep.aux_bf16 = sv.zd; ep.ld_out = 64; ep.act = act;
@@ -514,8 +520,13 @@ int pevit_block_bwd(const pevit_block_desc* desc, const pevit_block_weights* w, 
       TRY(gemm_tn(s, dyb, D, static_cast<const bf16*>(w->w_up_t), D, Mo, 64, D, EPI_DACT, ep));
     }
     // down projection: dW_down^T = a_n^T dzd, db_down = colsum(dzd), da_n = dzd W_down
-    if (g->d_w_down) TRY(atb_tc(s, sv.a_n, D, wk.dzd, 64, 64, Mo, D, 0, 64, 1.f, g->d_w_down, 64));
-    if (g->d_b_down) TRY(colsum_bf16(s, wk.dzd, nullptr, 64, Mo, 64, g->d_b_down));
+    {
+      const AtbColsum cs{wk.dzd, nullptr, 64, Mo, 64, g->d_b_down};
+      const bool ride = g->d_w_down && g->d_b_down && atb_colsum_rider_supported(64, 64);
+      const AtbProblem q{sv.a_n, D, wk.dzd, 64, 64, 0, 64, 1.f, g->d_w_down, 64};
+      if (g->d_w_down) TRY(atb_tc_batch(s, &q, 1, Mo, D, ride ? &cs : nullptr));
+      if (g->d_b_down && !ride) TRY(colsum_bf16(s, wk.dzd, nullptr, 64, Mo, 64, g->d_b_down));
+    }
     {
       GemmEpilogue ep;
       ep.out_f32 = wk.dxn; ep.ld_out = D;

@@ -57,51 +57,76 @@ struct PhmGradLayer {
   float* dright;
 };
 
-// one warp per output scalar; tasks of a layer: n K (dleft), n P (dright), n^3 (drule)
-__global__ void __launch_bounds__(256)
-phm_factor_grads_kernel(const float* __restrict__ rule, int n, PhmGradLayer l0, PhmGradLayer l1, float* __restrict__ drule,
-                        int accumulate) {
+// One CTA per (layer, a, c): the K x P block G_ac = dH[aK.., cP..] of the dense gradient is staged in shared memory once
+// (coalesced along whichever index is contiguous in the layer's storage) and contracted there,
+//   U_i[k] = sum_p G_ac[k][p] right[i][p],   V_i[p] = sum_k G_ac[k][p] left[i][k],
+//   dleft[i][k] += rule[i][a][c] U_i[k],  dright[i][p] += rule[i][a][c] V_i[p],  drule[i][a][c] += sum_k left[i][k] U_i[k];
+// the n^2 blocks of a layer (and, for the shared rule, all layers) meet in the outputs through atomicAdd -- the caller
+// zeroes them first unless it accumulates.  (The first version ran one warp per output scalar straight from global
+// memory: the 128 outputs that contract over the long index walked 96 dependent, uncoalesced loads each -- 33 us per launch.)
+constexpr int PFG_THREADS = 256;
+__global__ void __launch_bounds__(PFG_THREADS)
+phm_factor_grads_kernel(const float* __restrict__ rule, int n, PhmGradLayer l0, PhmGradLayer l1, float* __restrict__ drule) {
   pdl_launch_dependents();
   pdl_wait();
-  const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
-  const int K0 = l0.in_f / n, P0 = l0.out_f / n, K1 = l1.in_f / n, P1 = l1.out_f / n;
-  const int n3 = drule != nullptr ? n * n * n : 0;
-  const int tasks0 = n * K0 + n * P0 + n3, tasks1 = n * K1 + n * P1 + n3;
-  if (warp >= tasks0 + tasks1) return;
-  const bool second = warp >= tasks0;
-  const PhmGradLayer& l = second ? l1 : l0;
-  const int task = second ? warp - tasks0 : warp;
-  const int K = l.in_f / n, P = l.out_f / n;
-  auto dh_at = [&](int row, int col) {
-    return l.dh_out_in ? l.dh[static_cast<size_t>(col) * l.in_f + row] : l.dh[static_cast<size_t>(row) * l.out_f + col];
-  };
-  float g = 0.f;
-  if (task < n * K) {
-    const int i = task / K, k = task - i * K;
-    for (int e = lane; e < n * n * P; e += 32) {
-      const int a = e / (n * P), c = (e / P) % n, p = e % P;
-      g = fmaf(dh_at(a * K + k, c * P + p), rule[(i * n + a) * n + c] * l.right[i * P + p], g);
+  extern __shared__ float sm[];
+  const PhmGradLayer& l = blockIdx.y == 0 ? l0 : l1;
+  const int a = blockIdx.x / n, c = blockIdx.x - a * n;
+  const int K = l.in_f / n, P = l.out_f / n, PS = P + 1;
+  float* sG = sm;                 // [K][P + 1]
+  float* sL = sG + K * PS;        // [n][K]  left factors
+  float* sR = sL + n * K;         // [n][P]  right factors
+  float* sred = sR + n * P;       // [PFG_THREADS / 32]
+  if (l.dh_out_in) {              // stored [out][in]: k is the contiguous index
+    for (int e = threadIdx.x; e < K * P; e += PFG_THREADS) {
+      const int p = e / K, k = e - p * K;
+      sG[k * PS + p] = l.dh[static_cast<size_t>(c * P + p) * l.in_f + a * K + k];
     }
-    g = warp_sum(g);
-    if (lane == 0) l.dleft[task] = accumulate ? l.dleft[task] + g : g;
-  } else if (task < n * K + n * P) {
-    const int t2 = task - n * K;
-    const int i = t2 / P, p = t2 - i * P;
-    for (int e = lane; e < n * n * K; e += 32) {
-      const int a = e / (n * K), c = (e / K) % n, k = e % K;
-      g = fmaf(dh_at(a * K + k, c * P + p), rule[(i * n + a) * n + c] * l.left[i * K + k], g);
-    }
-    g = warp_sum(g);
-    if (lane == 0) l.dright[t2] = accumulate ? l.dright[t2] + g : g;
-  } else {
-    const int t3 = task - n * K - n * P;
-    const int i = t3 / (n * n), a = (t3 / n) % n, c = t3 % n;
-    for (int e = lane; e < K * P; e += 32) {
+  } else {                        // stored [in][out]: p is the contiguous index
+    for (int e = threadIdx.x; e < K * P; e += PFG_THREADS) {
       const int k = e / P, p = e - k * P;
-      g = fmaf(dh_at(a * K + k, c * P + p), l.left[i * K + k] * l.right[i * P + p], g);
+      sG[k * PS + p] = l.dh[static_cast<size_t>(a * K + k) * l.out_f + c * P + p];
     }
-    g = warp_sum(g);
-    if (lane == 0) atomicAdd(drule + t3, g);  // both layers (and every block of the model) add into the shared rule
+  }
+  for (int e = threadIdx.x; e < n * K; e += PFG_THREADS) sL[e] = l.left[e];
+  for (int e = threadIdx.x; e < n * P; e += PFG_THREADS) sR[e] = l.right[e];
+  __syncthreads();
+  // one WARP per output scalar (K values of U_i, P values of V_i): the lanes stride over the contracted index and meet
+  // in a shuffle reduction, so neither the long nor the short side of the block becomes a serial loop
+  constexpr int NWARPS = PFG_THREADS / 32;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  for (int i = 0; i < n; ++i) {
+    const float rv = rule[(i * n + a) * n + c];
+    const float* left = sL + i * K;
+    const float* right = sR + i * P;
+    float part = 0.f;             // lane 0: this warp's share of sum_k left[i][k] U_i[k]
+    for (int o = warp; o < K + P; o += NWARPS) {
+      float acc = 0.f;
+      if (o < K) {
+        for (int p = lane; p < P; p += 32) acc = fmaf(sG[o * PS + p], right[p], acc);
+      } else {
+        for (int k = lane; k < K; k += 32) acc = fmaf(sG[k * PS + (o - K)], left[k], acc);
+      }
+      acc = warp_sum(acc);
+      if (lane == 0) {
+        if (o < K) {
+          atomicAdd(l.dleft + i * K + o, rv * acc);
+          part = fmaf(left[o], acc, part);
+        } else {
+          atomicAdd(l.dright + i * P + (o - K), rv * acc);
+        }
+      }
+    }
+    if (drule != nullptr) {
+      if (lane == 0) sred[warp] = part;
+      __syncthreads();
+      if (threadIdx.x == 0) {
+        float t = 0.f;
+        for (int w = 0; w < NWARPS; ++w) t += sred[w];
+        atomicAdd(drule + (i * n + a) * n + c, t);   // both layers (and every block of the model) add into the shared rule
+      }
+      __syncthreads();
+    }
   }
 }
 
@@ -151,11 +176,17 @@ int phm_factor_grads(cudaStream_t s, const float* d_w_down, const float* d_w_up,
   // block backward layouts: d_w_down is [D][B] = dH_down ([in][out]); d_w_up is [D][B] = dW_up = dH_up^T ([out][in])
   PhmGradLayer dn{d_w_down, 0, down_left, down_right, D, B, d_down_left, d_down_right};
   PhmGradLayer up{d_w_up, 1, up_left, up_right, B, D, d_up_left, d_up_right};
-  const int n3 = d_rule != nullptr ? n * n * n : 0;
-  const int tasks = 2 * (n * (D / n) + n * (B / n) + n3);
+  if (!accumulate) {  // the kernel adds (n^2 CTAs per layer meet in every output): plain assignment = zero first
+    PEVIT_CHECK_CUDA(cudaMemsetAsync(d_down_left, 0, sizeof(float) * D, s));
+    PEVIT_CHECK_CUDA(cudaMemsetAsync(d_down_right, 0, sizeof(float) * B, s));
+    PEVIT_CHECK_CUDA(cudaMemsetAsync(d_up_left, 0, sizeof(float) * B, s));
+    PEVIT_CHECK_CUDA(cudaMemsetAsync(d_up_right, 0, sizeof(float) * D, s));
+  }
+  const int K = D / n, P = B / n;   // the up layer has the same block size, transposed
+  const size_t smem = (static_cast<size_t>(K > P ? K : P) * ((K > P ? P : K) + 1) + static_cast<size_t>(n) * (K + P) + PFG_THREADS / 32) * sizeof(float);
+  PEVIT_REQUIRE(smem <= 48 * 1024, "phm_factor_grads: block %d x %d does not fit in shared memory", K, P);
   ProfScope prof(s, PC_FACTOR_GRADS);
-  PEVIT_CHECK_CUDA(launch_kernel(phm_factor_grads_kernel, dim3((tasks + 7) / 8), dim3(256), 0, s, 1, rule, n, dn, up, d_rule,
-                                 accumulate ? 1 : 0));
+  PEVIT_CHECK_CUDA(launch_kernel(phm_factor_grads_kernel, dim3(n * n, 2), dim3(PFG_THREADS), smem, s, 1, rule, n, dn, up, d_rule));
   PEVIT_CHECK_LAUNCH();
   return 0;
 }
