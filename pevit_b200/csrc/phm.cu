@@ -91,33 +91,51 @@ phm_factor_grads_kernel(const float* __restrict__ rule, int n, PhmGradLayer l0, 
   for (int e = threadIdx.x; e < n * K; e += PFG_THREADS) sL[e] = l.left[e];
   for (int e = threadIdx.x; e < n * P; e += PFG_THREADS) sR[e] = l.right[e];
   __syncthreads();
-  // one WARP per output scalar (K values of U_i, P values of V_i): the lanes stride over the contracted index and meet
-  // in a shuffle reduction, so neither the long nor the short side of the block becomes a serial loop
+  // U_i has K outputs contracted over P, V_i has P outputs contracted over K; one side of the block is short (<= 32) and
+  // one long.  A short contraction is a serial loop of one THREAD per output; a long one takes a WARP per output (lanes
+  // stride over the contracted index, shuffle reduction).  (A warp per output for both sides cost 8 k instructions per
+  // warp, 39 us; one thread per output for both sides walked 192-long dependent chains.)
   constexpr int NWARPS = PFG_THREADS / 32;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   for (int i = 0; i < n; ++i) {
     const float rv = rule[(i * n + a) * n + c];
     const float* left = sL + i * K;
     const float* right = sR + i * P;
-    float part = 0.f;             // lane 0: this warp's share of sum_k left[i][k] U_i[k]
-    for (int o = warp; o < K + P; o += NWARPS) {
-      float acc = 0.f;
-      if (o < K) {
-        for (int p = lane; p < P; p += 32) acc = fmaf(sG[o * PS + p], right[p], acc);
-      } else {
-        for (int k = lane; k < K; k += 32) acc = fmaf(sG[k * PS + (o - K)], left[k], acc);
+    float part = 0.f;             // this thread's share of sum_k left[i][k] U_i[k]
+    if (P <= 32) {
+      for (int k = threadIdx.x; k < K; k += PFG_THREADS) {
+        float u = 0.f;
+        for (int p = 0; p < P; ++p) u = fmaf(sG[k * PS + p], right[p], u);
+        atomicAdd(l.dleft + i * K + k, rv * u);
+        part = fmaf(left[k], u, part);
       }
-      acc = warp_sum(acc);
-      if (lane == 0) {
-        if (o < K) {
-          atomicAdd(l.dleft + i * K + o, rv * acc);
-          part = fmaf(left[o], acc, part);
-        } else {
-          atomicAdd(l.dright + i * P + (o - K), rv * acc);
+    } else {
+      for (int k = warp; k < K; k += NWARPS) {
+        float u = 0.f;
+        for (int p = lane; p < P; p += 32) u = fmaf(sG[k * PS + p], right[p], u);
+        u = warp_sum(u);
+        if (lane == 0) {
+          atomicAdd(l.dleft + i * K + k, rv * u);
+          part = fmaf(left[k], u, part);
         }
       }
     }
+    if (K <= 32) {
+      for (int p = threadIdx.x; p < P; p += PFG_THREADS) {
+        float v = 0.f;
+        for (int k = 0; k < K; ++k) v = fmaf(sG[k * PS + p], left[k], v);
+        atomicAdd(l.dright + i * P + p, rv * v);
+      }
+    } else {
+      for (int p = warp; p < P; p += NWARPS) {
+        float v = 0.f;
+        for (int k = lane; k < K; k += 32) v = fmaf(sG[k * PS + p], left[k], v);
+        v = warp_sum(v);
+        if (lane == 0) atomicAdd(l.dright + i * P + p, rv * v);
+      }
+    }
     if (drule != nullptr) {
+      part = warp_sum(part);
       if (lane == 0) sred[warp] = part;
       __syncthreads();
       if (threadIdx.x == 0) {
