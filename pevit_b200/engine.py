@@ -179,6 +179,8 @@ class FineTuner(nn.Module):
     def _clear_block_scratch(self) -> None:
         """One fill for the gradient accumulators of ALL blocks (views of one pool) instead of one per block inside
         the backward pass; the pool is (re)built when the blocks' operand packs exist / have been rebuilt."""
+        if self.method not in ("kadaptation", "compacter"):
+            return                      # only these two accumulate in per-block scratch (ops._BlockFn.backward, direct mode)
         blocks = self.backbone.visual.transformer.resblocks
         packs = [getattr(b, "_pevit_pack", None) for b in blocks]
         if any(p is None for p in packs):

@@ -171,18 +171,28 @@ class BlockPack:
         bf = dict(dtype=torch.bfloat16, device=dev)
         cast, transpose = self.cast, self.transpose
 
+        fwd_only = bool(self.causal)   # text-tower blocks never run a backward: no transposed (dgrad) operand copies
         self.w_qkv_ext = torch.zeros(W3, D, **bf)
-        self.w_qkv_ext_t = torch.zeros(D, W3, **bf)
         cast(w_in, self.w_qkv_ext)                      # rows [0, 3D)
-        transpose(w_in, self.w_qkv_ext_t, W3)           # cols [0, 3D)
         wo = attn.out_proj.weight
-        self.w_o, self.w_o_t = torch.empty(D, D, **bf), torch.empty(D, D, **bf)
-        cast(wo, self.w_o); transpose(wo, self.w_o_t, D)
+        self.w_o = torch.empty(D, D, **bf)
+        cast(wo, self.w_o)
         wfc, wpr = block.mlp.c_fc.weight, block.mlp.c_proj.weight
-        self.w_fc, self.w_fc_t = torch.empty(4 * D, D, **bf), torch.empty(D, 4 * D, **bf)
-        cast(wfc, self.w_fc); transpose(wfc, self.w_fc_t, 4 * D)
-        self.w_proj, self.w_proj_t = torch.empty(D, 4 * D, **bf), torch.empty(4 * D, D, **bf)
-        cast(wpr, self.w_proj); transpose(wpr, self.w_proj_t, D)
+        self.w_fc = torch.empty(4 * D, D, **bf)
+        cast(wfc, self.w_fc)
+        self.w_proj = torch.empty(D, 4 * D, **bf)
+        cast(wpr, self.w_proj)
+        if fwd_only:   # the struct still wants valid pointers; pevit_block_bwd refuses causal descriptors
+            self.w_qkv_ext_t, self.w_o_t, self.w_fc_t, self.w_proj_t = self.w_qkv_ext, self.w_o, self.w_fc, self.w_proj
+        else:
+            self.w_qkv_ext_t = torch.zeros(D, W3, **bf)
+            transpose(w_in, self.w_qkv_ext_t, W3)       # cols [0, 3D)
+            self.w_o_t = torch.empty(D, D, **bf)
+            transpose(wo, self.w_o_t, D)
+            self.w_fc_t = torch.empty(D, 4 * D, **bf)
+            transpose(wfc, self.w_fc_t, 4 * D)
+            self.w_proj_t = torch.empty(4 * D, D, **bf)
+            transpose(wpr, self.w_proj_t, D)
         self.small = [_f32c(t.detach()) for t in (
             attn.in_proj_bias, attn.out_proj.bias, block.mlp.c_fc.bias, block.mlp.c_proj.bias,
             block.ln_1.weight, block.ln_1.bias, block.ln_2.weight, block.ln_2.bias)]
