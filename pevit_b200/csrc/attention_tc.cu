@@ -82,21 +82,53 @@ attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_consta
   const int n_local = (p.num_tiles - static_cast<int>(blockIdx.x) + static_cast<int>(gridDim.x) - 1) /
                       static_cast<int>(gridDim.x);
 
-  // zero every operand / P buffer once: TMA only ever writes rows < L of each head slot, so the pad
-  // rows (and P's off-diagonal blocks) stay exactly zero for the lifetime of the CTA.
-  {
-    uint4* z = reinterpret_cast<uint4*>(smem);
-    const int n16 = (TC_STAGES * STAGE_BYTES + 2 * P_BYTES) / 16;
-    for (int i = threadIdx.x; i < n16; i += FWD_THREADS) z[i] = make_uint4(0, 0, 0, 0);
-  }
-  if (warp == 8 && lane == 0) {
-    tma_prefetch_desc(&tm_q); tma_prefetch_desc(&tm_k); tma_prefetch_desc(&tm_v); tma_prefetch_desc(&tm_o);
-    for (int s = 0; s < TC_STAGES; ++s) { mbar_init(&full[s], 1); mbar_init(&empty[s], 1); }
-    for (int b = 0; b < 2; ++b) {
-      mbar_init(&s_full[b], 1); mbar_init(&p_full[b], 4); mbar_init(&o_full[b], 1); mbar_init(&o_empty[b], 4);
-      mbar_init(&p_free[b], 1);
+  // One tile's operands into ring slot it % TC_STAGES (TMA warp, one elected lane).
+  auto load_tile = [&](int it) {
+    const int tile = blockIdx.x + it * gridDim.x;
+    const int s = it % TC_STAGES;
+    const int g0 = tile * PACK;
+    const int nheads = min(PACK, p.heads_total - g0);
+    uint8_t* st = smem + s * STAGE_BYTES;
+    if (p.debug & 1) { mbar_arrive(&full[s]); return; }
+    mbar_expect_tx(&full[s], static_cast<uint32_t>(nheads) * 3u * static_cast<uint32_t>(L) * 128u);
+    for (int j = 0; j < nheads; ++j) {
+      const int row = (g0 + j) * L;
+      tma_load_2d(st + j * 8192, &tm_q, &full[s], 0, row);
+      tma_load_2d(st + TILE_BYTES + j * 8192, &tm_k, &full[s], 0, row);
+      tma_load_2d(st + 2 * TILE_BYTES + j * 8192, &tm_v, &full[s], 0, row);
     }
-    fence_mbar_init();
+  };
+  const int n_early = min(TC_STAGES, n_local);  // tiles whose loads are issued from the prologue
+  if (warp == 8) {
+    if (elect_one()) {
+      tma_prefetch_desc(&tm_q); tma_prefetch_desc(&tm_k); tma_prefetch_desc(&tm_v); tma_prefetch_desc(&tm_o);
+      for (int s = 0; s < TC_STAGES; ++s) { mbar_init(&full[s], 1); mbar_init(&empty[s], 1); }
+      for (int b = 0; b < 2; ++b) {
+        mbar_init(&s_full[b], 1); mbar_init(&p_full[b], 4); mbar_init(&o_full[b], 1); mbar_init(&o_empty[b], 4);
+        mbar_init(&p_free[b], 1);
+      }
+      fence_mbar_init();
+      // The first ring-full of tiles is requested NOW, under the zero fill and the TMEM allocation below: TMA writes rows
+      // < L of a head slot, the fill only rows >= L, so the two never touch the same bytes, and nobody waits on `full`
+      // before the __syncthreads() that follows.  (This was ~1.5 us of exposed load latency per launch of an 11-tile kernel.)
+      pdl_wait();
+      for (int it = 0; it < n_early; ++it) load_tile(it);
+    }
+    __syncwarp();
+  }
+  // zero what TMA never writes and the MMAs still read: the pad rows [L, slot rows) of every operand slot, and the P
+  // buffers (their off-diagonal blocks / pad rows must be exact zeros for the lifetime of the CTA)
+  {
+    constexpr int SLOT_ROWS = PACK == 2 ? 64 : 128;
+    uint4* zp = reinterpret_cast<uint4*>(sP);
+    for (int i = threadIdx.x; i < 2 * P_BYTES / 16; i += FWD_THREADS) zp[i] = make_uint4(0, 0, 0, 0);
+    const int pad16 = (SLOT_ROWS - L) * 8;                 // 16-byte chunks of one slot's pad rows
+    const int nslots = TC_STAGES * 3 * PACK;               // slots are contiguous: stage -> operand -> head slot
+    if (pad16 > 0)
+      for (int i = threadIdx.x; i < nslots * pad16; i += FWD_THREADS) {
+        const int slot = i / pad16, c = i - slot * pad16;
+        reinterpret_cast<uint4*>(smem + slot * (SLOT_ROWS * 128) + L * 128)[c] = make_uint4(0, 0, 0, 0);
+      }
   }
   if (warp == 9) {
     tmem_alloc(tmem_slot, 512);
@@ -125,24 +157,13 @@ attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_consta
           tma_prefetch_l2_2d(&tm_v, 0, (g0_ + j) * L);
         }
       };
-      for (int it_ = TC_STAGES; it_ < TC_STAGES + ATTN_PREFETCH; ++it_) prefetch_tile(it_);
-      for (int it = 0; it < n_local; ++it) {
-        const int tile = blockIdx.x + it * gridDim.x;
+      for (int it_ = TC_STAGES; it_ < 2 * TC_STAGES + ATTN_PREFETCH; ++it_) prefetch_tile(it_);
+      for (int it = n_early; it < n_local; ++it) {   // tiles [0, n_early) were requested in the prologue
         const int s = it % TC_STAGES;
         const uint32_t ph = (it / TC_STAGES) & 1;
         prefetch_tile(it + TC_STAGES + ATTN_PREFETCH);
         mbar_wait(&empty[s], ph ^ 1);
-        const int g0 = tile * PACK;
-        const int nheads = min(PACK, p.heads_total - g0);
-        uint8_t* st = smem + s * STAGE_BYTES;
-        if (p.debug & 1) { mbar_arrive(&full[s]); continue; }
-        mbar_expect_tx(&full[s], static_cast<uint32_t>(nheads) * 3u * static_cast<uint32_t>(L) * 128u);
-        for (int j = 0; j < nheads; ++j) {
-          const int row = (g0 + j) * L;
-          tma_load_2d(st + j * 8192, &tm_q, &full[s], 0, row);
-          tma_load_2d(st + TILE_BYTES + j * 8192, &tm_k, &full[s], 0, row);
-          tma_load_2d(st + 2 * TILE_BYTES + j * 8192, &tm_v, &full[s], 0, row);
-        }
+        load_tile(it);
       }
     }
   } else if (warp == 9) {
@@ -366,18 +387,49 @@ attn_bwd_tc_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_consta
   const int L = p.L;
   const int n_local = (p.num_tiles - static_cast<int>(blockIdx.x) + static_cast<int>(gridDim.x) - 1) /
                       static_cast<int>(gridDim.x);
-  {
-    uint4* z = reinterpret_cast<uint4*>(smem);
-    const int n16 = (BWD_STAGES * BWD_STAGE_BYTES + 2 * P_BYTES) / 16;
-    for (int i = threadIdx.x; i < n16; i += BWD_THREADS) z[i] = make_uint4(0, 0, 0, 0);
+  // One tile's operands (Q', K, V', dO) into ring slot it % BWD_STAGES (TMA warp, one elected lane).
+  auto load_tile = [&](int it) {
+    const int tile = blockIdx.x + it * gridDim.x;
+    const int s = it % BWD_STAGES;
+    const int g0 = tile * PACK;
+    const int nheads = min(PACK, p.heads_total - g0);
+    uint8_t* st = smem + s * BWD_STAGE_BYTES;
+    mbar_expect_tx(&full[s], static_cast<uint32_t>(nheads) * 4u * static_cast<uint32_t>(L) * 128u);
+    for (int j = 0; j < nheads; ++j) {
+      const int g = g0 + j, row = g * L;
+      const int n = g / p.H, h = g - n * p.H;
+      tma_load_2d(st + j * 8192, &tm_q, &full[s], 0, row);
+      tma_load_2d(st + TILE_BYTES + j * 8192, &tm_k, &full[s], 0, row);
+      tma_load_2d(st + 2 * TILE_BYTES + j * 8192, &tm_v, &full[s], 0, row);
+      tma_load_4d(st + 3 * TILE_BYTES + j * 8192, &tm_do, &full[s], 0, h, n, 0);
+    }
+  };
+  const int n_early = min(BWD_STAGES, n_local);  // tiles whose loads are issued from the prologue (see the forward kernel)
+  if (warp == 8) {
+    if (BWD_TMA_ONE) {
+      tma_prefetch_desc(&tm_q); tma_prefetch_desc(&tm_k); tma_prefetch_desc(&tm_v); tma_prefetch_desc(&tm_do);
+      tma_prefetch_desc(&tm_dqkv);
+      for (int s = 0; s < BWD_STAGES; ++s) { mbar_init(&full[s], 1); mbar_init(&empty[s], 1); }
+      for (int b = 0; b < 2; ++b) { mbar_init(&s_full[b], 1); mbar_init(&o2_full[b], 1); mbar_init(&o2_empty[b], 4); }
+      mbar_init(pds_full, 4);
+      fence_mbar_init();
+      pdl_wait();
+      for (int it = 0; it < n_early; ++it) load_tile(it);
+    }
+    __syncwarp();
   }
-  if (warp == 8 && lane == 0) {
-    tma_prefetch_desc(&tm_q); tma_prefetch_desc(&tm_k); tma_prefetch_desc(&tm_v); tma_prefetch_desc(&tm_do);
-    tma_prefetch_desc(&tm_dqkv);
-    for (int s = 0; s < BWD_STAGES; ++s) { mbar_init(&full[s], 1); mbar_init(&empty[s], 1); }
-    for (int b = 0; b < 2; ++b) { mbar_init(&s_full[b], 1); mbar_init(&o2_full[b], 1); mbar_init(&o2_empty[b], 4); }
-    mbar_init(pds_full, 4);
-    fence_mbar_init();
+  // zero the pad rows [L, slot rows) of every operand slot and the P / dS tiles (TMA only writes rows < L)
+  {
+    constexpr int SLOT_ROWS = PACK == 2 ? 64 : 128;
+    uint4* zp = reinterpret_cast<uint4*>(sP);
+    for (int i = threadIdx.x; i < 2 * P_BYTES / 16; i += BWD_THREADS) zp[i] = make_uint4(0, 0, 0, 0);
+    const int pad16 = (SLOT_ROWS - L) * 8;
+    const int nslots = BWD_STAGES * 4 * PACK;
+    if (pad16 > 0)
+      for (int i = threadIdx.x; i < nslots * pad16; i += BWD_THREADS) {
+        const int slot = i / pad16, c = i - slot * pad16;
+        reinterpret_cast<uint4*>(smem + slot * (SLOT_ROWS * 128) + L * 128)[c] = make_uint4(0, 0, 0, 0);
+      }
   }
   if (warp == 9) {
     tmem_alloc(tmem_slot, 512);
@@ -405,24 +457,12 @@ attn_bwd_tc_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_consta
           tma_prefetch_l2_4d(&tm_do, 0, h_, n_, 0);
         }
       };
-      for (int it_ = BWD_STAGES; it_ < BWD_STAGES + ATTN_PREFETCH; ++it_) prefetch_tile(it_);
-      for (int it = 0; it < n_local; ++it) {
-        const int tile = blockIdx.x + it * gridDim.x;
+      for (int it_ = BWD_STAGES; it_ < 2 * BWD_STAGES + ATTN_PREFETCH; ++it_) prefetch_tile(it_);
+      for (int it = n_early; it < n_local; ++it) {   // tiles [0, n_early) were requested in the prologue
         const int s = it % BWD_STAGES;
         prefetch_tile(it + BWD_STAGES + ATTN_PREFETCH);
         mbar_wait(&empty[s], ((it / BWD_STAGES) & 1) ^ 1);
-        const int g0 = tile * PACK;
-        const int nheads = min(PACK, p.heads_total - g0);
-        uint8_t* st = smem + s * BWD_STAGE_BYTES;
-        mbar_expect_tx(&full[s], static_cast<uint32_t>(nheads) * 4u * static_cast<uint32_t>(L) * 128u);
-        for (int j = 0; j < nheads; ++j) {
-          const int g = g0 + j, row = g * L;
-          const int n = g / p.H, h = g - n * p.H;
-          tma_load_2d(st + j * 8192, &tm_q, &full[s], 0, row);
-          tma_load_2d(st + TILE_BYTES + j * 8192, &tm_k, &full[s], 0, row);
-          tma_load_2d(st + 2 * TILE_BYTES + j * 8192, &tm_v, &full[s], 0, row);
-          tma_load_4d(st + 3 * TILE_BYTES + j * 8192, &tm_do, &full[s], 0, h, n, 0);
-        }
+        load_tile(it);
       }
     }
   } else if (warp == 9) {
