@@ -333,6 +333,7 @@ def run_reference(args):
     cfg = workload(args, shape)
     cfg["sample"] = (f"each step = the full {nb}-image batch" if nb == args.batch else
                      f"each step = {nb} images (bounded sample of the {args.batch}-image batch)")
+    cfg["reference_pixels"] = "fp32 (what the oracle consumes; `pixels` above is the b200 arm's transport format of the same batch)"
     cfg["reference_device"] = ("cuda eager PyTorch, " + ("autocast bf16" if args.ref_autocast else "fp32, TF32 off")
                                if on_gpu else "host CPU")
     line = {"impl": "reference", "metric": METRIC, "value": ips, "unit": "images/s", "n_gpus": args.gpus,
